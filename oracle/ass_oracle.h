@@ -1,0 +1,92 @@
+/* oracle/ass_oracle.h -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+ *
+ * Plain-C, single-threaded CPU restatement of the reference's per-step force + integration path and of its
+ * build-time neighbour queries.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may load
+ * it; the product (asteroid-spring-sims_b200/) never does.
+ *
+ * Parity status: PINNED.  Every function below is checked bit-for-bit (spring lists, generator output,
+ * accelerations, leapfrog state) or to 1e-13 (diagnostic sums) against
+ *   (1) the reference's own known-answer tests (modules/tests/tests.cpp SpringTest.* / PhysicsTest.*), and
+ *   (2) outputs of the unmodified reference compiled here (oracle/_ref, see oracle/Makefile) -- live when
+ *       oracle/_ref exists, and through the committed fixtures in tests/golden/ otherwise.
+ *
+ * Particle state is a packed array of rows of ORC_STRIDE doubles: x y z vx vy vz ax ay az m r, i.e. the first
+ * eleven fields of `struct reb_particle` (reference src/rebound.h:540-551).
+ */
+#ifndef ASS_ORACLE_H
+#define ASS_ORACLE_H
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ORC_STRIDE 11
+enum { ORC_X = 0, ORC_Y, ORC_Z, ORC_VX, ORC_VY, ORC_VZ, ORC_AX, ORC_AY, ORC_AZ, ORC_M, ORC_R };
+
+/* == struct spring, reference src_spring/springs.h:16-22 (32 bytes) */
+typedef struct {
+	double k, rs0, gamma;
+	int particle_1, particle_2;
+} orc_spring;
+
+/* Simulation scalars that the path reads from struct reb_simulation (src/rebound.h:589-836). */
+typedef struct {
+	double t, dt, dt_last_done;
+	double G, softening;
+	int gravity_basic;     /* 1: REB_GRAVITY_BASIC, 0: REB_GRAVITY_NONE */
+	int n_active;          /* -1 => all (src/gravity.c:64) */
+	int zero_first;        /* additional_forces = zero_accel + spring_forces (modules/asteroid_spin/problem.cpp:225-231) */
+	int center_heartbeat;  /* heartbeat = center_sim(0, N - n_perts)  (modules/asteroid_spin/problem.cpp:196) */
+	int n_perts;
+	int status;            /* enum REB_STATUS, src/rebound.h:358-368 */
+	int exact_finish_time;
+} orc_sim;
+
+/* ---- per-step path ---- */
+void orc_zero_accel(double* p, int n);                                            /* physics.cpp:557-564 */
+void orc_spring_forces(double* p, const orc_spring* s, int ns);                   /* springs.cpp:288-346 */
+void orc_gravity_basic(double* p, int n, int n_active, double G, double softening);/* gravity.c:57-125  */
+/* same sum, restricted to targets i in [i_lo, i_hi) -- bounded CPU-baseline samples */
+void orc_gravity_basic_slab(double* p, int n, int n_active, double G, double softening, int i_lo, int i_hi);
+void orc_leapfrog_part1(double* p, int n, orc_sim* sim);                          /* integrator_leapfrog.c:39-51 */
+void orc_leapfrog_part2(double* p, int n, orc_sim* sim);                          /* integrator_leapfrog.c:52-67 */
+void orc_step(double* p, int n, const orc_spring* s, int ns, orc_sim* sim);       /* rebound.c:69-144 */
+void orc_heartbeat(double* p, int n, orc_sim* sim);
+int orc_integrate(double* p, int n, const orc_spring* s, int ns, orc_sim* sim, double tmax); /* rebound.c:509-704 */
+
+/* ---- spring build ---- */
+/* Literal restatement: O(N^2) pair scan + O(NS) duplicate scan per add (springs.cpp:52-143). */
+int orc_connect_springs_dist_n2(const double* p, double max_dist, int i_low, int i_high, double k, double gamma,
+		orc_spring** springs, int* ns, int* cap);
+/* Results-identical uniform-grid version for N > 1e4. */
+int orc_connect_springs_dist(const double* p, double max_dist, int i_low, int i_high, double k, double gamma,
+		orc_spring** springs, int* ns, int* cap);
+int orc_add_spring(const double* p, int i, int j, double k, double gamma, orc_spring** springs, int* ns, int* cap);
+void orc_free(void* ptr);
+
+/* ---- node generators (shapes.cpp) ---- */
+/* Both return the new particle count; *p is realloc'd.  rand() stream = libc, seed with srand() first. */
+int orc_rand_ellipsoid_n2(double** p, int n0, double min_dist, double a, double b, double c, double total_mass); /* shapes.cpp:210-278 literal */
+int orc_rand_ellipsoid(double** p, int n0, double min_dist, double a, double b, double c, double total_mass);    /* cell-list */
+int orc_hcp_ellipsoid(double** p, int n0, double min_dist, double a, double b, double c, double total_mass);     /* shapes.cpp:282-352 */
+int orc_cubic_ellipsoid(double** p, int n0, double min_dist, double a, double b, double c, double total_mass);   /* shapes.cpp:356-431 */
+double orc_mindist_n2(const double* p, int i_low, int i_high);                                                    /* shapes.cpp:814-833 */
+double orc_mindist(const double* p, int i_low, int i_high);                                                       /* grid */
+double orc_random_uniform(double lo, double hi);                                                                  /* tools.c:44-46 */
+
+/* ---- heartbeat helpers / diagnostics (physics.cpp, orb.cpp) ---- */
+double orc_sum_mass(const double* p, int i_low, int i_high);
+void orc_compute_com(const double* p, int i_low, int i_high, double* out3);
+void orc_compute_cov(const double* p, int i_low, int i_high, double* out3);
+void orc_center_sim(double* p, int n, int i_low, int i_high);
+void orc_move_resolved(double* p, const double* dx, const double* dv, int i_low, int i_high);
+void orc_subtract_com(double* p, int i_low, int i_high);
+void orc_subtract_cov(double* p, int i_low, int i_high);
+void orc_spin_body(double* p, int i_low, int i_high, double ox, double oy, double oz);
+void orc_set_gamma(orc_spring* s, int ns, double g);
+/* out[20]: same layout as ref_diagnostics in oracle/ref_shim.cpp */
+void orc_diagnostics(const double* p, int i_low, int i_high, const orc_spring* s, int ns, double G, int want_gpe, double* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

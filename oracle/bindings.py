@@ -1,0 +1,328 @@
+"""ctypes bindings for the CPU oracle -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+Two libraries:
+  * ``libass_oracle.so``      oracle/ass_oracle.c, the plain-C restatement (class ``Oracle``)
+  * ``_ref/libref_oracle.so`` the UNMODIFIED reference compiled by ``make -C oracle ref`` with the shim in
+                              oracle/ref_shim.cpp (class ``Ref``); absent on machines without /root/reference
+                              unless the prebuilt .so travelled with the snapshot.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this
+module.  Particle state is an (N, 11) float64 array: x y z vx vy vz ax ay az m r.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REFERENCE = os.environ.get("ASS_REFERENCE", "/root/reference")
+STRIDE = 11
+X, Y, Z, VX, VY, VZ, AX, AY, AZ, M, R = range(11)
+
+SPRING_DTYPE = np.dtype([("k", "<f8"), ("rs0", "<f8"), ("gamma", "<f8"),
+                         ("particle_1", "<i4"), ("particle_2", "<i4")], align=True)
+assert SPRING_DTYPE.itemsize == 32
+
+_dp = C.POINTER(C.c_double)
+
+
+def _d(a):
+    return a.ctypes.data_as(_dp)
+
+
+class OrcSim(C.Structure):
+    _fields_ = [("t", C.c_double), ("dt", C.c_double), ("dt_last_done", C.c_double),
+                ("G", C.c_double), ("softening", C.c_double),
+                ("gravity_basic", C.c_int), ("n_active", C.c_int), ("zero_first", C.c_int),
+                ("center_heartbeat", C.c_int), ("n_perts", C.c_int), ("status", C.c_int),
+                ("exact_finish_time", C.c_int)]
+
+
+def make_sim(dt=1e-3, G=1.0, softening=0.0, gravity_basic=0, zero_first=0, center_heartbeat=0, n_perts=0, t=0.0):
+    return OrcSim(t=t, dt=dt, dt_last_done=0.0, G=G, softening=softening, gravity_basic=int(gravity_basic),
+                  n_active=-1, zero_first=int(zero_first), center_heartbeat=int(center_heartbeat),
+                  n_perts=n_perts, status=-1, exact_finish_time=1)
+
+
+def build_oracle(force=False):
+    so = os.path.join(HERE, "libass_oracle.so")
+    src = os.path.join(HERE, "ass_oracle.c")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-s", "-C", HERE, "libass_oracle.so"])
+    return so
+
+
+def build_ref(force=False):
+    """Compile the unmodified reference into oracle/_ref/ when its sources are present. Returns path or None."""
+    so = os.path.join(HERE, "_ref", "libref_oracle.so")
+    if os.path.isdir(os.path.join(REFERENCE, "src_spring")):
+        if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(os.path.join(HERE, "ref_shim.cpp")):
+            subprocess.check_call(["make", "-s", "-j8", "-C", HERE, "ref", "REF=" + REFERENCE])
+    return so if os.path.exists(so) else None
+
+
+class Oracle:
+    """oracle/ass_oracle.c through ctypes."""
+
+    def __init__(self):
+        self.lib = L = C.CDLL(build_oracle())
+        L.orc_mindist.restype = C.c_double
+        L.orc_mindist_n2.restype = C.c_double
+        L.orc_sum_mass.restype = C.c_double
+        L.orc_random_uniform.restype = C.c_double
+        L.orc_random_uniform.argtypes = [C.c_double, C.c_double]
+        self.libc = C.CDLL(None)
+
+    @staticmethod
+    def _p(p):
+        assert p.dtype == np.float64 and p.ndim == 2 and p.shape[1] == STRIDE and p.flags.c_contiguous
+        return _d(p)
+
+    @staticmethod
+    def _s(s):
+        assert s.dtype == SPRING_DTYPE and s.flags.c_contiguous
+        return s.ctypes.data_as(C.c_void_p)
+
+    def srand(self, seed):
+        self.libc.srand(C.c_uint(seed))
+
+    # -- per-step path --
+    def zero_accel(self, p):
+        self.lib.orc_zero_accel(self._p(p), C.c_int(len(p)))
+
+    def spring_forces(self, p, s):
+        self.lib.orc_spring_forces(self._p(p), self._s(s), C.c_int(len(s)))
+
+    def gravity_basic(self, p, G=1.0, softening=0.0, n_active=-1, i_lo=None, i_hi=None):
+        if i_lo is None:
+            self.lib.orc_gravity_basic(self._p(p), C.c_int(len(p)), C.c_int(n_active), C.c_double(G), C.c_double(softening))
+        else:
+            self.lib.orc_gravity_basic_slab(self._p(p), C.c_int(len(p)), C.c_int(n_active), C.c_double(G),
+                                            C.c_double(softening), C.c_int(i_lo), C.c_int(i_hi))
+
+    def leapfrog_part1(self, p, sim):
+        self.lib.orc_leapfrog_part1(self._p(p), C.c_int(len(p)), C.byref(sim))
+
+    def leapfrog_part2(self, p, sim):
+        self.lib.orc_leapfrog_part2(self._p(p), C.c_int(len(p)), C.byref(sim))
+
+    def step(self, p, s, sim, nsteps=1, heartbeat=False):
+        for _ in range(nsteps):
+            self.lib.orc_step(self._p(p), C.c_int(len(p)), self._s(s), C.c_int(len(s)), C.byref(sim))
+            if heartbeat:
+                self.lib.orc_heartbeat(self._p(p), C.c_int(len(p)), C.byref(sim))
+
+    def integrate(self, p, s, sim, tmax):
+        return self.lib.orc_integrate(self._p(p), C.c_int(len(p)), self._s(s), C.c_int(len(s)), C.byref(sim), C.c_double(tmax))
+
+    # -- spring build --
+    def connect_springs_dist(self, p, max_dist, i_low, i_high, k, gamma, existing=None, n2=False):
+        fn = self.lib.orc_connect_springs_dist_n2 if n2 else self.lib.orc_connect_springs_dist
+        ptr = C.c_void_p(None)
+        ns = C.c_int(0)
+        cap = C.c_int(0)
+        if existing is not None and len(existing):
+            # hand the C side a malloc'd copy it may realloc
+            self.libc.malloc.restype = C.c_void_p
+            nbytes = existing.nbytes
+            ptr = C.c_void_p(self.libc.malloc(C.c_size_t(nbytes)))
+            C.memmove(ptr, existing.ctypes.data, nbytes)
+            ns = C.c_int(len(existing))
+            cap = C.c_int(len(existing))
+        rc = fn(self._p(p), C.c_double(max_dist), C.c_int(i_low), C.c_int(i_high), C.c_double(k), C.c_double(gamma),
+                C.byref(ptr), C.byref(ns), C.byref(cap))
+        assert rc >= 0
+        out = np.empty(ns.value, dtype=SPRING_DTYPE)
+        if ns.value:
+            C.memmove(out.ctypes.data, ptr, out.nbytes)
+        if ptr.value:
+            self.lib.orc_free(ptr)
+        return out
+
+    # -- generators --
+    def _gen(self, fn, min_dist, a, b, c, total_mass, existing=None):
+        self.libc.malloc.restype = C.c_void_p
+        n0 = 0 if existing is None else len(existing)
+        ptr = C.c_void_p(None)
+        if n0:
+            ptr = C.c_void_p(self.libc.malloc(C.c_size_t(existing.nbytes)))
+            C.memmove(ptr, existing.ctypes.data, existing.nbytes)
+        n = fn(C.byref(ptr), C.c_int(n0), C.c_double(min_dist), C.c_double(a), C.c_double(b), C.c_double(c), C.c_double(total_mass))
+        assert n >= 0
+        out = np.empty((n, STRIDE), dtype=np.float64)
+        if n:
+            C.memmove(out.ctypes.data, ptr, out.nbytes)
+        if ptr.value:
+            self.lib.orc_free(ptr)
+        return out
+
+    def rand_ellipsoid(self, min_dist, a, b, c, total_mass, existing=None, n2=False):
+        return self._gen(self.lib.orc_rand_ellipsoid_n2 if n2 else self.lib.orc_rand_ellipsoid, min_dist, a, b, c, total_mass, existing)
+
+    def hcp_ellipsoid(self, min_dist, a, b, c, total_mass, existing=None):
+        return self._gen(self.lib.orc_hcp_ellipsoid, min_dist, a, b, c, total_mass, existing)
+
+    def cubic_ellipsoid(self, min_dist, a, b, c, total_mass, existing=None):
+        return self._gen(self.lib.orc_cubic_ellipsoid, min_dist, a, b, c, total_mass, existing)
+
+    def mindist(self, p, lo=0, hi=None, n2=False):
+        hi = len(p) if hi is None else hi
+        fn = self.lib.orc_mindist_n2 if n2 else self.lib.orc_mindist
+        return fn(self._p(p), C.c_int(lo), C.c_int(hi))
+
+    # -- helpers / diagnostics --
+    def center_sim(self, p, lo, hi):
+        self.lib.orc_center_sim(self._p(p), C.c_int(len(p)), C.c_int(lo), C.c_int(hi))
+
+    def subtract_com(self, p, lo, hi):
+        self.lib.orc_subtract_com(self._p(p), C.c_int(lo), C.c_int(hi))
+
+    def subtract_cov(self, p, lo, hi):
+        self.lib.orc_subtract_cov(self._p(p), C.c_int(lo), C.c_int(hi))
+
+    def spin_body(self, p, lo, hi, omega):
+        self.lib.orc_spin_body(self._p(p), C.c_int(lo), C.c_int(hi), C.c_double(omega[0]), C.c_double(omega[1]), C.c_double(omega[2]))
+
+    def diagnostics(self, p, s, lo=0, hi=None, G=1.0, want_gpe=False):
+        hi = len(p) if hi is None else hi
+        out = np.zeros(20)
+        self.lib.orc_diagnostics(self._p(p), C.c_int(lo), C.c_int(hi), self._s(s), C.c_int(len(s)), C.c_double(G), C.c_int(int(want_gpe)), _d(out))
+        return out
+
+
+class Ref:
+    """The unmodified reference (oracle/_ref/libref_oracle*.so). One live simulation at a time (its spring list is a
+    process-wide global, as in the reference's modules)."""
+
+    def __init__(self, omp=False):
+        so = build_ref()
+        if so is None:
+            raise FileNotFoundError("oracle/_ref/libref_oracle.so not built and /root/reference absent")
+        if omp:
+            so = so.replace("libref_oracle.so", "libref_oracle_omp.so")
+        self.lib = L = C.CDLL(so)
+        L.ref_new.restype = C.c_void_p
+        for name in ("ref_time", "ref_dt", "ref_mindist", "ref_mean_spring_length", "ref_strain"):
+            getattr(L, name).restype = C.c_double
+        L.ref_quiet(1)
+        self.h = C.c_void_p(L.ref_new())
+
+    def close(self):
+        if self.h:
+            self.lib.ref_free(self.h)
+            self.h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def seed(self, s):
+        self.lib.ref_seed(C.c_uint(s))
+
+    def config(self, gravity_basic=0, G=1.0, softening=0.0, dt=1e-3, zero_first=0, center_heartbeat=0, n_perts=0):
+        self.lib.ref_config(self.h, C.c_int(int(gravity_basic)), C.c_double(G), C.c_double(softening), C.c_double(dt),
+                            C.c_int(int(zero_first)), C.c_int(int(center_heartbeat)), C.c_int(n_perts))
+
+    @property
+    def n(self):
+        return self.lib.ref_n(self.h)
+
+    @property
+    def t(self):
+        return self.lib.ref_time(self.h)
+
+    @property
+    def dt(self):
+        return self.lib.ref_dt(self.h)
+
+    def rand_ellipsoid(self, d, a, b, c, M):
+        return self.lib.ref_rand_ellipsoid(self.h, C.c_double(d), C.c_double(a), C.c_double(b), C.c_double(c), C.c_double(M))
+
+    def hcp_ellipsoid(self, d, a, b, c, M):
+        return self.lib.ref_hcp_ellipsoid(self.h, C.c_double(d), C.c_double(a), C.c_double(b), C.c_double(c), C.c_double(M))
+
+    def cubic_ellipsoid(self, d, a, b, c, M):
+        return self.lib.ref_cubic_ellipsoid(self.h, C.c_double(d), C.c_double(a), C.c_double(b), C.c_double(c), C.c_double(M))
+
+    def mindist(self, lo, hi):
+        return self.lib.ref_mindist(self.h, C.c_int(lo), C.c_int(hi))
+
+    def add_particles(self, p):
+        p = np.ascontiguousarray(p, dtype=np.float64)
+        for row in p:
+            self.lib.ref_add_particle(self.h, _d(np.ascontiguousarray(row)))
+
+    def get(self):
+        out = np.empty((self.n, STRIDE))
+        self.lib.ref_get_particles(self.h, _d(out))
+        return out
+
+    def set(self, p):
+        assert p.shape == (self.n, STRIDE)
+        self.lib.ref_set_particles(self.h, _d(np.ascontiguousarray(p)))
+
+    def connect_springs_dist(self, max_dist, lo, hi, k, gamma):
+        return self.lib.ref_connect_springs_dist(self.h, C.c_double(max_dist), C.c_int(lo), C.c_int(hi), C.c_double(k), C.c_double(gamma))
+
+    def add_spring(self, i, j, k, rs0, gamma):
+        return self.lib.ref_add_spring(self.h, C.c_int(i), C.c_int(j), C.c_double(k), C.c_double(rs0), C.c_double(gamma))
+
+    def springs(self):
+        n = self.lib.ref_num_springs()
+        out = np.zeros(n, dtype=SPRING_DTYPE)
+        if n:
+            self.lib.ref_get_springs(out.ctypes.data_as(C.c_void_p))
+        return out
+
+    def set_springs(self, s):
+        s = np.ascontiguousarray(s)
+        self.lib.ref_set_springs(s.ctypes.data_as(C.c_void_p), C.c_int(len(s)))
+
+    def set_gamma(self, g):
+        self.lib.ref_set_gamma(C.c_double(g))
+
+    def spring_i_force(self, s, damped=True):
+        out = np.zeros(3)
+        self.lib.ref_spring_i_force(self.h, C.c_int(s), C.c_int(int(damped)), _d(out))
+        return out
+
+    def zero_accel(self):
+        self.lib.ref_zero_accel(self.h)
+
+    def spring_forces(self):
+        self.lib.ref_spring_forces(self.h)
+
+    def gravity(self):
+        self.lib.ref_gravity(self.h)
+
+    def leapfrog_part1(self):
+        self.lib.ref_leapfrog_part1(self.h)
+
+    def leapfrog_part2(self):
+        self.lib.ref_leapfrog_part2(self.h)
+
+    def step(self, n=1, heartbeat=False):
+        (self.lib.ref_step_hb if heartbeat else self.lib.ref_step)(self.h, C.c_int(n))
+
+    def integrate(self, tmax):
+        return self.lib.ref_integrate(self.h, C.c_double(tmax))
+
+    def center_sim(self, lo, hi):
+        self.lib.ref_center_sim(self.h, C.c_int(lo), C.c_int(hi))
+
+    def subtract_com(self, lo, hi):
+        self.lib.ref_subtract_com(self.h, C.c_int(lo), C.c_int(hi))
+
+    def subtract_cov(self, lo, hi):
+        self.lib.ref_subtract_cov(self.h, C.c_int(lo), C.c_int(hi))
+
+    def spin_body(self, lo, hi, omega):
+        self.lib.ref_spin_body(self.h, C.c_int(lo), C.c_int(hi), C.c_double(omega[0]), C.c_double(omega[1]), C.c_double(omega[2]))
+
+    def diagnostics(self, lo, hi, want_gpe=False):
+        out = np.zeros(20)
+        self.lib.ref_diagnostics(self.h, C.c_int(lo), C.c_int(hi), C.c_int(int(want_gpe)), _d(out))
+        return out
