@@ -1,0 +1,312 @@
+"""ctypes binding over the C-ABI in include/ass_b200.h.
+
+This is measurement / test plumbing, not a second implementation: every method is one C call into libass_b200.so.
+If the library is missing or there is no B200, construction raises -- there is no CPU fallback.
+
+Particle state on the host is an (N, 11) float64 array: x y z vx vy vz ax ay az m r (the leading fields of
+``struct reb_particle``, reference src/rebound.h:540-551) or any array of rows with that prefix and a byte stride.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+F_POS, F_VEL, F_ACC, F_MASS, F_ALL = 1, 2, 4, 8, 15
+K_NAMES = ("gravity", "springs", "leapfrog", "reduce", "connect", "xfer")
+
+SPRING_DTYPE = np.dtype([("k", "<f8"), ("rs0", "<f8"), ("gamma", "<f8"),
+                         ("particle_1", "<i4"), ("particle_2", "<i4")], align=True)
+assert SPRING_DTYPE.itemsize == 32
+
+
+class Params(C.Structure):
+    """struct ass_params"""
+    _fields_ = [("t", C.c_double), ("dt", C.c_double), ("dt_last_done", C.c_double),
+                ("G", C.c_double), ("softening", C.c_double),
+                ("gravity", C.c_int), ("n_active", C.c_int), ("n_perts", C.c_int),
+                ("additional_forces", C.c_int), ("heartbeat", C.c_int),
+                ("exact_finish_time", C.c_int), ("status", C.c_int)]
+
+
+class AssError(RuntimeError):
+    def __init__(self, code, text):
+        super().__init__("libass_b200: error %d: %s" % (code, text))
+        self.code = code
+
+
+_lib = None
+
+
+def lib():
+    """Load (building if needed) libass_b200.so. Raises if it cannot be built or loaded."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB
+    if not os.path.exists(path):
+        path = _build.build_native()
+    L = C.CDLL(path)
+    L.ass_last_error.restype = C.c_char_p
+    L.ass_launch_count.restype = C.c_longlong
+    _lib = L
+    return L
+
+
+def _chk(rc):
+    if rc < 0:
+        raise AssError(rc, lib().ass_last_error().decode())
+    return rc
+
+
+def device_count():
+    return lib().ass_device_count()
+
+
+def init(device=0):
+    _chk(lib().ass_init(C.c_int(device)))
+
+
+def device_info():
+    sm, cc, khz = C.c_int(), C.c_int(), C.c_int()
+    l2, mem = C.c_longlong(), C.c_longlong()
+    _chk(lib().ass_device_info(C.byref(sm), C.byref(l2), C.byref(mem), C.byref(khz), C.byref(cc)))
+    return {"sm_count": sm.value, "l2_bytes": l2.value, "mem_bytes": mem.value, "sm_clock_khz": khz.value, "cc": cc.value}
+
+
+def launch_count():
+    return lib().ass_launch_count()
+
+
+def probe_fp64_peak(iters=1 << 14):
+    tf, ms = C.c_double(), C.c_double()
+    _chk(lib().ass_probe_fp64_peak(C.c_int(iters), C.byref(tf), C.byref(ms)))
+    return tf.value, ms.value
+
+
+def probe_copy_bw(nbytes=1 << 30):
+    g = C.c_double()
+    _chk(lib().ass_probe_copy_bw(C.c_longlong(nbytes), C.byref(g)))
+    return g.value
+
+
+def _rows(p):
+    assert isinstance(p, np.ndarray) and p.dtype == np.float64 and p.ndim == 2 and p.shape[1] >= 10
+    assert p.strides[1] == 8, "rows must be contiguous doubles"
+    return p.ctypes.data_as(C.c_void_p), C.c_size_t(p.strides[0]), C.c_int(p.shape[0])
+
+
+def _springs(s):
+    s = np.ascontiguousarray(s, dtype=SPRING_DTYPE)
+    return s, s.ctypes.data_as(C.c_void_p), C.c_int(len(s))
+
+
+class Sim:
+    """One simulated body resident on the GPU (``ass_sim``)."""
+
+    def __init__(self):
+        self._h = C.c_void_p()
+        _chk(lib().ass_create(C.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            lib().ass_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # -- parameters --
+    @property
+    def params(self):
+        p = Params()
+        _chk(lib().ass_get_params(self._h, C.byref(p)))
+        return p
+
+    def set_params(self, **kw):
+        p = self.params
+        for k, v in kw.items():
+            if not hasattr(p, k):
+                raise AttributeError(k)
+            setattr(p, k, v)
+        _chk(lib().ass_set_params(self._h, C.byref(p)))
+
+    @property
+    def n(self):
+        return lib().ass_num_particles(self._h)
+
+    @property
+    def ns(self):
+        return lib().ass_num_springs(self._h)
+
+    # -- state --
+    def upload(self, p, fields=F_ALL):
+        base, stride, n = _rows(p)
+        _chk(lib().ass_upload_particles(self._h, base, stride, n, C.c_uint(fields)))
+
+    def download(self, p, fields=F_ALL):
+        base, stride, n = _rows(p)
+        _chk(lib().ass_download_particles(self._h, base, stride, n, C.c_uint(fields)))
+        return p
+
+    def set_springs(self, s):
+        s, ptr, n = _springs(s)
+        _chk(lib().ass_set_springs(self._h, ptr, n))
+
+    def update_spring_props(self, s):
+        s, ptr, n = _springs(s)
+        _chk(lib().ass_update_spring_props(self._h, ptr, n))
+
+    def sync(self):
+        _chk(lib().ass_sync(self._h))
+
+    # -- the path --
+    def zero_accel(self):
+        _chk(lib().ass_zero_accel(self._h))
+
+    def spring_forces(self):
+        _chk(lib().ass_spring_forces(self._h))
+
+    def gravity_basic(self):
+        _chk(lib().ass_gravity_basic(self._h))
+
+    def leapfrog_part1(self):
+        _chk(lib().ass_leapfrog_part1(self._h))
+
+    def leapfrog_part2(self):
+        _chk(lib().ass_leapfrog_part2(self._h))
+
+    def step(self, nsteps=1, heartbeat=False):
+        _chk(lib().ass_step(self._h, C.c_int(nsteps), C.c_int(int(heartbeat))))
+
+    def integrate(self, tmax):
+        return _chk(lib().ass_integrate(self._h, C.c_double(tmax)))
+
+    # -- helpers --
+    def center_sim(self, lo, hi):
+        _chk(lib().ass_center_sim(self._h, C.c_int(lo), C.c_int(hi)))
+
+    def subtract_com(self, lo, hi):
+        _chk(lib().ass_subtract_com(self._h, C.c_int(lo), C.c_int(hi)))
+
+    def subtract_cov(self, lo, hi):
+        _chk(lib().ass_subtract_cov(self._h, C.c_int(lo), C.c_int(hi)))
+
+    def move_resolved(self, dx, dv, lo, hi):
+        a = (C.c_double * 3)(*dx)
+        b = (C.c_double * 3)(*dv)
+        _chk(lib().ass_move_resolved(self._h, a, b, C.c_int(lo), C.c_int(hi)))
+
+    def compute_com(self, lo, hi):
+        out = (C.c_double * 3)()
+        _chk(lib().ass_compute_com(self._h, C.c_int(lo), C.c_int(hi), out))
+        return np.array(out[:])
+
+    def compute_cov(self, lo, hi):
+        out = (C.c_double * 3)()
+        _chk(lib().ass_compute_cov(self._h, C.c_int(lo), C.c_int(hi), out))
+        return np.array(out[:])
+
+    def spin_body(self, lo, hi, omega):
+        w = (C.c_double * 3)(*omega)
+        _chk(lib().ass_spin_body(self._h, C.c_int(lo), C.c_int(hi), w))
+
+    def diagnostics(self, lo=0, hi=None, want_gpe=False):
+        hi = self.n if hi is None else hi
+        out = (C.c_double * 20)()
+        _chk(lib().ass_diagnostics(self._h, C.c_int(lo), C.c_int(hi), C.c_int(int(want_gpe)), out))
+        return np.array(out[:])
+
+    # -- spring build --
+    def connect_springs_dist(self, max_dist, lo, hi, k, gamma, existing=None):
+        ptr = C.c_void_p()
+        n_out = C.c_int()
+        if existing is not None and len(existing):
+            ex, exp, exn = _springs(existing)
+        else:
+            ex, exp, exn = None, C.c_void_p(), C.c_int(0)
+        _chk(lib().ass_connect_springs_dist(self._h, C.c_double(max_dist), C.c_int(lo), C.c_int(hi), C.c_double(k),
+                                            C.c_double(gamma), exp, exn, C.byref(ptr), C.byref(n_out)))
+        out = np.empty(n_out.value, dtype=SPRING_DTYPE)
+        if n_out.value:
+            C.memmove(out.ctypes.data, ptr, out.nbytes)
+        if ptr.value:
+            lib().ass_free(ptr)
+        return out
+
+    def mindist(self, lo=0, hi=None):
+        hi = self.n if hi is None else hi
+        out = C.c_double()
+        _chk(lib().ass_mindist(self._h, C.c_int(lo), C.c_int(hi), C.byref(out)))
+        return out.value
+
+    # -- measurement --
+    def timing(self, on=True):
+        _chk(lib().ass_timing_enable(self._h, C.c_int(int(on))))
+
+    def timing_reset(self):
+        _chk(lib().ass_timing_reset(self._h))
+
+    def timing_get(self):
+        ms = (C.c_double * len(K_NAMES))()
+        nl = (C.c_longlong * len(K_NAMES))()
+        _chk(lib().ass_timing_get(self._h, ms, nl))
+        return {k: (ms[i], nl[i]) for i, k in enumerate(K_NAMES)}
+
+    def mark_begin(self):
+        _chk(lib().ass_mark_begin(self._h))
+
+    def mark_end(self):
+        ms = C.c_double()
+        _chk(lib().ass_mark_end(self._h, C.byref(ms)))
+        return ms.value
+
+    def l2_flush(self):
+        _chk(lib().ass_l2_flush(self._h))
+
+
+def _gen(fn, min_dist, a, b, c, total_mass, existing):
+    libc = C.CDLL(None)
+    libc.malloc.restype = C.c_void_p
+    n0 = 0 if existing is None else len(existing)
+    ptr = C.c_void_p(None)
+    cap = C.c_int(n0)
+    if n0:
+        existing = np.ascontiguousarray(existing, dtype=np.float64)
+        assert existing.shape[1] == 11
+        ptr = C.c_void_p(libc.malloc(C.c_size_t(existing.nbytes)))
+        C.memmove(ptr, existing.ctypes.data, existing.nbytes)
+    n = _chk(fn(C.byref(ptr), C.byref(cap), C.c_int(n0), C.c_double(min_dist), C.c_double(a), C.c_double(b), C.c_double(c), C.c_double(total_mass)))
+    out = np.empty((n, 11), dtype=np.float64)
+    if n:
+        C.memmove(out.ctypes.data, ptr, out.nbytes)
+    if ptr.value:
+        lib().ass_free(ptr)
+    return out
+
+
+def srand(seed):
+    """Seed libc's rand(): 'same seed' in the reference means srand() after reb_create_simulation."""
+    C.CDLL(None).srand(C.c_uint(seed))
+
+
+def rand_ellipsoid(min_dist, a, b, c, total_mass, existing=None):
+    return _gen(lib().ass_rand_ellipsoid, min_dist, a, b, c, total_mass, existing)
+
+
+def hcp_ellipsoid(min_dist, a, b, c, total_mass, existing=None):
+    return _gen(lib().ass_hcp_ellipsoid, min_dist, a, b, c, total_mass, existing)
+
+
+def cubic_ellipsoid(min_dist, a, b, c, total_mass, existing=None):
+    return _gen(lib().ass_cubic_ellipsoid, min_dist, a, b, c, total_mass, existing)

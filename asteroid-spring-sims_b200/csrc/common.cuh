@@ -1,0 +1,196 @@
+// common.cuh -- internal declarations shared by the sm_100a translation units of libass_b200.so.
+// Nothing here is part of the C-ABI (include/ass_b200.h is).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/ass_b200.h"
+
+// ---------------------------------------------------------------------------------------------------
+// Device data layout ("SoA of 32-byte vectors")
+//   posm[i] = {x, y, z, m}      one 32 B sector per gather
+//   vel[i]  = {vx, vy, vz, 0}
+//   acc[i]  = {ax, ay, az, 0}
+// A spring endpoint gather touches exactly two sectors (posm, vel); a gravity source tile is a dense
+// run of posm.  HalfEdge is the node-sorted (CSR) copy of `struct spring`, one per endpoint.
+// ---------------------------------------------------------------------------------------------------
+struct __align__(32) vec4d {
+	double x, y, z, w;
+};
+
+struct __align__(32) HalfEdge {
+	double k, rs0, gamma;
+	int nbr;  // the other endpoint
+	int sid;  // index in the caller's spring list
+};
+static_assert(sizeof(HalfEdge) == 32, "HalfEdge must be one sector");
+static_assert(sizeof(ass_spring) == 32, "ass_spring must match struct spring (32 B)");
+
+#define ASS_L_EPS 1e-6  // src_spring/springs.cpp:28
+
+// ---------------------------------------------------------------------------------------------------
+// error plumbing
+// ---------------------------------------------------------------------------------------------------
+void ass_set_error(const char* fmt, ...);
+extern long long g_launch_count;
+
+#define CU_TRY(expr)                                                                              \
+	do {                                                                                          \
+		cudaError_t _e = (expr);                                                                  \
+		if (_e != cudaSuccess) {                                                                  \
+			ass_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e));  \
+			return ASS_ECUDA;                                                                     \
+		}                                                                                         \
+	} while (0)
+
+#define REQUIRE(cond, code, msg)                              \
+	do {                                                      \
+		if (!(cond)) {                                        \
+			ass_set_error("%s: %s", __func__, msg);           \
+			return (code);                                    \
+		}                                                     \
+	} while (0)
+
+// ---------------------------------------------------------------------------------------------------
+// the simulation object
+// ---------------------------------------------------------------------------------------------------
+struct DevBuf {
+	void* p = nullptr;
+	size_t bytes = 0;
+};
+
+struct ShardInfo {
+	int rank = 0, nranks = 1;
+	int lo = 0, hi = 0;              // owned targets
+	std::vector<int> lo_of, hi_of;   // every rank's slab
+	vec4d* window = nullptr;         // exported copy of all N posm rows; owner keeps [lo,hi) current
+	std::vector<vec4d*> peer_window; // mapped peer windows (nullptr for self)
+	bool active = false;
+};
+
+struct ass_sim {
+	int n = 0, cap = 0;     // particles
+	int ns = 0;             // springs
+	int n_he = 0;           // half-edges (2*ns)
+	ass_params prm;
+	cudaStream_t stream = nullptr;
+
+	vec4d *posm = nullptr, *vel = nullptr, *acc = nullptr;
+	vec4d *posm_alt = nullptr, *vel_alt = nullptr;  // ping-pong targets of the fused spring+kick+drift kernel
+	bool have_state = false;
+	bool predrifted = false;  // positions already carry the next step's first half-drift (fused loop only)
+
+	// springs, node-sorted
+	HalfEdge* he = nullptr;
+	int* row_ptr = nullptr;   // n+1
+	int* slot = nullptr;      // 2*ns: half-edge slot of (spring s, endpoint e)
+	size_t he_cap = 0, row_cap = 0;
+	int max_degree = 0;
+
+	// scratch
+	DevBuf stage;             // raw host rows on the device
+	void* h_pinned = nullptr; // pinned bounce buffer
+	size_t h_pinned_bytes = 0;
+	DevBuf grav_partial;      // [split][n] vec4d
+	double* d_red = nullptr;  // reduction outputs (device)
+	double* h_red = nullptr;  // pinned mirror
+	DevBuf red_partial;
+	DevBuf flush;             // L2 flush target
+
+	// timing
+	bool timing = false;
+	double k_ms[ASS_K_COUNT];
+	long long k_launches[ASS_K_COUNT];
+	std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pool;
+	std::vector<std::pair<int, int>> ev_open;  // (class, pool index) pending
+	cudaEvent_t mark0 = nullptr, mark1 = nullptr;
+
+	ShardInfo shard;
+};
+
+int ass_buf_reserve(DevBuf& b, size_t bytes);
+int ass_ensure_device(void);
+int ass_sm_count(void);
+
+// RAII-free timing bracket: tic before a launch, toc after it
+void ass_tic(ass_sim* s, int klass);
+void ass_toc(ass_sim* s, int klass);
+
+#define LAUNCH_CHECK()                                                                        \
+	do {                                                                                      \
+		g_launch_count++;                                                                     \
+		cudaError_t _e = cudaGetLastError();                                                  \
+		if (_e != cudaSuccess) {                                                              \
+			ass_set_error("%s:%d: kernel launch -> %s", __FILE__, __LINE__, cudaGetErrorString(_e)); \
+			return ASS_ECUDA;                                                                 \
+		}                                                                                     \
+	} while (0)
+
+// ---------------------------------------------------------------------------------------------------
+// internal launchers (one per .cu file)
+// ---------------------------------------------------------------------------------------------------
+// springs.cu
+int ass_launch_spring_forces(ass_sim* s, bool zero_first);
+int ass_launch_spring_kick_drift(ass_sim* s, bool zero_first, double dt, bool pre_drift_next);
+// gravity.cu
+int ass_launch_gravity(ass_sim* s);
+int ass_launch_gpe(ass_sim* s, int lo, int hi, double* d_out);
+// leapfrog.cu
+int ass_launch_part1(ass_sim* s, double dt);
+int ass_launch_part2(ass_sim* s, double dt);
+int ass_launch_zero_accel(ass_sim* s);
+// reduce.cu
+int ass_launch_com(ass_sim* s, int lo, int hi, bool velocity, double* d_out3_and_mass);
+int ass_launch_shift(ass_sim* s, int lo, int hi, const double* d_shift3, bool velocity, double sign, double drift_half_dt);
+
+// ---------------------------------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+// Vector::len() of the reference as gcc compiles it (matrix_math.cpp:158-166 under GNU C++ -O3 with FMA):
+// sqrt(fma(z,z, fma(x,x, y*y))), every operation correctly rounded.  The intrinsics pin both the nesting and the
+// rounding so nvcc's own contraction cannot change the bits.
+__device__ __forceinline__ double ref_len2(double x, double y, double z) {
+	return __fma_rn(z, z, __fma_rn(x, x, __dmul_rn(y, y)));
+}
+__device__ __forceinline__ double ref_len(double x, double y, double z) {
+	return __dsqrt_rn(ref_len2(x, y, z));
+}
+__device__ __forceinline__ double ref_dot(double lx, double ly, double lz, double rx, double ry, double rz) {
+	return __fma_rn(lz, rz, __fma_rn(lx, rx, __dmul_rn(ly, ry)));
+}
+
+// 1/a to ~1 ulp without the IEEE-division slow path: hardware seed (MUFU.RCP64H, ~2^-20) + two Newton steps.
+__device__ __forceinline__ double fast_rcp(double a) {
+	double y;
+	asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+	double e = fma(-a, y, 1.0);
+	y = fma(y, e, y);
+	e = fma(-a, y, 1.0);
+	y = fma(y, e, y);
+	return y;
+}
+
+// 1/sqrt(a) to ~1 ulp: hardware seed (MUFU.RSQ64H) + one third-order (Householder) step:
+// eps = 1 - a*y0^2;  y1 = y0 * (1 + eps/2 + 3 eps^2/8), residual ~ (5/16) eps^3.
+__device__ __forceinline__ double fast_rsqrt(double a) {
+	double y;
+	asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+	const double t = a * y;
+	const double eps = fma(-t, y, 1.0);
+	const double p = fma(0.375, eps, 0.5);
+	const double q = eps * p;
+	return fma(y, q, y);
+}
+
+__device__ __forceinline__ double shfl_xor_d(double v, int mask, int width = 32) {
+	return __shfl_xor_sync(0xffffffffu, v, mask, width);
+}
+__device__ __forceinline__ double shfl_down_d(double v, int delta, int width = 32) {
+	return __shfl_down_sync(0xffffffffu, v, delta, width);
+}
+#endif

@@ -1,0 +1,101 @@
+// probe.cu -- roofline denominators measured on the box: a DFMA-only kernel (MEASURED_PEAKS.json carries no FP64
+// figure) and a plain device copy.  Not on the simulation path.
+#include "common.cuh"
+
+namespace {
+
+// 8 independent DFMA chains per thread, fully unrolled; 2 flop per DFMA.
+__global__ void __launch_bounds__(256) k_dfma(double* __restrict__ out, int iters, double a, double b) {
+	double r0 = threadIdx.x, r1 = r0 + 1, r2 = r0 + 2, r3 = r0 + 3, r4 = r0 + 4, r5 = r0 + 5, r6 = r0 + 6, r7 = r0 + 7;
+	for (int i = 0; i < iters; i++) {
+#pragma unroll
+		for (int u = 0; u < 8; u++) {
+			r0 = fma(r0, a, b); r1 = fma(r1, a, b); r2 = fma(r2, a, b); r3 = fma(r3, a, b);
+			r4 = fma(r4, a, b); r5 = fma(r5, a, b); r6 = fma(r6, a, b); r7 = fma(r7, a, b);
+		}
+	}
+	const double s = ((r0 + r1) + (r2 + r3)) + ((r4 + r5) + (r6 + r7));
+	if (s == 123.456) out[blockIdx.x * blockDim.x + threadIdx.x] = s;  // never true; keeps the chains alive
+}
+
+__global__ void k_copy(const double2* __restrict__ in, double2* __restrict__ out, size_t n) {
+	size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+	const size_t stride = (size_t) gridDim.x * blockDim.x;
+	for (; i < n; i += stride) out[i] = in[i];
+}
+
+}  // namespace
+
+extern "C" int ass_probe_fp64_peak(int iters, double* tflops, double* ms_out) {
+	REQUIRE(tflops, ASS_EINVAL, "null out");
+	REQUIRE(iters > 0, ASS_EINVAL, "iters must be positive");
+	int rc = ass_ensure_device();
+	if (rc) return rc;
+	const int blocks = ass_sm_count() * 8, threads = 256;
+	double* d = nullptr;
+	CU_TRY(cudaMalloc(&d, sizeof(double) * (size_t) blocks * threads));
+	cudaEvent_t e0, e1;
+	CU_TRY(cudaEventCreate(&e0));
+	CU_TRY(cudaEventCreate(&e1));
+	k_dfma<<<blocks, threads>>>(d, 64, 0.999999, 1e-9);  // warm-up
+	g_launch_count++;
+	float best = 1e30f;
+	for (int rep = 0; rep < 5; rep++) {
+		cudaEventRecord(e0);
+		k_dfma<<<blocks, threads>>>(d, iters, 0.999999, 1e-9);
+		g_launch_count++;
+		cudaEventRecord(e1);
+		cudaError_t e = cudaEventSynchronize(e1);
+		if (e != cudaSuccess) {
+			ass_set_error("fp64 probe: %s", cudaGetErrorString(e));
+			cudaFree(d);
+			return ASS_ECUDA;
+		}
+		float ms = 0.f;
+		cudaEventElapsedTime(&ms, e0, e1);
+		if (ms < best) best = ms;
+	}
+	const double flop = 2.0 * 64.0 * (double) iters * (double) blocks * threads;
+	*tflops = flop / (best * 1e-3) / 1e12;
+	if (ms_out) *ms_out = best;
+	cudaEventDestroy(e0);
+	cudaEventDestroy(e1);
+	cudaFree(d);
+	return ASS_OK;
+}
+
+extern "C" int ass_probe_copy_bw(long long bytes, double* gbs) {
+	REQUIRE(gbs, ASS_EINVAL, "null out");
+	REQUIRE(bytes >= (1 << 20), ASS_EINVAL, "use at least 1 MiB");
+	int rc = ass_ensure_device();
+	if (rc) return rc;
+	double2 *a = nullptr, *b = nullptr;
+	const size_t n = (size_t) bytes / sizeof(double2);
+	if (cudaMalloc(&a, n * sizeof(double2)) != cudaSuccess || cudaMalloc(&b, n * sizeof(double2)) != cudaSuccess) {
+		cudaGetLastError();
+		cudaFree(a);
+		ass_set_error("copy probe: out of device memory");
+		return ASS_ENOMEM;
+	}
+	cudaMemset(a, 0, n * sizeof(double2));
+	cudaEvent_t e0, e1;
+	cudaEventCreate(&e0);
+	cudaEventCreate(&e1);
+	float best = 1e30f;
+	for (int rep = 0; rep < 6; rep++) {
+		cudaEventRecord(e0);
+		k_copy<<<ass_sm_count() * 16, 256>>>(a, b, n);
+		g_launch_count++;
+		cudaEventRecord(e1);
+		cudaEventSynchronize(e1);
+		float ms = 0.f;
+		cudaEventElapsedTime(&ms, e0, e1);
+		if (rep > 0 && ms < best) best = ms;
+	}
+	*gbs = 2.0 * (double) (n * sizeof(double2)) / (best * 1e-3) / 1e9;
+	cudaEventDestroy(e0);
+	cudaEventDestroy(e1);
+	cudaFree(a);
+	cudaFree(b);
+	return ASS_OK;
+}

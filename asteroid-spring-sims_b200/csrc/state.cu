@@ -1,0 +1,527 @@
+// state.cu -- simulation lifecycle, host<->device state transfer, spring CSR construction, timers.
+#include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+
+// ---------------------------------------------------------------------------------------------------
+// errors / globals
+// ---------------------------------------------------------------------------------------------------
+static thread_local char g_err[1024] = "";
+long long g_launch_count = 0;
+static int g_device = -1;
+static int g_sm_count = 0;
+
+void ass_set_error(const char* fmt, ...) {
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(g_err, sizeof(g_err), fmt, ap);
+	va_end(ap);
+}
+
+extern "C" const char* ass_last_error(void) { return g_err; }
+extern "C" int ass_api_version(void) { return ASS_API_VERSION; }
+extern "C" long long ass_launch_count(void) { return g_launch_count; }
+extern "C" void ass_free(void* p) { free(p); }
+
+extern "C" int ass_device_count(void) {
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess) {
+		cudaGetLastError();
+		return 0;
+	}
+	return n;
+}
+
+extern "C" int ass_init(int device) {
+	int n = ass_device_count();
+	if (n <= 0) {
+		ass_set_error("ass_init: no CUDA device visible (this library has no CPU fallback)");
+		return ASS_ENODEVICE;
+	}
+	REQUIRE(device >= 0 && device < n, ASS_EINVAL, "device index out of range");
+	cudaDeviceProp prop;
+	CU_TRY(cudaGetDeviceProperties(&prop, device));
+	if (prop.major < 10) {
+		ass_set_error("ass_init: device %d is sm_%d%d; this library carries sm_100a code only", device, prop.major, prop.minor);
+		return ASS_ENODEVICE;
+	}
+	CU_TRY(cudaSetDevice(device));
+	CU_TRY(cudaFree(0));
+	g_device = device;
+	g_sm_count = prop.multiProcessorCount;
+	return ASS_OK;
+}
+
+int ass_ensure_device(void) {
+	if (g_device >= 0) {
+		// one process per GPU, but the caller may use several host threads (the reference's OPENGL build runs
+		// reb_integrate on a pthread, src/rebound.c:676-689): bind the device on whichever thread calls in.
+		cudaError_t e = cudaSetDevice(g_device);
+		if (e != cudaSuccess) {
+			ass_set_error("cudaSetDevice(%d) -> %s", g_device, cudaGetErrorString(e));
+			return ASS_ECUDA;
+		}
+		return ASS_OK;
+	}
+	return ass_init(0);
+}
+
+int ass_sm_count(void) { return g_sm_count > 0 ? g_sm_count : 148; }
+
+extern "C" int ass_device_info(int* sm_count, long long* l2_bytes, long long* mem_bytes, int* sm_clock_khz, int* cc) {
+	int rc = ass_ensure_device();
+	if (rc) return rc;
+	cudaDeviceProp prop;
+	CU_TRY(cudaGetDeviceProperties(&prop, g_device));
+	if (sm_count) *sm_count = prop.multiProcessorCount;
+	if (l2_bytes) *l2_bytes = prop.l2CacheSize;
+	if (mem_bytes) *mem_bytes = (long long) prop.totalGlobalMem;
+	if (sm_clock_khz) {
+		int khz = 0;
+		cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, g_device);
+		*sm_clock_khz = khz;
+	}
+	if (cc) *cc = prop.major * 10 + prop.minor;
+	return ASS_OK;
+}
+
+int ass_buf_reserve(DevBuf& b, size_t bytes) {
+	if (bytes <= b.bytes) return ASS_OK;
+	if (b.p) cudaFree(b.p);
+	b.p = nullptr;
+	b.bytes = 0;
+	size_t want = bytes + bytes / 4 + 256;
+	cudaError_t e = cudaMalloc(&b.p, want);
+	if (e != cudaSuccess) {
+		cudaGetLastError();
+		ass_set_error("cudaMalloc(%zu) -> %s", want, cudaGetErrorString(e));
+		return ASS_ENOMEM;
+	}
+	b.bytes = want;
+	return ASS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// timing
+// ---------------------------------------------------------------------------------------------------
+void ass_tic(ass_sim* s, int klass) {
+	if (!s->timing) return;
+	int idx = (int) s->ev_open.size();
+	if (idx >= (int) s->ev_pool.size()) {
+		cudaEvent_t a, b;
+		cudaEventCreate(&a);
+		cudaEventCreate(&b);
+		s->ev_pool.push_back({ a, b });
+	}
+	cudaEventRecord(s->ev_pool[idx].first, s->stream);
+	s->ev_open.push_back({ klass, idx });
+}
+void ass_toc(ass_sim* s, int klass) {
+	(void) klass;
+	if (!s->timing) return;
+	cudaEventRecord(s->ev_pool[s->ev_open.back().second].second, s->stream);
+}
+static int timing_drain(ass_sim* s) {
+	if (s->ev_open.empty()) return ASS_OK;
+	CU_TRY(cudaStreamSynchronize(s->stream));
+	for (auto& o : s->ev_open) {
+		float ms = 0.f;
+		// a bracket whose closing event was never recorded (early error return) is dropped
+		if (cudaEventElapsedTime(&ms, s->ev_pool[o.second].first, s->ev_pool[o.second].second) != cudaSuccess) {
+			cudaGetLastError();
+			continue;
+		}
+		s->k_ms[o.first] += ms;
+		s->k_launches[o.first]++;
+	}
+	s->ev_open.clear();
+	return ASS_OK;
+}
+extern "C" int ass_timing_enable(ass_sim* s, int on) {
+	REQUIRE(s, ASS_EINVAL, "null sim");
+	int rc = timing_drain(s);
+	s->timing = on != 0;
+	return rc;
+}
+extern "C" int ass_timing_reset(ass_sim* s) {
+	REQUIRE(s, ASS_EINVAL, "null sim");
+	int rc = timing_drain(s);
+	for (int i = 0; i < ASS_K_COUNT; i++) {
+		s->k_ms[i] = 0;
+		s->k_launches[i] = 0;
+	}
+	return rc;
+}
+extern "C" int ass_timing_get(ass_sim* s, double ms[ASS_K_COUNT], long long launches[ASS_K_COUNT]) {
+	REQUIRE(s, ASS_EINVAL, "null sim");
+	int rc = timing_drain(s);
+	if (rc) return rc;
+	for (int i = 0; i < ASS_K_COUNT; i++) {
+		if (ms) ms[i] = s->k_ms[i];
+		if (launches) launches[i] = s->k_launches[i];
+	}
+	return ASS_OK;
+}
+extern "C" int ass_mark_begin(ass_sim* s) {
+	REQUIRE(s, ASS_EINVAL, "null sim");
+	CU_TRY(cudaEventRecord(s->mark0, s->stream));
+	return ASS_OK;
+}
+extern "C" int ass_mark_end(ass_sim* s, double* ms) {
+	REQUIRE(s && ms, ASS_EINVAL, "null argument");
+	CU_TRY(cudaEventRecord(s->mark1, s->stream));
+	CU_TRY(cudaEventSynchronize(s->mark1));
+	float f = 0.f;
+	CU_TRY(cudaEventElapsedTime(&f, s->mark0, s->mark1));
+	*ms = f;
+	return ASS_OK;
+}
+
+__global__ void k_fill(double* p, size_t n, double v) {
+	size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+	size_t stride = (size_t) gridDim.x * blockDim.x;
+	for (; i < n; i += stride) p[i] = v;
+}
+extern "C" int ass_l2_flush(ass_sim* s) {
+	REQUIRE(s, ASS_EINVAL, "null sim");
+	const size_t bytes = (size_t) 256 << 20;  // > 126 MB L2
+	int rc = ass_buf_reserve(s->flush, bytes);
+	if (rc) return rc;
+	k_fill<<<ass_sm_count() * 8, 256, 0, s->stream>>>((double*) s->flush.p, bytes / sizeof(double), 0.0);
+	LAUNCH_CHECK();
+	return ASS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// lifecycle
+// ---------------------------------------------------------------------------------------------------
+extern "C" int ass_create(ass_sim** out) {
+	REQUIRE(out, ASS_EINVAL, "null out pointer");
+	int rc = ass_ensure_device();
+	if (rc) return rc;
+	ass_sim* s = new ass_sim();
+	memset(&s->prm, 0, sizeof(s->prm));
+	s->prm.dt = 0.001;  // reb_init_simulation defaults, src/rebound.c:372-376
+	s->prm.G = 1.0;
+	s->prm.n_active = -1;
+	s->prm.exact_finish_time = 1;
+	s->prm.status = -1;
+	s->prm.additional_forces = 1;
+	for (int i = 0; i < ASS_K_COUNT; i++) {
+		s->k_ms[i] = 0;
+		s->k_launches[i] = 0;
+	}
+	if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess ||
+	    cudaEventCreate(&s->mark0) != cudaSuccess || cudaEventCreate(&s->mark1) != cudaSuccess ||
+	    cudaMalloc(&s->d_red, 64 * sizeof(double)) != cudaSuccess ||
+	    cudaMallocHost(&s->h_red, 64 * sizeof(double)) != cudaSuccess) {
+		ass_set_error("ass_create: %s", cudaGetErrorString(cudaGetLastError()));
+		delete s;
+		return ASS_ECUDA;
+	}
+	*out = s;
+	return ASS_OK;
+}
+
+extern "C" int ass_destroy(ass_sim* s) {
+	if (!s) return ASS_OK;
+	ass_ensure_device();
+	if (s->stream) cudaStreamSynchronize(s->stream);
+	cudaFree(s->posm); cudaFree(s->vel); cudaFree(s->acc); cudaFree(s->posm_alt); cudaFree(s->vel_alt);
+	cudaFree(s->he); cudaFree(s->row_ptr); cudaFree(s->slot);
+	cudaFree(s->stage.p); cudaFree(s->grav_partial.p); cudaFree(s->red_partial.p); cudaFree(s->flush.p);
+	cudaFree(s->d_red);
+	if (s->h_red) cudaFreeHost(s->h_red);
+	if (s->h_pinned) cudaFreeHost(s->h_pinned);
+	for (auto& e : s->ev_pool) {
+		cudaEventDestroy(e.first);
+		cudaEventDestroy(e.second);
+	}
+	if (s->mark0) cudaEventDestroy(s->mark0);
+	if (s->mark1) cudaEventDestroy(s->mark1);
+	for (size_t r = 0; r < s->shard.peer_window.size(); r++)
+		if (s->shard.peer_window[r]) cudaIpcCloseMemHandle(s->shard.peer_window[r]);
+	cudaFree(s->shard.window);
+	if (s->stream) cudaStreamDestroy(s->stream);
+	cudaGetLastError();
+	delete s;
+	return ASS_OK;
+}
+
+extern "C" int ass_sync(ass_sim* s) {
+	REQUIRE(s, ASS_EINVAL, "null sim");
+	CU_TRY(cudaStreamSynchronize(s->stream));
+	return ASS_OK;
+}
+
+extern "C" int ass_set_params(ass_sim* s, const ass_params* p) {
+	REQUIRE(s && p, ASS_EINVAL, "null argument");
+	REQUIRE(p->gravity == 0 || p->gravity == 1, ASS_EINVAL, "gravity must be 0 (NONE) or 1 (BASIC)");
+	REQUIRE(p->additional_forces >= 0 && p->additional_forces <= 2, ASS_EINVAL, "additional_forces must be 0, 1 or 2");
+	REQUIRE(p->heartbeat == 0 || p->heartbeat == 1, ASS_EINVAL, "heartbeat must be 0 or 1");
+	if (p->dt != s->prm.dt) s->predrifted = false;
+	s->prm = *p;
+	return ASS_OK;
+}
+extern "C" int ass_get_params(ass_sim* s, ass_params* p) {
+	REQUIRE(s && p, ASS_EINVAL, "null argument");
+	*p = s->prm;
+	return ASS_OK;
+}
+extern "C" int ass_num_particles(ass_sim* s) { return s ? s->n : ASS_EINVAL; }
+extern "C" int ass_num_springs(ass_sim* s) { return s ? s->ns : ASS_EINVAL; }
+
+// ---------------------------------------------------------------------------------------------------
+// particles: host rows <-> device vectors
+// ---------------------------------------------------------------------------------------------------
+static int ensure_particles(ass_sim* s, int n) {
+	if (n <= s->cap) return ASS_OK;
+	int cap = std::max(n + n / 8, 1024);
+	vec4d* nb[5] = { nullptr, nullptr, nullptr, nullptr, nullptr };
+	for (int i = 0; i < 5; i++) {
+		if (cudaMalloc(&nb[i], sizeof(vec4d) * (size_t) cap) != cudaSuccess) {
+			cudaGetLastError();
+			for (int j = 0; j < i; j++) cudaFree(nb[j]);
+			ass_set_error("out of device memory for %d particles", cap);
+			return ASS_ENOMEM;
+		}
+		cudaMemsetAsync(nb[i], 0, sizeof(vec4d) * (size_t) cap, s->stream);
+	}
+	vec4d** old[5] = { &s->posm, &s->vel, &s->acc, &s->posm_alt, &s->vel_alt };
+	for (int i = 0; i < 5; i++) {
+		if (*old[i] && s->n > 0 && i < 3)
+			cudaMemcpyAsync(nb[i], *old[i], sizeof(vec4d) * (size_t) s->n, cudaMemcpyDeviceToDevice, s->stream);
+	}
+	cudaStreamSynchronize(s->stream);
+	for (int i = 0; i < 5; i++) {
+		cudaFree(*old[i]);
+		*old[i] = nb[i];
+	}
+	s->cap = cap;
+	return ASS_OK;
+}
+
+__global__ void k_unpack_rows(const unsigned char* __restrict__ rows, size_t stride, int n, unsigned fields,
+		vec4d* __restrict__ posm, vec4d* __restrict__ vel, vec4d* __restrict__ acc) {
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const double* r = (const double*) (rows + (size_t) i * stride);
+	if (fields & (ASS_F_POS | ASS_F_MASS)) {
+		vec4d p = posm[i];
+		if (fields & ASS_F_POS) { p.x = r[0]; p.y = r[1]; p.z = r[2]; }
+		if (fields & ASS_F_MASS) p.w = r[9];
+		posm[i] = p;
+	}
+	if (fields & ASS_F_VEL) { vec4d v; v.x = r[3]; v.y = r[4]; v.z = r[5]; v.w = 0.0; vel[i] = v; }
+	if (fields & ASS_F_ACC) { vec4d a; a.x = r[6]; a.y = r[7]; a.z = r[8]; a.w = 0.0; acc[i] = a; }
+}
+
+__global__ void k_pack_rows(unsigned char* __restrict__ rows, size_t stride, int n, unsigned fields,
+		const vec4d* __restrict__ posm, const vec4d* __restrict__ vel, const vec4d* __restrict__ acc) {
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	double* r = (double*) (rows + (size_t) i * stride);
+	if (fields & (ASS_F_POS | ASS_F_MASS)) {
+		vec4d p = posm[i];
+		if (fields & ASS_F_POS) { r[0] = p.x; r[1] = p.y; r[2] = p.z; }
+		if (fields & ASS_F_MASS) r[9] = p.w;
+	}
+	if (fields & ASS_F_VEL) { vec4d v = vel[i]; r[3] = v.x; r[4] = v.y; r[5] = v.z; }
+	if (fields & ASS_F_ACC) { vec4d a = acc[i]; r[6] = a.x; r[7] = a.y; r[8] = a.z; }
+}
+
+static int ensure_pinned(ass_sim* s, size_t bytes) {
+	if (bytes <= s->h_pinned_bytes) return ASS_OK;
+	if (s->h_pinned) cudaFreeHost(s->h_pinned);
+	s->h_pinned = nullptr;
+	s->h_pinned_bytes = 0;
+	size_t want = bytes + bytes / 4 + 4096;
+	if (cudaMallocHost(&s->h_pinned, want) != cudaSuccess) {
+		cudaGetLastError();
+		ass_set_error("cudaMallocHost(%zu) failed", want);
+		return ASS_ENOMEM;
+	}
+	s->h_pinned_bytes = want;
+	return ASS_OK;
+}
+
+extern "C" int ass_upload_particles(ass_sim* s, const void* base, size_t stride, int n, unsigned fields) {
+	REQUIRE(s, ASS_EINVAL, "null sim");
+	REQUIRE(n >= 0, ASS_EINVAL, "negative particle count");
+	REQUIRE(n == 0 || base, ASS_EINVAL, "null particle array");
+	REQUIRE(stride >= 10 * sizeof(double) && stride % sizeof(double) == 0, ASS_EINVAL, "stride must hold the 10 leading doubles and be 8-byte aligned");
+	REQUIRE((fields & ~ASS_F_ALL) == 0 && fields != 0, ASS_EINVAL, "bad field mask");
+	int rc = ass_ensure_device();
+	if (rc) return rc;
+	if (n != s->n) {
+		// a different particle count is a new body: everything must come from the host
+		REQUIRE(fields == ASS_F_ALL, ASS_ESTATE, "particle count changed: upload ASS_F_ALL");
+		if ((rc = ensure_particles(s, n))) return rc;
+		if (n != s->n) { s->ns = 0; s->n_he = 0; }  // springs refer to the old body
+		s->n = n;
+	}
+	s->predrifted = false;
+	if (n == 0) { s->have_state = true; return ASS_OK; }
+	const size_t bytes = (size_t) n * stride;
+	if ((rc = ass_buf_reserve(s->stage, bytes))) return rc;
+	ass_tic(s, ASS_K_XFER);
+	// The caller's array is ordinary pageable memory (realloc'd by reb_add, src/particle.c:53-56): one plain copy.
+	CU_TRY(cudaMemcpyAsync(s->stage.p, base, bytes, cudaMemcpyHostToDevice, s->stream));
+	k_unpack_rows<<<(n + 255) / 256, 256, 0, s->stream>>>((const unsigned char*) s->stage.p, stride, n, fields, s->posm, s->vel, s->acc);
+	LAUNCH_CHECK();
+	ass_toc(s, ASS_K_XFER);
+	// pageable source: the copy has been staged when cudaMemcpyAsync returns, but keep the contract simple
+	CU_TRY(cudaStreamSynchronize(s->stream));
+	s->have_state = true;
+	return ASS_OK;
+}
+
+extern "C" int ass_download_particles(ass_sim* s, void* base, size_t stride, int n, unsigned fields) {
+	REQUIRE(s, ASS_EINVAL, "null sim");
+	REQUIRE(s->have_state, ASS_ESTATE, "no particle state on the device");
+	REQUIRE(n == s->n, ASS_EINVAL, "particle count does not match the device state");
+	REQUIRE(n == 0 || base, ASS_EINVAL, "null particle array");
+	REQUIRE(stride >= 10 * sizeof(double) && stride % sizeof(double) == 0, ASS_EINVAL, "stride must hold the 10 leading doubles and be 8-byte aligned");
+	REQUIRE((fields & ~ASS_F_ALL) == 0 && fields != 0, ASS_EINVAL, "bad field mask");
+	REQUIRE(!s->predrifted, ASS_ESTATE, "internal: positions are mid-step");
+	if (n == 0) return ASS_OK;
+	int rc = ass_ensure_device();
+	if (rc) return rc;
+	// Only the requested doubles may change on the host (the rows also hold pointers, hash, r, ...): pack the
+	// fields densely on the device, copy that, and scatter into the caller's rows here.
+	const int nf = ((fields & ASS_F_POS) ? 3 : 0) + ((fields & ASS_F_VEL) ? 3 : 0) + ((fields & ASS_F_ACC) ? 3 : 0) + ((fields & ASS_F_MASS) ? 1 : 0);
+	const size_t dense = (size_t) n * 10 * sizeof(double);
+	if ((rc = ass_buf_reserve(s->stage, dense))) return rc;
+	if ((rc = ensure_pinned(s, dense))) return rc;
+	ass_tic(s, ASS_K_XFER);
+	k_pack_rows<<<(n + 255) / 256, 256, 0, s->stream>>>((unsigned char*) s->stage.p, 10 * sizeof(double), n, fields, s->posm, s->vel, s->acc);
+	LAUNCH_CHECK();
+	CU_TRY(cudaMemcpyAsync(s->h_pinned, s->stage.p, dense, cudaMemcpyDeviceToHost, s->stream));
+	ass_toc(s, ASS_K_XFER);
+	CU_TRY(cudaStreamSynchronize(s->stream));
+	(void) nf;
+	const double* src = (const double*) s->h_pinned;
+	unsigned char* dst = (unsigned char*) base;
+	for (int i = 0; i < n; i++) {
+		double* r = (double*) (dst + (size_t) i * stride);
+		const double* q = src + (size_t) i * 10;
+		if (fields & ASS_F_POS) { r[0] = q[0]; r[1] = q[1]; r[2] = q[2]; }
+		if (fields & ASS_F_VEL) { r[3] = q[3]; r[4] = q[4]; r[5] = q[5]; }
+		if (fields & ASS_F_ACC) { r[6] = q[6]; r[7] = q[7]; r[8] = q[8]; }
+		if (fields & ASS_F_MASS) r[9] = q[9];
+	}
+	return ASS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// springs: caller's list -> node-sorted half-edges
+// ---------------------------------------------------------------------------------------------------
+extern "C" int ass_set_springs(ass_sim* s, const ass_spring* sp, int ns) {
+	REQUIRE(s, ASS_EINVAL, "null sim");
+	REQUIRE(ns >= 0, ASS_EINVAL, "negative spring count");
+	REQUIRE(ns == 0 || sp, ASS_EINVAL, "null spring array");
+	REQUIRE(s->have_state, ASS_ESTATE, "upload particles before springs");
+	int rc = ass_ensure_device();
+	if (rc) return rc;
+	const int n = s->n;
+	std::vector<int> row((size_t) n + 1, 0);
+	for (int q = 0; q < ns; q++) {
+		const int i = sp[q].particle_1, j = sp[q].particle_2;
+		if (i < 0 || j < 0 || i >= n || j >= n) {
+			ass_set_error("ass_set_springs: spring %d joins (%d,%d) outside [0,%d)", q, i, j, n);
+			return ASS_EINVAL;
+		}
+		if (i == j) {  // add_spring throws "Cannot connect a particle to itself." (springs.cpp:57-59)
+			ass_set_error("ass_set_springs: spring %d connects particle %d to itself", q, i);
+			return ASS_EINVAL;
+		}
+		row[(size_t) i + 1]++;
+		row[(size_t) j + 1]++;
+	}
+	int maxdeg = 0;
+	for (int i = 0; i < n; i++) {
+		maxdeg = std::max(maxdeg, row[(size_t) i + 1]);
+		row[(size_t) i + 1] += row[i];
+	}
+	const size_t nhe = (size_t) 2 * ns;
+	std::vector<HalfEdge> he(nhe);
+	std::vector<int> slot(nhe);
+	std::vector<int> fill(row.begin(), row.end() - 1);
+	for (int q = 0; q < ns; q++) {
+		const int e[2] = { sp[q].particle_1, sp[q].particle_2 };
+		for (int side = 0; side < 2; side++) {
+			const int at = fill[e[side]]++;
+			HalfEdge h;
+			h.k = sp[q].k; h.rs0 = sp[q].rs0; h.gamma = sp[q].gamma;
+			h.nbr = e[1 - side];
+			h.sid = q;
+			he[at] = h;
+			slot[(size_t) 2 * q + side] = at;
+		}
+	}
+	if (nhe > s->he_cap) {
+		cudaFree(s->he); cudaFree(s->slot);
+		s->he = nullptr; s->slot = nullptr; s->he_cap = 0;
+		size_t cap = nhe + nhe / 8 + 64;
+		if (cudaMalloc(&s->he, sizeof(HalfEdge) * cap) != cudaSuccess || cudaMalloc(&s->slot, sizeof(int) * cap) != cudaSuccess) {
+			cudaGetLastError();
+			ass_set_error("out of device memory for %zu half-edges", cap);
+			return ASS_ENOMEM;
+		}
+		s->he_cap = cap;
+	}
+	if ((size_t) n + 1 > s->row_cap) {
+		cudaFree(s->row_ptr);
+		s->row_ptr = nullptr; s->row_cap = 0;
+		size_t cap = (size_t) n + 1 + n / 8 + 64;
+		if (cudaMalloc(&s->row_ptr, sizeof(int) * cap) != cudaSuccess) {
+			cudaGetLastError();
+			ass_set_error("out of device memory for %zu row pointers", cap);
+			return ASS_ENOMEM;
+		}
+		s->row_cap = cap;
+	}
+	ass_tic(s, ASS_K_XFER);
+	if (nhe) {
+		CU_TRY(cudaMemcpyAsync(s->he, he.data(), sizeof(HalfEdge) * nhe, cudaMemcpyHostToDevice, s->stream));
+		CU_TRY(cudaMemcpyAsync(s->slot, slot.data(), sizeof(int) * nhe, cudaMemcpyHostToDevice, s->stream));
+	}
+	CU_TRY(cudaMemcpyAsync(s->row_ptr, row.data(), sizeof(int) * ((size_t) n + 1), cudaMemcpyHostToDevice, s->stream));
+	ass_toc(s, ASS_K_XFER);
+	CU_TRY(cudaStreamSynchronize(s->stream));  // the vectors above die here
+	s->ns = ns;
+	s->n_he = (int) nhe;
+	s->max_degree = maxdeg;
+	return ASS_OK;
+}
+
+__global__ void k_scatter_props(const ass_spring* __restrict__ sp, const int* __restrict__ slot, HalfEdge* __restrict__ he, int ns) {
+	int q = blockIdx.x * blockDim.x + threadIdx.x;
+	if (q >= ns) return;
+	const ass_spring v = sp[q];
+	for (int side = 0; side < 2; side++) {
+		HalfEdge* h = he + slot[(size_t) 2 * q + side];
+		h->k = v.k; h->rs0 = v.rs0; h->gamma = v.gamma;
+	}
+}
+
+extern "C" int ass_update_spring_props(ass_sim* s, const ass_spring* sp, int ns) {
+	REQUIRE(s, ASS_EINVAL, "null sim");
+	REQUIRE(ns == s->ns, ASS_EINVAL, "spring count differs from the device list: call ass_set_springs");
+	if (ns == 0) return ASS_OK;
+	REQUIRE(sp, ASS_EINVAL, "null spring array");
+	int rc = ass_ensure_device();
+	if (rc) return rc;
+	if ((rc = ass_buf_reserve(s->stage, sizeof(ass_spring) * (size_t) ns))) return rc;
+	ass_tic(s, ASS_K_XFER);
+	CU_TRY(cudaMemcpyAsync(s->stage.p, sp, sizeof(ass_spring) * (size_t) ns, cudaMemcpyHostToDevice, s->stream));
+	k_scatter_props<<<(ns + 255) / 256, 256, 0, s->stream>>>((const ass_spring*) s->stage.p, s->slot, s->he, ns);
+	LAUNCH_CHECK();
+	ass_toc(s, ASS_K_XFER);
+	CU_TRY(cudaStreamSynchronize(s->stream));
+	return ASS_OK;
+}

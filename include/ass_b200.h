@@ -1,0 +1,176 @@
+/* include/ass_b200.h -- the C-ABI boundary of the B200-native hot path.
+ *
+ * One shared library, libass_b200.so (built from asteroid-spring-sims_b200/csrc/ for sm_100a), exports exactly the
+ * symbols declared here.  Plain pointers and sizes only: no C++ types, no torch types, no reference headers.  Every
+ * entry point names the reference function it replaces (paths relative to the reference tree).  Host code above this
+ * line stays C++ (asteroid-spring-sims_b200/host/): it mirrors the reference's own symbols (reb_integrate, reb_step,
+ * spring_forces, connect_springs_dist, ...) and forwards here.  See INTEGRATION.md.
+ *
+ * Conventions
+ *   - All functions return 0 on success, a negative ASS_E* code on failure; ass_last_error() gives the text.
+ *     Nothing throws across this boundary.  There is NO CPU fallback: without a CUDA device every compute call
+ *     fails with ASS_ENODEVICE.
+ *   - A simulation (`ass_sim`) owns device-resident SoA copies of the particle and spring state.  The host
+ *     `struct reb_particle[]` / `std::vector<spring>` stay the API-visible truth; the device copy is a cache that the
+ *     caller fills (ass_upload_*) and drains (ass_download_*) explicitly.
+ *   - Host particle arrays are addressed as (base, stride_bytes): row i starts at base + i*stride and begins with the
+ *     eleven doubles x y z vx vy vz ax ay az m r -- the leading fields of `struct reb_particle`
+ *     (src/rebound.h:540-551; sizeof == 128).  A packed (N,11) double matrix is stride 88.
+ *   - Work is queued on the simulation's own CUDA stream; calls that return data to the host synchronise it.
+ */
+#ifndef ASS_B200_H
+#define ASS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ASS_API_VERSION 1
+
+/* ---- error codes ---- */
+#define ASS_OK 0
+#define ASS_EINVAL (-1)    /* bad argument (also: spring with particle_1 == particle_2, springs.cpp:57-59) */
+#define ASS_ECUDA (-2)     /* CUDA runtime error; text in ass_last_error() */
+#define ASS_ENODEVICE (-3) /* no usable sm_100 device */
+#define ASS_ENOMEM (-4)
+#define ASS_ESTATE (-5)    /* call order violated (e.g. forces before upload) */
+#define ASS_ECOMM (-6)     /* multi-GPU exchange failed */
+
+/* ---- field masks for upload / download ---- */
+#define ASS_F_POS 1u
+#define ASS_F_VEL 2u
+#define ASS_F_ACC 4u
+#define ASS_F_MASS 8u /* m and r */
+#define ASS_F_ALL 15u
+
+/* == `struct spring`, src_spring/springs.h:16-22: 32 bytes, same field order, so a std::vector<spring>::data()
+ * pointer can be passed straight through. */
+typedef struct ass_spring {
+	double k;       /* spring constant */
+	double rs0;     /* rest length */
+	double gamma;   /* damping coefficient */
+	int particle_1; /* lower node index  */
+	int particle_2; /* higher node index */
+} ass_spring;
+
+/* The scalars of `struct reb_simulation` (src/rebound.h:589-836) that the path reads or writes. */
+typedef struct ass_params {
+	double t;            /* r->t */
+	double dt;           /* r->dt */
+	double dt_last_done; /* r->dt_last_done */
+	double G;            /* r->G */
+	double softening;    /* r->softening */
+	int gravity;         /* 0 = REB_GRAVITY_NONE, 1 = REB_GRAVITY_BASIC (src/rebound.h:771-776) */
+	int n_active;        /* r->N_active; -1 = all particles are sources (src/gravity.c:64) */
+	int n_perts;         /* module global num_perts: trailing point masses that carry no springs */
+	int additional_forces; /* what ass_step runs where reb_step calls r->additional_forces (src/rebound.c:114):
+	                          0 nothing, 1 spring_forces, 2 zero_accel + spring_forces
+	                          (modules/asteroid_spin/problem.cpp:225-231) */
+	int heartbeat;       /* what ass_integrate runs where reb_integrate_raw calls the heartbeat (src/rebound.c:633,641):
+	                          0 nothing, 1 center_sim(0, N - n_perts) (modules/asteroid_spin/problem.cpp:196) */
+	int exact_finish_time; /* r->exact_finish_time (src/rebound.c:519) */
+	int status;          /* enum REB_STATUS (src/rebound.h:358-368); written by ass_integrate */
+} ass_params;
+
+typedef struct ass_sim ass_sim; /* opaque */
+
+/* ---- library / device ---- */
+int ass_api_version(void);
+const char* ass_last_error(void);
+/* Select the CUDA device for this process (one process per GPU). Fails with ASS_ENODEVICE when there is none. */
+int ass_init(int device);
+int ass_device_count(void);
+/* sm count, L2 bytes, total memory bytes, max SM clock (kHz), compute capability major*10+minor */
+int ass_device_info(int* sm_count, long long* l2_bytes, long long* mem_bytes, int* sm_clock_khz, int* cc);
+
+/* ---- lifecycle ---- */
+int ass_create(ass_sim** out);
+int ass_destroy(ass_sim* sim);
+int ass_sync(ass_sim* sim);
+int ass_set_params(ass_sim* sim, const ass_params* p);
+int ass_get_params(ass_sim* sim, ass_params* p);
+
+/* ---- state transfer (replaces nothing: it is the residency boundary, SURVEY section 8b "Ownership") ---- */
+int ass_upload_particles(ass_sim* sim, const void* base, size_t stride_bytes, int n, unsigned fields);
+int ass_download_particles(ass_sim* sim, void* base, size_t stride_bytes, int n, unsigned fields);
+/* Replace the whole spring list (after connect_springs_dist / add_spring / del_spring). Builds the node-sorted
+ * half-edge (CSR) layout used by ass_spring_forces.  Checks 0 <= particle_1 != particle_2 < n. */
+int ass_set_springs(ass_sim* sim, const ass_spring* springs, int ns);
+/* Same topology, new k / rs0 / gamma (set_gamma, divide_gamma, adjust_spring_props, kill_springs;
+ * src_spring/springs.cpp:146-213). */
+int ass_update_spring_props(ass_sim* sim, const ass_spring* springs, int ns);
+int ass_num_particles(ass_sim* sim);
+int ass_num_springs(ass_sim* sim);
+
+/* ---- the per-step path, one reference function each ---- */
+int ass_zero_accel(ass_sim* sim);     /* zero_accel, src_spring/physics.cpp:557-564 */
+int ass_spring_forces(ass_sim* sim);  /* spring_forces, src_spring/springs.cpp:288-346: a += springs */
+int ass_gravity_basic(ass_sim* sim);  /* reb_calculate_acceleration, REB_GRAVITY_BASIC, src/gravity.c:72-103: a = gravity.
+                                         With params.gravity == 0 this is the NONE branch: a no-op. */
+int ass_leapfrog_part1(ass_sim* sim); /* reb_integrator_leapfrog_part1, src/integrator_leapfrog.c:39-51 */
+int ass_leapfrog_part2(ass_sim* sim); /* reb_integrator_leapfrog_part2, src/integrator_leapfrog.c:52-67 */
+/* reb_step (src/rebound.c:69-144) x nsteps with the built-in additional_forces of params.additional_forces, fused
+ * (gravity -> springs+kick+drift) and without returning to the host between steps.  with_heartbeat != 0 runs the
+ * built-in heartbeat (params.heartbeat) after each step, as reb_integrate_raw does (src/rebound.c:640-641). */
+int ass_step(ass_sim* sim, int nsteps, int with_heartbeat);
+/* reb_integrate (src/rebound.c:621-704): heartbeat at t=0, then steps until tmax with reb_check_exit's
+ * exact_finish_time handling (src/rebound.c:509-569).  Returns the REB_STATUS (>= 0) or a negative error. */
+int ass_integrate(ass_sim* sim, double tmax);
+
+/* ---- per-step heartbeat helpers (src_spring/physics.cpp) ---- */
+int ass_center_sim(ass_sim* sim, int i_low, int i_high);      /* physics.cpp:98-109 */
+int ass_subtract_com(ass_sim* sim, int i_low, int i_high);    /* physics.cpp:77-84  */
+int ass_subtract_cov(ass_sim* sim, int i_low, int i_high);    /* physics.cpp:88-94  */
+int ass_move_resolved(ass_sim* sim, const double dx[3], const double dv[3], int i_low, int i_high); /* physics.cpp:387-402 */
+int ass_compute_com(ass_sim* sim, int i_low, int i_high, double out[3]); /* physics.cpp:41-57 */
+int ass_compute_cov(ass_sim* sim, int i_low, int i_high, double out[3]); /* physics.cpp:60-74 */
+int ass_spin_body(ass_sim* sim, int i_low, int i_high, const double omega[3]); /* physics.cpp:184-210 */
+/* out[20]: [0..2] CoM, [3..5] CoV, [6..8] L = measure_L (physics.cpp:136-162), [9] compute_rot_kin (:508-528),
+ * [10] spring_potential_energy (:457-476), [11] grav_potential_energy (:479-504; 0 unless want_gpe),
+ * [12] dEdt_total (:409-454), [13..18] mom_inertia xx yy zz xy xz yz (:116-134), [19] sum_mass (orb.cpp:438-449) */
+int ass_diagnostics(ass_sim* sim, int i_low, int i_high, int want_gpe, double out[20]);
+
+/* ---- spring build: connect_springs_dist, src_spring/springs.cpp:110-143 ---- */
+/* Uniform-grid cell-list search on the device positions of particles [i_low, i_high).  Appends to the caller's list
+ * exactly what the reference would: pairs (i<j) with sqrt(fma(dz,dz,fma(dx,dx,dy*dy))) < max_dist (strict), in
+ * lexicographic (i,j) order, rs0 = that length bit for bit, k/gamma from the prototype, pairs already in
+ * existing[0..n_existing) skipped (add_spring's duplicate rule, springs.cpp:70-79).
+ * On return *out points at a malloc'd array of *n_out NEW springs (caller frees with ass_free). */
+int ass_connect_springs_dist(ass_sim* sim, double max_dist, int i_low, int i_high, double k, double gamma,
+		const ass_spring* existing, int n_existing, ass_spring** out, int* n_out);
+/* mindist, src_spring/shapes.cpp:814-833, by the same grid */
+int ass_mindist(ass_sim* sim, int i_low, int i_high, double* out);
+void ass_free(void* p);
+
+/* ---- node generators (host side of the build path; sequential by construction: one libc rand() stream and an
+ *      accept test that depends on every earlier accept).  src_spring/shapes.cpp:210-278, 282-352, 356-431 ---- */
+/* Appends to a packed (n,11) row array (realloc'd through *rows / *cap_rows); returns the new count or <0. */
+int ass_rand_ellipsoid(double** rows, int* cap_rows, int n0, double min_dist, double a, double b, double c, double total_mass);
+int ass_hcp_ellipsoid(double** rows, int* cap_rows, int n0, double min_dist, double a, double b, double c, double total_mass);
+int ass_cubic_ellipsoid(double** rows, int* cap_rows, int n0, double min_dist, double a, double b, double c, double total_mass);
+
+/* ---- measurement ---- */
+/* Kernel classes for the per-kernel CUDA-event timers */
+enum { ASS_K_GRAVITY = 0, ASS_K_SPRINGS = 1, ASS_K_LEAPFROG = 2, ASS_K_REDUCE = 3, ASS_K_CONNECT = 4, ASS_K_XFER = 5, ASS_K_COUNT = 6 };
+int ass_timing_enable(ass_sim* sim, int on);      /* record an event pair around every kernel launch (slower) */
+int ass_timing_reset(ass_sim* sim);
+/* total device ms and launch count per class since the last reset (synchronises) */
+int ass_timing_get(ass_sim* sim, double ms[ASS_K_COUNT], long long launches[ASS_K_COUNT]);
+/* stream-ordered stopwatch on the simulation's stream: returns device ms between the two marks (synchronises) */
+int ass_mark_begin(ass_sim* sim);
+int ass_mark_end(ass_sim* sim, double* ms);
+int ass_l2_flush(ass_sim* sim);                    /* overwrite a buffer larger than L2 */
+/* DFMA-only microbenchmark: the FP64 roofline denominator (MEASURED_PEAKS.json has none). iters ~ 1<<14. */
+int ass_probe_fp64_peak(int iters, double* tflops, double* ms);
+/* device copy bandwidth (read+write bytes / time) for a buffer of `bytes` */
+int ass_probe_copy_bw(long long bytes, double* gbs);
+/* total number of kernel launches issued by this library in this process */
+long long ass_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ASS_B200_H */

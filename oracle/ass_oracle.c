@@ -480,7 +480,9 @@ static int lattice_common(double** pp, int n0, double a, double b, double c, dou
 
 int orc_hcp_ellipsoid(double** pp, int n0, double min_dist, double a, double b, double c, double total_mass) {
 	/* shapes.cpp:282-352.  shapes.cpp is GNU C++: `dx*i + xfac*(j%2) + xfac*(k%2)` is contracted by gcc to
-	 * fma(xfac, k%2, fma(xfac, j%2, dx*i)); `yfac*(j + 0.5*(k%2))` to yfac * fma(0.5, k%2, j). */
+	 * fma(dx, i, t_j) + t_k with the loop invariants t_j = xfac*(j%2), t_k = xfac*(k%2) hoisted (found by matching
+	 * the reference's output bit for bit, tests/test_oracle.py::test_golden_lattices);
+	 * `yfac*(j + 0.5*(k%2))` to yfac * fma(0.5, k%2, j). */
 	double* p = *pp;
 	int cap = n0, n = n0;
 	const double dx = 1.08 * min_dist;
@@ -491,7 +493,7 @@ int orc_hcp_ellipsoid(double** pp, int n0, double min_dist, double a, double b, 
 		for (int j = -ny; j <= ny; j++) {
 			const double y = yfac * fma(0.5, (double) (k % 2), (double) j);
 			for (int i = -nx; i <= nx; i++) {
-				const double x = fma(xfac, (double) (k % 2), fma(xfac, (double) (j % 2), dx * i));
+				const double x = fma(dx, (double) i, xfac * (double) (j % 2)) + xfac * (double) (k % 2);
 				if (len3(x / a, y / b, z / c) <= 1.0) {
 					p = grow_rows(p, &cap, n + 1);
 					memset(&P(n, 0), 0, sizeof(double) * ORC_STRIDE);

@@ -238,6 +238,9 @@ class Ref:
     def dt(self):
         return self.lib.ref_dt(self.h)
 
+    def set_time(self, t):
+        self.lib.ref_set_time(self.h, C.c_double(t))
+
     def rand_ellipsoid(self, d, a, b, c, M):
         return self.lib.ref_rand_ellipsoid(self.h, C.c_double(d), C.c_double(a), C.c_double(b), C.c_double(c), C.c_double(M))
 

@@ -99,6 +99,7 @@ void ref_config(void* h, int gravity_basic, double G, double softening, double d
 	num_perts = n_perts;
 }
 double ref_time(void* h) { return ((reb_simulation*) h)->t; }
+void ref_set_time(void* h, double t) { ((reb_simulation*) h)->t = t; }
 double ref_dt(void* h) { return ((reb_simulation*) h)->dt; }
 int ref_n(void* h) { return ((reb_simulation*) h)->N; }
 

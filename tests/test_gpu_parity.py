@@ -1,0 +1,408 @@
+"""Parity of the CUDA path (through the C-ABI) against the CPU oracle and the reference's golden vectors.
+
+Bars (task section 3, BASELINE.json north_star):
+  * spring list: bit-exact (i, j, rs0 bits, order)
+  * leapfrog drift/kick given the same accelerations: bit-exact
+  * per-evaluation accelerations: max_i |a_gpu - a_ref| / max_i |a_ref| <= 1e-12   (ACC_TOL)
+  * energy / spin angular momentum history over 200 steps: 1e-9 relative             (HIST_TOL)
+"""
+import numpy as np
+import pytest
+
+from conftest import kat_particles, same_bits
+from oracle.bindings import SPRING_DTYPE, make_sim
+
+pytestmark = pytest.mark.gpu
+
+ACC_TOL = 1e-12
+HIST_TOL = 1e-9
+A_, B_, C_ = 1.0, 0.7, 0.5
+K, GAMMA = 0.08, 5.0
+OMEGA = (0.1, 0.0, 0.2)
+EMPTY = np.zeros(0, dtype=SPRING_DTYPE)
+
+
+def acc_err(got, want):
+    return np.abs(got - want).max() / max(np.abs(want).max(), 1e-300)
+
+
+def new_sim(gpu, p, springs=None, **params):
+    s = gpu.Sim()
+    s.upload(p)
+    if springs is not None:
+        s.set_springs(springs)
+    if params:
+        s.set_params(**params)
+    return s
+
+
+# ---------------------------------------------------------------------------------------------------
+# the reference's 3-particle known-answer fixture
+# ---------------------------------------------------------------------------------------------------
+def test_kat_connect_and_force(gpu, kat3):
+    P = kat_particles()
+    with new_sim(gpu, P) as s:
+        assert s.connect_springs_dist(5.0, 0, 3, 11.0, 35.0).tobytes() == kat3["connect5"].tobytes()
+        sp = s.connect_springs_dist(100.0, 0, 3, 11.0, 35.0)
+        assert sp.tobytes() == kat3["connect100"].tobytes()
+        # duplicate rule (springs.cpp:70-79) and empty ranges (springs.cpp:116-117)
+        again = s.connect_springs_dist(100.0, 0, 3, 2.0, 1.0, existing=kat3["connect5"])
+        assert [(a, b) for a, b in zip(again["particle_1"], again["particle_2"])] == [(0, 2)]
+        assert len(s.connect_springs_dist(100.0, 2, 2, 1.0, 1.0)) == 0
+        assert len(s.connect_springs_dist(100.0, 3, 1, 1.0, 1.0)) == 0
+        assert len(s.connect_springs_dist(-1.0, 0, 3, 1.0, 1.0)) == 0
+    # SpringTest.Force: gamma = 0 then gamma = 1 after moving particle 0 to (1,1,4)
+    P = kat3["force_in"].copy()
+    sp = kat3["connect100"].copy()
+    with new_sim(gpu, P, sp) as s:
+        for gamma, key in ((0.0, "acc_g0"), (1.0, "acc_g1")):
+            sp["gamma"] = gamma
+            s.update_spring_props(sp)
+            s.zero_accel()
+            s.spring_forces()
+            out = s.download(P.copy())
+            assert acc_err(out[:, 6:9], kat3[key]) <= ACC_TOL
+        d = s.diagnostics(0, 3, want_gpe=True)
+        assert np.allclose(d, kat3["diag_g1"], rtol=1e-13, atol=1e-13)
+
+
+def test_kat_physics_helpers(gpu, kat3):
+    P = kat_particles(); P[:, 6:9] = P[:, :3]
+    with new_sim(gpu, P, G=1.0) as s:
+        d = s.diagnostics(0, 3, want_gpe=True)
+        assert np.allclose(d, kat3["phys_diag"], rtol=1e-14, atol=1e-14)
+        assert np.allclose(d[0:3], (4. / 3., 13. / 6., 11. / 3.), rtol=1e-15)   # PhysicsTest.CoM
+        assert d[9] == 22.75                                                    # PhysicsTest.NonTransKE
+        s.zero_accel()
+        assert np.all(s.download(P.copy())[:, 6:9] == 0.0)                      # PhysicsTest.ZeroAccel
+        s.center_sim(0, 2)
+        assert np.allclose(s.download(P.copy())[:, :3], kat3["center_all"], rtol=0, atol=2e-16)
+    for op, key in (("subtract_com", "sub_com"), ("subtract_cov", "sub_cov")):
+        P = kat_particles()
+        with new_sim(gpu, P) as s:
+            getattr(s, op)(0, 3)
+            assert np.allclose(s.download(P.copy())[:, :6], kat3[key], rtol=0, atol=4e-16)
+    P = kat_particles()
+    with new_sim(gpu, P) as s:
+        s.spin_body(0, 3, (1.0, 12.0, 12.0))
+        assert np.allclose(s.download(P.copy())[:, :6], kat3["spin"], rtol=1e-15, atol=1e-14)
+        s.move_resolved((-1, -1, -1), (1, 1, 1), 0, 3)                          # PhysicsTest.MoveResolved
+        out = s.download(P.copy())
+        assert np.allclose(out[:, :3], kat3["spin"][:, :3] - 1, atol=1e-15)
+
+
+def test_kat_gravity_and_leapfrog(gpu, kat3):
+    P = kat_particles(); P[:, 6:9] = 7.0
+    with new_sim(gpu, P, gravity=1, G=1.0, softening=0.01, dt=0.01) as s:
+        s.gravity_basic()
+        out = s.download(P.copy())
+        assert acc_err(out[:, 6:9], kat3["grav_acc"]) <= ACC_TOL
+        # leapfrog is bit-exact when fed the reference's own accelerations
+        Q = P.copy(); Q[:, 6:9] = kat3["grav_acc"]
+        s.upload(Q)
+        s.leapfrog_part1()
+        assert same_bits(s.download(Q.copy()), kat3["lf1"])
+        s.leapfrog_part2()
+        assert same_bits(s.download(Q.copy()), kat3["lf2"])
+        assert s.params.t == kat3["lf_t"][0]
+    # REB_GRAVITY_NONE is a no-op that leaves a untouched (gravity.c:68-70)
+    with new_sim(gpu, P, gravity=0) as s:
+        s.gravity_basic()
+        assert np.all(s.download(P.copy())[:, 6:9] == 7.0)
+
+
+# ---------------------------------------------------------------------------------------------------
+# random-ellipsoid bodies: golden vectors written by the unmodified reference
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("fixture_name", ["body015", "body010"])
+def test_body_build(gpu, request, fixture_name):
+    g = request.getfixturevalue(fixture_name)
+    d = float(g["d"][0])
+    gpu.srand(12345)
+    p = gpu.rand_ellipsoid(d, A_, B_, C_, 1.0)
+    assert same_bits(p, g["gen"])
+    n = len(p)
+    with new_sim(gpu, p) as s:
+        assert s.mindist() == g["mindist"][0]
+        sp = s.connect_springs_dist(2.3 * d, 0, n, K, GAMMA)
+        assert sp.tobytes() == g["springs"].tobytes()           # bit-exact list: (i, j) order and rs0 bits
+        s.subtract_com(0, n); s.subtract_cov(0, n); s.spin_body(0, n, OMEGA)
+        out = s.download(p.copy())
+        assert np.allclose(out[:, :6], g["start"][:, :6], rtol=0, atol=1e-15)
+
+
+@pytest.mark.parametrize("fixture_name", ["body015", "body010"])
+def test_body_single_evaluations(gpu, oracle, request, fixture_name):
+    """Each reference function on its own, on the reference's own state."""
+    g = request.getfixturevalue(fixture_name)
+    d = float(g["d"][0])
+    p0 = g["step20_basic"].copy()       # a state with non-trivial strains and velocities
+    sp = g["springs"]
+    with new_sim(gpu, p0, sp, gravity=1, G=1.0, softening=d / 100.0, dt=2e-3) as s:
+        # spring_forces: a += f
+        want = p0.copy(); oracle.spring_forces(want, sp)
+        s.spring_forces()
+        got = s.download(p0.copy())
+        assert acc_err(got[:, 6:9] - p0[:, 6:9], want[:, 6:9] - p0[:, 6:9]) <= ACC_TOL
+        # gravity: a = g
+        want = p0.copy(); oracle.gravity_basic(want, G=1.0, softening=d / 100.0)
+        s.gravity_basic()
+        got = s.download(p0.copy())
+        assert acc_err(got[:, 6:9], want[:, 6:9]) <= ACC_TOL
+        # softening = 0 exercises the explicit i == j skip
+        s.set_params(softening=0.0)
+        want = p0.copy(); oracle.gravity_basic(want, G=1.0, softening=0.0)
+        s.gravity_basic()
+        got = s.download(p0.copy())
+        assert np.all(np.isfinite(got[:, 6:9]))
+        assert acc_err(got[:, 6:9], want[:, 6:9]) <= ACC_TOL
+        # N_active < N: only the first particles are sources (gravity.c:64,89)
+        s.set_params(softening=d / 100.0, n_active=len(p0) // 3)
+        want = p0.copy(); oracle.gravity_basic(want, G=1.0, softening=d / 100.0, n_active=len(p0) // 3)
+        s.gravity_basic()
+        got = s.download(p0.copy())
+        assert acc_err(got[:, 6:9], want[:, 6:9]) <= ACC_TOL
+
+
+@pytest.mark.parametrize("fixture_name", ["body015", "body010"])
+def test_body_steps(gpu, request, fixture_name):
+    """reb_step x 1 and x 20 against the reference, both shipped callback shapes."""
+    g = request.getfixturevalue(fixture_name)
+    d = float(g["d"][0])
+    sp = g["springs"]
+    for tag, grav, af, dt in (("none", 0, 2, 1e-2), ("basic", 1, 1, 2e-3)):
+        start = g["start"].copy()
+        with new_sim(gpu, start, sp, gravity=grav, G=1.0, softening=d / 100.0, dt=dt, additional_forces=af) as s:
+            s.step(1)
+            out = s.download(start.copy())
+            want = g["step1_" + tag]
+            assert acc_err(out[:, 6:9], want[:, 6:9]) <= ACC_TOL
+            assert np.allclose(out[:, :6], want[:, :6], rtol=0, atol=1e-14)
+            s.step(19)
+            out = s.download(start.copy())
+            want = g["step20_" + tag]
+            assert acc_err(out[:, 6:9], want[:, 6:9]) <= 1e-10      # 20 steps of accumulated rounding
+            assert np.allclose(out[:, :6], want[:, :6], rtol=0, atol=1e-12)
+            assert abs(s.params.t - 20 * dt) < 1e-12
+        # the unfused sequence of the same five calls gives the same state as the fused loop, bit for bit
+        with new_sim(gpu, start, sp, gravity=grav, G=1.0, softening=d / 100.0, dt=dt, additional_forces=af) as a, \
+                new_sim(gpu, start, sp, gravity=grav, G=1.0, softening=d / 100.0, dt=dt, additional_forces=af) as b:
+            a.step(3)
+            for _ in range(3):
+                b.leapfrog_part1()
+                b.gravity_basic()
+                if af == 2:
+                    b.zero_accel()
+                b.spring_forces()
+                b.leapfrog_part2()
+            assert same_bits(a.download(start.copy()), b.download(start.copy()))
+            assert a.params.t == b.params.t
+
+
+def test_history_energy_and_angular_momentum(gpu, body015):
+    """E = KErot + PEspr (+ PEgrav) and L over 200 steps within 1e-9 relative of the reference's history."""
+    g = body015
+    d = float(g["d"][0])
+    sp = g["springs"]
+    n = len(g["start"])
+    every = int(g["hist_every"][0])
+    for tag, grav, af, dt in (("none", 0, 2, 1e-2), ("basic", 1, 1, 2e-3)):
+        ref_hist = g["hist_" + tag]
+        with new_sim(gpu, g["start"].copy(), sp, gravity=grav, G=1.0, softening=d / 100.0, dt=dt, additional_forces=af) as s:
+            for row in ref_hist:
+                got = s.diagnostics(0, n, want_gpe=bool(grav))
+                e_ref = row[9] + row[10] + row[11]
+                e_got = got[9] + got[10] + got[11]
+                assert abs(e_got - e_ref) <= HIST_TOL * abs(e_ref)
+                assert np.abs(got[6:9] - row[6:9]).max() <= HIST_TOL * np.abs(row[6:9]).max()
+                # damping power; at t = 0 the body rotates rigidly and the strain rates are pure rounding noise
+                assert abs(got[12] - row[12]) <= 1e-8 * abs(row[12]) + 1e-20
+                s.step(every)
+
+
+def test_integrate_exact_finish_and_heartbeat(gpu, body015):
+    """reb_integrate: center_sim heartbeat every step (and at t=0), last step shortened to land on tmax."""
+    g = body015
+    d = float(g["d"][0])
+    start = g["start"].copy()
+    with new_sim(gpu, start, g["springs"], gravity=0, G=1.0, softening=d / 100.0, dt=1e-2, additional_forces=2, heartbeat=1) as s:
+        status = s.integrate(0.1234)
+        out = s.download(start.copy())
+        prm = s.params
+        assert (status, prm.t, prm.dt) == tuple(g["integrate_meta"])
+        assert prm.t == 0.1234
+        assert np.allclose(out[:, :6], g["integrate_state"][:, :6], rtol=0, atol=1e-13)
+        assert acc_err(out[:, 6:9], g["integrate_state"][:, 6:9]) <= 1e-10
+
+
+# ---------------------------------------------------------------------------------------------------
+# callback shapes, edge cases, error behaviour
+# ---------------------------------------------------------------------------------------------------
+def test_accelerations_accumulate_without_zero_accel(gpu, oracle, body015):
+    """with REB_GRAVITY_NONE and no zero_accel (bennu2, wobble_*) `a` accumulates across steps."""
+    g = body015
+    start = g["start"].copy(); start[:, 6:9] = 0.125
+    sp = g["springs"]
+    want = start.copy()
+    sim = make_sim(dt=1e-3, gravity_basic=0, zero_first=0)
+    oracle.step(want, sp, sim, 5)
+    with new_sim(gpu, start, sp, gravity=0, dt=1e-3, additional_forces=1) as s:
+        s.step(5)
+        out = s.download(start.copy())
+    assert acc_err(out[:, 6:9], want[:, 6:9]) <= 1e-11
+    assert np.allclose(out[:, :6], want[:, :6], rtol=0, atol=1e-13)
+
+
+def test_no_springs_no_forces(gpu, oracle, body015):
+    start = body015["start"].copy(); start[:, 6:9] = 0.5
+    for grav, af in ((0, 0), (0, 1), (0, 2), (1, 0), (1, 2)):
+        want = start.copy()
+        sim = make_sim(dt=1e-3, softening=1e-3, gravity_basic=grav, zero_first=(af == 2))
+        oracle.step(want, EMPTY, sim, 2)
+        with new_sim(gpu, start, None, gravity=grav, softening=1e-3, dt=1e-3, additional_forces=af) as s:
+            s.spring_forces()                    # no springs: a no-op
+            s.step(2)
+            out = s.download(start.copy())
+        assert acc_err(out[:, 6:9], want[:, 6:9]) <= ACC_TOL or np.abs(want[:, 6:9]).max() == 0.0
+        assert np.allclose(out[:, :6], want[:, :6], rtol=0, atol=1e-14)
+
+
+def test_point_mass_perturber(gpu, oracle, body015):
+    """phobos_deimos shape: resolved body + one heavy point mass at the end of the array, num_perts = 1; the heartbeat
+    recentres on the resolved body only but shifts everything (physics.cpp:98-109)."""
+    g = body015
+    body = g["start"].copy()
+    n = len(body)
+    pert = np.zeros((1, 11)); pert[0, :3] = (7.0, 0.0, 0.0); pert[0, 4] = 0.4; pert[0, 9] = 1.0
+    p = np.vstack([body, pert])
+    sp = g["springs"]
+    want = p.copy()
+    sim = make_sim(dt=2e-3, softening=1e-3, gravity_basic=1, zero_first=0, center_heartbeat=1, n_perts=1)
+    oracle.step(want, sp, sim, 4, heartbeat=True)
+    with new_sim(gpu, p, sp, gravity=1, softening=1e-3, dt=2e-3, additional_forces=1, heartbeat=1, n_perts=1) as s:
+        s.step(4, heartbeat=True)
+        out = s.download(p.copy())
+    assert acc_err(out[:, 6:9], want[:, 6:9]) <= 1e-11
+    assert np.allclose(out[:, :6], want[:, :6], rtol=0, atol=1e-13)
+
+
+def test_set_gamma_mid_run(gpu, oracle, body015):
+    """set_gamma at t ~ t_damp (every module's heartbeat): host list changes, device copy is refreshed."""
+    g = body015
+    start = g["start"].copy()
+    sp = g["springs"].copy()
+    want = start.copy()
+    sim = make_sim(dt=1e-2, gravity_basic=0, zero_first=1)
+    oracle.step(want, sp, sim, 3)
+    sp2 = sp.copy(); sp2["gamma"] = 1.0
+    oracle.step(want, sp2, sim, 3)
+    with new_sim(gpu, start, sp, gravity=0, dt=1e-2, additional_forces=2) as s:
+        s.step(3)
+        s.update_spring_props(sp2)
+        s.step(3)
+        out = s.download(start.copy())
+    assert acc_err(out[:, 6:9], want[:, 6:9]) <= 1e-11
+    assert np.allclose(out[:, :6], want[:, :6], rtol=0, atol=1e-13)
+
+
+def test_errors(gpu):
+    P = kat_particles()
+    s = gpu.Sim()
+    with pytest.raises(gpu.AssError):            # nothing uploaded yet
+        s.spring_forces()
+    s.upload(P)
+    bad = np.zeros(1, dtype=SPRING_DTYPE); bad["particle_1"] = 1; bad["particle_2"] = 1
+    with pytest.raises(gpu.AssError) as e:       # "Cannot connect a particle to itself." (springs.cpp:57-59)
+        s.set_springs(bad)
+    assert e.value.code == -1 and "itself" in str(e.value)
+    bad["particle_2"] = 9
+    with pytest.raises(gpu.AssError):
+        s.set_springs(bad)
+    with pytest.raises(gpu.AssError):
+        s.download(np.zeros((5, 11)))
+    with pytest.raises(gpu.AssError):
+        s.set_params(gravity=7)
+    with pytest.raises(gpu.AssError):
+        s.update_spring_props(np.zeros(4, dtype=SPRING_DTYPE))
+    s.close()
+
+
+def test_partial_upload_download_and_strides(gpu):
+    """Rows may be `struct reb_particle` (128-byte stride): only the requested doubles move."""
+    n = 100
+    rng = np.random.default_rng(5)
+    wide = rng.normal(size=(n, 16))                  # 128-byte rows; columns 11.. stand for pointers / hash
+    p = wide[:, :]
+    s = gpu.Sim()
+    s.upload(p)
+    back = np.full((n, 16), -7.0)
+    s.download(back, fields=gpu.F_POS | gpu.F_ACC)
+    assert np.array_equal(back[:, 0:3], wide[:, 0:3]) and np.array_equal(back[:, 6:9], wide[:, 6:9])
+    assert np.all(back[:, 3:6] == -7.0) and np.all(back[:, 9:] == -7.0)
+    newv = rng.normal(size=(n, 16))
+    s.upload(newv, fields=gpu.F_VEL)
+    full = np.zeros((n, 16))
+    s.download(full)
+    assert np.array_equal(full[:, 0:3], wide[:, 0:3]) and np.array_equal(full[:, 3:6], newv[:, 3:6])
+    assert np.array_equal(full[:, 9], wide[:, 9]) and np.all(full[:, 10:] == 0.0)
+    s.close()
+
+
+def test_deterministic(gpu, body010):
+    g = body010
+    d = float(g["d"][0])
+    outs = []
+    for _ in range(2):
+        with new_sim(gpu, g["start"].copy(), g["springs"], gravity=1, softening=d / 100.0, dt=2e-3, additional_forces=1) as s:
+            s.step(10)
+            outs.append(s.download(g["start"].copy()))
+    assert same_bits(outs[0], outs[1])
+
+
+# ---------------------------------------------------------------------------------------------------
+# full-size checks (BASELINE C2 / C3 sizes): oracle on a slab + size-independent properties
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("d,expect_n", [(0.0474, 9327), (0.0215, None)])
+def test_full_size(gpu, oracle, d, expect_n):
+    gpu.srand(12345)
+    p = gpu.rand_ellipsoid(d, A_, B_, C_, 1.0)
+    n = len(p)
+    if expect_n:
+        assert n == expect_n
+    else:
+        assert 90_000 < n < 110_000
+    soft = d / 100.0
+    with new_sim(gpu, p, gravity=1, G=1.0, softening=soft, dt=1e-3, additional_forces=1) as s:
+        # spring list: bit-exact against the oracle's cell-list restatement (itself pinned to the reference at C2)
+        sp = s.connect_springs_dist(2.3 * d, 0, n, K, GAMMA)
+        want_sp = oracle.connect_springs_dist(p, 2.3 * d, 0, n, K, GAMMA)
+        assert sp.tobytes() == want_sp.tobytes()
+        assert np.all(sp["particle_1"] < sp["particle_2"])
+        key = sp["particle_1"].astype(np.int64) * n + sp["particle_2"]
+        assert np.all(np.diff(key) > 0)                              # strictly lexicographic, no duplicates
+        assert s.mindist() == oracle.mindist(p)
+        s.set_springs(sp)
+        s.subtract_com(0, n); s.subtract_cov(0, n); s.spin_body(0, n, OMEGA)
+        s.step(2)                                                    # get off the rest state
+        state = s.download(p.copy())
+        # gravity on a slab of targets against the oracle (full sum over all N sources)
+        lo, hi = n // 2 - 128, n // 2 + 128
+        want = state.copy(); oracle.gravity_basic(want, G=1.0, softening=soft, i_lo=lo, i_hi=hi)
+        s.gravity_basic()
+        got = s.download(state.copy())
+        assert acc_err(got[lo:hi, 6:9], want[lo:hi, 6:9]) <= ACC_TOL
+        # Newton's third law: sum m a = 0 for gravity and for springs (size-independent)
+        scale = np.abs(got[:, 9:10] * got[:, 6:9]).sum(axis=0)
+        assert np.all(np.abs((got[:, 9:10] * got[:, 6:9]).sum(axis=0)) <= 1e-12 * scale)
+        # springs: full comparison (the oracle is O(NS))
+        want = state.copy(); want[:, 6:9] = 0.0; oracle.spring_forces(want, sp)
+        s.zero_accel(); s.spring_forces()
+        got = s.download(state.copy())
+        assert acc_err(got[:, 6:9], want[:, 6:9]) <= ACC_TOL
+        net = (got[:, 9:10] * got[:, 6:9]).sum(axis=0)
+        assert np.all(np.abs(net) <= 1e-12 * np.abs(got[:, 9:10] * got[:, 6:9]).sum(axis=0))
+        # angular momentum is conserved by the step (internal forces are central): 20 steps, 1e-11 relative
+        L0 = s.diagnostics(0, n)[6:9]
+        s.step(20)
+        L1 = s.diagnostics(0, n)[6:9]
+        assert np.abs(L1 - L0).max() <= 1e-11 * np.abs(L0).max()
