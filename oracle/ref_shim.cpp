@@ -98,6 +98,8 @@ void ref_config(void* h, int gravity_basic, double G, double softening, double d
 	g_center_hb = center_heartbeat;
 	num_perts = n_perts;
 }
+// r->N_active: number of gravity sources (src/gravity.c:64,89); -1 = all.  Used to time a bounded sample of the O(N^2) sum.
+void ref_set_n_active(void* h, int n_active) { ((reb_simulation*) h)->N_active = n_active; }
 double ref_time(void* h) { return ((reb_simulation*) h)->t; }
 void ref_set_time(void* h, double t) { ((reb_simulation*) h)->t = t; }
 double ref_dt(void* h) { return ((reb_simulation*) h)->dt; }
