@@ -193,6 +193,10 @@ class Sim:
         return _chk(lib().ass_integrate(self._h, C.c_double(tmax)))
 
     # -- helpers --
+    def set_sum_order(self, sequential=True):
+        """CoM / CoV sums in the reference's particle order (bit-exact, default) or as a parallel tree."""
+        _chk(lib().ass_set_sum_order(self._h, C.c_int(int(sequential))))
+
     def center_sim(self, lo, hi):
         _chk(lib().ass_center_sim(self._h, C.c_int(lo), C.c_int(hi)))
 

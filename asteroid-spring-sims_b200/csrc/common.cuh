@@ -83,6 +83,7 @@ struct ass_sim {
 	vec4d *posm_alt = nullptr, *vel_alt = nullptr;  // ping-pong targets of the fused spring+kick+drift kernel
 	bool have_state = false;
 	bool predrifted = false;  // positions already carry the next step's first half-drift (fused loop only)
+	bool sum_sequential = true;  // CoM / CoV sums in the reference's particle order (bit-exact) or as a parallel tree
 
 	// springs, node-sorted
 	HalfEdge* he = nullptr;

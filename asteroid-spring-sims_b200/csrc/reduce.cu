@@ -78,6 +78,42 @@ __global__ void __launch_bounds__(RB) k_moment(const vec4d* __restrict__ posm, c
 	block_reduce_store<4>(v, part);
 }
 
+// The same moments in the REFERENCE's order: m_tot = sum_mass() then x_times_m += m * x for i ascending, each product
+// and each add rounded separately (operator*(double, Vector) and operator+= are out-of-line calls in matrix_math.cpp,
+// so gcc cannot fuse them), then x_times_m / m_tot.  A floating-point sum in a fixed sequential order cannot be
+// parallelised without changing its bits, so one CTA stages 1024 products at a time into shared memory and four
+// threads run the four dependent chains.  ~8 cycles per particle: fine at set-up (subtract_com, spin_body before
+// connect_springs_dist, where one ulp of position would change rs0 bits); per-step callers can ask for the tree.
+constexpr int SEQ_CHUNK = 1024;
+__global__ void __launch_bounds__(256) k_moment_seq(const vec4d* __restrict__ posm, const vec4d* __restrict__ vel, int lo, int hi, int velocity,
+		double* __restrict__ out) {
+	__shared__ double buf[4][SEQ_CHUNK];
+	double acc = 0.0;
+	for (int base = lo; base < hi; base += SEQ_CHUNK) {
+		const int cnt = min(SEQ_CHUNK, hi - base);
+		for (int k = threadIdx.x; k < cnt; k += blockDim.x) {
+			const vec4d p = posm[base + k];
+			double x = p.x, y = p.y, z = p.z;
+			if (velocity) { const vec4d w = vel[base + k]; x = w.x; y = w.y; z = w.z; }
+			buf[0][k] = __dmul_rn(x, p.w);
+			buf[1][k] = __dmul_rn(y, p.w);
+			buf[2][k] = __dmul_rn(z, p.w);
+			buf[3][k] = p.w;
+		}
+		__syncthreads();
+		if (threadIdx.x < 4) {
+			const double* b = buf[threadIdx.x];
+			for (int k = 0; k < cnt; k++) acc = __dadd_rn(acc, b[k]);
+		}
+		__syncthreads();
+	}
+	__shared__ double tot[4];
+	if (threadIdx.x < 4) tot[threadIdx.x] = acc;
+	__syncthreads();
+	if (threadIdx.x < 3) out[threadIdx.x] = __ddiv_rn(tot[threadIdx.x], tot[3]);
+	if (threadIdx.x == 3) out[3] = tot[3];
+}
+
 // out[0..2] = sums / mass ; out[3] = mass
 __global__ void k_fold_com(const double* __restrict__ part, int nblk, double* __restrict__ out) {
 	__shared__ double sm[4];
@@ -246,6 +282,13 @@ int reduce_grid(int count) {
 
 // d_out[0..2] = CoM (or CoV), d_out[3] = mass; stays on the device
 int ass_launch_com(ass_sim* s, int lo, int hi, bool velocity, double* d_out) {
+	if (s->sum_sequential) {
+		ass_tic(s, ASS_K_REDUCE);
+		k_moment_seq<<<1, 256, 0, s->stream>>>(s->posm, s->vel, lo, hi, velocity ? 1 : 0, d_out);
+		LAUNCH_CHECK();
+		ass_toc(s, ASS_K_REDUCE);
+		return ASS_OK;
+	}
 	const int grid = reduce_grid(hi - lo);
 	int rc = ass_buf_reserve(s->red_partial, sizeof(double) * MAXV * (size_t) std::max(grid, ass_sm_count() * 4));
 	if (rc) return rc;
@@ -280,6 +323,12 @@ int ass_launch_shift(ass_sim* s, int lo, int hi, const double* d_shift3, bool ve
 static int fetch(ass_sim* s, int count) {
 	CU_TRY(cudaMemcpyAsync(s->h_red, s->d_red, sizeof(double) * count, cudaMemcpyDeviceToHost, s->stream));
 	CU_TRY(cudaStreamSynchronize(s->stream));
+	return ASS_OK;
+}
+
+extern "C" int ass_set_sum_order(ass_sim* s, int sequential) {
+	REQUIRE(s, ASS_EINVAL, "null sim");
+	s->sum_sequential = sequential != 0;
 	return ASS_OK;
 }
 

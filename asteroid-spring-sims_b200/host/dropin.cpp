@@ -1,0 +1,516 @@
+// dropin.cpp -- the reference's own symbols for the per-step path, re-implemented over the C-ABI of include/ass_b200.h.
+//
+// Compiled AGAINST the reference's headers (-I <reference>/src -I <reference>/src_spring), never with a copy of them:
+// struct reb_simulation / reb_particle / spring / Vector are the reference's.  Linked in front of the reference's
+// objects (whose same-named definitions are weakened) this makes an unmodified problem module run
+// its step loop on the B200.  Residency rules are described in ass_dropin.h.
+//
+// Each function cites what it replaces.  Error convention: REBOUND-side failures print and
+// exit(EXIT_FAILURE) through the reference's reb_exit(); spring-side failures `throw "literal"` exactly like
+// src_spring/springs.cpp so EXPECT_ANY_THROW-style callers keep working; nothing throws across the C-ABI.
+#ifdef __GNUC__
+#define restrict __restrict__
+#endif
+
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <iostream>
+#include <mutex>
+#include <unordered_map>
+#include <vector>
+
+extern "C" {
+#include "rebound.h"
+// exported by librebound but not declared in its public header
+int reb_check_exit(struct reb_simulation* const r, const double tmax, double* last_full_dt);  // src/rebound.c:509
+void reb_exit(const char* const msg);                                                           // src/rebound.c:147
+}
+#include "matrix_math.h"
+#include "stress.h"
+#include "springs.h"
+#include "physics.h"
+#include "shapes.h"
+
+#include "ass_b200.h"
+#include "ass_dropin.h"
+
+using std::vector;
+
+// module-owned globals (e.g. modules/asteroid_spin/problem.cpp:37-47)
+extern vector<spring> springs;
+extern int num_springs;
+extern int num_perts;
+extern vector<stress_tensor> stresses;
+
+static_assert(sizeof(spring) == sizeof(ass_spring), "struct spring must be 32 bytes {k, rs0, gamma, particle_1, particle_2}");
+
+namespace {
+
+struct Dropin {
+	ass_sim* sim = nullptr;
+	bool dev_fresh = false;    // device copy reflects the host arrays (or is newer)
+	bool host_fresh = true;    // host arrays reflect the device copy (or are newer)
+	unsigned pending = 0;      // fields written on the device inside a deferred sequence, not yet downloaded
+	int defer = 0;             // >0: inside one of our own multi-kernel sequences
+	bool in_run = false;       // inside reb_integrate
+	// spring cache validity
+	bool topo_stale = true, prop_stale = true;
+	size_t sp_size = 0;
+	const spring* sp_ptr = nullptr;
+	uint64_t sp_probe = 0;
+};
+
+std::mutex g_mu;
+std::unordered_map<reb_simulation*, Dropin> g_map;
+int g_resident = -1;
+
+bool resident() {
+	if (g_resident < 0) {
+		const char* e = getenv("ASS_RESIDENT");
+		g_resident = (e && *e && strcmp(e, "0") != 0) ? 1 : 0;
+	}
+	return g_resident == 1;
+}
+
+[[noreturn]] void fatal(const char* where) {
+	static char buf[1400];
+	snprintf(buf, sizeof(buf), "%s: %s", where, ass_last_error());
+	reb_exit(buf);  // prints "Fatal error! Exiting now." and exit(EXIT_FAILURE), src/rebound.c:147-153
+	abort();
+}
+#define OK(call)                      \
+	do {                              \
+		if ((call) < 0) fatal(#call); \
+	} while (0)
+
+Dropin& get(reb_simulation* r) {
+	std::lock_guard<std::mutex> lk(g_mu);
+	Dropin& d = g_map[r];
+	if (!d.sim) {
+		if (ass_create(&d.sim) < 0) fatal("ass_create");
+	}
+	return d;
+}
+
+void push_params(reb_simulation* r, Dropin& d) {
+	ass_params p;
+	memset(&p, 0, sizeof(p));
+	p.t = r->t; p.dt = r->dt; p.dt_last_done = r->dt_last_done;
+	p.G = r->G; p.softening = r->softening;
+	p.gravity = (r->gravity == reb_simulation::REB_GRAVITY_BASIC) ? 1 : 0;
+	p.n_active = r->N_active;
+	p.n_perts = num_perts;
+	p.additional_forces = 0;  // callbacks are the module's and run on the host side of this layer
+	p.heartbeat = 0;
+	p.exact_finish_time = r->exact_finish_time;
+	p.status = r->status;
+	OK(ass_set_params(d.sim, &p));
+}
+
+void ensure_dev(reb_simulation* r, Dropin& d) {
+	if (d.dev_fresh && ass_num_particles(d.sim) == r->N) return;
+	OK(ass_upload_particles(d.sim, r->particles, sizeof(reb_particle), r->N, ASS_F_ALL));
+	d.dev_fresh = true;
+	d.host_fresh = true;
+	d.pending = 0;
+}
+
+void flush_host(reb_simulation* r, Dropin& d) {
+	if (d.pending && r->N > 0) OK(ass_download_particles(d.sim, r->particles, sizeof(reb_particle), r->N, d.pending));
+	d.pending = 0;
+	d.host_fresh = true;
+}
+
+// a device operation wrote `fields`
+void wrote(reb_simulation* r, Dropin& d, unsigned fields) {
+	d.pending |= fields;
+	d.host_fresh = false;
+	if (resident() && d.in_run) return;  // the device copy is the truth until someone asks for the host arrays
+	if (d.defer) return;                 // end of the enclosing sequence flushes
+	flush_host(r, d);
+	d.dev_fresh = false;                 // coherent mode: anyone may edit the host arrays before the next call
+}
+
+struct Sequence {  // several kernels of ours back to back: transfer once at the end
+	reb_simulation* r;
+	Dropin& d;
+	Sequence(reb_simulation* r_, Dropin& d_) : r(r_), d(d_) { d.defer++; }
+	~Sequence() {
+		if (--d.defer == 0 && !(resident() && d.in_run)) {
+			flush_host(r, d);
+			d.dev_fresh = false;
+		}
+	}
+};
+
+uint64_t probe_springs() {
+	// cheap fingerprint of the module's list: catches add/del/set_gamma done by code we did not intercept
+	const size_t n = springs.size();
+	uint64_t h = 1469598103934665603ULL ^ n;
+	if (!n) return h;
+	const size_t step = n > 4096 ? n / 1024 : 1;
+	auto mix = [&](const spring& s) {
+		uint64_t w[4];
+		memcpy(w, &s, sizeof(w));
+		for (int q = 0; q < 4; q++) { h ^= w[q]; h *= 1099511628211ULL; }
+	};
+	for (size_t i = 0; i < n; i += step) mix(springs[i]);
+	mix(springs[n - 1]);
+	return h;
+}
+
+void ensure_springs(Dropin& d) {
+	if (num_springs != (int) springs.size()) throw "Spring count and size of spring array don't match.\n";  // springs.cpp:38-40,99-101
+	const uint64_t pr = probe_springs();
+	if (springs.size() != d.sp_size || springs.data() != d.sp_ptr) d.topo_stale = true;
+	else if (pr != d.sp_probe) d.topo_stale = true;  // cannot tell a property edit from a re-wiring: rebuild
+	if (d.topo_stale) {
+		OK(ass_set_springs(d.sim, (const ass_spring*) springs.data(), (int) springs.size()));
+	} else if (d.prop_stale) {
+		OK(ass_update_spring_props(d.sim, (const ass_spring*) springs.data(), (int) springs.size()));
+	}
+	d.topo_stale = d.prop_stale = false;
+	d.sp_size = springs.size();
+	d.sp_ptr = springs.data();
+	d.sp_probe = pr;
+}
+
+void props_changed() {
+	std::lock_guard<std::mutex> lk(g_mu);
+	for (auto& kv : g_map) kv.second.prop_stale = true;
+}
+void topo_changed() {
+	std::lock_guard<std::mutex> lk(g_mu);
+	for (auto& kv : g_map) kv.second.topo_stale = true;
+}
+
+void require_supported(reb_simulation* r) {
+	if (r->integrator != reb_simulation::REB_INTEGRATOR_LEAPFROG)
+		reb_exit("asteroid-spring-sims_b200: only REB_INTEGRATOR_LEAPFROG runs on the device (every reference module uses it).");
+	if (r->gravity != reb_simulation::REB_GRAVITY_NONE && r->gravity != reb_simulation::REB_GRAVITY_BASIC)
+		reb_exit("asteroid-spring-sims_b200: only REB_GRAVITY_NONE / REB_GRAVITY_BASIC run on the device.");
+	if (r->boundary != reb_simulation::REB_BOUNDARY_NONE || r->collision != reb_simulation::REB_COLLISION_NONE || r->N_var != 0 ||
+	    r->nghostx || r->nghosty || r->nghostz || r->testparticle_type)
+		reb_exit("asteroid-spring-sims_b200: boundaries, collisions, ghost boxes, variational and test particles are not on the accelerated path.");
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------
+// control surface
+// ---------------------------------------------------------------------------------------------------
+extern "C" void ass_dropin_set_resident(int on) { g_resident = on ? 1 : 0; }
+extern "C" int ass_dropin_is_resident(void) { return resident() ? 1 : 0; }
+extern "C" int ass_dropin_sync_host(struct reb_simulation* r) {
+	Dropin& d = get(r);
+	if (!d.host_fresh) flush_host(r, d);
+	return 0;
+}
+extern "C" void ass_dropin_host_modified(struct reb_simulation* r) {
+	Dropin& d = get(r);
+	if (!d.host_fresh) flush_host(r, d);  // keep what the device computed for the fields the caller did not touch
+	d.dev_fresh = false;
+}
+extern "C" void ass_dropin_springs_modified(void) { topo_changed(); }
+extern "C" void ass_dropin_release(struct reb_simulation* r) {
+	std::lock_guard<std::mutex> lk(g_mu);
+	auto it = g_map.find(r);
+	if (it == g_map.end()) return;
+	ass_destroy(it->second.sim);
+	g_map.erase(it);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// C symbols of librebound
+// ---------------------------------------------------------------------------------------------------
+// src/integrator_leapfrog.c:39-51
+extern "C" void reb_integrator_leapfrog_part1(struct reb_simulation* r) {
+	r->gravity_ignore_terms = 0;
+	Dropin& d = get(r);
+	ensure_dev(r, d);
+	push_params(r, d);
+	OK(ass_leapfrog_part1(d.sim));
+	r->t += r->dt / 2.;
+	wrote(r, d, ASS_F_POS);
+}
+
+// src/integrator_leapfrog.c:52-67
+extern "C" void reb_integrator_leapfrog_part2(struct reb_simulation* r) {
+	Dropin& d = get(r);
+	ensure_dev(r, d);
+	push_params(r, d);
+	OK(ass_leapfrog_part2(d.sim));
+	r->t += r->dt / 2.;
+	r->dt_last_done = r->dt;
+	wrote(r, d, ASS_F_POS | ASS_F_VEL);
+}
+
+// src/gravity.c:57-125, branches NONE and BASIC
+extern "C" void reb_calculate_acceleration(struct reb_simulation* r) {
+	if (r->gravity == reb_simulation::REB_GRAVITY_NONE) return;  // "Do nothing."
+	require_supported(r);
+	Dropin& d = get(r);
+	ensure_dev(r, d);
+	push_params(r, d);
+	OK(ass_gravity_basic(d.sim));
+	wrote(r, d, ASS_F_ACC);
+}
+
+// src/rebound.c:69-144 for the configuration every spring module runs (leapfrog, no tree, no boundary, no collisions)
+extern "C" void reb_step(struct reb_simulation* const r) {
+	require_supported(r);
+	Dropin& d = get(r);
+	{
+		Sequence seq(r, d);
+		reb_integrator_leapfrog_part1(r);   // :72
+		reb_calculate_acceleration(r);      // :109
+	}
+	if (r->additional_forces) r->additional_forces(r);  // :114 -- the module's callback; it calls back into this layer
+	reb_integrator_leapfrog_part2(r);       // :119
+	if (r->post_timestep_modifications) {   // :120-125 (NULL in every shipped module)
+		reb_integrator_synchronize(r);
+		r->post_timestep_modifications(r);
+	}
+	// reb_boundary_check / reb_collision_search are no-ops for BOUNDARY_NONE / COLLISION_NONE (:131-143)
+}
+
+// src/rebound.c:621-704, REB_VISUALIZATION_NONE branch
+extern "C" enum REB_STATUS reb_integrate(struct reb_simulation* const r, double tmax) {
+	if (r->visualization != reb_simulation::REB_VISUALIZATION_NONE) {
+		reb_error(r, "asteroid-spring-sims_b200 was built headless (the reference says the same when compiled without OPENGL).");
+		return REB_EXIT_ERROR;
+	}
+	require_supported(r);
+	Dropin& d = get(r);
+	double last_full_dt = r->dt;      // :629
+	r->dt_last_done = 0.;             // :630
+	r->status = REB_RUNNING;          // :632
+	d.in_run = true;
+	d.dev_fresh = false;              // whatever the module did during set-up is on the host
+	// Set-up helpers (subtract_com, spin_body, ...) sum in the reference's order so positions, hence rs0, keep their
+	// bits; the per-step heartbeat (center_sim every step in every module) uses the parallel tree unless told not to.
+	const char* exact = getenv("ASS_EXACT_SUMS");
+	ass_set_sum_order(d.sim, (exact && *exact && strcmp(exact, "0") != 0) ? 1 : 0);
+	const bool host_checks = r->exit_max_distance != 0 || r->exit_min_distance != 0;
+	auto heartbeat = [&]() {
+		if (host_checks) ass_dropin_sync_host(r);  // reb_run_heartbeat reads r->particles for the exit tests (:576-607)
+		reb_run_heartbeat(r);
+	};
+	heartbeat();                      // :633
+	while (reb_check_exit(r, tmax, &last_full_dt) < 0) {  // :634
+		reb_step(r);
+		heartbeat();
+	}
+	reb_integrator_synchronize(r);    // :649
+	if (r->exact_finish_time == 1) r->dt = last_full_dt;  // :653-655
+	d.in_run = false;
+	ass_set_sum_order(d.sim, 1);
+	ass_dropin_sync_host(r);
+	d.dev_fresh = false;
+	return r->status;
+}
+
+// src/output.c:47-61.  Modules gate every piece of host-side output on this test, which makes it the natural place
+// to bring the host arrays up to date in resident mode.
+extern "C" int reb_output_check(struct reb_simulation* r, double interval) {
+	const double shift = r->t;
+	int fire = 0;
+	if (floor(shift / interval) != floor((shift - r->dt) / interval)) fire = 1;
+	if (r->t == 0) fire = 1;
+	if (fire) ass_dropin_sync_host(r);
+	return fire;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// C++ symbols of src_spring
+// ---------------------------------------------------------------------------------------------------
+// src_spring/springs.cpp:288-346
+void spring_forces(reb_simulation* const r) {
+	Dropin& d = get(r);
+	ensure_dev(r, d);
+	ensure_springs(d);
+	OK(ass_spring_forces(d.sim));
+	wrote(r, d, ASS_F_ACC);
+}
+
+// src_spring/physics.cpp:557-564
+void zero_accel(reb_simulation* const r) {
+	Dropin& d = get(r);
+	ensure_dev(r, d);
+	OK(ass_zero_accel(d.sim));
+	wrote(r, d, ASS_F_ACC);
+}
+
+// src_spring/springs.cpp:96-106
+void add_spring_helper(spring spr) {
+	if (num_springs != (int) springs.size()) throw "Spring count and size of spring array don't match.\n";
+	springs.push_back(spr);
+	num_springs++;
+	topo_changed();
+}
+
+// src_spring/springs.cpp:35-45
+void del_spring(int spring_index) {
+	if (num_springs != (int) springs.size()) throw "Spring count and size of spring array don't match.\n";
+	springs.erase(springs.begin() + spring_index);
+	num_springs--;
+	topo_changed();
+}
+
+// src_spring/springs.cpp:110-143
+void connect_springs_dist(reb_simulation* const r, double max_dist, int i_low, int i_high, spring spr) {
+	if (i_high <= i_low) return;  // :116-117
+	if (num_springs != (int) springs.size()) throw "Spring count and size of spring array don't match.\n";
+	Dropin& d = get(r);
+	ensure_dev(r, d);
+	ass_spring* fresh = nullptr;
+	int n_new = 0;
+	OK(ass_connect_springs_dist(d.sim, max_dist, i_low, i_high, spr.k, spr.gamma, (const ass_spring*) springs.data(), (int) springs.size(), &fresh, &n_new));
+	springs.reserve(springs.size() + (size_t) n_new);
+	for (int q = 0; q < n_new; q++) {
+		spring s = spr;  // keeps any field a future `struct spring` may add
+		s.k = fresh[q].k; s.gamma = fresh[q].gamma; s.rs0 = fresh[q].rs0;
+		s.particle_1 = fresh[q].particle_1; s.particle_2 = fresh[q].particle_2;
+		springs.push_back(s);
+	}
+	num_springs = (int) springs.size();
+	ass_free(fresh);
+	topo_changed();
+}
+
+// src_spring/springs.cpp:146-154
+void set_gamma(double new_gamma) {
+	for (int i = 0; i < num_springs; i++) springs[i].gamma = new_gamma;
+	std::cout.precision(2);
+	std::cout << "Spring damping coefficients set to " << new_gamma << std::endl;
+	props_changed();
+}
+
+// src_spring/springs.cpp:157-164
+void divide_gamma(double gamma_fac) {
+	for (int i = 0; i < num_springs; i++) springs[i].gamma /= gamma_fac;
+	std::cout.precision(2);
+	std::cout << "All gammas divided by " << gamma_fac << std::endl;
+	props_changed();
+}
+
+// src_spring/springs.cpp:167-196
+void adjust_spring_props(reb_simulation* const r, double new_k, double new_gamma, double r_min, double r_max) {
+	const int i_low = 0, i_high = r->N - num_perts;
+	Vector CoM = compute_com(r, i_low, i_high);
+	ass_dropin_sync_host(r);  // spr_mid reads r->particles
+	int NC = 0;
+	for (int i = 0; i < num_springs; i++) {
+		Vector x_mid = spr_mid(r, springs[i], CoM);
+		const double r_mid = x_mid.len();
+		if ((r_mid >= r_min) && (r_mid <= r_max)) {
+			springs[i].k = new_k;
+			springs[i].gamma = new_gamma;
+			NC++;
+		}
+	}
+	std::cout.precision(3);
+	std::cout << "adjust_spring_props: \n\t Number of springs changed: " << NC << "\n\t Fraction of springs changed: "
+	          << (double) NC / (double) num_springs << std::endl;
+	props_changed();
+}
+
+// src_spring/springs.cpp:199-213
+void kill_springs(reb_simulation* const r) {
+	const int i_low = 0, i_high = r->N - num_perts;
+	for (int i = i_low; i < i_high; i++) {
+		if (stresses[i].failing) {
+			const int s = stresses[i].max_force_spring;
+			springs[s].k = 0.0;
+			springs[s].gamma = 0.0;
+		}
+	}
+	props_changed();
+}
+
+// src_spring/physics.cpp:41-57 -- parallel fixed-order sum; equals the reference's sequential sum to rounding
+Vector compute_com(reb_simulation* const r, int i_low, int i_high) {
+	Dropin& d = get(r);
+	ensure_dev(r, d);
+	double c[3];
+	OK(ass_compute_com(d.sim, i_low, i_high, c));
+	return Vector({ c[0], c[1], c[2] });
+}
+
+// src_spring/physics.cpp:60-74
+Vector compute_cov(reb_simulation* const r, int i_low, int i_high) {
+	Dropin& d = get(r);
+	ensure_dev(r, d);
+	double c[3];
+	OK(ass_compute_cov(d.sim, i_low, i_high, c));
+	return Vector({ c[0], c[1], c[2] });
+}
+
+// src_spring/physics.cpp:98-109
+void center_sim(reb_simulation* const r, int i_low, int i_high) {
+	Dropin& d = get(r);
+	ensure_dev(r, d);
+	OK(ass_center_sim(d.sim, i_low, i_high));
+	wrote(r, d, ASS_F_POS);
+}
+
+// src_spring/physics.cpp:77-84
+void subtract_com(reb_simulation* const r, int i_low, int i_high) {
+	Dropin& d = get(r);
+	ensure_dev(r, d);
+	OK(ass_subtract_com(d.sim, i_low, i_high));
+	wrote(r, d, ASS_F_POS);
+}
+
+// src_spring/physics.cpp:88-94
+void subtract_cov(reb_simulation* const r, int i_low, int i_high) {
+	Dropin& d = get(r);
+	ensure_dev(r, d);
+	OK(ass_subtract_cov(d.sim, i_low, i_high));
+	wrote(r, d, ASS_F_VEL);
+}
+
+// src_spring/physics.cpp:387-402
+void move_resolved(reb_simulation* const r, Vector dx, Vector dv, int i_low, int i_high) {
+	Dropin& d = get(r);
+	ensure_dev(r, d);
+	const double a[3] = { dx.getX(), dx.getY(), dx.getZ() }, b[3] = { dv.getX(), dv.getY(), dv.getZ() };
+	OK(ass_move_resolved(d.sim, a, b, i_low, i_high));
+	wrote(r, d, ASS_F_POS | ASS_F_VEL);
+}
+
+// src_spring/shapes.cpp:814-833
+double mindist(reb_simulation* const r, int i_low, int i_high) {
+	Dropin& d = get(r);
+	ensure_dev(r, d);
+	double out = 0.0;
+	OK(ass_mindist(d.sim, i_low, i_high, &out));
+	return out;
+}
+
+// src_spring/shapes.cpp:210-278
+void rand_ellipsoid(reb_simulation* const r, double min_dist, double x, double y, double z, double total_mass) {
+	const int n_part = 40 * pow(2.0 * x / min_dist, 3.0);
+	std::cout << "rand_ellipsoid: Trying to create " << n_part << " particles." << std::endl;
+	ass_dropin_sync_host(r);
+	double* rows = nullptr;
+	int cap = 0;
+	const int n_new = ass_rand_ellipsoid(&rows, &cap, 0, min_dist, x, y, z, total_mass);
+	if (n_new < 0) fatal("ass_rand_ellipsoid");
+	const int i_0 = r->N;
+	for (int i = 0; i < n_new; i++) {
+		reb_particle pt;
+		memset(&pt, 0, sizeof(pt));
+		const double* q = rows + (size_t) i * 11;
+		pt.x = q[0]; pt.y = q[1]; pt.z = q[2];
+		pt.m = q[9]; pt.r = q[10];
+		reb_add(r, pt);
+	}
+	ass_free(rows);
+	ass_dropin_host_modified(r);
+	const double min_d = mindist(r, i_0, r->N);
+	std::cout << "rand_ellipsoid: Created " << r->N - i_0 << " particles separated by minimum distance " << min_d << std::endl;
+}

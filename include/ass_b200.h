@@ -121,6 +121,12 @@ int ass_step(ass_sim* sim, int nsteps, int with_heartbeat);
 int ass_integrate(ass_sim* sim, double tmax);
 
 /* ---- per-step heartbeat helpers (src_spring/physics.cpp) ---- */
+/* How the mass-weighted sums behind compute_com / compute_cov (and everything built on them) are accumulated:
+ * sequential != 0 (default): in the reference's particle order, one rounding per operation -> bit-identical CoM / CoV,
+ *                            hence bit-identical subtract_com / subtract_cov / spin_body / center_sim results.  One CTA,
+ *                            ~8 cycles per particle: meant for set-up, where an ulp of position changes rs0 bits.
+ * sequential == 0:           fixed-order parallel tree; equal to rounding; for per-step heartbeats at large N. */
+int ass_set_sum_order(ass_sim* sim, int sequential);
 int ass_center_sim(ass_sim* sim, int i_low, int i_high);      /* physics.cpp:98-109 */
 int ass_subtract_com(ass_sim* sim, int i_low, int i_high);    /* physics.cpp:77-84  */
 int ass_subtract_cov(ass_sim* sim, int i_low, int i_high);    /* physics.cpp:88-94  */

@@ -1,0 +1,139 @@
+// tests/dropin/problem.cpp -- a problem module written against the REFERENCE's API only (rebound.h, springs.h,
+// shapes.h, physics.h, libconfig), in the shape of modules/asteroid_spin/problem.cpp and
+// modules/wobble_bennu2/problem.cpp: read problem.cfg, build a random ellipsoid, connect springs, spin it up, run
+// reb_integrate with an additional_forces callback and a per-step heartbeat.
+//
+// It exists because no shipped module can run as shipped (missing particle files, cfg keys that do not
+// match the lookups).  The same source is linked twice by tests/dropin/Makefile:
+//   synth_ref    against the unmodified reference objects                      -> the CPU answer
+//   synth_b200   against the same objects with the hot-path symbols replaced by asteroid-spring-sims_b200/host/dropin.cpp
+// and tests/test_dropin.py compares what the two write.  This file contains no ASS_/ass_ symbol.
+#ifdef __GNUC__
+#define restrict __restrict__
+#endif
+
+#include <cmath>
+#include <cstdlib>
+#include <fstream>
+#include <iomanip>
+#include <iostream>
+#include <string>
+#include <vector>
+extern "C" {
+#include "rebound.h"
+}
+#include "libconfig.h++"
+#include "matrix_math.h"
+#include "stress.h"
+#include "springs.h"
+#include "physics.h"
+#include "shapes.h"
+#include "input_spring.h"
+
+using namespace libconfig;
+using std::string;
+using std::vector;
+
+// Globals every module defines (modules/asteroid_spin/problem.cpp:37-47)
+int num_springs = 0;
+vector<spring> springs;
+int num_perts = 0;
+double def_gamma, t_damp, print_interval;
+string fileroot;
+double mass_scale, time_scale, length_scale, temp_scale, omega_scale, vel_scale, p_scale, L_scale, a_scale, F_scale,
+		E_scale, dEdt_scale, P_scale;
+int use_gravity = 0;
+
+void additional_forces(reb_simulation *n_body_sim);
+void heartbeat(reb_simulation *const n_body_sim);
+
+int main(int argc, char *argv[]) {
+	Config cfg;
+	cfg.readFile("problem.cfg");
+	read_scales(&cfg);
+
+	double t_max, dt, max_spring_dist, gamma_fac, k, omega_in[3], min_dist, mass_ball, r_ball, ratio1, ratio2;
+	int seed = 1;
+	if (!(cfg.lookupValue("fileroot", fileroot) && cfg.lookupValue("dt", dt) && cfg.lookupValue("t_max", t_max)
+			&& cfg.lookupValue("print_interval", print_interval) && cfg.lookupValue("max_spring_dist", max_spring_dist)
+			&& cfg.lookupValue("k", k) && cfg.lookupValue("gamma", def_gamma) && cfg.lookupValue("damp_fac", gamma_fac)
+			&& cfg.lookupValue("t_damp", t_damp) && cfg.lookupValue("omega_x", omega_in[0])
+			&& cfg.lookupValue("omega_y", omega_in[1]) && cfg.lookupValue("omega_z", omega_in[2])
+			&& cfg.lookupValue("min_particle_distance", min_dist) && cfg.lookupValue("mass_ball", mass_ball)
+			&& cfg.lookupValue("radius_ball", r_ball) && cfg.lookupValue("ratio1", ratio1)
+			&& cfg.lookupValue("ratio2", ratio2))) {
+		throw "Failed to read in problem.cfg. Exiting.";
+	}
+	cfg.lookupValue("seed", seed);
+	cfg.lookupValue("gravity", use_gravity);
+	Vector omega(omega_in);
+
+	reb_simulation *const n_body_sim = reb_create_simulation();
+	srand(seed);  // reb_create_simulation reseeds from the clock (src/rebound.c:369): "same seed" = srand after it
+
+	n_body_sim->integrator = reb_simulation::REB_INTEGRATOR_LEAPFROG;
+	n_body_sim->gravity = use_gravity ? reb_simulation::REB_GRAVITY_BASIC : reb_simulation::REB_GRAVITY_NONE;
+	n_body_sim->boundary = reb_simulation::REB_BOUNDARY_NONE;
+	n_body_sim->visualization = reb_simulation::REB_VISUALIZATION_NONE;
+	n_body_sim->G = 1.0;
+	n_body_sim->additional_forces = additional_forces;
+	n_body_sim->heartbeat = heartbeat;
+	n_body_sim->dt = dt;
+	n_body_sim->softening = min_dist / 100.0;  // modules/wobble_bennu2/problem.cpp:115
+
+	spring default_spring;
+	default_spring.gamma = gamma_fac * def_gamma;
+	default_spring.k = k;
+
+	rand_ellipsoid(n_body_sim, min_dist, r_ball, r_ball * ratio1, r_ball * ratio2, mass_ball);
+	const int i_low = 0, i_high = n_body_sim->N;
+	subtract_com(n_body_sim, i_low, i_high);
+	subtract_cov(n_body_sim, i_low, i_high);
+	spin_body(n_body_sim, i_low, i_high, omega);
+	connect_springs_dist(n_body_sim, max_spring_dist, i_low, i_high, default_spring);
+
+	std::ofstream runfile(fileroot + "_run.txt", std::ios::out | std::ios::trunc);
+	runfile << std::hexfloat << "N " << n_body_sim->N << "\nNS " << num_springs << "\nmean_rs0 " << mean_spring_length()
+			<< "\nmindist " << mindist(n_body_sim, i_low, i_high) << "\n";
+	for (int i = 0; i < num_springs; i++)
+		runfile << springs[i].particle_1 << " " << springs[i].particle_2 << " " << springs[i].rs0 << "\n";
+	runfile.close();
+	std::ofstream(fileroot + "_ext.txt", std::ios::out | std::ios::trunc).close();
+
+	if (t_max == 0.0) t_max = INFINITY;
+	reb_integrate(n_body_sim, t_max);
+
+	std::ofstream fin(fileroot + "_final.txt", std::ios::out | std::ios::trunc);
+	fin << std::hexfloat << "t " << n_body_sim->t << "\ndt " << n_body_sim->dt << "\nstatus " << n_body_sim->status << "\n";
+	for (int i = 0; i < n_body_sim->N; i++) {
+		const reb_particle &p = n_body_sim->particles[i];
+		fin << p.x << " " << p.y << " " << p.z << " " << p.vx << " " << p.vy << " " << p.vz << " " << p.ax << " " << p.ay
+				<< " " << p.az << " " << p.m << "\n";
+	}
+	return 0;
+}
+
+// modules/asteroid_spin/problem.cpp:225-231 (GRAVITY_NONE needs zero_accel) / modules/wobble_bennu2 (springs only)
+void additional_forces(reb_simulation *n_body_sim) {
+	if (!use_gravity)
+		zero_accel(n_body_sim);
+	spring_forces(n_body_sim);
+}
+
+// modules/asteroid_spin/problem.cpp:181-207
+void heartbeat(reb_simulation *const n_body_sim) {
+	static string extendedfile = fileroot + "_ext.txt";
+	if (std::abs(n_body_sim->t - t_damp) < 0.9 * n_body_sim->dt)
+		set_gamma(def_gamma);
+	center_sim(n_body_sim, 0, n_body_sim->N - num_perts);
+	if (reb_output_check(n_body_sim, print_interval)) {
+		const int i_low = 0, i_high = n_body_sim->N - num_perts;
+		Vector L = measure_L(n_body_sim, i_low, i_high);
+		const double KE = compute_rot_kin(n_body_sim, i_low, i_high);
+		const double SPE = spring_potential_energy(n_body_sim);
+		const double GPE = use_gravity ? grav_potential_energy(n_body_sim, i_low, i_high) : 0.0;
+		std::ofstream out(extendedfile, std::ios::out | std::ios::app);
+		out << std::setprecision(17) << n_body_sim->t << " " << L.getX() << " " << L.getY() << " " << L.getZ() << " " << KE
+				<< " " << SPE << " " << GPE << " " << dEdt_total(n_body_sim) << "\n";
+	}
+}

@@ -76,16 +76,16 @@ def test_kat_physics_helpers(gpu, kat3):
         s.zero_accel()
         assert np.all(s.download(P.copy())[:, 6:9] == 0.0)                      # PhysicsTest.ZeroAccel
         s.center_sim(0, 2)
-        assert np.allclose(s.download(P.copy())[:, :3], kat3["center_all"], rtol=0, atol=2e-16)
+        assert same_bits(s.download(P.copy())[:, :3], kat3["center_all"])       # PhysicsTest.CenterAll (EXPECT_EQ)
     for op, key in (("subtract_com", "sub_com"), ("subtract_cov", "sub_cov")):
         P = kat_particles()
         with new_sim(gpu, P) as s:
             getattr(s, op)(0, 3)
-            assert np.allclose(s.download(P.copy())[:, :6], kat3[key], rtol=0, atol=4e-16)
+            assert same_bits(s.download(P.copy())[:, :6], kat3[key])
     P = kat_particles()
     with new_sim(gpu, P) as s:
         s.spin_body(0, 3, (1.0, 12.0, 12.0))
-        assert np.allclose(s.download(P.copy())[:, :6], kat3["spin"], rtol=1e-15, atol=1e-14)
+        assert same_bits(s.download(P.copy())[:, :6], kat3["spin"])
         s.move_resolved((-1, -1, -1), (1, 1, 1), 0, 3)                          # PhysicsTest.MoveResolved
         out = s.download(P.copy())
         assert np.allclose(out[:, :3], kat3["spin"][:, :3] - 1, atol=1e-15)
@@ -126,6 +126,13 @@ def test_body_build(gpu, request, fixture_name):
         assert s.mindist() == g["mindist"][0]
         sp = s.connect_springs_dist(2.3 * d, 0, n, K, GAMMA)
         assert sp.tobytes() == g["springs"].tobytes()           # bit-exact list: (i, j) order and rs0 bits
+        # set-up helpers sum in the reference's particle order by default: bit-identical start state
+        s.subtract_com(0, n); s.subtract_cov(0, n); s.spin_body(0, n, OMEGA)
+        out = s.download(p.copy())
+        assert same_bits(out[:, :6], g["start"][:, :6])
+        # the parallel tree (per-step heartbeats at large N) agrees to rounding
+        s.upload(p)
+        s.set_sum_order(sequential=False)
         s.subtract_com(0, n); s.subtract_cov(0, n); s.spin_body(0, n, OMEGA)
         out = s.download(p.copy())
         assert np.allclose(out[:, :6], g["start"][:, :6], rtol=0, atol=1e-15)
