@@ -278,6 +278,105 @@ class Sim:
     def l2_flush(self):
         _chk(lib().ass_l2_flush(self._h))
 
+    # -- one large body sharded by particle slab over ranks (include/ass_b200.h, "multi-GPU") --
+    def shard_setup(self, rank, nranks, bounds):
+        b = (C.c_int * (nranks + 1))(*[int(x) for x in bounds])
+        _chk(lib().ass_shard_setup(self._h, C.c_int(rank), C.c_int(nranks), b))
+
+    def shard_export(self):
+        buf = (C.c_ubyte * 64)()
+        _chk(lib().ass_shard_export(self._h, buf))
+        return bytes(buf)
+
+    def shard_import(self, peer_rank, handle):
+        buf = (C.c_ubyte * 64).from_buffer_copy(handle)
+        _chk(lib().ass_shard_import(self._h, C.c_int(peer_rank), buf))
+
+    def shard_import_local(self, peer_rank, peer):
+        _chk(lib().ass_shard_import_local(self._h, C.c_int(peer_rank), peer._h))
+
+    def shard_begin(self):
+        _chk(lib().ass_shard_begin(self._h))
+
+    def shard_exchange(self):
+        _chk(lib().ass_shard_exchange(self._h))
+
+    def shard_finish(self, pre_drift_next=False):
+        _chk(lib().ass_shard_finish(self._h, C.c_int(int(pre_drift_next))))
+
+    def shard_gather(self):
+        _chk(lib().ass_shard_gather(self._h))
+
+
+def slab_bounds(n, nranks, align=256):
+    """Contiguous particle slabs of near-equal size, boundaries aligned to the gravity tile (256 sources)."""
+    per = -(-n // nranks)
+    per = -(-per // align) * align
+    return [min(n, r * per) for r in range(nranks)] + [n]
+
+
+class Ensemble:
+    """B independent small bodies stepped by one kernel, one CTA per body (``ass_ensemble``)."""
+
+    def __init__(self, bodies, springs, params):
+        """bodies: list of (n_b, >=10) float64 row arrays; springs: list of SPRING_DTYPE arrays with LOCAL indices;
+        params: list of dicts of Params fields."""
+        assert len(bodies) == len(springs) == len(params) and len(bodies) > 0
+        self.nb = len(bodies)
+        self.node_off = np.zeros(self.nb + 1, dtype=np.int32)
+        self.spring_off = np.zeros(self.nb + 1, dtype=np.int32)
+        self.node_off[1:] = np.cumsum([len(b) for b in bodies])
+        self.spring_off[1:] = np.cumsum([len(s) for s in springs])
+        rows = np.ascontiguousarray(np.vstack([np.asarray(b, dtype=np.float64)[:, :11] for b in bodies]))
+        sp = np.ascontiguousarray(np.concatenate([np.asarray(s, dtype=SPRING_DTYPE) for s in springs]))
+        P = (Params * self.nb)()
+        for i, kw in enumerate(params):
+            P[i].dt = 1e-3; P[i].G = 1.0; P[i].n_active = -1; P[i].exact_finish_time = 1; P[i].status = -1; P[i].additional_forces = 1
+            for k, v in kw.items():
+                setattr(P[i], k, v)
+        self._h = C.c_void_p()
+        _chk(lib().ass_ensemble_create(C.byref(self._h), C.c_int(self.nb), self.node_off.ctypes.data_as(C.c_void_p),
+                                       self.spring_off.ctypes.data_as(C.c_void_p), rows.ctypes.data_as(C.c_void_p),
+                                       C.c_size_t(rows.strides[0]), sp.ctypes.data_as(C.c_void_p), P))
+        self.total_nodes = int(self.node_off[-1])
+        self.total_springs = int(self.spring_off[-1])
+
+    def close(self):
+        if self._h:
+            lib().ass_ensemble_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def step(self, nsteps=1, heartbeat=False, timed=False):
+        ms = C.c_double()
+        _chk(lib().ass_ensemble_step(self._h, C.c_int(nsteps), C.c_int(int(heartbeat)), C.byref(ms) if timed else None))
+        return ms.value
+
+    def download(self, fields=F_ALL):
+        """Returns the list of per-body (n_b, 11) arrays (column 10, r, is not transferred)."""
+        out = np.zeros((self.total_nodes, 11))
+        _chk(lib().ass_ensemble_download(self._h, out.ctypes.data_as(C.c_void_p), C.c_size_t(out.strides[0]), C.c_uint(fields)))
+        return [out[self.node_off[b]:self.node_off[b + 1]] for b in range(self.nb)]
+
+    def params(self):
+        P = (Params * self.nb)()
+        _chk(lib().ass_ensemble_get_params(self._h, P))
+        return list(P)
+
+    def sync(self):
+        _chk(lib().ass_ensemble_sync(self._h))
+
 
 def _gen(fn, min_dist, a, b, c, total_mass, existing):
     libc = C.CDLL(None)

@@ -65,10 +65,14 @@ struct DevBuf {
 
 struct ShardInfo {
 	int rank = 0, nranks = 1;
-	int lo = 0, hi = 0;              // owned targets
-	std::vector<int> lo_of, hi_of;   // every rank's slab
-	vec4d* window = nullptr;         // exported copy of all N posm rows; owner keeps [lo,hi) current
-	std::vector<vec4d*> peer_window; // mapped peer windows (nullptr for self)
+	int lo = 0, hi = 0;               // owned slab of targets / spring owners
+	std::vector<int> bounds;          // nranks + 1 slab boundaries
+	vec4d* window = nullptr;          // one exportable allocation [posm (N) | vel (N)]; sim->posm / sim->vel point into it
+	std::vector<vec4d*> peer_window;  // peers' windows mapped here (nullptr for self)
+	std::vector<char> peer_is_ipc;    // mapped through cudaIpcOpenMemHandle (needs closing) or a same-process pointer
+	cudaStream_t copy_stream = nullptr;
+	cudaEvent_t pulled = nullptr;
+	int rows_local = 0;               // partial-sum rows written by the own-slab-sources launch of this step
 	bool active = false;
 };
 
@@ -113,6 +117,7 @@ struct ass_sim {
 	ShardInfo shard;
 };
 
+void ass_shard_release(ass_sim* s);  // shard.cu
 int ass_buf_reserve(DevBuf& b, size_t bytes);
 int ass_ensure_device(void);
 int ass_sm_count(void);
@@ -136,14 +141,20 @@ void ass_toc(ass_sim* s, int klass);
 // ---------------------------------------------------------------------------------------------------
 // springs.cu
 int ass_launch_spring_forces(ass_sim* s, bool zero_first);
+int ass_launch_spring_forces_range(ass_sim* s, bool zero_first, int lo, int hi);
 int ass_launch_spring_kick_drift(ass_sim* s, bool zero_first, double dt, bool pre_drift_next);
 // gravity.cu
 int ass_launch_gravity(ass_sim* s);
-int ass_launch_gpe(ass_sim* s, int lo, int hi, double* d_out);
+int ass_gravity_rows(int n_tgt, int n_src);
+int ass_launch_gravity_partial(ass_sim* s, const vec4d* src, int s_lo, int s_hi, int t_lo, int t_hi, int row_base, int* rows_out);
+int ass_launch_gravity_reduce(ass_sim* s, int t_lo, int t_hi, int rows);
 // leapfrog.cu
 int ass_launch_part1(ass_sim* s, double dt);
 int ass_launch_part2(ass_sim* s, double dt);
+int ass_launch_part1_range(ass_sim* s, double dt, int lo, int hi);
+int ass_launch_part2_range(ass_sim* s, double dt, bool pre_drift_next, int lo, int hi);
 int ass_launch_zero_accel(ass_sim* s);
+int ass_launch_zero_accel_range(ass_sim* s, int lo, int hi);
 // reduce.cu
 int ass_launch_com(ass_sim* s, int lo, int hi, bool velocity, double* d_out3_and_mass);
 int ass_launch_shift(ass_sim* s, int lo, int hi, const double* d_shift3, bool velocity, double sign, double drift_half_dt);

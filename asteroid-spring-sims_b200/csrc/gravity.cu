@@ -15,9 +15,13 @@
 // per pair; we factor -G out of the sum and use rsqrt: agreement is ~1e-15 relative per term (tests bound the sum at
 // 1e-12 of max|a|).
 //
-// Load balance: the grid is (target blocks) x (source splits); each split writes its own partial sum row and a
+// Load balance: the grid is (target blocks) x (source splits); each split writes its own partial-sum row and a
 // fixed-order pass adds the rows, so the result stays deterministic.  The split count is chosen so that the CTA count
-// is a near-multiple of the SM count (all CTAs take the same time; see choose_split).
+// is a near-multiple of the SM count (all CTAs take the same time; see plan_split).  The same machinery lets a sharded
+// simulation (shard.cu) evaluate "sources in my slab" and "sources in the other slabs" as separate launches that land
+// in different rows and are reduced once.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace {
@@ -72,18 +76,18 @@ __device__ __forceinline__ void pair_update(Targets<TI>& t, const vec4d sj, int 
 	}
 }
 
-// grid.x = target blocks of GB*TI, grid.y = source splits.
-// src: source vectors (length >= j_end rounded up to... see padding note), tgt: target vectors.
+// grid.x = target blocks of GB*TI over [t_lo, t_hi); grid.y = source splits of split_len over [s_lo, s_hi).
+// Row blockIdx.y of `out` (stride out_stride vectors) receives -G * (partial sum).
 template <int TI, bool CHECK>
-__global__ void __launch_bounds__(GB) k_gravity(const vec4d* __restrict__ src, int n_src, const vec4d* __restrict__ tgt,
+__global__ void __launch_bounds__(GB) k_gravity(const vec4d* __restrict__ src, int s_lo, int s_hi, const vec4d* __restrict__ tgt,
 		int t_lo, int t_hi, int split_len, double soft2, double negG, vec4d* __restrict__ out, size_t out_stride) {
 	__shared__ __align__(128) vec4d tile[2][JT];
 	__shared__ __align__(8) uint64_t full[2];
 
 	const int tid = threadIdx.x;
 	const int i0 = t_lo + blockIdx.x * (GB * TI);
-	const int j_beg = blockIdx.y * split_len;
-	const int j_end = min(n_src, j_beg + split_len);
+	const int j_beg = s_lo + blockIdx.y * split_len;
+	const int j_end = min(s_hi, j_beg + split_len);
 	const int n_tiles = (j_end - j_beg + JT - 1) / JT;
 
 	Targets<TI> t;
@@ -144,12 +148,12 @@ __global__ void __launch_bounds__(GB) k_gravity(const vec4d* __restrict__ src, i
 	}
 }
 
-// acc[i] = sum over splits, fixed order
-__global__ void k_gravity_reduce(const vec4d* __restrict__ part, size_t stride, int splits, int lo, int hi, vec4d* __restrict__ acc) {
+// acc[i] = sum over rows, fixed order
+__global__ void k_gravity_reduce(const vec4d* __restrict__ part, size_t stride, int rows, int lo, int hi, vec4d* __restrict__ acc) {
 	const int i = lo + blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= hi) return;
 	vec4d a = part[i];
-	for (int s = 1; s < splits; s++) {
+	for (int s = 1; s < rows; s++) {
 		const vec4d b = part[(size_t) s * stride + i];
 		a.x += b.x; a.y += b.y; a.z += b.z;
 	}
@@ -157,7 +161,6 @@ __global__ void k_gravity_reduce(const vec4d* __restrict__ part, size_t stride, 
 	acc[i] = a;
 }
 
-// zero the accelerations of particles that are not targets of this evaluation (gravity.c:76-80 zeroes all N)
 __global__ void k_zero_range(vec4d* __restrict__ acc, int lo, int hi) {
 	const int i = lo + blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= hi) return;
@@ -165,86 +168,103 @@ __global__ void k_zero_range(vec4d* __restrict__ acc, int lo, int hi) {
 	acc[i] = z;
 }
 
+int pick_ti(int n_tgt, int sms) {
+	if (n_tgt >= sms * GB * 4 * 2) return 4;
+	if (n_tgt >= sms * GB * 2) return 2;
+	return 1;
+}
+
 // All CTAs do the same amount of work, and the block scheduler hands them out as SMs free up, so the makespan is
 // ceil(ctas / sms) CTA-times.  Pick the number of source splits that wastes the least of the last round, preferring
 // few splits (each costs one more partial-sum row).
-int choose_split(int target_blocks, int n_src, int sms) {
+void plan_split(int n_tgt, int n_src, int sms, int* ti_out, int* split_out, int* split_len_out) {
+	const int ti = pick_ti(n_tgt, sms);
+	const int tblocks = (n_tgt + GB * ti - 1) / (GB * ti);
 	int best = 1;
 	double best_score = -1.0;
 	const int max_split = std::max(1, std::min(32, n_src / (4 * JT)));
 	for (int s = 1; s <= max_split; s++) {
-		const double ctas = (double) target_blocks * s;
+		const double ctas = (double) tblocks * s;
 		const double rounds = ceil(ctas / sms);
-		const double eff = ctas / (rounds * sms);
-		const double score = eff - 0.002 * s;
+		const double score = ctas / (rounds * sms) - 0.002 * s;
 		if (score > best_score + 1e-12) { best_score = score; best = s; }
 	}
-	return best;
+	int split_len = (n_src + best - 1) / best;
+	split_len = ((split_len + JT - 1) / JT) * JT;  // tile-aligned split boundaries
+	*ti_out = ti;
+	*split_len_out = split_len;
+	*split_out = (n_src + split_len - 1) / split_len;
 }
 
 template <int TI>
-int launch_gravity_ti(ass_sim* s, const vec4d* src, int n_src, int t_lo, int t_hi, double soft2, double negG) {
-	const int n_tgt = t_hi - t_lo;
-	const int tblocks = (n_tgt + GB * TI - 1) / (GB * TI);
-	int split = choose_split(tblocks, n_src, ass_sm_count());
-	int split_len = (n_src + split - 1) / split;
-	split_len = ((split_len + JT - 1) / JT) * JT;  // tile-aligned split boundaries keep every bulk copy 16 B aligned
-	split = (n_src + split_len - 1) / split_len;
-	vec4d* out = s->acc;
-	size_t stride = 0;
-	if (split > 1) {
-		int rc = ass_buf_reserve(s->grav_partial, sizeof(vec4d) * (size_t) split * (size_t) s->n);
-		if (rc) return rc;
-		out = (vec4d*) s->grav_partial.p;
-		stride = (size_t) s->n;
-	}
+void launch_ti(ass_sim* s, const vec4d* src, int s_lo, int s_hi, int t_lo, int t_hi, int split, int split_len, double soft2, double negG,
+		vec4d* out, size_t stride) {
+	const int tblocks = (t_hi - t_lo + GB * TI - 1) / (GB * TI);
 	dim3 grid(tblocks, split);
-	ass_tic(s, ASS_K_GRAVITY);
 	if (soft2 > 0.0)
-		k_gravity<TI, false><<<grid, GB, 0, s->stream>>>(src, n_src, s->posm, t_lo, t_hi, split_len, soft2, negG, out, stride);
+		k_gravity<TI, false><<<grid, GB, 0, s->stream>>>(src, s_lo, s_hi, s->posm, t_lo, t_hi, split_len, soft2, negG, out, stride);
 	else
-		k_gravity<TI, true><<<grid, GB, 0, s->stream>>>(src, n_src, s->posm, t_lo, t_hi, split_len, soft2, negG, out, stride);
-	LAUNCH_CHECK();
-	if (split > 1) {
-		k_gravity_reduce<<<(n_tgt + 255) / 256, 256, 0, s->stream>>>(out, stride, split, t_lo, t_hi, s->acc);
-		LAUNCH_CHECK();
-	}
-	ass_toc(s, ASS_K_GRAVITY);
-	return ASS_OK;
+		k_gravity<TI, true><<<grid, GB, 0, s->stream>>>(src, s_lo, s_hi, s->posm, t_lo, t_hi, split_len, soft2, negG, out, stride);
 }
 
 }  // namespace
 
-// a = gravity for targets [t_lo, t_hi) from sources src[0, n_src)
+// Number of partial rows a launch over (n_tgt targets, n_src sources) will write.
+int ass_gravity_rows(int n_tgt, int n_src) {
+	if (n_tgt <= 0 || n_src <= 0) return 0;
+	int ti, split, len;
+	plan_split(n_tgt, n_src, ass_sm_count(), &ti, &split, &len);
+	return split;
+}
+
+// Partial sums of targets [t_lo,t_hi) over sources src[s_lo,s_hi) into rows [row_base, row_base + rows) of grav_partial
+// (which the caller has reserved).  Returns the number of rows written through *rows_out.
+int ass_launch_gravity_partial(ass_sim* s, const vec4d* src, int s_lo, int s_hi, int t_lo, int t_hi, int row_base, int* rows_out) {
+	*rows_out = 0;
+	if (t_hi <= t_lo || s_hi <= s_lo) return ASS_OK;
+	int ti, split, len;
+	plan_split(t_hi - t_lo, s_hi - s_lo, ass_sm_count(), &ti, &split, &len);
+	const double soft2 = s->prm.softening * s->prm.softening;
+	const double negG = -s->prm.G;
+	vec4d* out = (vec4d*) s->grav_partial.p + (size_t) row_base * (size_t) s->n;
+	ass_tic(s, ASS_K_GRAVITY);
+	if (ti == 4) launch_ti<4>(s, src, s_lo, s_hi, t_lo, t_hi, split, len, soft2, negG, out, (size_t) s->n);
+	else if (ti == 2) launch_ti<2>(s, src, s_lo, s_hi, t_lo, t_hi, split, len, soft2, negG, out, (size_t) s->n);
+	else launch_ti<1>(s, src, s_lo, s_hi, t_lo, t_hi, split, len, soft2, negG, out, (size_t) s->n);
+	LAUNCH_CHECK();
+	ass_toc(s, ASS_K_GRAVITY);
+	*rows_out = split;
+	return ASS_OK;
+}
+
+int ass_launch_gravity_reduce(ass_sim* s, int t_lo, int t_hi, int rows) {
+	if (t_hi <= t_lo) return ASS_OK;
+	ass_tic(s, ASS_K_GRAVITY);
+	if (rows <= 0) k_zero_range<<<(t_hi - t_lo + 255) / 256, 256, 0, s->stream>>>(s->acc, t_lo, t_hi);
+	else k_gravity_reduce<<<(t_hi - t_lo + 255) / 256, 256, 0, s->stream>>>((const vec4d*) s->grav_partial.p, (size_t) s->n, rows, t_lo, t_hi, s->acc);
+	LAUNCH_CHECK();
+	ass_toc(s, ASS_K_GRAVITY);
+	return ASS_OK;
+}
+
+// a = gravity for every particle, all sources local (the unsharded path)
 int ass_launch_gravity(ass_sim* s) {
 	const int n = s->n;
 	if (n == 0) return ASS_OK;
-	const int n_src = (s->prm.n_active == -1) ? n : std::min(s->prm.n_active, n);
-	const double soft2 = s->prm.softening * s->prm.softening;
-	const double negG = -s->prm.G;
-	int t_lo = 0, t_hi = n;
-	const vec4d* src = s->posm;
-	if (s->shard.active) {
-		t_lo = s->shard.lo;
-		t_hi = s->shard.hi;
-		src = s->shard.window;  // filled by ass_shard_gather / read in place from peers (shard.cu)
-	}
-	if (n_src <= 0 || t_hi <= t_lo) {
-		k_zero_range<<<(n + 255) / 256, 256, 0, s->stream>>>(s->acc, 0, n);
-		LAUNCH_CHECK();
-		return ASS_OK;
-	}
-	const int n_tgt = t_hi - t_lo;
-	const int sms = ass_sm_count();
-	if (n_tgt >= sms * GB * 4 * 2) return launch_gravity_ti<4>(s, src, n_src, t_lo, t_hi, soft2, negG);
-	if (n_tgt >= sms * GB * 2) return launch_gravity_ti<2>(s, src, n_src, t_lo, t_hi, soft2, negG);
-	return launch_gravity_ti<1>(s, src, n_src, t_lo, t_hi, soft2, negG);
+	const int n_src = (s->prm.n_active == -1) ? n : std::max(0, std::min(s->prm.n_active, n));
+	const int rows = ass_gravity_rows(n, n_src);
+	int rc = ass_buf_reserve(s->grav_partial, sizeof(vec4d) * (size_t) std::max(rows, 1) * (size_t) n);
+	if (rc) return rc;
+	int used = 0;
+	if ((rc = ass_launch_gravity_partial(s, s->posm, 0, n_src, 0, n, 0, &used))) return rc;
+	return ass_launch_gravity_reduce(s, 0, n, used);
 }
 
 extern "C" int ass_gravity_basic(ass_sim* s) {
 	REQUIRE(s, ASS_EINVAL, "null sim");
 	REQUIRE(s->have_state, ASS_ESTATE, "no particle state on the device");
 	REQUIRE(!s->predrifted, ASS_ESTATE, "internal: positions are mid-step");
+	REQUIRE(!s->shard.active, ASS_ESTATE, "sharded simulations evaluate gravity inside ass_shard_exchange / ass_shard_finish");
 	int rc = ass_ensure_device();
 	if (rc) return rc;
 	if (s->prm.gravity == 0) return ASS_OK;  // REB_GRAVITY_NONE: "Do nothing." (gravity.c:68-70)

@@ -12,9 +12,9 @@
 
 namespace {
 
-__global__ void k_part1(vec4d* __restrict__ posm, const vec4d* __restrict__ vel, int n, double dt) {
-	const int i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= n) return;
+__global__ void k_part1(vec4d* __restrict__ posm, const vec4d* __restrict__ vel, int lo, int hi, double dt) {
+	const int i = lo + blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= hi) return;
 	const double h = __dmul_rn(0.5, dt);
 	vec4d p = posm[i];
 	const vec4d v = vel[i];
@@ -24,9 +24,9 @@ __global__ void k_part1(vec4d* __restrict__ posm, const vec4d* __restrict__ vel,
 	posm[i] = p;
 }
 
-__global__ void k_part2(vec4d* __restrict__ posm, vec4d* __restrict__ vel, const vec4d* __restrict__ acc, int n, double dt, int pre_drift_next) {
-	const int i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= n) return;
+__global__ void k_part2(vec4d* __restrict__ posm, vec4d* __restrict__ vel, const vec4d* __restrict__ acc, int lo, int hi, double dt, int pre_drift_next) {
+	const int i = lo + blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= hi) return;
 	const double h = __dmul_rn(0.5, dt);
 	vec4d p = posm[i];
 	vec4d v = vel[i];
@@ -46,40 +46,43 @@ __global__ void k_part2(vec4d* __restrict__ posm, vec4d* __restrict__ vel, const
 	posm[i] = p;
 }
 
-__global__ void k_zero_accel(vec4d* __restrict__ acc, int n) {
-	const int i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= n) return;
+__global__ void k_zero_accel(vec4d* __restrict__ acc, int lo, int hi) {
+	const int i = lo + blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= hi) return;
 	vec4d z; z.x = 0.0; z.y = 0.0; z.z = 0.0; z.w = 0.0;
 	acc[i] = z;
 }
 
 }  // namespace
 
-int ass_launch_part1(ass_sim* s, double dt) {
-	if (s->n == 0) return ASS_OK;
+int ass_launch_part1_range(ass_sim* s, double dt, int lo, int hi) {
+	if (hi <= lo) return ASS_OK;
 	ass_tic(s, ASS_K_LEAPFROG);
-	k_part1<<<(s->n + 255) / 256, 256, 0, s->stream>>>(s->posm, s->vel, s->n, dt);
+	k_part1<<<(hi - lo + 255) / 256, 256, 0, s->stream>>>(s->posm, s->vel, lo, hi, dt);
 	LAUNCH_CHECK();
 	ass_toc(s, ASS_K_LEAPFROG);
 	return ASS_OK;
 }
-static int launch_part2(ass_sim* s, double dt, bool pre_drift_next) {
-	if (s->n == 0) return ASS_OK;
+int ass_launch_part2_range(ass_sim* s, double dt, bool pre_drift_next, int lo, int hi) {
+	if (hi <= lo) return ASS_OK;
 	ass_tic(s, ASS_K_LEAPFROG);
-	k_part2<<<(s->n + 255) / 256, 256, 0, s->stream>>>(s->posm, s->vel, s->acc, s->n, dt, pre_drift_next ? 1 : 0);
+	k_part2<<<(hi - lo + 255) / 256, 256, 0, s->stream>>>(s->posm, s->vel, s->acc, lo, hi, dt, pre_drift_next ? 1 : 0);
 	LAUNCH_CHECK();
 	ass_toc(s, ASS_K_LEAPFROG);
 	return ASS_OK;
 }
+int ass_launch_zero_accel_range(ass_sim* s, int lo, int hi) {
+	if (hi <= lo) return ASS_OK;
+	ass_tic(s, ASS_K_LEAPFROG);
+	k_zero_accel<<<(hi - lo + 255) / 256, 256, 0, s->stream>>>(s->acc, lo, hi);
+	LAUNCH_CHECK();
+	ass_toc(s, ASS_K_LEAPFROG);
+	return ASS_OK;
+}
+int ass_launch_part1(ass_sim* s, double dt) { return ass_launch_part1_range(s, dt, 0, s->n); }
+static int launch_part2(ass_sim* s, double dt, bool pre_drift_next) { return ass_launch_part2_range(s, dt, pre_drift_next, 0, s->n); }
 int ass_launch_part2(ass_sim* s, double dt) { return launch_part2(s, dt, false); }
-int ass_launch_zero_accel(ass_sim* s) {
-	if (s->n == 0) return ASS_OK;
-	ass_tic(s, ASS_K_LEAPFROG);
-	k_zero_accel<<<(s->n + 255) / 256, 256, 0, s->stream>>>(s->acc, s->n);
-	LAUNCH_CHECK();
-	ass_toc(s, ASS_K_LEAPFROG);
-	return ASS_OK;
-}
+int ass_launch_zero_accel(ass_sim* s) { return ass_launch_zero_accel_range(s, 0, s->n); }
 
 #define ENTER(s)                                                              \
 	REQUIRE(s, ASS_EINVAL, "null sim");                                       \

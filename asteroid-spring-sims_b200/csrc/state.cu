@@ -231,6 +231,7 @@ extern "C" int ass_destroy(ass_sim* s) {
 	if (!s) return ASS_OK;
 	ass_ensure_device();
 	if (s->stream) cudaStreamSynchronize(s->stream);
+	ass_shard_release(s);  // a sharded simulation's posm / vel alias its exported window
 	cudaFree(s->posm); cudaFree(s->vel); cudaFree(s->acc); cudaFree(s->posm_alt); cudaFree(s->vel_alt);
 	cudaFree(s->he); cudaFree(s->row_ptr); cudaFree(s->slot);
 	cudaFree(s->stage.p); cudaFree(s->grav_partial.p); cudaFree(s->red_partial.p); cudaFree(s->flush.p);
@@ -243,9 +244,6 @@ extern "C" int ass_destroy(ass_sim* s) {
 	}
 	if (s->mark0) cudaEventDestroy(s->mark0);
 	if (s->mark1) cudaEventDestroy(s->mark1);
-	for (size_t r = 0; r < s->shard.peer_window.size(); r++)
-		if (s->shard.peer_window[r]) cudaIpcCloseMemHandle(s->shard.peer_window[r]);
-	cudaFree(s->shard.window);
 	if (s->stream) cudaStreamDestroy(s->stream);
 	cudaGetLastError();
 	delete s;

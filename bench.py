@@ -247,8 +247,167 @@ def run_reference(args, rank, world):
     print(json.dumps(out))
 
 
+def finish_line(out, dist):
+    print(json.dumps(out))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
 def run_c5(args, A, rank, world, local, dist):
-    raise SystemExit("workload C5 (4096 x 1k-node ensemble) needs the ensemble kernel, which this build does not carry yet")
+    """BASELINE config 5: 4096 independent ~1k-node bodies (C1 generator), omega_z swept 0.1 -> 0.9, k in
+    {0.02, 0.04, 0.08, 0.16}, GRAVITY_NONE + zero_accel + springs; members dealt round-robin to the ranks, no collective."""
+    total = int(os.environ.get("ASS_C5_BODIES", "4096"))
+    distinct = int(os.environ.get("ASS_C5_DISTINCT_SEEDS", "64"))   # bodies are regenerated per seed; 64 shapes x sweeps
+    d = WORKLOADS["C1"]["d"]
+    mine = [b for b in range(total) if b % world == rank]
+    t0 = time.perf_counter()
+    shapes = {}
+    for sd in sorted({b % distinct for b in mine}):
+        A.srand(SEED + sd)
+        p = A.rand_ellipsoid(d, *ABC, 1.0)
+        with A.Sim() as s:
+            s.upload(p)
+            sp = s.connect_springs_dist(2.3 * d, 0, len(p), 1.0, GAMMA)
+            s.subtract_com(0, len(p)); s.subtract_cov(0, len(p))
+            s.download(p)
+        shapes[sd] = (p, sp)
+    bodies, springs, params = [], [], []
+    for b in mine:
+        p, sp = shapes[b % distinct]
+        wz = 0.1 + 0.8 * b / max(total - 1, 1)
+        k = (0.02, 0.04, 0.08, 0.16)[b % 4]
+        q = p.copy()
+        q[:, 3] = -wz * q[:, 1]; q[:, 4] = wz * q[:, 0]; q[:, 5] = 0.0      # spin_body about z for a centred body
+        s2 = sp.copy(); s2["k"] = k
+        bodies.append(q); springs.append(s2)
+        params.append(dict(dt=WORKLOADS["C1"]["dt"], gravity=0, additional_forces=2, heartbeat=0))
+    setup_s = time.perf_counter() - t0
+    ens = A.Ensemble(bodies, springs, params)
+    nodes = ens.total_nodes
+    ens.step(args.warmup)
+    ens.sync()
+    clocks = ClockSampler(local)
+    barrier(dist)
+    launches0 = A.launch_count()
+    clocks.start()
+    ms = ens.step(args.steps, timed=True)
+    barrier(dist)
+    clk = clocks.stop()
+    launches = A.launch_count() - launches0
+    ms_max = max_over_ranks(dist, ms, local)
+    total_nodes = sum_over_ranks(dist, float(nodes), local)
+    total_springs = sum_over_ranks(dist, float(ens.total_springs), local)
+    value = total_nodes * args.steps / (ms_max * 1e-3)
+    # e2e: state is resident by design (that is the point of the ensemble kernel); every step's result is read back
+    barrier(dist)
+    t0 = time.perf_counter()
+    for _ in range(min(args.steps, 20)):
+        ens.step(1)
+        ens.download(A.F_POS | A.F_VEL | A.F_ACC)
+    barrier(dist)
+    t_e2e = max_over_ranks(dist, time.perf_counter() - t0, local)
+    if rank != 0:
+        return
+    peaks = read_json(os.path.join(ROOT, "MEASURED_PEAKS.json")) or {}
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    alg = (32.0 * total_springs + 80.0 * total_nodes) / world              # per GPU per step (SURVEY 8d)
+    ach = alg * args.steps / (ms_max * 1e-3) / 1e9
+    cpu = None
+    if not args.no_cpu_baseline:
+        try:
+            cfg1 = dict(WORKLOADS["C1"])
+            v, sample, cores, _ = reference_arm_value(cfg1, np.ascontiguousarray(bodies[0]), springs[0], budget_s=5.0, omp=False)
+            cpu = {"value": v, "unit": "node-steps/s", "cores": cores, "host_cores": os.cpu_count(), "kind": "reference",
+                   "sample": "one member of the ensemble (N=%d) stepped by the reference; the ensemble is that x %d" % (len(bodies[0]), total)}
+        except FileNotFoundError as e:
+            cpu = {"value": None, "unit": "node-steps/s", "cores": 0, "kind": "reference", "sample": "unavailable: %s" % e}
+    out = {"metric": "node-steps/s", "value": value, "unit": "node-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "strong",
+           "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": "C5: ensemble spin-rate/material sweep, %d independent ~1k-node bodies (C1 generator, %d distinct seeds), GRAVITY_NONE + zero_accel + springs" % (total, distinct),
+                      "bodies": total, "bodies_per_gpu": len(mine), "nodes_total": int(total_nodes), "springs_total": int(total_springs),
+                      "l2": "inputs larger than L2: %.0f MB of half-edge records per GPU streamed every step" % (64.0 * total_springs / world / 1e6),
+                      "parallelism": "ensemble x%d, no collective" % world},
+           "clocks": clk,
+           "e2e": {"value": total_nodes * min(args.steps, 20) / t_e2e, "unit": "node-steps/s", "h2d_bytes_per_step": 0,
+                   "d2h_bytes_per_step": int(nodes * 80), "note": "state resident (the point of the ensemble kernel); every step's x, v, a read back"},
+           "gpu_launches": int(launches),
+           "roofline": {"kernel": "k_ensemble (spring phase)", "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+                        "traffic": None, "algorithmic_bytes_per_step_per_gpu": alg},
+           "cpu_baseline": cpu, "setup": {"build_bodies_s": setup_s}}
+    finish_line(out, dist)
+
+
+def run_c4_sharded(args, A, rank, world, local, dist):
+    """BASELINE config 4: one N ~ 1e6 body (+ a Mars-like point mass) split into particle slabs over the ranks; the only
+    exchange is the per-step pull of the other slabs' x and v through CUDA-IPC peer mappings (strong scaling)."""
+    cfg = dict(WORKLOADS["C4"])
+    if os.environ.get("ASS_C4_D"):
+        cfg["d"] = float(os.environ["ASS_C4_D"])
+    sim, p, springs, setup = build_body(A, cfg, cfg["omega"], with_point_mass=True)
+    n, ns = len(p), len(springs)
+    bounds = A.slab_bounds(n, world)
+    sim.shard_setup(rank, world, bounds)
+    handles = [None] * world
+    dist.all_gather_object(handles, sim.shard_export())
+    for q in range(world):
+        if q != rank:
+            sim.shard_import(q, handles[q])
+    dist.barrier()
+
+    def run(nsteps):
+        for s in range(nsteps):
+            sim.shard_begin()
+            dist.barrier()
+            sim.shard_exchange()
+            dist.barrier()
+            sim.shard_finish(pre_drift_next=(s < nsteps - 1))
+
+    run(args.warmup)
+    fp64_peak, _ = A.probe_fp64_peak(1 << 13)
+    sim.timing(True); sim.timing_reset()
+    clocks = ClockSampler(local)
+    dist.barrier()
+    launches0 = A.launch_count()
+    clocks.start()
+    sim.sync()
+    t0 = time.perf_counter()
+    run(args.steps)
+    sim.sync()
+    dist.barrier()
+    t_wall = max_over_ranks(dist, time.perf_counter() - t0, local)
+    clk = clocks.stop()
+    launches = A.launch_count() - launches0
+    kt = sim.timing_get()
+    sim.timing(False)
+    g_ms = max_over_ranks(dist, kt["gravity"][0], local)
+    value = n * args.steps / t_wall
+    # e2e: the sharded body's natural host interaction is a gather + download at print cadence; per step that is
+    # x, v of the own slab (the module's heartbeat) -- measured as one full download every step
+    host = np.zeros((n, 16))
+    dist.barrier()
+    t0 = time.perf_counter()
+    for s in range(min(args.steps, 3)):
+        sim.shard_begin(); dist.barrier(); sim.shard_exchange(); dist.barrier(); sim.shard_finish(False)
+        sim.download(host, A.F_POS | A.F_VEL | A.F_ACC)
+    dist.barrier()
+    t_e2e = max_over_ranks(dist, time.perf_counter() - t0, local)
+    if rank != 0:
+        return
+    pairs = float(n) * float(n) / world
+    ach = 20.0 * pairs * args.steps / (g_ms * 1e-3) / 1e12
+    out = {"metric": "node-steps/s", "value": value, "unit": "node-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": 1e3 * t_wall / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": "C4: %s, slabs over %d GPUs" % (cfg["desc"], world), "N": n, "NS": ns, "bounds": bounds,
+                      "exchange": "per step: pull of the other slabs' x and v (%.1f MB) over CUDA-IPC peer mappings, copy engines, overlapped with own-slab gravity; 2 host barriers" % (64e-6 * (n - (bounds[1] - bounds[0]))),
+                      "l2": "inputs larger than L2 (half-edges %.0f MB)" % (64e-6 * ns), "parallelism": "particle slabs x%d" % world},
+           "clocks": clk, "gpu_launches": int(launches),
+           "e2e": {"value": n * min(args.steps, 3) / t_e2e, "unit": "node-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": int(n * 80)},
+           "roofline": {"kernel": "k_gravity", "bound": "fp64", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach / fp64_peak, "traffic": None,
+                        "note": "per GPU: 20 flop x N x N/%d pairs per step over the gravity kernels' device time (max over ranks)" % world},
+           "cpu_baseline": None,
+           "kernel_ms": {k: {"ms": v[0], "launches": v[1]} for k, v in kt.items()}, "setup": setup}
+    finish_line(out, dist)
 
 
 def main():
@@ -276,7 +435,7 @@ def main():
     if name == "C5":
         return run_c5(args, A, rank, world, local, dist)
     if name == "C4" and world > 1:
-        raise SystemExit("workload C4 sharded over ranks needs the shard exchange, which this build does not carry yet")
+        return run_c4_sharded(args, A, rank, world, local, dist)
     cfg = dict(WORKLOADS[name])
     # ensemble member `rank`: spin rate swept across members (BASELINE config 5's sweep, applied to bodies of this size)
     omega = tuple(np.array(cfg["omega"]) * (1.0 + 0.1 * rank))

@@ -158,6 +158,40 @@ int ass_rand_ellipsoid(double** rows, int* cap_rows, int n0, double min_dist, do
 int ass_hcp_ellipsoid(double** rows, int* cap_rows, int n0, double min_dist, double a, double b, double c, double total_mass);
 int ass_cubic_ellipsoid(double** rows, int* cap_rows, int n0, double min_dist, double a, double b, double c, double total_mass);
 
+/* ---- ensembles: B independent small bodies, one CTA per body, no collective (BASELINE C5) ---- */
+typedef struct ass_ensemble ass_ensemble;
+/* Bodies are given concatenated: body b owns particle rows [node_off[b], node_off[b+1]) of `base` and springs
+ * [spring_off[b], spring_off[b+1]) whose particle indices are LOCAL to the body (0 .. n_b-1).  params[b] per body
+ * (dt, G, softening, gravity, additional_forces, heartbeat, n_perts, t).  A body must fit in shared memory (~2400 nodes);
+ * larger bodies use ass_sim.  The per-step arithmetic is that of ass_step, member by member. */
+int ass_ensemble_create(ass_ensemble** out, int n_bodies, const int* node_off, const int* spring_off,
+		const void* base, size_t stride_bytes, const ass_spring* springs, const ass_params* params);
+int ass_ensemble_set_params(ass_ensemble* e, const ass_params* params);
+/* reb_step x nsteps for every member in ONE launch; *device_ms (may be NULL) receives the CUDA-event time (synchronises). */
+int ass_ensemble_step(ass_ensemble* e, int nsteps, int with_heartbeat, double* device_ms);
+int ass_ensemble_download(ass_ensemble* e, void* base, size_t stride_bytes, unsigned fields);
+int ass_ensemble_get_params(ass_ensemble* e, ass_params* params);
+int ass_ensemble_sync(ass_ensemble* e);
+int ass_ensemble_destroy(ass_ensemble* e);
+
+/* ---- multi-GPU: ONE large body, particles split into contiguous slabs, one rank (process, GPU) per slab (SURVEY 8e,
+ *      BASELINE C4).  Every rank uploads the whole body and the whole spring list, then calls ass_shard_setup.  Rank g
+ *      integrates, and evaluates forces onto, particles [bounds[g], bounds[g+1]) only.  Per step every rank pulls the
+ *      other slabs' x and v through peer-mapped memory (CUDA IPC over NVLink) with the copy engines while its SMs
+ *      already run gravity against its own slab's sources -- the step's only exchange, the analogue of one all-gather.
+ *      The launcher owns two barriers per step (torch.distributed in bench.py):
+ *          ass_shard_begin -> barrier -> ass_shard_exchange -> barrier -> ass_shard_finish                        ---- */
+#define ASS_IPC_HANDLE_BYTES 64
+int ass_shard_setup(ass_sim* sim, int rank, int nranks, const int* bounds /* nranks + 1 */);
+int ass_shard_export(ass_sim* sim, unsigned char handle[ASS_IPC_HANDLE_BYTES]);
+int ass_shard_import(ass_sim* sim, int peer_rank, const unsigned char handle[ASS_IPC_HANDLE_BYTES]);
+/* same-process peers (several ass_sim in one process): share the pointer instead of an IPC handle */
+int ass_shard_import_local(ass_sim* sim, int peer_rank, ass_sim* peer);
+int ass_shard_begin(ass_sim* sim);                        /* part1 on the own slab (if not pre-drifted); synchronises */
+int ass_shard_exchange(ass_sim* sim);                     /* pulls + gravity(own-slab sources); returns when pulls landed */
+int ass_shard_finish(ass_sim* sim, int pre_drift_next);   /* gravity(remote sources), springs, part2 on the own slab */
+int ass_shard_gather(ass_sim* sim);                       /* bring every slab's x, v home (before a full download) */
+
 /* ---- measurement ---- */
 /* Kernel classes for the per-kernel CUDA-event timers */
 enum { ASS_K_GRAVITY = 0, ASS_K_SPRINGS = 1, ASS_K_LEAPFROG = 2, ASS_K_REDUCE = 3, ASS_K_CONNECT = 4, ASS_K_XFER = 5, ASS_K_COUNT = 6 };
