@@ -180,6 +180,10 @@ class Sim:
     def gravity_basic(self):
         _chk(lib().ass_gravity_basic(self._h))
 
+    def set_gravity_kernel(self, which):
+        """0 = by size (default), 1 = one-sided source tiles, 2 = pair-once (Newton's third law)."""
+        _chk(lib().ass_set_gravity_kernel(self._h, C.c_int(int(which))))
+
     def leapfrog_part1(self):
         _chk(lib().ass_leapfrog_part1(self._h))
 

@@ -88,6 +88,8 @@ struct ass_sim {
 	bool have_state = false;
 	bool predrifted = false;  // positions already carry the next step's first half-drift (fused loop only)
 	bool sum_sequential = true;  // CoM / CoV sums in the reference's particle order (bit-exact) or as a parallel tree
+	int gravity_kernel = 0;      // 0 auto, 1 one-sided tiles (gravity.cu), 2 pair-once (gravity_sym.cu)
+	struct SymPlan* sym_plan = nullptr;  // CTA table + scratch rows of the pair-once kernel
 
 	// springs, node-sorted
 	HalfEdge* he = nullptr;
@@ -118,6 +120,10 @@ struct ass_sim {
 };
 
 void ass_shard_release(ass_sim* s);  // shard.cu
+// gravity_sym.cu
+void ass_sym_plan_free(struct SymPlan* p);
+bool ass_gravity_sym_applicable(int count);
+int ass_launch_gravity_sym(ass_sim* s, int lo, int hi);
 int ass_buf_reserve(DevBuf& b, size_t bytes);
 int ass_ensure_device(void);
 int ass_sm_count(void);

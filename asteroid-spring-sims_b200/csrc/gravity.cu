@@ -252,12 +252,21 @@ int ass_launch_gravity(ass_sim* s) {
 	const int n = s->n;
 	if (n == 0) return ASS_OK;
 	const int n_src = (s->prm.n_active == -1) ? n : std::max(0, std::min(s->prm.n_active, n));
+	// every particle both source and target: each unordered pair can be evaluated once (gravity_sym.cu)
+	if (n_src == n && s->gravity_kernel != 1 && (s->gravity_kernel == 2 || ass_gravity_sym_applicable(n))) return ass_launch_gravity_sym(s, 0, n);
 	const int rows = ass_gravity_rows(n, n_src);
 	int rc = ass_buf_reserve(s->grav_partial, sizeof(vec4d) * (size_t) std::max(rows, 1) * (size_t) n);
 	if (rc) return rc;
 	int used = 0;
 	if ((rc = ass_launch_gravity_partial(s, s->posm, 0, n_src, 0, n, 0, &used))) return rc;
 	return ass_launch_gravity_reduce(s, 0, n, used);
+}
+
+extern "C" int ass_set_gravity_kernel(ass_sim* s, int which) {
+	REQUIRE(s, ASS_EINVAL, "null sim");
+	REQUIRE(which >= 0 && which <= 2, ASS_EINVAL, "0 = auto, 1 = one-sided tiles, 2 = pair-once");
+	s->gravity_kernel = which;
+	return ASS_OK;
 }
 
 extern "C" int ass_gravity_basic(ass_sim* s) {

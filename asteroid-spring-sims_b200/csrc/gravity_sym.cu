@@ -1,0 +1,255 @@
+// gravity_sym.cu -- REB_GRAVITY_BASIC (reference src/gravity.c:72-103) with every unordered pair evaluated ONCE.
+//
+// The reference's double loop computes pair (i,j) and pair (j,i) separately; they share everything but the mass factor
+// and the sign (Newton's third law).  Evaluating the pair once and applying it to both particles costs
+//     3 DADD (d) + 3 DFMA (r^2) + 5 (rsqrt refinement) + 2 DMUL (y^3) + 2 DMUL (y^3 m_r, y^3 m_s) + 6 DFMA (both sides)
+//   = 21 FP64 instructions per unordered pair = 10.5 per ordered pair, against 17 in the one-sided kernel (gravity.cu),
+// i.e. against SURVEY 8d's 20 flop per ordered pair the ceiling moves from 59 % to 95 % of the DFMA peak.
+//
+// Layout of the computation (all deterministic, no atomics):
+//   * particles are cut into blocks of P = 1024.  A CTA keeps ONE block "resident" in registers (4 particles per
+//     thread: position, mass, accumulator) and streams other blocks past it through shared memory.
+//   * a warp takes 32 streamed particles at a time and runs a 32-step systolic rotation: at step s lane l meets streamed
+//     particle (l+s) mod 32 -- its position comes from shared memory (conflict-free, every lane a different particle),
+//     its accumulator travels from lane to lane by shuffle -- and evaluates the 4 pairs with its residents.  After 32
+//     steps every resident of the warp has met every streamed particle of the chunk, each pair exactly once.
+//   * streamed-side sums are folded over the CTA's 8 warps in shared memory (fixed order) and written to a scratch row
+//     owned by the tile (resident block, streamed block); resident-side sums go to a scratch row owned by the CTA.
+//     k_gravity_sym_reduce adds, for every particle, its rows in a fixed order and applies -G.
+//   * tiles: strictly-lower-triangle pairs of blocks are symmetric; the diagonal tile (a block against itself) is
+//     evaluated one-sided with the self pair masked.  CTAs take runs of at most U tiles of one resident block; the
+//     block scheduler balances them (thousands of equal-size CTAs).
+// Scratch: N^2/(2P) x 24 B for the streamed side (110 MB at N = 1e5, 11 GB at N = 1e6 -- HBM is 180 GB and the rows are
+// written and read once per evaluation: < 2 % of the kernel's time).
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int SG_T = 256;            // threads per CTA
+constexpr int SG_W = SG_T / 32;      // warps
+constexpr int SG_R = 4;              // resident particles per thread
+constexpr int SG_P = SG_T * SG_R;    // particles per block (1024)
+constexpr int SG_TILE = 128;         // streamed particles between block-wide reductions (4 chunks of 32)
+
+struct SymCta {
+	int rb, s0, s1;  // resident block, streamed blocks [s0, s1); a streamed block equal to rb is the diagonal tile
+};
+
+__device__ __forceinline__ vec4d load_or_dummy(const vec4d* __restrict__ posm, int idx, int hi) {
+	if (idx < hi) return posm[idx];
+	vec4d p;  // massless, far away, distinct from every other dummy: contributes exactly 0 to real particles
+	p.x = 1.0e8 + (double) idx; p.y = 1.0e8; p.z = 1.0e8; p.w = 0.0;
+	return p;
+}
+
+template <bool DIAG>
+__device__ __forceinline__ void meet(const double2 xy, const double2 zm, int sidx, const double (&rx)[SG_R], const double (&ry)[SG_R],
+		const double (&rz)[SG_R], const double (&rm)[SG_R], const int (&ridx)[SG_R], double (&rax)[SG_R], double (&ray)[SG_R],
+		double (&raz)[SG_R], double& sax, double& say, double& saz, double soft2) {
+#pragma unroll
+	for (int k = 0; k < SG_R; k++) {
+		const double dx = xy.x - rx[k], dy = xy.y - ry[k], dz = zm.x - rz[k];  // d = x_streamed - x_resident
+		double r2 = fma(dz, dz, fma(dy, dy, fma(dx, dx, soft2)));
+		if (DIAG) r2 = (sidx == ridx[k]) ? 1.0 : r2;  // self pair: d == 0, contributes exactly 0
+		const double y = fast_rsqrt(r2);
+		const double y3 = (y * y) * y;
+		const double ts = y3 * zm.y;  // streamed mass -> acts on the resident
+		rax[k] = fma(ts, dx, rax[k]);  // S_r = sum m_s y^3 (x_s - x_r)  [a_r = +G S_r]
+		ray[k] = fma(ts, dy, ray[k]);
+		raz[k] = fma(ts, dz, raz[k]);
+		if (!DIAG) {
+			const double tr = y3 * rm[k];  // resident mass -> acts on the streamed particle
+			sax = fma(tr, dx, sax);        // S_s = sum m_r y^3 (x_s - x_r)  [a_s = -G S_s]
+			say = fma(tr, dy, say);
+			saz = fma(tr, dz, saz);
+		}
+	}
+}
+
+__global__ void __launch_bounds__(SG_T, 2) k_gravity_sym(const vec4d* __restrict__ posm, int lo, int hi, const SymCta* __restrict__ ctas,
+		double soft2, double* __restrict__ res, size_t res_plane, double* __restrict__ str, size_t str_plane) {
+	__shared__ double2 s_xy[SG_TILE], s_zm[SG_TILE];
+	__shared__ double s_acc[SG_W][3][SG_TILE];
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const SymCta C = ctas[blockIdx.x];
+
+	double rx[SG_R], ry[SG_R], rz[SG_R], rm[SG_R], rax[SG_R], ray[SG_R], raz[SG_R];
+	int ridx[SG_R];
+#pragma unroll
+	for (int k = 0; k < SG_R; k++) {
+		ridx[k] = lo + C.rb * SG_P + tid + k * SG_T;
+		const vec4d p = load_or_dummy(posm, ridx[k], hi);
+		rx[k] = p.x; ry[k] = p.y; rz[k] = p.z; rm[k] = p.w;
+		rax[k] = 0.0; ray[k] = 0.0; raz[k] = 0.0;
+	}
+
+	for (int sb = C.s0; sb < C.s1; sb++) {
+		const bool diag = (sb == C.rb);
+		const int sbase = lo + sb * SG_P;
+		const size_t tile_row = ((size_t) C.rb * (size_t) (C.rb - 1) / 2 + (size_t) sb) * (size_t) SG_P;  // strict lower triangle
+		for (int t0 = 0; t0 < SG_P; t0 += SG_TILE) {
+			vec4d mine;
+			if (tid < SG_TILE) mine = load_or_dummy(posm, sbase + t0 + tid, hi);
+			__syncthreads();  // the previous tile's fold has finished reading s_acc / nobody still reads s_xy
+			if (tid < SG_TILE) {
+				s_xy[tid] = make_double2(mine.x, mine.y);
+				s_zm[tid] = make_double2(mine.z, mine.w);
+			}
+			__syncthreads();
+			if (sbase + t0 >= hi) continue;  // a tile of pure padding (uniform across the CTA)
+#pragma unroll 1
+			for (int c0 = 0; c0 < SG_TILE; c0 += 32) {
+				double sax = 0.0, say = 0.0, saz = 0.0;
+				if (diag) {
+#pragma unroll 2
+					for (int s = 0; s < 32; s++) {
+						const int q = c0 + ((lane + s) & 31);
+						meet<true>(s_xy[q], s_zm[q], sbase + t0 + q, rx, ry, rz, rm, ridx, rax, ray, raz, sax, say, saz, soft2);
+					}
+				} else {
+#pragma unroll 2
+					for (int s = 0; s < 32; s++) {
+						const int q = c0 + ((lane + s) & 31);
+						meet<false>(s_xy[q], s_zm[q], 0, rx, ry, rz, rm, ridx, rax, ray, raz, sax, say, saz, soft2);
+						// the streamed particle moves on to the lane below; take over the one from the lane above
+						sax = __shfl_sync(0xffffffffu, sax, (lane + 1) & 31);
+						say = __shfl_sync(0xffffffffu, say, (lane + 1) & 31);
+						saz = __shfl_sync(0xffffffffu, saz, (lane + 1) & 31);
+					}
+					// after 32 steps lane l holds the sums of streamed particle c0 + l again
+					s_acc[warp][0][c0 + lane] = sax;
+					s_acc[warp][1][c0 + lane] = say;
+					s_acc[warp][2][c0 + lane] = saz;
+				}
+			}
+			if (!diag) {
+				__syncthreads();
+				for (int v = tid; v < 3 * SG_TILE; v += SG_T) {
+					const int comp = v / SG_TILE, q = v - comp * SG_TILE;
+					double a = s_acc[0][comp][q];
+#pragma unroll
+					for (int w = 1; w < SG_W; w++) a += s_acc[w][comp][q];
+					str[(size_t) comp * str_plane + tile_row + (size_t) (t0 + q)] = a;
+				}
+			}
+		}
+	}
+#pragma unroll
+	for (int k = 0; k < SG_R; k++) {
+		const size_t at = (size_t) blockIdx.x * SG_P + (size_t) (tid + k * SG_T);
+		res[at] = rax[k];
+		res[res_plane + at] = ray[k];
+		res[2 * res_plane + at] = raz[k];
+	}
+}
+
+// a_i = G * (resident rows) - G * (streamed rows), rows added in a fixed order.  be[2b], be[2b+1] = the CTAs whose
+// resident block is b.
+__global__ void k_gravity_sym_reduce(const double* __restrict__ res, size_t res_plane, const double* __restrict__ str, size_t str_plane,
+		const int* __restrict__ be, int nb, int lo, int hi, double G, vec4d* __restrict__ acc) {
+	const int i = lo + blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= hi) return;
+	const int b = (i - lo) / SG_P, o = (i - lo) - b * SG_P;
+	double rs[3] = { 0.0, 0.0, 0.0 }, ss[3] = { 0.0, 0.0, 0.0 };
+	for (int c = be[2 * b]; c < be[2 * b + 1]; c++) {
+		const size_t at = (size_t) c * SG_P + o;
+		rs[0] += res[at]; rs[1] += res[res_plane + at]; rs[2] += res[2 * res_plane + at];
+	}
+	for (int rb = b + 1; rb < nb; rb++) {
+		const size_t at = ((size_t) rb * (size_t) (rb - 1) / 2 + (size_t) b) * SG_P + o;
+		ss[0] += str[at]; ss[1] += str[str_plane + at]; ss[2] += str[2 * str_plane + at];
+	}
+	vec4d a;
+	a.x = G * (rs[0] - ss[0]); a.y = G * (rs[1] - ss[1]); a.z = G * (rs[2] - ss[2]); a.w = 0.0;
+	acc[i] = a;
+}
+
+}  // namespace
+
+struct SymPlan {
+	int lo = -1, hi = -1, nb = 0, n_cta = 0;
+	size_t n_tiles = 0;
+	SymCta* d_ctas = nullptr;
+	int* d_cta_begin = nullptr;
+	double *d_res = nullptr, *d_str = nullptr;
+	size_t res_plane = 0, str_plane = 0;
+};
+
+void ass_sym_plan_free(SymPlan* p) {
+	if (!p) return;
+	cudaFree(p->d_ctas); cudaFree(p->d_cta_begin); cudaFree(p->d_res); cudaFree(p->d_str);
+	delete p;
+}
+
+// Is the pair-once kernel worth it for this many particles?  It needs enough tiles to fill the machine.
+bool ass_gravity_sym_applicable(int count) {
+	const long long nb = (count + SG_P - 1) / SG_P;
+	return nb * (nb + 1) / 2 >= 4LL * ass_sm_count();
+}
+
+static int build_plan(ass_sim* s, int lo, int hi) {
+	SymPlan*& plan = s->sym_plan;
+	if (plan && plan->lo == lo && plan->hi == hi) return ASS_OK;
+	ass_sym_plan_free(plan);
+	plan = new SymPlan();
+	plan->lo = lo; plan->hi = hi;
+	const int nb = (hi - lo + SG_P - 1) / SG_P;
+	plan->nb = nb;
+	const long long tiles = (long long) nb * (nb + 1) / 2;
+	// tiles per CTA: enough CTAs (>= ~16 per resident slot) for the block scheduler to balance, few enough rows
+	const long long slots = 2LL * ass_sm_count();
+	int U = (int) std::max(1LL, tiles / (slots * 16));
+	std::vector<std::vector<SymCta>> per_block(nb);
+	for (int rb = 0; rb < nb; rb++)
+		for (int s0 = 0; s0 <= rb; s0 += U) per_block[rb].push_back({ rb, s0, std::min(s0 + U, rb + 1) });
+	// CTAs of one resident block stay contiguous (the reduction walks cta_begin[b] .. cta_begin[b+1]); big blocks first
+	std::vector<SymCta> ctas;
+	std::vector<int> begin(nb + 1, 0);
+	std::vector<int> order(nb);
+	for (int b = 0; b < nb; b++) order[b] = nb - 1 - b;
+	std::vector<int> start_of(nb, 0), count_of(nb, 0);
+	for (int b : order) {
+		start_of[b] = (int) ctas.size();
+		count_of[b] = (int) per_block[b].size();
+		ctas.insert(ctas.end(), per_block[b].begin(), per_block[b].end());
+	}
+	// cta_begin must be indexable by block: store [begin, end) pairs
+	std::vector<int> be((size_t) 2 * nb);
+	for (int b = 0; b < nb; b++) { be[2 * b] = start_of[b]; be[2 * b + 1] = start_of[b] + count_of[b]; }
+	plan->n_cta = (int) ctas.size();
+	plan->n_tiles = (size_t) nb * (size_t) (nb - 1) / 2;
+	plan->res_plane = (size_t) plan->n_cta * SG_P;
+	plan->str_plane = std::max<size_t>(plan->n_tiles, 1) * SG_P;
+	if (cudaMalloc(&plan->d_ctas, sizeof(SymCta) * ctas.size()) != cudaSuccess || cudaMalloc(&plan->d_cta_begin, sizeof(int) * be.size()) != cudaSuccess ||
+	    cudaMalloc(&plan->d_res, sizeof(double) * 3 * plan->res_plane) != cudaSuccess || cudaMalloc(&plan->d_str, sizeof(double) * 3 * plan->str_plane) != cudaSuccess) {
+		cudaGetLastError();
+		ass_set_error("pair-once gravity: out of device memory for %zu scratch bytes", sizeof(double) * 3 * (plan->res_plane + plan->str_plane));
+		ass_sym_plan_free(plan);
+		plan = nullptr;
+		return ASS_ENOMEM;
+	}
+	CU_TRY(cudaMemcpyAsync(plan->d_ctas, ctas.data(), sizeof(SymCta) * ctas.size(), cudaMemcpyHostToDevice, s->stream));
+	CU_TRY(cudaMemcpyAsync(plan->d_cta_begin, be.data(), sizeof(int) * be.size(), cudaMemcpyHostToDevice, s->stream));
+	CU_TRY(cudaStreamSynchronize(s->stream));
+	return ASS_OK;
+}
+
+// a = gravity among particles [lo, hi) (every particle both source and target), pair-once
+int ass_launch_gravity_sym(ass_sim* s, int lo, int hi) {
+	if (hi - lo <= 0) return ASS_OK;
+	int rc = build_plan(s, lo, hi);
+	if (rc) return rc;
+	SymPlan* p = s->sym_plan;
+	const double soft2 = s->prm.softening * s->prm.softening;
+	ass_tic(s, ASS_K_GRAVITY);
+	k_gravity_sym<<<p->n_cta, SG_T, 0, s->stream>>>(s->posm, lo, hi, p->d_ctas, soft2, p->d_res, p->res_plane, p->d_str, p->str_plane);
+	LAUNCH_CHECK();
+	k_gravity_sym_reduce<<<(hi - lo + 255) / 256, 256, 0, s->stream>>>(p->d_res, p->res_plane, p->d_str, p->str_plane, p->d_cta_begin, p->nb, lo, hi,
+			s->prm.G, s->acc);
+	LAUNCH_CHECK();
+	ass_toc(s, ASS_K_GRAVITY);
+	return ASS_OK;
+}

@@ -232,6 +232,7 @@ extern "C" int ass_destroy(ass_sim* s) {
 	ass_ensure_device();
 	if (s->stream) cudaStreamSynchronize(s->stream);
 	ass_shard_release(s);  // a sharded simulation's posm / vel alias its exported window
+	ass_sym_plan_free(s->sym_plan);
 	cudaFree(s->posm); cudaFree(s->vel); cudaFree(s->acc); cudaFree(s->posm_alt); cudaFree(s->vel_alt);
 	cudaFree(s->he); cudaFree(s->row_ptr); cudaFree(s->slot);
 	cudaFree(s->stage.p); cudaFree(s->grav_partial.p); cudaFree(s->red_partial.p); cudaFree(s->flush.p);

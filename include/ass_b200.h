@@ -110,6 +110,10 @@ int ass_zero_accel(ass_sim* sim);     /* zero_accel, src_spring/physics.cpp:557-
 int ass_spring_forces(ass_sim* sim);  /* spring_forces, src_spring/springs.cpp:288-346: a += springs */
 int ass_gravity_basic(ass_sim* sim);  /* reb_calculate_acceleration, REB_GRAVITY_BASIC, src/gravity.c:72-103: a = gravity.
                                          With params.gravity == 0 this is the NONE branch: a no-op. */
+/* Which kernel evaluates the direct sum: 0 = choose by size (default), 1 = one-sided source tiles (17 FP64 instructions
+ * per ordered pair), 2 = pair-once / Newton's third law (10.5 per ordered pair; needs N_active == N). Same result to
+ * rounding; both deterministic. */
+int ass_set_gravity_kernel(ass_sim* sim, int which);
 int ass_leapfrog_part1(ass_sim* sim); /* reb_integrator_leapfrog_part1, src/integrator_leapfrog.c:39-51 */
 int ass_leapfrog_part2(ass_sim* sim); /* reb_integrator_leapfrog_part2, src/integrator_leapfrog.c:52-67 */
 /* reb_step (src/rebound.c:69-144) x nsteps with the built-in additional_forces of params.additional_forces, fused
