@@ -22,12 +22,16 @@ struct __align__(32) vec4d {
 	double x, y, z, w;
 };
 
-struct __align__(32) HalfEdge {
-	double k, rs0, gamma;
+// One endpoint's view of a spring, 16 bytes: the rest length, the other endpoint, and an index into the palette of
+// distinct (k, gamma) pairs.  A body has a handful of distinct pairs (set_gamma makes gamma uniform, adjust_spring_props
+// paints a few radial shells), so two half-edges cost 32 B per spring -- exactly sizeof(struct spring), the algorithmic
+// figure of SURVEY 8d -- although every spring is stored at both of its endpoints.  Lossless for any number of pairs.
+struct __align__(16) HalfEdge {
+	double rs0;
 	int nbr;  // the other endpoint
-	int sid;  // index in the caller's spring list
+	int pal;  // index into the (k, gamma) palette
 };
-static_assert(sizeof(HalfEdge) == 32, "HalfEdge must be one sector");
+static_assert(sizeof(HalfEdge) == 16, "HalfEdge must be 16 bytes");
 static_assert(sizeof(ass_spring) == 32, "ass_spring must match struct spring (32 B)");
 
 #define ASS_L_EPS 1e-6  // src_spring/springs.cpp:28
@@ -95,7 +99,9 @@ struct ass_sim {
 	HalfEdge* he = nullptr;
 	int* row_ptr = nullptr;   // n+1
 	int* slot = nullptr;      // 2*ns: half-edge slot of (spring s, endpoint e)
-	size_t he_cap = 0, row_cap = 0;
+	double2* pal = nullptr;   // palette of distinct (k, gamma) pairs
+	int n_pal = 0;
+	size_t he_cap = 0, row_cap = 0, pal_cap = 0;
 	int max_degree = 0;
 
 	// scratch
@@ -203,6 +209,32 @@ __device__ __forceinline__ double fast_rsqrt(double a) {
 	const double p = fma(0.375, eps, 0.5);
 	const double q = eps * p;
 	return fma(y, q, y);
+}
+
+// ---- bulk-copy engine (TMA, 1-D, no tensor map) + mbarrier: global -> shared staging with completion by byte count ----
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t) __cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
+	asm volatile(
+		"{\n\t"
+		".reg .pred p;\n\t"
+		"WAIT_%=:\n\t"
+		"mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+		"@p bra DONE_%=;\n\t"
+		"bra WAIT_%=;\n\t"
+		"DONE_%=:\n\t"
+		"}" ::"r"(smem_u32(bar)), "r"(phase) : "memory");
+}
+// size and both addresses must be multiples of 16 bytes
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+			"l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
 __device__ __forceinline__ double shfl_xor_d(double v, int mask, int width = 32) {

@@ -1,21 +1,28 @@
 // ensemble.cu -- B independent small bodies (spin-rate / material sweeps, BASELINE config 5: 4096 x ~1k nodes).
 //
-// The members never interact, so there is nothing to exchange: one CTA owns one body for a whole batch of steps.
-// The body's node state (posm, vel, acc: 96 B/node, ~100 KB for 1065 nodes) lives in shared memory for the batch;
-// only the half-edge records (2 x 32 B per spring, ~0.9 MB per body) are streamed from HBM/L2 each step, so a step
-// costs one pass over the spring data and no launch.  Per step inside the kernel:
-//     part1 | [gravity: all pairs in shared memory] | springs (same arithmetic and lane order as springs.cu, so a member
-//     gets the bits the single-body path would give it) | kick + drift (+ next part1) | [center_sim]
-// with __syncthreads between the phases.  Across GPUs the members are dealt round-robin by the host launcher; no
-// collective is involved.
+// The members never interact, so there is nothing to exchange: one CTA owns one body for a whole batch of steps
+// ("body in shared memory, springs streamed").
+//   * node positions and velocities (64 B/node, 68 KB for 1065 nodes) and the CSR row offsets live in shared memory for
+//     the whole batch; accelerations go through global memory (written once, read once per step, L2-resident);
+//   * the half-edge records (2 x 16 B per spring, ~445 KB per body) are streamed every step by the bulk-copy engine
+//     (cp.async.bulk -> mbarrier, SASS UBLKCP): nodes are processed in waves of 64 (one node per 8-lane group), the
+//     records of a wave are one contiguous run of the node-sorted array, and the run of wave w+2 is in flight while wave
+//     w is being evaluated (two-deep ring).  So inside the spring phase every operand comes from shared memory and the
+//     dependent chain "row offset -> record -> endpoint gather" costs shared-memory latencies, not HBM ones;
+//   * per step:  part1 | [gravity: all pairs out of shared memory] | springs (same arithmetic and lane order as springs.cu,
+//     so a member gets the bits the single-body path would give it) | kick + drift (+ next part1) | [center_sim].
+// Across GPUs the members are dealt round-robin by the host launcher; no collective is involved.
 #include <algorithm>
+#include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "spring_math.cuh"
 
 namespace {
 
-constexpr int ET = 512;  // threads per CTA (64 node groups)
+constexpr int ET = 1024;                       // threads per CTA: one body owns a whole SM
+constexpr int EW = ET / SPRING_LANES;          // nodes per wave (64)
 
 struct BodyDesc {
 	int node_off, n, row_off, n_perts;
@@ -23,48 +30,87 @@ struct BodyDesc {
 	int gravity, af, heartbeat, pad;
 };
 
-__global__ void __launch_bounds__(ET, 2) k_ensemble(const BodyDesc* __restrict__ desc, vec4d* __restrict__ posm_g, vec4d* __restrict__ vel_g,
-		vec4d* __restrict__ acc_g, const int* __restrict__ row_ptr, const HalfEdge* __restrict__ he, int nsteps, int with_hb) {
-	extern __shared__ __align__(32) unsigned char smem_raw[];
+// endpoint state out of shared memory (see the layout note in k_ensemble)
+struct SharedNodes {
+	const double2 *xy, *zm, *vxy, *vz0;
+	__device__ __forceinline__ vec4d pos(int i) const { const double2 a = xy[i], b = zm[i]; vec4d p; p.x = a.x; p.y = a.y; p.z = b.x; p.w = b.y; return p; }
+	__device__ __forceinline__ vec4d velocity(int i) const { const double2 a = vxy[i], b = vz0[i]; vec4d v; v.x = a.x; v.y = a.y; v.z = b.x; v.w = 0.0; return v; }
+};
+
+__global__ void __launch_bounds__(ET, 1) k_ensemble(const BodyDesc* __restrict__ desc, vec4d* __restrict__ posm_g, vec4d* __restrict__ vel_g,
+		vec4d* __restrict__ acc_g, const int* __restrict__ row_ptr, const HalfEdge* __restrict__ he, const double2* __restrict__ pal, int nsteps,
+		int with_hb, int max_n, int ring_records) {
+	extern __shared__ __align__(128) unsigned char smem_raw[];
 	__shared__ double red[ET / 32][4];
 	__shared__ double com[4];
+	__shared__ __align__(8) uint64_t full[2];
 	const BodyDesc B = desc[blockIdx.x];
 	const int n = B.n, tid = threadIdx.x;
-	vec4d* sp = (vec4d*) smem_raw;
-	vec4d* sv = sp + n;
-	vec4d* sa = sv + n;
+	// carve: ring[2][ring_records] | xy | zm | vxy | vz0 (16-byte entries) | srow[max_n + 1]
+	// Node state is kept as four arrays of 16-byte pairs rather than 32-byte vectors: a random gather of 32-byte
+	// entries starts on only four distinct bank groups (8-way conflicts); 16-byte entries start on eight and tile all 32 banks.
+	HalfEdge* ring = (HalfEdge*) smem_raw;
+	double2* s_xy = (double2*) (ring + 2 * (size_t) ring_records);
+	double2* s_zm = s_xy + max_n;
+	double2* s_vxy = s_zm + max_n;
+	double2* s_vz0 = s_vxy + max_n;
+	int* srow = (int*) (s_vz0 + max_n);
+	vec4d* acc = acc_g + B.node_off;
+	auto ldp = [&](int i) { const double2 a = s_xy[i], b = s_zm[i]; vec4d p; p.x = a.x; p.y = a.y; p.z = b.x; p.w = b.y; return p; };
+	auto ldv = [&](int i) { const double2 a = s_vxy[i], b = s_vz0[i]; vec4d v; v.x = a.x; v.y = a.y; v.z = b.x; v.w = 0.0; return v; };
+	auto stp = [&](int i, const vec4d p) { s_xy[i] = make_double2(p.x, p.y); s_zm[i] = make_double2(p.z, p.w); };
+	auto stv = [&](int i, const vec4d v) { s_vxy[i] = make_double2(v.x, v.y); s_vz0[i] = make_double2(v.z, 0.0); };
+	const SharedNodes nodes{ s_xy, s_zm, s_vxy, s_vz0 };
 	for (int i = tid; i < n; i += ET) {
-		sp[i] = posm_g[B.node_off + i];
-		sv[i] = vel_g[B.node_off + i];
-		sa[i] = acc_g[B.node_off + i];
+		stp(i, posm_g[B.node_off + i]);
+		stv(i, vel_g[B.node_off + i]);
+	}
+	for (int i = tid; i <= n; i += ET) srow[i] = row_ptr[B.row_off + i];
+	if (tid == 0) {
+		mbar_init(&full[0], 1);
+		mbar_init(&full[1], 1);
+		mbar_fence_init();
 	}
 	__syncthreads();
-	const int* row = row_ptr + B.row_off;
 	const double dt = B.dt, h = __dmul_rn(0.5, dt);
 	const bool hb = with_hb && B.heartbeat == 1;
-	const bool have_springs = B.af != 0;
+	const bool have_springs = B.af != 0 && srow[n] > srow[0];
 	const bool grav = B.gravity == 1 && B.af != 2;
 	const int lane = tid & (SPRING_LANES - 1), group = tid / SPRING_LANES;
+	const int nw = (n + EW - 1) / EW;
+	const int total_waves = have_springs ? nsteps * nw : 0;
+	// records of wave c (counted over all steps of the batch) -> ring buffer c & 1
+	auto issue = [&](int c) {  // thread 0 only
+		const int w = c % nw;
+		const int e0 = srow[w * EW], e1 = srow[min(n, (w + 1) * EW)];
+		const uint32_t bytes = (uint32_t) (e1 - e0) * (uint32_t) sizeof(HalfEdge);
+		mbar_expect_tx(&full[c & 1], bytes);
+		if (bytes) bulk_g2s(ring + (size_t) (c & 1) * ring_records, he + e0, bytes, &full[c & 1]);
+	};
+	if (tid == 0) {
+		if (total_waves > 0) issue(0);
+		if (total_waves > 1) issue(1);
+	}
 	bool predrifted = false;
 	for (int step = 0; step < nsteps; step++) {
 		const bool last = step == nsteps - 1;
 		if (!predrifted) {  // reb_integrator_leapfrog_part1, integrator_leapfrog.c:44-48
 			for (int i = tid; i < n; i += ET) {
-				vec4d p = sp[i];
-				const vec4d v = sv[i];
+				vec4d p = ldp(i);
+				const vec4d v = ldv(i);
 				p.x = __dadd_rn(p.x, __dmul_rn(h, v.x));
 				p.y = __dadd_rn(p.y, __dmul_rn(h, v.y));
 				p.z = __dadd_rn(p.z, __dmul_rn(h, v.z));
-				sp[i] = p;
+				stp(i, p);
 			}
 			__syncthreads();
 		}
 		if (grav) {  // REB_GRAVITY_BASIC, gravity.c:72-103, all pairs out of shared memory
 			for (int i = tid; i < n; i += ET) {
-				const vec4d pi = sp[i];
+				const vec4d pi = ldp(i);
 				double ax = 0.0, ay = 0.0, az = 0.0;
 				for (int j = 0; j < n; j++) {
-					const vec4d pj = sp[j];
+					const vec4d pj = ldp(j);
 					const double dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
 					double r2 = fma(dz, dz, fma(dy, dy, fma(dx, dx, B.soft2)));
 					r2 = (j == i) ? 1.0 : r2;
@@ -74,37 +120,44 @@ __global__ void __launch_bounds__(ET, 2) k_ensemble(const BodyDesc* __restrict__
 				}
 				vec4d a;
 				a.x = B.negG * ax; a.y = B.negG * ay; a.z = B.negG * az; a.w = 0.0;
-				sa[i] = a;
+				acc[i] = a;
 			}
-			__syncthreads();
+			__syncthreads();  // also orders the global acc writes before the spring phase's reads (same CTA)
 		}
-		if (have_springs) {  // spring_forces (+ zero_accel when af == 2)
-			for (int base = 0; base < n; base += ET / SPRING_LANES) {
-				const int gid = base + group;
+		if (have_springs) {  // spring_forces (+ zero_accel when af == 2), one wave of 64 nodes at a time
+			for (int w = 0; w < nw; w++) {
+				const int c = step * nw + w;
+				mbar_wait(&full[c & 1], (uint32_t) ((c >> 1) & 1));
+				const int gid = w * EW + group;
 				const bool live = gid < n;
 				const int node = live ? gid : n - 1;
-				const vec4d pi = sp[node], vi = sv[node];
-				const int beg = row[node], end = live ? row[node + 1] : beg;
-				const Force3 f = node_spring_sum(he, beg, end, lane, pi, vi, sp, sv);
+				const vec4d pi = ldp(node), vi = ldv(node);
+				const int beg = srow[node], end = live ? srow[node + 1] : beg;
+				// the ring buffer holds records [srow[w*EW], ...): index it with global record numbers
+				const HalfEdge* wave_he = ring + (size_t) (c & 1) * ring_records - srow[w * EW];
+				const Force3 f = node_spring_sum(wave_he, pal, beg, end, lane, pi, vi, nodes);
 				if (live && lane == 0) {
 					const double inv_m = (end > beg) ? fast_rcp(pi.w) : 0.0;
 					vec4d a;
 					if (B.af == 2) { a.x = 0.0; a.y = 0.0; a.z = 0.0; a.w = 0.0; }
-					else a = sa[node];
+					else a = acc[node];
 					a.x = fma(f.x, inv_m, a.x);
 					a.y = fma(f.y, inv_m, a.y);
 					a.z = fma(f.z, inv_m, a.z);
-					sa[node] = a;
+					acc[node] = a;
 				}
+				__syncthreads();  // everyone is done with ring buffer c & 1 (and, after the last wave, with sp / sv)
+				if (tid == 0 && c + 2 < total_waves) issue(c + 2);
 			}
-		} else if (B.af == 2) {
-			for (int i = tid; i < n; i += ET) { vec4d z; z.x = 0; z.y = 0; z.z = 0; z.w = 0; sa[i] = z; }
+		} else {
+			if (B.af == 2)
+				for (int i = tid; i < n; i += ET) { vec4d z; z.x = 0; z.y = 0; z.z = 0; z.w = 0; acc[i] = z; }
+			__syncthreads();
 		}
-		__syncthreads();  // every neighbour read of sp/sv is done before anyone moves
 		const bool pre = !last && !hb;
 		for (int i = tid; i < n; i += ET) {  // reb_integrator_leapfrog_part2, integrator_leapfrog.c:57-63
-			vec4d p = sp[i], v = sv[i];
-			const vec4d a = sa[i];
+			vec4d p = ldp(i), v = ldv(i);
+			const vec4d a = acc[i];
 			v.x = __dadd_rn(v.x, __dmul_rn(dt, a.x));
 			v.y = __dadd_rn(v.y, __dmul_rn(dt, a.y));
 			v.z = __dadd_rn(v.z, __dmul_rn(dt, a.z));
@@ -116,8 +169,8 @@ __global__ void __launch_bounds__(ET, 2) k_ensemble(const BodyDesc* __restrict__
 				p.y = __dadd_rn(p.y, __dmul_rn(h, v.y));
 				p.z = __dadd_rn(p.z, __dmul_rn(h, v.z));
 			}
-			sv[i] = v;
-			sp[i] = p;
+			stv(i, v);
+			stp(i, p);
 		}
 		predrifted = pre;
 		__syncthreads();
@@ -125,7 +178,7 @@ __global__ void __launch_bounds__(ET, 2) k_ensemble(const BodyDesc* __restrict__
 			const int hi = n - B.n_perts;
 			double v[4] = { 0.0, 0.0, 0.0, 0.0 };
 			for (int i = tid; i < hi; i += ET) {
-				const vec4d p = sp[i];
+				const vec4d p = ldp(i);
 				v[0] += p.w * p.x; v[1] += p.w * p.y; v[2] += p.w * p.z; v[3] += p.w;
 			}
 #pragma unroll
@@ -142,24 +195,23 @@ __global__ void __launch_bounds__(ET, 2) k_ensemble(const BodyDesc* __restrict__
 			__syncthreads();
 			const double cx = com[0] / com[3], cy = com[1] / com[3], cz = com[2] / com[3];
 			for (int i = tid; i < n; i += ET) {
-				vec4d p = sp[i];
+				vec4d p = ldp(i);
 				p.x = __dadd_rn(p.x, -cx); p.y = __dadd_rn(p.y, -cy); p.z = __dadd_rn(p.z, -cz);
 				if (!last) {
-					const vec4d w = sv[i];
+					const vec4d w = ldv(i);
 					p.x = __dadd_rn(p.x, __dmul_rn(h, w.x));
 					p.y = __dadd_rn(p.y, __dmul_rn(h, w.y));
 					p.z = __dadd_rn(p.z, __dmul_rn(h, w.z));
 				}
-				sp[i] = p;
+				stp(i, p);
 			}
 			predrifted = !last;
 			__syncthreads();
 		}
 	}
 	for (int i = tid; i < n; i += ET) {
-		posm_g[B.node_off + i] = sp[i];
-		vel_g[B.node_off + i] = sv[i];
-		acc_g[B.node_off + i] = sa[i];
+		posm_g[B.node_off + i] = ldp(i);
+		vel_g[B.node_off + i] = ldv(i);
 	}
 }
 
@@ -193,15 +245,17 @@ struct ass_ensemble {
 	vec4d *posm = nullptr, *vel = nullptr, *acc = nullptr;
 	int* row_ptr = nullptr;
 	HalfEdge* he = nullptr;
+	double2* pal = nullptr;  // distinct (k, gamma) pairs over all members
 	double* d_dense = nullptr;
 	cudaStream_t stream = nullptr;
 	cudaEvent_t e0 = nullptr, e1 = nullptr;
 	size_t smem = 0;
+	int ring_records = 0;  // capacity of one ring buffer: the longest run of half-edges of 64 consecutive nodes
 };
 
 static void ens_free(ass_ensemble* e) {
 	if (!e) return;
-	cudaFree(e->d_desc); cudaFree(e->posm); cudaFree(e->vel); cudaFree(e->acc); cudaFree(e->row_ptr); cudaFree(e->he); cudaFree(e->d_dense);
+	cudaFree(e->d_desc); cudaFree(e->posm); cudaFree(e->vel); cudaFree(e->acc); cudaFree(e->row_ptr); cudaFree(e->he); cudaFree(e->pal); cudaFree(e->d_dense);
 	if (e->e0) cudaEventDestroy(e->e0);
 	if (e->e1) cudaEventDestroy(e->e1);
 	if (e->stream) cudaStreamDestroy(e->stream);
@@ -237,6 +291,19 @@ extern "C" int ass_ensemble_create(ass_ensemble** out, int n_bodies, const int* 
 	// CSR per body: row entries are offsets into the concatenated half-edge array; indices stay local to the body
 	std::vector<int> row((size_t) total_nodes + n_bodies, 0);
 	std::vector<HalfEdge> he((size_t) 2 * total_springs);
+	// palette of distinct (k, gamma) bit patterns over the whole ensemble (a sweep has a handful)
+	std::vector<double2> pal;
+	std::unordered_map<std::string, int> seen;
+	auto pal_index = [&](const ass_spring& v) {
+		std::string key((const char*) &v.k, 8);
+		key.append((const char*) &v.gamma, 8);
+		auto it = seen.find(key);
+		if (it == seen.end()) {
+			it = seen.emplace(key, (int) pal.size()).first;
+			pal.push_back(make_double2(v.k, v.gamma));
+		}
+		return it->second;
+	};
 	size_t he_base = 0;
 	for (int b = 0; b < n_bodies; b++) {
 		const int n = node_off[b + 1] - node_off[b], ns = spring_off[b + 1] - spring_off[b];
@@ -262,12 +329,14 @@ extern "C" int ass_ensemble_create(ass_ensemble** out, int n_bodies, const int* 
 		}
 		for (int i = 0; i < n; i++) deg[(size_t) i + 1] += deg[i];
 		for (int i = 0; i <= n; i++) r[i] = (int) (he_base + deg[i]);
+		for (int w0 = 0; w0 < n; w0 += EW) e->ring_records = std::max(e->ring_records, deg[std::min(n, w0 + EW)] - deg[w0]);
 		std::vector<int> fill(deg.begin(), deg.end() - 1);
 		for (int q = 0; q < ns; q++) {
 			const int ends[2] = { sp[q].particle_1, sp[q].particle_2 };
+			const int pidx = pal_index(sp[q]);
 			for (int side = 0; side < 2; side++) {
 				HalfEdge hrec;
-				hrec.k = sp[q].k; hrec.rs0 = sp[q].rs0; hrec.gamma = sp[q].gamma; hrec.nbr = ends[1 - side]; hrec.sid = q;
+				hrec.rs0 = sp[q].rs0; hrec.nbr = ends[1 - side]; hrec.pal = pidx;
 				he[he_base + fill[ends[side]]++] = hrec;
 			}
 		}
@@ -275,10 +344,12 @@ extern "C" int ass_ensemble_create(ass_ensemble** out, int n_bodies, const int* 
 	}
 	e->total_he = (long long) he_base;
 	fill_desc(e);
-	e->smem = sizeof(vec4d) * 3 * (size_t) e->max_n;
+	e->ring_records = std::max(16, (e->ring_records + 7) / 8 * 8);
+	e->smem = sizeof(HalfEdge) * 2 * (size_t) e->ring_records + sizeof(vec4d) * 2 * (size_t) e->max_n + sizeof(int) * ((size_t) e->max_n + 1) + 64;
 	if (e->smem > 227 * 1024 - 2048) {
 		ens_free(e);
-		ass_set_error("ass_ensemble_create: a body of %d nodes does not fit in shared memory (limit ~2400); use ass_sim for large bodies", e->max_n);
+		ass_set_error("ass_ensemble_create: a body of %d nodes (%d half-edges per 64-node wave) does not fit in shared memory (limit ~3000 nodes); use ass_sim for large bodies",
+		              e->max_n, e->ring_records);
 		return ASS_EINVAL;
 	}
 	const size_t nb = (size_t) total_nodes * stride;
@@ -288,6 +359,7 @@ extern "C" int ass_ensemble_create(ass_ensemble** out, int n_bodies, const int* 
 	          cudaMalloc(&e->posm, sizeof(vec4d) * total_nodes) == cudaSuccess && cudaMalloc(&e->vel, sizeof(vec4d) * total_nodes) == cudaSuccess &&
 	          cudaMalloc(&e->acc, sizeof(vec4d) * total_nodes) == cudaSuccess && cudaMalloc(&e->row_ptr, sizeof(int) * row.size()) == cudaSuccess &&
 	          cudaMalloc(&e->he, sizeof(HalfEdge) * std::max<size_t>(he.size(), 1)) == cudaSuccess &&
+	          cudaMalloc(&e->pal, sizeof(double2) * std::max<size_t>(pal.size(), 1)) == cudaSuccess &&
 	          cudaMalloc(&e->d_dense, sizeof(double) * 10 * (size_t) total_nodes) == cudaSuccess && cudaMalloc(&d_rows, nb) == cudaSuccess;
 	if (!ok) {
 		cudaFree(d_rows);
@@ -298,6 +370,7 @@ extern "C" int ass_ensemble_create(ass_ensemble** out, int n_bodies, const int* 
 	cudaMemcpyAsync(d_rows, base, nb, cudaMemcpyHostToDevice, e->stream);
 	cudaMemcpyAsync(e->row_ptr, row.data(), sizeof(int) * row.size(), cudaMemcpyHostToDevice, e->stream);
 	if (!he.empty()) cudaMemcpyAsync(e->he, he.data(), sizeof(HalfEdge) * he.size(), cudaMemcpyHostToDevice, e->stream);
+	if (!pal.empty()) cudaMemcpyAsync(e->pal, pal.data(), sizeof(double2) * pal.size(), cudaMemcpyHostToDevice, e->stream);
 	cudaMemcpyAsync(e->d_desc, e->desc.data(), sizeof(BodyDesc) * n_bodies, cudaMemcpyHostToDevice, e->stream);
 	k_unpack<<<(total_nodes + 255) / 256, 256, 0, e->stream>>>((const unsigned char*) d_rows, stride, total_nodes, e->posm, e->vel, e->acc);
 	g_launch_count++;
@@ -332,7 +405,7 @@ extern "C" int ass_ensemble_step(ass_ensemble* e, int nsteps, int with_heartbeat
 	if (device_ms) *device_ms = 0.0;
 	if (nsteps == 0) return ASS_OK;
 	if (device_ms) CU_TRY(cudaEventRecord(e->e0, e->stream));
-	k_ensemble<<<e->n_bodies, ET, e->smem, e->stream>>>(e->d_desc, e->posm, e->vel, e->acc, e->row_ptr, e->he, nsteps, with_heartbeat);
+	k_ensemble<<<e->n_bodies, ET, e->smem, e->stream>>>(e->d_desc, e->posm, e->vel, e->acc, e->row_ptr, e->he, e->pal, nsteps, with_heartbeat, e->max_n, e->ring_records);
 	LAUNCH_CHECK();
 	for (auto& p : e->prm)
 		for (int s = 0; s < nsteps; s++) {  // the reference's own rounding of t (integrator_leapfrog.c:50,65)

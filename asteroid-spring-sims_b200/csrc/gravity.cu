@@ -29,30 +29,6 @@ namespace {
 constexpr int GB = 128;   // threads per CTA
 constexpr int JT = 256;   // sources per tile (8 KB)
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t) __cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
-	asm volatile(
-		"{\n\t"
-		".reg .pred p;\n\t"
-		"WAIT_%=:\n\t"
-		"mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-		"@p bra DONE_%=;\n\t"
-		"bra WAIT_%=;\n\t"
-		"DONE_%=:\n\t"
-		"}" ::"r"(smem_u32(bar)), "r"(phase) : "memory");
-}
-// 1-D bulk copy global -> shared, completion signalled on the mbarrier (TMA engine, no tensor map needed)
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-			"l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-
 template <int TI>
 struct Targets {
 	double x[TI], y[TI], z[TI];

@@ -211,23 +211,24 @@ __global__ void __launch_bounds__(RB) k_node_diag(const vec4d* __restrict__ posm
 // spring sums: SPE (physics.cpp:457-476) and damping power (physics.cpp:409-454).  Each spring appears as two
 // half-edges; take the one stored at its lower endpoint (nbr > owner) so every spring counts once.
 __global__ void __launch_bounds__(RB) k_spring_diag(const vec4d* __restrict__ posm, const vec4d* __restrict__ vel,
-		const int* __restrict__ row_ptr, const HalfEdge* __restrict__ he, int n, double* __restrict__ part) {
+		const int* __restrict__ row_ptr, const HalfEdge* __restrict__ he, const double2* __restrict__ pal, int n, double* __restrict__ part) {
 	double v[2] = { 0.0, 0.0 };
 	for (int i = blockIdx.x * RB + threadIdx.x; i < n; i += gridDim.x * RB) {
 		const vec4d pi = posm[i], vi = vel[i];
 		for (int e = row_ptr[i]; e < row_ptr[i + 1]; e++) {
 			const HalfEdge h = he[e];
 			if (h.nbr < i) continue;
+			const double2 kg = pal[h.pal];
 			const vec4d pj = posm[h.nbr];
 			const double dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
 			const double len = __dadd_rn(ref_len(dx, dy, dz), ASS_L_EPS);
 			const double ext = len - h.rs0;
-			v[0] += h.k * (ext * ext) / 2.0;
-			if (h.gamma != 0.0) {
+			v[0] += kg.x * (ext * ext) / 2.0;
+			if (kg.y != 0.0) {
 				const vec4d vj = vel[h.nbr];
 				const double sr = ((vi.x - vj.x) * dx + (vi.y - vj.y) * dy + (vi.z - vj.z) * dz) / (len * len);
 				const double m_red = pi.w * pj.w / (pi.w + pj.w);
-				v[1] += h.gamma * m_red * (sr * sr);
+				v[1] += kg.y * m_red * (sr * sr);
 			}
 		}
 	}
@@ -410,7 +411,7 @@ extern "C" int ass_diagnostics(ass_sim* s, int lo, int hi, int want_gpe, double 
 	LAUNCH_CHECK();
 	if (s->ns > 0) {
 		const int g2 = reduce_grid(s->n);
-		k_spring_diag<<<g2, RB, 0, s->stream>>>(s->posm, s->vel, s->row_ptr, s->he, s->n, part);
+		k_spring_diag<<<g2, RB, 0, s->stream>>>(s->posm, s->vel, s->row_ptr, s->he, s->pal, s->n, part);
 		LAUNCH_CHECK();
 		k_fold<2><<<1, RB, 0, s->stream>>>(part, g2, d + 18);
 		LAUNCH_CHECK();

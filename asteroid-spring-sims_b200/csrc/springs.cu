@@ -18,7 +18,7 @@ constexpr int BLOCK = 256;  // 32 nodes per CTA
 // KICK        additionally v += dt*a ; x += (dt/2)*v [; x += (dt/2)*v again = next step's part1] into the alt buffers
 template <bool ZERO_FIRST, bool KICK>
 __global__ void __launch_bounds__(BLOCK) k_spring_forces(const vec4d* __restrict__ posm, const vec4d* __restrict__ vel,
-		vec4d* __restrict__ acc, const int* __restrict__ row_ptr, const HalfEdge* __restrict__ he, int lo, int hi,
+		vec4d* __restrict__ acc, const int* __restrict__ row_ptr, const HalfEdge* __restrict__ he, const double2* __restrict__ pal, int lo, int hi,
 		vec4d* __restrict__ posm_out, vec4d* __restrict__ vel_out, double dt, int pre_drift_next) {
 	const int gid = lo + (blockIdx.x * BLOCK + threadIdx.x) / SPRING_LANES;
 	const int lane = threadIdx.x & (SPRING_LANES - 1);
@@ -27,7 +27,8 @@ __global__ void __launch_bounds__(BLOCK) k_spring_forces(const vec4d* __restrict
 	const vec4d pi = posm[node];
 	const vec4d vi = vel[node];
 	const int beg = row_ptr[node], end = live ? row_ptr[node + 1] : beg;
-	const Force3 f = node_spring_sum(he, beg, end, lane, pi, vi, posm, vel);
+	const GlobalNodes nodes{ posm, vel };
+	const Force3 f = node_spring_sum(he, pal, beg, end, lane, pi, vi, nodes);
 	if (!live || lane != 0) return;
 	// a node without springs (e.g. a point-mass perturber, possibly massless) is left untouched
 	const double inv_m = (end > beg) ? fast_rcp(pi.w) : 0.0;
@@ -67,9 +68,9 @@ int ass_launch_spring_forces_range(ass_sim* s, bool zero_first, int lo, int hi) 
 	const int grid = (hi - lo + groups_per_block - 1) / groups_per_block;
 	ass_tic(s, ASS_K_SPRINGS);
 	if (zero_first)
-		k_spring_forces<true, false><<<grid, BLOCK, 0, s->stream>>>(s->posm, s->vel, s->acc, s->row_ptr, s->he, lo, hi, nullptr, nullptr, 0.0, 0);
+		k_spring_forces<true, false><<<grid, BLOCK, 0, s->stream>>>(s->posm, s->vel, s->acc, s->row_ptr, s->he, s->pal,lo, hi, nullptr, nullptr, 0.0, 0);
 	else
-		k_spring_forces<false, false><<<grid, BLOCK, 0, s->stream>>>(s->posm, s->vel, s->acc, s->row_ptr, s->he, lo, hi, nullptr, nullptr, 0.0, 0);
+		k_spring_forces<false, false><<<grid, BLOCK, 0, s->stream>>>(s->posm, s->vel, s->acc, s->row_ptr, s->he, s->pal,lo, hi, nullptr, nullptr, 0.0, 0);
 	LAUNCH_CHECK();
 	ass_toc(s, ASS_K_SPRINGS);
 	return ASS_OK;
@@ -83,9 +84,9 @@ int ass_launch_spring_kick_drift(ass_sim* s, bool zero_first, double dt, bool pr
 	const int grid = (s->n + groups_per_block - 1) / groups_per_block;
 	ass_tic(s, ASS_K_SPRINGS);
 	if (zero_first)
-		k_spring_forces<true, true><<<grid, BLOCK, 0, s->stream>>>(s->posm, s->vel, s->acc, s->row_ptr, s->he, 0, s->n, s->posm_alt, s->vel_alt, dt, pre_drift_next ? 1 : 0);
+		k_spring_forces<true, true><<<grid, BLOCK, 0, s->stream>>>(s->posm, s->vel, s->acc, s->row_ptr, s->he, s->pal,0, s->n, s->posm_alt, s->vel_alt, dt, pre_drift_next ? 1 : 0);
 	else
-		k_spring_forces<false, true><<<grid, BLOCK, 0, s->stream>>>(s->posm, s->vel, s->acc, s->row_ptr, s->he, 0, s->n, s->posm_alt, s->vel_alt, dt, pre_drift_next ? 1 : 0);
+		k_spring_forces<false, true><<<grid, BLOCK, 0, s->stream>>>(s->posm, s->vel, s->acc, s->row_ptr, s->he, s->pal,0, s->n, s->posm_alt, s->vel_alt, dt, pre_drift_next ? 1 : 0);
 	LAUNCH_CHECK();
 	ass_toc(s, ASS_K_SPRINGS);
 	std::swap(s->posm, s->posm_alt);

@@ -4,6 +4,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <unordered_map>
 
 #include "common.cuh"
 
@@ -234,7 +235,7 @@ extern "C" int ass_destroy(ass_sim* s) {
 	ass_shard_release(s);  // a sharded simulation's posm / vel alias its exported window
 	ass_sym_plan_free(s->sym_plan);
 	cudaFree(s->posm); cudaFree(s->vel); cudaFree(s->acc); cudaFree(s->posm_alt); cudaFree(s->vel_alt);
-	cudaFree(s->he); cudaFree(s->row_ptr); cudaFree(s->slot);
+	cudaFree(s->he); cudaFree(s->row_ptr); cudaFree(s->slot); cudaFree(s->pal);
 	cudaFree(s->stage.p); cudaFree(s->grav_partial.p); cudaFree(s->red_partial.p); cudaFree(s->flush.p);
 	cudaFree(s->d_red);
 	if (s->h_red) cudaFreeHost(s->h_red);
@@ -417,8 +418,55 @@ extern "C" int ass_download_particles(ass_sim* s, void* base, size_t stride, int
 }
 
 // ---------------------------------------------------------------------------------------------------
-// springs: caller's list -> node-sorted half-edges
+// springs: caller's list -> node-sorted 16-byte half-edges + palette of distinct (k, gamma) pairs
 // ---------------------------------------------------------------------------------------------------
+namespace {
+struct KG {
+	uint64_t k, g;
+	bool operator==(const KG& o) const { return k == o.k && g == o.g; }
+};
+struct KGHash {
+	size_t operator()(const KG& v) const {
+		uint64_t x = v.k * 0x9E3779B97F4A7C15ULL ^ (v.g + 0x7F4A7C15ULL + (v.k << 6) + (v.k >> 2));
+		x ^= x >> 31;
+		return (size_t) (x * 0xD6E8FEB86659FD93ULL);
+	}
+};
+// bit patterns, not values: -0.0 and 0.0, or two NaNs, stay distinct entries and round-trip exactly
+void build_palette(const ass_spring* sp, int ns, std::vector<double2>& pal, std::vector<int>& idx) {
+	std::unordered_map<KG, int, KGHash> seen;
+	idx.resize((size_t) ns);
+	pal.clear();
+	for (int q = 0; q < ns; q++) {
+		KG key;
+		memcpy(&key.k, &sp[q].k, 8);
+		memcpy(&key.g, &sp[q].gamma, 8);
+		auto it = seen.find(key);
+		if (it == seen.end()) {
+			it = seen.emplace(key, (int) pal.size()).first;
+			pal.push_back(make_double2(sp[q].k, sp[q].gamma));
+		}
+		idx[(size_t) q] = it->second;
+	}
+}
+int upload_palette(ass_sim* s, const std::vector<double2>& pal) {
+	if (pal.size() > s->pal_cap) {
+		cudaFree(s->pal);
+		s->pal = nullptr; s->pal_cap = 0;
+		const size_t cap = pal.size() + pal.size() / 4 + 16;
+		if (cudaMalloc(&s->pal, sizeof(double2) * cap) != cudaSuccess) {
+			cudaGetLastError();
+			ass_set_error("out of device memory for a palette of %zu (k, gamma) pairs", cap);
+			return ASS_ENOMEM;
+		}
+		s->pal_cap = cap;
+	}
+	if (!pal.empty()) CU_TRY(cudaMemcpyAsync(s->pal, pal.data(), sizeof(double2) * pal.size(), cudaMemcpyHostToDevice, s->stream));
+	s->n_pal = (int) pal.size();
+	return ASS_OK;
+}
+}  // namespace
+
 extern "C" int ass_set_springs(ass_sim* s, const ass_spring* sp, int ns) {
 	REQUIRE(s, ASS_EINVAL, "null sim");
 	REQUIRE(ns >= 0, ASS_EINVAL, "negative spring count");
@@ -446,6 +494,9 @@ extern "C" int ass_set_springs(ass_sim* s, const ass_spring* sp, int ns) {
 		maxdeg = std::max(maxdeg, row[(size_t) i + 1]);
 		row[(size_t) i + 1] += row[i];
 	}
+	std::vector<double2> pal;
+	std::vector<int> pidx;
+	build_palette(sp, ns, pal, pidx);
 	const size_t nhe = (size_t) 2 * ns;
 	std::vector<HalfEdge> he(nhe);
 	std::vector<int> slot(nhe);
@@ -455,9 +506,9 @@ extern "C" int ass_set_springs(ass_sim* s, const ass_spring* sp, int ns) {
 		for (int side = 0; side < 2; side++) {
 			const int at = fill[e[side]]++;
 			HalfEdge h;
-			h.k = sp[q].k; h.rs0 = sp[q].rs0; h.gamma = sp[q].gamma;
+			h.rs0 = sp[q].rs0;
 			h.nbr = e[1 - side];
-			h.sid = q;
+			h.pal = pidx[(size_t) q];
 			he[at] = h;
 			slot[(size_t) 2 * q + side] = at;
 		}
@@ -485,6 +536,7 @@ extern "C" int ass_set_springs(ass_sim* s, const ass_spring* sp, int ns) {
 		s->row_cap = cap;
 	}
 	ass_tic(s, ASS_K_XFER);
+	if ((rc = upload_palette(s, pal))) return rc;
 	if (nhe) {
 		CU_TRY(cudaMemcpyAsync(s->he, he.data(), sizeof(HalfEdge) * nhe, cudaMemcpyHostToDevice, s->stream));
 		CU_TRY(cudaMemcpyAsync(s->slot, slot.data(), sizeof(int) * nhe, cudaMemcpyHostToDevice, s->stream));
@@ -498,13 +550,17 @@ extern "C" int ass_set_springs(ass_sim* s, const ass_spring* sp, int ns) {
 	return ASS_OK;
 }
 
-__global__ void k_scatter_props(const ass_spring* __restrict__ sp, const int* __restrict__ slot, HalfEdge* __restrict__ he, int ns) {
+// stage holds [ns x ass_spring | ns x int palette index]
+__global__ void k_scatter_props(const ass_spring* __restrict__ sp, const int* __restrict__ pidx, const int* __restrict__ slot,
+		HalfEdge* __restrict__ he, int ns) {
 	int q = blockIdx.x * blockDim.x + threadIdx.x;
 	if (q >= ns) return;
-	const ass_spring v = sp[q];
+	const double rs0 = sp[q].rs0;
+	const int pi = pidx[q];
 	for (int side = 0; side < 2; side++) {
 		HalfEdge* h = he + slot[(size_t) 2 * q + side];
-		h->k = v.k; h->rs0 = v.rs0; h->gamma = v.gamma;
+		h->rs0 = rs0;
+		h->pal = pi;
 	}
 }
 
@@ -515,10 +571,16 @@ extern "C" int ass_update_spring_props(ass_sim* s, const ass_spring* sp, int ns)
 	REQUIRE(sp, ASS_EINVAL, "null spring array");
 	int rc = ass_ensure_device();
 	if (rc) return rc;
-	if ((rc = ass_buf_reserve(s->stage, sizeof(ass_spring) * (size_t) ns))) return rc;
+	std::vector<double2> pal;
+	std::vector<int> pidx;
+	build_palette(sp, ns, pal, pidx);
+	const size_t sp_bytes = sizeof(ass_spring) * (size_t) ns;
+	if ((rc = ass_buf_reserve(s->stage, sp_bytes + sizeof(int) * (size_t) ns))) return rc;
 	ass_tic(s, ASS_K_XFER);
-	CU_TRY(cudaMemcpyAsync(s->stage.p, sp, sizeof(ass_spring) * (size_t) ns, cudaMemcpyHostToDevice, s->stream));
-	k_scatter_props<<<(ns + 255) / 256, 256, 0, s->stream>>>((const ass_spring*) s->stage.p, s->slot, s->he, ns);
+	if ((rc = upload_palette(s, pal))) return rc;
+	CU_TRY(cudaMemcpyAsync(s->stage.p, sp, sp_bytes, cudaMemcpyHostToDevice, s->stream));
+	CU_TRY(cudaMemcpyAsync((char*) s->stage.p + sp_bytes, pidx.data(), sizeof(int) * (size_t) ns, cudaMemcpyHostToDevice, s->stream));
+	k_scatter_props<<<(ns + 255) / 256, 256, 0, s->stream>>>((const ass_spring*) s->stage.p, (const int*) ((char*) s->stage.p + sp_bytes), s->slot, s->he, ns);
 	LAUNCH_CHECK();
 	ass_toc(s, ASS_K_XFER);
 	CU_TRY(cudaStreamSynchronize(s->stream));
