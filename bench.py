@@ -222,6 +222,8 @@ def run_reference(args, rank, world):
     """--impl reference: the reference's own CPU path, all host threads it can correctly use. Rank 0 only."""
     if rank != 0:
         return
+    # torchrun pins OMP_NUM_THREADS=1 for its children; the reference arm is meant to use every host thread it can
+    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
     import asteroid_spring_sims_b200 as A  # host-side generator only (no GPU needed): builds the same body
     name = args.workload or "C3"
     cfg = WORKLOADS[name]
