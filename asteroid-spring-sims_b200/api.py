@@ -91,6 +91,39 @@ def probe_copy_bw(nbytes=1 << 30):
     return g.value
 
 
+class PinnedRows:
+    """An (n, cols) float64 row array in page-locked, device-mapped host memory (``ass_host_alloc``): the host side of
+    an upload / download at PCIe link rate.  ``.a`` is the numpy view; keep this object alive while the view is used."""
+
+    def __init__(self, n, cols=16):
+        self._p = C.c_void_p()
+        self.nbytes = max(int(n) * int(cols) * 8, 8)
+        _chk(lib().ass_host_alloc(C.byref(self._p), C.c_size_t(self.nbytes)))
+        buf = (C.c_double * (int(n) * int(cols))).from_address(self._p.value)
+        self.a = np.frombuffer(buf, dtype=np.float64).reshape(int(n), int(cols))
+
+    def close(self):
+        if self._p:
+            self.a = None
+            lib().ass_host_free(self._p)
+            self._p = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def host_register(arr):
+    """Pin an existing numpy array in place (``ass_host_register``); pair with host_unregister before it is freed."""
+    _chk(lib().ass_host_register(C.c_void_p(arr.ctypes.data), C.c_size_t(arr.nbytes)))
+
+
+def host_unregister(arr):
+    _chk(lib().ass_host_unregister(C.c_void_p(arr.ctypes.data)))
+
+
 def _rows(p):
     assert isinstance(p, np.ndarray) and p.dtype == np.float64 and p.ndim == 2 and p.shape[1] >= 10
     assert p.strides[1] == 8, "rows must be contiguous doubles"

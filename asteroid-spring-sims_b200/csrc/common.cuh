@@ -89,6 +89,7 @@ struct ass_sim {
 
 	vec4d *posm = nullptr, *vel = nullptr, *acc = nullptr;
 	vec4d *posm_alt = nullptr, *vel_alt = nullptr;  // ping-pong targets of the fused spring+kick+drift kernel
+	long long mass_epoch = 0;  // bumped whenever masses may have changed on the device (uploads carrying ASS_F_MASS)
 	bool have_state = false;
 	bool predrifted = false;  // positions already carry the next step's first half-drift (fused loop only)
 	bool sum_sequential = true;  // CoM / CoV sums in the reference's particle order (bit-exact) or as a parallel tree

@@ -61,6 +61,9 @@ struct Dropin {
 	size_t sp_size = 0;
 	const spring* sp_ptr = nullptr;
 	uint64_t sp_probe = 0;
+	// r->particles page-locked for the length of a reb_integrate (uploads / downloads at PCIe link rate)
+	void* pinned = nullptr;
+	size_t pinned_bytes = 0;
 };
 
 std::mutex g_mu;
@@ -110,8 +113,28 @@ void push_params(reb_simulation* r, Dropin& d) {
 	OK(ass_set_params(d.sim, &p));
 }
 
+// Inside reb_integrate the particle array is page-locked so transfers run at link rate.  reb_add may realloc it
+// (src/particle.c:53-56): the registration follows the pointer; a failure to pin is not an error (transfers are staged).
+void unpin_particles(Dropin& d) {
+	if (d.pinned) ass_host_unregister(d.pinned);
+	d.pinned = nullptr;
+	d.pinned_bytes = 0;
+}
+void pin_particles(reb_simulation* r, Dropin& d) {
+	const size_t bytes = sizeof(reb_particle) * (size_t) r->N;
+	if (d.pinned == (void*) r->particles && bytes <= d.pinned_bytes) return;
+	unpin_particles(d);
+	const char* off = getenv("ASS_NO_PIN");
+	if (!d.in_run || r->N <= 0 || (off && *off && strcmp(off, "0") != 0)) return;
+	if (ass_host_register(r->particles, bytes) == ASS_OK) {
+		d.pinned = r->particles;
+		d.pinned_bytes = bytes;
+	}
+}
+
 void ensure_dev(reb_simulation* r, Dropin& d) {
 	if (d.dev_fresh && ass_num_particles(d.sim) == r->N) return;
+	if (d.in_run) pin_particles(r, d);
 	OK(ass_upload_particles(d.sim, r->particles, sizeof(reb_particle), r->N, ASS_F_ALL));
 	d.dev_fresh = true;
 	d.host_fresh = true;
@@ -119,6 +142,7 @@ void ensure_dev(reb_simulation* r, Dropin& d) {
 }
 
 void flush_host(reb_simulation* r, Dropin& d) {
+	if (d.in_run && d.pending && r->N > 0) pin_particles(r, d);
 	if (d.pending && r->N > 0) OK(ass_download_particles(d.sim, r->particles, sizeof(reb_particle), r->N, d.pending));
 	d.pending = 0;
 	d.host_fresh = true;
@@ -219,6 +243,7 @@ extern "C" void ass_dropin_release(struct reb_simulation* r) {
 	std::lock_guard<std::mutex> lk(g_mu);
 	auto it = g_map.find(r);
 	if (it == g_map.end()) return;
+	unpin_particles(it->second);
 	ass_destroy(it->second.sim);
 	g_map.erase(it);
 }
@@ -306,9 +331,10 @@ extern "C" enum REB_STATUS reb_integrate(struct reb_simulation* const r, double 
 	}
 	reb_integrator_synchronize(r);    // :649
 	if (r->exact_finish_time == 1) r->dt = last_full_dt;  // :653-655
-	d.in_run = false;
 	ass_set_sum_order(d.sim, 1);
 	ass_dropin_sync_host(r);
+	d.in_run = false;
+	unpin_particles(d);
 	d.dev_fresh = false;
 	return r->status;
 }

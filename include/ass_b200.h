@@ -96,6 +96,15 @@ int ass_get_params(ass_sim* sim, ass_params* p);
 /* ---- state transfer (replaces nothing: it is the residency boundary, SURVEY section 8b "Ownership") ---- */
 int ass_upload_particles(ass_sim* sim, const void* base, size_t stride_bytes, int n, unsigned fields);
 int ass_download_particles(ass_sim* sim, void* base, size_t stride_bytes, int n, unsigned fields);
+/* Page-lock and map a host range so the two calls above move rows at PCIe link rate: uploads are read by the copy
+ * engine straight from the caller's rows, downloads are written by the pack kernel straight into them (no bounce buffer,
+ * no host-side scatter).  ass_host_register pins memory the caller already owns -- e.g. r->particles (malloc'd by
+ * reb_add, src/particle.c:53-56) for the length of a reb_integrate; unregister BEFORE the memory is freed or realloc'd.
+ * ass_host_alloc / ass_host_free hand out pinned memory directly.  Unpinned arrays keep working (driver-staged). */
+int ass_host_register(void* base, size_t bytes);
+int ass_host_unregister(void* base);
+int ass_host_alloc(void** out, size_t bytes);
+int ass_host_free(void* p);
 /* Replace the whole spring list (after connect_springs_dist / add_spring / del_spring). Builds the node-sorted
  * half-edge (CSR) layout used by ass_spring_forces.  Checks 0 <= particle_1 != particle_2 < n. */
 int ass_set_springs(ass_sim* sim, const ass_spring* springs, int ns);

@@ -245,16 +245,20 @@ def test_integrate_exact_finish_and_heartbeat(gpu, body015):
 # ---------------------------------------------------------------------------------------------------
 # callback shapes, edge cases, error behaviour
 # ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("uniform_mass", [False, True])
 @pytest.mark.parametrize("softening", [1e-3, 0.0])
-def test_gravity_kernels_agree(gpu, oracle, body010, softening):
+def test_gravity_kernels_agree(gpu, oracle, body010, softening, uniform_mass):
     """The one-sided tile kernel and the pair-once kernel against the oracle, on sizes that exercise padding (N not a
-    multiple of the 1024-particle block), the diagonal tile's self-pair mask (softening = 0) and several blocks."""
+    multiple of the 1024-particle block), the diagonal tile's self-pair mask (softening = 0) and several blocks.
+    uniform_mass: every particle carries the same mass (the pair-once kernel's 19-instruction specialisation, mass
+    applied by the reduction) / a heavy point mass at the end (the general 21-instruction kernel)."""
     g = body010
     base = g["step20_basic"].copy()
     # 1065 particles -> 2 blocks; stack shifted copies for 4 blocks + a heavy point mass at the end
     p = np.vstack([base, base + np.r_[3.0, 0, 0, np.zeros(8)], base + np.r_[0, 3.0, 0, np.zeros(8)], base[:777] + np.r_[0, 0, 3.0, np.zeros(8)]])
     pm = np.zeros((1, 11)); pm[0, :3] = (9.0, 1.0, -2.0); pm[0, 9] = 25.0
-    p = np.ascontiguousarray(np.vstack([p, pm]))
+    p = np.ascontiguousarray(p if uniform_mass else np.vstack([p, pm]))
+    assert (len(set(p[:, 9])) == 1) == uniform_mass
     want = p.copy(); oracle.gravity_basic(want, G=0.7, softening=softening)
     for which in (1, 2):
         with new_sim(gpu, p, gravity=1, G=0.7, softening=softening) as s:
@@ -265,6 +269,13 @@ def test_gravity_kernels_agree(gpu, oracle, body010, softening):
             assert acc_err(got[:, 6:9], want[:, 6:9]) <= ACC_TOL, which
             s.gravity_basic()                                     # deterministic: same bits on a second evaluation
             assert same_bits(s.download(p.copy())[:, 6:9], got[:, 6:9])
+            if which == 2 and uniform_mass:
+                # a mass edit must be noticed: the plan re-checks the masses after an upload that carries them
+                q = p.copy(); q[5, 9] *= 3.0
+                want2 = q.copy(); oracle.gravity_basic(want2, G=0.7, softening=softening)
+                s.upload(q)
+                s.gravity_basic()
+                assert acc_err(s.download(q.copy())[:, 6:9], want2[:, 6:9]) <= ACC_TOL
 
 
 def test_accelerations_accumulate_without_zero_accel(gpu, oracle, body015):
@@ -435,3 +446,50 @@ def test_full_size(gpu, oracle, d, expect_n):
         s.step(20)
         L1 = s.diagnostics(0, n)[6:9]
         assert np.abs(L1 - L0).max() <= 1e-11 * np.abs(L0).max()
+
+
+# ---------------------------------------------------------------------------------------------------
+# pinned host rows: the link-rate transfer path moves the same bits and touches only the requested doubles
+# ---------------------------------------------------------------------------------------------------
+def test_pinned_rows_transfer_matches_pageable(gpu):
+    rng = np.random.default_rng(7)
+    n = 5003
+    P = rng.standard_normal((n, 16))                   # 128-byte rows, like struct reb_particle
+    pin = gpu.PinnedRows(n, 16)
+    try:
+        pin.a[:] = P
+        with gpu.Sim() as s:
+            s.upload(pin.a)                            # copy engine reads the pinned rows directly
+            out_pageable = np.full((n, 16), -7.0)
+            s.download(out_pageable)
+            pin.a[:] = -7.0
+            s.download(pin.a)                          # pack kernel writes straight into the pinned rows
+            assert same_bits(pin.a, out_pageable)
+            assert same_bits(pin.a[:, :10], P[:, :10]) and np.all(pin.a[:, 10:] == -7.0)
+            for fields, cols in ((gpu.F_POS, [0, 1, 2]), (gpu.F_VEL, [3, 4, 5]), (gpu.F_ACC, [6, 7, 8]), (gpu.F_MASS, [9]),
+                                 (gpu.F_POS | gpu.F_ACC, [0, 1, 2, 6, 7, 8])):
+                pin.a[:] = -7.0
+                s.download(pin.a, fields)
+                want = np.full((n, 16), -7.0)
+                want[:, cols] = P[:, cols]
+                assert same_bits(pin.a, want), fields
+            # a sub-range of the pinned allocation (rows 10..) is still recognised as pinned
+            with gpu.Sim() as t:
+                pin.a[:] = P
+                t.upload(pin.a[10:])
+                got = np.zeros((n - 10, 16))
+                t.download(got)
+                assert same_bits(got[:, :10], P[10:, :10])
+        # registering an existing array in place
+        Q = P.copy()
+        gpu.host_register(Q)
+        try:
+            with gpu.Sim() as s:
+                s.upload(Q)
+                Q[:, :10] = 0.0
+                s.download(Q)
+                assert same_bits(Q, P)
+        finally:
+            gpu.host_unregister(Q)
+    finally:
+        pin.close()
