@@ -124,6 +124,13 @@ def host_unregister(arr):
     _chk(lib().ass_host_unregister(C.c_void_p(arr.ctypes.data)))
 
 
+def selfcheck_sqrt(samples=1 << 28, exp_lo=-200, exp_hi=200):
+    """(mismatches, first differing argument) of the spring kernels' branch-free sqrt against __dsqrt_rn."""
+    bad, first = C.c_longlong(), C.c_double()
+    _chk(lib().ass_selfcheck_sqrt(C.c_longlong(samples), C.c_int(exp_lo), C.c_int(exp_hi), C.byref(bad), C.byref(first)))
+    return bad.value, first.value
+
+
 def _rows(p):
     assert isinstance(p, np.ndarray) and p.dtype == np.float64 and p.ndim == 2 and p.shape[1] >= 10
     assert p.strides[1] == 8, "rows must be contiguous doubles"

@@ -8,6 +8,9 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libass_b200.so")
+# tuning only: ASS_LIB loads / builds a differently-named library, ASS_NVCC_EXTRA appends flags (e.g. -DASS_SPRING_LANES=4)
+if os.environ.get("ASS_LIB"):
+    LIB = os.path.abspath(os.environ["ASS_LIB"])
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -38,14 +41,15 @@ def build_native(force=False, verbose=False):
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         raise RuntimeError("nvcc not found: cannot build libass_b200.so (there is no CPU fallback)")
-    objdir = os.path.join(PKG, "build")
+    objdir = os.path.join(PKG, "build") if not os.environ.get("ASS_LIB") else LIB + ".obj"
+    extra = os.environ.get("ASS_NVCC_EXTRA", "").split()
     os.makedirs(objdir, exist_ok=True)
     objs = []
     procs = []
     for src in sources():
         obj = os.path.join(objdir, os.path.basename(src) + ".o")
         objs.append(obj)
-        cmd = [nvcc] + NVCC_FLAGS + ["-I", os.path.join(ROOT, "include"), "-c", src, "-o", obj]
+        cmd = [nvcc] + NVCC_FLAGS + extra + ["-I", os.path.join(ROOT, "include"), "-c", src, "-o", obj]
         if src.endswith(".cpp"):
             cmd = [nvcc] + [f for f in NVCC_FLAGS if f not in ("-Xptxas", "-v")] + ["-x", "c++", "-I", os.path.join(ROOT, "include"), "-c", src, "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

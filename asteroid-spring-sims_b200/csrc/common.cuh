@@ -28,13 +28,14 @@ struct __align__(32) vec4d {
 // figure of SURVEY 8d -- although every spring is stored at both of its endpoints.  Lossless for any number of pairs.
 struct __align__(16) HalfEdge {
 	double rs0;
-	int nbr;  // the other endpoint
+	int nbr;  // the other endpoint: ass_sim -- its spatial rank (see ass_sim::order); ensemble -- its node index
 	int pal;  // index into the (k, gamma) palette
 };
 static_assert(sizeof(HalfEdge) == 16, "HalfEdge must be 16 bytes");
 static_assert(sizeof(ass_spring) == 32, "ass_spring must match struct spring (32 B)");
 
 #define ASS_L_EPS 1e-6  // src_spring/springs.cpp:28
+#define ASS_SPRING_WAVE 64  // ranks per wave of the streaming spring kernel (springs.cu)
 
 // ---------------------------------------------------------------------------------------------------
 // error plumbing
@@ -90,16 +91,34 @@ struct ass_sim {
 	vec4d *posm = nullptr, *vel = nullptr, *acc = nullptr;
 	vec4d *posm_alt = nullptr, *vel_alt = nullptr;  // ping-pong targets of the fused spring+kick+drift kernel
 	long long mass_epoch = 0;  // bumped whenever masses may have changed on the device (uploads carrying ASS_F_MASS)
+	long long spring_epoch = 0;  // bumped by ass_set_springs
+	// "every node that carries springs has the same mass" (springs.cu), valid for (uni_mass_epoch, uni_spring_epoch)
+	bool uni_mass = false;
+	long long uni_mass_epoch = -1, uni_spring_epoch = -1;
 	bool have_state = false;
 	bool predrifted = false;  // positions already carry the next step's first half-drift (fused loop only)
 	bool sum_sequential = true;  // CoM / CoV sums in the reference's particle order (bit-exact) or as a parallel tree
 	int gravity_kernel = 0;      // 0 auto, 1 one-sided tiles (gravity.cu), 2 pair-once (gravity_sym.cu)
 	struct SymPlan* sym_plan = nullptr;  // CTA table + scratch rows of the pair-once kernel
 
-	// springs, node-sorted
+	// springs: CSR over nodes in SPATIAL order.  ass_set_springs ranks the nodes along a Morton curve through their
+	// positions (a solid body: neighbours stay neighbours); row k belongs to node order[k], HalfEdge::nbr is the
+	// neighbour's rank, and ps / vs mirror posm / vel in rank order.  The spring kernel streams rows in rank order and
+	// gathers endpoint state from ps / vs, so the lanes of one request touch a handful of adjacent cache lines instead
+	// of 32 random ones (the generators emit nodes in random order).  Everything else keeps the caller's node order.
 	HalfEdge* he = nullptr;
-	int* row_ptr = nullptr;   // n+1
+	int* row_ptr = nullptr;   // n+1, by rank
 	int* slot = nullptr;      // 2*ns: half-edge slot of (spring s, endpoint e)
+	int* order = nullptr;     // rank -> node
+	int* rank = nullptr;      // node -> rank
+	vec4d *ps = nullptr, *vs = nullptr, *ps_alt = nullptr, *vs_alt = nullptr;
+	size_t sorted_cap = 0;
+	// the streaming spring kernel takes ranks in waves of ASS_SPRING_WAVE: wave_off[w] = row_ptr[w * ASS_SPRING_WAVE]
+	// (n_waves + 1 entries), wave_he_max = the largest number of half-edge records any wave owns.  row_ptr and order are
+	// padded so every wave can be copied whole (row_ptr: (n_waves * WAVE + 4) entries, padding = n_he; order: n_waves * WAVE)
+	int* wave_off = nullptr;
+	int n_waves = 0, wave_he_max = 0;
+	size_t wave_cap = 0;
 	double2* pal = nullptr;   // palette of distinct (k, gamma) pairs
 	int n_pal = 0;
 	size_t he_cap = 0, row_cap = 0, pal_cap = 0;
@@ -132,6 +151,8 @@ void ass_sym_plan_free(struct SymPlan* p);
 bool ass_gravity_sym_applicable(int count);
 int ass_launch_gravity_sym(ass_sim* s, int lo, int hi);
 int ass_buf_reserve(DevBuf& b, size_t bytes);
+// order[k] = node of rank k along a Morton curve through pos[0..n) (state.cu); deterministic, ties keep node order
+void ass_morton_order(const vec4d* pos, size_t n, std::vector<int>& order);
 int ass_ensure_device(void);
 int ass_sm_count(void);
 
@@ -153,9 +174,10 @@ void ass_toc(ass_sim* s, int klass);
 // internal launchers (one per .cu file)
 // ---------------------------------------------------------------------------------------------------
 // springs.cu
-int ass_launch_spring_forces(ass_sim* s, bool zero_first);
+// mirror_fresh: ps / vs already mirror posm / vel (the caller just produced them); otherwise they are re-gathered first
+int ass_launch_spring_forces(ass_sim* s, bool zero_first, bool mirror_fresh);
 int ass_launch_spring_forces_range(ass_sim* s, bool zero_first, int lo, int hi);
-int ass_launch_spring_kick_drift(ass_sim* s, bool zero_first, double dt, bool pre_drift_next);
+int ass_launch_spring_kick_drift(ass_sim* s, bool zero_first, double dt, bool pre_drift_next, bool mirror_fresh);
 // gravity.cu
 int ass_launch_gravity(ass_sim* s);
 int ass_gravity_rows(int n_tgt, int n_src);
@@ -163,6 +185,7 @@ int ass_launch_gravity_partial(ass_sim* s, const vec4d* src, int s_lo, int s_hi,
 int ass_launch_gravity_reduce(ass_sim* s, int t_lo, int t_hi, int rows);
 // leapfrog.cu
 int ass_launch_part1(ass_sim* s, double dt);
+int ass_launch_part1_mirrored(ass_sim* s, double dt);  // part1 that also refreshes the rank-ordered mirror ps / vs
 int ass_launch_part2(ass_sim* s, double dt);
 int ass_launch_part1_range(ass_sim* s, double dt, int lo, int hi);
 int ass_launch_part2_range(ass_sim* s, double dt, bool pre_drift_next, int lo, int hi);
@@ -232,11 +255,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
 		"DONE_%=:\n\t"
 		"}" ::"r"(smem_u32(bar)), "r"(phase) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 // size and both addresses must be multiples of 16 bytes
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
 	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
 			"l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+
+// per-thread asynchronous copy global -> shared (LDGSTS), 16 bytes; completion by cp.async.wait_all
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+	asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 __device__ __forceinline__ double shfl_xor_d(double v, int mask, int width = 32) {
 	return __shfl_xor_sync(0xffffffffu, v, mask, width);

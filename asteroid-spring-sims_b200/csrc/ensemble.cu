@@ -12,6 +12,8 @@
 //   * per step:  part1 | [gravity: all pairs out of shared memory] | springs (same arithmetic and lane order as springs.cu,
 //     so a member gets the bits the single-body path would give it) | kick + drift (+ next part1) | [center_sim].
 // Across GPUs the members are dealt round-robin by the host launcher; no collective is involved.
+#include <string.h>
+
 #include <algorithm>
 #include <string>
 #include <unordered_map>
@@ -22,7 +24,7 @@
 namespace {
 
 constexpr int ET = 1024;                       // threads per CTA: one body owns a whole SM
-constexpr int EW = ET / SPRING_LANES;          // nodes per wave (64)
+constexpr int EW = ET / SPRING_LANES;          // nodes per wave (128)
 
 struct BodyDesc {
 	int node_off, n, row_off, n_perts;
@@ -37,6 +39,7 @@ struct SharedNodes {
 	__device__ __forceinline__ vec4d velocity(int i) const { const double2 a = vxy[i], b = vz0[i]; vec4d v; v.x = a.x; v.y = a.y; v.z = b.x; v.w = 0.0; return v; }
 };
 
+template <bool UNI>
 __global__ void __launch_bounds__(ET, 1) k_ensemble(const BodyDesc* __restrict__ desc, vec4d* __restrict__ posm_g, vec4d* __restrict__ vel_g,
 		vec4d* __restrict__ acc_g, const int* __restrict__ row_ptr, const HalfEdge* __restrict__ he, const double2* __restrict__ pal, int nsteps,
 		int with_hb, int max_n, int ring_records) {
@@ -135,7 +138,7 @@ __global__ void __launch_bounds__(ET, 1) k_ensemble(const BodyDesc* __restrict__
 				const int beg = srow[node], end = live ? srow[node + 1] : beg;
 				// the ring buffer holds records [srow[w*EW], ...): index it with global record numbers
 				const HalfEdge* wave_he = ring + (size_t) (c & 1) * ring_records - srow[w * EW];
-				const Force3 f = node_spring_sum(wave_he, pal, beg, end, lane, pi, vi, nodes);
+				const Force3 f = node_spring_sum<false, UNI>(wave_he, pal, beg, end, lane, pi, vi, nodes);
 				if (live && lane == 0) {
 					const double inv_m = (end > beg) ? fast_rcp(pi.w) : 0.0;
 					vec4d a;
@@ -250,7 +253,8 @@ struct ass_ensemble {
 	cudaStream_t stream = nullptr;
 	cudaEvent_t e0 = nullptr, e1 = nullptr;
 	size_t smem = 0;
-	int ring_records = 0;  // capacity of one ring buffer: the longest run of half-edges of 64 consecutive nodes
+	int ring_records = 0;  // capacity of one ring buffer: the longest run of half-edges of one wave of nodes
+	bool uni_mass = true;  // within every member, all nodes carry the same mass (m_red = m / 2, spring_math.cuh)
 };
 
 static void ens_free(ass_ensemble* e) {
@@ -330,15 +334,29 @@ extern "C" int ass_ensemble_create(ass_ensemble** out, int n_bodies, const int* 
 		for (int i = 0; i < n; i++) deg[(size_t) i + 1] += deg[i];
 		for (int i = 0; i <= n; i++) r[i] = (int) (he_base + deg[i]);
 		for (int w0 = 0; w0 < n; w0 += EW) e->ring_records = std::max(e->ring_records, deg[std::min(n, w0 + EW)] - deg[w0]);
+		// Within a node's row the records are ordered like the single-body path orders them (state.cu: by the
+		// neighbour's spatial rank, ties by spring number), so a member sums in the same order and gets the same bits.
+		std::vector<vec4d> pos((size_t) n);
+		for (int i = 0; i < n; i++) {
+			const double* rr = (const double*) ((const unsigned char*) base + (size_t) (node_off[b] + i) * stride);
+			pos[(size_t) i].x = rr[0]; pos[(size_t) i].y = rr[1]; pos[(size_t) i].z = rr[2]; pos[(size_t) i].w = rr[9];
+			if (memcmp(&pos[(size_t) i].w, &pos[0].w, sizeof(double)) != 0) e->uni_mass = false;
+		}
+		std::vector<int> order, rank((size_t) n);
+		ass_morton_order(pos.data(), pos.size(), order);
+		for (int k = 0; k < n; k++) rank[(size_t) order[(size_t) k]] = k;
+		std::vector<std::pair<std::pair<int, int>, int>> ent((size_t) 2 * ns);  // ((neighbour rank, spring), neighbour)
 		std::vector<int> fill(deg.begin(), deg.end() - 1);
 		for (int q = 0; q < ns; q++) {
 			const int ends[2] = { sp[q].particle_1, sp[q].particle_2 };
-			const int pidx = pal_index(sp[q]);
-			for (int side = 0; side < 2; side++) {
-				HalfEdge hrec;
-				hrec.rs0 = sp[q].rs0; hrec.nbr = ends[1 - side]; hrec.pal = pidx;
-				he[he_base + fill[ends[side]]++] = hrec;
-			}
+			for (int side = 0; side < 2; side++) ent[(size_t) fill[ends[side]]++] = { { rank[(size_t) ends[1 - side]], 2 * q + side }, ends[1 - side] };
+		}
+		for (int i = 0; i < n; i++) std::sort(ent.begin() + deg[(size_t) i], ent.begin() + deg[(size_t) i + 1]);
+		for (size_t at = 0; at < ent.size(); at++) {
+			const int q = ent[at].first.second >> 1;
+			HalfEdge hrec;
+			hrec.rs0 = sp[q].rs0; hrec.nbr = ent[at].second; hrec.pal = pal_index(sp[q]);
+			he[he_base + at] = hrec;
 		}
 		he_base += (size_t) 2 * ns;
 	}
@@ -376,7 +394,8 @@ extern "C" int ass_ensemble_create(ass_ensemble** out, int n_bodies, const int* 
 	g_launch_count++;
 	cudaError_t err = cudaStreamSynchronize(e->stream);
 	cudaFree(d_rows);
-	if (err == cudaSuccess) err = cudaFuncSetAttribute(k_ensemble, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) e->smem);
+	if (err == cudaSuccess) err = cudaFuncSetAttribute(k_ensemble<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) e->smem);
+	if (err == cudaSuccess) err = cudaFuncSetAttribute(k_ensemble<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) e->smem);
 	if (err != cudaSuccess) {
 		ass_set_error("ass_ensemble_create: %s", cudaGetErrorString(err));
 		ens_free(e);
@@ -405,7 +424,10 @@ extern "C" int ass_ensemble_step(ass_ensemble* e, int nsteps, int with_heartbeat
 	if (device_ms) *device_ms = 0.0;
 	if (nsteps == 0) return ASS_OK;
 	if (device_ms) CU_TRY(cudaEventRecord(e->e0, e->stream));
-	k_ensemble<<<e->n_bodies, ET, e->smem, e->stream>>>(e->d_desc, e->posm, e->vel, e->acc, e->row_ptr, e->he, e->pal, nsteps, with_heartbeat, e->max_n, e->ring_records);
+	if (e->uni_mass)
+		k_ensemble<true><<<e->n_bodies, ET, e->smem, e->stream>>>(e->d_desc, e->posm, e->vel, e->acc, e->row_ptr, e->he, e->pal, nsteps, with_heartbeat, e->max_n, e->ring_records);
+	else
+		k_ensemble<false><<<e->n_bodies, ET, e->smem, e->stream>>>(e->d_desc, e->posm, e->vel, e->acc, e->row_ptr, e->he, e->pal, nsteps, with_heartbeat, e->max_n, e->ring_records);
 	LAUNCH_CHECK();
 	for (auto& p : e->prm)
 		for (int s = 0; s < nsteps; s++) {  // the reference's own rounding of t (integrator_leapfrog.c:50,65)

@@ -24,6 +24,23 @@ __global__ void k_part1(vec4d* __restrict__ posm, const vec4d* __restrict__ vel,
 	posm[i] = p;
 }
 
+// part1 that also writes the rank-ordered mirror the spring kernel gathers from (common.cuh)
+__global__ void k_part1_mirrored(vec4d* __restrict__ posm, const vec4d* __restrict__ vel, const int* __restrict__ rank, vec4d* __restrict__ ps,
+		vec4d* __restrict__ vs, int n, double dt) {
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const double h = __dmul_rn(0.5, dt);
+	vec4d p = posm[i];
+	const vec4d v = vel[i];
+	p.x = __dadd_rn(p.x, __dmul_rn(h, v.x));
+	p.y = __dadd_rn(p.y, __dmul_rn(h, v.y));
+	p.z = __dadd_rn(p.z, __dmul_rn(h, v.z));
+	posm[i] = p;
+	const int k = rank[i];
+	ps[k] = p;
+	vs[k] = v;
+}
+
 __global__ void k_part2(vec4d* __restrict__ posm, vec4d* __restrict__ vel, const vec4d* __restrict__ acc, int lo, int hi, double dt, int pre_drift_next) {
 	const int i = lo + blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= hi) return;
@@ -59,6 +76,14 @@ int ass_launch_part1_range(ass_sim* s, double dt, int lo, int hi) {
 	if (hi <= lo) return ASS_OK;
 	ass_tic(s, ASS_K_LEAPFROG);
 	k_part1<<<(hi - lo + 255) / 256, 256, 0, s->stream>>>(s->posm, s->vel, lo, hi, dt);
+	LAUNCH_CHECK();
+	ass_toc(s, ASS_K_LEAPFROG);
+	return ASS_OK;
+}
+int ass_launch_part1_mirrored(ass_sim* s, double dt) {
+	if (s->n <= 0) return ASS_OK;
+	ass_tic(s, ASS_K_LEAPFROG);
+	k_part1_mirrored<<<(s->n + 255) / 256, 256, 0, s->stream>>>(s->posm, s->vel, s->rank, s->ps, s->vs, s->n, dt);
 	LAUNCH_CHECK();
 	ass_toc(s, ASS_K_LEAPFROG);
 	return ASS_OK;
@@ -131,11 +156,16 @@ static int step_loop(ass_sim* s, int nsteps, bool with_hb) {
 	// does gravity's result reach the kick?  (af == 2 zeroes it again, as the reference would)
 	const bool grav = P.gravity == 1 && af != 2;
 	int rc;
+	// does the rank-ordered mirror (ps / vs) hold exactly posm / vel?  Only the two kernels of this loop that write
+	// both keep it so; anything else (heartbeat shift, a caller's own kernels between calls) leaves it stale and the
+	// spring launcher re-gathers it.
+	bool mirror_fresh = false;
 	for (int step = 0; step < nsteps; step++) {
 		const double dt = s->prm.dt;
 		const bool last = (step == nsteps - 1);
 		if (!s->predrifted) {
-			if ((rc = ass_launch_part1(s, dt))) return rc;
+			if ((rc = have_springs ? ass_launch_part1_mirrored(s, dt) : ass_launch_part1(s, dt))) return rc;
+			mirror_fresh = have_springs;
 		}
 		s->predrifted = false;
 		s->prm.t += dt / 2.;
@@ -148,7 +178,8 @@ static int step_loop(ass_sim* s, int nsteps, bool with_hb) {
 		if (have_springs) {
 			// af == 1 with gravity NONE: accelerations accumulate across steps, exactly as in the reference
 			const bool zero_first = (af == 2);
-			if ((rc = ass_launch_spring_kick_drift(s, zero_first, dt, pre))) return rc;
+			if ((rc = ass_launch_spring_kick_drift(s, zero_first, dt, pre, mirror_fresh))) return rc;
+			mirror_fresh = pre;
 		} else {
 			if (af == 2) {
 				if ((rc = ass_launch_zero_accel(s))) return rc;
@@ -164,6 +195,7 @@ static int step_loop(ass_sim* s, int nsteps, bool with_hb) {
 			// x -= CoM for all N particles (physics.cpp:103-108) and, unless this is the last step, the next part1
 			if ((rc = ass_launch_shift(s, 0, s->n, s->d_red, false, -1.0, last ? 0.0 : dt))) return rc;
 			s->predrifted = !last;
+			mirror_fresh = false;
 		}
 	}
 	return ASS_OK;

@@ -99,3 +99,56 @@ extern "C" int ass_probe_copy_bw(long long bytes, double* gbs) {
 	cudaFree(b);
 	return ASS_OK;
 }
+
+// ---- self-check of the branch-free square root used by the spring kernels (spring_math.cuh) ----
+#include "spring_math.cuh"
+
+namespace {
+__device__ __forceinline__ uint64_t splitmix(uint64_t& x) {
+	x += 0x9E3779B97F4A7C15ULL;
+	uint64_t z = x;
+	z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+	z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+	return z ^ (z >> 31);
+}
+// every thread tries `per_thread` arguments: random mantissa, exponent uniform in [2^e_lo, 2^e_hi)
+__global__ void k_check_sqrt(long long per_thread, int e_lo, int e_hi, uint64_t seed, unsigned long long* mismatches, double* first_bad) {
+	uint64_t st = seed + 0x1234567ULL * ((uint64_t) blockIdx.x * blockDim.x + threadIdx.x);
+	unsigned long long bad = 0;
+	for (long long q = 0; q < per_thread; q++) {
+		const uint64_t r = splitmix(st);
+		const int ex = e_lo + (int) ((r >> 52) % (uint64_t) (e_hi - e_lo));
+		const uint64_t bits = ((uint64_t) (ex + 1023) << 52) | (r & 0x000FFFFFFFFFFFFFULL);
+		const double a = __longlong_as_double((long long) bits);
+		if (__double_as_longlong(sqrt_rn_normal(a)) != __double_as_longlong(__dsqrt_rn(a))) {
+			if (bad == 0 && atomicAdd(mismatches, 0ULL) == 0) *first_bad = a;
+			bad++;
+		}
+	}
+	if (bad) atomicAdd(mismatches, bad);
+}
+}  // namespace
+
+extern "C" int ass_selfcheck_sqrt(long long samples, int exp_lo, int exp_hi, long long* mismatches, double* first_bad) {
+	REQUIRE(mismatches && first_bad, ASS_EINVAL, "null out");
+	REQUIRE(samples > 0 && exp_hi > exp_lo && exp_lo > -960 && exp_hi < 1020, ASS_EINVAL, "bad range");
+	int rc = ass_ensure_device();
+	if (rc) return rc;
+	const int blocks = ass_sm_count() * 8, threads = 256;
+	const long long per_thread = (samples + (long long) blocks * threads - 1) / ((long long) blocks * threads);
+	unsigned long long* d_bad = nullptr;
+	double* d_first = nullptr;
+	CU_TRY(cudaMalloc(&d_bad, sizeof(unsigned long long)));
+	CU_TRY(cudaMalloc(&d_first, sizeof(double)));
+	CU_TRY(cudaMemset(d_bad, 0, sizeof(unsigned long long)));
+	CU_TRY(cudaMemset(d_first, 0, sizeof(double)));
+	k_check_sqrt<<<blocks, threads>>>(per_thread, exp_lo, exp_hi, 0xC0FFEEULL, d_bad, d_first);
+	LAUNCH_CHECK();
+	unsigned long long bad = 0;
+	CU_TRY(cudaMemcpy(&bad, d_bad, sizeof(bad), cudaMemcpyDeviceToHost));
+	CU_TRY(cudaMemcpy(first_bad, d_first, sizeof(double), cudaMemcpyDeviceToHost));
+	cudaFree(d_bad);
+	cudaFree(d_first);
+	*mismatches = (long long) bad;
+	return ASS_OK;
+}

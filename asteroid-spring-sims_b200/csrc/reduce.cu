@@ -209,23 +209,27 @@ __global__ void __launch_bounds__(RB) k_node_diag(const vec4d* __restrict__ posm
 }
 
 // spring sums: SPE (physics.cpp:457-476) and damping power (physics.cpp:409-454).  Each spring appears as two
-// half-edges; take the one stored at its lower endpoint (nbr > owner) so every spring counts once.
-__global__ void __launch_bounds__(RB) k_spring_diag(const vec4d* __restrict__ posm, const vec4d* __restrict__ vel,
+// half-edges; take the one whose neighbour ranks above its owner so every spring counts once.  Rows and HalfEdge::nbr
+// are in spatial rank order (common.cuh); `order` maps a rank back to the node.
+__global__ void __launch_bounds__(RB) k_spring_diag(const vec4d* __restrict__ posm, const vec4d* __restrict__ vel, const int* __restrict__ order,
 		const int* __restrict__ row_ptr, const HalfEdge* __restrict__ he, const double2* __restrict__ pal, int n, double* __restrict__ part) {
 	double v[2] = { 0.0, 0.0 };
-	for (int i = blockIdx.x * RB + threadIdx.x; i < n; i += gridDim.x * RB) {
+	for (int k = blockIdx.x * RB + threadIdx.x; k < n; k += gridDim.x * RB) {
+		const int i = order[k];
 		const vec4d pi = posm[i], vi = vel[i];
-		for (int e = row_ptr[i]; e < row_ptr[i + 1]; e++) {
+		for (int e = row_ptr[k]; e < row_ptr[k + 1]; e++) {
 			const HalfEdge h = he[e];
-			if (h.nbr < i) continue;
+			const int kn = h.nbr;
+			if (kn < k) continue;
+			const int j = order[kn];
 			const double2 kg = pal[h.pal];
-			const vec4d pj = posm[h.nbr];
+			const vec4d pj = posm[j];
 			const double dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
 			const double len = __dadd_rn(ref_len(dx, dy, dz), ASS_L_EPS);
 			const double ext = len - h.rs0;
 			v[0] += kg.x * (ext * ext) / 2.0;
 			if (kg.y != 0.0) {
-				const vec4d vj = vel[h.nbr];
+				const vec4d vj = vel[j];
 				const double sr = ((vi.x - vj.x) * dx + (vi.y - vj.y) * dy + (vi.z - vj.z) * dz) / (len * len);
 				const double m_red = pi.w * pj.w / (pi.w + pj.w);
 				v[1] += kg.y * m_red * (sr * sr);
@@ -411,7 +415,7 @@ extern "C" int ass_diagnostics(ass_sim* s, int lo, int hi, int want_gpe, double 
 	LAUNCH_CHECK();
 	if (s->ns > 0) {
 		const int g2 = reduce_grid(s->n);
-		k_spring_diag<<<g2, RB, 0, s->stream>>>(s->posm, s->vel, s->row_ptr, s->he, s->pal, s->n, part);
+		k_spring_diag<<<g2, RB, 0, s->stream>>>(s->posm, s->vel, s->order, s->row_ptr, s->he, s->pal, s->n, part);
 		LAUNCH_CHECK();
 		k_fold<2><<<1, RB, 0, s->stream>>>(part, g2, d + 18);
 		LAUNCH_CHECK();

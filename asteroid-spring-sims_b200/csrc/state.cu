@@ -3,7 +3,10 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <math.h>
+
 #include <algorithm>
+#include <cmath>
 #include <unordered_map>
 
 #include "common.cuh"
@@ -334,6 +337,8 @@ extern "C" int ass_destroy(ass_sim* s) {
 	if (s->stream) cudaStreamSynchronize(s->stream);
 	ass_shard_release(s);  // a sharded simulation's posm / vel alias its exported window
 	ass_sym_plan_free(s->sym_plan);
+	cudaFree(s->wave_off);
+	cudaFree(s->order); cudaFree(s->rank); cudaFree(s->ps); cudaFree(s->vs); cudaFree(s->ps_alt); cudaFree(s->vs_alt);
 	cudaFree(s->posm); cudaFree(s->vel); cudaFree(s->acc); cudaFree(s->posm_alt); cudaFree(s->vel_alt);
 	cudaFree(s->he); cudaFree(s->row_ptr); cudaFree(s->slot); cudaFree(s->pal);
 	cudaFree(s->stage.p); cudaFree(s->grav_partial.p); cudaFree(s->red_partial.p); cudaFree(s->flush.p);
@@ -593,15 +598,91 @@ int upload_palette(ass_sim* s, const std::vector<double2>& pal) {
 }
 }  // namespace
 
+namespace {
+// interleave the low 21 bits of v with two zero bits between each
+inline uint64_t spread21(uint64_t v) {
+	v &= 0x1fffffULL;
+	v = (v | v << 32) & 0x1f00000000ffffULL;
+	v = (v | v << 16) & 0x1f0000ff0000ffULL;
+	v = (v | v << 8) & 0x100f00f00f00f00fULL;
+	v = (v | v << 4) & 0x10c30c30c30c30c3ULL;
+	v = (v | v << 2) & 0x1249249249249249ULL;
+	return v;
+}
+
+// Rank the nodes along a Morton (Z-order) curve through their current positions: order[k] = node of rank k.
+// Non-finite coordinates rank as the box corner; ties keep node order (stable), so the ranking is deterministic.
+void morton_order(const vec4d* pos, size_t n, std::vector<int>& order) {
+	double lo[3] = { INFINITY, INFINITY, INFINITY }, hi[3] = { -INFINITY, -INFINITY, -INFINITY };
+	for (size_t i = 0; i < n; i++) {
+		const double c[3] = { pos[i].x, pos[i].y, pos[i].z };
+		for (int a = 0; a < 3; a++)
+			if (std::isfinite(c[a])) { lo[a] = std::min(lo[a], c[a]); hi[a] = std::max(hi[a], c[a]); }
+	}
+	double span = 0.0;
+	for (int a = 0; a < 3; a++)
+		if (hi[a] >= lo[a]) span = std::max(span, hi[a] - lo[a]);
+	const double scale = span > 0.0 ? 2097151.0 / span : 0.0;  // one cubic grid over the bounding box: cells stay cubes
+	std::vector<std::pair<uint64_t, int>> keyed(n);
+	for (size_t i = 0; i < n; i++) {
+		const double c[3] = { pos[i].x, pos[i].y, pos[i].z };
+		uint64_t key = 0;
+		for (int a = 0; a < 3; a++) {
+			double q = std::isfinite(c[a]) ? (c[a] - lo[a]) * scale : 0.0;
+			q = std::min(std::max(q, 0.0), 2097151.0);
+			key |= spread21((uint64_t) q) << a;
+		}
+		keyed[i] = { key, (int) i };
+	}
+	std::sort(keyed.begin(), keyed.end());
+	order.resize(n);
+	for (size_t k = 0; k < n; k++) order[k] = keyed[k].second;
+}
+
+int reserve_waves(ass_sim* s, int n_waves) {
+	if ((size_t) n_waves + 1 <= s->wave_cap) return ASS_OK;
+	cudaFree(s->wave_off);
+	s->wave_off = nullptr; s->wave_cap = 0;
+	const size_t cap = (size_t) n_waves + 1 + n_waves / 8 + 16;
+	if (cudaMalloc(&s->wave_off, sizeof(int) * cap) != cudaSuccess) {
+		cudaGetLastError();
+		ass_set_error("out of device memory for %zu wave offsets", cap);
+		return ASS_ENOMEM;
+	}
+	s->wave_cap = cap;
+	return ASS_OK;
+}
+
+int reserve_sorted(ass_sim* s, int n) {
+	if ((size_t) n + ASS_SPRING_WAVE <= s->sorted_cap) return ASS_OK;
+	cudaFree(s->order); cudaFree(s->rank); cudaFree(s->ps); cudaFree(s->vs); cudaFree(s->ps_alt); cudaFree(s->vs_alt);
+	s->order = s->rank = nullptr;
+	s->ps = s->vs = s->ps_alt = s->vs_alt = nullptr;
+	s->sorted_cap = 0;
+	const size_t cap = (size_t) n + n / 8 + 64 + ASS_SPRING_WAVE;
+	if (cudaMalloc(&s->order, sizeof(int) * cap) != cudaSuccess || cudaMalloc(&s->rank, sizeof(int) * cap) != cudaSuccess ||
+	    cudaMalloc(&s->ps, sizeof(vec4d) * cap) != cudaSuccess || cudaMalloc(&s->vs, sizeof(vec4d) * cap) != cudaSuccess ||
+	    cudaMalloc(&s->ps_alt, sizeof(vec4d) * cap) != cudaSuccess || cudaMalloc(&s->vs_alt, sizeof(vec4d) * cap) != cudaSuccess) {
+		cudaGetLastError();
+		ass_set_error("out of device memory for the rank-ordered mirror of %zu nodes", cap);
+		return ASS_ENOMEM;
+	}
+	s->sorted_cap = cap;
+	return ASS_OK;
+}
+}  // namespace
+
+void ass_morton_order(const vec4d* pos, size_t n, std::vector<int>& order) { morton_order(pos, n, order); }
+
 extern "C" int ass_set_springs(ass_sim* s, const ass_spring* sp, int ns) {
 	REQUIRE(s, ASS_EINVAL, "null sim");
 	REQUIRE(ns >= 0, ASS_EINVAL, "negative spring count");
 	REQUIRE(ns == 0 || sp, ASS_EINVAL, "null spring array");
 	REQUIRE(s->have_state, ASS_ESTATE, "upload particles before springs");
+	REQUIRE(!s->predrifted, ASS_ESTATE, "internal: positions are mid-step");
 	int rc = ass_ensure_device();
 	if (rc) return rc;
 	const int n = s->n;
-	std::vector<int> row((size_t) n + 1, 0);
 	for (int q = 0; q < ns; q++) {
 		const int i = sp[q].particle_1, j = sp[q].particle_2;
 		if (i < 0 || j < 0 || i >= n || j >= n) {
@@ -612,33 +693,56 @@ extern "C" int ass_set_springs(ass_sim* s, const ass_spring* sp, int ns) {
 			ass_set_error("ass_set_springs: spring %d connects particle %d to itself", q, i);
 			return ASS_EINVAL;
 		}
-		row[(size_t) i + 1]++;
-		row[(size_t) j + 1]++;
+	}
+	// spatial ranking of the nodes from their positions now (common.cuh: "springs")
+	std::vector<vec4d> pos((size_t) n);
+	if (n) {
+		CU_TRY(cudaMemcpyAsync(pos.data(), s->posm, sizeof(vec4d) * (size_t) n, cudaMemcpyDeviceToHost, s->stream));
+		CU_TRY(cudaStreamSynchronize(s->stream));
+	}
+	std::vector<int> order, rank((size_t) n);
+	morton_order(pos.data(), pos.size(), order);
+	for (int k = 0; k < n; k++) rank[(size_t) order[k]] = k;
+	std::vector<vec4d>().swap(pos);
+	// rows by rank
+	std::vector<int> row((size_t) n + 1, 0);
+	for (int q = 0; q < ns; q++) {
+		row[(size_t) rank[sp[q].particle_1] + 1]++;
+		row[(size_t) rank[sp[q].particle_2] + 1]++;
 	}
 	int maxdeg = 0;
-	for (int i = 0; i < n; i++) {
-		maxdeg = std::max(maxdeg, row[(size_t) i + 1]);
-		row[(size_t) i + 1] += row[i];
+	for (int k = 0; k < n; k++) {
+		maxdeg = std::max(maxdeg, row[(size_t) k + 1]);
+		row[(size_t) k + 1] += row[k];
 	}
 	std::vector<double2> pal;
 	std::vector<int> pidx;
 	build_palette(sp, ns, pal, pidx);
 	const size_t nhe = (size_t) 2 * ns;
-	std::vector<HalfEdge> he(nhe);
-	std::vector<int> slot(nhe);
-	std::vector<int> fill(row.begin(), row.end() - 1);
-	for (int q = 0; q < ns; q++) {
-		const int e[2] = { sp[q].particle_1, sp[q].particle_2 };
-		for (int side = 0; side < 2; side++) {
-			const int at = fill[e[side]]++;
-			HalfEdge h;
-			h.rs0 = sp[q].rs0;
-			h.nbr = e[1 - side];
-			h.pal = pidx[(size_t) q];
-			he[at] = h;
-			slot[(size_t) 2 * q + side] = at;
+	// (neighbour rank, 2*spring + side) per half-edge, bucketed by owner row, then each row ordered by neighbour rank so
+	// the lanes that share a request gather ascending, mostly adjacent sectors
+	std::vector<std::pair<int, int>> ent(nhe);
+	{
+		std::vector<int> fill(row.begin(), row.end() - 1);
+		for (int q = 0; q < ns; q++) {
+			const int e[2] = { rank[sp[q].particle_1], rank[sp[q].particle_2] };
+			for (int side = 0; side < 2; side++) ent[(size_t) fill[e[side]]++] = { e[1 - side], 2 * q + side };
 		}
 	}
+	for (int k = 0; k < n; k++) std::sort(ent.begin() + row[k], ent.begin() + row[(size_t) k + 1]);
+	std::vector<HalfEdge> he(nhe);
+	std::vector<int> slot(nhe);
+	for (size_t at = 0; at < nhe; at++) {
+		const int q = ent[at].second >> 1;
+		HalfEdge h;
+		h.rs0 = sp[q].rs0;
+		h.nbr = ent[at].first;
+		h.pal = pidx[(size_t) q];
+		he[at] = h;
+		slot[(size_t) ent[at].second] = (int) at;
+	}
+	std::vector<std::pair<int, int>>().swap(ent);
+	if ((rc = reserve_sorted(s, n))) return rc;
 	if (nhe > s->he_cap) {
 		cudaFree(s->he); cudaFree(s->slot);
 		s->he = nullptr; s->slot = nullptr; s->he_cap = 0;
@@ -650,10 +754,20 @@ extern "C" int ass_set_springs(ass_sim* s, const ass_spring* sp, int ns) {
 		}
 		s->he_cap = cap;
 	}
-	if ((size_t) n + 1 > s->row_cap) {
+	// waves of the streaming kernel; row_ptr and order padded so a wave is always a whole, 16-byte-multiple copy
+	const int W = ASS_SPRING_WAVE;
+	const int n_waves = (n + W - 1) / W;
+	row.resize((size_t) n_waves * W + 4, (int) nhe);
+	order.resize((size_t) n_waves * W, 0);
+	std::vector<int> wave_off((size_t) n_waves + 1);
+	int wave_he_max = 0;
+	for (int w = 0; w <= n_waves; w++) wave_off[(size_t) w] = row[(size_t) w * W];
+	for (int w = 0; w < n_waves; w++) wave_he_max = std::max(wave_he_max, wave_off[(size_t) w + 1] - wave_off[(size_t) w]);
+	if ((rc = reserve_waves(s, n_waves))) return rc;
+	if (row.size() > s->row_cap) {
 		cudaFree(s->row_ptr);
 		s->row_ptr = nullptr; s->row_cap = 0;
-		size_t cap = (size_t) n + 1 + n / 8 + 64;
+		size_t cap = row.size() + n / 8 + 64;
 		if (cudaMalloc(&s->row_ptr, sizeof(int) * cap) != cudaSuccess) {
 			cudaGetLastError();
 			ass_set_error("out of device memory for %zu row pointers", cap);
@@ -667,12 +781,20 @@ extern "C" int ass_set_springs(ass_sim* s, const ass_spring* sp, int ns) {
 		CU_TRY(cudaMemcpyAsync(s->he, he.data(), sizeof(HalfEdge) * nhe, cudaMemcpyHostToDevice, s->stream));
 		CU_TRY(cudaMemcpyAsync(s->slot, slot.data(), sizeof(int) * nhe, cudaMemcpyHostToDevice, s->stream));
 	}
-	CU_TRY(cudaMemcpyAsync(s->row_ptr, row.data(), sizeof(int) * ((size_t) n + 1), cudaMemcpyHostToDevice, s->stream));
+	CU_TRY(cudaMemcpyAsync(s->row_ptr, row.data(), sizeof(int) * row.size(), cudaMemcpyHostToDevice, s->stream));
+	CU_TRY(cudaMemcpyAsync(s->wave_off, wave_off.data(), sizeof(int) * wave_off.size(), cudaMemcpyHostToDevice, s->stream));
+	if (n) {
+		CU_TRY(cudaMemcpyAsync(s->order, order.data(), sizeof(int) * order.size(), cudaMemcpyHostToDevice, s->stream));
+		CU_TRY(cudaMemcpyAsync(s->rank, rank.data(), sizeof(int) * (size_t) n, cudaMemcpyHostToDevice, s->stream));
+	}
 	ass_toc(s, ASS_K_XFER);
 	CU_TRY(cudaStreamSynchronize(s->stream));  // the vectors above die here
 	s->ns = ns;
 	s->n_he = (int) nhe;
 	s->max_degree = maxdeg;
+	s->n_waves = n_waves;
+	s->wave_he_max = wave_he_max;
+	s->spring_epoch++;
 	return ASS_OK;
 }
 

@@ -220,6 +220,10 @@ int ass_l2_flush(ass_sim* sim);                    /* overwrite a buffer larger 
 int ass_probe_fp64_peak(int iters, double* tflops, double* ms);
 /* device copy bandwidth (read+write bytes / time) for a buffer of `bytes` */
 int ass_probe_copy_bw(long long bytes, double* gbs);
+/* Self-check of the branch-free, correctly rounded square root inside the spring kernels (csrc/spring_math.cuh) against
+ * CUDA's __dsqrt_rn on `samples` pseudo-random arguments with binary exponents in [exp_lo, exp_hi): the number of
+ * arguments whose results differ in any bit, and the first such argument. */
+int ass_selfcheck_sqrt(long long samples, int exp_lo, int exp_hi, long long* mismatches, double* first_bad);
 /* total number of kernel launches issued by this library in this process */
 long long ass_launch_count(void);
 

@@ -493,3 +493,12 @@ def test_pinned_rows_transfer_matches_pageable(gpu):
             gpu.host_unregister(Q)
     finally:
         pin.close()
+
+
+def test_branch_free_sqrt_matches_dsqrt_rn(gpu):
+    """len = sqrt(...) must be the reference's correctly rounded value bit for bit (at rest one ulp of len is 1e-10 of the
+    force).  The spring kernels use the fast path of __dsqrt_rn without its range check (csrc/spring_math.cuh)."""
+    bad, first = gpu.selfcheck_sqrt(1 << 28, -200, 200)
+    assert bad == 0, (bad, first)
+    bad, first = gpu.selfcheck_sqrt(1 << 26, -40, 8)      # the range squared spring lengths live in
+    assert bad == 0, (bad, first)
