@@ -23,7 +23,10 @@
 
 namespace {
 
-constexpr int ET = 1024;                       // threads per CTA: one body owns a whole SM
+#ifndef ASS_ENS_THREADS
+#define ASS_ENS_THREADS 1024
+#endif
+constexpr int ET = ASS_ENS_THREADS;            // threads per CTA: one body owns a whole SM
 constexpr int EW = ET / SPRING_LANES;          // nodes per wave (128)
 
 struct BodyDesc {
