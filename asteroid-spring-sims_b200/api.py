@@ -275,6 +275,27 @@ class Sim:
         _chk(lib().ass_diagnostics(self._h, C.c_int(lo), C.c_int(hi), C.c_int(int(want_gpe)), out))
         return np.array(out[:])
 
+    # -- phobos* terms (orb.cpp) --
+    def quadrupole_accel(self, J2, R, phi, theta, i_p):
+        _chk(lib().ass_quadrupole_accel(self._h, C.c_double(J2), C.c_double(R), C.c_double(phi), C.c_double(theta), C.c_int(i_p)))
+
+    def drift_resolved(self, timestep, inv_tau_a, inv_tau_e, i_part, lo, hi):
+        _chk(lib().ass_drift_resolved(self._h, C.c_double(timestep), C.c_double(inv_tau_a), C.c_double(inv_tau_e), C.c_int(i_part),
+                                      C.c_int(lo), C.c_int(hi)))
+
+    def drift_bin(self, timestep, inv_tau_a, inv_tau_e, part_1, part_2):
+        _chk(lib().ass_drift_bin(self._h, C.c_double(timestep), C.c_double(inv_tau_a), C.c_double(inv_tau_e), C.c_int(part_1), C.c_int(part_2)))
+
+    def sum_mass(self, lo, hi):
+        out = C.c_double()
+        _chk(lib().ass_sum_mass(self._h, C.c_int(lo), C.c_int(hi), C.byref(out)))
+        return out.value
+
+    def download_range(self, p, lo, hi, fields=F_ALL):
+        base, stride, n = _rows(p)
+        _chk(lib().ass_download_range(self._h, base, stride, C.c_int(lo), C.c_int(hi), C.c_uint(fields)))
+        return p
+
     # -- spring build --
     def connect_springs_dist(self, max_dist, lo, hi, k, gamma, existing=None):
         ptr = C.c_void_p()

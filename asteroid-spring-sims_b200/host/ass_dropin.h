@@ -8,7 +8,8 @@
 //                      reb_output_check
 //   C++ (src_spring)   spring_forces, zero_accel, connect_springs_dist, mindist, rand_ellipsoid,
 //                      center_sim, subtract_com, subtract_cov, move_resolved, compute_com, compute_cov,
-//                      set_gamma, divide_gamma, adjust_spring_props, kill_springs, add_spring_helper, del_spring
+//                      set_gamma, divide_gamma, adjust_spring_props, kill_springs, add_spring_helper, del_spring,
+//                      quadrupole_accel, drift_resolved, drift_bin, sum_mass
 //
 // Residency.  The host `r->particles[]` and the module-owned `std::vector<spring> springs` remain the API-visible
 // truth (SURVEY 8b "Ownership"); the device copy is a cache.

@@ -33,6 +33,7 @@ void reb_exit(const char* const msg);                                           
 #include "springs.h"
 #include "physics.h"
 #include "shapes.h"
+#include "orb.h"
 
 #include "ass_b200.h"
 #include "ass_dropin.h"
@@ -506,6 +507,47 @@ void move_resolved(reb_simulation* const r, Vector dx, Vector dv, int i_low, int
 	const double a[3] = { dx.getX(), dx.getY(), dx.getZ() }, b[3] = { dv.getX(), dv.getY(), dv.getZ() };
 	OK(ass_move_resolved(d.sim, a, b, i_low, i_high));
 	wrote(r, d, ASS_F_POS | ASS_F_VEL);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// src_spring/orb.cpp: the per-step terms of the phobos / phobos_deimos modules
+// ---------------------------------------------------------------------------------------------------
+// orb.cpp:311-366 (called from additional_forces after spring_forces, modules/phobos_deimos/problem.cpp:380-387)
+void quadrupole_accel(reb_simulation* const r, double J2_p, double R_p, double phi_p, double theta_p, int i_p) {
+	if (i_p >= r->N) return;
+	if (J2_p == 0.0) return;
+	Dropin& d = get(r);
+	ensure_dev(r, d);
+	push_params(r, d);
+	OK(ass_quadrupole_accel(d.sim, J2_p, R_p, phi_p, theta_p, i_p));
+	wrote(r, d, ASS_F_ACC);
+}
+
+// orb.cpp:253-302 (heartbeat of the phobos* modules)
+void drift_resolved(reb_simulation* const r, double timestep, double inv_tau_a, double inv_tau_e, int i_part, int i_low, int i_high) {
+	Dropin& d = get(r);
+	ensure_dev(r, d);
+	push_params(r, d);
+	OK(ass_drift_resolved(d.sim, timestep, inv_tau_a, inv_tau_e, i_part, i_low, i_high));
+	wrote(r, d, ASS_F_VEL);
+}
+
+// orb.cpp:198-250
+void drift_bin(reb_simulation* const r, double timestep, double inv_tau_a, double inv_tau_e, int part_1, int part_2) {
+	Dropin& d = get(r);
+	ensure_dev(r, d);
+	push_params(r, d);
+	OK(ass_drift_bin(d.sim, timestep, inv_tau_a, inv_tau_e, part_1, part_2));
+	wrote(r, d, ASS_F_VEL);
+}
+
+// orb.cpp:438-449
+double sum_mass(reb_simulation* const r, int i_low, int i_high) {
+	Dropin& d = get(r);
+	ensure_dev(r, d);
+	double m = 0.0;
+	OK(ass_sum_mass(d.sim, i_low, i_high > i_low ? i_high : i_low, &m));
+	return m;
 }
 
 // src_spring/shapes.cpp:814-833

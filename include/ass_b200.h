@@ -152,6 +152,20 @@ int ass_spin_body(ass_sim* sim, int i_low, int i_high, const double omega[3]); /
  * [12] dEdt_total (:409-454), [13..18] mom_inertia xx yy zz xy xz yz (:116-134), [19] sum_mass (orb.cpp:438-449) */
 int ass_diagnostics(ass_sim* sim, int i_low, int i_high, int want_gpe, double out[20]);
 
+/* ---- the other per-step terms of the phobos / phobos_deimos modules (src_spring/orb.cpp) ---- */
+/* quadrupole_accel, orb.cpp:311-366: a += J2 acceleration from particle i_p (with params.G), reaction onto i_p.
+ * No-op for i_p >= N or J2_p == 0, as in the reference. */
+int ass_quadrupole_accel(ass_sim* sim, double J2_p, double R_p, double phi_p, double theta_p, int i_p);
+/* drift_resolved, orb.cpp:253-302: orbital migration between point mass i_part and the resolved body [i_low, i_high):
+ * velocities only, momentum of the pair conserved.  Entirely on the device (no host round trip). */
+int ass_drift_resolved(ass_sim* sim, double timestep, double inv_tau_a, double inv_tau_e, int i_part, int i_low, int i_high);
+/* drift_bin, orb.cpp:198-250: the same between two point masses */
+int ass_drift_bin(ass_sim* sim, double timestep, double inv_tau_a, double inv_tau_e, int part_1, int part_2);
+int ass_sum_mass(ass_sim* sim, int i_low, int i_high, double* out); /* orb.cpp:438-449 */
+/* ass_download_particles for rows [i_low, i_high) only: `base` is row 0 of the caller's array (e.g. to read one point
+ * mass for output while the body stays resident). */
+int ass_download_range(ass_sim* sim, void* base, size_t stride_bytes, int i_low, int i_high, unsigned fields);
+
 /* ---- spring build: connect_springs_dist, src_spring/springs.cpp:110-143 ---- */
 /* Uniform-grid cell-list search on the device positions of particles [i_low, i_high).  Appends to the caller's list
  * exactly what the reference would: pairs (i<j) with sqrt(fma(dz,dz,fma(dx,dx,dy*dy))) < max_dist (strict), in

@@ -744,3 +744,80 @@ void orc_diagnostics(const double* p, int i_low, int i_high, const orc_spring* s
 	memcpy(out + 13, I, sizeof(I));
 	out[19] = orc_sum_mass(p, i_low, i_high);
 }
+
+/* ------------------------------------------------------------------------------------------------ */
+/* the other per-step terms of the phobos* modules (src_spring/orb.cpp)                             */
+/* ------------------------------------------------------------------------------------------------ */
+
+/* quadrupole_accel, orb.cpp:311-366.  Operator order of
+ *     Vector a = constant * r / r5 * (5.0 * cos2 - diff) / particles[i].m;
+ * is ((((constant * r) / r5) * (5 cos2 - diff)) / m), all component-wise (matrix_math.cpp:418-424, 453-460);
+ * `scalar - Vector` is -(Vector - scalar) (matrix_math.cpp:453-455).  The reaction on i_p is accumulated in particle
+ * order.  The racy `#pragma omp parallel for` of the reference is off. */
+void orc_quadrupole_accel(double* p, int n, double G, double J2, double R, double phi, double theta, int i_p) {
+	if (i_p >= n) return;       /* :315-316 */
+	if (J2 == 0.0) return;      /* :319-320 */
+	const double Gmc = G * P(i_p, ORC_M);
+	const double constant = 1.5 * Gmc * J2 * pow(R, 2.0);
+	const double xhat[3] = { sin(theta) * cos(phi), sin(theta) * sin(phi), cos(theta) };
+	const double diff[3] = { 1.0, 1.0, 3.0 };
+	for (int i = 0; i < n; i++) {
+		if (i == i_p) continue;
+		const double r[3] = { P(i, ORC_X) - P(i_p, ORC_X), P(i, ORC_Y) - P(i_p, ORC_Y), P(i, ORC_Z) - P(i_p, ORC_Z) };
+		const double rl = len3(r[0], r[1], r[2]);
+		const double r5 = pow(rl, 5.0) + 0.5;
+		const double cos2 = pow(dot3(r[0], r[1], r[2], xhat[0], xhat[1], xhat[2]) / rl, 2.0);
+		double a[3];
+		for (int c = 0; c < 3; c++) a[c] = (constant * r[c]) / r5 * (-(diff[c] - 5.0 * cos2)) / P(i, ORC_M);
+		P(i, ORC_AX) += a[0]; P(i, ORC_AY) += a[1]; P(i, ORC_AZ) += a[2];
+		const double mfac = P(i, ORC_M) / P(i_p, ORC_M);
+		P(i_p, ORC_AX) -= a[0] * mfac; P(i_p, ORC_AY) -= a[1] * mfac; P(i_p, ORC_AZ) -= a[2] * mfac;
+	}
+}
+
+/* the common tail of drift_bin / drift_resolved (orb.cpp:218-238, 271-291): dv from the relative state (x, v) */
+static void drift_dv(const double* x, const double* v, double GM, double timestep, double inv_tau_a, double inv_tau_e, double* dv) {
+	const double rad = len3(x[0], x[1], x[2]);
+	const double v_cent = sqrt(GM / rad);
+	double xv[3], rl[3];
+	cross3(x, v, xv);
+	cross3(x, xv, rl);
+	const double n = len3(rl[0], rl[1], rl[2]);
+	for (int c = 0; c < 3; c++) {
+		const double dir = rl[c] / n;
+		const double delta_v = v[c] - v_cent * dir;
+		dv[c] = timestep * (v[c] * inv_tau_a / 2.0 + delta_v * inv_tau_e);
+	}
+}
+
+void orc_drift_resolved(double* p, double G, double timestep, double inv_tau_a, double inv_tau_e, int i_part, int i_low, int i_high) {
+	const double m1 = P(i_part, ORC_M), m2 = orc_sum_mass(p, i_low, i_high);
+	double com[3], cov[3], x[3], v[3], dv[3];
+	orc_compute_com(p, i_low, i_high, com);
+	orc_compute_cov(p, i_low, i_high, cov);
+	for (int c = 0; c < 3; c++) {
+		x[c] = com[c] - P(i_part, ORC_X + c);
+		v[c] = cov[c] - P(i_part, ORC_VX + c);
+	}
+	drift_dv(x, v, G * (m1 + m2), timestep, inv_tau_a, inv_tau_e, dv);
+	double dv2[3], zero[3] = { 0, 0, 0 };
+	for (int c = 0; c < 3; c++) {
+		P(i_part, ORC_VX + c) -= m1 * dv[c] / (m1 + m2);   /* dv_1, orb.cpp:293-298 */
+		dv2[c] = -(m2 * dv[c] / (m1 + m2));                /* move_resolved(zero, -dv_2), orb.cpp:301 */
+	}
+	orc_move_resolved(p, zero, dv2, i_low, i_high);
+}
+
+void orc_drift_bin(double* p, double G, double timestep, double inv_tau_a, double inv_tau_e, int part_1, int part_2) {
+	const double m1 = P(part_1, ORC_M), m2 = P(part_2, ORC_M);
+	double x[3], v[3], dv[3];
+	for (int c = 0; c < 3; c++) {
+		x[c] = P(part_2, ORC_X + c) - P(part_1, ORC_X + c);
+		v[c] = P(part_2, ORC_VX + c) - P(part_1, ORC_VX + c);
+	}
+	drift_dv(x, v, G * (m1 + m2), timestep, inv_tau_a, inv_tau_e, dv);
+	for (int c = 0; c < 3; c++) {
+		P(part_1, ORC_VX + c) -= m1 * dv[c] / (m1 + m2);
+		P(part_2, ORC_VX + c) -= m2 * dv[c] / (m1 + m2);
+	}
+}

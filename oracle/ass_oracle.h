@@ -86,6 +86,11 @@ void orc_set_gamma(orc_spring* s, int ns, double g);
 /* out[20]: same layout as ref_diagnostics in oracle/ref_shim.cpp */
 void orc_diagnostics(const double* p, int i_low, int i_high, const orc_spring* s, int ns, double G, int want_gpe, double* out);
 
+/* ---- the other per-step terms of the phobos* modules (orb.cpp) ---- */
+void orc_quadrupole_accel(double* p, int n, double G, double J2, double R, double phi, double theta, int i_p);     /* orb.cpp:311-366 */
+void orc_drift_resolved(double* p, double G, double timestep, double inv_tau_a, double inv_tau_e, int i_part, int i_low, int i_high); /* orb.cpp:253-302 */
+void orc_drift_bin(double* p, double G, double timestep, double inv_tau_a, double inv_tau_e, int part_1, int part_2);                 /* orb.cpp:198-250 */
+
 #ifdef __cplusplus
 }
 #endif

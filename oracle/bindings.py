@@ -191,6 +191,19 @@ class Oracle:
         return out
 
 
+    def quadrupole_accel(self, p, G, J2, R, phi, theta, i_p):
+        self.lib.orc_quadrupole_accel(self._p(p), C.c_int(len(p)), C.c_double(G), C.c_double(J2), C.c_double(R), C.c_double(phi),
+                                      C.c_double(theta), C.c_int(i_p))
+
+    def drift_resolved(self, p, G, timestep, inv_tau_a, inv_tau_e, i_part, lo, hi):
+        self.lib.orc_drift_resolved(self._p(p), C.c_double(G), C.c_double(timestep), C.c_double(inv_tau_a), C.c_double(inv_tau_e),
+                                    C.c_int(i_part), C.c_int(lo), C.c_int(hi))
+
+    def drift_bin(self, p, G, timestep, inv_tau_a, inv_tau_e, part_1, part_2):
+        self.lib.orc_drift_bin(self._p(p), C.c_double(G), C.c_double(timestep), C.c_double(inv_tau_a), C.c_double(inv_tau_e),
+                               C.c_int(part_1), C.c_int(part_2))
+
+
 class Ref:
     """The unmodified reference (oracle/_ref/libref_oracle*.so). One live simulation at a time (its spring list is a
     process-wide global, as in the reference's modules)."""
@@ -329,3 +342,13 @@ class Ref:
         out = np.zeros(20)
         self.lib.ref_diagnostics(self.h, C.c_int(lo), C.c_int(hi), C.c_int(int(want_gpe)), _d(out))
         return out
+
+    def quadrupole_accel(self, J2, R, phi, theta, i_p):
+        self.lib.ref_quadrupole_accel(self.h, C.c_double(J2), C.c_double(R), C.c_double(phi), C.c_double(theta), C.c_int(i_p))
+
+    def drift_resolved(self, timestep, inv_tau_a, inv_tau_e, i_part, lo, hi):
+        self.lib.ref_drift_resolved(self.h, C.c_double(timestep), C.c_double(inv_tau_a), C.c_double(inv_tau_e), C.c_int(i_part),
+                                    C.c_int(lo), C.c_int(hi))
+
+    def drift_bin(self, timestep, inv_tau_a, inv_tau_e, part_1, part_2):
+        self.lib.ref_drift_bin(self.h, C.c_double(timestep), C.c_double(inv_tau_a), C.c_double(inv_tau_e), C.c_int(part_1), C.c_int(part_2))

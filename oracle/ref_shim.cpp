@@ -220,4 +220,15 @@ void ref_diagnostics(void* h, int lo, int hi, int want_gpe, double* out) {
 	out[19] = sum_mass(r, lo, hi);
 }
 
+// ---- the other per-step force / heartbeat terms of the phobos* modules (src_spring/orb.cpp) ----
+void ref_quadrupole_accel(void* h, double J2, double R, double phi, double theta, int i_p) {
+	quadrupole_accel((reb_simulation*) h, J2, R, phi, theta, i_p);   // orb.cpp:311-366
+}
+void ref_drift_resolved(void* h, double timestep, double inv_tau_a, double inv_tau_e, int i_part, int lo, int hi) {
+	drift_resolved((reb_simulation*) h, timestep, inv_tau_a, inv_tau_e, i_part, lo, hi);   // orb.cpp:253-302
+}
+void ref_drift_bin(void* h, double timestep, double inv_tau_a, double inv_tau_e, int part_1, int part_2) {
+	drift_bin((reb_simulation*) h, timestep, inv_tau_a, inv_tau_e, part_1, part_2);   // orb.cpp:198-250
+}
+
 }  // extern "C"

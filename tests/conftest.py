@@ -89,3 +89,8 @@ def gpu():
     import asteroid_spring_sims_b200 as A
     A.init(int(os.environ.get("LOCAL_RANK", "0")))
     return A
+
+
+@pytest.fixture(scope="session")
+def orb_golden():
+    return load_golden("orb")

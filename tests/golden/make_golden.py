@@ -146,6 +146,49 @@ def lattices():
     print("lattices", {k: v.shape for k, v in out.items()})
 
 
+def orb():
+    """src_spring/orb.cpp terms of the phobos* modules run by the reference: quadrupole_accel, drift_resolved, drift_bin.
+    Fixture A is OrbTest's (modules/tests/tests.cpp:152-225: 3 body particles + a 400-mass perturber); fixture B is a
+    330-node random ellipsoid with a Mars-like point mass and a second point mass."""
+    out = {}
+    P = np.zeros((4, 11))
+    P[0, :3] = (0, 0, 0); P[1, :3] = (1, 2, 2); P[2, :3] = (2, 3, 6); P[3, :3] = (60, 3, -20)
+    P[:, 3:6] = P[:, :3] * 0.1; P[3, 3:6] = (0.3, -1.0, 0.25)
+    P[:, 9] = (1, 2, 3, 400); P[:, 6:9] = 0.5
+    out["A_in"] = P
+    for tag, (phi, theta) in (("pole", (0.0, 0.0)), ("tilt", (0.7, 1.1))):
+        with Ref() as r:
+            r.config(gravity_basic=0, G=0.7, n_perts=1); r.add_particles(P)
+            r.quadrupole_accel(5.0, 50.0, phi, theta, 3)      # OrbTest.QuadAccel's J2, R_p
+            out["A_quad_" + tag] = r.get()
+    with Ref() as r:
+        r.config(gravity_basic=0, G=0.7, n_perts=1); r.add_particles(P)
+        r.drift_resolved(10.0, 0.2, 0.2, 3, 0, 3)             # OrbTest.DriftRes's arguments
+        out["A_drift_resolved"] = r.get()
+    with Ref() as r:
+        r.config(gravity_basic=0, G=0.7, n_perts=1); r.add_particles(P)
+        r.drift_bin(10.0, 0.2, 0.2, 3, 1)
+        out["A_drift_bin"] = r.get()
+    with Ref() as r:
+        r.seed(SEED)
+        n = r.rand_ellipsoid(0.15, A, B, C_, 1.0)
+        r.subtract_com(0, n); r.subtract_cov(0, n); r.spin_body(0, n, OMEGA)
+        body = r.get()
+    pm = np.zeros((2, 11)); pm[0, :3] = (7.0, 0.3, -0.2); pm[0, 3:6] = (0.01, 0.38, 0.02); pm[0, 9] = 1.0
+    pm[1, :3] = (-3.0, 9.0, 1.0); pm[1, 3:6] = (-0.2, -0.1, 0.0); pm[1, 9] = 0.05
+    Q = np.vstack([body, pm]); Q[:, 6:9] = Q[:, :3] * 0.01
+    out["B_in"] = Q
+    with Ref() as r:
+        r.config(gravity_basic=0, G=1.0, n_perts=2); r.add_particles(Q)
+        r.quadrupole_accel(1.96e-3, 0.5, 0.3, 0.4, n)        # a Mars-like J2 seen from a body at a = 7
+        out["B_quad"] = r.get()
+        r.drift_resolved(1e-3, 1e-2, 3e-2, n, 0, n)
+        r.drift_bin(1e-3, 1e-2, 3e-2, n, n + 1)
+        out["B_drift"] = r.get()
+    np.savez_compressed(os.path.join(HERE, "orb.npz"), **out)
+    print("orb", {k: v.shape for k, v in out.items()})
+
+
 def c2():
     """BASELINE config C2: d = 0.0474 -> N = 9327, NS = 134162.  ~90 s of reference time (its O(N^2) paths)."""
     d = 0.0474
@@ -170,5 +213,6 @@ if __name__ == "__main__":
     lattices()
     body("ellipsoid_d015", 0.15, 20, 200, 10)
     body("c1_d010", 0.10, 20, 200, 20)
+    orb()
     if "--c2" in sys.argv:
         c2()

@@ -58,7 +58,9 @@ def test_module_links_both_ways_and_reference_runs(tmp_path):
     assert len(ext) >= 4 and state.shape == (330, 10)
     # the drop-in build exports the reference's symbols (it defines them itself)
     syms = subprocess.run(["nm", "--defined-only", os.path.join(BUILD, "synth_b200")], stdout=subprocess.PIPE, text=True).stdout
-    for s in ("reb_integrate", "reb_step", "_Z13spring_forcesP14reb_simulation", "_Z20connect_springs_distP14reb_simulationdii6spring"):
+    for s in ("reb_integrate", "reb_step", "_Z13spring_forcesP14reb_simulation", "_Z20connect_springs_distP14reb_simulationdii6spring",
+              "_Z16quadrupole_accelP14reb_simulationddddi", "_Z14drift_resolvedP14reb_simulationdddiii", "_Z9drift_binP14reb_simulationdddii",
+              "_Z8sum_massP14reb_simulationii"):
         assert re.search(r" T %s$" % re.escape(s), syms, re.M), s
 
 

@@ -502,3 +502,48 @@ def test_branch_free_sqrt_matches_dsqrt_rn(gpu):
     assert bad == 0, (bad, first)
     bad, first = gpu.selfcheck_sqrt(1 << 26, -40, 8)      # the range squared spring lengths live in
     assert bad == 0, (bad, first)
+
+
+# ---------------------------------------------------------------------------------------------------
+# src_spring/orb.cpp terms of the phobos* modules
+# ---------------------------------------------------------------------------------------------------
+def test_orb_terms_match_reference(gpu, oracle, orb_golden):
+    g = orb_golden
+    A = g["A_in"]
+    with new_sim(gpu, A, G=0.7, n_perts=1) as s:
+        for tag, (phi, theta) in (("pole", (0.0, 0.0)), ("tilt", (0.7, 1.1))):
+            s.upload(A)
+            s.quadrupole_accel(5.0, 50.0, phi, theta, 3)
+            out = s.download(A.copy())
+            assert acc_err(out[:, 6:9], g["A_quad_" + tag][:, 6:9]) <= ACC_TOL, tag
+            assert same_bits(out[:, :6], A[:, :6])
+        s.upload(A); s.quadrupole_accel(0.0, 50.0, 0.0, 0.0, 3); s.quadrupole_accel(5.0, 50.0, 0.0, 0.0, 4)   # orb.cpp:315-320
+        assert same_bits(s.download(A.copy()), A)
+        s.upload(A); s.drift_resolved(10.0, 0.2, 0.2, 3, 0, 3)
+        out = s.download(A.copy())
+        assert np.allclose(out[:, 3:6], g["A_drift_resolved"][:, 3:6], rtol=1e-13, atol=1e-15)
+        assert same_bits(out[:, :3], A[:, :3])
+        s.upload(A); s.drift_bin(10.0, 0.2, 0.2, 3, 1)
+        out = s.download(A.copy())
+        assert np.allclose(out[:, 3:6], g["A_drift_bin"][:, 3:6], rtol=1e-13, atol=1e-15)
+        assert s.sum_mass(0, 3) == 6.0 and s.sum_mass(1, 1) == 0.0                                        # OrbTest.TotMass
+    B = g["B_in"]; n = len(B) - 2
+    for sequential in (True, False):
+        with new_sim(gpu, B, G=1.0, n_perts=2) as s:
+            s.set_sum_order(sequential)
+            s.quadrupole_accel(1.96e-3, 0.5, 0.3, 0.4, n)
+            out = s.download(B.copy())
+            assert acc_err(out[:, 6:9], g["B_quad"][:, 6:9]) <= ACC_TOL
+            s.drift_resolved(1e-3, 1e-2, 3e-2, n, 0, n)
+            s.drift_bin(1e-3, 1e-2, 3e-2, n, n + 1)
+            out = s.download(B.copy())
+            assert np.allclose(out[:, 3:6], g["B_drift"][:, 3:6], rtol=1e-13, atol=1e-16)
+            # a row range comes back alone (the point masses, for write_pt_mass while the body stays resident)
+            part = np.full_like(B, -1.0)
+            s.download_range(part, n, n + 2)
+            assert same_bits(part[n:, :10], out[n:, :10]) and np.all(part[:n] == -1.0)
+    with new_sim(gpu, A) as s:
+        with pytest.raises(gpu.AssError):
+            s.drift_resolved(1.0, 0.1, 0.1, 1, 0, 3)        # the point mass lies inside the body range
+        with pytest.raises(gpu.AssError):
+            s.drift_bin(1.0, 0.1, 0.1, 2, 2)

@@ -309,3 +309,45 @@ def test_live_reference_random_bodies(oracle, ref):
             assert sim.t == r.t
         finally:
             r.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# src_spring/orb.cpp terms of the phobos* modules: quadrupole_accel, drift_resolved, drift_bin
+# ---------------------------------------------------------------------------------------------------
+def test_golden_orb_terms(oracle, orb_golden):
+    g = orb_golden
+    A = g["A_in"]
+    for tag, (phi, theta) in (("pole", (0.0, 0.0)), ("tilt", (0.7, 1.1))):
+        p = A.copy(); oracle.quadrupole_accel(p, 0.7, 5.0, 50.0, phi, theta, 3)
+        assert same_bits(p, g["A_quad_" + tag]), tag
+    p = A.copy(); oracle.drift_resolved(p, 0.7, 10.0, 0.2, 0.2, 3, 0, 3)
+    assert same_bits(p, g["A_drift_resolved"])
+    p = A.copy(); oracle.drift_bin(p, 0.7, 10.0, 0.2, 0.2, 3, 1)
+    assert same_bits(p, g["A_drift_bin"])
+    B = g["B_in"]; n = len(B) - 2
+    p = B.copy(); oracle.quadrupole_accel(p, 1.0, 1.96e-3, 0.5, 0.3, 0.4, n)
+    assert same_bits(p, g["B_quad"])
+    oracle.drift_resolved(p, 1.0, 1e-3, 1e-2, 3e-2, n, 0, n)
+    oracle.drift_bin(p, 1.0, 1e-3, 1e-2, 3e-2, n, n + 1)
+    assert same_bits(p, g["B_drift"])
+    # no-op rules of orb.cpp:315-320
+    p = A.copy(); oracle.quadrupole_accel(p, 0.7, 0.0, 50.0, 0.0, 0.0, 3); assert same_bits(p, A)
+    p = A.copy(); oracle.quadrupole_accel(p, 0.7, 5.0, 50.0, 0.0, 0.0, 4); assert same_bits(p, A)
+
+
+def test_kat_quadrupole_closed_form(oracle, orb_golden):
+    """OrbTest.QuadAccel (modules/tests/tests.cpp:1684-1733): pole along z, closed-form J2 field, 1e-5 relative --
+    away from the reference's `+ 0.5` softening of r^5 (orb.cpp:340), i.e. with the perturber far away."""
+    P = orb_golden["A_in"].copy(); P[:, 6:9] = 0.0
+    G, J2s, Rp = 0.7, 5.0, 50.0
+    want = np.zeros((4, 3))
+    J2 = -J2s * G * P[3, 9] * Rp ** 2
+    for i in range(3):
+        x, y, z = P[3, :3] - P[i, :3]
+        r7 = np.linalg.norm(P[3, :3] - P[i, :3]) ** 7
+        want[i] = (J2 * x / r7 * (6 * z * z - 1.5 * (x * x + y * y)), J2 * y / r7 * (6 * z * z - 1.5 * (x * x + y * y)),
+                   J2 * z / r7 * (3 * z * z - 4.5 * (x * x + y * y)))
+        want[i] /= P[i, 9]
+        want[3] -= want[i] * P[i, 9] / P[3, 9]
+    oracle.quadrupole_accel(P, G, J2s, Rp, 0.0, 0.0, 3)
+    assert np.all(np.abs(P[:, 6:9] - want) <= 1e-5 * np.abs(want))
