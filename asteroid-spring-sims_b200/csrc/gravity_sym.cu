@@ -41,6 +41,8 @@ constexpr int SG_TILE = 128;         // streamed particles between block-wide re
 
 struct SymCta {
 	int rb, s0, s1;  // resident block, streamed blocks [s0, s1); a streamed block equal to rb is the diagonal tile
+	int t_lo, t_hi;  // streamed particles [t_lo, t_hi) of each of those blocks (multiples of SG_TILE); the whole block is
+	                 // [0, SG_P).  Bodies of ~1e4 particles have too few tiles to fill the machine: their tiles are cut.
 };
 
 __device__ __forceinline__ vec4d load_or_dummy(const vec4d* __restrict__ posm, int idx, int hi) {
@@ -155,7 +157,7 @@ __global__ void __launch_bounds__(SG_T, 2) k_gravity_sym(const vec4d* __restrict
 		const bool diag = (sb == C.rb);
 		const int sbase = lo + sb * SG_P;
 		const size_t tile_row = ((size_t) C.rb * (size_t) (C.rb - 1) / 2 + (size_t) sb) * (size_t) SG_P;  // strict lower triangle
-		for (int t0 = 0; t0 < SG_P; t0 += SG_TILE) {
+		for (int t0 = C.t_lo; t0 < C.t_hi; t0 += SG_TILE) {
 			vec4d mine;
 			if (tid < SG_TILE) mine = load_or_dummy(posm, sbase + t0 + tid, hi);
 			__syncthreads();  // the previous tile's fold has finished reading s_acc / nobody still reads s_xy
@@ -259,10 +261,11 @@ void ass_sym_plan_free(SymPlan* p) {
 	delete p;
 }
 
-// Is the pair-once kernel worth it for this many particles?  It needs enough tiles to fill the machine.
+// Is the pair-once kernel worth it for this many particles?  It needs enough (possibly cut) tiles to fill the machine:
+// a tile can be cut into SG_P / SG_TILE pieces.
 bool ass_gravity_sym_applicable(int count) {
 	const long long nb = (count + SG_P - 1) / SG_P;
-	return nb * (nb + 1) / 2 >= 4LL * ass_sm_count();
+	return nb * (nb + 1) / 2 * (SG_P / SG_TILE) >= 2LL * ass_sm_count();
 }
 
 static int check_masses(ass_sim* s, SymPlan* plan) {
@@ -294,9 +297,14 @@ static int build_plan(ass_sim* s, int lo, int hi) {
 	// tiles per CTA: enough CTAs (>= ~16 per resident slot) for the block scheduler to balance, few enough rows
 	const long long slots = 2LL * ass_sm_count();
 	int U = (int) std::max(1LL, tiles / (slots * 16));
+	// few tiles (N ~ 1e4): cut every tile's streamed side into `cut` pieces so that ~2 CTAs per slot exist
+	int cut = 1;
+	while (U == 1 && tiles * cut < 2 * slots && cut < SG_P / SG_TILE) cut *= 2;
+	const int piece = SG_P / cut;
 	std::vector<std::vector<SymCta>> per_block(nb);
 	for (int rb = 0; rb < nb; rb++)
-		for (int s0 = 0; s0 <= rb; s0 += U) per_block[rb].push_back({ rb, s0, std::min(s0 + U, rb + 1) });
+		for (int s0 = 0; s0 <= rb; s0 += U)
+			for (int c = 0; c < cut; c++) per_block[rb].push_back({ rb, s0, std::min(s0 + U, rb + 1), c * piece, (c + 1) * piece });
 	// CTAs of one resident block stay contiguous (the reduction walks cta_begin[b] .. cta_begin[b+1]); big blocks first
 	std::vector<SymCta> ctas;
 	std::vector<int> begin(nb + 1, 0);
