@@ -373,11 +373,7 @@ class Sim:
         _chk(lib().ass_shard_gather(self._h))
 
 
-def slab_bounds(n, nranks, align=256):
-    """Contiguous particle slabs of near-equal size, boundaries aligned to the gravity tile (256 sources)."""
-    per = -(-n // nranks)
-    per = -(-per // align) * align
-    return [min(n, r * per) for r in range(nranks)] + [n]
+from .launcher import slab_bounds  # noqa: E402,F401  (kept here for callers of the binding)
 
 
 class Ensemble:

@@ -127,21 +127,13 @@ def barrier(dist):
 
 
 def max_over_ranks(dist, x, local):
-    if dist is None:
-        return x
-    import torch
-    t = torch.tensor([x], dtype=torch.float64, device=torch.device("cuda", local))
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    return float(t.item())
+    from asteroid_spring_sims_b200 import launcher
+    return launcher.reduce_max(dist, x, None if dist is None else "cuda:%d" % local)
 
 
 def sum_over_ranks(dist, x, local):
-    if dist is None:
-        return x
-    import torch
-    t = torch.tensor([x], dtype=torch.float64, device=torch.device("cuda", local))
-    dist.all_reduce(t, op=dist.ReduceOp.SUM)
-    return float(t.item())
+    from asteroid_spring_sims_b200 import launcher
+    return launcher.reduce_sum(dist, x, None if dist is None else "cuda:%d" % local)
 
 
 def build_body(A, cfg, omega, with_point_mass=False):
@@ -264,7 +256,7 @@ def run_c5(args, A, rank, world, local, dist):
     total = int(os.environ.get("ASS_C5_BODIES", "4096"))
     distinct = int(os.environ.get("ASS_C5_DISTINCT_SEEDS", "64"))   # bodies are regenerated per seed; 64 shapes x sweeps
     d = WORKLOADS["C1"]["d"]
-    mine = [b for b in range(total) if b % world == rank]
+    mine = A.launcher.deal_members(total, world, rank)
     t0 = time.perf_counter()
     shapes = {}
     for sd in sorted({b % distinct for b in mine}):
@@ -353,20 +345,10 @@ def run_c4_sharded(args, A, rank, world, local, dist):
     n, ns = len(p), len(springs)
     bounds = A.slab_bounds(n, world)
     sim.shard_setup(rank, world, bounds)
-    handles = [None] * world
-    dist.all_gather_object(handles, sim.shard_export())
-    for q in range(world):
-        if q != rank:
-            sim.shard_import(q, handles[q])
-    dist.barrier()
+    A.launcher.exchange_windows(dist, sim, rank, world)
 
     def run(nsteps):
-        for s in range(nsteps):
-            sim.shard_begin()
-            dist.barrier()
-            sim.shard_exchange()
-            dist.barrier()
-            sim.shard_finish(pre_drift_next=(s < nsteps - 1))
+        A.launcher.sharded_steps(dist, sim, nsteps)
 
     run(args.warmup)
     fp64_peak, _ = A.probe_fp64_peak(1 << 13)
@@ -393,7 +375,7 @@ def run_c4_sharded(args, A, rank, world, local, dist):
     dist.barrier()
     t0 = time.perf_counter()
     for s in range(min(args.steps, 3)):
-        sim.shard_begin(); dist.barrier(); sim.shard_exchange(); dist.barrier(); sim.shard_finish(False)
+        A.launcher.sharded_steps(dist, sim, 1, pre_drift=False)
         sim.download(host, A.F_POS | A.F_VEL | A.F_ACC)
     dist.barrier()
     t_e2e = max_over_ranks(dist, time.perf_counter() - t0, local)
