@@ -366,6 +366,9 @@ class Sim:
     def shard_exchange(self):
         _chk(lib().ass_shard_exchange(self._h))
 
+    def shard_gravity(self):
+        _chk(lib().ass_shard_gravity(self._h))
+
     def shard_finish(self, pre_drift_next=False):
         _chk(lib().ass_shard_finish(self._h, C.c_int(int(pre_drift_next))))
 

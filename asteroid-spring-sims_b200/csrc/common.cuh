@@ -99,7 +99,7 @@ struct ass_sim {
 	bool predrifted = false;  // positions already carry the next step's first half-drift (fused loop only)
 	bool sum_sequential = true;  // CoM / CoV sums in the reference's particle order (bit-exact) or as a parallel tree
 	int gravity_kernel = 0;      // 0 auto, 1 one-sided tiles (gravity.cu), 2 pair-once (gravity_sym.cu)
-	struct SymPlan* sym_plan = nullptr;  // CTA table + scratch rows of the pair-once kernel
+	std::vector<struct SymPlan*> sym_plans;  // CTA tables + scratch rows of the pair-once kernel, one per (resident, streamed) range pair
 
 	// springs: CSR over nodes in SPATIAL order.  ass_set_springs ranks the nodes along a Morton curve through their
 	// positions (a solid body: neighbours stay neighbours); row k belongs to node order[k], HalfEdge::nbr is the
@@ -147,9 +147,10 @@ struct ass_sim {
 
 void ass_shard_release(ass_sim* s);  // shard.cu
 // gravity_sym.cu
-void ass_sym_plan_free(struct SymPlan* p);
+void ass_sym_plans_free(ass_sim* s);
 bool ass_gravity_sym_applicable(int count);
 int ass_launch_gravity_sym(ass_sim* s, int lo, int hi);
+int ass_launch_gravity_sym_pair(ass_sim* s, int rlo, int rhi, int slo, int shi, vec4d* res_out, bool res_add, vec4d* str_out, bool str_add);
 int ass_buf_reserve(DevBuf& b, size_t bytes);
 // order[k] = node of rank k along a Morton curve through pos[0..n) (state.cu); deterministic, ties keep node order
 void ass_morton_order(const vec4d* pos, size_t n, std::vector<int>& order);
@@ -182,7 +183,7 @@ int ass_launch_spring_kick_drift(ass_sim* s, bool zero_first, double dt, bool pr
 int ass_launch_gravity(ass_sim* s);
 int ass_gravity_rows(int n_tgt, int n_src);
 int ass_launch_gravity_partial(ass_sim* s, const vec4d* src, int s_lo, int s_hi, int t_lo, int t_hi, int row_base, int* rows_out);
-int ass_launch_gravity_reduce(ass_sim* s, int t_lo, int t_hi, int rows);
+int ass_launch_gravity_reduce(ass_sim* s, int t_lo, int t_hi, int rows, bool add = false);
 // leapfrog.cu
 int ass_launch_part1(ass_sim* s, double dt);
 int ass_launch_part1_mirrored(ass_sim* s, double dt);  // part1 that also refreshes the rank-ordered mirror ps / vs

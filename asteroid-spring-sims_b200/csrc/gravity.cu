@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(GB) k_gravity(const vec4d* __restrict__ src, i
 }
 
 // acc[i] = sum over rows, fixed order
-__global__ void k_gravity_reduce(const vec4d* __restrict__ part, size_t stride, int rows, int lo, int hi, vec4d* __restrict__ acc) {
+__global__ void k_gravity_reduce(const vec4d* __restrict__ part, size_t stride, int rows, int lo, int hi, vec4d* __restrict__ acc, int add) {
 	const int i = lo + blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= hi) return;
 	vec4d a = part[i];
@@ -133,6 +133,7 @@ __global__ void k_gravity_reduce(const vec4d* __restrict__ part, size_t stride, 
 		const vec4d b = part[(size_t) s * stride + i];
 		a.x += b.x; a.y += b.y; a.z += b.z;
 	}
+	if (add) { const vec4d p = acc[i]; a.x += p.x; a.y += p.y; a.z += p.z; }
 	a.w = 0.0;
 	acc[i] = a;
 }
@@ -213,11 +214,13 @@ int ass_launch_gravity_partial(ass_sim* s, const vec4d* src, int s_lo, int s_hi,
 	return ASS_OK;
 }
 
-int ass_launch_gravity_reduce(ass_sim* s, int t_lo, int t_hi, int rows) {
+// acc[t_lo, t_hi) (=|+=) the sum of the first `rows` partial rows
+int ass_launch_gravity_reduce(ass_sim* s, int t_lo, int t_hi, int rows, bool add) {
 	if (t_hi <= t_lo) return ASS_OK;
+	if (rows <= 0 && add) return ASS_OK;
 	ass_tic(s, ASS_K_GRAVITY);
 	if (rows <= 0) k_zero_range<<<(t_hi - t_lo + 255) / 256, 256, 0, s->stream>>>(s->acc, t_lo, t_hi);
-	else k_gravity_reduce<<<(t_hi - t_lo + 255) / 256, 256, 0, s->stream>>>((const vec4d*) s->grav_partial.p, (size_t) s->n, rows, t_lo, t_hi, s->acc);
+	else k_gravity_reduce<<<(t_hi - t_lo + 255) / 256, 256, 0, s->stream>>>((const vec4d*) s->grav_partial.p, (size_t) s->n, rows, t_lo, t_hi, s->acc, add ? 1 : 0);
 	LAUNCH_CHECK();
 	ass_toc(s, ASS_K_GRAVITY);
 	return ASS_OK;
@@ -228,8 +231,23 @@ int ass_launch_gravity(ass_sim* s) {
 	const int n = s->n;
 	if (n == 0) return ASS_OK;
 	const int n_src = (s->prm.n_active == -1) ? n : std::max(0, std::min(s->prm.n_active, n));
-	// every particle both source and target: each unordered pair can be evaluated once (gravity_sym.cu)
-	if (n_src == n && s->gravity_kernel != 1 && (s->gravity_kernel == 2 || ass_gravity_sym_applicable(n))) return ass_launch_gravity_sym(s, 0, n);
+	// every particle both source and target: each unordered pair can be evaluated once (gravity_sym.cu).  Trailing
+	// point masses (params.n_perts, e.g. Mars next to a body of equal-mass nodes) are taken out of the pair-once part so
+	// that it keeps its equal-mass form: body x body pair-once, then body <- perturbers and perturbers <- everything
+	// one-sided (N x n_perts pairs: nothing).
+	if (n_src == n && s->gravity_kernel != 1 && (s->gravity_kernel == 2 || ass_gravity_sym_applicable(n))) {
+		const int np = std::max(0, std::min(s->prm.n_perts, n)), nb = n - np;
+		if (np == 0 || nb == 0) return ass_launch_gravity_sym(s, 0, n);
+		int rc = ass_launch_gravity_sym(s, 0, nb);
+		if (rc) return rc;
+		const int rows = std::max(ass_gravity_rows(nb, np), ass_gravity_rows(np, n));
+		if ((rc = ass_buf_reserve(s->grav_partial, sizeof(vec4d) * (size_t) std::max(rows, 1) * (size_t) n))) return rc;
+		int used = 0;
+		if ((rc = ass_launch_gravity_partial(s, s->posm, nb, n, 0, nb, 0, &used))) return rc;
+		if ((rc = ass_launch_gravity_reduce(s, 0, nb, used, true))) return rc;
+		if ((rc = ass_launch_gravity_partial(s, s->posm, 0, n, nb, n, 0, &used))) return rc;
+		return ass_launch_gravity_reduce(s, nb, n, used, false);
+	}
 	const int rows = ass_gravity_rows(n, n_src);
 	int rc = ass_buf_reserve(s->grav_partial, sizeof(vec4d) * (size_t) std::max(rows, 1) * (size_t) n);
 	if (rc) return rc;

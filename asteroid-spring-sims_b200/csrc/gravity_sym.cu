@@ -135,9 +135,12 @@ __device__ __forceinline__ void meet(const double2 xy, const double2 zm, int sid
 	}
 }
 
+// Resident particles come from [rlo, rhi), streamed particles from [slo, shi).  rect == 0: the two ranges are the same
+// range and the tiles are its lower triangle incl. the diagonal; rect != 0: the ranges are disjoint (two slabs of a
+// sharded body) and the tiles are the full rectangle, nsb streamed blocks wide.
 template <bool UNI>
-__global__ void __launch_bounds__(SG_T, 2) k_gravity_sym(const vec4d* __restrict__ posm, int lo, int hi, const SymCta* __restrict__ ctas,
-		double soft2, double* __restrict__ res, size_t res_plane, double* __restrict__ str, size_t str_plane) {
+__global__ void __launch_bounds__(SG_T, 2) k_gravity_sym(const vec4d* __restrict__ posm, int rlo, int rhi, int slo, int shi, int rect, int nsb,
+		const SymCta* __restrict__ ctas, double soft2, double* __restrict__ res, size_t res_plane, double* __restrict__ str, size_t str_plane) {
 	__shared__ double2 s_xy[SG_TILE], s_zm[SG_TILE];
 	__shared__ double s_acc[SG_W][3][SG_TILE];
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -147,26 +150,27 @@ __global__ void __launch_bounds__(SG_T, 2) k_gravity_sym(const vec4d* __restrict
 	int ridx[SG_R];
 #pragma unroll
 	for (int k = 0; k < SG_R; k++) {
-		ridx[k] = lo + C.rb * SG_P + tid + k * SG_T;
-		const vec4d p = load_or_dummy(posm, ridx[k], hi);
+		ridx[k] = rlo + C.rb * SG_P + tid + k * SG_T;
+		const vec4d p = load_or_dummy(posm, ridx[k], rhi);
 		rx[k] = p.x; ry[k] = p.y; rz[k] = p.z; rm[k] = p.w;
 		rax[k] = 0.0; ray[k] = 0.0; raz[k] = 0.0;
 	}
 
 	for (int sb = C.s0; sb < C.s1; sb++) {
-		const bool diag = (sb == C.rb);
-		const int sbase = lo + sb * SG_P;
-		const size_t tile_row = ((size_t) C.rb * (size_t) (C.rb - 1) / 2 + (size_t) sb) * (size_t) SG_P;  // strict lower triangle
+		const bool diag = !rect && (sb == C.rb);
+		const int sbase = slo + sb * SG_P;
+		const size_t tile_row = (rect ? (size_t) C.rb * (size_t) nsb + (size_t) sb                       // rectangle, row-major
+		                              : (size_t) C.rb * (size_t) (C.rb - 1) / 2 + (size_t) sb) * (size_t) SG_P;  // strict lower triangle
 		for (int t0 = C.t_lo; t0 < C.t_hi; t0 += SG_TILE) {
 			vec4d mine;
-			if (tid < SG_TILE) mine = load_or_dummy(posm, sbase + t0 + tid, hi);
+			if (tid < SG_TILE) mine = load_or_dummy(posm, sbase + t0 + tid, shi);
 			__syncthreads();  // the previous tile's fold has finished reading s_acc / nobody still reads s_xy
 			if (tid < SG_TILE) {
 				s_xy[tid] = make_double2(mine.x, mine.y);
 				s_zm[tid] = make_double2(mine.z, mine.w);
 			}
 			__syncthreads();
-			if (sbase + t0 >= hi) continue;  // a tile of pure padding (uniform across the CTA)
+			if (sbase + t0 >= shi) continue;  // a tile of pure padding (uniform across the CTA)
 #pragma unroll 1
 			for (int c0 = 0; c0 < SG_TILE; c0 += 32) {
 				double sax = 0.0, say = 0.0, saz = 0.0;
@@ -213,10 +217,11 @@ __global__ void __launch_bounds__(SG_T, 2) k_gravity_sym(const vec4d* __restrict
 	}
 }
 
-// a_i = G * (resident rows) - G * (streamed rows), rows added in a fixed order.  be[2b], be[2b+1] = the CTAs whose
-// resident block is b.  uniform != 0: the rows hold unweighted sums and every particle has the mass of particle `lo`.
+// Triangle plans: a_i = G * (resident rows) - G * (streamed rows) for every particle of the range, rows added in a fixed
+// order.  be[2b], be[2b+1] = the CTAs whose resident block is b.  uniform != 0: the rows hold unweighted sums and every
+// particle has the mass of particle `lo`.  add != 0: out[i] += a_i instead of out[i] = a_i.
 __global__ void k_gravity_sym_reduce(const double* __restrict__ res, size_t res_plane, const double* __restrict__ str, size_t str_plane,
-		const int* __restrict__ be, int nb, int lo, int hi, double G, int uniform, const vec4d* __restrict__ posm, vec4d* __restrict__ acc) {
+		const int* __restrict__ be, int nb, int lo, int hi, double G, int uniform, const vec4d* __restrict__ posm, vec4d* __restrict__ out, int add) {
 	const int i = lo + blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= hi) return;
 	if (uniform) G *= posm[lo].w;
@@ -232,33 +237,75 @@ __global__ void k_gravity_sym_reduce(const double* __restrict__ res, size_t res_
 	}
 	vec4d a;
 	a.x = G * (rs[0] - ss[0]); a.y = G * (rs[1] - ss[1]); a.z = G * (rs[2] - ss[2]); a.w = 0.0;
-	acc[i] = a;
+	if (add) { const vec4d p = out[i]; a.x += p.x; a.y += p.y; a.z += p.z; }
+	out[i] = a;
 }
 
-// *differs = 1 if any particle of [lo, hi) has a mass whose bits differ from particle lo's
-__global__ void k_mass_differs(const vec4d* __restrict__ posm, int lo, int hi, int* __restrict__ differs) {
+// Rectangle plans, resident side: a_i = +G * (rows of the CTAs whose resident block holds i), i in [rlo, rhi)
+__global__ void k_gravity_rect_reduce_res(const double* __restrict__ res, size_t res_plane, const int* __restrict__ be, int rlo, int rhi, double Gm,
+		vec4d* __restrict__ out, int add) {
+	const int i = rlo + blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= rhi) return;
+	const int b = (i - rlo) / SG_P, o = (i - rlo) - b * SG_P;
+	double rs[3] = { 0.0, 0.0, 0.0 };
+	for (int c = be[2 * b]; c < be[2 * b + 1]; c++) {
+		const size_t at = (size_t) c * SG_P + o;
+		rs[0] += res[at]; rs[1] += res[res_plane + at]; rs[2] += res[2 * res_plane + at];
+	}
+	vec4d a;
+	a.x = Gm * rs[0]; a.y = Gm * rs[1]; a.z = Gm * rs[2]; a.w = 0.0;
+	if (add) { const vec4d p = out[i]; a.x += p.x; a.y += p.y; a.z += p.z; }
+	out[i] = a;
+}
+
+// Rectangle plans, streamed side: a_j = -G * (rows of column block b over all resident blocks), j in [slo, shi)
+__global__ void k_gravity_rect_reduce_str(const double* __restrict__ str, size_t str_plane, int nrb, int nsb, int slo, int shi, double Gm,
+		vec4d* __restrict__ out, int add) {
+	const int j = slo + blockIdx.x * blockDim.x + threadIdx.x;
+	if (j >= shi) return;
+	const int b = (j - slo) / SG_P, o = (j - slo) - b * SG_P;
+	double ss[3] = { 0.0, 0.0, 0.0 };
+	for (int rb = 0; rb < nrb; rb++) {
+		const size_t at = ((size_t) rb * (size_t) nsb + (size_t) b) * SG_P + o;
+		ss[0] += str[at]; ss[1] += str[str_plane + at]; ss[2] += str[2 * str_plane + at];
+	}
+	vec4d a;
+	a.x = -Gm * ss[0]; a.y = -Gm * ss[1]; a.z = -Gm * ss[2]; a.w = 0.0;
+	if (add) { const vec4d p = out[j]; a.x += p.x; a.y += p.y; a.z += p.z; }
+	out[j] = a;
+}
+
+// *differs = 1 if any particle of [lo, hi) has a mass whose bits differ from particle ref's
+__global__ void k_mass_differs(const vec4d* __restrict__ posm, int lo, int hi, int ref, int* __restrict__ differs) {
 	const int i = lo + blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= hi) return;
-	if (__double_as_longlong(posm[i].w) != __double_as_longlong(posm[lo].w)) *differs = 1;
+	if (__double_as_longlong(posm[i].w) != __double_as_longlong(posm[ref].w)) *differs = 1;
 }
 
 }  // namespace
 
 struct SymPlan {
-	int lo = -1, hi = -1, nb = 0, n_cta = 0;
+	int rlo = -1, rhi = -1, slo = -1, shi = -1;  // resident / streamed ranges (identical: triangle; disjoint: rectangle)
+	bool rect = false;
+	int nrb = 0, nsb = 0, n_cta = 0;
 	long long mass_epoch = -1;  // masses the `uniform` verdict was taken from (ass_sim::mass_epoch)
 	int uniform = 0;
-	size_t n_tiles = 0;
+	double m_ref = 0.0;         // mass of particle rlo (the common mass when uniform)
 	SymCta* d_ctas = nullptr;
 	int* d_cta_begin = nullptr;
 	double *d_res = nullptr, *d_str = nullptr;
 	size_t res_plane = 0, str_plane = 0;
 };
 
-void ass_sym_plan_free(SymPlan* p) {
+static void plan_free(SymPlan* p) {
 	if (!p) return;
 	cudaFree(p->d_ctas); cudaFree(p->d_cta_begin); cudaFree(p->d_res); cudaFree(p->d_str);
 	delete p;
+}
+
+void ass_sym_plans_free(ass_sim* s) {
+	for (SymPlan* p : s->sym_plans) plan_free(p);
+	s->sym_plans.clear();
 }
 
 // Is the pair-once kernel worth it for this many particles?  It needs enough (possibly cut) tiles to fill the machine:
@@ -271,10 +318,15 @@ bool ass_gravity_sym_applicable(int count) {
 static int check_masses(ass_sim* s, SymPlan* plan) {
 	int* d_flag = (int*) s->d_red;  // the simulation's small reduction scratch (device), free between launches
 	CU_TRY(cudaMemsetAsync(d_flag, 0, sizeof(int), s->stream));
-	k_mass_differs<<<(plan->hi - plan->lo + 255) / 256, 256, 0, s->stream>>>(s->posm, plan->lo, plan->hi, d_flag);
+	k_mass_differs<<<(plan->rhi - plan->rlo + 255) / 256, 256, 0, s->stream>>>(s->posm, plan->rlo, plan->rhi, plan->rlo, d_flag);
 	LAUNCH_CHECK();
+	if (plan->rect) {
+		k_mass_differs<<<(plan->shi - plan->slo + 255) / 256, 256, 0, s->stream>>>(s->posm, plan->slo, plan->shi, plan->rlo, d_flag);
+		LAUNCH_CHECK();
+	}
 	int differs = 1;
 	CU_TRY(cudaMemcpyAsync(&differs, d_flag, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+	CU_TRY(cudaMemcpyAsync(&plan->m_ref, &s->posm[plan->rlo].w, sizeof(double), cudaMemcpyDeviceToHost, s->stream));
 	CU_TRY(cudaStreamSynchronize(s->stream));
 	const char* off = getenv("ASS_GRAVITY_NO_UNIFORM");
 	plan->uniform = (!differs && !(off && *off && *off != '0')) ? 1 : 0;
@@ -282,18 +334,18 @@ static int check_masses(ass_sim* s, SymPlan* plan) {
 	return ASS_OK;
 }
 
-static int build_plan(ass_sim* s, int lo, int hi) {
-	SymPlan*& plan = s->sym_plan;
-	if (plan && plan->lo == lo && plan->hi == hi) {
-		if (plan->mass_epoch != s->mass_epoch) return check_masses(s, plan);
-		return ASS_OK;
-	}
-	ass_sym_plan_free(plan);
-	plan = new SymPlan();
-	plan->lo = lo; plan->hi = hi;
-	const int nb = (hi - lo + SG_P - 1) / SG_P;
-	plan->nb = nb;
-	const long long tiles = (long long) nb * (nb + 1) / 2;
+static int get_plan(ass_sim* s, int rlo, int rhi, int slo, int shi, SymPlan** out) {
+	for (SymPlan* q : s->sym_plans)
+		if (q->rlo == rlo && q->rhi == rhi && q->slo == slo && q->shi == shi) {
+			*out = q;
+			return (q->mass_epoch != s->mass_epoch) ? check_masses(s, q) : ASS_OK;
+		}
+	SymPlan* plan = new SymPlan();
+	plan->rlo = rlo; plan->rhi = rhi; plan->slo = slo; plan->shi = shi;
+	plan->rect = !(rlo == slo && rhi == shi);
+	const int nrb = (rhi - rlo + SG_P - 1) / SG_P, nsb = (shi - slo + SG_P - 1) / SG_P;
+	plan->nrb = nrb; plan->nsb = nsb;
+	const long long tiles = plan->rect ? (long long) nrb * nsb : (long long) nrb * (nrb + 1) / 2;
 	// tiles per CTA: enough CTAs (>= ~16 per resident slot) for the block scheduler to balance, few enough rows
 	const long long slots = 2LL * ass_sm_count();
 	int U = (int) std::max(1LL, tiles / (slots * 16));
@@ -301,58 +353,74 @@ static int build_plan(ass_sim* s, int lo, int hi) {
 	int cut = 1;
 	while (U == 1 && tiles * cut < 2 * slots && cut < SG_P / SG_TILE) cut *= 2;
 	const int piece = SG_P / cut;
-	std::vector<std::vector<SymCta>> per_block(nb);
-	for (int rb = 0; rb < nb; rb++)
-		for (int s0 = 0; s0 <= rb; s0 += U)
-			for (int c = 0; c < cut; c++) per_block[rb].push_back({ rb, s0, std::min(s0 + U, rb + 1), c * piece, (c + 1) * piece });
-	// CTAs of one resident block stay contiguous (the reduction walks cta_begin[b] .. cta_begin[b+1]); big blocks first
-	std::vector<SymCta> ctas;
-	std::vector<int> begin(nb + 1, 0);
-	std::vector<int> order(nb);
-	for (int b = 0; b < nb; b++) order[b] = nb - 1 - b;
-	std::vector<int> start_of(nb, 0), count_of(nb, 0);
-	for (int b : order) {
-		start_of[b] = (int) ctas.size();
-		count_of[b] = (int) per_block[b].size();
-		ctas.insert(ctas.end(), per_block[b].begin(), per_block[b].end());
+	std::vector<std::vector<SymCta>> per_block(nrb);
+	for (int rb = 0; rb < nrb; rb++) {
+		const int s_end = plan->rect ? nsb : rb + 1;  // rectangle: every streamed block; triangle: up to the diagonal
+		for (int s0 = 0; s0 < s_end; s0 += U)
+			for (int c = 0; c < cut; c++) per_block[rb].push_back({ rb, s0, std::min(s0 + U, s_end), c * piece, (c + 1) * piece });
 	}
-	// cta_begin must be indexable by block: store [begin, end) pairs
-	std::vector<int> be((size_t) 2 * nb);
-	for (int b = 0; b < nb; b++) { be[2 * b] = start_of[b]; be[2 * b + 1] = start_of[b] + count_of[b]; }
+	// CTAs of one resident block stay contiguous (the reduction walks be[2b] .. be[2b+1]); big blocks first
+	std::vector<SymCta> ctas;
+	std::vector<int> be((size_t) 2 * nrb);
+	for (int b = nrb - 1; b >= 0; b--) {
+		be[2 * b] = (int) ctas.size();
+		ctas.insert(ctas.end(), per_block[b].begin(), per_block[b].end());
+		be[2 * b + 1] = (int) ctas.size();
+	}
 	plan->n_cta = (int) ctas.size();
-	plan->n_tiles = (size_t) nb * (size_t) (nb - 1) / 2;
+	const size_t n_str_tiles = plan->rect ? (size_t) nrb * (size_t) nsb : (size_t) nrb * (size_t) (nrb - 1) / 2;
 	plan->res_plane = (size_t) plan->n_cta * SG_P;
-	plan->str_plane = std::max<size_t>(plan->n_tiles, 1) * SG_P;
-	if (cudaMalloc(&plan->d_ctas, sizeof(SymCta) * ctas.size()) != cudaSuccess || cudaMalloc(&plan->d_cta_begin, sizeof(int) * be.size()) != cudaSuccess ||
-	    cudaMalloc(&plan->d_res, sizeof(double) * 3 * plan->res_plane) != cudaSuccess || cudaMalloc(&plan->d_str, sizeof(double) * 3 * plan->str_plane) != cudaSuccess) {
+	plan->str_plane = std::max<size_t>(n_str_tiles, 1) * SG_P;
+	if (cudaMalloc(&plan->d_ctas, sizeof(SymCta) * std::max<size_t>(ctas.size(), 1)) != cudaSuccess ||
+	    cudaMalloc(&plan->d_cta_begin, sizeof(int) * std::max<size_t>(be.size(), 1)) != cudaSuccess ||
+	    cudaMalloc(&plan->d_res, sizeof(double) * 3 * std::max<size_t>(plan->res_plane, 1)) != cudaSuccess ||
+	    cudaMalloc(&plan->d_str, sizeof(double) * 3 * plan->str_plane) != cudaSuccess) {
 		cudaGetLastError();
 		ass_set_error("pair-once gravity: out of device memory for %zu scratch bytes", sizeof(double) * 3 * (plan->res_plane + plan->str_plane));
-		ass_sym_plan_free(plan);
-		plan = nullptr;
+		plan_free(plan);
 		return ASS_ENOMEM;
 	}
 	CU_TRY(cudaMemcpyAsync(plan->d_ctas, ctas.data(), sizeof(SymCta) * ctas.size(), cudaMemcpyHostToDevice, s->stream));
 	CU_TRY(cudaMemcpyAsync(plan->d_cta_begin, be.data(), sizeof(int) * be.size(), cudaMemcpyHostToDevice, s->stream));
 	CU_TRY(cudaStreamSynchronize(s->stream));
+	s->sym_plans.push_back(plan);
+	*out = plan;
 	return check_masses(s, plan);
 }
 
-// a = gravity among particles [lo, hi) (every particle both source and target), pair-once
-int ass_launch_gravity_sym(ass_sim* s, int lo, int hi) {
-	if (hi - lo <= 0) return ASS_OK;
-	int rc = build_plan(s, lo, hi);
+// Pair-once gravity between resident particles [rlo, rhi) and streamed particles [slo, shi) of s->posm.
+//   identical ranges : every unordered pair of the range once; res_out[i] (=|+=) a_i for i in the range; str_out unused
+//   disjoint ranges  : every (resident, streamed) pair once; res_out[i] (=|+=) the pull of the streamed range on resident i,
+//                      str_out[j] (=|+=) the pull of the resident range on streamed j (Newton's third law)
+int ass_launch_gravity_sym_pair(ass_sim* s, int rlo, int rhi, int slo, int shi, vec4d* res_out, bool res_add, vec4d* str_out, bool str_add) {
+	if (rhi <= rlo || shi <= slo) return ASS_OK;
+	SymPlan* p = nullptr;
+	int rc = get_plan(s, rlo, rhi, slo, shi, &p);
 	if (rc) return rc;
-	SymPlan* p = s->sym_plan;
 	const double soft2 = s->prm.softening * s->prm.softening;
 	ass_tic(s, ASS_K_GRAVITY);
 	if (p->uniform)
-		k_gravity_sym<true><<<p->n_cta, SG_T, 0, s->stream>>>(s->posm, lo, hi, p->d_ctas, soft2, p->d_res, p->res_plane, p->d_str, p->str_plane);
+		k_gravity_sym<true><<<p->n_cta, SG_T, 0, s->stream>>>(s->posm, rlo, rhi, slo, shi, p->rect ? 1 : 0, p->nsb, p->d_ctas, soft2, p->d_res, p->res_plane,
+				p->d_str, p->str_plane);
 	else
-		k_gravity_sym<false><<<p->n_cta, SG_T, 0, s->stream>>>(s->posm, lo, hi, p->d_ctas, soft2, p->d_res, p->res_plane, p->d_str, p->str_plane);
+		k_gravity_sym<false><<<p->n_cta, SG_T, 0, s->stream>>>(s->posm, rlo, rhi, slo, shi, p->rect ? 1 : 0, p->nsb, p->d_ctas, soft2, p->d_res, p->res_plane,
+				p->d_str, p->str_plane);
 	LAUNCH_CHECK();
-	k_gravity_sym_reduce<<<(hi - lo + 255) / 256, 256, 0, s->stream>>>(p->d_res, p->res_plane, p->d_str, p->str_plane, p->d_cta_begin, p->nb, lo, hi,
-			s->prm.G, p->uniform, s->posm, s->acc);
-	LAUNCH_CHECK();
+	if (!p->rect) {
+		k_gravity_sym_reduce<<<(rhi - rlo + 255) / 256, 256, 0, s->stream>>>(p->d_res, p->res_plane, p->d_str, p->str_plane, p->d_cta_begin, p->nrb, rlo, rhi,
+				s->prm.G, p->uniform, s->posm, res_out, res_add ? 1 : 0);
+		LAUNCH_CHECK();
+	} else {
+		// uniform: the rows are unweighted sums and every particle of both ranges has the mass of particle rlo
+		const double Gm = p->uniform ? s->prm.G * p->m_ref : s->prm.G;
+		k_gravity_rect_reduce_res<<<(rhi - rlo + 255) / 256, 256, 0, s->stream>>>(p->d_res, p->res_plane, p->d_cta_begin, rlo, rhi, Gm, res_out, res_add ? 1 : 0);
+		LAUNCH_CHECK();
+		k_gravity_rect_reduce_str<<<(shi - slo + 255) / 256, 256, 0, s->stream>>>(p->d_str, p->str_plane, p->nrb, p->nsb, slo, shi, Gm, str_out, str_add ? 1 : 0);
+		LAUNCH_CHECK();
+	}
 	ass_toc(s, ASS_K_GRAVITY);
 	return ASS_OK;
 }
+
+// a = gravity among particles [lo, hi) (every particle both source and target), pair-once
+int ass_launch_gravity_sym(ass_sim* s, int lo, int hi) { return ass_launch_gravity_sym_pair(s, lo, hi, lo, hi, s->acc, false, nullptr, false); }

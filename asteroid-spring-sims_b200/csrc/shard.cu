@@ -1,24 +1,35 @@
 // shard.cu -- one large body split over the GPUs of a node by contiguous slabs of particles (BASELINE C4).
 //
-// Rank g owns particles [bounds[g], bounds[g+1]): it is the only rank that integrates them, evaluates gravity onto them
-// and sums the springs incident on them.  Every rank keeps arrays for all N particles, because a gravity target needs
-// every source and a spring owner needs its neighbours' positions and velocities.  The reference has no counterpart
-// (its MPI path is tree-only and never used with springs); the nearest analogue is one all-gather of x and v per step.
+// Rank g owns particles [bounds[g], bounds[g+1]): it is the only rank that integrates them and sums the springs incident
+// on them.  Every rank keeps arrays for all N particles, because gravity needs every source and a spring owner needs
+// its neighbours' positions and velocities.  The reference has no counterpart (its MPI path is tree-only and never used
+// with springs); the nearest analogue is one all-gather of x and v plus one reduce-scatter of partial accelerations.
 //
-// Exchange.  posm and vel live in ONE exportable allocation (the "window").  Peers map it (CUDA IPC across processes,
-// or the raw pointer inside one process) and each step every rank PULLS the other slabs with the copy engines on a
-// side stream while its SMs already evaluate gravity against the sources of its own slab; the rest of the sources
-// follow once the pull has landed.  So the all-gather is hidden behind 1/P of the gravity work.  (Reading remote tiles
-// from inside the gravity kernel would be the literal "fused" form, but peer loads bypass the local L2: every target
-// block would re-fetch every remote slab over NVLink, ~tblocks x the bytes of one gather.)
+// Gravity is divided by PAIRS OF SLABS so that every unordered particle pair is still evaluated once (gravity_sym.cu)
+// and every rank does the same amount of work.  With P ranks and D = (P-1)/2, rank g evaluates
+//     slab g x slab g                     (triangle)                         -> its own accelerations
+//     slab g x slab (g+d) mod P, d = 1..D (rectangle)                        -> its own, and a partial for slab g+d
+//     slab g <- slab (g+P/2) mod P        (P even only: one-sided, both ranks of the antipodal pair do their half)
+// and trailing point masses (params.n_perts) are handled one-sidedly by whoever owns the targets.  The partials for
+// foreign slabs are left in an exported buffer; their owners pull and add them in a fixed order.
 //
-// A step is three calls separated by two barriers that the launcher owns (torch.distributed, or nothing in-process):
+// Exchange.  posm, vel and the partial-acceleration buffer live in ONE exportable allocation (the "window").  Peers map
+// it (CUDA IPC across processes, or the raw pointer inside one process); every transfer is a PULL by the copy engines on
+// a side stream: the peers' slabs while the SMs already run the own-slab triangle, the partials before the springs.
+// (Reading remote tiles from inside the gravity kernel would be the literal "fused" form, but peer loads bypass the
+// local L2: every tile would re-fetch remote particles over NVLink, hundreds of times the bytes of one gather.)
+//
+// A step is four calls separated by three barriers that the launcher owns (torch.distributed; launcher.py):
 //   ass_shard_begin     part1 on the own slab unless the previous finish already pre-drifted it; sync.
 //   --- barrier ---     every slab is final
-//   ass_shard_exchange  start the pulls + launch gravity(own-slab sources); returns when the pulls have landed.
+//   ass_shard_exchange  start the pulls + launch the own-slab triangle; returns when the pulls have landed.
 //   --- barrier ---     nobody is still reading my slab
-//   ass_shard_finish    gravity(remote sources), fixed-order row reduction, [zero_accel], spring_forces on the own slab,
+//   ass_shard_gravity   the rectangles, the antipodal half, the point masses; sync (my partials are complete).
+//   --- barrier ---     every partial is complete
+//   ass_shard_finish    pull + add the partials for the own slab, [zero_accel], spring_forces on the own slab,
 //                       part2 (+ next part1) on the own slab; sync.
+// With params.n_active restricting the sources the pair-once division does not apply and the ranks fall back to
+// one-sided sums over all sources (own slab first, the rest after the pulls).
 #include <string.h>
 
 #include <algorithm>
@@ -38,7 +49,8 @@ extern "C" int ass_shard_setup(ass_sim* s, int rank, int nranks, const int* boun
 	if (rc) return rc;
 	ShardInfo& sh = s->shard;
 	const size_t n = (size_t) s->n;
-	CU_TRY(cudaMalloc(&sh.window, sizeof(vec4d) * 2 * std::max<size_t>(n, 1)));
+	CU_TRY(cudaMalloc(&sh.window, sizeof(vec4d) * 3 * std::max<size_t>(n, 1)));  // posm | vel | partial accelerations
+	CU_TRY(cudaMemsetAsync(sh.window + 2 * n, 0, sizeof(vec4d) * n, s->stream));
 	CU_TRY(cudaMemcpyAsync(sh.window, s->posm, sizeof(vec4d) * n, cudaMemcpyDeviceToDevice, s->stream));
 	CU_TRY(cudaMemcpyAsync(sh.window + n, s->vel, sizeof(vec4d) * n, cudaMemcpyDeviceToDevice, s->stream));
 	CU_TRY(cudaStreamSynchronize(s->stream));
@@ -115,6 +127,16 @@ extern "C" int ass_shard_begin(ass_sim* s) {
 	return ASS_OK;
 }
 
+// does the pair-once division apply?  (every particle a source; gravity on and not zeroed again by zero_accel)
+static bool gravity_on(const ass_sim* s) { return s->prm.gravity == 1 && s->prm.additional_forces != 2; }
+static bool pairwise(const ass_sim* s) { return gravity_on(s) && n_sources(s) == s->n; }
+// body part of rank r's slab: trailing point masses [N - n_perts, N) are kept out of the pair-once kernels
+static void body_slab(const ass_sim* s, int r, int* lo, int* hi) {
+	const int nb = s->n - std::max(0, std::min(s->prm.n_perts, s->n));
+	*lo = std::min(s->shard.bounds[r], nb);
+	*hi = std::min(s->shard.bounds[r + 1], nb);
+}
+
 extern "C" int ass_shard_exchange(ass_sim* s) {
 	REQUIRE(s, ASS_EINVAL, "null sim");
 	ShardInfo& sh = s->shard;
@@ -132,9 +154,19 @@ extern "C" int ass_shard_exchange(ass_sim* s) {
 		CU_TRY(cudaMemcpyAsync(sh.window + n + lo, sh.peer_window[r] + n + lo, sizeof(vec4d) * cnt, cudaMemcpyDeviceToDevice, sh.copy_stream));
 	}
 	CU_TRY(cudaEventRecord(sh.pulled, sh.copy_stream));
-	// 2. meanwhile: gravity onto the own slab from the sources of the own slab
+	// 2. meanwhile: the part of gravity that needs the own slab only
 	sh.rows_local = 0;
-	if (s->prm.gravity == 1 && s->prm.additional_forces != 2) {
+	if (pairwise(s)) {
+		int lo, hi;
+		body_slab(s, sh.rank, &lo, &hi);
+		// a = triangle of the own slab; slabs too small for the pair-once tiles still go through it (forced), so that
+		// every rank evaluates exactly the pairs the division assigns to it
+		if (hi > lo) {
+			if ((rc = ass_launch_gravity_sym(s, lo, hi))) return rc;
+		}
+		// own particles outside the body part (point masses) start from zero
+		if ((rc = ass_launch_zero_accel_range(s, std::max(sh.lo, hi), sh.hi))) return rc;
+	} else if (gravity_on(s)) {
 		const int ns = n_sources(s);
 		const int a = std::min(sh.lo, ns), b = std::min(sh.hi, ns);
 		const int rows = ass_gravity_rows(sh.hi - sh.lo, b - a) + ass_gravity_rows(sh.hi - sh.lo, a) + ass_gravity_rows(sh.hi - sh.lo, ns - b);
@@ -146,6 +178,56 @@ extern "C" int ass_shard_exchange(ass_sim* s) {
 	return ASS_OK;
 }
 
+// one-sided: acc[t_lo, t_hi) += pull of sources [s_lo, s_hi)
+static int one_sided_add(ass_sim* s, int s_lo, int s_hi, int t_lo, int t_hi) {
+	if (t_hi <= t_lo || s_hi <= s_lo) return ASS_OK;
+	int rc = ass_buf_reserve(s->grav_partial, sizeof(vec4d) * (size_t) std::max(ass_gravity_rows(t_hi - t_lo, s_hi - s_lo), 1) * (size_t) s->n);
+	if (rc) return rc;
+	int used = 0;
+	if ((rc = ass_launch_gravity_partial(s, s->posm, s_lo, s_hi, t_lo, t_hi, 0, &used))) return rc;
+	return ass_launch_gravity_reduce(s, t_lo, t_hi, used, true);
+}
+
+extern "C" int ass_shard_gravity(ass_sim* s) {
+	REQUIRE(s, ASS_EINVAL, "null sim");
+	ShardInfo& sh = s->shard;
+	REQUIRE(sh.active, ASS_ESTATE, "not sharded");
+	int rc = ass_ensure_device();
+	if (rc) return rc;
+	CU_TRY(cudaStreamWaitEvent(s->stream, sh.pulled, 0));
+	if (pairwise(s)) {
+		const int P = sh.nranks, g = sh.rank, D = (P - 1) / 2;
+		const int n = s->n, nb = n - std::max(0, std::min(s->prm.n_perts, n));
+		vec4d* fpart = sh.window + 2 * (size_t) n;
+		int lo, hi;
+		body_slab(s, g, &lo, &hi);
+		for (int d = 1; d <= D; d++) {  // rectangles: both sides of every pair
+			int plo, phi;
+			body_slab(s, (g + d) % P, &plo, &phi);
+			if ((rc = ass_launch_gravity_sym_pair(s, lo, hi, plo, phi, s->acc, true, fpart, false))) return rc;
+		}
+		if (P % 2 == 0 && P > 1) {  // antipodal slab: each of the two ranks sums its own side
+			int plo, phi;
+			body_slab(s, (g + P / 2) % P, &plo, &phi);
+			if ((rc = one_sided_add(s, plo, phi, lo, hi))) return rc;
+		}
+		// point masses: they pull on my body particles; whoever owns them sums everything onto them
+		if ((rc = one_sided_add(s, nb, n, lo, hi))) return rc;
+		if ((rc = one_sided_add(s, 0, n, std::max(sh.lo, nb), sh.hi))) return rc;
+	}
+	CU_TRY(cudaStreamSynchronize(s->stream));  // my partials for other slabs are complete
+	return ASS_OK;
+}
+
+__global__ void k_add_partial(vec4d* __restrict__ acc, const vec4d* __restrict__ part, int lo, int hi) {
+	const int i = lo + blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= hi) return;
+	vec4d a = acc[i];
+	const vec4d b = part[i - lo];
+	a.x += b.x; a.y += b.y; a.z += b.z;
+	acc[i] = a;
+}
+
 extern "C" int ass_shard_finish(ass_sim* s, int pre_drift_next) {
 	REQUIRE(s, ASS_EINVAL, "null sim");
 	ShardInfo& sh = s->shard;
@@ -155,7 +237,28 @@ extern "C" int ass_shard_finish(ass_sim* s, int pre_drift_next) {
 	const ass_params& P = s->prm;
 	const double dt = P.dt;
 	CU_TRY(cudaStreamWaitEvent(s->stream, sh.pulled, 0));
-	if (P.gravity == 1 && P.additional_forces != 2) {
+	if (pairwise(s)) {
+		// the partials other ranks computed for my slab, pulled and added in a fixed order (d = 1..D)
+		const int R = sh.nranks, g = sh.rank, D = (R - 1) / 2;
+		int lo, hi;
+		body_slab(s, g, &lo, &hi);
+		const size_t cnt = (size_t) std::max(hi - lo, 0), n = (size_t) s->n;
+		if (cnt && D > 0) {
+			if ((rc = ass_buf_reserve(s->grav_partial, sizeof(vec4d) * cnt * (size_t) D))) return rc;
+			vec4d* land = (vec4d*) s->grav_partial.p;
+			for (int d = 1; d <= D; d++) {
+				const int r = ((g - d) % R + R) % R;
+				REQUIRE(sh.peer_window[r], ASS_ESTATE, "a peer window has not been imported");
+				CU_TRY(cudaMemcpyAsync(land + (size_t) (d - 1) * cnt, sh.peer_window[r] + 2 * n + (size_t) lo, sizeof(vec4d) * cnt, cudaMemcpyDeviceToDevice, s->stream));
+			}
+			ass_tic(s, ASS_K_GRAVITY);
+			for (int d = 1; d <= D; d++) {
+				k_add_partial<<<(unsigned) ((cnt + 255) / 256), 256, 0, s->stream>>>(s->acc, land + (size_t) (d - 1) * cnt, lo, hi);
+				LAUNCH_CHECK();
+			}
+			ass_toc(s, ASS_K_GRAVITY);
+		}
+	} else if (gravity_on(s)) {
 		const int ns = n_sources(s);
 		const int a = std::min(sh.lo, ns), b = std::min(sh.hi, ns);
 		int rows = sh.rows_local, used = 0;

@@ -336,7 +336,7 @@ extern "C" int ass_destroy(ass_sim* s) {
 	ass_ensure_device();
 	if (s->stream) cudaStreamSynchronize(s->stream);
 	ass_shard_release(s);  // a sharded simulation's posm / vel alias its exported window
-	ass_sym_plan_free(s->sym_plan);
+	ass_sym_plans_free(s);
 	cudaFree(s->wave_off);
 	cudaFree(s->order); cudaFree(s->rank); cudaFree(s->ps); cudaFree(s->vs); cudaFree(s->ps_alt); cudaFree(s->vs_alt);
 	cudaFree(s->posm); cudaFree(s->vel); cudaFree(s->acc); cudaFree(s->posm_alt); cudaFree(s->vel_alt);
@@ -482,7 +482,7 @@ extern "C" int ass_upload_particles(ass_sim* s, const void* base, size_t stride,
 		// a different particle count is a new body: everything must come from the host
 		REQUIRE(fields == ASS_F_ALL, ASS_ESTATE, "particle count changed: upload ASS_F_ALL");
 		if ((rc = ensure_particles(s, n))) return rc;
-		if (n != s->n) { s->ns = 0; s->n_he = 0; }  // springs refer to the old body
+		if (n != s->n) { s->ns = 0; s->n_he = 0; ass_sym_plans_free(s); }  // springs and gravity plans refer to the old body
 		s->n = n;
 	}
 	s->predrifted = false;

@@ -3,9 +3,9 @@
 Two ways the path shards (include/ass_b200.h "multi-GPU"):
   * ensemble members are independent: they are dealt round-robin to the ranks, no data-path collective;
   * one large body is cut into contiguous particle slabs; per step the ranks run
-        shard_begin -> barrier -> shard_exchange -> barrier -> shard_finish
-    where the exchange is a pull of the peers' slabs through CUDA-IPC windows (handles swapped once with
-    all_gather_object).
+        shard_begin -> barrier -> shard_exchange -> barrier -> shard_gravity -> barrier -> shard_finish
+    where the exchanges are pulls through CUDA-IPC windows (handles swapped once with all_gather_object): the peers'
+    slabs of x and v, and the partial accelerations the peers computed for this rank's slab.
 Everything here is backend-agnostic (NCCL on the GPU box, gloo in the CPU tests: tests/test_launcher_gloo.py) and
 touches the simulation only through the methods named above, so the ordering rules can be tested without a GPU.
 """
@@ -67,10 +67,13 @@ def exchange_windows(dist, sim, rank, world):
 
 def sharded_steps(dist, sim, nsteps, pre_drift=True):
     """reb_step x nsteps of a slab-sharded body.  Barrier 1: every slab carries its drifted positions before anyone
-    pulls.  Barrier 2: every pull has landed before anyone overwrites its slab with the kick."""
+    pulls.  Barrier 2: every pull has landed before anyone overwrites anything a peer reads.  Barrier 3: every rank's
+    partial accelerations for the other slabs are complete before their owners pull them."""
     for s in range(nsteps):
         sim.shard_begin()
         dist.barrier()
         sim.shard_exchange()
+        dist.barrier()
+        sim.shard_gravity()
         dist.barrier()
         sim.shard_finish(pre_drift_next=(pre_drift and s < nsteps - 1))

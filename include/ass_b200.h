@@ -203,11 +203,13 @@ int ass_ensemble_destroy(ass_ensemble* e);
 
 /* ---- multi-GPU: ONE large body, particles split into contiguous slabs, one rank (process, GPU) per slab (SURVEY 8e,
  *      BASELINE C4).  Every rank uploads the whole body and the whole spring list, then calls ass_shard_setup.  Rank g
- *      integrates, and evaluates forces onto, particles [bounds[g], bounds[g+1]) only.  Per step every rank pulls the
- *      other slabs' x and v through peer-mapped memory (CUDA IPC over NVLink) with the copy engines while its SMs
- *      already run gravity against its own slab's sources -- the step's only exchange, the analogue of one all-gather.
- *      The launcher owns two barriers per step (torch.distributed in bench.py):
- *          ass_shard_begin -> barrier -> ass_shard_exchange -> barrier -> ass_shard_finish                        ---- */
+ *      integrates, and sums the springs onto, particles [bounds[g], bounds[g+1]) only.  Gravity is divided by pairs of
+ *      slabs so that every unordered particle pair is evaluated once and every rank does the same work; a rank leaves
+ *      the partial accelerations it computed for other slabs in an exported buffer.  All transfers are pulls through
+ *      peer-mapped memory (CUDA IPC over NVLink) by the copy engines: the peers' x and v while the SMs already work on
+ *      the own slab (the analogue of one all-gather), the partials before the springs (one reduce-scatter).
+ *      The launcher owns three barriers per step (torch.distributed; asteroid-spring-sims_b200/launcher.py):
+ *          ass_shard_begin -> barrier -> ass_shard_exchange -> barrier -> ass_shard_gravity -> barrier -> ass_shard_finish ---- */
 #define ASS_IPC_HANDLE_BYTES 64
 int ass_shard_setup(ass_sim* sim, int rank, int nranks, const int* bounds /* nranks + 1 */);
 int ass_shard_export(ass_sim* sim, unsigned char handle[ASS_IPC_HANDLE_BYTES]);
@@ -215,8 +217,9 @@ int ass_shard_import(ass_sim* sim, int peer_rank, const unsigned char handle[ASS
 /* same-process peers (several ass_sim in one process): share the pointer instead of an IPC handle */
 int ass_shard_import_local(ass_sim* sim, int peer_rank, ass_sim* peer);
 int ass_shard_begin(ass_sim* sim);                        /* part1 on the own slab (if not pre-drifted); synchronises */
-int ass_shard_exchange(ass_sim* sim);                     /* pulls + gravity(own-slab sources); returns when pulls landed */
-int ass_shard_finish(ass_sim* sim, int pre_drift_next);   /* gravity(remote sources), springs, part2 on the own slab */
+int ass_shard_exchange(ass_sim* sim);                     /* pulls + gravity within the own slab; returns when pulls landed */
+int ass_shard_gravity(ass_sim* sim);                      /* gravity between slabs; synchronises (partials complete) */
+int ass_shard_finish(ass_sim* sim, int pre_drift_next);   /* add the peers' partials, springs, part2 on the own slab */
 int ass_shard_gather(ass_sim* sim);                       /* bring every slab's x, v home (before a full download) */
 
 /* ---- measurement ---- */

@@ -92,7 +92,7 @@ def test_ensemble_errors(gpu):
     assert "shared memory" in str(e.value)
 
 
-@pytest.mark.parametrize("nranks", [1, 2, 3])
+@pytest.mark.parametrize("nranks", [1, 2, 3, 4, 5])
 def test_sharded_body_in_process(gpu, oracle, body010, nranks):
     """C4's protocol at small size: every 'rank' is an ass_sim of this process; result = the unsharded path's."""
     g = body010
@@ -118,6 +118,7 @@ def test_sharded_body_in_process(gpu, oracle, body010, nranks):
     for step in range(nsteps):
         for s in sims: s.shard_begin()
         for s in sims: s.shard_exchange()
+        for s in sims: s.shard_gravity()
         for s in sims: s.shard_finish(pre_drift_next=(step < nsteps - 1))
     for s in sims: s.shard_gather()
     # reference: the oracle, and the unsharded GPU path
@@ -160,7 +161,7 @@ dist.all_gather_object(handles, s.shard_export())
 for q in range(world):
     if q != rank: s.shard_import(q, handles[q])
 for step in range(4):
-    s.shard_begin(); dist.barrier(); s.shard_exchange(); dist.barrier(); s.shard_finish(step < 3)
+    s.shard_begin(); dist.barrier(); s.shard_exchange(); dist.barrier(); s.shard_gravity(); dist.barrier(); s.shard_finish(step < 3)
 dist.barrier(); s.shard_gather(); dist.barrier()
 out = s.download(p.copy())
 u = A.Sim(); u.upload(p); u.set_springs(sp); u.set_params(**prm); u.step(4); want = u.download(p.copy())

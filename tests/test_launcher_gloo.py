@@ -39,6 +39,8 @@ WORKER = textwrap.dedent('''
         def shard_exchange(self):
             assert sorted(self.peers) == [q for q in range(world) if q != rank]
             self._run("exchange", 0.03 * (world - rank))
+        def shard_gravity(self):
+            self._run("gravity", 0.015 * (rank + 1))
         def shard_finish(self, pre_drift_next=False):
             self._run("finish:%%d" %% int(pre_drift_next), 0.01)
             self.step += 1
@@ -81,14 +83,17 @@ def test_two_rank_launcher_protocol_over_gloo(tmp_path):
     assert ranks[0]["members"] == [0, 2, 4, 6, 8, 10] and ranks[1]["members"] == [1, 3, 5, 7, 9]
     # reductions reach every rank
     assert all(r["max"] == 2.5 and r["sum"] == 30.0 for r in ranks)
-    # ordering: in every step, nobody starts pulling before every slab has drifted, and nobody kicks before every pull landed
+    # ordering: in every step, nobody starts pulling before every slab has drifted, nobody writes partials before every
+    # pull landed, and nobody collects partials before every rank finished writing them
     for step in range(3):
         ev = {(r["rank"], e[0].split(":")[0]): e for r in ranks for e in r["log"] if e[1] == step}
         begin_end = max(ev[(q, "begin")][3] for q in (0, 1))
         exch_start = min(ev[(q, "exchange")][2] for q in (0, 1))
         exch_end = max(ev[(q, "exchange")][3] for q in (0, 1))
+        grav_start = min(ev[(q, "gravity")][2] for q in (0, 1))
+        grav_end = max(ev[(q, "gravity")][3] for q in (0, 1))
         fin_start = min(ev[(q, "finish")][2] for q in (0, 1))
-        assert begin_end <= exch_start and exch_end <= fin_start, step
+        assert begin_end <= exch_start and exch_end <= grav_start and grav_end <= fin_start, step
     # the last step of a batch does not pre-drift (the caller sees end-of-step positions)
     assert [e[0] for e in ranks[0]["log"] if e[0].startswith("finish")] == ["finish:1", "finish:1", "finish:0"]
 
