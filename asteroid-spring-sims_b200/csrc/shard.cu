@@ -9,7 +9,9 @@
 // and every rank does the same amount of work.  With P ranks and D = (P-1)/2, rank g evaluates
 //     slab g x slab g                     (triangle)                         -> its own accelerations
 //     slab g x slab (g+d) mod P, d = 1..D (rectangle)                        -> its own, and a partial for slab g+d
-//     slab g <- slab (g+P/2) mod P        (P even only: one-sided, both ranks of the antipodal pair do their half)
+//     half of slab g x slab (g+P/2) mod P (P even only: the two ranks of an antipodal pair split its rectangle -- the
+//                                          lower rank takes its own lower half against the whole other slab, the higher
+//                                          rank its whole slab against the other's upper half)
 // and trailing point masses (params.n_perts) are handled one-sidedly by whoever owns the targets.  The partials for
 // foreign slabs are left in an exported buffer; their owners pull and add them in a fixed order.
 //
@@ -33,6 +35,8 @@
 #include <string.h>
 
 #include <algorithm>
+#include <utility>
+#include <vector>
 
 #include "common.cuh"
 
@@ -178,6 +182,9 @@ extern "C" int ass_shard_exchange(ass_sim* s) {
 	return ASS_OK;
 }
 
+// where an antipodal pair cuts the lower rank's slab
+static int half_point(int lo, int hi) { return lo + (hi - lo) / 2; }
+
 // one-sided: acc[t_lo, t_hi) += pull of sources [s_lo, s_hi)
 static int one_sided_add(ass_sim* s, int s_lo, int s_hi, int t_lo, int t_hi) {
 	if (t_hi <= t_lo || s_hi <= s_lo) return ASS_OK;
@@ -206,10 +213,13 @@ extern "C" int ass_shard_gravity(ass_sim* s) {
 			body_slab(s, (g + d) % P, &plo, &phi);
 			if ((rc = ass_launch_gravity_sym_pair(s, lo, hi, plo, phi, s->acc, true, fpart, false))) return rc;
 		}
-		if (P % 2 == 0 && P > 1) {  // antipodal slab: each of the two ranks sums its own side
+		if (P % 2 == 0) {  // antipodal slab: the pair's rectangle is split between its two ranks
+			const int h = (g + P / 2) % P;
 			int plo, phi;
-			body_slab(s, (g + P / 2) % P, &plo, &phi);
-			if ((rc = one_sided_add(s, plo, phi, lo, hi))) return rc;
+			body_slab(s, h, &plo, &phi);
+			if (g < h) rc = ass_launch_gravity_sym_pair(s, lo, half_point(lo, hi), plo, phi, s->acc, true, fpart, false);
+			else rc = ass_launch_gravity_sym_pair(s, lo, hi, half_point(plo, phi), phi, s->acc, true, fpart, false);
+			if (rc) return rc;
 		}
 		// point masses: they pull on my body particles; whoever owns them sums everything onto them
 		if ((rc = one_sided_add(s, nb, n, lo, hi))) return rc;
@@ -243,17 +253,27 @@ extern "C" int ass_shard_finish(ass_sim* s, int pre_drift_next) {
 		int lo, hi;
 		body_slab(s, g, &lo, &hi);
 		const size_t cnt = (size_t) std::max(hi - lo, 0), n = (size_t) s->n;
-		if (cnt && D > 0) {
-			if ((rc = ass_buf_reserve(s->grav_partial, sizeof(vec4d) * cnt * (size_t) D))) return rc;
+		// (rank, first particle) of every contribution, in the order they are added
+		std::vector<std::pair<int, int>> from;
+		for (int d = 1; d <= D; d++) from.push_back({ ((g - d) % R + R) % R, lo });
+		if (R % 2 == 0) {
+			const int h = (g + R / 2) % R;
+			from.push_back({ h, g < h ? half_point(lo, hi) : lo });  // the higher rank covered only my upper half
+		}
+		if (cnt && !from.empty()) {
+			if ((rc = ass_buf_reserve(s->grav_partial, sizeof(vec4d) * cnt * from.size()))) return rc;
 			vec4d* land = (vec4d*) s->grav_partial.p;
-			for (int d = 1; d <= D; d++) {
-				const int r = ((g - d) % R + R) % R;
+			for (size_t q = 0; q < from.size(); q++) {
+				const int r = from[q].first, first = from[q].second;
+				if (hi <= first) continue;
 				REQUIRE(sh.peer_window[r], ASS_ESTATE, "a peer window has not been imported");
-				CU_TRY(cudaMemcpyAsync(land + (size_t) (d - 1) * cnt, sh.peer_window[r] + 2 * n + (size_t) lo, sizeof(vec4d) * cnt, cudaMemcpyDeviceToDevice, s->stream));
+				CU_TRY(cudaMemcpyAsync(land + q * cnt, sh.peer_window[r] + 2 * n + (size_t) first, sizeof(vec4d) * (size_t) (hi - first), cudaMemcpyDeviceToDevice, s->stream));
 			}
 			ass_tic(s, ASS_K_GRAVITY);
-			for (int d = 1; d <= D; d++) {
-				k_add_partial<<<(unsigned) ((cnt + 255) / 256), 256, 0, s->stream>>>(s->acc, land + (size_t) (d - 1) * cnt, lo, hi);
+			for (size_t q = 0; q < from.size(); q++) {
+				const int first = from[q].second;
+				if (hi <= first) continue;
+				k_add_partial<<<(unsigned) ((hi - first + 255) / 256), 256, 0, s->stream>>>(s->acc, land + q * cnt, first, hi);
 				LAUNCH_CHECK();
 			}
 			ass_toc(s, ASS_K_GRAVITY);

@@ -241,11 +241,11 @@ def run_reference(args, rank, world):
            "cpu_baseline": {"value": value, "unit": "node-steps/s", "cores": cores, "kind": "reference", "sample": sample},
            "e2e": {"value": value, "unit": "node-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "detail": detail}
-    print(json.dumps(out))
+    emit(out)
 
 
 def finish_line(out, dist):
-    print(json.dumps(out))
+    emit(out)
     if dist is not None:
         dist.destroy_process_group()
 
@@ -386,18 +386,43 @@ def run_c4_sharded(args, A, rank, world, local, dist):
     out = {"metric": "node-steps/s", "value": value, "unit": "node-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": 1e3 * t_wall / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
            "config": {"workload": "C4: %s, slabs over %d GPUs" % (cfg["desc"], world), "N": n, "NS": ns, "bounds": bounds,
-                      "exchange": "per step: pull of the other slabs' x and v (%.1f MB) over CUDA-IPC peer mappings, copy engines, overlapped with own-slab gravity; 2 host barriers" % (64e-6 * (n - (bounds[1] - bounds[0]))),
+                      "exchange": "per step: pull of the other slabs' x and v (%.1f MB, overlapped with the own-slab gravity triangle) and of the partial accelerations the peers computed for this slab (%.1f MB) over CUDA-IPC peer mappings, copy engines; 3 host barriers" % (
+                          64e-6 * (n - (bounds[1] - bounds[0])), 32e-6 * (bounds[1] - bounds[0]) * (world // 2)),
+                      "gravity": "divided by pairs of slabs: every unordered particle pair evaluated once, the same work on every rank",
                       "l2": "inputs larger than L2 (half-edges %.0f MB)" % (64e-6 * ns), "parallelism": "particle slabs x%d" % world},
            "clocks": clk, "gpu_launches": int(launches),
            "e2e": {"value": n * min(args.steps, 3) / t_e2e, "unit": "node-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": int(n * 80)},
            "roofline": {"kernel": "k_gravity", "bound": "fp64", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach / fp64_peak, "traffic": None,
-                        "note": "per GPU: 20 flop x N x N/%d pairs per step over the gravity kernels' device time (max over ranks)" % world},
+                        "note": "per GPU: 20 flop x N x N/%d ordered pairs per step (SURVEY 8d convention; the pair-once kernels execute 9.5 FP64 instructions per ordered pair) over the gravity kernels' device time (max over ranks)" % world},
            "cpu_baseline": None,
            "kernel_ms": {k: {"ms": v[0], "launches": v[1]} for k, v in kt.items()}, "setup": setup}
     finish_line(out, dist)
 
 
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Everything any library prints on fd 1 during the run (NCCL's version banner comes from C, past sys.stdout) goes
+    to stderr; emit() writes the one JSON line to the real stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    line = (json.dumps(obj) + "\n").encode()
+    sys.stdout.flush()
+    if _REAL_STDOUT is None:
+        os.write(1, line)
+    else:
+        os.write(_REAL_STDOUT, line)
+
+
 def main():
+    quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -424,6 +449,8 @@ def main():
     if name == "C4" and world > 1:
         return run_c4_sharded(args, A, rank, world, local, dist)
     cfg = dict(WORKLOADS[name])
+    if name == "C4" and os.environ.get("ASS_C4_D"):
+        cfg["d"] = float(os.environ["ASS_C4_D"])      # a smaller body of the same kind, for quick checks
     # ensemble member `rank`: spin rate swept across members (BASELINE config 5's sweep, applied to bodies of this size)
     omega = tuple(np.array(cfg["omega"]) * (1.0 + 0.1 * rank))
     sim, p, springs, setup = build_body(A, cfg, omega, with_point_mass=(name == "C4"))
@@ -529,7 +556,7 @@ def main():
         "kernel_ms": {k: {"ms": v[0], "launches": v[1]} for k, v in kt.items()},
         "wall_ms_per_step_incl_flush": 1e3 * t_wall / args.steps, "setup": setup, "fp64_peak_tflops_measured": fp64_peak,
     }
-    print(json.dumps(out))
+    emit(out)
     if dist is not None:
         dist.destroy_process_group()
 
