@@ -35,11 +35,17 @@ struct BodyDesc {
 	int gravity, af, heartbeat, pad;
 };
 
-// endpoint state out of shared memory (see the layout note in k_ensemble)
+// endpoint state out of shared memory (see the layout note in k_ensemble): three 16-byte reads per endpoint, plus the
+// mass only when the member's masses differ (with equal masses the arithmetic never looks at the neighbour's)
+template <bool UNI>
 struct SharedNodes {
-	const double2 *xy, *zm, *vxy, *vz0;
-	__device__ __forceinline__ vec4d pos(int i) const { const double2 a = xy[i], b = zm[i]; vec4d p; p.x = a.x; p.y = a.y; p.z = b.x; p.w = b.y; return p; }
-	__device__ __forceinline__ vec4d velocity(int i) const { const double2 a = vxy[i], b = vz0[i]; vec4d v; v.x = a.x; v.y = a.y; v.z = b.x; v.w = 0.0; return v; }
+	const double2 *xy, *zv, *vxy;
+	const double* m;
+	__device__ __forceinline__ void get(int i, vec4d& p, vec4d& v) const {
+		const double2 a = xy[i], b = zv[i], c = vxy[i];
+		p.x = a.x; p.y = a.y; p.z = b.x; p.w = UNI ? 0.0 : m[i];
+		v.x = c.x; v.y = c.y; v.z = b.y; v.w = 0.0;
+	}
 };
 
 template <bool UNI>
@@ -52,21 +58,23 @@ __global__ void __launch_bounds__(ET, 1) k_ensemble(const BodyDesc* __restrict__
 	__shared__ __align__(8) uint64_t full[2];
 	const BodyDesc B = desc[blockIdx.x];
 	const int n = B.n, tid = threadIdx.x;
-	// carve: ring[2][ring_records] | xy | zm | vxy | vz0 (16-byte entries) | srow[max_n + 1]
-	// Node state is kept as four arrays of 16-byte pairs rather than 32-byte vectors: a random gather of 32-byte
-	// entries starts on only four distinct bank groups (8-way conflicts); 16-byte entries start on eight and tile all 32 banks.
+	// carve: ring[2][ring_records] | xy | zv | vxy (16-byte entries) | m (8-byte) | srow[max_n + 1]
+	// Node state is kept as arrays of 16-byte pairs -- (x, y), (z, vz), (vx, vy) -- rather than 32-byte vectors: a random
+	// gather of 32-byte entries starts on only four distinct bank groups (8-way conflicts); 16-byte entries start on
+	// eight and tile all 32 banks.  Three reads per endpoint instead of four: the shared-memory pipe is what bounds this
+	// kernel.  The mass has its own array.
 	HalfEdge* ring = (HalfEdge*) smem_raw;
 	double2* s_xy = (double2*) (ring + 2 * (size_t) ring_records);
-	double2* s_zm = s_xy + max_n;
-	double2* s_vxy = s_zm + max_n;
-	double2* s_vz0 = s_vxy + max_n;
-	int* srow = (int*) (s_vz0 + max_n);
+	double2* s_zv = s_xy + max_n;
+	double2* s_vxy = s_zv + max_n;
+	double* s_m = (double*) (s_vxy + max_n);
+	int* srow = (int*) (s_m + max_n + (max_n & 1));
 	vec4d* acc = acc_g + B.node_off;
-	auto ldp = [&](int i) { const double2 a = s_xy[i], b = s_zm[i]; vec4d p; p.x = a.x; p.y = a.y; p.z = b.x; p.w = b.y; return p; };
-	auto ldv = [&](int i) { const double2 a = s_vxy[i], b = s_vz0[i]; vec4d v; v.x = a.x; v.y = a.y; v.z = b.x; v.w = 0.0; return v; };
-	auto stp = [&](int i, const vec4d p) { s_xy[i] = make_double2(p.x, p.y); s_zm[i] = make_double2(p.z, p.w); };
-	auto stv = [&](int i, const vec4d v) { s_vxy[i] = make_double2(v.x, v.y); s_vz0[i] = make_double2(v.z, 0.0); };
-	const SharedNodes nodes{ s_xy, s_zm, s_vxy, s_vz0 };
+	auto ldp = [&](int i) { const double2 a = s_xy[i]; vec4d p; p.x = a.x; p.y = a.y; p.z = s_zv[i].x; p.w = s_m[i]; return p; };
+	auto ldv = [&](int i) { const double2 a = s_vxy[i]; vec4d v; v.x = a.x; v.y = a.y; v.z = s_zv[i].y; v.w = 0.0; return v; };
+	auto stp = [&](int i, const vec4d p) { s_xy[i] = make_double2(p.x, p.y); s_zv[i].x = p.z; s_m[i] = p.w; };
+	auto stv = [&](int i, const vec4d v) { s_vxy[i] = make_double2(v.x, v.y); s_zv[i].y = v.z; };
+	const SharedNodes<UNI> nodes{ s_xy, s_zv, s_vxy, s_m };
 	for (int i = tid; i < n; i += ET) {
 		stp(i, posm_g[B.node_off + i]);
 		stv(i, vel_g[B.node_off + i]);
@@ -366,7 +374,7 @@ extern "C" int ass_ensemble_create(ass_ensemble** out, int n_bodies, const int* 
 	e->total_he = (long long) he_base;
 	fill_desc(e);
 	e->ring_records = std::max(16, (e->ring_records + 7) / 8 * 8);
-	e->smem = sizeof(HalfEdge) * 2 * (size_t) e->ring_records + sizeof(vec4d) * 2 * (size_t) e->max_n + sizeof(int) * ((size_t) e->max_n + 1) + 64;
+	e->smem = sizeof(HalfEdge) * 2 * (size_t) e->ring_records + (3 * sizeof(double2) + sizeof(double)) * ((size_t) e->max_n + 1) + sizeof(int) * ((size_t) e->max_n + 1) + 64;
 	if (e->smem > 227 * 1024 - 2048) {
 		ens_free(e);
 		ass_set_error("ass_ensemble_create: a body of %d nodes (%d half-edges per 64-node wave) does not fit in shared memory (limit ~3000 nodes); use ass_sim for large bodies",
