@@ -28,6 +28,8 @@ extern "C" {
 #include "springs.h"
 #include "physics.h"
 #include "shapes.h"
+#include "kepcart.h"
+#include "orb.h"
 #include "input_spring.h"
 
 using namespace libconfig;
@@ -43,6 +45,9 @@ string fileroot;
 double mass_scale, time_scale, length_scale, temp_scale, omega_scale, vel_scale, p_scale, L_scale, a_scale, F_scale,
 		E_scale, dEdt_scale, P_scale;
 int use_gravity = 0;
+// phobos / phobos_deimos shape (modules/phobos_deimos/problem.cpp): one central point mass with a J2, migration drift
+int point_mass = 0;
+double J2_plus = 1.96e-3, R_plus = 0.5, theta_plus = 0.4, phi_plus = 0.3, inv_tau_a = 1e-2, inv_tau_e = 3e-2;
 
 void additional_forces(reb_simulation *n_body_sim);
 void heartbeat(reb_simulation *const n_body_sim);
@@ -66,6 +71,7 @@ int main(int argc, char *argv[]) {
 	}
 	cfg.lookupValue("seed", seed);
 	cfg.lookupValue("gravity", use_gravity);
+	cfg.lookupValue("point_mass", point_mass);
 	Vector omega(omega_in);
 
 	reb_simulation *const n_body_sim = reb_create_simulation();
@@ -91,6 +97,13 @@ int main(int argc, char *argv[]) {
 	subtract_cov(n_body_sim, i_low, i_high);
 	spin_body(n_body_sim, i_low, i_high, omega);
 	connect_springs_dist(n_body_sim, max_spring_dist, i_low, i_high, default_spring);
+	if (point_mass) {
+		// modules/phobos_deimos/problem.cpp:246-262: a Mars-like mass on a slightly eccentric, inclined orbit about the body
+		OrbitalElements orb_el;
+		orb_el.a = 7.0; orb_el.e = 0.02; orb_el.i = 0.1; orb_el.long_asc_node = 0.3; orb_el.arg_peri = 0.2; orb_el.mean_anom = 1.0;
+		add_pt_mass_kep(n_body_sim, i_low, i_high, -1, 1.0, 0.5, orb_el);
+		num_perts = 1;
+	}
 
 	std::ofstream runfile(fileroot + "_run.txt", std::ios::out | std::ios::trunc);
 	runfile << std::hexfloat << "N " << n_body_sim->N << "\nNS " << num_springs << "\nmean_rs0 " << mean_spring_length()
@@ -118,6 +131,8 @@ void additional_forces(reb_simulation *n_body_sim) {
 	if (!use_gravity)
 		zero_accel(n_body_sim);
 	spring_forces(n_body_sim);
+	if (point_mass)  // modules/phobos_deimos/problem.cpp:384-386
+		quadrupole_accel(n_body_sim, J2_plus, R_plus, phi_plus, theta_plus, n_body_sim->N - num_perts);
 }
 
 // modules/asteroid_spin/problem.cpp:181-207
@@ -126,6 +141,11 @@ void heartbeat(reb_simulation *const n_body_sim) {
 	if (std::abs(n_body_sim->t - t_damp) < 0.9 * n_body_sim->dt)
 		set_gamma(def_gamma);
 	center_sim(n_body_sim, 0, n_body_sim->N - num_perts);
+	if (point_mass) {  // modules/phobos_deimos/problem.cpp:322-344
+		const double migfac = exp(-n_body_sim->t / 10.0);
+		drift_resolved(n_body_sim, n_body_sim->dt, inv_tau_a * migfac, inv_tau_e * migfac, n_body_sim->N - num_perts, 0,
+				n_body_sim->N - num_perts);
+	}
 	if (reb_output_check(n_body_sim, print_interval)) {
 		const int i_low = 0, i_high = n_body_sim->N - num_perts;
 		Vector L = measure_L(n_body_sim, i_low, i_high);

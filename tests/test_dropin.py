@@ -27,10 +27,11 @@ def build():
         pytest.skip("tests/dropin/_build not built and /root/reference absent")
 
 
-def run(binary, workdir, gravity, env_extra=None, expect_ok=True):
+def run(binary, workdir, gravity, env_extra=None, expect_ok=True, point_mass=0):
     os.makedirs(workdir, exist_ok=True)
     cfg = open(os.path.join(DROPIN, "problem.cfg")).read()
     cfg = re.sub(r"gravity = \d;", "gravity = %d;" % gravity, cfg)
+    cfg = re.sub(r"point_mass = \d;", "point_mass = %d;" % point_mass, cfg)
     open(os.path.join(workdir, "problem.cfg"), "w").write(cfg)
     env = dict(os.environ)
     env.update(env_extra or {})
@@ -95,6 +96,28 @@ def test_dropin_matches_reference(tmp_path, gravity, resident):
     # history written by the module's heartbeat through the reference's own diagnostics: t, L, KE, SPE, GPE, power
     assert g_ext.shape == r_ext.shape
     assert np.array_equal(g_ext[:, 0], r_ext[:, 0])
+    e_r = r_ext[:, 4] + r_ext[:, 5] + r_ext[:, 6]
+    e_g = g_ext[:, 4] + g_ext[:, 5] + g_ext[:, 6]
+    assert np.all(np.abs(e_g - e_r) <= 1e-9 * np.abs(e_r))
+    assert np.abs(g_ext[:, 1:4] - r_ext[:, 1:4]).max() <= 1e-9 * np.abs(r_ext[:, 1:4]).max()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("resident", ["0", "1"])
+def test_dropin_matches_reference_phobos_shape(tmp_path, resident):
+    """modules/phobos_deimos's shape: a point mass added by the reference's own add_pt_mass_kep, REB_GRAVITY_BASIC,
+    additional_forces = spring_forces + quadrupole_accel, heartbeat = center_sim + drift_resolved."""
+    build()
+    ref_dir, gpu_dir = str(tmp_path / "ref"), str(tmp_path / "b200")
+    run("synth_ref", ref_dir, 1, point_mass=1)
+    run("synth_b200", gpu_dir, 1, {"ASS_RESIDENT": resident}, point_mass=1)
+    r_run, r_ext, r_head, r_state = parse(ref_dir)
+    g_run, g_ext, g_head, g_state = parse(gpu_dir)
+    assert g_run == r_run and g_head == r_head
+    assert r_state.shape == (331, 10) and r_state[-1, 9] == 1.0            # the point mass is the last particle
+    amax = np.abs(r_state[:, 6:9]).max()
+    assert np.abs(g_state[:, 6:9] - r_state[:, 6:9]).max() <= 1e-10 * amax
+    assert np.allclose(g_state[:, :6], r_state[:, :6], rtol=0, atol=1e-12)
     e_r = r_ext[:, 4] + r_ext[:, 5] + r_ext[:, 6]
     e_g = g_ext[:, 4] + g_ext[:, 5] + g_ext[:, 6]
     assert np.all(np.abs(e_g - e_r) <= 1e-9 * np.abs(e_r))
