@@ -119,6 +119,12 @@ struct ass_sim {
 	int* wave_off = nullptr;
 	int n_waves = 0, wave_he_max = 0;
 	size_t wave_cap = 0;
+	std::vector<int> h_wave_off;  // host copy of wave_off
+	// which waves each CTA of the streaming kernel takes: cta_wave[c] .. cta_wave[c+1] (springs.cu: ensure_cta_waves)
+	int* cta_wave = nullptr;
+	size_t cta_wave_cap = 0;
+	int cta_wave_grid = 0;
+	long long cta_wave_epoch = -1;
 	double2* pal = nullptr;   // palette of distinct (k, gamma) pairs
 	int n_pal = 0;
 	size_t he_cap = 0, row_cap = 0, pal_cap = 0;

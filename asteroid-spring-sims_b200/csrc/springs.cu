@@ -140,8 +140,9 @@ struct StageLayout {
 template <bool ZERO_FIRST, bool KICK, bool UNI>
 __global__ void __launch_bounds__(ST_THREADS, 1) k_spring_stream(const vec4d* __restrict__ ps, const vec4d* __restrict__ vs,
 		const int* __restrict__ order, vec4d* __restrict__ acc, const int* __restrict__ row_ptr, const int* __restrict__ wave_off,
-		const HalfEdge* __restrict__ he, const double2* __restrict__ pal, int n, int n_waves, int wave_he_max, vec4d* __restrict__ posm_out,
-		vec4d* __restrict__ vel_out, vec4d* __restrict__ ps_out, vec4d* __restrict__ vs_out, double dt, int pre_drift_next) {
+		const int* __restrict__ cta_wave, const HalfEdge* __restrict__ he, const double2* __restrict__ pal, int n, int wave_he_max,
+		vec4d* __restrict__ posm_out, vec4d* __restrict__ vel_out, vec4d* __restrict__ ps_out, vec4d* __restrict__ vs_out, double dt,
+		int pre_drift_next) {
 	extern __shared__ __align__(128) unsigned char st_smem[];
 	__shared__ __align__(8) uint64_t full[ST_STAGES], empty[ST_STAGES];
 	__shared__ vec4d a_old[ST_WAVE];  // landing zone of the old accelerations (slot g is private to group g's lane 0)
@@ -157,9 +158,12 @@ __global__ void __launch_bounds__(ST_THREADS, 1) k_spring_stream(const vec4d* __
 	__syncthreads();
 	// thread 0 only: queue the copies of this CTA's `jt`-th wave into stage jt % ST_STAGES (waiting, from the second lap
 	// on, until every warp has handed that stage back)
+	// this CTA's waves: a contiguous run [w_beg, w_end), cut on the host so that every CTA owns the same number of
+	// half-edges (+ a per-node constant), not the same number of waves
+	const int w_beg = cta_wave[blockIdx.x], w_end = cta_wave[blockIdx.x + 1];
 	auto produce = [&](int jt) {
-		const int w = blockIdx.x + jt * gridDim.x;
-		if (w >= n_waves) return;
+		const int w = w_beg + jt;
+		if (w >= w_end) return;
 		const int st = jt % ST_STAGES;
 		if (jt >= ST_STAGES) mbar_wait(&empty[st], (uint32_t) (((jt / ST_STAGES) & 1) ^ 1));
 		unsigned char* stage = st_smem + (size_t) st * L.bytes;
@@ -178,19 +182,38 @@ __global__ void __launch_bounds__(ST_THREADS, 1) k_spring_stream(const vec4d* __
 	if (tid == 0)
 		for (int jt = 0; jt < ST_STAGES - 1; jt++) produce(jt);
 	// ---- consumers: one group of SPRING_LANES lanes per rank of the wave ----
+	// The trip pipeline of spring_math.cuh (operands of trip t+1 requested before the arithmetic of trip t) runs ACROSS
+	// waves: during the warp's last trip of a wave every lane requests the first trip of its node in the NEXT wave, so
+	// the only gather latency a warp ever exposes is that of its very first trip.
 	const int g = tid / SPRING_LANES, lane = tid & (SPRING_LANES - 1);
 	const GlobalNodes nodes{ ps, vs };
-	int it = 0;
-	for (int w = blockIdx.x; w < n_waves; w += gridDim.x, it++) {
+	if (w_beg >= w_end) return;
+	// state of the node this lane is working on
+	int e, end;
+	bool v0, v1;
+	const HalfEdge* wave_he;
+	TripOperands cur;
+	auto open_wave = [&](int it) {  // rows and records of wave w_beg + it are (or become) available: position the lane on its node
 		const int st = it % ST_STAGES;
-		if (tid == 0) produce(it + ST_STAGES - 1);  // refills the stage every warp left one wave ago
 		mbar_wait(&full[st], (uint32_t) ((it / ST_STAGES) & 1));
 		const unsigned char* stage = st_smem + (size_t) st * L.bytes;
 		const int* rows = (const int*) (stage + L.rows);
-		const int k = w * ST_WAVE + g;
+		const bool live = (w_beg + it) * ST_WAVE + g < n;
+		wave_he = (const HalfEdge*) (stage + L.he) - rows[0];  // indexed with global record numbers
+		e = rows[g] + lane;
+		end = live ? rows[g + 1] : rows[g];
+		v0 = e < end; v1 = e + SPRING_LANES < end;
+	};
+	open_wave(0);
+	if (v0) cur = trip_request(wave_he, pal, e, v1, nodes);
+	for (int it = 0; w_beg + it < w_end; it++) {
+		const int st = it % ST_STAGES;
+		if (tid == 0) produce(it + ST_STAGES - 1);  // refills the stage every warp left one wave ago
+		const unsigned char* stage = st_smem + (size_t) st * L.bytes;
+		const int k = (w_beg + it) * ST_WAVE + g;
 		const bool live = k < n;
-		const int beg = rows[g], end = live ? rows[g + 1] : beg;
 		const int node = ((const int*) (stage + L.ord))[g];
+		const bool has_springs = ((const int*) (stage + L.rows))[g + 1] > ((const int*) (stage + L.rows))[g];
 		// the node's old acceleration: requested now (asynchronously, into shared memory: no register is held and
 		// nothing waits), needed after the sum
 		if (!ZERO_FIRST && live && lane == 0) {
@@ -199,8 +222,34 @@ __global__ void __launch_bounds__(ST_THREADS, 1) k_spring_stream(const vec4d* __
 		}
 		const vec4d pi = ((const vec4d*) (stage + L.ps))[live ? g : 0];
 		const vec4d vi = ((const vec4d*) (stage + L.vs))[live ? g : 0];
-		const HalfEdge* wave_he = (const HalfEdge*) (stage + L.he) - rows[0];  // indexed with global record numbers
-		const Force3 F = node_spring_sum<true, UNI>(wave_he, pal, beg, end, lane, pi, vi, nodes);
+		const bool more_waves = w_beg + it + 1 < w_end;
+		double ax = 0.0, ay = 0.0, az = 0.0;
+		while (true) {
+			// request trip t+1 of this node, or -- on the warp's last trip of the wave -- the first trip of the next wave's
+			const int en = e + 2 * SPRING_LANES;
+			const bool w0 = v0 && en < end, w1 = v0 && en + SPRING_LANES < end;
+			TripOperands nxt = cur;
+			const bool warp_last = !__any_sync(0xffffffffu, w0);
+			if (w0) nxt = trip_request(wave_he, pal, en, w1, nodes);
+			// arithmetic of trip t (the operands were requested one trip ago)
+			const TripOperands now = cur;
+			const bool n0 = v0, n1 = v1;
+			if (warp_last && more_waves) {  // every lane of the warp is on its last trip (or done): look into the next wave
+				open_wave(it + 1);
+				if (v0) nxt = trip_request(wave_he, pal, e, v1, nodes);
+			} else {
+				v0 = w0; v1 = w1; e = en;
+			}
+			if (n0) trip_accumulate<UNI>(now, n1, pi, vi, ax, ay, az);
+			cur = nxt;
+			if (warp_last) break;
+		}
+#pragma unroll
+		for (int m = SPRING_LANES / 2; m > 0; m >>= 1) {
+			ax += shfl_xor_d(ax, m, SPRING_LANES);
+			ay += shfl_xor_d(ay, m, SPRING_LANES);
+			az += shfl_xor_d(az, m, SPRING_LANES);
+		}
 		__syncwarp();
 		if ((tid & 31) == 0) mbar_arrive(&empty[st]);  // this warp has read everything it needs from the stage
 		if (live && lane == 0) {
@@ -210,7 +259,9 @@ __global__ void __launch_bounds__(ST_THREADS, 1) k_spring_stream(const vec4d* __
 				cp_async_wait_all();
 				a = a_old[g];
 			}
-			finish_node<KICK>(F, end > beg, a, pi, vi, node, k, acc, posm_out, vel_out, ps_out, vs_out, dt, pre_drift_next);
+			Force3 F;
+			F.x = ax; F.y = ay; F.z = az;
+			finish_node<KICK>(F, has_springs, a, pi, vi, node, k, acc, posm_out, vel_out, ps_out, vs_out, dt, pre_drift_next);
 		}
 	}
 }
@@ -249,6 +300,42 @@ static int springs_uniform_mass(ass_sim* s, bool* uni) {
 	return ASS_OK;
 }
 
+// Cut the waves into `grid` contiguous runs of equal weight (half-edges + a constant per node for the row epilogue): a
+// CTA's share of the work, not of the wave count, is what must be equal -- surface waves carry half the springs of
+// interior ones.  Cached per (grid, spring list).
+static int ensure_cta_waves(ass_sim* s, int grid) {
+	if (s->cta_wave && s->cta_wave_grid == grid && s->cta_wave_epoch == s->spring_epoch) return ASS_OK;
+	const int nw = s->n_waves;
+	std::vector<double> prefix((size_t) nw + 1, 0.0);
+	for (int w = 0; w < nw; w++)
+		prefix[(size_t) w + 1] = prefix[w] + (double) (s->h_wave_off[(size_t) w + 1] - s->h_wave_off[w]) + 6.0 * ASS_SPRING_WAVE;
+	std::vector<int> cut((size_t) grid + 1, nw);
+	cut[0] = 0;
+	int w = 0;
+	for (int c = 1; c < grid; c++) {
+		const double target = prefix[nw] * (double) c / (double) grid;
+		while (w < nw && prefix[(size_t) w + 1] <= target) w++;
+		// the boundary wave goes to whichever side leaves the smaller error
+		if (w < nw && target - prefix[w] > prefix[(size_t) w + 1] - target) w++;
+		cut[c] = std::max(w, cut[(size_t) c - 1]);
+	}
+	if ((size_t) grid + 1 > s->cta_wave_cap) {
+		cudaFree(s->cta_wave);
+		s->cta_wave = nullptr; s->cta_wave_cap = 0;
+		if (cudaMalloc(&s->cta_wave, sizeof(int) * ((size_t) grid + 1)) != cudaSuccess) {
+			cudaGetLastError();
+			ass_set_error("out of device memory for %d wave cuts", grid + 1);
+			return ASS_ENOMEM;
+		}
+		s->cta_wave_cap = (size_t) grid + 1;
+	}
+	CU_TRY(cudaMemcpyAsync(s->cta_wave, cut.data(), sizeof(int) * cut.size(), cudaMemcpyHostToDevice, s->stream));
+	CU_TRY(cudaStreamSynchronize(s->stream));
+	s->cta_wave_grid = grid;
+	s->cta_wave_epoch = s->spring_epoch;
+	return ASS_OK;
+}
+
 // Launch the streaming kernel if one stage ring fits in shared memory; returns 1 if it did not (caller falls back).
 template <bool ZERO_FIRST, bool KICK, bool UNI>
 static int launch_stream_t(ass_sim* s, double dt, bool pre_drift_next) {
@@ -268,7 +355,9 @@ static int launch_stream_t(ass_sim* s, double dt, bool pre_drift_next) {
 		if (ctas_per_sm < 1) return 1;
 	}
 	const int grid = std::min(s->n_waves, ass_sm_count() * ctas_per_sm);
-	kern<<<grid, ST_THREADS, smem_set, s->stream>>>(s->ps, s->vs, s->order, s->acc, s->row_ptr, s->wave_off, s->he, s->pal, s->n, s->n_waves,
+	int rc = ensure_cta_waves(s, grid);
+	if (rc) return rc;
+	kern<<<grid, ST_THREADS, smem_set, s->stream>>>(s->ps, s->vs, s->order, s->acc, s->row_ptr, s->wave_off, s->cta_wave, s->he, s->pal, s->n,
 			s->wave_he_max, s->posm_alt, s->vel_alt, s->ps_alt, s->vs_alt, dt, pre_drift_next ? 1 : 0);
 	LAUNCH_CHECK();
 	return ASS_OK;

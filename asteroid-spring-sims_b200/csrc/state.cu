@@ -337,7 +337,7 @@ extern "C" int ass_destroy(ass_sim* s) {
 	if (s->stream) cudaStreamSynchronize(s->stream);
 	ass_shard_release(s);  // a sharded simulation's posm / vel alias its exported window
 	ass_sym_plans_free(s);
-	cudaFree(s->wave_off);
+	cudaFree(s->wave_off); cudaFree(s->cta_wave);
 	cudaFree(s->order); cudaFree(s->rank); cudaFree(s->ps); cudaFree(s->vs); cudaFree(s->ps_alt); cudaFree(s->vs_alt);
 	cudaFree(s->posm); cudaFree(s->vel); cudaFree(s->acc); cudaFree(s->posm_alt); cudaFree(s->vel_alt);
 	cudaFree(s->he); cudaFree(s->row_ptr); cudaFree(s->slot); cudaFree(s->pal);
@@ -794,6 +794,7 @@ extern "C" int ass_set_springs(ass_sim* s, const ass_spring* sp, int ns) {
 	s->max_degree = maxdeg;
 	s->n_waves = n_waves;
 	s->wave_he_max = wave_he_max;
+	s->h_wave_off = wave_off;
 	s->spring_epoch++;
 	return ASS_OK;
 }
