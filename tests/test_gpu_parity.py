@@ -547,3 +547,47 @@ def test_orb_terms_match_reference(gpu, oracle, orb_golden):
             s.drift_resolved(1.0, 0.1, 0.1, 1, 0, 3)        # the point mass lies inside the body range
         with pytest.raises(gpu.AssError):
             s.drift_bin(1.0, 0.1, 0.1, 2, 2)
+
+
+def test_spring_kernels_agree_bit_for_bit(gpu, body015, monkeypatch):
+    """The streaming kernel (bulk-copy ring, persistent CTAs) and the plain kernel it falls back to when a ring does not
+    fit in shared memory run the same arithmetic in the same order: identical bits, with and without the fused kick."""
+    g = body015
+    start = g["start"].copy(); start[:, 6:9] = 0.25
+    sp = g["springs"]
+    outs = []
+    for no_stream in ("", "1"):
+        if no_stream:
+            monkeypatch.setenv("ASS_SPRINGS_NO_STREAM", "1")
+        else:
+            monkeypatch.delenv("ASS_SPRINGS_NO_STREAM", raising=False)
+        with new_sim(gpu, start, sp, gravity=0, dt=1e-3, additional_forces=1) as s:
+            s.spring_forces()
+            a1 = s.download(start.copy())
+            s.step(3)
+            outs.append((a1, s.download(start.copy())))
+    assert same_bits(outs[0][0], outs[1][0]) and same_bits(outs[0][1], outs[1][1])
+    # a mass edit on one sprung node switches both kernels to the general reduced-mass form
+    q = start.copy(); q[7, 9] *= 1.5
+    res = []
+    for no_stream in ("", "1"):
+        if no_stream:
+            monkeypatch.setenv("ASS_SPRINGS_NO_STREAM", "1")
+        else:
+            monkeypatch.delenv("ASS_SPRINGS_NO_STREAM", raising=False)
+        with new_sim(gpu, q, sp, gravity=0, dt=1e-3, additional_forces=2) as s:
+            s.step(2)
+            res.append(s.download(q.copy()))
+    assert same_bits(res[0], res[1])
+
+
+def test_spring_forces_nonuniform_mass_matches_oracle(gpu, oracle, body015):
+    g = body015
+    rng = np.random.default_rng(3)
+    p = g["start"].copy(); p[:, 9] *= rng.uniform(0.5, 2.0, len(p)); p[:, 6:9] = 0.0
+    sp = g["springs"]
+    want = p.copy(); oracle.spring_forces(want, sp)
+    with new_sim(gpu, p, sp) as s:
+        s.spring_forces()
+        out = s.download(p.copy())
+    assert acc_err(out[:, 6:9], want[:, 6:9]) <= ACC_TOL
