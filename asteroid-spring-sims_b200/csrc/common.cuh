@@ -242,6 +242,20 @@ __device__ __forceinline__ double fast_rsqrt(double a) {
 	return fma(y, q, y);
 }
 
+// a^(-3/2) in SIX FP64 instructions from the hardware seed y0 = MUFU.RSQ64H(a).  The seed carries 20 mantissa bits (the
+// instruction produces the high word only), so c2 = y0*y0 is exact and eps = 1 - a*c2 costs one FMA with one rounding:
+//   a^(-3/2) = y0^3 (1 - eps)^(-3/2) = y0^3 (1 + eps (3/2 + 15/8 eps)) + O(eps^3),   eps ~ 2^-21: 35/16 eps^3 ~ 2^-62.
+// y0^3 does not wait for the correction: the dependent chain is 4 deep after the seed.
+__device__ __forceinline__ double rsqrt_cubed(double a) {
+	double y0;
+	asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(a));
+	const double c2 = y0 * y0;
+	const double eps = fma(-a, c2, 1.0);
+	const double c = c2 * y0;
+	const double q = eps * fma(1.875, eps, 1.5);
+	return fma(c, q, c);
+}
+
 // ---- bulk-copy engine (TMA, 1-D, no tensor map) + mbarrier: global -> shared staging with completion by byte count ----
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t) __cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {

@@ -128,8 +128,7 @@ __global__ void __launch_bounds__(ET, 1) k_ensemble(const BodyDesc* __restrict__
 					const double dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
 					double r2 = fma(dz, dz, fma(dy, dy, fma(dx, dx, B.soft2)));
 					r2 = (j == i) ? 1.0 : r2;
-					const double y = fast_rsqrt(r2);
-					const double s = (y * y) * (y * pj.w);
+					const double s = rsqrt_cubed(r2) * pj.w;
 					ax = fma(s, dx, ax); ay = fma(s, dy, ay); az = fma(s, dz, az);
 				}
 				vec4d a;

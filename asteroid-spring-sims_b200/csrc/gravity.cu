@@ -44,8 +44,7 @@ __device__ __forceinline__ void pair_update(Targets<TI>& t, const vec4d sj, int 
 		const double dx = t.x[k] - sj.x, dy = t.y[k] - sj.y, dz = t.z[k] - sj.z;
 		double r2 = fma(dz, dz, fma(dy, dy, fma(dx, dx, soft2)));
 		if (CHECK) r2 = (j == t.idx[k]) ? 1.0 : r2;  // d == 0 there, so the term is exactly 0
-		const double y = fast_rsqrt(r2);
-		const double s = (y * y) * (y * sj.w);
+		const double s = rsqrt_cubed(r2) * sj.w;
 		t.ax[k] = fma(s, dx, t.ax[k]);
 		t.ay[k] = fma(s, dy, t.ay[k]);
 		t.az[k] = fma(s, dz, t.az[k]);

@@ -2,12 +2,12 @@
 //
 // The reference's double loop computes pair (i,j) and pair (j,i) separately; they share everything but the mass factor
 // and the sign (Newton's third law).  Evaluating the pair once and applying it to both particles costs
-//     3 DADD (d) + 3 DFMA (r^2) + 5 (rsqrt refinement) + 2 DMUL (y^3) + 2 DMUL (y^3 m_r, y^3 m_s) + 6 DFMA (both sides)
-//   = 21 FP64 instructions per unordered pair = 10.5 per ordered pair, against 17 in the one-sided kernel (gravity.cu),
-// i.e. against SURVEY 8d's 20 flop per ordered pair the ceiling moves from 59 % to 95 % of the DFMA peak.
+//     3 DADD (d) + 3 DFMA (r^2) + 6 (y^3 = r^-3 from the rsqrt seed) + 2 DMUL (y^3 m_r, y^3 m_s) + 6 DFMA (both sides)
+//   = 20 FP64 instructions per unordered pair = 10 per ordered pair, against 16 in the one-sided kernel (gravity.cu),
+// i.e. against SURVEY 8d's 20 flop per ordered pair the ceiling moves from 62 % to 100 % of the DFMA peak.
 // When every particle of the range carries the same mass -- the generators give every node M/N (shapes.cpp:262-267), so
 // this is the normal case -- the two mass products drop out of the pair (m is applied once per particle by the
-// reduction): 19 instructions per unordered pair.  The plan checks the masses on the device and picks the kernel.
+// reduction): 18 instructions per unordered pair.  The plan checks the masses on the device and picks the kernel.
 //
 // Layout of the computation (all deterministic, no atomics):
 //   * particles are cut into blocks of P = 1024.  A CTA keeps ONE block "resident" in registers (4 particles per
@@ -56,8 +56,8 @@ __device__ __forceinline__ vec4d load_or_dummy(const vec4d* __restrict__ posm, i
 
 // y^3 = r2^(-3/2) from the hardware seed y0 = MUFU.RSQ64H(r2) (relative error ~2^-22): with eps = 1 - r2 y0^2,
 //   r2^(-3/2) = y0^3 (1 - eps)^(-3/2) = y0^3 (1 + eps (3/2 + 15/8 eps)) + O(eps^3)        [35/16 eps^3 ~ 2^-62]
-// Seven FP64 instructions like "refine y, then cube it", but y0^3 does not wait for the refinement: the dependent
-// chain is 5 deep instead of 7.
+// SIX FP64 instructions (common.cuh: rsqrt_cubed): the seed has 20 mantissa bits, so y0^2 is exact and eps is one FMA;
+// y0^3 does not wait for the correction.
 __device__ __forceinline__ double rsqrt_seed(double a) {
 	double y;
 	asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
@@ -86,11 +86,9 @@ __device__ __forceinline__ void meet(const double2 xy, const double2 zm, int sid
 #pragma unroll
 	for (int k = 0; k < SG_R; k++) y0[k] = rsqrt_seed(r2[k]);
 #pragma unroll
-	for (int k = 0; k < SG_R; k++) e[k] = r2[k] * y0[k];
+	for (int k = 0; k < SG_R; k++) c[k] = y0[k] * y0[k];           // exact: the seed has 20 mantissa bits
 #pragma unroll
-	for (int k = 0; k < SG_R; k++) c[k] = y0[k] * y0[k];
-#pragma unroll
-	for (int k = 0; k < SG_R; k++) e[k] = fma(-e[k], y0[k], 1.0);
+	for (int k = 0; k < SG_R; k++) e[k] = fma(-r2[k], c[k], 1.0);  // eps = 1 - r2 y0^2, one rounding
 #pragma unroll
 	for (int k = 0; k < SG_R; k++) c[k] = c[k] * y0[k];
 #pragma unroll
