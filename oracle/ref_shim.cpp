@@ -231,4 +231,23 @@ void ref_drift_bin(void* h, double timestep, double inv_tau_a, double inv_tau_e,
 	drift_bin((reb_simulation*) h, timestep, inv_tau_a, inv_tau_e, part_1, part_2);   // orb.cpp:198-250
 }
 
+// update_stress (stress.cpp:32-98).  Returns 0 on success, 1 if the reference threw (its eigenvalues() throws a
+// `const char*` when the summed stress matrix is not EXACTLY symmetric, matrix_math.cpp:273-276, which update_stress's own
+// `catch (char*)` does not match); out[i*4 + 0..2] = eigenvalues, out[i*4 + 3] = max_force.
+int ref_update_stress(void* h, double* out) {
+	reb_simulation* r = (reb_simulation*) h;
+	extern std::vector<stress_tensor> stresses;
+	stresses.clear();
+	try {
+		update_stress(r);
+	} catch (const char*) {
+		return 1;
+	}
+	for (int i = 0; i < r->N; i++) {
+		out[4 * i + 0] = stresses[i].eigs[0]; out[4 * i + 1] = stresses[i].eigs[1]; out[4 * i + 2] = stresses[i].eigs[2];
+		out[4 * i + 3] = stresses[i].max_force;
+	}
+	return 0;
+}
+
 }  // extern "C"

@@ -351,3 +351,16 @@ def test_kat_quadrupole_closed_form(oracle, orb_golden):
         want[3] -= want[i] * P[i, 9] / P[3, 9]
     oracle.quadrupole_accel(P, G, J2s, Rp, 0.0, 0.0, 3)
     assert np.all(np.abs(P[:, 6:9] - want) <= 1e-5 * np.abs(want))
+
+
+def test_reference_update_stress_is_unusable_on_real_bodies(ref, body015):
+    """Why SURVEY 8f's N4 (stress tensor) is not built: on any body that is not the unit test's integer-coordinate
+    fixture the reference's own update_stress throws -- eigenvalues() demands an EXACTLY symmetric matrix
+    (matrix_math.cpp:273-276) and the sum of outer(F, L) is symmetric only up to rounding -- and its `catch (char*)`
+    (stress.cpp:88-93) does not match the `const char*` thrown, so a module calling it would terminate.  No shipped
+    module calls it.  There is nothing to be in parity with."""
+    import ctypes as C
+    p = body015["start"].copy()
+    ref.add_particles(p); ref.set_springs(body015["springs"])
+    out = np.zeros((len(p), 4))
+    assert ref.lib.ref_update_stress(ref.h, out.ctypes.data_as(C.c_void_p)) == 1
