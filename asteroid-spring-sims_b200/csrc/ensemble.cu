@@ -12,6 +12,7 @@
 //   * per step:  part1 | [gravity: all pairs out of shared memory] | springs (same arithmetic and lane order as springs.cu,
 //     so a member gets the bits the single-body path would give it) | kick + drift (+ next part1) | [center_sim].
 // Across GPUs the members are dealt round-robin by the host launcher; no collective is involved.
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -35,6 +36,15 @@ struct BodyDesc {
 	int gravity, af, heartbeat, pad;
 };
 
+// A member's state and accelerations may have been written by another SM earlier in the same launch (the previous batch
+// of its steps): read them past the (non-coherent) L1.
+__device__ __forceinline__ vec4d ldcg4(const vec4d* p) {
+	const double2 a = __ldcg((const double2*) p), b = __ldcg((const double2*) p + 1);
+	vec4d r;
+	r.x = a.x; r.y = a.y; r.z = b.x; r.w = b.y;
+	return r;
+}
+
 // endpoint state out of shared memory (see the layout note in k_ensemble): three 16-byte reads per endpoint, plus the
 // mass only when the member's masses differ (with equal masses the arithmetic never looks at the neighbour's)
 template <bool UNI>
@@ -48,16 +58,45 @@ struct SharedNodes {
 	}
 };
 
+// Work is handed out in ITEMS = (member b, batch j of `item_steps` consecutive steps), numbered j * n_bodies + b and
+// pulled from one atomic counter by persistent CTAs (one per SM).  With one CTA per member for the whole run, 512
+// members on 148 SMs take 4 rounds of which the last is half empty (86 % at BASELINE C5 on 8 GPUs); with items the
+// machine stays full and a member costs one extra 2 x 68 KB trip of its state through global memory per batch.
+// done[b] = number of batches of member b that are complete: an item waits (briefly, and only near a batch boundary)
+// until its predecessor has published the member's state.
 template <bool UNI>
 __global__ void __launch_bounds__(ET, 1) k_ensemble(const BodyDesc* __restrict__ desc, vec4d* __restrict__ posm_g, vec4d* __restrict__ vel_g,
-		vec4d* __restrict__ acc_g, const int* __restrict__ row_ptr, const HalfEdge* __restrict__ he, const double2* __restrict__ pal, int nsteps,
-		int with_hb, int max_n, int ring_records) {
+		vec4d* __restrict__ acc_g, const int* __restrict__ row_ptr, const HalfEdge* __restrict__ he, const double2* __restrict__ pal, int nsteps_total,
+		int with_hb, int max_n, int ring_records, int n_bodies, int item_steps, int* __restrict__ queue, int* __restrict__ done) {
 	extern __shared__ __align__(128) unsigned char smem_raw[];
 	__shared__ double red[ET / 32][4];
 	__shared__ double com[4];
 	__shared__ __align__(8) uint64_t full[2];
-	const BodyDesc B = desc[blockIdx.x];
-	const int n = B.n, tid = threadIdx.x;
+	__shared__ int s_item;
+	const int tid = threadIdx.x;
+	if (tid == 0) {
+		mbar_init(&full[0], 1);
+		mbar_init(&full[1], 1);
+		mbar_fence_init();
+	}
+	__syncthreads();
+	const int n_batches = (nsteps_total + item_steps - 1) / item_steps;
+	int c_base = 0;  // waves this CTA has streamed so far: ring slot and mbarrier parity carry across items
+	while (true) {
+	if (tid == 0) s_item = atomicAdd(queue, 1);
+	__syncthreads();
+	const int item = s_item;
+	__syncthreads();
+	if (item >= n_bodies * n_batches) break;
+	const int batch = item / n_bodies, body = item - batch * n_bodies;
+	const int nsteps = min(item_steps, nsteps_total - batch * item_steps);
+	if (tid == 0) {  // the member's previous batch must have published its state
+		while (atomicAdd(done + body, 0) < batch) __nanosleep(200);
+		__threadfence();
+	}
+	__syncthreads();
+	const BodyDesc B = desc[body];
+	const int n = B.n;
 	// carve: ring[2][ring_records] | xy | zv | vxy (16-byte entries) | m (8-byte) | srow[max_n + 1]
 	// Node state is kept as arrays of 16-byte pairs -- (x, y), (z, vz), (vx, vy) -- rather than 32-byte vectors: a random
 	// gather of 32-byte entries starts on only four distinct bank groups (8-way conflicts); 16-byte entries start on
@@ -76,15 +115,10 @@ __global__ void __launch_bounds__(ET, 1) k_ensemble(const BodyDesc* __restrict__
 	auto stv = [&](int i, const vec4d v) { s_vxy[i] = make_double2(v.x, v.y); s_zv[i].y = v.z; };
 	const SharedNodes<UNI> nodes{ s_xy, s_zv, s_vxy, s_m };
 	for (int i = tid; i < n; i += ET) {
-		stp(i, posm_g[B.node_off + i]);
-		stv(i, vel_g[B.node_off + i]);
+		stp(i, ldcg4(posm_g + B.node_off + i));
+		stv(i, ldcg4(vel_g + B.node_off + i));
 	}
 	for (int i = tid; i <= n; i += ET) srow[i] = row_ptr[B.row_off + i];
-	if (tid == 0) {
-		mbar_init(&full[0], 1);
-		mbar_init(&full[1], 1);
-		mbar_fence_init();
-	}
 	__syncthreads();
 	const double dt = B.dt, h = __dmul_rn(0.5, dt);
 	const bool hb = with_hb && B.heartbeat == 1;
@@ -93,13 +127,13 @@ __global__ void __launch_bounds__(ET, 1) k_ensemble(const BodyDesc* __restrict__
 	const int lane = tid & (SPRING_LANES - 1), group = tid / SPRING_LANES;
 	const int nw = (n + EW - 1) / EW;
 	const int total_waves = have_springs ? nsteps * nw : 0;
-	// records of wave c (counted over all steps of the batch) -> ring buffer c & 1
+	// records of wave c (counted over all steps of the item) -> ring buffer (c_base + c) & 1
 	auto issue = [&](int c) {  // thread 0 only
-		const int w = c % nw;
+		const int w = c % nw, slot = (c_base + c) & 1;
 		const int e0 = srow[w * EW], e1 = srow[min(n, (w + 1) * EW)];
 		const uint32_t bytes = (uint32_t) (e1 - e0) * (uint32_t) sizeof(HalfEdge);
-		mbar_expect_tx(&full[c & 1], bytes);
-		if (bytes) bulk_g2s(ring + (size_t) (c & 1) * ring_records, he + e0, bytes, &full[c & 1]);
+		mbar_expect_tx(&full[slot], bytes);
+		if (bytes) bulk_g2s(ring + (size_t) slot * ring_records, he + e0, bytes, &full[slot]);
 	};
 	if (tid == 0) {
 		if (total_waves > 0) issue(0);
@@ -139,21 +173,21 @@ __global__ void __launch_bounds__(ET, 1) k_ensemble(const BodyDesc* __restrict__
 		}
 		if (have_springs) {  // spring_forces (+ zero_accel when af == 2), one wave of 64 nodes at a time
 			for (int w = 0; w < nw; w++) {
-				const int c = step * nw + w;
-				mbar_wait(&full[c & 1], (uint32_t) ((c >> 1) & 1));
+				const int c = step * nw + w, cg = c_base + c;
+				mbar_wait(&full[cg & 1], (uint32_t) ((cg >> 1) & 1));
 				const int gid = w * EW + group;
 				const bool live = gid < n;
 				const int node = live ? gid : n - 1;
 				const vec4d pi = ldp(node), vi = ldv(node);
 				const int beg = srow[node], end = live ? srow[node + 1] : beg;
 				// the ring buffer holds records [srow[w*EW], ...): index it with global record numbers
-				const HalfEdge* wave_he = ring + (size_t) (c & 1) * ring_records - srow[w * EW];
+				const HalfEdge* wave_he = ring + (size_t) (cg & 1) * ring_records - srow[w * EW];
 				const Force3 f = node_spring_sum<false, UNI>(wave_he, pal, beg, end, lane, pi, vi, nodes);
 				if (live && lane == 0) {
 					const double inv_m = (end > beg) ? fast_rcp(pi.w) : 0.0;
 					vec4d a;
 					if (B.af == 2) { a.x = 0.0; a.y = 0.0; a.z = 0.0; a.w = 0.0; }
-					else a = acc[node];
+					else a = ldcg4(acc + node);
 					a.x = fma(f.x, inv_m, a.x);
 					a.y = fma(f.y, inv_m, a.y);
 					a.z = fma(f.z, inv_m, a.z);
@@ -170,7 +204,8 @@ __global__ void __launch_bounds__(ET, 1) k_ensemble(const BodyDesc* __restrict__
 		const bool pre = !last && !hb;
 		for (int i = tid; i < n; i += ET) {  // reb_integrator_leapfrog_part2, integrator_leapfrog.c:57-63
 			vec4d p = ldp(i), v = ldv(i);
-			const vec4d a = acc[i];
+			// written by this CTA earlier in this step unless no force term is active (then: by an earlier batch)
+			const vec4d a = (have_springs || grav || B.af == 2) ? acc[i] : ldcg4(acc + i);
 			v.x = __dadd_rn(v.x, __dmul_rn(dt, a.x));
 			v.y = __dadd_rn(v.y, __dmul_rn(dt, a.y));
 			v.z = __dadd_rn(v.z, __dmul_rn(dt, a.z));
@@ -226,6 +261,11 @@ __global__ void __launch_bounds__(ET, 1) k_ensemble(const BodyDesc* __restrict__
 		posm_g[B.node_off + i] = ldp(i);
 		vel_g[B.node_off + i] = ldv(i);
 	}
+	c_base += total_waves;
+	__threadfence();  // state and accelerations of this batch are visible before the member is released
+	__syncthreads();
+	if (tid == 0) atomicExch(done + body, batch + 1);
+	}  // next item
 }
 
 __global__ void k_unpack(const unsigned char* __restrict__ rows, size_t stride, int n, vec4d* __restrict__ posm, vec4d* __restrict__ vel,
@@ -265,11 +305,12 @@ struct ass_ensemble {
 	size_t smem = 0;
 	int ring_records = 0;  // capacity of one ring buffer: the longest run of half-edges of one wave of nodes
 	bool uni_mass = true;  // within every member, all nodes carry the same mass (m_red = m / 2, spring_math.cuh)
+	int* d_queue = nullptr;  // [0] the item counter, [1 .. n_bodies] batches completed per member (k_ensemble)
 };
 
 static void ens_free(ass_ensemble* e) {
 	if (!e) return;
-	cudaFree(e->d_desc); cudaFree(e->posm); cudaFree(e->vel); cudaFree(e->acc); cudaFree(e->row_ptr); cudaFree(e->he); cudaFree(e->pal); cudaFree(e->d_dense);
+	cudaFree(e->d_queue); cudaFree(e->d_desc); cudaFree(e->posm); cudaFree(e->vel); cudaFree(e->acc); cudaFree(e->row_ptr); cudaFree(e->he); cudaFree(e->pal); cudaFree(e->d_dense);
 	if (e->e0) cudaEventDestroy(e->e0);
 	if (e->e1) cudaEventDestroy(e->e1);
 	if (e->stream) cudaStreamDestroy(e->stream);
@@ -434,10 +475,22 @@ extern "C" int ass_ensemble_step(ass_ensemble* e, int nsteps, int with_heartbeat
 	if (device_ms) *device_ms = 0.0;
 	if (nsteps == 0) return ASS_OK;
 	if (device_ms) CU_TRY(cudaEventRecord(e->e0, e->stream));
+	// persistent CTAs pulling (member, batch of steps) items; one batch when the members fit the machine in one round
+	const int grid = std::min(e->n_bodies, ass_sm_count());
+	// Items cost ~0.6 % per batch boundary per 10 steps (state through global memory, ring drain): cut the run into
+	// batches only when whole-run items would leave the last round of members badly filled.
+	int item_steps = nsteps;
+	const int rounds = (e->n_bodies + grid - 1) / grid;
+	if ((double) e->n_bodies / ((double) rounds * grid) < 0.95) item_steps = std::max(1, std::min(nsteps, std::max(5, std::min(25, (nsteps + 7) / 8))));
+	if (const char* env = getenv("ASS_ENS_ITEM_STEPS")) item_steps = std::max(1, std::min(nsteps, atoi(env)));
+	if (!e->d_queue) CU_TRY(cudaMalloc(&e->d_queue, sizeof(int) * ((size_t) e->n_bodies + 1)));
+	CU_TRY(cudaMemsetAsync(e->d_queue, 0, sizeof(int) * ((size_t) e->n_bodies + 1), e->stream));
 	if (e->uni_mass)
-		k_ensemble<true><<<e->n_bodies, ET, e->smem, e->stream>>>(e->d_desc, e->posm, e->vel, e->acc, e->row_ptr, e->he, e->pal, nsteps, with_heartbeat, e->max_n, e->ring_records);
+		k_ensemble<true><<<grid, ET, e->smem, e->stream>>>(e->d_desc, e->posm, e->vel, e->acc, e->row_ptr, e->he, e->pal, nsteps, with_heartbeat, e->max_n,
+				e->ring_records, e->n_bodies, item_steps, e->d_queue, e->d_queue + 1);
 	else
-		k_ensemble<false><<<e->n_bodies, ET, e->smem, e->stream>>>(e->d_desc, e->posm, e->vel, e->acc, e->row_ptr, e->he, e->pal, nsteps, with_heartbeat, e->max_n, e->ring_records);
+		k_ensemble<false><<<grid, ET, e->smem, e->stream>>>(e->d_desc, e->posm, e->vel, e->acc, e->row_ptr, e->he, e->pal, nsteps, with_heartbeat, e->max_n,
+				e->ring_records, e->n_bodies, item_steps, e->d_queue, e->d_queue + 1);
 	LAUNCH_CHECK();
 	for (auto& p : e->prm)
 		for (int s = 0; s < nsteps; s++) {  // the reference's own rounding of t (integrator_leapfrog.c:50,65)

@@ -33,7 +33,15 @@ def make_body(gpu, d, seed, omega, k=0.08, gamma=5.0):
     return p, sp
 
 
-def test_ensemble_matches_single_body_path(gpu, oracle):
+@pytest.mark.parametrize("item_steps", [None, "1", "3"])
+def test_ensemble_matches_single_body_path(gpu, oracle, monkeypatch, item_steps):
+    """item_steps: how many consecutive steps of a member one work item covers (k_ensemble's persistent CTAs pull
+    (member, batch) items; None = the library's choice).  A member's state crosses global memory between batches,
+    possibly from one SM to another: the result must not depend on it."""
+    if item_steps is None:
+        monkeypatch.delenv("ASS_ENS_ITEM_STEPS", raising=False)
+    else:
+        monkeypatch.setenv("ASS_ENS_ITEM_STEPS", item_steps)
     bodies, springs, params = [], [], []
     for b, (d, seed, wz, k) in enumerate([(0.15, 12345, 0.2, 0.08), (0.2, 7, 0.5, 0.02), (0.15, 99, 0.9, 0.16), (0.12, 5, 0.1, 0.04)]):
         p, sp = make_body(gpu, d, seed, (0.0, 0.0, wz), k=k)
@@ -60,7 +68,12 @@ def test_ensemble_matches_single_body_path(gpu, oracle):
         assert np.allclose(got[b][:, :6], ref[:, :6], rtol=0, atol=1e-13)
 
 
-def test_ensemble_gravity_heartbeat_and_accumulating_modes(gpu, oracle):
+@pytest.mark.parametrize("item_steps", [None, "2"])
+def test_ensemble_gravity_heartbeat_and_accumulating_modes(gpu, oracle, monkeypatch, item_steps):
+    if item_steps is None:
+        monkeypatch.delenv("ASS_ENS_ITEM_STEPS", raising=False)
+    else:
+        monkeypatch.setenv("ASS_ENS_ITEM_STEPS", item_steps)
     p, sp = make_body(gpu, 0.15, 12345, (0.1, 0.0, 0.2))
     cases = [dict(dt=2e-3, gravity=1, additional_forces=1, heartbeat=1, softening=1.5e-3),
              dict(dt=1e-3, gravity=0, additional_forces=1, heartbeat=0),      # accelerations accumulate
@@ -183,3 +196,19 @@ def test_ipc_two_ranks(gpu, tmp_path):
                         "--master-port", "29541", str(script)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:]
     assert r.stdout.count("ok") >= 2, r.stdout[-3000:]   # both ranks print "rank <r> ok" (their lines may interleave)
+
+
+def test_ensemble_more_members_than_sms(gpu):
+    """More members than SMs: items of ten steps keep every SM busy; members must still come out identical to the same
+    member stepped alone (here: 200 copies of one body => every copy bit-identical to copy 0, and to a 1-member run)."""
+    p, sp = make_body(gpu, 0.2, 3, (0.0, 0.0, 0.3))
+    prm = dict(dt=1e-2, gravity=0, additional_forces=2, heartbeat=0)
+    with gpu.Ensemble([p], [sp], [prm]) as e:
+        e.step(23)
+        want = e.download()[0]
+    nb = 200
+    with gpu.Ensemble([p] * nb, [sp] * nb, [prm] * nb) as e:
+        e.step(23)
+        got = e.download()
+    for b in range(nb):
+        assert same_bits(got[b][:, :10], want[:, :10]), b
