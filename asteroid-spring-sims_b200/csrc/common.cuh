@@ -35,7 +35,12 @@ static_assert(sizeof(HalfEdge) == 16, "HalfEdge must be 16 bytes");
 static_assert(sizeof(ass_spring) == 32, "ass_spring must match struct spring (32 B)");
 
 #define ASS_L_EPS 1e-6  // src_spring/springs.cpp:28
-#define ASS_SPRING_WAVE 64  // ranks per wave of the streaming spring kernel (springs.cu)
+#ifndef ASS_SPRING_LANES
+#define ASS_SPRING_LANES 4
+#endif
+constexpr int SPRING_LANES = ASS_SPRING_LANES;  // lanes cooperating on one node's half-edge list (2, 4 or 8)
+static_assert(SPRING_LANES == 2 || SPRING_LANES == 4 || SPRING_LANES == 8, "SPRING_LANES must be 2, 4 or 8");
+#define ASS_SORT_BLOCK 256  // ranks per block inside which nodes are dealt to lane groups by degree (ass_sim::grp)
 
 // ---------------------------------------------------------------------------------------------------
 // error plumbing
@@ -81,6 +86,11 @@ struct ShardInfo {
 	bool active = false;
 };
 
+// rank-ordered node state as the spring kernels gather it (see ass_sim::mir)
+struct SpringMirror {
+	double2 *xy = nullptr, *zv = nullptr, *vxy = nullptr;  // (x, y), (z, vz), (vx, vy)
+};
+
 struct ass_sim {
 	int n = 0, cap = 0;     // particles
 	int ns = 0;             // springs
@@ -103,29 +113,39 @@ struct ass_sim {
 
 	// springs: CSR over nodes in SPATIAL order.  ass_set_springs ranks the nodes along a Morton curve through their
 	// positions (a solid body: neighbours stay neighbours); row k belongs to node order[k], HalfEdge::nbr is the
-	// neighbour's rank, and ps / vs mirror posm / vel in rank order.  The spring kernel streams rows in rank order and
-	// gathers endpoint state from ps / vs, so the lanes of one request touch a handful of adjacent cache lines instead
-	// of 32 random ones (the generators emit nodes in random order).  Everything else keeps the caller's node order.
-	HalfEdge* he = nullptr;
+	// neighbour's rank, and the mirror (below) holds positions / velocities in rank order.  The spring kernels walk rows
+	// in rank order and gather endpoint state from the mirror, so the lanes of one request touch a handful of adjacent
+	// cache lines instead of 32 random ones (the generators emit nodes in random order).  Everything else keeps the
+	// caller's node order.
+	HalfEdge* he = nullptr;   // CSR copy (rows by rank, each row sorted by neighbour rank): diagnostics, node-slab kernel
 	int* row_ptr = nullptr;   // n+1, by rank
-	int* slot = nullptr;      // 2*ns: half-edge slot of (spring s, endpoint e)
+	int* slot = nullptr;      // 2*ns: position in he of (spring s, endpoint e)
 	int* order = nullptr;     // rank -> node
 	int* rank = nullptr;      // node -> rank
-	vec4d *ps = nullptr, *vs = nullptr, *ps_alt = nullptr, *vs_alt = nullptr;
+	// The rank-ordered mirror of posm / vel, as three arrays of 16-byte pairs -- (x, y), (z, vz), (vx, vy) -- plus the
+	// masses.  A random gather of 32-byte {x,y,z,m} entries can start on only four of the eight 16-byte bank groups of
+	// the L1 data array and is processed in two passes (measured: 22 data wavefronts per warp-wide 256-bit gather);
+	// 16-byte entries use all eight groups, and the endpoint costs 48 bytes instead of 64.
+	SpringMirror mir, mir_alt;  // mir_alt: written by the fused kick (a node may not move while neighbours still read it)
+	double2* mir_block = nullptr;  // the one allocation behind mir and mir_alt
+	double* mir_m = nullptr;
 	size_t sorted_cap = 0;
-	// the streaming spring kernel takes ranks in waves of ASS_SPRING_WAVE: wave_off[w] = row_ptr[w * ASS_SPRING_WAVE]
-	// (n_waves + 1 entries), wave_he_max = the largest number of half-edge records any wave owns.  row_ptr and order are
-	// padded so every wave can be copied whole (row_ptr: (n_waves * WAVE + 4) entries, padding = n_he; order: n_waves * WAVE)
-	int* wave_off = nullptr;
-	int n_waves = 0, wave_he_max = 0;
-	size_t wave_cap = 0;
-	std::vector<int> h_wave_off;  // host copy of wave_off
-	// which waves each CTA of the streaming kernel takes: cta_wave[c] .. cta_wave[c+1] (springs.cu: ensure_cta_waves)
-	int* cta_wave = nullptr;
-	size_t cta_wave_cap = 0;
-	int cta_wave_grid = 0;
-	long long cta_wave_epoch = -1;
+	// The lane-transposed copy of the half-edge list, read by the whole-body spring kernel (springs.cu: k_spring_lanes).
+	// Groups of SPRING_LANES lanes own one node; 32 / SPRING_LANES groups make a warp; within blocks of ASS_SORT_BLOCK
+	// ranks the nodes are dealt to groups in order of decreasing degree, so the groups of a warp have rows of similar
+	// length.  grp[g] = (rank, degree) of group g, (-1, 0) for padding groups.  Warp w owns records
+	// [warp_off[w], warp_off[w+1]): step t of lane l is record warp_off[w] + 32 t + l, so a warp reads 512 contiguous
+	// bytes per step; lane l of a group takes entries l, l + SPRING_LANES, ... of its node's row; rows are padded (with
+	// records that are loaded but never accumulated) to the warp's longest, rounded up to an even number of steps.
+	HalfEdge* heT = nullptr;
+	int* slotT = nullptr;     // 2*ns: position in heT of (spring s, endpoint e)
+	int2* grp = nullptr;
+	int* warp_off = nullptr;  // n_swarps + 1
+	int n_swarps = 0;
+	size_t heT_cap = 0, grp_cap = 0, swarp_cap = 0;
+	long long n_heT = 0;
 	double2* pal = nullptr;   // palette of distinct (k, gamma) pairs
+	double2* palf = nullptr;  // the same entries as the force kernels want them: (-k, -max(gamma, 0)); lives behind pal
 	int n_pal = 0;
 	size_t he_cap = 0, row_cap = 0, pal_cap = 0;
 	int max_degree = 0;
@@ -160,6 +180,14 @@ int ass_launch_gravity_sym_pair(ass_sim* s, int rlo, int rhi, int slo, int shi, 
 int ass_buf_reserve(DevBuf& b, size_t bytes);
 // order[k] = node of rank k along a Morton curve through pos[0..n) (state.cu); deterministic, ties keep node order
 void ass_morton_order(const vec4d* pos, size_t n, std::vector<int>& order);
+// everything the spring kernels read, built on the host (state.cu); the fields mirror ass_sim's
+struct SpringLayout {
+	std::vector<int> order, rank, row, slot, slotT, warp_off;
+	std::vector<HalfEdge> he, heT;
+	std::vector<int2> grp;
+	int max_degree = 0;
+};
+int ass_build_spring_layout(const vec4d* pos, int n, const ass_spring* sp, int ns, const int* pidx, SpringLayout& out, int* bad_spring);
 int ass_ensure_device(void);
 int ass_sm_count(void);
 
@@ -181,7 +209,7 @@ void ass_toc(ass_sim* s, int klass);
 // internal launchers (one per .cu file)
 // ---------------------------------------------------------------------------------------------------
 // springs.cu
-// mirror_fresh: ps / vs already mirror posm / vel (the caller just produced them); otherwise they are re-gathered first
+// mirror_fresh: the mirror already holds posm / vel (the caller just produced them); otherwise they are re-gathered first
 int ass_launch_spring_forces(ass_sim* s, bool zero_first, bool mirror_fresh);
 int ass_launch_spring_forces_range(ass_sim* s, bool zero_first, int lo, int hi);
 int ass_launch_spring_kick_drift(ass_sim* s, bool zero_first, double dt, bool pre_drift_next, bool mirror_fresh);
@@ -192,7 +220,7 @@ int ass_launch_gravity_partial(ass_sim* s, const vec4d* src, int s_lo, int s_hi,
 int ass_launch_gravity_reduce(ass_sim* s, int t_lo, int t_hi, int rows, bool add = false);
 // leapfrog.cu
 int ass_launch_part1(ass_sim* s, double dt);
-int ass_launch_part1_mirrored(ass_sim* s, double dt);  // part1 that also refreshes the rank-ordered mirror ps / vs
+int ass_launch_part1_mirrored(ass_sim* s, double dt);  // part1 that also refreshes the rank-ordered mirror
 int ass_launch_part2(ass_sim* s, double dt);
 int ass_launch_part1_range(ass_sim* s, double dt, int lo, int hi);
 int ass_launch_part2_range(ass_sim* s, double dt, bool pre_drift_next, int lo, int hi);

@@ -2,15 +2,15 @@
 //
 // The members never interact, so there is nothing to exchange: one CTA owns one body for a whole batch of steps
 // ("body in shared memory, springs streamed").
-//   * node positions and velocities (64 B/node, 68 KB for 1065 nodes) and the CSR row offsets live in shared memory for
-//     the whole batch; accelerations go through global memory (written once, read once per step, L2-resident);
-//   * the half-edge records (2 x 16 B per spring, ~445 KB per body) are streamed every step by the bulk-copy engine
-//     (cp.async.bulk -> mbarrier, SASS UBLKCP): nodes are processed in waves of 64 (one node per 8-lane group), the
-//     records of a wave are one contiguous run of the node-sorted array, and the run of wave w+2 is in flight while wave
-//     w is being evaluated (two-deep ring).  So inside the spring phase every operand comes from shared memory and the
-//     dependent chain "row offset -> record -> endpoint gather" costs shared-memory latencies, not HBM ones;
-//   * per step:  part1 | [gravity: all pairs out of shared memory] | springs (same arithmetic and lane order as springs.cu,
-//     so a member gets the bits the single-body path would give it) | kick + drift (+ next part1) | [center_sim].
+//   * node positions and velocities (56 B/node: three arrays of 16-byte pairs + the mass) live in shared memory for the
+//     whole batch, in the member's spatial RANK order -- the same ranking, rows and lane-transposed half-edge records
+//     (state.cu: ass_build_spring_layout) as the single-body path, so a member sums in the same order and gets the same
+//     bits; accelerations go through global memory (written once, read once per step, L2-resident);
+//   * the half-edge records (2 x 16 B per spring, ~470 KB per body with padding) are read every step straight from L2
+//     by the warps that need them, 512 contiguous bytes per warp and step, one pair of steps ahead of the arithmetic
+//     (spring_math.cuh: lane_spring_sum) -- nothing is staged and the spring phase has no CTA-wide barrier inside it;
+//   * per step:  part1 | [gravity: all pairs out of shared memory] | springs | kick + drift (+ next part1) | [center_sim].
+// The C-ABI keeps the caller's node order: upload and download go through the permutation `perm`.
 // Across GPUs the members are dealt round-robin by the host launcher; no collective is involved.
 #include <stdlib.h>
 #include <string.h>
@@ -25,15 +25,16 @@
 namespace {
 
 #ifndef ASS_ENS_THREADS
-#define ASS_ENS_THREADS 1024
+#define ASS_ENS_THREADS 512
 #endif
-constexpr int ET = ASS_ENS_THREADS;            // threads per CTA: one body owns a whole SM
-constexpr int EW = ET / SPRING_LANES;          // nodes per wave (128)
+constexpr int ET = ASS_ENS_THREADS;  // threads per CTA: one body owns a whole SM (16 warps x 128 registers)
+constexpr int GPW = 32 / SPRING_LANES;  // nodes per warp
 
 struct BodyDesc {
-	int node_off, n, row_off, n_perts;
+	int node_off, n, grp_off, swarp_off;  // first node / lane group / warp-offset entry of the member in the concatenated arrays
+	int n_swarps, n_perts, gravity, af;
 	double dt, negG, soft2;
-	int gravity, af, heartbeat, pad;
+	int heartbeat, pad;
 };
 
 // A member's state and accelerations may have been written by another SM earlier in the same launch (the previous batch
@@ -45,43 +46,39 @@ __device__ __forceinline__ vec4d ldcg4(const vec4d* p) {
 	return r;
 }
 
-// endpoint state out of shared memory (see the layout note in k_ensemble): three 16-byte reads per endpoint, plus the
-// mass only when the member's masses differ (with equal masses the arithmetic never looks at the neighbour's)
-template <bool UNI>
+// endpoint state out of shared memory: three 16-byte reads per endpoint, plus the mass only when the member's masses
+// differ (with equal masses the arithmetic never looks at the neighbour's).  16-byte entries start on all eight bank
+// groups; a random gather of 32-byte entries would start on only four (8-way conflicts).
 struct SharedNodes {
 	const double2 *xy, *zv, *vxy;
 	const double* m;
-	__device__ __forceinline__ void get(int i, vec4d& p, vec4d& v) const {
-		const double2 a = xy[i], b = zv[i], c = vxy[i];
-		p.x = a.x; p.y = a.y; p.z = b.x; p.w = UNI ? 0.0 : m[i];
-		v.x = c.x; v.y = c.y; v.z = b.y; v.w = 0.0;
+	template <bool UNI>
+	__device__ __forceinline__ NodeState get(int i) const {
+		NodeState s;
+		s.xy = xy[i]; s.zv = zv[i]; s.vxy = vxy[i];
+		s.m = UNI ? 0.0 : m[i];
+		return s;
 	}
 };
 
 // Work is handed out in ITEMS = (member b, batch j of `item_steps` consecutive steps), numbered j * n_bodies + b and
 // pulled from one atomic counter by persistent CTAs (one per SM).  With one CTA per member for the whole run, 512
 // members on 148 SMs take 4 rounds of which the last is half empty (86 % at BASELINE C5 on 8 GPUs); with items the
-// machine stays full and a member costs one extra 2 x 68 KB trip of its state through global memory per batch.
+// machine stays full and a member costs one extra trip of its state through global memory per batch.
 // done[b] = number of batches of member b that are complete: an item waits (briefly, and only near a batch boundary)
 // until its predecessor has published the member's state.
-template <bool UNI>
+// All per-node arrays (posm_g, vel_g, acc_g, ord) are in the member's rank order.
+template <bool UNI, bool PAL1>
 __global__ void __launch_bounds__(ET, 1) k_ensemble(const BodyDesc* __restrict__ desc, vec4d* __restrict__ posm_g, vec4d* __restrict__ vel_g,
-		vec4d* __restrict__ acc_g, const int* __restrict__ row_ptr, const HalfEdge* __restrict__ he, const double2* __restrict__ pal, int nsteps_total,
-		int with_hb, int max_n, int ring_records, int n_bodies, int item_steps, int* __restrict__ queue, int* __restrict__ done) {
+		vec4d* __restrict__ acc_g, const int* __restrict__ ord, const int2* __restrict__ grp, const int* __restrict__ warp_off,
+		const HalfEdge* __restrict__ heT, const double2* __restrict__ palf, int nsteps_total, int with_hb, int max_n, int n_bodies, int item_steps,
+		int* __restrict__ queue, int* __restrict__ done) {
 	extern __shared__ __align__(128) unsigned char smem_raw[];
 	__shared__ double red[ET / 32][4];
 	__shared__ double com[4];
-	__shared__ __align__(8) uint64_t full[2];
 	__shared__ int s_item;
 	const int tid = threadIdx.x;
-	if (tid == 0) {
-		mbar_init(&full[0], 1);
-		mbar_init(&full[1], 1);
-		mbar_fence_init();
-	}
-	__syncthreads();
 	const int n_batches = (nsteps_total + item_steps - 1) / item_steps;
-	int c_base = 0;  // waves this CTA has streamed so far: ring slot and mbarrier parity carry across items
 	while (true) {
 	if (tid == 0) s_item = atomicAdd(queue, 1);
 	__syncthreads();
@@ -97,48 +94,29 @@ __global__ void __launch_bounds__(ET, 1) k_ensemble(const BodyDesc* __restrict__
 	__syncthreads();
 	const BodyDesc B = desc[body];
 	const int n = B.n;
-	// carve: ring[2][ring_records] | xy | zv | vxy (16-byte entries) | m (8-byte) | srow[max_n + 1]
-	// Node state is kept as arrays of 16-byte pairs -- (x, y), (z, vz), (vx, vy) -- rather than 32-byte vectors: a random
-	// gather of 32-byte entries starts on only four distinct bank groups (8-way conflicts); 16-byte entries start on
-	// eight and tile all 32 banks.  Three reads per endpoint instead of four: the shared-memory pipe is what bounds this
-	// kernel.  The mass has its own array.
-	HalfEdge* ring = (HalfEdge*) smem_raw;
-	double2* s_xy = (double2*) (ring + 2 * (size_t) ring_records);
+	// carve: xy | zv | vxy (16-byte entries) | m (8-byte), each max_n long
+	double2* s_xy = (double2*) smem_raw;
 	double2* s_zv = s_xy + max_n;
 	double2* s_vxy = s_zv + max_n;
 	double* s_m = (double*) (s_vxy + max_n);
-	int* srow = (int*) (s_m + max_n + (max_n & 1));
 	vec4d* acc = acc_g + B.node_off;
 	auto ldp = [&](int i) { const double2 a = s_xy[i]; vec4d p; p.x = a.x; p.y = a.y; p.z = s_zv[i].x; p.w = s_m[i]; return p; };
 	auto ldv = [&](int i) { const double2 a = s_vxy[i]; vec4d v; v.x = a.x; v.y = a.y; v.z = s_zv[i].y; v.w = 0.0; return v; };
 	auto stp = [&](int i, const vec4d p) { s_xy[i] = make_double2(p.x, p.y); s_zv[i].x = p.z; s_m[i] = p.w; };
 	auto stv = [&](int i, const vec4d v) { s_vxy[i] = make_double2(v.x, v.y); s_zv[i].y = v.z; };
-	const SharedNodes<UNI> nodes{ s_xy, s_zv, s_vxy, s_m };
+	const SharedNodes nodes{ s_xy, s_zv, s_vxy, s_m };
 	for (int i = tid; i < n; i += ET) {
 		stp(i, ldcg4(posm_g + B.node_off + i));
 		stv(i, ldcg4(vel_g + B.node_off + i));
 	}
-	for (int i = tid; i <= n; i += ET) srow[i] = row_ptr[B.row_off + i];
 	__syncthreads();
 	const double dt = B.dt, h = __dmul_rn(0.5, dt);
 	const bool hb = with_hb && B.heartbeat == 1;
-	const bool have_springs = B.af != 0 && srow[n] > srow[0];
+	const bool have_springs = B.af != 0 && warp_off[B.swarp_off + B.n_swarps] > warp_off[B.swarp_off];
 	const bool grav = B.gravity == 1 && B.af != 2;
-	const int lane = tid & (SPRING_LANES - 1), group = tid / SPRING_LANES;
-	const int nw = (n + EW - 1) / EW;
-	const int total_waves = have_springs ? nsteps * nw : 0;
-	// records of wave c (counted over all steps of the item) -> ring buffer (c_base + c) & 1
-	auto issue = [&](int c) {  // thread 0 only
-		const int w = c % nw, slot = (c_base + c) & 1;
-		const int e0 = srow[w * EW], e1 = srow[min(n, (w + 1) * EW)];
-		const uint32_t bytes = (uint32_t) (e1 - e0) * (uint32_t) sizeof(HalfEdge);
-		mbar_expect_tx(&full[slot], bytes);
-		if (bytes) bulk_g2s(ring + (size_t) slot * ring_records, he + e0, bytes, &full[slot]);
-	};
-	if (tid == 0) {
-		if (total_waves > 0) issue(0);
-		if (total_waves > 1) issue(1);
-	}
+	const int lane = tid & 31, warp = tid >> 5;
+	double2 nkg1 = make_double2(0.0, 0.0);
+	if (PAL1) nkg1 = __ldg(palf);
 	bool predrifted = false;
 	for (int step = 0; step < nsteps; step++) {
 		const bool last = step == nsteps - 1;
@@ -171,31 +149,28 @@ __global__ void __launch_bounds__(ET, 1) k_ensemble(const BodyDesc* __restrict__
 			}
 			__syncthreads();  // also orders the global acc writes before the spring phase's reads (same CTA)
 		}
-		if (have_springs) {  // spring_forces (+ zero_accel when af == 2), one wave of 64 nodes at a time
-			for (int w = 0; w < nw; w++) {
-				const int c = step * nw + w, cg = c_base + c;
-				mbar_wait(&full[cg & 1], (uint32_t) ((cg >> 1) & 1));
-				const int gid = w * EW + group;
-				const bool live = gid < n;
-				const int node = live ? gid : n - 1;
-				const vec4d pi = ldp(node), vi = ldv(node);
-				const int beg = srow[node], end = live ? srow[node + 1] : beg;
-				// the ring buffer holds records [srow[w*EW], ...): index it with global record numbers
-				const HalfEdge* wave_he = ring + (size_t) (cg & 1) * ring_records - srow[w * EW];
-				const Force3 f = node_spring_sum<false, UNI>(wave_he, pal, beg, end, lane, pi, vi, nodes);
-				if (live && lane == 0) {
-					const double inv_m = (end > beg) ? fast_rcp(pi.w) : 0.0;
+		if (have_springs) {  // spring_forces (+ zero_accel when af == 2): every warp takes every (ET / 32)-th slice of 32 / SPRING_LANES nodes
+			for (int sw = warp; sw < B.n_swarps; sw += ET / 32) {
+				const int2 gi = __ldg(grp + B.grp_off + sw * GPW + lane / SPRING_LANES);  // (rank, degree); (-1, 0): padding group
+				const int off = __ldg(warp_off + B.swarp_off + sw);
+				const int P = (__ldg(warp_off + B.swarp_off + sw + 1) - off) >> 6;
+				const bool live = gi.x >= 0;
+				const int k = live ? gi.x : 0;
+				const int nt = (gi.y - (lane & (SPRING_LANES - 1)) + SPRING_LANES - 1) / SPRING_LANES;
+				const NodeState ni = nodes.get<false>(k);
+				const Force3 f = lane_spring_sum<UNI, PAL1, false>((const int4*) heT + off + lane, P, nt, ni, nodes, palf, nkg1);
+				if (live && (lane & (SPRING_LANES - 1)) == 0) {
+					const double inv_m = (gi.y > 0) ? fast_rcp(ni.m) : 0.0;
 					vec4d a;
 					if (B.af == 2) { a.x = 0.0; a.y = 0.0; a.z = 0.0; a.w = 0.0; }
-					else a = ldcg4(acc + node);
+					else a = ldcg4(acc + k);
 					a.x = fma(f.x, inv_m, a.x);
 					a.y = fma(f.y, inv_m, a.y);
 					a.z = fma(f.z, inv_m, a.z);
-					acc[node] = a;
+					acc[k] = a;
 				}
-				__syncthreads();  // everyone is done with ring buffer c & 1 (and, after the last wave, with sp / sv)
-				if (tid == 0 && c + 2 < total_waves) issue(c + 2);
 			}
+			__syncthreads();  // nobody reads positions any more: the kick may move them
 		} else {
 			if (B.af == 2)
 				for (int i = tid; i < n; i += ET) { vec4d z; z.x = 0; z.y = 0; z.z = 0; z.w = 0; acc[i] = z; }
@@ -223,9 +198,10 @@ __global__ void __launch_bounds__(ET, 1) k_ensemble(const BodyDesc* __restrict__
 		predrifted = pre;
 		__syncthreads();
 		if (hb) {  // center_sim(0, n - n_perts): CoM of the resolved body, shift everything (physics.cpp:98-109)
-			const int hi = n - B.n_perts;
+			const int hi = n - B.n_perts;  // in the caller's numbering: ord[] maps a rank back to it
 			double v[4] = { 0.0, 0.0, 0.0, 0.0 };
-			for (int i = tid; i < hi; i += ET) {
+			for (int i = tid; i < n; i += ET) {
+				if (B.n_perts > 0 && __ldg(ord + B.node_off + i) >= hi) continue;
 				const vec4d p = ldp(i);
 				v[0] += p.w * p.x; v[1] += p.w * p.y; v[2] += p.w * p.z; v[3] += p.w;
 			}
@@ -261,15 +237,15 @@ __global__ void __launch_bounds__(ET, 1) k_ensemble(const BodyDesc* __restrict__
 		posm_g[B.node_off + i] = ldp(i);
 		vel_g[B.node_off + i] = ldv(i);
 	}
-	c_base += total_waves;
 	__threadfence();  // state and accelerations of this batch are visible before the member is released
 	__syncthreads();
 	if (tid == 0) atomicExch(done + body, batch + 1);
 	}  // next item
 }
 
-__global__ void k_unpack(const unsigned char* __restrict__ rows, size_t stride, int n, vec4d* __restrict__ posm, vec4d* __restrict__ vel,
-		vec4d* __restrict__ acc) {
+// rows in the caller's node order <-> device arrays in rank order: perm[i] = device index of the caller's node i
+__global__ void k_unpack(const unsigned char* __restrict__ rows, size_t stride, int n, const int* __restrict__ perm, vec4d* __restrict__ posm,
+		vec4d* __restrict__ vel, vec4d* __restrict__ acc) {
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) return;
 	const double* r = (const double*) (rows + (size_t) i * stride);
@@ -277,13 +253,16 @@ __global__ void k_unpack(const unsigned char* __restrict__ rows, size_t stride, 
 	p.x = r[0]; p.y = r[1]; p.z = r[2]; p.w = r[9];
 	v.x = r[3]; v.y = r[4]; v.z = r[5]; v.w = 0.0;
 	a.x = r[6]; a.y = r[7]; a.z = r[8]; a.w = 0.0;
-	posm[i] = p; vel[i] = v; acc[i] = a;
+	const int k = perm[i];
+	posm[k] = p; vel[k] = v; acc[k] = a;
 }
-__global__ void k_pack(double* __restrict__ dense, int n, const vec4d* __restrict__ posm, const vec4d* __restrict__ vel, const vec4d* __restrict__ acc) {
+__global__ void k_pack(double* __restrict__ dense, int n, const int* __restrict__ perm, const vec4d* __restrict__ posm, const vec4d* __restrict__ vel,
+		const vec4d* __restrict__ acc) {
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) return;
 	double* r = dense + (size_t) i * 10;
-	const vec4d p = posm[i], v = vel[i], a = acc[i];
+	const int k = perm[i];
+	const vec4d p = posm[k], v = vel[k], a = acc[k];
 	r[0] = p.x; r[1] = p.y; r[2] = p.z; r[3] = v.x; r[4] = v.y; r[5] = v.z; r[6] = a.x; r[7] = a.y; r[8] = a.z; r[9] = p.w;
 }
 
@@ -295,22 +274,26 @@ struct ass_ensemble {
 	std::vector<ass_params> prm;
 	std::vector<BodyDesc> desc;
 	BodyDesc* d_desc = nullptr;
-	vec4d *posm = nullptr, *vel = nullptr, *acc = nullptr;
-	int* row_ptr = nullptr;
-	HalfEdge* he = nullptr;
-	double2* pal = nullptr;  // distinct (k, gamma) pairs over all members
+	vec4d *posm = nullptr, *vel = nullptr, *acc = nullptr;  // rank order within each member
+	int* perm = nullptr;      // caller's global node index -> device index (node_off + rank)
+	int* ord = nullptr;       // device index -> caller's node index inside its member
+	int2* grp = nullptr;      // lane groups of all members (common.cuh: ass_sim::grp), ranks local to the member
+	int* warp_off = nullptr;  // per member n_swarps + 1 offsets into heT
+	HalfEdge* heT = nullptr;  // lane-transposed records of all members; nbr = rank inside the member
+	double2* palf = nullptr;  // distinct (-k, -max(gamma, 0)) pairs over all members
 	double* d_dense = nullptr;
 	cudaStream_t stream = nullptr;
 	cudaEvent_t e0 = nullptr, e1 = nullptr;
 	size_t smem = 0;
-	int ring_records = 0;  // capacity of one ring buffer: the longest run of half-edges of one wave of nodes
+	bool pal1 = false;     // every spring of the ensemble has the same (k, gamma): the palette travels in registers
 	bool uni_mass = true;  // within every member, all nodes carry the same mass (m_red = m / 2, spring_math.cuh)
 	int* d_queue = nullptr;  // [0] the item counter, [1 .. n_bodies] batches completed per member (k_ensemble)
 };
 
 static void ens_free(ass_ensemble* e) {
 	if (!e) return;
-	cudaFree(e->d_queue); cudaFree(e->d_desc); cudaFree(e->posm); cudaFree(e->vel); cudaFree(e->acc); cudaFree(e->row_ptr); cudaFree(e->he); cudaFree(e->pal); cudaFree(e->d_dense);
+	cudaFree(e->d_queue); cudaFree(e->d_desc); cudaFree(e->posm); cudaFree(e->vel); cudaFree(e->acc); cudaFree(e->perm); cudaFree(e->ord);
+	cudaFree(e->grp); cudaFree(e->warp_off); cudaFree(e->heT); cudaFree(e->palf); cudaFree(e->d_dense);
 	if (e->e0) cudaEventDestroy(e->e0);
 	if (e->e1) cudaEventDestroy(e->e1);
 	if (e->stream) cudaStreamDestroy(e->stream);
@@ -323,7 +306,7 @@ static void fill_desc(ass_ensemble* e) {
 		BodyDesc& d = e->desc[b];
 		const ass_params& p = e->prm[b];
 		d.n_perts = p.n_perts; d.dt = p.dt; d.negG = -p.G; d.soft2 = p.softening * p.softening;
-		d.gravity = p.gravity; d.af = p.additional_forces; d.heartbeat = p.heartbeat; d.pad = 0;
+		d.gravity = p.gravity; d.af = p.additional_forces; d.heartbeat = p.heartbeat;
 	}
 }
 
@@ -343,23 +326,25 @@ extern "C" int ass_ensemble_create(ass_ensemble** out, int n_bodies, const int* 
 	e->total_nodes = total_nodes;
 	e->prm.assign(params, params + n_bodies);
 	e->desc.resize(n_bodies);
-	// CSR per body: row entries are offsets into the concatenated half-edge array; indices stay local to the body
-	std::vector<int> row((size_t) total_nodes + n_bodies, 0);
-	std::vector<HalfEdge> he((size_t) 2 * total_springs);
-	// palette of distinct (k, gamma) bit patterns over the whole ensemble (a sweep has a handful)
-	std::vector<double2> pal;
+	// per member: the single-body path's spring layout (state.cu), concatenated; ranks stay local to the member
+	std::vector<int> perm((size_t) std::max(total_nodes, 0)), ord((size_t) std::max(total_nodes, 0));
+	std::vector<int2> grp;
+	std::vector<int> warp_off;
+	std::vector<HalfEdge> heT;
+	// palette of distinct (k, gamma) bit patterns over the whole ensemble (a sweep has a handful), stored as the force
+	// kernels want it (spring_math.cuh)
+	std::vector<double2> palf;
 	std::unordered_map<std::string, int> seen;
 	auto pal_index = [&](const ass_spring& v) {
 		std::string key((const char*) &v.k, 8);
 		key.append((const char*) &v.gamma, 8);
 		auto it = seen.find(key);
 		if (it == seen.end()) {
-			it = seen.emplace(key, (int) pal.size()).first;
-			pal.push_back(make_double2(v.k, v.gamma));
+			it = seen.emplace(key, (int) palf.size()).first;
+			palf.push_back(make_double2(-v.k, v.gamma > 0.0 ? -v.gamma : -0.0));
 		}
 		return it->second;
 	};
-	size_t he_base = 0;
 	for (int b = 0; b < n_bodies; b++) {
 		const int n = node_off[b + 1] - node_off[b], ns = spring_off[b + 1] - spring_off[b];
 		if (n <= 0 || ns < 0) { ens_free(e); ass_set_error("ass_ensemble_create: body %d is empty or offsets decrease", b); return ASS_EINVAL; }
@@ -368,57 +353,49 @@ extern "C" int ass_ensemble_create(ass_ensemble** out, int n_bodies, const int* 
 			ens_free(e); ass_set_error("ass_ensemble_create: bad params for body %d", b); return ASS_EINVAL;
 		}
 		e->max_n = std::max(e->max_n, n);
-		BodyDesc& d = e->desc[b];
-		d.node_off = node_off[b]; d.n = n; d.row_off = node_off[b] + b;
-		int* r = row.data() + d.row_off;  // n + 1 entries
 		const ass_spring* sp = springs + spring_off[b];
-		std::vector<int> deg((size_t) n + 1, 0);
-		for (int q = 0; q < ns; q++) {
-			const int i = sp[q].particle_1, j = sp[q].particle_2;
-			if (i < 0 || j < 0 || i >= n || j >= n || i == j) {
-				ens_free(e);
-				ass_set_error("ass_ensemble_create: body %d spring %d joins (%d,%d): indices are local to the body and must differ", b, q, i, j);
-				return ASS_EINVAL;
-			}
-			deg[(size_t) i + 1]++; deg[(size_t) j + 1]++;
-		}
-		for (int i = 0; i < n; i++) deg[(size_t) i + 1] += deg[i];
-		for (int i = 0; i <= n; i++) r[i] = (int) (he_base + deg[i]);
-		for (int w0 = 0; w0 < n; w0 += EW) e->ring_records = std::max(e->ring_records, deg[std::min(n, w0 + EW)] - deg[w0]);
-		// Within a node's row the records are ordered like the single-body path orders them (state.cu: by the
-		// neighbour's spatial rank, ties by spring number), so a member sums in the same order and gets the same bits.
 		std::vector<vec4d> pos((size_t) n);
 		for (int i = 0; i < n; i++) {
 			const double* rr = (const double*) ((const unsigned char*) base + (size_t) (node_off[b] + i) * stride);
 			pos[(size_t) i].x = rr[0]; pos[(size_t) i].y = rr[1]; pos[(size_t) i].z = rr[2]; pos[(size_t) i].w = rr[9];
 			if (memcmp(&pos[(size_t) i].w, &pos[0].w, sizeof(double)) != 0) e->uni_mass = false;
 		}
-		std::vector<int> order, rank((size_t) n);
-		ass_morton_order(pos.data(), pos.size(), order);
-		for (int k = 0; k < n; k++) rank[(size_t) order[(size_t) k]] = k;
-		std::vector<std::pair<std::pair<int, int>, int>> ent((size_t) 2 * ns);  // ((neighbour rank, spring), neighbour)
-		std::vector<int> fill(deg.begin(), deg.end() - 1);
-		for (int q = 0; q < ns; q++) {
-			const int ends[2] = { sp[q].particle_1, sp[q].particle_2 };
-			for (int side = 0; side < 2; side++) ent[(size_t) fill[ends[side]]++] = { { rank[(size_t) ends[1 - side]], 2 * q + side }, ends[1 - side] };
+		std::vector<int> pidx((size_t) ns);
+		for (int q = 0; q < ns; q++) pidx[(size_t) q] = pal_index(sp[q]);
+		SpringLayout lay;
+		int bad = -1;
+		rc = ass_build_spring_layout(pos.data(), n, sp, ns, pidx.data(), lay, &bad);
+		if (rc == ASS_EINVAL) {
+			ass_set_error("ass_ensemble_create: body %d spring %d joins (%d,%d): indices are local to the body and must differ", b, bad,
+			              sp[bad].particle_1, sp[bad].particle_2);
+			ens_free(e);
+			return rc;
 		}
-		for (int i = 0; i < n; i++) std::sort(ent.begin() + deg[(size_t) i], ent.begin() + deg[(size_t) i + 1]);
-		for (size_t at = 0; at < ent.size(); at++) {
-			const int q = ent[at].first.second >> 1;
-			HalfEdge hrec;
-			hrec.rs0 = sp[q].rs0; hrec.nbr = ent[at].second; hrec.pal = pal_index(sp[q]);
-			he[he_base + at] = hrec;
+		const long long rec_base = (long long) heT.size();
+		if (rc || rec_base + (long long) lay.heT.size() > 0x7fffffffLL) {
+			ass_set_error("ass_ensemble_create: the members' half-edge records overflow a 32-bit index at body %d", b);
+			ens_free(e);
+			return ASS_EINVAL;
 		}
-		he_base += (size_t) 2 * ns;
+		BodyDesc& d = e->desc[b];
+		d.node_off = node_off[b]; d.n = n;
+		d.grp_off = (int) grp.size(); d.swarp_off = (int) warp_off.size(); d.n_swarps = (int) lay.warp_off.size() - 1;
+		d.pad = 0;
+		for (int i = 0; i < n; i++) {
+			perm[(size_t) node_off[b] + i] = node_off[b] + lay.rank[(size_t) i];
+			ord[(size_t) node_off[b] + lay.rank[(size_t) i]] = i;
+		}
+		grp.insert(grp.end(), lay.grp.begin(), lay.grp.end());
+		for (int w : lay.warp_off) warp_off.push_back((int) (rec_base + w));
+		heT.insert(heT.end(), lay.heT.begin(), lay.heT.end());
+		e->total_he += 2LL * ns;
 	}
-	e->total_he = (long long) he_base;
 	fill_desc(e);
-	e->ring_records = std::max(16, (e->ring_records + 7) / 8 * 8);
-	e->smem = sizeof(HalfEdge) * 2 * (size_t) e->ring_records + (3 * sizeof(double2) + sizeof(double)) * ((size_t) e->max_n + 1) + sizeof(int) * ((size_t) e->max_n + 1) + 64;
+	e->pal1 = palf.size() == 1;
+	e->smem = (3 * sizeof(double2) + sizeof(double)) * ((size_t) e->max_n + 1) + 64;
 	if (e->smem > 227 * 1024 - 2048) {
 		ens_free(e);
-		ass_set_error("ass_ensemble_create: a body of %d nodes (%d half-edges per 64-node wave) does not fit in shared memory (limit ~3000 nodes); use ass_sim for large bodies",
-		              e->max_n, e->ring_records);
+		ass_set_error("ass_ensemble_create: a body of %d nodes does not fit in shared memory (limit ~4000 nodes); use ass_sim for large bodies", e->max_n);
 		return ASS_EINVAL;
 	}
 	const size_t nb = (size_t) total_nodes * stride;
@@ -426,9 +403,11 @@ extern "C" int ass_ensemble_create(ass_ensemble** out, int n_bodies, const int* 
 	bool ok = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) == cudaSuccess && cudaEventCreate(&e->e0) == cudaSuccess &&
 	          cudaEventCreate(&e->e1) == cudaSuccess && cudaMalloc(&e->d_desc, sizeof(BodyDesc) * n_bodies) == cudaSuccess &&
 	          cudaMalloc(&e->posm, sizeof(vec4d) * total_nodes) == cudaSuccess && cudaMalloc(&e->vel, sizeof(vec4d) * total_nodes) == cudaSuccess &&
-	          cudaMalloc(&e->acc, sizeof(vec4d) * total_nodes) == cudaSuccess && cudaMalloc(&e->row_ptr, sizeof(int) * row.size()) == cudaSuccess &&
-	          cudaMalloc(&e->he, sizeof(HalfEdge) * std::max<size_t>(he.size(), 1)) == cudaSuccess &&
-	          cudaMalloc(&e->pal, sizeof(double2) * std::max<size_t>(pal.size(), 1)) == cudaSuccess &&
+	          cudaMalloc(&e->acc, sizeof(vec4d) * total_nodes) == cudaSuccess && cudaMalloc(&e->perm, sizeof(int) * total_nodes) == cudaSuccess &&
+	          cudaMalloc(&e->ord, sizeof(int) * total_nodes) == cudaSuccess && cudaMalloc(&e->grp, sizeof(int2) * std::max<size_t>(grp.size(), 1)) == cudaSuccess &&
+	          cudaMalloc(&e->warp_off, sizeof(int) * std::max<size_t>(warp_off.size(), 1)) == cudaSuccess &&
+	          cudaMalloc(&e->heT, sizeof(HalfEdge) * std::max<size_t>(heT.size(), 1)) == cudaSuccess &&
+	          cudaMalloc(&e->palf, sizeof(double2) * std::max<size_t>(palf.size(), 1)) == cudaSuccess &&
 	          cudaMalloc(&e->d_dense, sizeof(double) * 10 * (size_t) total_nodes) == cudaSuccess && cudaMalloc(&d_rows, nb) == cudaSuccess;
 	if (!ok) {
 		cudaFree(d_rows);
@@ -437,16 +416,21 @@ extern "C" int ass_ensemble_create(ass_ensemble** out, int n_bodies, const int* 
 		return ASS_ENOMEM;
 	}
 	cudaMemcpyAsync(d_rows, base, nb, cudaMemcpyHostToDevice, e->stream);
-	cudaMemcpyAsync(e->row_ptr, row.data(), sizeof(int) * row.size(), cudaMemcpyHostToDevice, e->stream);
-	if (!he.empty()) cudaMemcpyAsync(e->he, he.data(), sizeof(HalfEdge) * he.size(), cudaMemcpyHostToDevice, e->stream);
-	if (!pal.empty()) cudaMemcpyAsync(e->pal, pal.data(), sizeof(double2) * pal.size(), cudaMemcpyHostToDevice, e->stream);
+	cudaMemcpyAsync(e->perm, perm.data(), sizeof(int) * perm.size(), cudaMemcpyHostToDevice, e->stream);
+	cudaMemcpyAsync(e->ord, ord.data(), sizeof(int) * ord.size(), cudaMemcpyHostToDevice, e->stream);
+	if (!grp.empty()) cudaMemcpyAsync(e->grp, grp.data(), sizeof(int2) * grp.size(), cudaMemcpyHostToDevice, e->stream);
+	if (!warp_off.empty()) cudaMemcpyAsync(e->warp_off, warp_off.data(), sizeof(int) * warp_off.size(), cudaMemcpyHostToDevice, e->stream);
+	if (!heT.empty()) cudaMemcpyAsync(e->heT, heT.data(), sizeof(HalfEdge) * heT.size(), cudaMemcpyHostToDevice, e->stream);
+	if (!palf.empty()) cudaMemcpyAsync(e->palf, palf.data(), sizeof(double2) * palf.size(), cudaMemcpyHostToDevice, e->stream);
 	cudaMemcpyAsync(e->d_desc, e->desc.data(), sizeof(BodyDesc) * n_bodies, cudaMemcpyHostToDevice, e->stream);
-	k_unpack<<<(total_nodes + 255) / 256, 256, 0, e->stream>>>((const unsigned char*) d_rows, stride, total_nodes, e->posm, e->vel, e->acc);
+	k_unpack<<<(total_nodes + 255) / 256, 256, 0, e->stream>>>((const unsigned char*) d_rows, stride, total_nodes, e->perm, e->posm, e->vel, e->acc);
 	g_launch_count++;
 	cudaError_t err = cudaStreamSynchronize(e->stream);
 	cudaFree(d_rows);
-	if (err == cudaSuccess) err = cudaFuncSetAttribute(k_ensemble<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) e->smem);
-	if (err == cudaSuccess) err = cudaFuncSetAttribute(k_ensemble<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) e->smem);
+	if (err == cudaSuccess) err = cudaFuncSetAttribute(k_ensemble<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) e->smem);
+	if (err == cudaSuccess) err = cudaFuncSetAttribute(k_ensemble<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) e->smem);
+	if (err == cudaSuccess) err = cudaFuncSetAttribute(k_ensemble<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) e->smem);
+	if (err == cudaSuccess) err = cudaFuncSetAttribute(k_ensemble<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) e->smem);
 	if (err != cudaSuccess) {
 		ass_set_error("ass_ensemble_create: %s", cudaGetErrorString(err));
 		ens_free(e);
@@ -485,12 +469,12 @@ extern "C" int ass_ensemble_step(ass_ensemble* e, int nsteps, int with_heartbeat
 	if (const char* env = getenv("ASS_ENS_ITEM_STEPS")) item_steps = std::max(1, std::min(nsteps, atoi(env)));
 	if (!e->d_queue) CU_TRY(cudaMalloc(&e->d_queue, sizeof(int) * ((size_t) e->n_bodies + 1)));
 	CU_TRY(cudaMemsetAsync(e->d_queue, 0, sizeof(int) * ((size_t) e->n_bodies + 1), e->stream));
-	if (e->uni_mass)
-		k_ensemble<true><<<grid, ET, e->smem, e->stream>>>(e->d_desc, e->posm, e->vel, e->acc, e->row_ptr, e->he, e->pal, nsteps, with_heartbeat, e->max_n,
-				e->ring_records, e->n_bodies, item_steps, e->d_queue, e->d_queue + 1);
-	else
-		k_ensemble<false><<<grid, ET, e->smem, e->stream>>>(e->d_desc, e->posm, e->vel, e->acc, e->row_ptr, e->he, e->pal, nsteps, with_heartbeat, e->max_n,
-				e->ring_records, e->n_bodies, item_steps, e->d_queue, e->d_queue + 1);
+#define ASS_ENS(U, P1)                                                                                                                       \
+	k_ensemble<U, P1><<<grid, ET, e->smem, e->stream>>>(e->d_desc, e->posm, e->vel, e->acc, e->ord, e->grp, e->warp_off, e->heT, e->palf, nsteps, \
+			with_heartbeat, e->max_n, e->n_bodies, item_steps, e->d_queue, e->d_queue + 1)
+	if (e->uni_mass) { if (e->pal1) ASS_ENS(true, true); else ASS_ENS(true, false); }
+	else { if (e->pal1) ASS_ENS(false, true); else ASS_ENS(false, false); }
+#undef ASS_ENS
 	LAUNCH_CHECK();
 	for (auto& p : e->prm)
 		for (int s = 0; s < nsteps; s++) {  // the reference's own rounding of t (integrator_leapfrog.c:50,65)
@@ -515,7 +499,7 @@ extern "C" int ass_ensemble_download(ass_ensemble* e, void* base, size_t stride,
 	int rc = ass_ensure_device();
 	if (rc) return rc;
 	const int n = e->total_nodes;
-	k_pack<<<(n + 255) / 256, 256, 0, e->stream>>>(e->d_dense, n, e->posm, e->vel, e->acc);
+	k_pack<<<(n + 255) / 256, 256, 0, e->stream>>>(e->d_dense, n, e->perm, e->posm, e->vel, e->acc);
 	LAUNCH_CHECK();
 	std::vector<double> h((size_t) n * 10);
 	CU_TRY(cudaMemcpyAsync(h.data(), e->d_dense, sizeof(double) * h.size(), cudaMemcpyDeviceToHost, e->stream));

@@ -25,8 +25,8 @@ __global__ void k_part1(vec4d* __restrict__ posm, const vec4d* __restrict__ vel,
 }
 
 // part1 that also writes the rank-ordered mirror the spring kernel gathers from (common.cuh)
-__global__ void k_part1_mirrored(vec4d* __restrict__ posm, const vec4d* __restrict__ vel, const int* __restrict__ rank, vec4d* __restrict__ ps,
-		vec4d* __restrict__ vs, int n, double dt) {
+__global__ void k_part1_mirrored(vec4d* __restrict__ posm, const vec4d* __restrict__ vel, const int* __restrict__ rank, const SpringMirror mir,
+		double* __restrict__ mir_m, int n, double dt) {
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) return;
 	const double h = __dmul_rn(0.5, dt);
@@ -37,8 +37,10 @@ __global__ void k_part1_mirrored(vec4d* __restrict__ posm, const vec4d* __restri
 	p.z = __dadd_rn(p.z, __dmul_rn(h, v.z));
 	posm[i] = p;
 	const int k = rank[i];
-	ps[k] = p;
-	vs[k] = v;
+	mir.xy[k] = make_double2(p.x, p.y);
+	mir.zv[k] = make_double2(p.z, v.z);
+	mir.vxy[k] = make_double2(v.x, v.y);
+	mir_m[k] = p.w;
 }
 
 __global__ void k_part2(vec4d* __restrict__ posm, vec4d* __restrict__ vel, const vec4d* __restrict__ acc, int lo, int hi, double dt, int pre_drift_next) {
@@ -83,7 +85,7 @@ int ass_launch_part1_range(ass_sim* s, double dt, int lo, int hi) {
 int ass_launch_part1_mirrored(ass_sim* s, double dt) {
 	if (s->n <= 0) return ASS_OK;
 	ass_tic(s, ASS_K_LEAPFROG);
-	k_part1_mirrored<<<(s->n + 255) / 256, 256, 0, s->stream>>>(s->posm, s->vel, s->rank, s->ps, s->vs, s->n, dt);
+	k_part1_mirrored<<<(s->n + 255) / 256, 256, 0, s->stream>>>(s->posm, s->vel, s->rank, s->mir, s->mir_m, s->n, dt);
 	LAUNCH_CHECK();
 	ass_toc(s, ASS_K_LEAPFROG);
 	return ASS_OK;
@@ -156,7 +158,7 @@ static int step_loop(ass_sim* s, int nsteps, bool with_hb) {
 	// does gravity's result reach the kick?  (af == 2 zeroes it again, as the reference would)
 	const bool grav = P.gravity == 1 && af != 2;
 	int rc;
-	// does the rank-ordered mirror (ps / vs) hold exactly posm / vel?  Only the two kernels of this loop that write
+	// does the rank-ordered mirror hold exactly posm / vel?  Only the two kernels of this loop that write
 	// both keep it so; anything else (heartbeat shift, a caller's own kernels between calls) leaves it stale and the
 	// spring launcher re-gathers it.
 	bool mirror_fresh = false;

@@ -337,8 +337,8 @@ extern "C" int ass_destroy(ass_sim* s) {
 	if (s->stream) cudaStreamSynchronize(s->stream);
 	ass_shard_release(s);  // a sharded simulation's posm / vel alias its exported window
 	ass_sym_plans_free(s);
-	cudaFree(s->wave_off); cudaFree(s->cta_wave);
-	cudaFree(s->order); cudaFree(s->rank); cudaFree(s->ps); cudaFree(s->vs); cudaFree(s->ps_alt); cudaFree(s->vs_alt);
+	cudaFree(s->heT); cudaFree(s->slotT); cudaFree(s->grp); cudaFree(s->warp_off);
+	cudaFree(s->order); cudaFree(s->rank); cudaFree(s->mir_block); cudaFree(s->mir_m);
 	cudaFree(s->posm); cudaFree(s->vel); cudaFree(s->acc); cudaFree(s->posm_alt); cudaFree(s->vel_alt);
 	cudaFree(s->he); cudaFree(s->row_ptr); cudaFree(s->slot); cudaFree(s->pal);
 	cudaFree(s->stage.p); cudaFree(s->grav_partial.p); cudaFree(s->red_partial.p); cudaFree(s->flush.p);
@@ -580,19 +580,28 @@ void build_palette(const ass_spring* sp, int ns, std::vector<double2>& pal, std:
 		idx[(size_t) q] = it->second;
 	}
 }
+// device palette: pal_cap entries (k, gamma) for the diagnostics, then pal_cap entries (-k, -max(gamma, 0)) for the
+// force kernels (spring_math.cuh); the negations are exact, so the forces carry the bits of (-k)*(len - rs0)
 int upload_palette(ass_sim* s, const std::vector<double2>& pal) {
 	if (pal.size() > s->pal_cap) {
 		cudaFree(s->pal);
-		s->pal = nullptr; s->pal_cap = 0;
+		s->pal = nullptr; s->palf = nullptr; s->pal_cap = 0;
 		const size_t cap = pal.size() + pal.size() / 4 + 16;
-		if (cudaMalloc(&s->pal, sizeof(double2) * cap) != cudaSuccess) {
+		if (cudaMalloc(&s->pal, sizeof(double2) * 2 * cap) != cudaSuccess) {
 			cudaGetLastError();
 			ass_set_error("out of device memory for a palette of %zu (k, gamma) pairs", cap);
 			return ASS_ENOMEM;
 		}
 		s->pal_cap = cap;
+		s->palf = s->pal + cap;
 	}
-	if (!pal.empty()) CU_TRY(cudaMemcpyAsync(s->pal, pal.data(), sizeof(double2) * pal.size(), cudaMemcpyHostToDevice, s->stream));
+	if (!pal.empty()) {
+		std::vector<double2> palf(pal.size());
+		for (size_t i = 0; i < pal.size(); i++) palf[i] = make_double2(-pal[i].x, pal[i].y > 0.0 ? -pal[i].y : -0.0);
+		CU_TRY(cudaMemcpyAsync(s->pal, pal.data(), sizeof(double2) * pal.size(), cudaMemcpyHostToDevice, s->stream));
+		CU_TRY(cudaMemcpyAsync(s->palf, palf.data(), sizeof(double2) * pal.size(), cudaMemcpyHostToDevice, s->stream));
+		CU_TRY(cudaStreamSynchronize(s->stream));  // both vectors are pageable and die with their scopes
+	}
 	s->n_pal = (int) pal.size();
 	return ASS_OK;
 }
@@ -639,40 +648,146 @@ void morton_order(const vec4d* pos, size_t n, std::vector<int>& order) {
 	for (size_t k = 0; k < n; k++) order[k] = keyed[k].second;
 }
 
-int reserve_waves(ass_sim* s, int n_waves) {
-	if ((size_t) n_waves + 1 <= s->wave_cap) return ASS_OK;
-	cudaFree(s->wave_off);
-	s->wave_off = nullptr; s->wave_cap = 0;
-	const size_t cap = (size_t) n_waves + 1 + n_waves / 8 + 16;
-	if (cudaMalloc(&s->wave_off, sizeof(int) * cap) != cudaSuccess) {
-		cudaGetLastError();
-		ass_set_error("out of device memory for %zu wave offsets", cap);
-		return ASS_ENOMEM;
-	}
-	s->wave_cap = cap;
-	return ASS_OK;
-}
-
 int reserve_sorted(ass_sim* s, int n) {
-	if ((size_t) n + ASS_SPRING_WAVE <= s->sorted_cap) return ASS_OK;
-	cudaFree(s->order); cudaFree(s->rank); cudaFree(s->ps); cudaFree(s->vs); cudaFree(s->ps_alt); cudaFree(s->vs_alt);
+	if ((size_t) n <= s->sorted_cap) return ASS_OK;
+	cudaFree(s->order); cudaFree(s->rank); cudaFree(s->mir_block); cudaFree(s->mir_m);
 	s->order = s->rank = nullptr;
-	s->ps = s->vs = s->ps_alt = s->vs_alt = nullptr;
+	s->mir = SpringMirror(); s->mir_alt = SpringMirror(); s->mir_m = nullptr; s->mir_block = nullptr;
 	s->sorted_cap = 0;
-	const size_t cap = (size_t) n + n / 8 + 64 + ASS_SPRING_WAVE;
+	const size_t cap = ((size_t) n + n / 8 + 64 + 7) & ~(size_t) 7;
+	double2* block = nullptr;  // the mirror and its ping-pong twin: six arrays of 16-byte pairs
 	if (cudaMalloc(&s->order, sizeof(int) * cap) != cudaSuccess || cudaMalloc(&s->rank, sizeof(int) * cap) != cudaSuccess ||
-	    cudaMalloc(&s->ps, sizeof(vec4d) * cap) != cudaSuccess || cudaMalloc(&s->vs, sizeof(vec4d) * cap) != cudaSuccess ||
-	    cudaMalloc(&s->ps_alt, sizeof(vec4d) * cap) != cudaSuccess || cudaMalloc(&s->vs_alt, sizeof(vec4d) * cap) != cudaSuccess) {
+	    cudaMalloc(&block, sizeof(double2) * 6 * cap) != cudaSuccess || cudaMalloc(&s->mir_m, sizeof(double) * cap) != cudaSuccess) {
 		cudaGetLastError();
+		cudaFree(block);
 		ass_set_error("out of device memory for the rank-ordered mirror of %zu nodes", cap);
 		return ASS_ENOMEM;
 	}
+	s->mir_block = block;
+	s->mir.xy = block; s->mir.zv = block + cap; s->mir.vxy = block + 2 * cap;
+	s->mir_alt.xy = block + 3 * cap; s->mir_alt.zv = block + 4 * cap; s->mir_alt.vxy = block + 5 * cap;
 	s->sorted_cap = cap;
+	return ASS_OK;
+}
+
+template <class T>
+int reserve_array(T*& ptr, size_t& cap, size_t need, const char* what) {
+	if (need <= cap) return ASS_OK;
+	cudaFree(ptr);
+	ptr = nullptr; cap = 0;
+	const size_t c = need + need / 8 + 64;
+	if (cudaMalloc(&ptr, sizeof(T) * c) != cudaSuccess) {
+		cudaGetLastError();
+		ass_set_error("out of device memory for %zu %s", c, what);
+		return ASS_ENOMEM;
+	}
+	cap = c;
 	return ASS_OK;
 }
 }  // namespace
 
 void ass_morton_order(const vec4d* pos, size_t n, std::vector<int>& order) { morton_order(pos, n, order); }
+
+// Host-side construction of everything the spring kernels read (common.cuh: SpringLayout): spatial ranking, CSR rows
+// by rank with each row sorted by neighbour rank, and the lane-transposed copy.  Shared by ass_set_springs and the
+// ensemble (one layout per member), so a member sums in the same order as the single-body path and gets the same bits.
+// pidx[q] = palette index of spring q; *bad_spring = first spring with an endpoint outside [0, n) or i == j, else -1.
+int ass_build_spring_layout(const vec4d* pos, int n, const ass_spring* sp, int ns, const int* pidx, SpringLayout& out, int* bad_spring) {
+	*bad_spring = -1;
+	for (int q = 0; q < ns; q++) {
+		const int i = sp[q].particle_1, j = sp[q].particle_2;
+		if (i < 0 || j < 0 || i >= n || j >= n || i == j) {
+			*bad_spring = q;
+			return ASS_EINVAL;
+		}
+	}
+	std::vector<int>& order = out.order;
+	std::vector<int>& rank = out.rank;
+	std::vector<int>& row = out.row;
+	rank.assign((size_t) n, 0);
+	morton_order(pos, (size_t) n, order);
+	for (int k = 0; k < n; k++) rank[(size_t) order[k]] = k;
+	// rows by rank
+	row.assign((size_t) n + 1, 0);
+	for (int q = 0; q < ns; q++) {
+		row[(size_t) rank[sp[q].particle_1] + 1]++;
+		row[(size_t) rank[sp[q].particle_2] + 1]++;
+	}
+	out.max_degree = 0;
+	for (int k = 0; k < n; k++) {
+		out.max_degree = std::max(out.max_degree, row[(size_t) k + 1]);
+		row[(size_t) k + 1] += row[k];
+	}
+	const size_t nhe = (size_t) 2 * ns;
+	// (neighbour rank, 2*spring + side) per half-edge, bucketed by owner row, then each row ordered by neighbour rank so
+	// the lanes of a group gather ascending, mostly adjacent entries
+	std::vector<std::pair<int, int>> ent(nhe);
+	{
+		std::vector<int> fill(row.begin(), row.end() - 1);
+		for (int q = 0; q < ns; q++) {
+			const int e[2] = { rank[sp[q].particle_1], rank[sp[q].particle_2] };
+			for (int side = 0; side < 2; side++) ent[(size_t) fill[e[side]]++] = { e[1 - side], 2 * q + side };
+		}
+	}
+	for (int k = 0; k < n; k++) std::sort(ent.begin() + row[k], ent.begin() + row[(size_t) k + 1]);
+	out.he.resize(nhe);
+	out.slot.resize(nhe);
+	for (size_t at = 0; at < nhe; at++) {
+		const int q = ent[at].second >> 1;
+		HalfEdge h;
+		h.rs0 = sp[q].rs0;
+		h.nbr = ent[at].first;
+		h.pal = pidx[(size_t) q];
+		out.he[at] = h;
+		out.slot[(size_t) ent[at].second] = (int) at;
+	}
+	// ---- the lane-transposed copy (common.cuh: ass_sim::heT) ----
+	// nodes -> lane groups: inside every block of ASS_SORT_BLOCK ranks, by decreasing degree (ties: by rank)
+	constexpr int L = SPRING_LANES, GPW = 32 / SPRING_LANES;
+	const int n_swarps = (n + GPW - 1) / GPW;
+	const size_t n_grp = (size_t) n_swarps * GPW;
+	std::vector<int2>& grp = out.grp;
+	grp.assign(n_grp, make_int2(-1, 0));
+	for (int b0 = 0; b0 < n; b0 += ASS_SORT_BLOCK) {
+		const int b1 = std::min(n, b0 + ASS_SORT_BLOCK);
+		for (int k = b0; k < b1; k++) grp[(size_t) k] = make_int2(k, row[(size_t) k + 1] - row[k]);
+		std::stable_sort(grp.begin() + b0, grp.begin() + b1, [](const int2& x, const int2& y) { return x.y > y.y; });
+	}
+	std::vector<int>& warp_off = out.warp_off;
+	warp_off.assign((size_t) n_swarps + 1, 0);
+	for (int w = 0; w < n_swarps; w++) {
+		int steps = 0;
+		for (int g = 0; g < GPW; g++) steps = std::max(steps, (grp[(size_t) w * GPW + g].y + L - 1) / L);
+		steps = (steps + 1) & ~1;  // the kernels work on pairs of steps
+		const long long next = (long long) warp_off[w] + 32LL * steps;
+		if (next > 0x7fffffffLL) return ASS_ENOMEM;  // 32-bit record index
+		warp_off[(size_t) w + 1] = (int) next;
+	}
+	const size_t n_heT = (size_t) warp_off[n_swarps];
+	out.heT.resize(n_heT);
+	out.slotT.resize(nhe);
+	for (int w = 0; w < n_swarps; w++) {
+		const int steps = (warp_off[(size_t) w + 1] - warp_off[w]) / 32;
+		for (int g = 0; g < GPW; g++) {
+			const int2 gi = grp[(size_t) w * GPW + g];
+			HalfEdge padrec;  // loaded and computed, never accumulated: must gather from a valid entry
+			padrec.rs0 = 0.0; padrec.nbr = gi.x >= 0 ? gi.x : 0; padrec.pal = 0;
+			for (int t = 0; t < steps; t++)
+				for (int l = 0; l < L; l++) {
+					const int e = t * L + l;
+					const size_t at_t = (size_t) warp_off[w] + (size_t) t * 32 + (size_t) g * L + l;
+					if (e < gi.y) {
+						const size_t at = (size_t) row[gi.x] + e;
+						out.heT[at_t] = out.he[at];
+						out.slotT[(size_t) ent[at].second] = (int) at_t;
+					} else {
+						out.heT[at_t] = padrec;
+					}
+				}
+		}
+	}
+	return ASS_OK;
+}
 
 extern "C" int ass_set_springs(ass_sim* s, const ass_spring* sp, int ns) {
 	REQUIRE(s, ASS_EINVAL, "null sim");
@@ -683,125 +798,76 @@ extern "C" int ass_set_springs(ass_sim* s, const ass_spring* sp, int ns) {
 	int rc = ass_ensure_device();
 	if (rc) return rc;
 	const int n = s->n;
-	for (int q = 0; q < ns; q++) {
-		const int i = sp[q].particle_1, j = sp[q].particle_2;
-		if (i < 0 || j < 0 || i >= n || j >= n) {
-			ass_set_error("ass_set_springs: spring %d joins (%d,%d) outside [0,%d)", q, i, j, n);
-			return ASS_EINVAL;
-		}
-		if (i == j) {  // add_spring throws "Cannot connect a particle to itself." (springs.cpp:57-59)
-			ass_set_error("ass_set_springs: spring %d connects particle %d to itself", q, i);
-			return ASS_EINVAL;
-		}
-	}
 	// spatial ranking of the nodes from their positions now (common.cuh: "springs")
 	std::vector<vec4d> pos((size_t) n);
 	if (n) {
 		CU_TRY(cudaMemcpyAsync(pos.data(), s->posm, sizeof(vec4d) * (size_t) n, cudaMemcpyDeviceToHost, s->stream));
 		CU_TRY(cudaStreamSynchronize(s->stream));
 	}
-	std::vector<int> order, rank((size_t) n);
-	morton_order(pos.data(), pos.size(), order);
-	for (int k = 0; k < n; k++) rank[(size_t) order[k]] = k;
-	std::vector<vec4d>().swap(pos);
-	// rows by rank
-	std::vector<int> row((size_t) n + 1, 0);
-	for (int q = 0; q < ns; q++) {
-		row[(size_t) rank[sp[q].particle_1] + 1]++;
-		row[(size_t) rank[sp[q].particle_2] + 1]++;
-	}
-	int maxdeg = 0;
-	for (int k = 0; k < n; k++) {
-		maxdeg = std::max(maxdeg, row[(size_t) k + 1]);
-		row[(size_t) k + 1] += row[k];
-	}
 	std::vector<double2> pal;
 	std::vector<int> pidx;
 	build_palette(sp, ns, pal, pidx);
-	const size_t nhe = (size_t) 2 * ns;
-	// (neighbour rank, 2*spring + side) per half-edge, bucketed by owner row, then each row ordered by neighbour rank so
-	// the lanes that share a request gather ascending, mostly adjacent sectors
-	std::vector<std::pair<int, int>> ent(nhe);
-	{
-		std::vector<int> fill(row.begin(), row.end() - 1);
-		for (int q = 0; q < ns; q++) {
-			const int e[2] = { rank[sp[q].particle_1], rank[sp[q].particle_2] };
-			for (int side = 0; side < 2; side++) ent[(size_t) fill[e[side]]++] = { e[1 - side], 2 * q + side };
-		}
+	SpringLayout lay;
+	int bad = -1;
+	rc = ass_build_spring_layout(pos.data(), n, sp, ns, pidx.data(), lay, &bad);
+	if (rc == ASS_EINVAL) {
+		const int i = sp[bad].particle_1, j = sp[bad].particle_2;
+		if (i == j) ass_set_error("ass_set_springs: spring %d connects particle %d to itself", bad, i);  // springs.cpp:57-59 throws
+		else ass_set_error("ass_set_springs: spring %d joins (%d,%d) outside [0,%d)", bad, i, j, n);
+		return rc;
 	}
-	for (int k = 0; k < n; k++) std::sort(ent.begin() + row[k], ent.begin() + row[(size_t) k + 1]);
-	std::vector<HalfEdge> he(nhe);
-	std::vector<int> slot(nhe);
-	for (size_t at = 0; at < nhe; at++) {
-		const int q = ent[at].second >> 1;
-		HalfEdge h;
-		h.rs0 = sp[q].rs0;
-		h.nbr = ent[at].first;
-		h.pal = pidx[(size_t) q];
-		he[at] = h;
-		slot[(size_t) ent[at].second] = (int) at;
+	if (rc) {
+		ass_set_error("ass_set_springs: %d springs overflow the 32-bit record index of the lane layout", ns);
+		return rc;
 	}
-	std::vector<std::pair<int, int>>().swap(ent);
+	std::vector<vec4d>().swap(pos);
+	const size_t nhe = lay.he.size(), n_heT = lay.heT.size(), n_grp = lay.grp.size();
 	if ((rc = reserve_sorted(s, n))) return rc;
 	if (nhe > s->he_cap) {
-		cudaFree(s->he); cudaFree(s->slot);
-		s->he = nullptr; s->slot = nullptr; s->he_cap = 0;
+		cudaFree(s->he); cudaFree(s->slot); cudaFree(s->slotT);
+		s->he = nullptr; s->slot = nullptr; s->slotT = nullptr; s->he_cap = 0;
 		size_t cap = nhe + nhe / 8 + 64;
-		if (cudaMalloc(&s->he, sizeof(HalfEdge) * cap) != cudaSuccess || cudaMalloc(&s->slot, sizeof(int) * cap) != cudaSuccess) {
+		if (cudaMalloc(&s->he, sizeof(HalfEdge) * cap) != cudaSuccess || cudaMalloc(&s->slot, sizeof(int) * cap) != cudaSuccess ||
+		    cudaMalloc(&s->slotT, sizeof(int) * cap) != cudaSuccess) {
 			cudaGetLastError();
 			ass_set_error("out of device memory for %zu half-edges", cap);
 			return ASS_ENOMEM;
 		}
 		s->he_cap = cap;
 	}
-	// waves of the streaming kernel; row_ptr and order padded so a wave is always a whole, 16-byte-multiple copy
-	const int W = ASS_SPRING_WAVE;
-	const int n_waves = (n + W - 1) / W;
-	row.resize((size_t) n_waves * W + 4, (int) nhe);
-	order.resize((size_t) n_waves * W, 0);
-	std::vector<int> wave_off((size_t) n_waves + 1);
-	int wave_he_max = 0;
-	for (int w = 0; w <= n_waves; w++) wave_off[(size_t) w] = row[(size_t) w * W];
-	for (int w = 0; w < n_waves; w++) wave_he_max = std::max(wave_he_max, wave_off[(size_t) w + 1] - wave_off[(size_t) w]);
-	if ((rc = reserve_waves(s, n_waves))) return rc;
-	if (row.size() > s->row_cap) {
-		cudaFree(s->row_ptr);
-		s->row_ptr = nullptr; s->row_cap = 0;
-		size_t cap = row.size() + n / 8 + 64;
-		if (cudaMalloc(&s->row_ptr, sizeof(int) * cap) != cudaSuccess) {
-			cudaGetLastError();
-			ass_set_error("out of device memory for %zu row pointers", cap);
-			return ASS_ENOMEM;
-		}
-		s->row_cap = cap;
-	}
+	if ((rc = reserve_array(s->heT, s->heT_cap, n_heT, "lane-transposed half-edge records"))) return rc;
+	if ((rc = reserve_array(s->grp, s->grp_cap, n_grp, "lane groups"))) return rc;
+	if ((rc = reserve_array(s->warp_off, s->swarp_cap, lay.warp_off.size(), "warp offsets"))) return rc;
+	if ((rc = reserve_array(s->row_ptr, s->row_cap, lay.row.size(), "row pointers"))) return rc;
 	ass_tic(s, ASS_K_XFER);
 	if ((rc = upload_palette(s, pal))) return rc;
 	if (nhe) {
-		CU_TRY(cudaMemcpyAsync(s->he, he.data(), sizeof(HalfEdge) * nhe, cudaMemcpyHostToDevice, s->stream));
-		CU_TRY(cudaMemcpyAsync(s->slot, slot.data(), sizeof(int) * nhe, cudaMemcpyHostToDevice, s->stream));
+		CU_TRY(cudaMemcpyAsync(s->he, lay.he.data(), sizeof(HalfEdge) * nhe, cudaMemcpyHostToDevice, s->stream));
+		CU_TRY(cudaMemcpyAsync(s->slot, lay.slot.data(), sizeof(int) * nhe, cudaMemcpyHostToDevice, s->stream));
+		CU_TRY(cudaMemcpyAsync(s->slotT, lay.slotT.data(), sizeof(int) * nhe, cudaMemcpyHostToDevice, s->stream));
 	}
-	CU_TRY(cudaMemcpyAsync(s->row_ptr, row.data(), sizeof(int) * row.size(), cudaMemcpyHostToDevice, s->stream));
-	CU_TRY(cudaMemcpyAsync(s->wave_off, wave_off.data(), sizeof(int) * wave_off.size(), cudaMemcpyHostToDevice, s->stream));
+	if (n_heT) CU_TRY(cudaMemcpyAsync(s->heT, lay.heT.data(), sizeof(HalfEdge) * n_heT, cudaMemcpyHostToDevice, s->stream));
+	CU_TRY(cudaMemcpyAsync(s->row_ptr, lay.row.data(), sizeof(int) * lay.row.size(), cudaMemcpyHostToDevice, s->stream));
+	CU_TRY(cudaMemcpyAsync(s->warp_off, lay.warp_off.data(), sizeof(int) * lay.warp_off.size(), cudaMemcpyHostToDevice, s->stream));
+	if (n_grp) CU_TRY(cudaMemcpyAsync(s->grp, lay.grp.data(), sizeof(int2) * n_grp, cudaMemcpyHostToDevice, s->stream));
 	if (n) {
-		CU_TRY(cudaMemcpyAsync(s->order, order.data(), sizeof(int) * order.size(), cudaMemcpyHostToDevice, s->stream));
-		CU_TRY(cudaMemcpyAsync(s->rank, rank.data(), sizeof(int) * (size_t) n, cudaMemcpyHostToDevice, s->stream));
+		CU_TRY(cudaMemcpyAsync(s->order, lay.order.data(), sizeof(int) * (size_t) n, cudaMemcpyHostToDevice, s->stream));
+		CU_TRY(cudaMemcpyAsync(s->rank, lay.rank.data(), sizeof(int) * (size_t) n, cudaMemcpyHostToDevice, s->stream));
 	}
 	ass_toc(s, ASS_K_XFER);
-	CU_TRY(cudaStreamSynchronize(s->stream));  // the vectors above die here
+	CU_TRY(cudaStreamSynchronize(s->stream));  // the layout dies here
 	s->ns = ns;
 	s->n_he = (int) nhe;
-	s->max_degree = maxdeg;
-	s->n_waves = n_waves;
-	s->wave_he_max = wave_he_max;
-	s->h_wave_off = wave_off;
+	s->n_heT = (long long) n_heT;
+	s->n_swarps = (int) lay.warp_off.size() - 1;
+	s->max_degree = lay.max_degree;
 	s->spring_epoch++;
 	return ASS_OK;
 }
 
 // stage holds [ns x ass_spring | ns x int palette index]
 __global__ void k_scatter_props(const ass_spring* __restrict__ sp, const int* __restrict__ pidx, const int* __restrict__ slot,
-		HalfEdge* __restrict__ he, int ns) {
+		const int* __restrict__ slotT, HalfEdge* __restrict__ he, HalfEdge* __restrict__ heT, int ns) {
 	int q = blockIdx.x * blockDim.x + threadIdx.x;
 	if (q >= ns) return;
 	const double rs0 = sp[q].rs0;
@@ -810,6 +876,9 @@ __global__ void k_scatter_props(const ass_spring* __restrict__ sp, const int* __
 		HalfEdge* h = he + slot[(size_t) 2 * q + side];
 		h->rs0 = rs0;
 		h->pal = pi;
+		HalfEdge* ht = heT + slotT[(size_t) 2 * q + side];
+		ht->rs0 = rs0;
+		ht->pal = pi;
 	}
 }
 
@@ -829,7 +898,7 @@ extern "C" int ass_update_spring_props(ass_sim* s, const ass_spring* sp, int ns)
 	if ((rc = upload_palette(s, pal))) return rc;
 	CU_TRY(cudaMemcpyAsync(s->stage.p, sp, sp_bytes, cudaMemcpyHostToDevice, s->stream));
 	CU_TRY(cudaMemcpyAsync((char*) s->stage.p + sp_bytes, pidx.data(), sizeof(int) * (size_t) ns, cudaMemcpyHostToDevice, s->stream));
-	k_scatter_props<<<(ns + 255) / 256, 256, 0, s->stream>>>((const ass_spring*) s->stage.p, (const int*) ((char*) s->stage.p + sp_bytes), s->slot, s->he, ns);
+	k_scatter_props<<<(ns + 255) / 256, 256, 0, s->stream>>>((const ass_spring*) s->stage.p, (const int*) ((char*) s->stage.p + sp_bytes), s->slot, s->slotT, s->he, s->heT, ns);
 	LAUNCH_CHECK();
 	ass_toc(s, ASS_K_XFER);
 	CU_TRY(cudaStreamSynchronize(s->stream));

@@ -99,7 +99,7 @@ def test_ensemble_errors(gpu):
     bad = sp.copy(); bad["particle_2"][0] = len(p) + 5
     with pytest.raises(gpu.AssError):
         gpu.Ensemble([p], [bad], [dict()])
-    big = np.zeros((4000, 11)); big[:, 9] = 1.0
+    big = np.zeros((6000, 11)); big[:, 9] = 1.0   # 56 B of shared memory per node: the limit is ~4000
     with pytest.raises(gpu.AssError) as e:
         gpu.Ensemble([big], [sp[:0]], [dict()])
     assert "shared memory" in str(e.value)
