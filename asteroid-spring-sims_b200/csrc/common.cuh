@@ -142,6 +142,13 @@ struct ass_sim {
 	int2* grp = nullptr;
 	int* warp_off = nullptr;  // n_swarps + 1
 	int n_swarps = 0;
+	std::vector<int> h_warp_off;  // host copy of warp_off
+	// which slices each persistent CTA of the lane kernel takes: ccut[c] .. ccut[c+1], followed by the per-warp pair
+	// counts (springs.cu: ensure_cta_cuts)
+	int* ccut = nullptr;
+	size_t ccut_cap = 0;
+	int ccut_grid = 0;
+	long long ccut_epoch = -1;
 	size_t heT_cap = 0, grp_cap = 0, swarp_cap = 0;
 	long long n_heT = 0;
 	double2* pal = nullptr;   // palette of distinct (k, gamma) pairs

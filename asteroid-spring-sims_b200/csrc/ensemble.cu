@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(ET, 1) k_ensemble(const BodyDesc* __restrict__
 	extern __shared__ __align__(128) unsigned char smem_raw[];
 	__shared__ double red[ET / 32][4];
 	__shared__ double com[4];
-	__shared__ int s_item;
+	__shared__ int s_item, s_next;  // s_next: the next slice of the spring phase (warps pull slices: no warp waits for a longer share)
 	const int tid = threadIdx.x;
 	const int n_batches = (nsteps_total + item_steps - 1) / item_steps;
 	while (true) {
@@ -109,12 +109,13 @@ __global__ void __launch_bounds__(ET, 1) k_ensemble(const BodyDesc* __restrict__
 		stp(i, ldcg4(posm_g + B.node_off + i));
 		stv(i, ldcg4(vel_g + B.node_off + i));
 	}
+	if (tid == 0) s_next = 0;
 	__syncthreads();
 	const double dt = B.dt, h = __dmul_rn(0.5, dt);
 	const bool hb = with_hb && B.heartbeat == 1;
 	const bool have_springs = B.af != 0 && warp_off[B.swarp_off + B.n_swarps] > warp_off[B.swarp_off];
 	const bool grav = B.gravity == 1 && B.af != 2;
-	const int lane = tid & 31, warp = tid >> 5;
+	const int lane = tid & 31;
 	double2 nkg1 = make_double2(0.0, 0.0);
 	if (PAL1) nkg1 = __ldg(palf);
 	bool predrifted = false;
@@ -149,8 +150,12 @@ __global__ void __launch_bounds__(ET, 1) k_ensemble(const BodyDesc* __restrict__
 			}
 			__syncthreads();  // also orders the global acc writes before the spring phase's reads (same CTA)
 		}
-		if (have_springs) {  // spring_forces (+ zero_accel when af == 2): every warp takes every (ET / 32)-th slice of 32 / SPRING_LANES nodes
-			for (int sw = warp; sw < B.n_swarps; sw += ET / 32) {
+		if (have_springs) {  // spring_forces (+ zero_accel when af == 2): warps pull slices of 32 / SPRING_LANES nodes from a counter
+			while (true) {
+				int sw = 0;
+				if (lane == 0) sw = atomicAdd(&s_next, 1);
+				sw = __shfl_sync(0xffffffffu, sw, 0);
+				if (sw >= B.n_swarps) break;
 				const int2 gi = __ldg(grp + B.grp_off + sw * GPW + lane / SPRING_LANES);  // (rank, degree); (-1, 0): padding group
 				const int off = __ldg(warp_off + B.swarp_off + sw);
 				const int P = (__ldg(warp_off + B.swarp_off + sw + 1) - off) >> 6;
@@ -171,6 +176,7 @@ __global__ void __launch_bounds__(ET, 1) k_ensemble(const BodyDesc* __restrict__
 				}
 			}
 			__syncthreads();  // nobody reads positions any more: the kick may move them
+			if (tid == 0) s_next = 0;  // for the next step's spring phase (two barriers away)
 		} else {
 			if (B.af == 2)
 				for (int i = tid; i < n; i += ET) { vec4d z; z.x = 0; z.y = 0; z.z = 0; z.w = 0; acc[i] = z; }

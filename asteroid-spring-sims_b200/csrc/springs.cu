@@ -101,48 +101,170 @@ __global__ void __launch_bounds__(BLOCK) k_spring_forces(const GlobalNodes nodes
 // ---------------------------------------------------------------------------------------------------
 // The lane kernel (whole body): reads the lane-transposed copy of the half-edge list (ass_sim::heT, common.cuh).
 //
-// A warp owns 32 / SPRING_LANES nodes of similar degree and walks their rows in lock step (spring_math.cuh:
-// lane_spring_sum): step t of lane l is ONE record at heT[warp_off + 32 t + l], so the warp reads 512 contiguous bytes
-// per step and the trip count is the same for every lane.  Nothing is staged in shared memory: the L1 is left to the
-// endpoint gathers, which are 16-byte reads of the rank-ordered mirror -- a group's SPRING_LANES lanes read consecutive entries
-// of a row sorted by neighbour rank, i.e. mostly one or two cache lines per group.
-// Launch: plain grid, one warp per 32 / SPRING_LANES nodes, LN_THREADS threads per CTA; CTAs of different length
-// overlap through the block scheduler.
+// A warp owns 32 / SPRING_LANES nodes of similar degree -- a SLICE -- and walks their rows in lock step: step t of lane
+// l is ONE record at heT[warp_off + 32 t + l], so a step of the warp is 512 contiguous bytes and the trip count is
+// the same for every lane (no votes, no divergence, no per-row bookkeeping).  CTAs are persistent, one per SM: CTA c owns
+// the contiguous run of slices [ccut[c], ccut[c+1]) (cut on the host so that every CTA carries the same number of step
+// pairs) and its sixteen warps take them round-robin, so at any moment the whole SM works on ~128 nodes that are
+// neighbours in space and the L1 holds one neighbourhood, not sixteen.  A slice's records are one contiguous run of
+// heT: each warp streams its records through a private ring in shared memory with the bulk-copy engine
+// (cp.async.bulk -> mbarrier, SASS UBLKCP; LN_STAGES pairs of steps = 4 KB ahead, across its slices; producer and
+// consumer are the same warp, so handing a stage back needs no second barrier), and its software
+// pipeline -- records of pair p+1 out of the ring, their endpoint gathers issued, arithmetic of pair p (two interleaved
+// FP64 chains per lane, spring_math.cuh) -- runs straight across slice boundaries: at a boundary the warp folds its
+// partial sums, runs the node epilogue (acc, optionally kick + drift + mirror) and switches to the next slice's nodes,
+// whose header was read one slice ago and whose state was prefetched one pair ago.  The only exposed memory latency
+// of a warp is that of its very first pair.
+// The loop is unrolled by two over explicit operand sets A / B so that the pipeline costs no register moves.
+// Padding records (rows shorter than the slice's longest) point at the node itself and enter the sum with a zero
+// coefficient.  The L1 is left to the endpoint gathers: 16-byte reads of the rank-ordered mirror -- a group's
+// SPRING_LANES lanes read consecutive entries of a row sorted by neighbour rank, i.e. mostly one or two cache lines.
 // ---------------------------------------------------------------------------------------------------
 #ifndef ASS_LANES_THREADS
-#define ASS_LANES_THREADS 128
+#define ASS_LANES_THREADS 512
 #endif
 #ifndef ASS_LANES_MINBLOCKS
-#define ASS_LANES_MINBLOCKS 4
+#define ASS_LANES_MINBLOCKS 1
+#endif
+#ifndef ASS_LANES_STAGES
+#define ASS_LANES_STAGES 4
 #endif
 constexpr int LN_THREADS = ASS_LANES_THREADS;
+constexpr int LN_WARPS = LN_THREADS / 32;
+constexpr int LN_STAGES = ASS_LANES_STAGES;  // power of two
+constexpr int LN_PAIR_BYTES = 64 * (int) sizeof(HalfEdge);  // two steps of a warp
+static_assert((LN_STAGES & (LN_STAGES - 1)) == 0, "LN_STAGES must be a power of two");
+constexpr int GPW = 32 / SPRING_LANES;
+
 template <bool ZERO_FIRST, bool KICK, bool UNI, bool PAL1>
 __global__ void __launch_bounds__(LN_THREADS, ASS_LANES_MINBLOCKS) k_spring_lanes(const GlobalNodes nodes, const int* __restrict__ order,
-		vec4d* __restrict__ acc, const int2* __restrict__ grp, const int* __restrict__ warp_off, const HalfEdge* __restrict__ heT,
-		const double2* __restrict__ palf, int n_swarps, vec4d* __restrict__ posm_out, vec4d* __restrict__ vel_out, const SpringMirror out, double dt,
-		int pre_drift_next) {
-	const int gt = blockIdx.x * LN_THREADS + threadIdx.x;
-	const int w = gt >> 5;
-	if (w >= n_swarps) return;  // whole warps
-	const int lane = threadIdx.x & 31;
-	const int2 gi = grp[gt / SPRING_LANES];  // (rank, degree); (-1, 0): padding group
-	const int off = warp_off[w];
-	const int P = (warp_off[w + 1] - off) >> 6;  // pairs of steps (the warp's step count is even)
-	const bool live = gi.x >= 0;
-	const int k = live ? gi.x : 0;
-	// entries l, l + SPRING_LANES, ... of the row are this lane's: nt of them
-	const int nt = (gi.y - (lane & (SPRING_LANES - 1)) + SPRING_LANES - 1) / SPRING_LANES;
-	const NodeState ni = nodes.get<false>(k);
-	const int node = order[k];
-	if (!ZERO_FIRST) asm volatile("prefetch.global.L1 [%0];" ::"l"(acc + node));  // needed after the sum
+		vec4d* __restrict__ acc, const int2* __restrict__ grp, const int* __restrict__ warp_off, const int* __restrict__ ccut, const int* __restrict__ wpairs,
+		const HalfEdge* __restrict__ heT, const double2* __restrict__ palf, vec4d* __restrict__ posm_out, vec4d* __restrict__ vel_out,
+		const SpringMirror out, double dt, int pre_drift_next) {
+	extern __shared__ __align__(128) unsigned char ring_all[];  // [LN_WARPS][LN_STAGES][LN_PAIR_BYTES]
+	__shared__ __align__(8) uint64_t full_all[LN_WARPS][LN_STAGES];
+	const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
+	const int sub = lane & (SPRING_LANES - 1);
+	unsigned char(*ring)[LN_PAIR_BYTES] = (unsigned char(*)[LN_PAIR_BYTES]) (ring_all + (size_t) wi * LN_STAGES * LN_PAIR_BYTES);
+	uint64_t* full = full_all[wi];
+	if (lane == 0) {
+#pragma unroll
+		for (int q = 0; q < LN_STAGES; q++) mbar_init(&full[q], 1);
+		mbar_fence_init();
+	}
+	__syncwarp();
+	// this CTA's slices: [c0, s1); warp wi takes c0 + wi, c0 + wi + LN_WARPS, ...
+	const int c0 = ccut[blockIdx.x], s1 = ccut[blockIdx.x + 1];
+	int s = c0 + wi;
+	const int Ptot = wpairs[blockIdx.x * LN_WARPS + wi];  // pairs of steps over all of this warp's slices
+	if (s >= s1) return;  // whole warps
+	// lane 0 only: the producer's cursor runs up to LN_STAGES pairs ahead of the consumers, through the same slices
+	int p_slice = s - LN_WARPS, p_left = 0;
+	const unsigned char* p_src = nullptr;
+	int p_q = 0;
+	auto produce = [&]() {  // the next pair of the warp's stream -> ring stage p_q % LN_STAGES
+		while (p_left == 0) {  // (a loop: slices without springs have no pairs; Ptot bounds the calls, so a slice exists)
+			p_slice += LN_WARPS;
+			const int off = __ldg(warp_off + p_slice);
+			p_left = (__ldg(warp_off + p_slice + 1) - off) >> 6;
+			p_src = (const unsigned char*) (heT + off);
+		}
+		uint64_t* bar = &full[p_q & (LN_STAGES - 1)];
+		mbar_expect_tx(bar, LN_PAIR_BYTES);
+		bulk_g2s(ring[p_q & (LN_STAGES - 1)], p_src, LN_PAIR_BYTES, bar);
+		p_src += LN_PAIR_BYTES;
+		p_left--;
+		p_q++;
+	};
+	if (lane == 0)
+		for (int q = 0; q < LN_STAGES && q < Ptot; q++) produce();
 	double2 nkg1 = make_double2(0.0, 0.0);
 	if (PAL1) nkg1 = __ldg(palf);
-	const Force3 F = lane_spring_sum<UNI, PAL1, true>((const int4*) heT + off + lane, P, nt, ni, nodes, palf, nkg1);
-	if (!live || (lane & (SPRING_LANES - 1)) != 0) return;
-	vec4d a;
-	if (ZERO_FIRST) { a.x = 0.0; a.y = 0.0; a.z = 0.0; a.w = 0.0; }
-	else a = acc[node];
-	finish_node<KICK>(F, gi.y > 0, a, ni, node, k, acc, posm_out, vel_out, out, dt, pre_drift_next);
+	// ---- the slice this warp is on ----
+	int2 gi, gi_next;     // (rank, degree) of this lane's group; (-1, 0): padding group
+	int P_s, P_next;      // pairs of steps of the slice
+	int lp = 0, nt = 0, k = 0, node = 0;
+	bool live = false;
+	NodeState ni;
+	double ax = 0.0, ay = 0.0, az = 0.0;
+	auto read_header = [&](int sl, int2& g, int& P) {
+		g = __ldg(grp + (size_t) sl * GPW + lane / SPRING_LANES);
+		P = (__ldg(warp_off + sl + 1) - __ldg(warp_off + sl)) >> 6;
+	};
+	auto open_slice = [&]() {  // slice s: its header was read one slice ago
+		gi = gi_next; P_s = P_next;
+		if (s + LN_WARPS < s1) read_header(s + LN_WARPS, gi_next, P_next);
+		live = gi.x >= 0;
+		k = live ? gi.x : 0;
+		nt = (gi.y - sub + SPRING_LANES - 1) / SPRING_LANES;  // entries sub, sub + SPRING_LANES, ... of the row are this lane's
+		ni = nodes.get<false>(k);
+		node = __ldg(order + k);
+		if (!ZERO_FIRST) asm volatile("prefetch.global.L1 [%0];" ::"l"(acc + node));  // needed after the sum
+		lp = 0;
+		ax = 0.0; ay = 0.0; az = 0.0;
+	};
+	auto close_slice = [&]() {
+		fold_lanes(ax, ay, az);
+		if (live && sub == 0) {
+			vec4d a;
+			if (ZERO_FIRST) { a.x = 0.0; a.y = 0.0; a.z = 0.0; a.w = 0.0; }
+			else a = acc[node];
+			Force3 F;
+			F.x = ax; F.y = ay; F.z = az;
+			finish_node<KICK>(F, gi.y > 0, a, ni, node, k, acc, posm_out, vel_out, out, dt, pre_drift_next);
+		}
+	};
+	// after the arithmetic of a pair: step the slice; false when the warp's run is exhausted
+	auto retire = [&]() -> bool {
+		lp++;
+		if (lp + 1 == P_s && s + LN_WARPS < s1 && gi_next.x >= 0) {  // one pair to go: bring the next slice's own state close
+			asm volatile("prefetch.global.L1 [%0];" ::"l"(nodes.xy + gi_next.x));
+			asm volatile("prefetch.global.L1 [%0];" ::"l"(nodes.zv + gi_next.x));
+			asm volatile("prefetch.global.L1 [%0];" ::"l"(nodes.vxy + gi_next.x));
+		}
+		while (lp == P_s) {  // (a loop: slices without springs have no pairs)
+			close_slice();
+			if ((s += LN_WARPS) >= s1) return false;
+			open_slice();
+		}
+		return true;
+	};
+	auto fetch = [&](int q) {  // records of pair q out of the ring, their gathers issued, the stage refilled
+		const int st = q & (LN_STAGES - 1);
+		mbar_wait(&full[st], (uint32_t) ((q / LN_STAGES) & 1));
+		const int4 r0 = *(const int4*) (ring[st] + lane * 16);
+		const int4 r1 = *(const int4*) (ring[st] + 512 + lane * 16);
+		PairOperands o;
+		o.rs0[0] = __hiloint2double(r0.y, r0.x); o.rs0[1] = __hiloint2double(r1.y, r1.x);
+		o.pal[0] = r0.w; o.pal[1] = r1.w;
+		o.nj[0] = nodes.get<UNI>(r0.z);
+		o.nj[1] = nodes.get<UNI>(r1.z);
+		// the gathers above could not be issued before the whole warp's record reads had returned: the stage is free
+		__syncwarp();
+		if (lane == 0 && q + LN_STAGES < Ptot) produce();
+		return o;
+	};
+	auto compute = [&](const PairOperands& o) {
+		const bool valid[2] = { 2 * lp < nt, 2 * lp + 1 < nt };
+		const double2 nkg[2] = { PAL1 ? nkg1 : __ldg(palf + o.pal[0]), PAL1 ? nkg1 : __ldg(palf + o.pal[1]) };
+		half_edges_accumulate<2, UNI>(o.rs0, nkg, o.nj, valid, ni, ax, ay, az);
+	};
+	read_header(s, gi_next, P_next);
+	open_slice();
+	while (P_s == 0) {  // leading slices without springs
+		close_slice();
+		if ((s += LN_WARPS) >= s1) return;
+		open_slice();
+	}
+	PairOperands A = fetch(0), B;
+	for (int p = 0; p < Ptot; p += 2) {
+		if (p + 1 < Ptot) B = fetch(p + 1);
+		compute(A);
+		if (!retire()) break;
+		if (p + 2 < Ptot) A = fetch(p + 2);
+		compute(B);
+		if (!retire()) break;
+	}
 }
 
 // *differs = 1 if two nodes that carry springs have masses with different bits (rows are by rank, masses by node)
@@ -195,18 +317,69 @@ static void launch_csr(ass_sim* s, bool zero_first, bool uni, int lo, int hi, do
 #undef ASS_CSR
 }
 
+// Cut the slices into one contiguous run per CTA, of equal weight (pairs of steps + a constant per slice for the
+// boundary work): a CTA's share of the work, not of the slice count, is what must be equal -- surface slices carry half
+// the springs of interior ones.  wpairs[c * LN_WARPS + w] = pairs of steps of warp w's slices.  Cached per (grid, list).
+static int ensure_cta_cuts(ass_sim* s, int grid) {
+	if (s->ccut && s->ccut_grid == grid && s->ccut_epoch == s->spring_epoch) return ASS_OK;
+	const int ns = s->n_swarps;
+	auto pairs = [&](int w) { return (s->h_warp_off[(size_t) w + 1] - s->h_warp_off[w]) >> 6; };
+	std::vector<double> prefix((size_t) ns + 1, 0.0);
+	for (int w = 0; w < ns; w++) prefix[(size_t) w + 1] = prefix[w] + (double) pairs(w) + 0.75;
+	std::vector<int> cut((size_t) grid + 1 + (size_t) grid * LN_WARPS, 0);  // [cuts | wpairs]
+	int w = 0;
+	for (int c = 1; c < grid; c++) {
+		const double target = prefix[ns] * (double) c / (double) grid;
+		while (w < ns && prefix[(size_t) w + 1] <= target) w++;
+		// the boundary slice goes to whichever side leaves the smaller error
+		if (w < ns && target - prefix[w] > prefix[(size_t) w + 1] - target) w++;
+		cut[c] = std::max(w, cut[(size_t) c - 1]);
+	}
+	cut[grid] = ns;
+	for (int c = 0; c < grid; c++)
+		for (int sl = cut[c]; sl < cut[(size_t) c + 1]; sl++) cut[(size_t) grid + 1 + (size_t) c * LN_WARPS + (sl - cut[c]) % LN_WARPS] += pairs(sl);
+	if (cut.size() > s->ccut_cap) {
+		cudaFree(s->ccut);
+		s->ccut = nullptr; s->ccut_cap = 0;
+		if (cudaMalloc(&s->ccut, sizeof(int) * cut.size()) != cudaSuccess) {
+			cudaGetLastError();
+			ass_set_error("out of device memory for %zu slice cuts", cut.size());
+			return ASS_ENOMEM;
+		}
+		s->ccut_cap = cut.size();
+	}
+	CU_TRY(cudaMemcpyAsync(s->ccut, cut.data(), sizeof(int) * cut.size(), cudaMemcpyHostToDevice, s->stream));
+	CU_TRY(cudaStreamSynchronize(s->stream));
+	s->ccut_grid = grid;
+	s->ccut_epoch = s->spring_epoch;
+	return ASS_OK;
+}
+
+template <bool ZERO_FIRST, bool KICK, bool UNI, bool PAL1>
+static int launch_lanes_t(ass_sim* s, double dt, int pre) {
+	auto kern = k_spring_lanes<ZERO_FIRST, KICK, UNI, PAL1>;
+	static int ctas_per_sm = 0;  // per instantiation
+	constexpr size_t smem = (size_t) LN_WARPS * LN_STAGES * LN_PAIR_BYTES;
+	if (ctas_per_sm == 0) {
+		CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+		CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, LN_THREADS, smem));
+		if (ctas_per_sm < 1) ctas_per_sm = 1;
+	}
+	const int grid = std::max(1, std::min((s->n_swarps + LN_WARPS - 1) / LN_WARPS, ass_sm_count() * ctas_per_sm));
+	int rc = ensure_cta_cuts(s, grid);
+	if (rc) return rc;
+	kern<<<grid, LN_THREADS, smem, s->stream>>>(mirror_nodes(s), s->order, s->acc, s->grp, s->warp_off, s->ccut, s->ccut + grid + 1, s->heT, s->palf,
+			KICK ? s->posm_alt : nullptr, KICK ? s->vel_alt : nullptr, s->mir_alt, dt, pre);
+	return ASS_OK;
+}
+
 template <bool KICK>
-static void launch_lanes(ass_sim* s, bool zero_first, bool uni, double dt, int pre) {
-	const int grid = (s->n_swarps * 32 + LN_THREADS - 1) / LN_THREADS;
-	const bool pals = s->n_pal == 1;
-#define ASS_LANES(Z, U, PS)                                                                                                                   \
-	k_spring_lanes<Z, KICK, U, PS><<<grid, LN_THREADS, 0, s->stream>>>(mirror_nodes(s), s->order, s->acc, s->grp, s->warp_off, s->heT, s->palf,    \
-			s->n_swarps, KICK ? s->posm_alt : nullptr, KICK ? s->vel_alt : nullptr, s->mir_alt, dt, pre)
-#define ASS_LANES_U(Z, U) do { if (pals) ASS_LANES(Z, U, true); else ASS_LANES(Z, U, false); } while (0)
-	if (zero_first) { if (uni) ASS_LANES_U(true, true); else ASS_LANES_U(true, false); }
-	else { if (uni) ASS_LANES_U(false, true); else ASS_LANES_U(false, false); }
+static int launch_lanes(ass_sim* s, bool zero_first, bool uni, double dt, int pre) {
+	const bool pal1 = s->n_pal == 1;
+#define ASS_LANES_U(Z, U) (pal1 ? launch_lanes_t<Z, KICK, U, true>(s, dt, pre) : launch_lanes_t<Z, KICK, U, false>(s, dt, pre))
+	if (zero_first) return uni ? ASS_LANES_U(true, true) : ASS_LANES_U(true, false);
+	return uni ? ASS_LANES_U(false, true) : ASS_LANES_U(false, false);
 #undef ASS_LANES_U
-#undef ASS_LANES
 }
 
 // ASS_SPRINGS_NO_STREAM=1 runs the whole-body evaluations on the CSR kernel instead (same bits: tests)
@@ -244,7 +417,7 @@ int ass_launch_spring_forces(ass_sim* s, bool zero_first, bool mirror_fresh) {
 	ass_tic(s, ASS_K_SPRINGS);
 	if (!mirror_fresh && (rc = launch_mirror(s))) return rc;
 	if (use_csr_kernel()) launch_csr<false, false>(s, zero_first, uni, 0, s->n, 0.0, 0);
-	else launch_lanes<false>(s, zero_first, uni, 0.0, 0);
+	else if ((rc = launch_lanes<false>(s, zero_first, uni, 0.0, 0))) return rc;
 	LAUNCH_CHECK();
 	ass_toc(s, ASS_K_SPRINGS);
 	return ASS_OK;
@@ -258,7 +431,7 @@ int ass_launch_spring_kick_drift(ass_sim* s, bool zero_first, double dt, bool pr
 	ass_tic(s, ASS_K_SPRINGS);
 	if (!mirror_fresh && (rc = launch_mirror(s))) return rc;
 	if (use_csr_kernel()) launch_csr<true, false>(s, zero_first, uni, 0, s->n, dt, pre_drift_next ? 1 : 0);
-	else launch_lanes<true>(s, zero_first, uni, dt, pre_drift_next ? 1 : 0);
+	else if ((rc = launch_lanes<true>(s, zero_first, uni, dt, pre_drift_next ? 1 : 0))) return rc;
 	LAUNCH_CHECK();
 	ass_toc(s, ASS_K_SPRINGS);
 	std::swap(s->posm, s->posm_alt);

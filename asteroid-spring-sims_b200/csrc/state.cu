@@ -337,7 +337,7 @@ extern "C" int ass_destroy(ass_sim* s) {
 	if (s->stream) cudaStreamSynchronize(s->stream);
 	ass_shard_release(s);  // a sharded simulation's posm / vel alias its exported window
 	ass_sym_plans_free(s);
-	cudaFree(s->heT); cudaFree(s->slotT); cudaFree(s->grp); cudaFree(s->warp_off);
+	cudaFree(s->heT); cudaFree(s->slotT); cudaFree(s->grp); cudaFree(s->warp_off); cudaFree(s->ccut);
 	cudaFree(s->order); cudaFree(s->rank); cudaFree(s->mir_block); cudaFree(s->mir_m);
 	cudaFree(s->posm); cudaFree(s->vel); cudaFree(s->acc); cudaFree(s->posm_alt); cudaFree(s->vel_alt);
 	cudaFree(s->he); cudaFree(s->row_ptr); cudaFree(s->slot); cudaFree(s->pal);
@@ -689,7 +689,7 @@ int reserve_array(T*& ptr, size_t& cap, size_t need, const char* what) {
 void ass_morton_order(const vec4d* pos, size_t n, std::vector<int>& order) { morton_order(pos, n, order); }
 
 // Host-side construction of everything the spring kernels read (common.cuh: SpringLayout): spatial ranking, CSR rows
-// by rank with each row sorted by neighbour rank, and the lane-transposed copy.  Shared by ass_set_springs and the
+// by rank (rows ordered bank-group-aware, see below), and the lane-transposed copy.  Shared by ass_set_springs and the
 // ensemble (one layout per member), so a member sums in the same order as the single-body path and gets the same bits.
 // pidx[q] = palette index of spring q; *bad_spring = first spring with an endpoint outside [0, n) or i == j, else -1.
 int ass_build_spring_layout(const vec4d* pos, int n, const ass_spring* sp, int ns, const int* pidx, SpringLayout& out, int* bad_spring) {
@@ -730,17 +730,6 @@ int ass_build_spring_layout(const vec4d* pos, int n, const ass_spring* sp, int n
 		}
 	}
 	for (int k = 0; k < n; k++) std::sort(ent.begin() + row[k], ent.begin() + row[(size_t) k + 1]);
-	out.he.resize(nhe);
-	out.slot.resize(nhe);
-	for (size_t at = 0; at < nhe; at++) {
-		const int q = ent[at].second >> 1;
-		HalfEdge h;
-		h.rs0 = sp[q].rs0;
-		h.nbr = ent[at].first;
-		h.pal = pidx[(size_t) q];
-		out.he[at] = h;
-		out.slot[(size_t) ent[at].second] = (int) at;
-	}
 	// ---- the lane-transposed copy (common.cuh: ass_sim::heT) ----
 	// nodes -> lane groups: inside every block of ASS_SORT_BLOCK ranks, by decreasing degree (ties: by rank)
 	constexpr int L = SPRING_LANES, GPW = 32 / SPRING_LANES;
@@ -752,6 +741,77 @@ int ass_build_spring_layout(const vec4d* pos, int n, const ass_spring* sp, int n
 		const int b1 = std::min(n, b0 + ASS_SORT_BLOCK);
 		for (int k = b0; k < b1; k++) grp[(size_t) k] = make_int2(k, row[(size_t) k + 1] - row[k]);
 		std::stable_sort(grp.begin() + b0, grp.begin() + b1, [](const int2& x, const int2& y) { return x.y > y.y; });
+	}
+	// ---- order inside the rows: spread every step's gathers over the eight 16-byte bank groups ----
+	// Eight consecutive lanes (a quarter warp: QG = 8 / SPRING_LANES groups, i.e. QG nodes) are served together by the
+	// L1 / shared-memory data array, 128 bytes per pass; their eight 16-byte gathers of a step take one pass only if the
+	// eight neighbour ranks differ mod 8.  With rows simply sorted by neighbour rank a step costs ~2.1 passes (measured).
+	// So the rows of the QG nodes that share a quarter warp are re-ordered TOGETHER, step by step: each bank group goes
+	// to the row that has most entries left in it (greedy, groups with the fullest rows first), a row short of
+	// distinct groups takes what it has left; inside a step entries stay in ascending rank.  The order of a row is the
+	// order of its sum, in every kernel (spring_math.cuh): deterministic, a function of the spring list and positions.
+	{
+		constexpr int QG = 8 / SPRING_LANES;
+		std::vector<std::pair<int, int>> bucket[QG][8], picked[QG];
+		size_t taken[QG][8];
+		for (size_t q0 = 0; q0 < n_grp; q0 += QG) {
+			int left[QG], written[QG];
+			bool any = false;
+			for (int r = 0; r < QG; r++) {
+				const int2 g = grp[q0 + r];
+				left[r] = g.x >= 0 ? g.y : 0;
+				written[r] = 0;
+				for (int c = 0; c < 8; c++) { bucket[r][c].clear(); taken[r][c] = 0; }
+				if (left[r] > 0) {
+					any = true;
+					for (int e = row[g.x]; e < row[(size_t) g.x + 1]; e++) bucket[r][ent[(size_t) e].first & 7].push_back(ent[(size_t) e]);
+				}
+			}
+			if (!any) continue;
+			auto remaining = [&](int r, int c) { return (int) (bucket[r][c].size() - taken[r][c]); };
+			while (true) {
+				int need[QG], total_need = 0;
+				for (int r = 0; r < QG; r++) { need[r] = std::min(L, left[r]); total_need += need[r]; picked[r].clear(); }
+				if (total_need == 0) break;
+				int corder[8];
+				for (int c = 0; c < 8; c++) corder[c] = c;
+				std::stable_sort(corder, corder + 8, [&](int a, int b) {
+					int ma = 0, mb = 0;
+					for (int r = 0; r < QG; r++) { ma = std::max(ma, remaining(r, a)); mb = std::max(mb, remaining(r, b)); }
+					return ma > mb;
+				});
+				for (int ci = 0; ci < 8; ci++) {
+					const int c = corder[ci];
+					int best = -1, best_left = 0;
+					for (int r = 0; r < QG; r++)
+						if ((int) picked[r].size() < need[r] && remaining(r, c) > best_left) { best = r; best_left = remaining(r, c); }
+					if (best >= 0) picked[best].push_back(bucket[best][c][taken[best][c]++]);
+				}
+				for (int r = 0; r < QG; r++) {
+					while ((int) picked[r].size() < need[r]) {  // not enough distinct groups left: take from the fullest
+						int c_best = 0;
+						for (int c = 1; c < 8; c++)
+							if (remaining(r, c) > remaining(r, c_best)) c_best = c;
+						picked[r].push_back(bucket[r][c_best][taken[r][c_best]++]);
+					}
+					std::sort(picked[r].begin(), picked[r].end());
+					const int2 g = grp[q0 + r];
+					for (auto& pe : picked[r]) ent[(size_t) row[g.x] + written[r]++] = pe;
+					left[r] -= need[r];
+				}
+			}
+		}
+	}
+	out.he.resize(nhe);
+	out.slot.resize(nhe);
+	for (size_t at = 0; at < nhe; at++) {
+		const int q = ent[at].second >> 1;
+		HalfEdge h;
+		h.rs0 = sp[q].rs0;
+		h.nbr = ent[at].first;
+		h.pal = pidx[(size_t) q];
+		out.he[at] = h;
+		out.slot[(size_t) ent[at].second] = (int) at;
 	}
 	std::vector<int>& warp_off = out.warp_off;
 	warp_off.assign((size_t) n_swarps + 1, 0);
@@ -860,6 +920,7 @@ extern "C" int ass_set_springs(ass_sim* s, const ass_spring* sp, int ns) {
 	s->n_he = (int) nhe;
 	s->n_heT = (long long) n_heT;
 	s->n_swarps = (int) lay.warp_off.size() - 1;
+	s->h_warp_off = lay.warp_off;
 	s->max_degree = lay.max_degree;
 	s->spring_epoch++;
 	return ASS_OK;
