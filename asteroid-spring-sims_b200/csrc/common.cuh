@@ -130,27 +130,29 @@ struct ass_sim {
 	double2* mir_block = nullptr;  // the one allocation behind mir and mir_alt
 	double* mir_m = nullptr;
 	size_t sorted_cap = 0;
-	// The lane-transposed copy of the half-edge list, read by the whole-body spring kernel (springs.cu: k_spring_lanes).
-	// Groups of SPRING_LANES lanes own one node; 32 / SPRING_LANES groups make a warp; within blocks of ASS_SORT_BLOCK
-	// ranks the nodes are dealt to groups in order of decreasing degree, so the groups of a warp have rows of similar
-	// length.  grp[g] = (rank, degree) of group g, (-1, 0) for padding groups.  Warp w owns records
-	// [warp_off[w], warp_off[w+1]): step t of lane l is record warp_off[w] + 32 t + l, so a warp reads 512 contiguous
-	// bytes per step; lane l of a group takes entries l, l + SPRING_LANES, ... of its node's row; rows are padded (with
-	// records that are loaded but never accumulated) to the warp's longest, rounded up to an even number of steps.
-	HalfEdge* heT = nullptr;
-	int* slotT = nullptr;     // 2*ns: position in heT of (spring s, endpoint e)
-	int2* grp = nullptr;
+	// The lane-transposed copy of the half-edge list, read by the whole-body spring kernel (springs.cu: k_spring_tiles)
+	// and, per member, by the ensemble kernel.  Groups of SPRING_LANES lanes own one node; 32 / SPRING_LANES groups make
+	// a warp's SLICE; within blocks of ASS_SORT_BLOCK ranks the nodes are dealt to groups in order of decreasing degree,
+	// so the groups of a slice have rows of similar length.  Slice w owns records [warp_off[w], warp_off[w+1]): step t of
+	// lane l is record warp_off[w] + 32 t + l, so a warp reads 512 contiguous bytes per step; lane l of a group takes
+	// entries l, l + SPRING_LANES, ... of its node's row; rows are padded (with records that are loaded and computed but
+	// enter the sum with a zero coefficient) to the slice's longest, rounded up to an even number of steps.
+	int* slotT = nullptr;     // 2*ns: position in the lane-transposed copy of (spring s, endpoint e)
 	int* warp_off = nullptr;  // n_swarps + 1
 	int n_swarps = 0;
-	std::vector<int> h_warp_off;  // host copy of warp_off
-	// which slices each persistent CTA of the lane kernel takes: ccut[c] .. ccut[c+1], followed by the per-warp pair
-	// counts (springs.cu: ensure_cta_cuts)
-	int* ccut = nullptr;
-	size_t ccut_cap = 0;
-	int ccut_grid = 0;
-	long long ccut_epoch = -1;
-	size_t heT_cap = 0, grp_cap = 0, swarp_cap = 0;
-	long long n_heT = 0;
+	size_t swarp_cap = 0;
+	// On the device the copy lives in the tiled kernel's form: every persistent CTA's run of slices is cut into TILES
+	// whose nodes AND their neighbours fit in shared memory; tile_tab lists each tile's table (slot -> rank, -1: unused;
+	// slot = rank mod 8, so the bank-group-aware row order survives), heL holds the records with HalfEdge::nbr renumbered
+	// to table slots, grpT[g] = (slot, rank, degree, node) of lane group g, (-1, -1, 0, 0) for padding groups.  Built by
+	// ass_set_springs for one CTA per SM.
+	HalfEdge* heL = nullptr;
+	int4* grpT = nullptr;
+	int* tile_tab = nullptr;
+	int4* tile_desc = nullptr;  // (first slice, end slice, offset into tile_tab, slots)
+	int* cta_tile = nullptr;    // tiles_grid + 1: CTA c takes tiles [cta_tile[c], cta_tile[c+1])
+	int tiles_grid = 0, tile_slots_max = 0, tile_slices_max = 0;
+	size_t heL_cap = 0, grpT_cap = 0, tile_tab_cap = 0, tile_desc_cap = 0, cta_tile_cap = 0;
 	double2* pal = nullptr;   // palette of distinct (k, gamma) pairs
 	double2* palf = nullptr;  // the same entries as the force kernels want them: (-k, -max(gamma, 0)); lives behind pal
 	int n_pal = 0;
@@ -195,6 +197,7 @@ struct SpringLayout {
 	int max_degree = 0;
 };
 int ass_build_spring_layout(const vec4d* pos, int n, const ass_spring* sp, int ns, const int* pidx, SpringLayout& out, int* bad_spring);
+int ass_build_spring_tiles(ass_sim* s, const SpringLayout& lay);  // springs.cu; queues uploads on s->stream and waits for them
 int ass_ensure_device(void);
 int ass_sm_count(void);
 

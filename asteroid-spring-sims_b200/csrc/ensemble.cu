@@ -46,21 +46,6 @@ __device__ __forceinline__ vec4d ldcg4(const vec4d* p) {
 	return r;
 }
 
-// endpoint state out of shared memory: three 16-byte reads per endpoint, plus the mass only when the member's masses
-// differ (with equal masses the arithmetic never looks at the neighbour's).  16-byte entries start on all eight bank
-// groups; a random gather of 32-byte entries would start on only four (8-way conflicts).
-struct SharedNodes {
-	const double2 *xy, *zv, *vxy;
-	const double* m;
-	template <bool UNI>
-	__device__ __forceinline__ NodeState get(int i) const {
-		NodeState s;
-		s.xy = xy[i]; s.zv = zv[i]; s.vxy = vxy[i];
-		s.m = UNI ? 0.0 : m[i];
-		return s;
-	}
-};
-
 // Work is handed out in ITEMS = (member b, batch j of `item_steps` consecutive steps), numbered j * n_bodies + b and
 // pulled from one atomic counter by persistent CTAs (one per SM).  With one CTA per member for the whole run, 512
 // members on 148 SMs take 4 rounds of which the last is half empty (86 % at BASELINE C5 on 8 GPUs); with items the

@@ -99,171 +99,87 @@ __global__ void __launch_bounds__(BLOCK) k_spring_forces(const GlobalNodes nodes
 }
 
 // ---------------------------------------------------------------------------------------------------
-// The lane kernel (whole body): reads the lane-transposed copy of the half-edge list (ass_sim::heT, common.cuh).
+// The tiled kernel (whole body; the default): reads the lane-transposed copy of the half-edge list (common.cuh).
 //
 // A warp owns 32 / SPRING_LANES nodes of similar degree -- a SLICE -- and walks their rows in lock step: step t of lane
-// l is ONE record at heT[warp_off + 32 t + l], so a step of the warp is 512 contiguous bytes and the trip count is
-// the same for every lane (no votes, no divergence, no per-row bookkeeping).  CTAs are persistent, one per SM: CTA c owns
-// the contiguous run of slices [ccut[c], ccut[c+1]) (cut on the host so that every CTA carries the same number of step
-// pairs) and its sixteen warps take them round-robin, so at any moment the whole SM works on ~128 nodes that are
-// neighbours in space and the L1 holds one neighbourhood, not sixteen.  A slice's records are one contiguous run of
-// heT: each warp streams its records through a private ring in shared memory with the bulk-copy engine
-// (cp.async.bulk -> mbarrier, SASS UBLKCP; LN_STAGES pairs of steps = 4 KB ahead, across its slices; producer and
-// consumer are the same warp, so handing a stage back needs no second barrier), and its software
-// pipeline -- records of pair p+1 out of the ring, their endpoint gathers issued, arithmetic of pair p (two interleaved
-// FP64 chains per lane, spring_math.cuh) -- runs straight across slice boundaries: at a boundary the warp folds its
-// partial sums, runs the node epilogue (acc, optionally kick + drift + mirror) and switches to the next slice's nodes,
-// whose header was read one slice ago and whose state was prefetched one pair ago.  The only exposed memory latency
-// of a warp is that of its very first pair.
-// The loop is unrolled by two over explicit operand sets A / B so that the pipeline costs no register moves.
+// l is ONE record at warp_off + 32 t + l, so a step of the warp is 512 contiguous bytes and the trip count is the same
+// for every lane (no votes, no divergence, no per-row bookkeeping; spring_math.cuh: lane_spring_sum).
+// Endpoint state comes out of SHARED memory.  Gathering it through L1 (an earlier version of this kernel) is bounded
+// by latency: even at a 90 % L1 hit rate nearly every warp-wide request contains a miss, and ~120 registers per thread
+// leave four warps per scheduler to hide it; the ensemble kernel, which gathers from shared memory, spends half the
+// time per half-edge.  So the body is treated like an ensemble of TILES.  CTAs are persistent, one per SM; CTA c owns
+// a contiguous run of slices (cut on the host so that every CTA carries the same number of step pairs), cut further
+// into tiles whose nodes AND all their neighbours (~3 x as many: 14 MB of L2 reads per evaluation at C3) fit in a
+// shared-memory table.  Per tile the CTA copies that state from the rank-ordered mirror into the table (and the
+// tile's slice headers next to it), then its sixteen warps pull slices from a counter -- no warp waits for a longer
+// share -- and run the arithmetic with table slots in place of ranks (heL: records renumbered on the host, slot =
+// rank mod 8 so the bank-group-aware row order still holds).  Records come straight from L2 / HBM, one pair of steps
+// ahead of the arithmetic, and a slice's records are requested into L2 while the slice before it is worked on.
 // Padding records (rows shorter than the slice's longest) point at the node itself and enter the sum with a zero
-// coefficient.  The L1 is left to the endpoint gathers: 16-byte reads of the rank-ordered mirror -- a group's
-// SPRING_LANES lanes read consecutive entries of a row sorted by neighbour rank, i.e. mostly one or two cache lines.
+// coefficient.  Same rows, same lanes, same order of summation as the CSR kernel: identical bits (tests).
+// (Streaming the records through per-warp bulk-copy rings, with the slices dealt round-robin so a warp's stream is
+// known in advance, was built and measured slower -- 32 us against 28 at C3: the polling and the fixed shares cost more
+// than the deeper prefetch saves.)
 // ---------------------------------------------------------------------------------------------------
-#ifndef ASS_LANES_THREADS
-#define ASS_LANES_THREADS 512
-#endif
-#ifndef ASS_LANES_MINBLOCKS
-#define ASS_LANES_MINBLOCKS 1
-#endif
-#ifndef ASS_LANES_STAGES
-#define ASS_LANES_STAGES 4
-#endif
-constexpr int LN_THREADS = ASS_LANES_THREADS;
-constexpr int LN_WARPS = LN_THREADS / 32;
-constexpr int LN_STAGES = ASS_LANES_STAGES;  // power of two
-constexpr int LN_PAIR_BYTES = 64 * (int) sizeof(HalfEdge);  // two steps of a warp
-static_assert((LN_STAGES & (LN_STAGES - 1)) == 0, "LN_STAGES must be a power of two");
+constexpr int TL_THREADS = 512;
 constexpr int GPW = 32 / SPRING_LANES;
+struct TileDesc {
+	int s0, s1, tab_off, n_slots;
+};
+static_assert(sizeof(TileDesc) == sizeof(int4), "TileDesc is uploaded as int4");
 
 template <bool ZERO_FIRST, bool KICK, bool UNI, bool PAL1>
-__global__ void __launch_bounds__(LN_THREADS, ASS_LANES_MINBLOCKS) k_spring_lanes(const GlobalNodes nodes, const int* __restrict__ order,
-		vec4d* __restrict__ acc, const int2* __restrict__ grp, const int* __restrict__ warp_off, const int* __restrict__ ccut, const int* __restrict__ wpairs,
-		const HalfEdge* __restrict__ heT, const double2* __restrict__ palf, vec4d* __restrict__ posm_out, vec4d* __restrict__ vel_out,
-		const SpringMirror out, double dt, int pre_drift_next) {
-	extern __shared__ __align__(128) unsigned char ring_all[];  // [LN_WARPS][LN_STAGES][LN_PAIR_BYTES]
-	__shared__ __align__(8) uint64_t full_all[LN_WARPS][LN_STAGES];
-	const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
-	const int sub = lane & (SPRING_LANES - 1);
-	unsigned char(*ring)[LN_PAIR_BYTES] = (unsigned char(*)[LN_PAIR_BYTES]) (ring_all + (size_t) wi * LN_STAGES * LN_PAIR_BYTES);
-	uint64_t* full = full_all[wi];
-	if (lane == 0) {
-#pragma unroll
-		for (int q = 0; q < LN_STAGES; q++) mbar_init(&full[q], 1);
-		mbar_fence_init();
-	}
-	__syncwarp();
-	// this CTA's slices: [c0, s1); warp wi takes c0 + wi, c0 + wi + LN_WARPS, ...
-	const int c0 = ccut[blockIdx.x], s1 = ccut[blockIdx.x + 1];
-	int s = c0 + wi;
-	const int Ptot = wpairs[blockIdx.x * LN_WARPS + wi];  // pairs of steps over all of this warp's slices
-	if (s >= s1) return;  // whole warps
-	// lane 0 only: the producer's cursor runs up to LN_STAGES pairs ahead of the consumers, through the same slices
-	int p_slice = s - LN_WARPS, p_left = 0;
-	const unsigned char* p_src = nullptr;
-	int p_q = 0;
-	auto produce = [&]() {  // the next pair of the warp's stream -> ring stage p_q % LN_STAGES
-		while (p_left == 0) {  // (a loop: slices without springs have no pairs; Ptot bounds the calls, so a slice exists)
-			p_slice += LN_WARPS;
-			const int off = __ldg(warp_off + p_slice);
-			p_left = (__ldg(warp_off + p_slice + 1) - off) >> 6;
-			p_src = (const unsigned char*) (heT + off);
-		}
-		uint64_t* bar = &full[p_q & (LN_STAGES - 1)];
-		mbar_expect_tx(bar, LN_PAIR_BYTES);
-		bulk_g2s(ring[p_q & (LN_STAGES - 1)], p_src, LN_PAIR_BYTES, bar);
-		p_src += LN_PAIR_BYTES;
-		p_left--;
-		p_q++;
-	};
-	if (lane == 0)
-		for (int q = 0; q < LN_STAGES && q < Ptot; q++) produce();
+__global__ void __launch_bounds__(TL_THREADS, 1) k_spring_tiles(const GlobalNodes mir, vec4d* __restrict__ acc, const TileDesc* __restrict__ tiles,
+		const int* __restrict__ cta_tile, const int* __restrict__ tab, const int4* __restrict__ grpT, const int* __restrict__ warp_off,
+		const HalfEdge* __restrict__ heL, const double2* __restrict__ palf, int cap, int max_slices, vec4d* __restrict__ posm_out,
+		vec4d* __restrict__ vel_out, const SpringMirror out, double dt, int pre_drift_next) {
+	extern __shared__ __align__(128) unsigned char tile_smem[];  // [table: xy | zv | vxy | m, cap slots each][headers: groups | record offsets]
+	__shared__ int s_next;
+	double2* s_xy = (double2*) tile_smem;
+	double2* s_zv = s_xy + cap;
+	double2* s_vxy = s_zv + cap;
+	double* s_m = (double*) (s_vxy + cap);
+	int4* s_grp = (int4*) (s_m + cap);                 // max_slices * GPW
+	int* s_off = (int*) (s_grp + (size_t) max_slices * GPW);  // max_slices + 1
+	const SharedNodes nodes{ s_xy, s_zv, s_vxy, s_m };
+	const int tid = threadIdx.x, lane = tid & 31, sub = lane & (SPRING_LANES - 1);
 	double2 nkg1 = make_double2(0.0, 0.0);
 	if (PAL1) nkg1 = __ldg(palf);
-	// ---- the slice this warp is on ----
-	int2 gi, gi_next;     // (rank, degree) of this lane's group; (-1, 0): padding group
-	int P_s, P_next;      // pairs of steps of the slice
-	int lp = 0, nt = 0, k = 0, node = 0;
-	bool live = false;
-	NodeState ni;
-	double ax = 0.0, ay = 0.0, az = 0.0;
-	auto read_header = [&](int sl, int2& g, int& P) {
-		g = __ldg(grp + (size_t) sl * GPW + lane / SPRING_LANES);
-		P = (__ldg(warp_off + sl + 1) - __ldg(warp_off + sl)) >> 6;
-	};
-	auto open_slice = [&]() {  // slice s: its header was read one slice ago
-		gi = gi_next; P_s = P_next;
-		if (s + LN_WARPS < s1) read_header(s + LN_WARPS, gi_next, P_next);
-		live = gi.x >= 0;
-		k = live ? gi.x : 0;
-		nt = (gi.y - sub + SPRING_LANES - 1) / SPRING_LANES;  // entries sub, sub + SPRING_LANES, ... of the row are this lane's
-		ni = nodes.get<false>(k);
-		node = __ldg(order + k);
-		if (!ZERO_FIRST) asm volatile("prefetch.global.L1 [%0];" ::"l"(acc + node));  // needed after the sum
-		lp = 0;
-		ax = 0.0; ay = 0.0; az = 0.0;
-	};
-	auto close_slice = [&]() {
-		fold_lanes(ax, ay, az);
-		if (live && sub == 0) {
-			vec4d a;
-			if (ZERO_FIRST) { a.x = 0.0; a.y = 0.0; a.z = 0.0; a.w = 0.0; }
-			else a = acc[node];
-			Force3 F;
-			F.x = ax; F.y = ay; F.z = az;
-			finish_node<KICK>(F, gi.y > 0, a, ni, node, k, acc, posm_out, vel_out, out, dt, pre_drift_next);
+	for (int t = cta_tile[blockIdx.x]; t < cta_tile[blockIdx.x + 1]; t++) {
+		const TileDesc T = tiles[t];
+		const int n_sl = T.s1 - T.s0;
+		__syncthreads();  // everyone has left the previous tile (its table, headers and s_next)
+		for (int i = tid; i < T.n_slots; i += TL_THREADS) {
+			const int r = __ldg(tab + T.tab_off + i);
+			double2 a = make_double2(0.0, 0.0), b = a, c = a;
+			double m = 1.0;
+			if (r >= 0) { a = __ldcg(mir.xy + r); b = __ldcg(mir.zv + r); c = __ldcg(mir.vxy + r); m = __ldcg(mir.m + r); }
+			s_xy[i] = a; s_zv[i] = b; s_vxy[i] = c; s_m[i] = m;
 		}
-	};
-	// after the arithmetic of a pair: step the slice; false when the warp's run is exhausted
-	auto retire = [&]() -> bool {
-		lp++;
-		if (lp + 1 == P_s && s + LN_WARPS < s1 && gi_next.x >= 0) {  // one pair to go: bring the next slice's own state close
-			asm volatile("prefetch.global.L1 [%0];" ::"l"(nodes.xy + gi_next.x));
-			asm volatile("prefetch.global.L1 [%0];" ::"l"(nodes.zv + gi_next.x));
-			asm volatile("prefetch.global.L1 [%0];" ::"l"(nodes.vxy + gi_next.x));
+		for (int i = tid; i < n_sl * GPW; i += TL_THREADS) s_grp[i] = __ldg(grpT + (size_t) T.s0 * GPW + i);
+		for (int i = tid; i <= n_sl; i += TL_THREADS) s_off[i] = __ldg(warp_off + T.s0 + i);
+		if (tid == 0) s_next = 0;
+		__syncthreads();
+		while (true) {
+			int sw = 0;
+			if (lane == 0) sw = atomicAdd(&s_next, 1);
+			sw = __shfl_sync(0xffffffffu, sw, 0);
+			if (sw >= n_sl) break;
+			const int4 gi = s_grp[sw * GPW + lane / SPRING_LANES];  // (slot, rank, degree, node); slot < 0: padding group
+			const int off = s_off[sw];
+			const int P = (s_off[sw + 1] - off) >> 6;
+			// ask for the next slice's records (at most 4 KB = 32 lines; the counter hands it out next, to some warp of this CTA)
+			if (sw + 1 < n_sl && lane * 8 < s_off[sw + 2] - s_off[sw + 1]) asm volatile("prefetch.global.L2 [%0];" ::"l"(heL + s_off[sw + 1] + lane * 8));
+			const bool live = gi.x >= 0;
+			const int slot = live ? gi.x : 0;
+			const int nt = (gi.z - sub + SPRING_LANES - 1) / SPRING_LANES;  // entries sub, sub + SPRING_LANES, ... of the row are this lane's
+			vec4d a_old;
+			a_old.x = 0.0; a_old.y = 0.0; a_old.z = 0.0; a_old.w = 0.0;
+			if (!ZERO_FIRST && live && sub == 0) a_old = acc[gi.w];  // needed after the sum: requested now
+			const NodeState ni = nodes.get<false>(slot);
+			const Force3 F = lane_spring_sum<UNI, PAL1, false>((const int4*) heL + off + lane, P, nt, ni, nodes, palf, nkg1);
+			if (live && sub == 0) finish_node<KICK>(F, gi.z > 0, a_old, ni, gi.w, gi.y, acc, posm_out, vel_out, out, dt, pre_drift_next);
 		}
-		while (lp == P_s) {  // (a loop: slices without springs have no pairs)
-			close_slice();
-			if ((s += LN_WARPS) >= s1) return false;
-			open_slice();
-		}
-		return true;
-	};
-	auto fetch = [&](int q) {  // records of pair q out of the ring, their gathers issued, the stage refilled
-		const int st = q & (LN_STAGES - 1);
-		mbar_wait(&full[st], (uint32_t) ((q / LN_STAGES) & 1));
-		const int4 r0 = *(const int4*) (ring[st] + lane * 16);
-		const int4 r1 = *(const int4*) (ring[st] + 512 + lane * 16);
-		PairOperands o;
-		o.rs0[0] = __hiloint2double(r0.y, r0.x); o.rs0[1] = __hiloint2double(r1.y, r1.x);
-		o.pal[0] = r0.w; o.pal[1] = r1.w;
-		o.nj[0] = nodes.get<UNI>(r0.z);
-		o.nj[1] = nodes.get<UNI>(r1.z);
-		// the gathers above could not be issued before the whole warp's record reads had returned: the stage is free
-		__syncwarp();
-		if (lane == 0 && q + LN_STAGES < Ptot) produce();
-		return o;
-	};
-	auto compute = [&](const PairOperands& o) {
-		const bool valid[2] = { 2 * lp < nt, 2 * lp + 1 < nt };
-		const double2 nkg[2] = { PAL1 ? nkg1 : __ldg(palf + o.pal[0]), PAL1 ? nkg1 : __ldg(palf + o.pal[1]) };
-		half_edges_accumulate<2, UNI>(o.rs0, nkg, o.nj, valid, ni, ax, ay, az);
-	};
-	read_header(s, gi_next, P_next);
-	open_slice();
-	while (P_s == 0) {  // leading slices without springs
-		close_slice();
-		if ((s += LN_WARPS) >= s1) return;
-		open_slice();
-	}
-	PairOperands A = fetch(0), B;
-	for (int p = 0; p < Ptot; p += 2) {
-		if (p + 1 < Ptot) B = fetch(p + 1);
-		compute(A);
-		if (!retire()) break;
-		if (p + 2 < Ptot) A = fetch(p + 2);
-		compute(B);
-		if (!retire()) break;
 	}
 }
 
@@ -317,75 +233,161 @@ static void launch_csr(ass_sim* s, bool zero_first, bool uni, int lo, int hi, do
 #undef ASS_CSR
 }
 
-// Cut the slices into one contiguous run per CTA, of equal weight (pairs of steps + a constant per slice for the
-// boundary work): a CTA's share of the work, not of the slice count, is what must be equal -- surface slices carry half
-// the springs of interior ones.  wpairs[c * LN_WARPS + w] = pairs of steps of warp w's slices.  Cached per (grid, list).
-static int ensure_cta_cuts(ass_sim* s, int grid) {
-	if (s->ccut && s->ccut_grid == grid && s->ccut_epoch == s->spring_epoch) return ASS_OK;
-	const int ns = s->n_swarps;
-	auto pairs = [&](int w) { return (s->h_warp_off[(size_t) w + 1] - s->h_warp_off[w]) >> 6; };
+// shared memory per table slot of the tiled kernel: three 16-byte pairs and the mass
+constexpr size_t TILE_SLOT_BYTES = 3 * sizeof(double2) + sizeof(double);
+// the table's share of the SM's 227 KB; the rest holds the slice headers of the tile (a tile of TILE_SLOTS_LIMIT slots has
+// at most that many own nodes, i.e. TILE_SLOTS_LIMIT / GPW slices of 16 GPW + 4 bytes)
+constexpr int TILE_SLOTS_LIMIT = 2944;
+static_assert(TILE_SLOTS_LIMIT * TILE_SLOT_BYTES + (TILE_SLOTS_LIMIT / GPW + 2) * (16 * GPW + 4) + 4096 <= 227 * 1024, "tile does not fit in shared memory");
+
+template <class T>
+static int tiles_reserve(T*& ptr, size_t& cap, size_t need, const char* what) {
+	if (need <= cap && ptr) return ASS_OK;
+	cudaFree(ptr);
+	ptr = nullptr; cap = 0;
+	const size_t c = need + need / 8 + 64;
+	if (cudaMalloc(&ptr, sizeof(T) * c) != cudaSuccess) {
+		cudaGetLastError();
+		ass_set_error("out of device memory for %zu %s", c, what);
+		return ASS_ENOMEM;
+	}
+	cap = c;
+	return ASS_OK;
+}
+
+// Cut the slices into one run per CTA (equal weight: pairs of steps + a constant per slice for the boundary work) and every run into tiles whose node tables fit
+// in shared memory; renumber the records.  Host work proportional to the half-edge count, done once per spring list.
+int ass_build_spring_tiles(ass_sim* s, const SpringLayout& lay) {
+	s->tiles_grid = 0;
+	const int ns = (int) lay.warp_off.size() - 1;
+	const int n = (int) lay.rank.size();
+	if (ns <= 0 || lay.heT.empty()) return ASS_OK;
+	const int grid = std::max(1, std::min((ns + TL_THREADS / 32 - 1) / (TL_THREADS / 32), ass_sm_count()));
+	auto pairs = [&](int w) { return (lay.warp_off[(size_t) w + 1] - lay.warp_off[w]) >> 6; };
 	std::vector<double> prefix((size_t) ns + 1, 0.0);
 	for (int w = 0; w < ns; w++) prefix[(size_t) w + 1] = prefix[w] + (double) pairs(w) + 0.75;
-	std::vector<int> cut((size_t) grid + 1 + (size_t) grid * LN_WARPS, 0);  // [cuts | wpairs]
-	int w = 0;
-	for (int c = 1; c < grid; c++) {
-		const double target = prefix[ns] * (double) c / (double) grid;
-		while (w < ns && prefix[(size_t) w + 1] <= target) w++;
-		// the boundary slice goes to whichever side leaves the smaller error
-		if (w < ns && target - prefix[w] > prefix[(size_t) w + 1] - target) w++;
-		cut[c] = std::max(w, cut[(size_t) c - 1]);
-	}
-	cut[grid] = ns;
-	for (int c = 0; c < grid; c++)
-		for (int sl = cut[c]; sl < cut[(size_t) c + 1]; sl++) cut[(size_t) grid + 1 + (size_t) c * LN_WARPS + (sl - cut[c]) % LN_WARPS] += pairs(sl);
-	if (cut.size() > s->ccut_cap) {
-		cudaFree(s->ccut);
-		s->ccut = nullptr; s->ccut_cap = 0;
-		if (cudaMalloc(&s->ccut, sizeof(int) * cut.size()) != cudaSuccess) {
-			cudaGetLastError();
-			ass_set_error("out of device memory for %zu slice cuts", cut.size());
-			return ASS_ENOMEM;
+	std::vector<int> cut((size_t) grid + 1, 0);
+	{
+		int w = 0;
+		for (int c = 1; c < grid; c++) {
+			const double target = prefix[ns] * (double) c / (double) grid;
+			while (w < ns && prefix[(size_t) w + 1] <= target) w++;
+			if (w < ns && target - prefix[w] > prefix[(size_t) w + 1] - target) w++;
+			cut[c] = std::max(w, cut[(size_t) c - 1]);
 		}
-		s->ccut_cap = cut.size();
+		cut[grid] = ns;
 	}
-	CU_TRY(cudaMemcpyAsync(s->ccut, cut.data(), sizeof(int) * cut.size(), cudaMemcpyHostToDevice, s->stream));
+	std::vector<TileDesc> tiles;
+	std::vector<int> cta_tile((size_t) grid + 1, 0), tab;
+	std::vector<HalfEdge> heL(lay.heT);
+	std::vector<int4> grpT(lay.grp.size(), make_int4(-1, -1, 0, 0));
+	std::vector<int> stamp((size_t) n, -1), slot_of((size_t) n, -1), members, added;
+	int slots_max = 0, slices_max = 0;
+	for (int c = 0; c < grid; c++) {
+		cta_tile[c] = (int) tiles.size();
+		int sl = cut[c];
+		while (sl < cut[(size_t) c + 1]) {
+			// grow a tile slice by slice while its table (8 x the fullest class: slot = rank mod 8) fits
+			const int tile_id = (int) tiles.size();
+			int cnt[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+			members.clear();
+			const int s0 = sl;
+			while (sl < cut[(size_t) c + 1]) {
+				added.clear();
+				auto touch = [&](int r) {
+					if (stamp[(size_t) r] != tile_id) { stamp[(size_t) r] = tile_id; cnt[r & 7]++; added.push_back(r); }
+				};
+				for (int g = 0; g < GPW; g++) {
+					const int2 gi = lay.grp[(size_t) sl * GPW + g];
+					if (gi.x >= 0) touch(gi.x);
+				}
+				for (int at = lay.warp_off[sl]; at < lay.warp_off[(size_t) sl + 1]; at++) touch(lay.heT[(size_t) at].nbr);
+				const int need = 8 * *std::max_element(cnt, cnt + 8);
+				if (need > TILE_SLOTS_LIMIT && sl > s0) {  // does not fit any more: take the slice back, close the tile
+					for (int r : added) { stamp[(size_t) r] = -1; cnt[r & 7]--; }
+					break;
+				}
+				if (need > TILE_SLOTS_LIMIT) {
+					ass_set_error("ass_set_springs: one slice of %d nodes touches more nodes than a shared-memory table holds", GPW);
+					return ASS_EINVAL;
+				}
+				members.insert(members.end(), added.begin(), added.end());
+				sl++;
+			}
+			// table: ranks ascending inside their class; slot = 8 j + class
+			std::sort(members.begin(), members.end());
+			int fill[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+			const int n_slots = 8 * *std::max_element(cnt, cnt + 8);
+			TileDesc T;
+			T.s0 = s0; T.s1 = sl; T.tab_off = (int) tab.size(); T.n_slots = n_slots;
+			tab.resize(tab.size() + (size_t) n_slots, -1);
+			for (int r : members) {
+				const int slot = 8 * fill[r & 7]++ + (r & 7);
+				slot_of[(size_t) r] = slot;
+				tab[(size_t) T.tab_off + slot] = r;
+			}
+			for (int w = s0; w < sl; w++) {
+				for (int g = 0; g < GPW; g++) {
+					const int2 gi = lay.grp[(size_t) w * GPW + g];
+					if (gi.x >= 0) grpT[(size_t) w * GPW + g] = make_int4(slot_of[(size_t) gi.x], gi.x, gi.y, lay.order[(size_t) gi.x]);
+				}
+				for (int at = lay.warp_off[w]; at < lay.warp_off[(size_t) w + 1]; at++) {
+					const int g = ((at - lay.warp_off[w]) & 31) / SPRING_LANES;
+					const bool live = lay.grp[(size_t) w * GPW + g].x >= 0;
+					heL[(size_t) at].nbr = live ? slot_of[(size_t) lay.heT[(size_t) at].nbr] : 0;
+				}
+			}
+			slots_max = std::max(slots_max, n_slots);
+			tiles.push_back(T);
+			slices_max = std::max(slices_max, sl - s0);
+		}
+	}
+	cta_tile[grid] = (int) tiles.size();
+	int rc;
+	if ((rc = tiles_reserve(s->heL, s->heL_cap, heL.size(), "renumbered half-edge records"))) return rc;
+	if ((rc = tiles_reserve(s->grpT, s->grpT_cap, grpT.size(), "tile lane groups"))) return rc;
+	if ((rc = tiles_reserve(s->tile_tab, s->tile_tab_cap, tab.size(), "tile table entries"))) return rc;
+	if ((rc = tiles_reserve(s->tile_desc, s->tile_desc_cap, tiles.size(), "tile descriptors"))) return rc;
+	if ((rc = tiles_reserve(s->cta_tile, s->cta_tile_cap, cta_tile.size(), "tile cuts"))) return rc;
+	CU_TRY(cudaMemcpyAsync(s->heL, heL.data(), sizeof(HalfEdge) * heL.size(), cudaMemcpyHostToDevice, s->stream));
+	CU_TRY(cudaMemcpyAsync(s->grpT, grpT.data(), sizeof(int4) * grpT.size(), cudaMemcpyHostToDevice, s->stream));
+	CU_TRY(cudaMemcpyAsync(s->tile_tab, tab.data(), sizeof(int) * tab.size(), cudaMemcpyHostToDevice, s->stream));
+	CU_TRY(cudaMemcpyAsync(s->tile_desc, tiles.data(), sizeof(TileDesc) * tiles.size(), cudaMemcpyHostToDevice, s->stream));
+	CU_TRY(cudaMemcpyAsync(s->cta_tile, cta_tile.data(), sizeof(int) * cta_tile.size(), cudaMemcpyHostToDevice, s->stream));
 	CU_TRY(cudaStreamSynchronize(s->stream));
-	s->ccut_grid = grid;
-	s->ccut_epoch = s->spring_epoch;
+	s->tiles_grid = grid;
+	s->tile_slots_max = slots_max;
+	s->tile_slices_max = slices_max;
 	return ASS_OK;
 }
 
 template <bool ZERO_FIRST, bool KICK, bool UNI, bool PAL1>
-static int launch_lanes_t(ass_sim* s, double dt, int pre) {
-	auto kern = k_spring_lanes<ZERO_FIRST, KICK, UNI, PAL1>;
-	static int ctas_per_sm = 0;  // per instantiation
-	constexpr size_t smem = (size_t) LN_WARPS * LN_STAGES * LN_PAIR_BYTES;
-	if (ctas_per_sm == 0) {
+static int launch_tiles_t(ass_sim* s, double dt, int pre) {
+	auto kern = k_spring_tiles<ZERO_FIRST, KICK, UNI, PAL1>;
+	static size_t smem_set = 0;  // per instantiation
+	const size_t smem = TILE_SLOT_BYTES * (size_t) s->tile_slots_max + (size_t) s->tile_slices_max * GPW * sizeof(int4) + sizeof(int) * ((size_t) s->tile_slices_max + 2);
+	if (smem > smem_set) {
 		CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-		CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, LN_THREADS, smem));
-		if (ctas_per_sm < 1) ctas_per_sm = 1;
+		smem_set = smem;
 	}
-	const int grid = std::max(1, std::min((s->n_swarps + LN_WARPS - 1) / LN_WARPS, ass_sm_count() * ctas_per_sm));
-	int rc = ensure_cta_cuts(s, grid);
-	if (rc) return rc;
-	kern<<<grid, LN_THREADS, smem, s->stream>>>(mirror_nodes(s), s->order, s->acc, s->grp, s->warp_off, s->ccut, s->ccut + grid + 1, s->heT, s->palf,
-			KICK ? s->posm_alt : nullptr, KICK ? s->vel_alt : nullptr, s->mir_alt, dt, pre);
+	kern<<<s->tiles_grid, TL_THREADS, smem, s->stream>>>(mirror_nodes(s), s->acc, (const TileDesc*) s->tile_desc, s->cta_tile, s->tile_tab, s->grpT,
+			s->warp_off, s->heL, s->palf, s->tile_slots_max, s->tile_slices_max, KICK ? s->posm_alt : nullptr, KICK ? s->vel_alt : nullptr, s->mir_alt, dt, pre);
 	return ASS_OK;
 }
 
 template <bool KICK>
-static int launch_lanes(ass_sim* s, bool zero_first, bool uni, double dt, int pre) {
+static int launch_tiles(ass_sim* s, bool zero_first, bool uni, double dt, int pre) {
 	const bool pal1 = s->n_pal == 1;
-#define ASS_LANES_U(Z, U) (pal1 ? launch_lanes_t<Z, KICK, U, true>(s, dt, pre) : launch_lanes_t<Z, KICK, U, false>(s, dt, pre))
-	if (zero_first) return uni ? ASS_LANES_U(true, true) : ASS_LANES_U(true, false);
-	return uni ? ASS_LANES_U(false, true) : ASS_LANES_U(false, false);
-#undef ASS_LANES_U
+#define ASS_TILES_U(Z, U) (pal1 ? launch_tiles_t<Z, KICK, U, true>(s, dt, pre) : launch_tiles_t<Z, KICK, U, false>(s, dt, pre))
+	if (zero_first) return uni ? ASS_TILES_U(true, true) : ASS_TILES_U(true, false);
+	return uni ? ASS_TILES_U(false, true) : ASS_TILES_U(false, false);
+#undef ASS_TILES_U
 }
 
 // ASS_SPRINGS_NO_STREAM=1 runs the whole-body evaluations on the CSR kernel instead (same bits: tests)
-static bool use_csr_kernel() {
+static bool use_csr_kernel(const ass_sim* s) {
 	const char* e = getenv("ASS_SPRINGS_NO_STREAM");
-	return e && *e && *e != '0';
+	return s->tiles_grid <= 0 || (e && *e && *e != '0');
 }
 
 static int launch_mirror(ass_sim* s) {
@@ -416,8 +418,8 @@ int ass_launch_spring_forces(ass_sim* s, bool zero_first, bool mirror_fresh) {
 	if (rc) return rc;
 	ass_tic(s, ASS_K_SPRINGS);
 	if (!mirror_fresh && (rc = launch_mirror(s))) return rc;
-	if (use_csr_kernel()) launch_csr<false, false>(s, zero_first, uni, 0, s->n, 0.0, 0);
-	else if ((rc = launch_lanes<false>(s, zero_first, uni, 0.0, 0))) return rc;
+	if (use_csr_kernel(s)) launch_csr<false, false>(s, zero_first, uni, 0, s->n, 0.0, 0);
+	else if ((rc = launch_tiles<false>(s, zero_first, uni, 0.0, 0))) return rc;
 	LAUNCH_CHECK();
 	ass_toc(s, ASS_K_SPRINGS);
 	return ASS_OK;
@@ -430,8 +432,8 @@ int ass_launch_spring_kick_drift(ass_sim* s, bool zero_first, double dt, bool pr
 	if (rc) return rc;
 	ass_tic(s, ASS_K_SPRINGS);
 	if (!mirror_fresh && (rc = launch_mirror(s))) return rc;
-	if (use_csr_kernel()) launch_csr<true, false>(s, zero_first, uni, 0, s->n, dt, pre_drift_next ? 1 : 0);
-	else if ((rc = launch_lanes<true>(s, zero_first, uni, dt, pre_drift_next ? 1 : 0))) return rc;
+	if (use_csr_kernel(s)) launch_csr<true, false>(s, zero_first, uni, 0, s->n, dt, pre_drift_next ? 1 : 0);
+	else if ((rc = launch_tiles<true>(s, zero_first, uni, dt, pre_drift_next ? 1 : 0))) return rc;
 	LAUNCH_CHECK();
 	ass_toc(s, ASS_K_SPRINGS);
 	std::swap(s->posm, s->posm_alt);

@@ -337,7 +337,8 @@ extern "C" int ass_destroy(ass_sim* s) {
 	if (s->stream) cudaStreamSynchronize(s->stream);
 	ass_shard_release(s);  // a sharded simulation's posm / vel alias its exported window
 	ass_sym_plans_free(s);
-	cudaFree(s->heT); cudaFree(s->slotT); cudaFree(s->grp); cudaFree(s->warp_off); cudaFree(s->ccut);
+	cudaFree(s->slotT); cudaFree(s->warp_off);
+	cudaFree(s->heL); cudaFree(s->grpT); cudaFree(s->tile_tab); cudaFree(s->tile_desc); cudaFree(s->cta_tile);
 	cudaFree(s->order); cudaFree(s->rank); cudaFree(s->mir_block); cudaFree(s->mir_m);
 	cudaFree(s->posm); cudaFree(s->vel); cudaFree(s->acc); cudaFree(s->posm_alt); cudaFree(s->vel_alt);
 	cudaFree(s->he); cudaFree(s->row_ptr); cudaFree(s->slot); cudaFree(s->pal);
@@ -881,7 +882,7 @@ extern "C" int ass_set_springs(ass_sim* s, const ass_spring* sp, int ns) {
 		return rc;
 	}
 	std::vector<vec4d>().swap(pos);
-	const size_t nhe = lay.he.size(), n_heT = lay.heT.size(), n_grp = lay.grp.size();
+	const size_t nhe = lay.he.size();
 	if ((rc = reserve_sorted(s, n))) return rc;
 	if (nhe > s->he_cap) {
 		cudaFree(s->he); cudaFree(s->slot); cudaFree(s->slotT);
@@ -895,8 +896,6 @@ extern "C" int ass_set_springs(ass_sim* s, const ass_spring* sp, int ns) {
 		}
 		s->he_cap = cap;
 	}
-	if ((rc = reserve_array(s->heT, s->heT_cap, n_heT, "lane-transposed half-edge records"))) return rc;
-	if ((rc = reserve_array(s->grp, s->grp_cap, n_grp, "lane groups"))) return rc;
 	if ((rc = reserve_array(s->warp_off, s->swarp_cap, lay.warp_off.size(), "warp offsets"))) return rc;
 	if ((rc = reserve_array(s->row_ptr, s->row_cap, lay.row.size(), "row pointers"))) return rc;
 	ass_tic(s, ASS_K_XFER);
@@ -906,21 +905,18 @@ extern "C" int ass_set_springs(ass_sim* s, const ass_spring* sp, int ns) {
 		CU_TRY(cudaMemcpyAsync(s->slot, lay.slot.data(), sizeof(int) * nhe, cudaMemcpyHostToDevice, s->stream));
 		CU_TRY(cudaMemcpyAsync(s->slotT, lay.slotT.data(), sizeof(int) * nhe, cudaMemcpyHostToDevice, s->stream));
 	}
-	if (n_heT) CU_TRY(cudaMemcpyAsync(s->heT, lay.heT.data(), sizeof(HalfEdge) * n_heT, cudaMemcpyHostToDevice, s->stream));
 	CU_TRY(cudaMemcpyAsync(s->row_ptr, lay.row.data(), sizeof(int) * lay.row.size(), cudaMemcpyHostToDevice, s->stream));
 	CU_TRY(cudaMemcpyAsync(s->warp_off, lay.warp_off.data(), sizeof(int) * lay.warp_off.size(), cudaMemcpyHostToDevice, s->stream));
-	if (n_grp) CU_TRY(cudaMemcpyAsync(s->grp, lay.grp.data(), sizeof(int2) * n_grp, cudaMemcpyHostToDevice, s->stream));
 	if (n) {
 		CU_TRY(cudaMemcpyAsync(s->order, lay.order.data(), sizeof(int) * (size_t) n, cudaMemcpyHostToDevice, s->stream));
 		CU_TRY(cudaMemcpyAsync(s->rank, lay.rank.data(), sizeof(int) * (size_t) n, cudaMemcpyHostToDevice, s->stream));
 	}
 	ass_toc(s, ASS_K_XFER);
-	CU_TRY(cudaStreamSynchronize(s->stream));  // the layout dies here
+	CU_TRY(cudaStreamSynchronize(s->stream));
+	s->n_swarps = (int) lay.warp_off.size() - 1;
+	if ((rc = ass_build_spring_tiles(s, lay))) return rc;  // the layout dies after this
 	s->ns = ns;
 	s->n_he = (int) nhe;
-	s->n_heT = (long long) n_heT;
-	s->n_swarps = (int) lay.warp_off.size() - 1;
-	s->h_warp_off = lay.warp_off;
 	s->max_degree = lay.max_degree;
 	s->spring_epoch++;
 	return ASS_OK;
@@ -928,7 +924,7 @@ extern "C" int ass_set_springs(ass_sim* s, const ass_spring* sp, int ns) {
 
 // stage holds [ns x ass_spring | ns x int palette index]
 __global__ void k_scatter_props(const ass_spring* __restrict__ sp, const int* __restrict__ pidx, const int* __restrict__ slot,
-		const int* __restrict__ slotT, HalfEdge* __restrict__ he, HalfEdge* __restrict__ heT, int ns) {
+		const int* __restrict__ slotT, HalfEdge* __restrict__ he, HalfEdge* __restrict__ heL, int ns) {
 	int q = blockIdx.x * blockDim.x + threadIdx.x;
 	if (q >= ns) return;
 	const double rs0 = sp[q].rs0;
@@ -937,9 +933,9 @@ __global__ void k_scatter_props(const ass_spring* __restrict__ sp, const int* __
 		HalfEdge* h = he + slot[(size_t) 2 * q + side];
 		h->rs0 = rs0;
 		h->pal = pi;
-		HalfEdge* ht = heT + slotT[(size_t) 2 * q + side];
-		ht->rs0 = rs0;
-		ht->pal = pi;
+		HalfEdge* hl = heL + slotT[(size_t) 2 * q + side];  // the tiled kernel's copy
+		hl->rs0 = rs0;
+		hl->pal = pi;
 	}
 }
 
@@ -959,7 +955,7 @@ extern "C" int ass_update_spring_props(ass_sim* s, const ass_spring* sp, int ns)
 	if ((rc = upload_palette(s, pal))) return rc;
 	CU_TRY(cudaMemcpyAsync(s->stage.p, sp, sp_bytes, cudaMemcpyHostToDevice, s->stream));
 	CU_TRY(cudaMemcpyAsync((char*) s->stage.p + sp_bytes, pidx.data(), sizeof(int) * (size_t) ns, cudaMemcpyHostToDevice, s->stream));
-	k_scatter_props<<<(ns + 255) / 256, 256, 0, s->stream>>>((const ass_spring*) s->stage.p, (const int*) ((char*) s->stage.p + sp_bytes), s->slot, s->slotT, s->he, s->heT, ns);
+	k_scatter_props<<<(ns + 255) / 256, 256, 0, s->stream>>>((const ass_spring*) s->stage.p, (const int*) ((char*) s->stage.p + sp_bytes), s->slot, s->slotT, s->he, s->heL, ns);
 	LAUNCH_CHECK();
 	ass_toc(s, ASS_K_XFER);
 	CU_TRY(cudaStreamSynchronize(s->stream));

@@ -549,36 +549,63 @@ def test_orb_terms_match_reference(gpu, oracle, orb_golden):
             s.drift_bin(1.0, 0.1, 0.1, 2, 2)
 
 
+def _spring_kernel_mode(monkeypatch, mode):
+    """tiles (default): lane-transposed records, endpoint state in shared-memory tables; csr: one group of lanes per node
+    reading the CSR copy of the list through L1 (the kernel node slabs of a sharded body use)."""
+    monkeypatch.delenv("ASS_SPRINGS_NO_STREAM", raising=False)
+    if mode == "csr":
+        monkeypatch.setenv("ASS_SPRINGS_NO_STREAM", "1")
+
+
 def test_spring_kernels_agree_bit_for_bit(gpu, body015, monkeypatch):
-    """The streaming kernel (bulk-copy ring, persistent CTAs) and the plain kernel it falls back to when a ring does not
-    fit in shared memory run the same arithmetic in the same order: identical bits, with and without the fused kick."""
+    """The two spring kernels (springs.cu: tiled, CSR) run the same arithmetic in the same order: identical bits,
+    with and without the fused kick, for uniform and non-uniform masses, for one and for several (k, gamma) pairs."""
     g = body015
     start = g["start"].copy(); start[:, 6:9] = 0.25
     sp = g["springs"]
     outs = []
-    for no_stream in ("", "1"):
-        if no_stream:
-            monkeypatch.setenv("ASS_SPRINGS_NO_STREAM", "1")
-        else:
-            monkeypatch.delenv("ASS_SPRINGS_NO_STREAM", raising=False)
+    for mode in ("tiles", "csr"):
+        _spring_kernel_mode(monkeypatch, mode)
         with new_sim(gpu, start, sp, gravity=0, dt=1e-3, additional_forces=1) as s:
             s.spring_forces()
             a1 = s.download(start.copy())
             s.step(3)
             outs.append((a1, s.download(start.copy())))
-    assert same_bits(outs[0][0], outs[1][0]) and same_bits(outs[0][1], outs[1][1])
-    # a mass edit on one sprung node switches both kernels to the general reduced-mass form
+    for o in outs[1:]:
+        assert same_bits(outs[0][0], o[0]) and same_bits(outs[0][1], o[1])
+    # a mass edit on one sprung node switches the kernels to the general reduced-mass form; two (k, gamma) pairs to the
+    # general palette path
     q = start.copy(); q[7, 9] *= 1.5
+    sp2 = sp.copy(); sp2["k"][::3] *= 2.0; sp2["gamma"][::5] = 0.0
+    for body, springs in ((q, sp), (start, sp2), (q, sp2)):
+        res = []
+        for mode in ("tiles", "csr"):
+            _spring_kernel_mode(monkeypatch, mode)
+            with new_sim(gpu, body, springs, gravity=0, dt=1e-3, additional_forces=2) as s:
+                s.step(2)
+                res.append(s.download(body.copy()))
+        assert same_bits(res[0], res[1])
+
+
+def test_spring_props_update_reaches_every_copy_of_the_list(gpu, oracle, body015, monkeypatch):
+    """set_gamma / adjust_spring_props style edits go through ass_update_spring_props, which patches the CSR and the tile
+    copies of the half-edge list in place: both kernels must see the new values."""
+    g = body015
+    p = g["start"].copy(); p[:, 6:9] = 0.0
+    sp = g["springs"]
+    sp2 = sp.copy(); sp2["gamma"] *= 0.25; sp2["k"][1::2] *= 1.5; sp2["rs0"] *= 1.001
+    want = p.copy(); oracle.spring_forces(want, sp2)
     res = []
-    for no_stream in ("", "1"):
-        if no_stream:
-            monkeypatch.setenv("ASS_SPRINGS_NO_STREAM", "1")
-        else:
-            monkeypatch.delenv("ASS_SPRINGS_NO_STREAM", raising=False)
-        with new_sim(gpu, q, sp, gravity=0, dt=1e-3, additional_forces=2) as s:
-            s.step(2)
-            res.append(s.download(q.copy()))
+    for mode in ("tiles", "csr"):
+        _spring_kernel_mode(monkeypatch, mode)
+        with new_sim(gpu, p, sp) as s:
+            s.spring_forces()
+            s.update_spring_props(sp2)
+            s.zero_accel()
+            s.spring_forces()
+            res.append(s.download(p.copy()))
     assert same_bits(res[0], res[1])
+    assert acc_err(res[0][:, 6:9], want[:, 6:9]) <= ACC_TOL
 
 
 def test_spring_forces_nonuniform_mass_matches_oracle(gpu, oracle, body015):
