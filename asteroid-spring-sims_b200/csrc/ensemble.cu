@@ -34,7 +34,7 @@ struct BodyDesc {
 	int node_off, n, grp_off, swarp_off;  // first node / lane group / warp-offset entry of the member in the concatenated arrays
 	int n_swarps, n_perts, gravity, af;
 	double dt, negG, soft2;
-	int heartbeat, pad;
+	int heartbeat, pal_idx;  // pal_idx: the palette entry all of the member's springs share, -1 if they differ
 };
 
 // A member's state and accelerations may have been written by another SM earlier in the same launch (the previous batch
@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(ET, 1) k_ensemble(const BodyDesc* __restrict__
 	const bool grav = B.gravity == 1 && B.af != 2;
 	const int lane = tid & 31;
 	double2 nkg1 = make_double2(0.0, 0.0);
-	if (PAL1) nkg1 = __ldg(palf);
+	if (PAL1) nkg1 = __ldg(palf + B.pal_idx);  // every member's springs share one (k, gamma): the pair travels in registers
 	bool predrifted = false;
 	for (int step = 0; step < nsteps; step++) {
 		const bool last = step == nsteps - 1;
@@ -276,7 +276,7 @@ struct ass_ensemble {
 	cudaStream_t stream = nullptr;
 	cudaEvent_t e0 = nullptr, e1 = nullptr;
 	size_t smem = 0;
-	bool pal1 = false;     // every spring of the ensemble has the same (k, gamma): the palette travels in registers
+	bool pal1 = false;     // inside every member all springs have the same (k, gamma): the pair travels in registers
 	bool uni_mass = true;  // within every member, all nodes carry the same mass (m_red = m / 2, spring_math.cuh)
 	int* d_queue = nullptr;  // [0] the item counter, [1 .. n_bodies] batches completed per member (k_ensemble)
 };
@@ -325,6 +325,7 @@ extern "C" int ass_ensemble_create(ass_ensemble** out, int n_bodies, const int* 
 	// palette of distinct (k, gamma) bit patterns over the whole ensemble (a sweep has a handful), stored as the force
 	// kernels want it (spring_math.cuh)
 	std::vector<double2> palf;
+	bool all_pal1 = true;  // inside every member, all springs share one palette entry (a material sweep: k differs between members)
 	std::unordered_map<std::string, int> seen;
 	auto pal_index = [&](const ass_spring& v) {
 		std::string key((const char*) &v.k, 8);
@@ -371,7 +372,10 @@ extern "C" int ass_ensemble_create(ass_ensemble** out, int n_bodies, const int* 
 		BodyDesc& d = e->desc[b];
 		d.node_off = node_off[b]; d.n = n;
 		d.grp_off = (int) grp.size(); d.swarp_off = (int) warp_off.size(); d.n_swarps = (int) lay.warp_off.size() - 1;
-		d.pad = 0;
+		d.pal_idx = ns > 0 ? pidx[0] : 0;
+		for (int q = 1; q < ns; q++)
+			if (pidx[(size_t) q] != pidx[0]) { d.pal_idx = -1; break; }
+		if (d.pal_idx < 0) all_pal1 = false;
 		for (int i = 0; i < n; i++) {
 			perm[(size_t) node_off[b] + i] = node_off[b] + lay.rank[(size_t) i];
 			ord[(size_t) node_off[b] + lay.rank[(size_t) i]] = i;
@@ -382,7 +386,7 @@ extern "C" int ass_ensemble_create(ass_ensemble** out, int n_bodies, const int* 
 		e->total_he += 2LL * ns;
 	}
 	fill_desc(e);
-	e->pal1 = palf.size() == 1;
+	e->pal1 = all_pal1;
 	e->smem = (3 * sizeof(double2) + sizeof(double)) * ((size_t) e->max_n + 1) + 64;
 	if (e->smem > 227 * 1024 - 2048) {
 		ens_free(e);

@@ -262,7 +262,8 @@ int ass_build_spring_tiles(ass_sim* s, const SpringLayout& lay) {
 	const int ns = (int) lay.warp_off.size() - 1;
 	const int n = (int) lay.rank.size();
 	if (ns <= 0 || lay.heT.empty()) return ASS_OK;
-	const int grid = std::max(1, std::min((ns + TL_THREADS / 32 - 1) / (TL_THREADS / 32), ass_sm_count()));
+	// small bodies: at least ~4 slices per CTA, so that a few thousand nodes already spread over the whole machine
+	const int grid = std::max(1, std::min((ns + 3) / 4, ass_sm_count()));
 	auto pairs = [&](int w) { return (lay.warp_off[(size_t) w + 1] - lay.warp_off[w]) >> 6; };
 	std::vector<double> prefix((size_t) ns + 1, 0.0);
 	for (int w = 0; w < ns; w++) prefix[(size_t) w + 1] = prefix[w] + (double) pairs(w) + 0.75;

@@ -530,7 +530,7 @@ def main():
     if s_n:
         alg = 32.0 * ns + 80.0 * n
         ach = alg * s_n / (s_ms * 1e-3) / 1e9
-        roof_s = {"kernel": "k_spring_forces(+kick+drift)", "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+        roof_s = {"kernel": "k_spring_tiles<KICK> (springs + kick + drift)", "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
                   "traffic": traffic.get("springs"), "peak_source": hbm_src, "algorithmic_bytes_per_launch": alg, "ms_per_launch": s_ms / s_n}
     dominant = roof_g if (roof_g and g_ms >= s_ms) else roof_s
 
