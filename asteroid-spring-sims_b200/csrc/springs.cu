@@ -263,7 +263,11 @@ int ass_build_spring_tiles(ass_sim* s, const SpringLayout& lay) {
 	const int n = (int) lay.rank.size();
 	if (ns <= 0 || lay.heT.empty()) return ASS_OK;
 	// small bodies: at least ~4 slices per CTA, so that a few thousand nodes already spread over the whole machine
-	const int grid = std::max(1, std::min((ns + 3) / 4, ass_sm_count()));
+	int grid = std::max(1, std::min((ns + 3) / 4, ass_sm_count()));
+	int slots_limit = TILE_SLOTS_LIMIT;
+	// test hooks: fewer CTAs / smaller tables, so that a small body exercises several tiles per CTA
+	if (const char* e = getenv("ASS_TILE_GRID")) grid = std::max(1, std::min(grid, atoi(e)));
+	if (const char* e = getenv("ASS_TILE_SLOTS")) slots_limit = std::max(64, std::min(TILE_SLOTS_LIMIT, atoi(e) & ~7));
 	auto pairs = [&](int w) { return (lay.warp_off[(size_t) w + 1] - lay.warp_off[w]) >> 6; };
 	std::vector<double> prefix((size_t) ns + 1, 0.0);
 	for (int w = 0; w < ns; w++) prefix[(size_t) w + 1] = prefix[w] + (double) pairs(w) + 0.75;
@@ -304,11 +308,11 @@ int ass_build_spring_tiles(ass_sim* s, const SpringLayout& lay) {
 				}
 				for (int at = lay.warp_off[sl]; at < lay.warp_off[(size_t) sl + 1]; at++) touch(lay.heT[(size_t) at].nbr);
 				const int need = 8 * *std::max_element(cnt, cnt + 8);
-				if (need > TILE_SLOTS_LIMIT && sl > s0) {  // does not fit any more: take the slice back, close the tile
+				if (need > slots_limit && sl > s0) {  // does not fit any more: take the slice back, close the tile
 					for (int r : added) { stamp[(size_t) r] = -1; cnt[r & 7]--; }
 					break;
 				}
-				if (need > TILE_SLOTS_LIMIT) {
+				if (need > TILE_SLOTS_LIMIT) {  // (a lone slice above the test hook's limit is accepted)
 					ass_set_error("ass_set_springs: one slice of %d nodes touches more nodes than a shared-memory table holds", GPW);
 					return ASS_EINVAL;
 				}
