@@ -131,6 +131,17 @@ def selfcheck_sqrt(samples=1 << 28, exp_lo=-200, exp_hi=200):
     return bad.value, first.value
 
 
+def selfcheck_spring_layout(p, springs, grid=148, slots=1 << 20):
+    """Host-only check of what ass_set_springs builds (ranking, CSR and lane-transposed half-edge copies, tile cut for
+    `grid` CTAs with tables of at most `slots` entries); needs no GPU.  Returns a dict of counts; 'violations' must be 0."""
+    pos = np.ascontiguousarray(np.column_stack([p[:, 0], p[:, 1], p[:, 2], p[:, 9]]), dtype=np.float64)
+    s, ptr, n = _springs(springs)
+    stats = (C.c_longlong * 8)()
+    _chk(lib().ass_selfcheck_spring_layout(pos.ctypes.data_as(C.c_void_p), C.c_int(len(pos)), ptr, n, C.c_int(grid), C.c_int(slots), stats))
+    keys = ("slices", "padding", "tiles", "max_slots", "gather_passes", "gather_passes_min", "violations", "records")
+    return dict(zip(keys, [int(v) for v in stats]))
+
+
 def _rows(p):
     assert isinstance(p, np.ndarray) and p.dtype == np.float64 and p.ndim == 2 and p.shape[1] >= 10
     assert p.strides[1] == 8, "rows must be contiguous doubles"

@@ -15,8 +15,8 @@
 //   posm[i] = {x, y, z, m}      one 32 B sector per gather
 //   vel[i]  = {vx, vy, vz, 0}
 //   acc[i]  = {ax, ay, az, 0}
-// A spring endpoint gather touches exactly two sectors (posm, vel); a gravity source tile is a dense
-// run of posm.  HalfEdge is the node-sorted (CSR) copy of `struct spring`, one per endpoint.
+// A gravity source tile is a dense run of posm.  The spring kernels gather from a rank-ordered mirror of posm / vel in
+// 16-byte pairs (ass_sim::mir).  HalfEdge is the node-sorted copy of `struct spring`, one per endpoint.
 // ---------------------------------------------------------------------------------------------------
 struct __align__(32) vec4d {
 	double x, y, z, w;
@@ -28,7 +28,7 @@ struct __align__(32) vec4d {
 // figure of SURVEY 8d -- although every spring is stored at both of its endpoints.  Lossless for any number of pairs.
 struct __align__(16) HalfEdge {
 	double rs0;
-	int nbr;  // the other endpoint: ass_sim -- its spatial rank (see ass_sim::order); ensemble -- its node index
+	int nbr;  // the other endpoint: its spatial rank (see ass_sim::order); in heL: its slot in the tile's shared-memory table
 	int pal;  // index into the (k, gamma) palette
 };
 static_assert(sizeof(HalfEdge) == 16, "HalfEdge must be 16 bytes");
@@ -268,18 +268,6 @@ __device__ __forceinline__ double fast_rcp(double a) {
 	return y;
 }
 
-// 1/sqrt(a) to ~1 ulp: hardware seed (MUFU.RSQ64H) + one third-order (Householder) step:
-// eps = 1 - a*y0^2;  y1 = y0 * (1 + eps/2 + 3 eps^2/8), residual ~ (5/16) eps^3.
-__device__ __forceinline__ double fast_rsqrt(double a) {
-	double y;
-	asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
-	const double t = a * y;
-	const double eps = fma(-t, y, 1.0);
-	const double p = fma(0.375, eps, 0.5);
-	const double q = eps * p;
-	return fma(y, q, y);
-}
-
 // a^(-3/2) in SIX FP64 instructions from the hardware seed y0 = MUFU.RSQ64H(a).  The seed carries 20 mantissa bits (the
 // instruction produces the high word only), so c2 = y0*y0 is exact and eps = 1 - a*c2 costs one FMA with one rounding:
 //   a^(-3/2) = y0^3 (1 - eps)^(-3/2) = y0^3 (1 + eps (3/2 + 15/8 eps)) + O(eps^3),   eps ~ 2^-21: 35/16 eps^3 ~ 2^-62.
@@ -314,20 +302,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
 		"DONE_%=:\n\t"
 		"}" ::"r"(smem_u32(bar)), "r"(phase) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
 // size and both addresses must be multiples of 16 bytes
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
 	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
 			"l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
-
-// per-thread asynchronous copy global -> shared (LDGSTS), 16 bytes; completion by cp.async.wait_all
-__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
-	asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 __device__ __forceinline__ double shfl_xor_d(double v, int mask, int width = 32) {
 	return __shfl_xor_sync(0xffffffffu, v, mask, width);

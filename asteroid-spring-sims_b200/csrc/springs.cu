@@ -255,19 +255,22 @@ static int tiles_reserve(T*& ptr, size_t& cap, size_t need, const char* what) {
 	return ASS_OK;
 }
 
-// Cut the slices into one run per CTA (equal weight: pairs of steps + a constant per slice for the boundary work) and every run into tiles whose node tables fit
-// in shared memory; renumber the records.  Host work proportional to the half-edge count, done once per spring list.
-int ass_build_spring_tiles(ass_sim* s, const SpringLayout& lay) {
-	s->tiles_grid = 0;
+// What the tiled kernel reads besides the mirror, as built on the host.
+struct TilesHost {
+	int grid = 0, slots_max = 0, slices_max = 0;
+	std::vector<TileDesc> tiles;
+	std::vector<int> cta_tile, tab;
+	std::vector<HalfEdge> heL;
+	std::vector<int4> grpT;
+};
+
+// Cut the slices into one run per CTA (equal weight: pairs of steps + a constant per slice for the boundary work) and
+// every run into tiles whose node tables fit in `slots_limit` slots; renumber the records.  Pure host work,
+// proportional to the half-edge count, done once per spring list.  Returns ASS_EINVAL if a single slice does not fit.
+static int build_tiles_host(const SpringLayout& lay, int grid, int slots_limit, TilesHost& out) {
 	const int ns = (int) lay.warp_off.size() - 1;
 	const int n = (int) lay.rank.size();
-	if (ns <= 0 || lay.heT.empty()) return ASS_OK;
-	// small bodies: at least ~4 slices per CTA, so that a few thousand nodes already spread over the whole machine
-	int grid = std::max(1, std::min((ns + 3) / 4, ass_sm_count()));
-	int slots_limit = TILE_SLOTS_LIMIT;
-	// test hooks: fewer CTAs / smaller tables, so that a small body exercises several tiles per CTA
-	if (const char* e = getenv("ASS_TILE_GRID")) grid = std::max(1, std::min(grid, atoi(e)));
-	if (const char* e = getenv("ASS_TILE_SLOTS")) slots_limit = std::max(64, std::min(TILE_SLOTS_LIMIT, atoi(e) & ~7));
+	out.grid = grid;
 	auto pairs = [&](int w) { return (lay.warp_off[(size_t) w + 1] - lay.warp_off[w]) >> 6; };
 	std::vector<double> prefix((size_t) ns + 1, 0.0);
 	for (int w = 0; w < ns; w++) prefix[(size_t) w + 1] = prefix[w] + (double) pairs(w) + 0.75;
@@ -277,17 +280,22 @@ int ass_build_spring_tiles(ass_sim* s, const SpringLayout& lay) {
 		for (int c = 1; c < grid; c++) {
 			const double target = prefix[ns] * (double) c / (double) grid;
 			while (w < ns && prefix[(size_t) w + 1] <= target) w++;
+			// the boundary slice goes to whichever side leaves the smaller error
 			if (w < ns && target - prefix[w] > prefix[(size_t) w + 1] - target) w++;
 			cut[c] = std::max(w, cut[(size_t) c - 1]);
 		}
 		cut[grid] = ns;
 	}
-	std::vector<TileDesc> tiles;
-	std::vector<int> cta_tile((size_t) grid + 1, 0), tab;
-	std::vector<HalfEdge> heL(lay.heT);
-	std::vector<int4> grpT(lay.grp.size(), make_int4(-1, -1, 0, 0));
+	std::vector<TileDesc>& tiles = out.tiles;
+	std::vector<int>& cta_tile = out.cta_tile;
+	std::vector<int>& tab = out.tab;
+	std::vector<HalfEdge>& heL = out.heL;
+	std::vector<int4>& grpT = out.grpT;
+	tiles.clear(); tab.clear();
+	cta_tile.assign((size_t) grid + 1, 0);
+	heL = lay.heT;
+	grpT.assign(lay.grp.size(), make_int4(-1, -1, 0, 0));
 	std::vector<int> stamp((size_t) n, -1), slot_of((size_t) n, -1), members, added;
-	int slots_max = 0, slices_max = 0;
 	for (int c = 0; c < grid; c++) {
 		cta_tile[c] = (int) tiles.size();
 		int sl = cut[c];
@@ -312,10 +320,7 @@ int ass_build_spring_tiles(ass_sim* s, const SpringLayout& lay) {
 					for (int r : added) { stamp[(size_t) r] = -1; cnt[r & 7]--; }
 					break;
 				}
-				if (need > TILE_SLOTS_LIMIT) {  // (a lone slice above the test hook's limit is accepted)
-					ass_set_error("ass_set_springs: one slice of %d nodes touches more nodes than a shared-memory table holds", GPW);
-					return ASS_EINVAL;
-				}
+				if (need > TILE_SLOTS_LIMIT) return ASS_EINVAL;  // (a lone slice above a test hook's smaller limit is accepted)
 				members.insert(members.end(), added.begin(), added.end());
 				sl++;
 			}
@@ -342,27 +347,156 @@ int ass_build_spring_tiles(ass_sim* s, const SpringLayout& lay) {
 					heL[(size_t) at].nbr = live ? slot_of[(size_t) lay.heT[(size_t) at].nbr] : 0;
 				}
 			}
-			slots_max = std::max(slots_max, n_slots);
+			out.slots_max = std::max(out.slots_max, n_slots);
+			out.slices_max = std::max(out.slices_max, sl - s0);
 			tiles.push_back(T);
-			slices_max = std::max(slices_max, sl - s0);
 		}
 	}
 	cta_tile[grid] = (int) tiles.size();
-	int rc;
-	if ((rc = tiles_reserve(s->heL, s->heL_cap, heL.size(), "renumbered half-edge records"))) return rc;
-	if ((rc = tiles_reserve(s->grpT, s->grpT_cap, grpT.size(), "tile lane groups"))) return rc;
-	if ((rc = tiles_reserve(s->tile_tab, s->tile_tab_cap, tab.size(), "tile table entries"))) return rc;
-	if ((rc = tiles_reserve(s->tile_desc, s->tile_desc_cap, tiles.size(), "tile descriptors"))) return rc;
-	if ((rc = tiles_reserve(s->cta_tile, s->cta_tile_cap, cta_tile.size(), "tile cuts"))) return rc;
-	CU_TRY(cudaMemcpyAsync(s->heL, heL.data(), sizeof(HalfEdge) * heL.size(), cudaMemcpyHostToDevice, s->stream));
-	CU_TRY(cudaMemcpyAsync(s->grpT, grpT.data(), sizeof(int4) * grpT.size(), cudaMemcpyHostToDevice, s->stream));
-	CU_TRY(cudaMemcpyAsync(s->tile_tab, tab.data(), sizeof(int) * tab.size(), cudaMemcpyHostToDevice, s->stream));
-	CU_TRY(cudaMemcpyAsync(s->tile_desc, tiles.data(), sizeof(TileDesc) * tiles.size(), cudaMemcpyHostToDevice, s->stream));
-	CU_TRY(cudaMemcpyAsync(s->cta_tile, cta_tile.data(), sizeof(int) * cta_tile.size(), cudaMemcpyHostToDevice, s->stream));
+	return ASS_OK;
+}
+
+int ass_build_spring_tiles(ass_sim* s, const SpringLayout& lay) {
+	s->tiles_grid = 0;
+	const int ns = (int) lay.warp_off.size() - 1;
+	if (ns <= 0 || lay.heT.empty()) return ASS_OK;
+	// small bodies: at least ~4 slices per CTA, so that a few thousand nodes already spread over the whole machine
+	int grid = std::max(1, std::min((ns + 3) / 4, ass_sm_count()));
+	int slots_limit = TILE_SLOTS_LIMIT;
+	// test hooks: fewer CTAs / smaller tables, so that a small body exercises several tiles per CTA
+	if (const char* e = getenv("ASS_TILE_GRID")) grid = std::max(1, std::min(grid, atoi(e)));
+	if (const char* e = getenv("ASS_TILE_SLOTS")) slots_limit = std::max(64, std::min(TILE_SLOTS_LIMIT, atoi(e) & ~7));
+	TilesHost th;
+	int rc = build_tiles_host(lay, grid, slots_limit, th);
+	if (rc) {
+		ass_set_error("ass_set_springs: one slice of %d nodes touches more nodes than a shared-memory table holds", GPW);
+		return rc;
+	}
+	if ((rc = tiles_reserve(s->heL, s->heL_cap, th.heL.size(), "renumbered half-edge records"))) return rc;
+	if ((rc = tiles_reserve(s->grpT, s->grpT_cap, th.grpT.size(), "tile lane groups"))) return rc;
+	if ((rc = tiles_reserve(s->tile_tab, s->tile_tab_cap, th.tab.size(), "tile table entries"))) return rc;
+	if ((rc = tiles_reserve(s->tile_desc, s->tile_desc_cap, th.tiles.size(), "tile descriptors"))) return rc;
+	if ((rc = tiles_reserve(s->cta_tile, s->cta_tile_cap, th.cta_tile.size(), "tile cuts"))) return rc;
+	CU_TRY(cudaMemcpyAsync(s->heL, th.heL.data(), sizeof(HalfEdge) * th.heL.size(), cudaMemcpyHostToDevice, s->stream));
+	CU_TRY(cudaMemcpyAsync(s->grpT, th.grpT.data(), sizeof(int4) * th.grpT.size(), cudaMemcpyHostToDevice, s->stream));
+	CU_TRY(cudaMemcpyAsync(s->tile_tab, th.tab.data(), sizeof(int) * th.tab.size(), cudaMemcpyHostToDevice, s->stream));
+	CU_TRY(cudaMemcpyAsync(s->tile_desc, th.tiles.data(), sizeof(TileDesc) * th.tiles.size(), cudaMemcpyHostToDevice, s->stream));
+	CU_TRY(cudaMemcpyAsync(s->cta_tile, th.cta_tile.data(), sizeof(int) * th.cta_tile.size(), cudaMemcpyHostToDevice, s->stream));
 	CU_TRY(cudaStreamSynchronize(s->stream));
 	s->tiles_grid = grid;
-	s->tile_slots_max = slots_max;
-	s->tile_slices_max = slices_max;
+	s->tile_slots_max = th.slots_max;
+	s->tile_slices_max = th.slices_max;
+	return ASS_OK;
+}
+
+// Host-only self-check of everything ass_set_springs builds for the spring kernels (include/ass_b200.h): no device
+// is touched, so the CPU test suite can drive it.
+extern "C" int ass_selfcheck_spring_layout(const double* pos_xyzm, int n, const ass_spring* springs, int ns, int grid, int slots, long long* stats) {
+	REQUIRE(n >= 0 && ns >= 0 && (n == 0 || pos_xyzm) && (ns == 0 || springs) && stats, ASS_EINVAL, "bad argument");
+	REQUIRE(grid >= 1, ASS_EINVAL, "grid must be positive");
+	std::vector<vec4d> pos((size_t) n);
+	for (int i = 0; i < n; i++) { pos[(size_t) i].x = pos_xyzm[4 * i]; pos[(size_t) i].y = pos_xyzm[4 * i + 1]; pos[(size_t) i].z = pos_xyzm[4 * i + 2]; pos[(size_t) i].w = pos_xyzm[4 * i + 3]; }
+	std::vector<int> pidx((size_t) ns);
+	for (int q = 0; q < ns; q++) pidx[(size_t) q] = q & 3;  // any palette indices: they must travel with their spring
+	SpringLayout lay;
+	int bad = -1;
+	int rc = ass_build_spring_layout(pos.data(), n, springs, ns, pidx.data(), lay, &bad);
+	if (rc) {
+		ass_set_error("ass_selfcheck_spring_layout: layout failed (rc %d, spring %d)", rc, bad);
+		return rc;
+	}
+	const int n_sl = (int) lay.warp_off.size() - 1;
+	TilesHost th;
+	const int slots_limit = std::max(64, std::min(TILE_SLOTS_LIMIT, slots & ~7));
+	if (n_sl > 0 && (rc = build_tiles_host(lay, std::min(grid, std::max(1, n_sl)), slots_limit, th))) {
+		ass_set_error("ass_selfcheck_spring_layout: a slice does not fit in a table");
+		return rc;
+	}
+	long long viol = 0, pad = 0, passes = 0, ideal = 0;
+	// (1) every rank owns exactly one lane group; rows hold exactly the springs of their node, with their properties
+	std::vector<int> seen((size_t) n, 0);
+	for (const int2& g : lay.grp)
+		if (g.x >= 0) { seen[(size_t) g.x]++; if (g.y != lay.row[(size_t) g.x + 1] - lay.row[g.x]) viol++; }
+	for (int k = 0; k < n; k++) if (seen[(size_t) k] != 1) viol++;
+	for (int q = 0; q < ns; q++)
+		for (int side = 0; side < 2; side++) {
+			const int own = lay.rank[(size_t) (side ? springs[q].particle_2 : springs[q].particle_1)];
+			const int oth = lay.rank[(size_t) (side ? springs[q].particle_1 : springs[q].particle_2)];
+			const int at = lay.slot[(size_t) 2 * q + side], at_t = lay.slotT[(size_t) 2 * q + side];
+			if (at < lay.row[own] || at >= lay.row[(size_t) own + 1]) { viol++; continue; }
+			const HalfEdge& h = lay.he[(size_t) at];
+			const HalfEdge& ht = lay.heT[(size_t) at_t];
+			if (h.nbr != oth || ht.nbr != oth || h.rs0 != springs[q].rs0 || ht.rs0 != springs[q].rs0 || h.pal != (q & 3) || ht.pal != (q & 3)) viol++;
+		}
+	// (2) the lane-transposed copy is the CSR copy, step by step; padding points at the node itself; step counts are even
+	for (int w = 0; w < n_sl; w++) {
+		const int steps = (lay.warp_off[(size_t) w + 1] - lay.warp_off[w]) / 32;
+		if ((steps & 1) || (lay.warp_off[(size_t) w + 1] - lay.warp_off[w]) % 32) viol++;
+		for (int t = 0; t < steps; t++) {
+			for (int lane = 0; lane < 32; lane++) {
+				const int g = lane / SPRING_LANES, e = t * SPRING_LANES + lane % SPRING_LANES;
+				const int2 gi = lay.grp[(size_t) w * GPW + g];
+				const HalfEdge& h = lay.heT[(size_t) lay.warp_off[w] + (size_t) t * 32 + lane];
+				if (e < gi.y) {
+					const HalfEdge& c = lay.he[(size_t) lay.row[gi.x] + e];
+					if (c.nbr != h.nbr || c.rs0 != h.rs0 || c.pal != h.pal) viol++;
+				} else {
+					pad++;
+					if (h.nbr != (gi.x >= 0 ? gi.x : 0)) viol++;
+				}
+			}
+			// gather passes of this step: per quarter warp, the fullest bank group among the distinct entries
+			for (int qw = 0; qw < 4; qw++) {
+				int distinct[8], nd = 0, cnt[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+				bool real = false;
+				for (int l8 = 0; l8 < 8; l8++) {
+					const int lane = qw * 8 + l8;
+					const int2 gi = lay.grp[(size_t) w * GPW + lane / SPRING_LANES];
+					if (t * SPRING_LANES + lane % SPRING_LANES < gi.y) real = true;
+					const int r = lay.heT[(size_t) lay.warp_off[w] + (size_t) t * 32 + lane].nbr;
+					bool dup = false;
+					for (int i = 0; i < nd; i++) dup = dup || distinct[i] == r;
+					if (!dup) { distinct[nd++] = r; cnt[r & 7]++; }
+				}
+				if (real) { passes += *std::max_element(cnt, cnt + 8); ideal++; }
+			}
+		}
+	}
+	// (3) tiles: CTA runs and tiles partition the slices in order; a table holds every rank its tile touches, at a slot
+	//     congruent to the rank mod 8; renumbered records and group headers lead back to the same ranks
+	long long expect = 0;
+	if (n_sl > 0) {
+		if ((int) th.cta_tile.size() != th.grid + 1 || th.cta_tile[0] != 0 || th.cta_tile[(size_t) th.grid] != (int) th.tiles.size()) viol++;
+		for (size_t t = 0; t < th.tiles.size(); t++) {
+			const TileDesc& T = th.tiles[t];
+			if (T.s0 != expect || T.s1 <= T.s0 || (T.n_slots & 7) || T.n_slots > th.slots_max || T.s1 - T.s0 > th.slices_max) viol++;
+			if (T.n_slots > slots_limit && T.s1 - T.s0 > 1) viol++;
+			expect = T.s1;
+			for (int i = 0; i < T.n_slots; i++) {
+				const int r = th.tab[(size_t) T.tab_off + i];
+				if (r >= 0 && (r & 7) != (i & 7)) viol++;
+			}
+			for (int w = T.s0; w < T.s1; w++) {
+				for (int g = 0; g < GPW; g++) {
+					const int2 gi = lay.grp[(size_t) w * GPW + g];
+					const int4 gt = th.grpT[(size_t) w * GPW + g];
+					if (gi.x < 0) { if (gt.x >= 0) viol++; continue; }
+					if (gt.x < 0 || gt.x >= T.n_slots || th.tab[(size_t) T.tab_off + gt.x] != gi.x || gt.y != gi.x || gt.z != gi.y || gt.w != lay.order[(size_t) gi.x]) viol++;
+				}
+				for (int at = lay.warp_off[w]; at < lay.warp_off[(size_t) w + 1]; at++) {
+					const int g = ((at - lay.warp_off[w]) & 31) / SPRING_LANES;
+					const HalfEdge& hl = th.heL[(size_t) at];
+					const HalfEdge& ht = lay.heT[(size_t) at];
+					if (hl.rs0 != ht.rs0 || hl.pal != ht.pal) viol++;
+					if (lay.grp[(size_t) w * GPW + g].x < 0) { if (hl.nbr != 0) viol++; continue; }
+					if (hl.nbr < 0 || hl.nbr >= T.n_slots || th.tab[(size_t) T.tab_off + hl.nbr] != ht.nbr) viol++;
+				}
+			}
+		}
+		if (expect != n_sl) viol++;
+	}
+	stats[0] = n_sl; stats[1] = pad; stats[2] = (long long) th.tiles.size(); stats[3] = th.slots_max;
+	stats[4] = passes; stats[5] = ideal; stats[6] = viol; stats[7] = (long long) lay.heT.size();
 	return ASS_OK;
 }
 

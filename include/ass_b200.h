@@ -241,6 +241,12 @@ int ass_probe_copy_bw(long long bytes, double* gbs);
  * CUDA's __dsqrt_rn on `samples` pseudo-random arguments with binary exponents in [exp_lo, exp_hi): the number of
  * arguments whose results differ in any bit, and the first such argument. */
 int ass_selfcheck_sqrt(long long samples, int exp_lo, int exp_hi, long long* mismatches, double* first_bad);
+/* Host-only self-check of what ass_set_springs builds for the spring kernels (no device is touched, so it runs in the CPU
+ * test suite): the spatial ranking, the CSR and the lane-transposed copy of the half-edge list, and the tile cut for `grid`
+ * persistent CTAs with shared-memory tables of at most `slots` entries.  pos_xyzm: n x {x, y, z, m}.  stats[0] slices,
+ * [1] padding records, [2] tiles, [3] largest table, [4] gather passes per step summed over all quarter warps and
+ * [5] their minimum (one each), [6] violated invariants (must be 0), [7] records in the lane-transposed copy. */
+int ass_selfcheck_spring_layout(const double* pos_xyzm, int n, const ass_spring* springs, int ns, int grid, int slots, long long* stats);
 /* total number of kernel launches issued by this library in this process */
 long long ass_launch_count(void);
 
