@@ -3,13 +3,14 @@
 // The reference walks the spring list once and scatter-adds +F/m_i, -F/m_j into both endpoints.  Here every node owns
 // the list of its incident half-edges (built by ass_set_springs) and a group of SPRING_LANES lanes sums them: no
 // atomics, fixed summation order (spring_math.cuh: fold_lanes), so the result is deterministic run to run.  Rows are
-// laid out in spatial (Morton) rank order and endpoint state is gathered from the rank-ordered mirror (common.cuh):
-// the neighbours of the nodes a warp works on are close in rank, so one request touches a few adjacent cache lines.
+// laid out in spatial (Morton) rank order and endpoint state comes from the rank-ordered mirror (common.cuh): through a
+// per-tile shared-memory table in the whole-body kernel (k_spring_tiles), through L1 in the CSR kernel that node slabs
+// of a sharded body use (k_spring_forces) -- the neighbours of the nodes a warp works on are close in rank.
 // The arithmetic is in spring_math.cuh.
 //
-// Algorithmic traffic: 32 B x NS + 80 B x N per evaluation.  Real traffic of this layout: 32 B x NS of
-// half-edge stream (two 16-byte records per spring, + ~6 % padding) + 48 B gathered per half-edge (L1/L2-resident)
-// + ~170 B x N.
+// Algorithmic traffic: 32 B x NS + 80 B x N per evaluation.  Real DRAM traffic of the tiled kernel (ncu, C3):
+// 35 B x NS of half-edge stream (two 16-byte records per spring, + 11 % padding) + ~150 B x N of mirror, acc and outputs;
+// the 48 B gathered per half-edge come out of shared memory, the tables are filled from L2 (~3 x 56 B x N).
 #include <stdlib.h>
 
 #include <algorithm>
