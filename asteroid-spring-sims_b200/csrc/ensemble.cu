@@ -16,7 +16,9 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -345,45 +347,80 @@ extern "C" int ass_ensemble_create(ass_ensemble** out, int n_bodies, const int* 
 			ens_free(e); ass_set_error("ass_ensemble_create: bad params for body %d", b); return ASS_EINVAL;
 		}
 		e->max_n = std::max(e->max_n, n);
-		const ass_spring* sp = springs + spring_off[b];
-		std::vector<vec4d> pos((size_t) n);
-		for (int i = 0; i < n; i++) {
-			const double* rr = (const double*) ((const unsigned char*) base + (size_t) (node_off[b] + i) * stride);
-			pos[(size_t) i].x = rr[0]; pos[(size_t) i].y = rr[1]; pos[(size_t) i].z = rr[2]; pos[(size_t) i].w = rr[9];
-			if (memcmp(&pos[(size_t) i].w, &pos[0].w, sizeof(double)) != 0) e->uni_mass = false;
+	}
+	// The members' layouts are independent: built a chunk at a time by a few host threads (a layout is ~10 ms of host work
+	// per 1k-node member), then appended in member order.
+	constexpr int CHUNK = 64;
+	const int n_threads = (int) std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+	std::vector<SpringLayout> lays(CHUNK);
+	std::vector<std::vector<int>> pidxs(CHUNK);
+	std::vector<int> rcs(CHUNK), bads(CHUNK);
+	std::vector<char> unis(CHUNK);
+	for (int b0 = 0; b0 < n_bodies; b0 += CHUNK) {
+		const int nb_chunk = std::min(CHUNK, n_bodies - b0);
+		for (int j = 0; j < nb_chunk; j++) {  // palette indices: one palette for the whole ensemble, filled in member order
+			const int b = b0 + j, ns = spring_off[b + 1] - spring_off[b];
+			const ass_spring* sp = springs + spring_off[b];
+			pidxs[(size_t) j].resize((size_t) ns);
+			for (int q = 0; q < ns; q++) pidxs[(size_t) j][(size_t) q] = pal_index(sp[q]);
 		}
-		std::vector<int> pidx((size_t) ns);
-		for (int q = 0; q < ns; q++) pidx[(size_t) q] = pal_index(sp[q]);
-		SpringLayout lay;
-		int bad = -1;
-		rc = ass_build_spring_layout(pos.data(), n, sp, ns, pidx.data(), lay, &bad);
-		if (rc == ASS_EINVAL) {
-			ass_set_error("ass_ensemble_create: body %d spring %d joins (%d,%d): indices are local to the body and must differ", b, bad,
-			              sp[bad].particle_1, sp[bad].particle_2);
-			ens_free(e);
-			return rc;
+		std::atomic<int> next(0);
+		auto work = [&]() {
+			for (int j = next.fetch_add(1); j < nb_chunk; j = next.fetch_add(1)) {
+				const int b = b0 + j, n = node_off[b + 1] - node_off[b], ns = spring_off[b + 1] - spring_off[b];
+				std::vector<vec4d> pos((size_t) n);
+				bool uni = true;
+				for (int i = 0; i < n; i++) {
+					const double* rr = (const double*) ((const unsigned char*) base + (size_t) (node_off[b] + i) * stride);
+					pos[(size_t) i].x = rr[0]; pos[(size_t) i].y = rr[1]; pos[(size_t) i].z = rr[2]; pos[(size_t) i].w = rr[9];
+					if (memcmp(&pos[(size_t) i].w, &pos[0].w, sizeof(double)) != 0) uni = false;
+				}
+				unis[(size_t) j] = uni ? 1 : 0;
+				bads[(size_t) j] = -1;
+				rcs[(size_t) j] = ass_build_spring_layout(pos.data(), n, springs + spring_off[b], ns, pidxs[(size_t) j].data(), lays[(size_t) j], &bads[(size_t) j]);
+			}
+		};
+		{
+			std::vector<std::thread> pool;
+			for (int t = 1; t < std::min(n_threads, nb_chunk); t++) pool.emplace_back(work);
+			work();
+			for (auto& th : pool) th.join();
 		}
-		const long long rec_base = (long long) heT.size();
-		if (rc || rec_base + (long long) lay.heT.size() > 0x7fffffffLL) {
-			ass_set_error("ass_ensemble_create: the members' half-edge records overflow a 32-bit index at body %d", b);
-			ens_free(e);
-			return ASS_EINVAL;
+		for (int j = 0; j < nb_chunk; j++) {
+			const int b = b0 + j, n = node_off[b + 1] - node_off[b], ns = spring_off[b + 1] - spring_off[b];
+			const ass_spring* sp = springs + spring_off[b];
+			const SpringLayout& lay = lays[(size_t) j];
+			const std::vector<int>& pidx = pidxs[(size_t) j];
+			if (!unis[(size_t) j]) e->uni_mass = false;
+			if (rcs[(size_t) j] == ASS_EINVAL) {
+				const int bad = bads[(size_t) j];
+				ass_set_error("ass_ensemble_create: body %d spring %d joins (%d,%d): indices are local to the body and must differ", b, bad,
+				              sp[bad].particle_1, sp[bad].particle_2);
+				ens_free(e);
+				return ASS_EINVAL;
+			}
+			const long long rec_base = (long long) heT.size();
+			if (rcs[(size_t) j] || rec_base + (long long) lay.heT.size() > 0x7fffffffLL) {
+				ass_set_error("ass_ensemble_create: the members' half-edge records overflow a 32-bit index at body %d", b);
+				ens_free(e);
+				return ASS_EINVAL;
+			}
+			BodyDesc& d = e->desc[b];
+			d.node_off = node_off[b]; d.n = n;
+			d.grp_off = (int) grp.size(); d.swarp_off = (int) warp_off.size(); d.n_swarps = (int) lay.warp_off.size() - 1;
+			d.pal_idx = ns > 0 ? pidx[0] : 0;
+			for (int q = 1; q < ns; q++)
+				if (pidx[(size_t) q] != pidx[0]) { d.pal_idx = -1; break; }
+			if (d.pal_idx < 0) all_pal1 = false;
+			for (int i = 0; i < n; i++) {
+				perm[(size_t) node_off[b] + i] = node_off[b] + lay.rank[(size_t) i];
+				ord[(size_t) node_off[b] + lay.rank[(size_t) i]] = i;
+			}
+			grp.insert(grp.end(), lay.grp.begin(), lay.grp.end());
+			for (int w : lay.warp_off) warp_off.push_back((int) (rec_base + w));
+			heT.insert(heT.end(), lay.heT.begin(), lay.heT.end());
+			e->total_he += 2LL * ns;
 		}
-		BodyDesc& d = e->desc[b];
-		d.node_off = node_off[b]; d.n = n;
-		d.grp_off = (int) grp.size(); d.swarp_off = (int) warp_off.size(); d.n_swarps = (int) lay.warp_off.size() - 1;
-		d.pal_idx = ns > 0 ? pidx[0] : 0;
-		for (int q = 1; q < ns; q++)
-			if (pidx[(size_t) q] != pidx[0]) { d.pal_idx = -1; break; }
-		if (d.pal_idx < 0) all_pal1 = false;
-		for (int i = 0; i < n; i++) {
-			perm[(size_t) node_off[b] + i] = node_off[b] + lay.rank[(size_t) i];
-			ord[(size_t) node_off[b] + lay.rank[(size_t) i]] = i;
-		}
-		grp.insert(grp.end(), lay.grp.begin(), lay.grp.end());
-		for (int w : lay.warp_off) warp_off.push_back((int) (rec_base + w));
-		heT.insert(heT.end(), lay.heT.begin(), lay.heT.end());
-		e->total_he += 2LL * ns;
 	}
 	fill_desc(e);
 	e->pal1 = all_pal1;
