@@ -1032,9 +1032,11 @@ __global__ void k_scatter_props(const ass_spring* __restrict__ sp, const int* __
 		HalfEdge* h = he + slot[(size_t) 2 * q + side];
 		h->rs0 = rs0;
 		h->pal = pi;
-		HalfEdge* hl = heL + slotT[(size_t) 2 * q + side];  // the tiled kernel's copy
-		hl->rs0 = rs0;
-		hl->pal = pi;
+		if (heL) {  // the tiled kernel's copy (absent when no tile cut exists: springs.cu, ass_build_spring_tiles)
+			HalfEdge* hl = heL + slotT[(size_t) 2 * q + side];
+			hl->rs0 = rs0;
+			hl->pal = pi;
+		}
 	}
 }
 
@@ -1054,7 +1056,7 @@ extern "C" int ass_update_spring_props(ass_sim* s, const ass_spring* sp, int ns)
 	if ((rc = upload_palette(s, pal))) return rc;
 	CU_TRY(cudaMemcpyAsync(s->stage.p, sp, sp_bytes, cudaMemcpyHostToDevice, s->stream));
 	CU_TRY(cudaMemcpyAsync((char*) s->stage.p + sp_bytes, pidx.data(), sizeof(int) * (size_t) ns, cudaMemcpyHostToDevice, s->stream));
-	k_scatter_props<<<(ns + 255) / 256, 256, 0, s->stream>>>((const ass_spring*) s->stage.p, (const int*) ((char*) s->stage.p + sp_bytes), s->slot, s->slotT, s->he, s->heL, ns);
+	k_scatter_props<<<(ns + 255) / 256, 256, 0, s->stream>>>((const ass_spring*) s->stage.p, (const int*) ((char*) s->stage.p + sp_bytes), s->slot, s->slotT, s->he, s->tiles_grid > 0 ? s->heL : nullptr, ns);
 	LAUNCH_CHECK();
 	ass_toc(s, ASS_K_XFER);
 	CU_TRY(cudaStreamSynchronize(s->stream));

@@ -616,6 +616,30 @@ def test_tiled_spring_kernel_with_many_tiles_per_cta(gpu, body015, monkeypatch):
         assert same_bits(ref[0], o[0]) and same_bits(ref[1], o[1])
 
 
+def test_hub_body_is_served_by_the_csr_kernel(gpu, oracle):
+    """A node with more neighbours than a shared-memory table holds (~2 900) cannot be tiled: ass_set_springs then builds no
+    tile cut and whole-body evaluations run on the CSR kernel -- including property updates -- with the usual accuracy."""
+    rng = np.random.default_rng(11)
+    n = 3200
+    p = np.zeros((n, 11)); p[:, :3] = rng.uniform(-1.0, 1.0, (n, 3)); p[:, 3:6] = rng.normal(0.0, 0.01, (n, 3)); p[:, 9] = 1.0 / n
+    pairs = [(0, j) for j in range(1, n)] + [(j, j + 1) for j in range(1, n - 1)]
+    sp = np.zeros(len(pairs), dtype=gpu.SPRING_DTYPE)
+    sp["particle_1"] = [a for a, _ in pairs]; sp["particle_2"] = [b for _, b in pairs]
+    sp["k"] = 0.05; sp["gamma"] = 2.0
+    sp["rs0"] = np.linalg.norm(p[sp["particle_1"], :3] - p[sp["particle_2"], :3], axis=1) * 0.98
+    want = p.copy(); oracle.spring_forces(want, sp)
+    sp2 = sp.copy(); sp2["k"] *= 1.5
+    want2 = p.copy(); oracle.spring_forces(want2, sp2)
+    with new_sim(gpu, p, sp) as s:
+        s.spring_forces()
+        out = s.download(p.copy())
+        s.update_spring_props(sp2)
+        s.zero_accel(); s.spring_forces()
+        out2 = s.download(p.copy())
+    assert acc_err(out[:, 6:9], want[:, 6:9]) <= ACC_TOL
+    assert acc_err(out2[:, 6:9], want2[:, 6:9]) <= ACC_TOL
+
+
 def test_spring_props_update_reaches_every_copy_of_the_list(gpu, oracle, body015, monkeypatch):
     """set_gamma / adjust_spring_props style edits go through ass_update_spring_props, which patches the CSR and the tile
     copies of the half-edge list in place: both kernels must see the new values."""
