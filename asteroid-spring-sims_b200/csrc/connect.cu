@@ -13,6 +13,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <cmath>
 #include <unordered_set>
 #include <vector>
 
@@ -26,10 +27,15 @@ struct Grid {
 };
 
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+// fmin / fmax first: they map NaN to the bound and keep +-inf inside the int range, so a non-finite coordinate lands in
+// a border cell instead of in an undefined double -> int conversion
+__device__ __forceinline__ int cell_axis(double x, double x0, double inv_h, int n) {
+	return (int) fmin(fmax(floor((x - x0) * inv_h), 0.0), (double) (n - 1));
+}
 __device__ __forceinline__ void cell_of(const Grid g, double x, double y, double z, int& cx, int& cy, int& cz) {
-	cx = clampi((int) floor((x - g.x0) * g.inv_h), 0, g.nx - 1);
-	cy = clampi((int) floor((y - g.y0) * g.inv_h), 0, g.ny - 1);
-	cz = clampi((int) floor((z - g.z0) * g.inv_h), 0, g.nz - 1);
+	cx = cell_axis(x, g.x0, g.inv_h, g.nx);
+	cy = cell_axis(y, g.y0, g.inv_h, g.ny);
+	cz = cell_axis(z, g.z0, g.inv_h, g.nz);
 }
 
 // ---- bounding box ----
@@ -37,6 +43,9 @@ __global__ void k_bbox(const vec4d* __restrict__ posm, int lo, int hi, double* _
 	double mn[3] = { 1e308, 1e308, 1e308 }, mx[3] = { -1e308, -1e308, -1e308 };
 	for (int i = lo + blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += gridDim.x * blockDim.x) {
 		const vec4d p = posm[i];
+		// a particle with a non-finite coordinate (a blown-up run) has no partner within any cutoff -- every length to it
+		// is inf or NaN, which is never < max_dist -- so it stays out of the box; cell_of() clamps it into a border cell
+		if (!(isfinite(p.x) && isfinite(p.y) && isfinite(p.z))) continue;
 		mn[0] = fmin(mn[0], p.x); mn[1] = fmin(mn[1], p.y); mn[2] = fmin(mn[2], p.z);
 		mx[0] = fmax(mx[0], p.x); mx[1] = fmax(mx[1], p.y); mx[2] = fmax(mx[2], p.z);
 	}
@@ -226,10 +235,16 @@ int build_grid(ass_sim* s, int lo, int hi, double h, Scratch& sc, Grid& g) {
 	// inflate the edge a hair so that |x_i - x_j| < cutoff can never straddle two cells after rounding, and coarsen
 	// sparse clouds: a coarser grid finds the same pairs
 	h *= (1.0 + 1e-9);
+	for (int d = 0; d < 3; d++)
+		if (!(mx[d] >= mn[d])) mn[d] = mx[d] = 0.0;  // no finite particle at all: one cell
 	const double max_cells = 8.0 * cnt + 4096.0;
-	for (;;) {
+	for (int tries = 0;; tries++) {
 		const double cells = (floor((mx[0] - mn[0]) / h) + 1) * (floor((mx[1] - mn[1]) / h) + 1) * (floor((mx[2] - mn[2]) / h) + 1);
 		if (cells <= max_cells) break;
+		if (tries > 2000 || !std::isfinite(h)) {  // cannot happen for a finite box; never spin
+			h = std::max(std::max(mx[0] - mn[0], mx[1] - mn[1]), mx[2] - mn[2]) * 2.0 + 1.0;
+			break;
+		}
 		h *= 1.5;
 	}
 	g.x0 = mn[0]; g.y0 = mn[1]; g.z0 = mn[2];
@@ -307,10 +322,9 @@ extern "C" int ass_connect_springs_dist(ass_sim* s, double max_dist, int lo, int
 		// add_spring returns the existing index instead of adding (springs.cpp:70-79)
 		std::unordered_set<uint64_t> have;
 		have.reserve((size_t) n_existing * 2);
-		for (int q = 0; q < n_existing; q++) {
-			const int a = std::min(existing[q].particle_1, existing[q].particle_2), b = std::max(existing[q].particle_1, existing[q].particle_2);
-			have.insert(((uint64_t) (uint32_t) a << 32) | (uint32_t) b);
-		}
+		// ... matching (particle_1, particle_2) == (low, high) AS STORED: a list entry written the other way round does not
+		// count as a duplicate there, so it does not here
+		for (int q = 0; q < n_existing; q++) have.insert(((uint64_t) (uint32_t) existing[q].particle_1 << 32) | (uint32_t) existing[q].particle_2);
 		kept = 0;
 		for (int q = 0; q < total; q++) {
 			const uint64_t key = ((uint64_t) (uint32_t) h[q].particle_1 << 32) | (uint32_t) h[q].particle_2;

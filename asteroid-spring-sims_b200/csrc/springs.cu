@@ -201,7 +201,7 @@ __global__ void k_sprung_mass_differs(const vec4d* __restrict__ posm, const int*
 // Do all nodes that carry springs have the same mass (m_red = m / 2, spring_math.cuh)?  Cached per (masses, topology).
 static int springs_uniform_mass(ass_sim* s, bool* uni) {
 	if (s->uni_mass_epoch != s->mass_epoch || s->uni_spring_epoch != s->spring_epoch) {
-		int* d_flag = (int*) s->d_red + 32;  // tail of the simulation's small reduction scratch
+		int* d_flag = (int*) (s->d_red + 48);  // doubles [48..63] of the reduction scratch: nothing else uses them (diagnostics [0..20], mindist [32])
 		CU_TRY(cudaMemsetAsync(d_flag, 0, sizeof(int), s->stream));
 		if (s->n > 0 && s->ns > 0) {
 			k_sprung_mass_differs<<<(s->n + 255) / 256, 256, 0, s->stream>>>(s->posm, s->order, s->row_ptr, s->n, d_flag);

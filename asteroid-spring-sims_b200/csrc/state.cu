@@ -369,7 +369,9 @@ extern "C" int ass_set_params(ass_sim* s, const ass_params* p) {
 	REQUIRE(p->gravity == 0 || p->gravity == 1, ASS_EINVAL, "gravity must be 0 (NONE) or 1 (BASIC)");
 	REQUIRE(p->additional_forces >= 0 && p->additional_forces <= 2, ASS_EINVAL, "additional_forces must be 0, 1 or 2");
 	REQUIRE(p->heartbeat == 0 || p->heartbeat == 1, ASS_EINVAL, "heartbeat must be 0 or 1");
-	if (p->dt != s->prm.dt) s->predrifted = false;
+	// positions that already carry the next step's half-drift (ass_shard_finish(pre_drift_next = 1)) were drifted with
+	// the OLD dt: changing it now would silently mix two step sizes
+	REQUIRE(!(s->predrifted && p->dt != s->prm.dt), ASS_ESTATE, "dt cannot change while positions are pre-drifted: finish a step without pre_drift_next first");
 	s->prm = *p;
 	return ASS_OK;
 }
@@ -486,6 +488,10 @@ extern "C" int ass_upload_particles(ass_sim* s, const void* base, size_t stride,
 		if (n != s->n) { s->ns = 0; s->n_he = 0; ass_sym_plans_free(s); }  // springs and gravity plans refer to the old body
 		s->n = n;
 	}
+	// a pre-drifted body (ass_shard_finish(pre_drift_next = 1)) may only be REPLACED: patching positions or velocities
+	// into a half-drifted state would be applied to the wrong instant
+	REQUIRE(!s->predrifted || (fields & (ASS_F_POS | ASS_F_VEL)) == (ASS_F_POS | ASS_F_VEL), ASS_ESTATE,
+	        "positions are pre-drifted: upload positions and velocities together, or finish a step without pre_drift_next first");
 	s->predrifted = false;
 	if (fields & ASS_F_MASS) s->mass_epoch++;
 	if (n == 0) { s->have_state = true; return ASS_OK; }
@@ -982,6 +988,10 @@ extern "C" int ass_set_springs(ass_sim* s, const ass_spring* sp, int ns) {
 	}
 	std::vector<vec4d>().swap(pos);
 	const size_t nhe = lay.he.size();
+	// from here on the old list's arrays may be freed and re-allocated: until the new list is complete the simulation
+	// has NO springs (an allocation failure below must not leave kernels pointed at freed rows)
+	s->ns = 0; s->n_he = 0; s->n_swarps = 0; s->tiles_grid = 0;
+	s->spring_epoch++;
 	if ((rc = reserve_sorted(s, n))) return rc;
 	if (nhe > s->he_cap) {
 		cudaFree(s->he); cudaFree(s->slot); cudaFree(s->slotT);
@@ -1017,7 +1027,6 @@ extern "C" int ass_set_springs(ass_sim* s, const ass_spring* sp, int ns) {
 	s->ns = ns;
 	s->n_he = (int) nhe;
 	s->max_degree = lay.max_degree;
-	s->spring_epoch++;
 	return ASS_OK;
 }
 

@@ -242,10 +242,17 @@ typedef struct {
 } grid_t;
 
 static inline int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+/* a non-finite coordinate (a blown-up run) goes to a border cell: such a particle is never within any cutoff of another */
+static inline int cell_axis(double x, double x0, double inv_h, int n) {
+	const double q = floor((x - x0) * inv_h);
+	if (!(q >= 0.0)) return 0; /* also NaN */
+	if (q > (double) (n - 1)) return n - 1;
+	return (int) q;
+}
 static inline int cell_of(const grid_t* g, double x, double y, double z, int* cx, int* cy, int* cz) {
-	*cx = clampi((int) floor((x - g->x0) * g->inv_h), 0, g->nx - 1);
-	*cy = clampi((int) floor((y - g->y0) * g->inv_h), 0, g->ny - 1);
-	*cz = clampi((int) floor((z - g->z0) * g->inv_h), 0, g->nz - 1);
+	*cx = cell_axis(x, g->x0, g->inv_h, g->nx);
+	*cy = cell_axis(y, g->y0, g->inv_h, g->ny);
+	*cz = cell_axis(z, g->z0, g->inv_h, g->nz);
 	return (*cz * g->ny + *cy) * g->nx + *cx;
 }
 
@@ -255,7 +262,10 @@ static int grid_alloc(grid_t* g, double xmin, double ymin, double zmin, double x
 		double h, int lo, int count, double max_cells) {
 	h *= (1.0 + 1e-9);
 	/* bound the cell count (sparse clouds): coarsening the grid never changes which pairs pass the cutoff */
-	for (;;) {
+	if (!(xmax >= xmin)) xmin = xmax = 0.0; /* no finite particle at all: one cell */
+	if (!(ymax >= ymin)) ymin = ymax = 0.0;
+	if (!(zmax >= zmin)) zmin = zmax = 0.0;
+	for (int tries = 0; tries < 4000; tries++) {
 		double cells = (floor((xmax - xmin) / h) + 1) * (floor((ymax - ymin) / h) + 1) * (floor((zmax - zmin) / h) + 1);
 		if (cells <= max_cells) break;
 		h *= 1.5;
@@ -282,11 +292,13 @@ static inline void grid_insert(grid_t* g, const double* p, int idx) {
 }
 static void bbox(const double* p, int lo, int hi, double* mn, double* mx) {
 	for (int d = 0; d < 3; d++) { mn[d] = DBL_MAX; mx[d] = -DBL_MAX; }
-	for (int i = lo; i < hi; i++)
+	for (int i = lo; i < hi; i++) {
+		if (!(isfinite(P(i, 0)) && isfinite(P(i, 1)) && isfinite(P(i, 2)))) continue; /* pairs with nobody: stays out of the box */
 		for (int d = 0; d < 3; d++) {
 			if (P(i, d) < mn[d]) mn[d] = P(i, d);
 			if (P(i, d) > mx[d]) mx[d] = P(i, d);
 		}
+	}
 }
 
 static int cmp_int(const void* a, const void* b) { return (*(const int*) a > *(const int*) b) - (*(const int*) a < *(const int*) b); }

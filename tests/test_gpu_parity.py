@@ -671,3 +671,67 @@ def test_spring_forces_nonuniform_mass_matches_oracle(gpu, oracle, body015):
         s.spring_forces()
         out = s.download(p.copy())
     assert acc_err(out[:, 6:9], want[:, 6:9]) <= ACC_TOL
+
+
+# ---------------------------------------------------------------------------------------------------
+# degenerate inputs the reference is well defined on (round-1 advisor findings)
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("mode", ["tiles", "csr"])
+def test_zero_length_spring_gives_zero_force(gpu, oracle, body015, monkeypatch, mode):
+    """Duplicate points get a spring with rs0 = 0 from connect_springs_dist; the reference gives it len = L_EPS,
+    len_hat = 0 and a zero force (springs.cpp:302-312).  The branch-free sqrt must not turn that into NaN."""
+    _spring_kernel_mode(monkeypatch, mode)
+    g = body015
+    p = g["start"].copy(); p[:, 6:9] = 0.0
+    p[7, :3] = p[3, :3]                      # node 7 sits exactly on node 3 ...
+    p[7, 3:6] = p[3, 3:6] + 0.01            # ... and moves relative to it
+    with new_sim(gpu, p) as s:
+        sp = s.connect_springs_dist(2.3 * 0.15, 0, len(p), K, GAMMA)
+        want_sp = oracle.connect_springs_dist(p, 2.3 * 0.15, 0, len(p), K, GAMMA)
+        assert sp.tobytes() == want_sp.tobytes()
+        zero = sp[(sp["particle_1"] == 3) & (sp["particle_2"] == 7)]
+        assert len(zero) == 1 and zero["rs0"][0] == 0.0
+        s.set_springs(sp)
+        s.spring_forces()
+        out = s.download(p.copy())
+        want = p.copy(); oracle.spring_forces(want, sp)
+        assert np.all(np.isfinite(out[:, 6:9]))
+        assert acc_err(out[:, 6:9], want[:, 6:9]) <= ACC_TOL
+        s.set_params(dt=1e-3, gravity=0, additional_forces=2)
+        s.step(3)
+        assert np.all(np.isfinite(s.download(p.copy())[:, :9]))
+
+
+def test_connect_duplicate_rule_matches_entries_as_stored(gpu, oracle):
+    """add_spring only recognises an existing spring stored as (low, high) (springs.cpp:72-79): an entry written the
+    other way round does not suppress the pair."""
+    P = kat_particles()
+    ex = np.zeros(2, dtype=SPRING_DTYPE)
+    ex["particle_1"] = (1, 0); ex["particle_2"] = (0, 2)          # (1,0) is reversed, (0,2) is canonical
+    ex["k"] = 1.0
+    want = oracle.connect_springs_dist(P, 100.0, 0, 3, 2.0, 1.0, existing=ex, n2=True)
+    with new_sim(gpu, P) as s:
+        got = s.connect_springs_dist(100.0, 0, 3, 2.0, 1.0, existing=ex)
+    assert got.tobytes() == want[len(ex):].tobytes()
+    assert [(a, b) for a, b in zip(got["particle_1"], got["particle_2"])] == [(0, 1), (1, 2)]
+
+
+def test_connect_and_mindist_survive_non_finite_positions(gpu, oracle, body015):
+    """A blown-up particle (inf / NaN coordinate) pairs with nobody in the reference; the grid must neither hang nor
+    lose the finite pairs."""
+    g = body015
+    p = g["start"].copy()
+    p[5, 0] = np.inf
+    p[11, 1] = np.nan
+    p[17, 2] = -np.inf
+    with new_sim(gpu, p) as s:
+        got = s.connect_springs_dist(2.3 * 0.15, 0, len(p), K, GAMMA)
+        md = s.mindist()
+    want = oracle.connect_springs_dist(p, 2.3 * 0.15, 0, len(p), K, GAMMA, n2=True)
+    assert got.tobytes() == want.tobytes()
+    touched = set(got["particle_1"]) | set(got["particle_2"])
+    assert not ({5, 11, 17} & touched)
+    q = np.delete(p, [5, 11, 17], axis=0)
+    assert md == oracle.mindist(q, n2=True)
+    with new_sim(gpu, np.full((4, 11), np.nan)) as s:      # nothing finite at all
+        assert len(s.connect_springs_dist(1.0, 0, 4, K, GAMMA)) == 0
