@@ -302,6 +302,11 @@ class Sim:
         _chk(lib().ass_sum_mass(self._h, C.c_int(lo), C.c_int(hi), C.byref(out)))
         return out.value
 
+    def upload_range(self, p, lo, hi, fields=F_ALL):
+        """Rows [lo, hi) of the caller's full array `p` -> particles [lo, hi)."""
+        base, stride, n = _rows(p)
+        _chk(lib().ass_upload_range(self._h, base, stride, C.c_int(lo), C.c_int(hi), C.c_uint(fields)))
+
     def download_range(self, p, lo, hi, fields=F_ALL):
         base, stride, n = _rows(p)
         _chk(lib().ass_download_range(self._h, base, stride, C.c_int(lo), C.c_int(hi), C.c_uint(fields)))
@@ -351,6 +356,18 @@ class Sim:
         _chk(lib().ass_mark_end(self._h, C.byref(ms)))
         return ms.value
 
+    def lap_begin(self):
+        _chk(lib().ass_lap_begin(self._h))
+
+    def lap_end(self):
+        _chk(lib().ass_lap_end(self._h))
+
+    def lap_collect(self):
+        """(sum of the laps in ms, number of laps) since the last collect; synchronises."""
+        ms, n = C.c_double(), C.c_int()
+        _chk(lib().ass_lap_collect(self._h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
     def l2_flush(self):
         _chk(lib().ass_l2_flush(self._h))
 
@@ -371,17 +388,9 @@ class Sim:
     def shard_import_local(self, peer_rank, peer):
         _chk(lib().ass_shard_import_local(self._h, C.c_int(peer_rank), peer._h))
 
-    def shard_begin(self):
-        _chk(lib().ass_shard_begin(self._h))
-
-    def shard_exchange(self):
-        _chk(lib().ass_shard_exchange(self._h))
-
-    def shard_gravity(self):
-        _chk(lib().ass_shard_gravity(self._h))
-
-    def shard_finish(self, pre_drift_next=False):
-        _chk(lib().ass_shard_finish(self._h, C.c_int(int(pre_drift_next))))
+    def shard_step(self, nsteps=1, pre_drift_last=False):
+        """reb_step x nsteps for the own slab; collective, queued (sync() or a download waits for it)."""
+        _chk(lib().ass_shard_step(self._h, C.c_int(nsteps), C.c_int(int(pre_drift_last))))
 
     def shard_gather(self):
         _chk(lib().ass_shard_gather(self._h))

@@ -74,16 +74,28 @@ struct DevBuf {
 	size_t bytes = 0;
 };
 
+// device-side meeting points of a sharded body's ranks (shard.cu): 64-bit epochs, one row per phase, one slot per rank
+#define ASS_SHARD_MAX_RANKS 16
+#define ASS_SHARD_PHASES 3
+#define ASS_SHARD_POS 0     // slab carries the drifted positions / velocities of step e
+#define ASS_SHARD_PART 1    // partial accelerations of step e for the other slabs are complete
+#define ASS_SHARD_GATHER 2  // 2c - 1: slab final for gather c;  2c: this rank has pulled everybody's
+
 struct ShardInfo {
 	int rank = 0, nranks = 1;
 	int lo = 0, hi = 0;               // owned slab of targets / spring owners
 	std::vector<int> bounds;          // nranks + 1 slab boundaries
-	vec4d* window = nullptr;          // one exportable allocation [posm (N) | vel (N)]; sim->posm / sim->vel point into it
+	// one exportable allocation [posm0 | vel0 | posm1 | vel1 | partial accelerations | flags]; sim->posm / vel point at
+	// buffer `cur`, sim->posm_alt / vel_alt at the other one
+	vec4d* window = nullptr;
+	int cur = 0;
+	unsigned long long epoch = 0;         // steps started since ass_shard_setup
+	unsigned long long gather_epoch = 0;  // gathers started
+	unsigned long long gather_pending = 0;  // GATHER value every peer must reach before the own slab may move again
 	std::vector<vec4d*> peer_window;  // peers' windows mapped here (nullptr for self)
 	std::vector<char> peer_is_ipc;    // mapped through cudaIpcOpenMemHandle (needs closing) or a same-process pointer
 	cudaStream_t copy_stream = nullptr;
 	cudaEvent_t pulled = nullptr;
-	int rows_local = 0;               // partial-sum rows written by the own-slab-sources launch of this step
 	bool active = false;
 };
 
@@ -151,9 +163,9 @@ struct ass_sim {
 	int4* grpT = nullptr;
 	int* tile_tab = nullptr;
 	int4* tile_desc = nullptr;  // (first slice, end slice, offset into tile_tab, slots)
-	int* cta_tile = nullptr;    // tiles_grid + 1: CTA c takes tiles [cta_tile[c], cta_tile[c+1])
+	std::vector<int> tile_heads;  // per CTA: (first tile, tile count, first tile's descriptor, last slice): kernel parameters
 	int tiles_grid = 0, tile_slots_max = 0, tile_slices_max = 0;
-	size_t heL_cap = 0, grpT_cap = 0, tile_tab_cap = 0, tile_desc_cap = 0, cta_tile_cap = 0;
+	size_t heL_cap = 0, grpT_cap = 0, tile_tab_cap = 0, tile_desc_cap = 0;
 	double2* pal = nullptr;   // palette of distinct (k, gamma) pairs
 	double2* palf = nullptr;  // the same entries as the force kernels want them: (-k, -max(gamma, 0)); lives behind pal
 	int n_pal = 0;
@@ -177,16 +189,21 @@ struct ass_sim {
 	std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pool;
 	std::vector<std::pair<int, int>> ev_open;  // (class, pool index) pending
 	cudaEvent_t mark0 = nullptr, mark1 = nullptr;
+	std::vector<std::pair<cudaEvent_t, cudaEvent_t>> lap_ev;  // ass_lap_begin / ass_lap_end
+	int lap_open = 0;
 
 	ShardInfo shard;
 };
 
 void ass_shard_release(ass_sim* s);  // shard.cu
+int ass_shard_sync(ass_sim* s);
 // gravity_sym.cu
 void ass_sym_plans_free(ass_sim* s);
 bool ass_gravity_sym_applicable(int count);
 int ass_launch_gravity_sym(ass_sim* s, int lo, int hi);
 int ass_launch_gravity_sym_pair(ass_sim* s, int rlo, int rhi, int slo, int shi, vec4d* res_out, bool res_add, vec4d* str_out, bool str_add);
+// build (or refresh) the plan of a range pair now: whatever allocation and synchronisation it needs happens here, not in the launch
+int ass_gravity_sym_prepare(ass_sim* s, int rlo, int rhi, int slo, int shi);
 int ass_buf_reserve(DevBuf& b, size_t bytes);
 // order[k] = node of rank k along a Morton curve through pos[0..n) (state.cu); deterministic, ties keep node order
 void ass_morton_order(const vec4d* pos, size_t n, std::vector<int>& order);
@@ -224,6 +241,9 @@ void ass_toc(ass_sim* s, int klass);
 int ass_launch_spring_forces(ass_sim* s, bool zero_first, bool mirror_fresh);
 int ass_launch_spring_forces_range(ass_sim* s, bool zero_first, int lo, int hi);
 int ass_launch_spring_kick_drift(ass_sim* s, bool zero_first, double dt, bool pre_drift_next, bool mirror_fresh);
+// the same for NODES [lo, hi) of a sharded body: reads posm / vel (all nodes), writes posm_alt / vel_alt (own nodes); no swap
+int ass_launch_spring_kick_drift_range(ass_sim* s, bool zero_first, double dt, bool pre_drift_next, int lo, int hi);
+int ass_springs_prepare(ass_sim* s);  // the equal-mass verdict (may synchronise), taken before a step is queued
 // gravity.cu
 int ass_launch_gravity(ass_sim* s);
 int ass_gravity_rows(int n_tgt, int n_src);

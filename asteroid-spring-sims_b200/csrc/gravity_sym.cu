@@ -420,5 +420,11 @@ int ass_launch_gravity_sym_pair(ass_sim* s, int rlo, int rhi, int slo, int shi, 
 	return ASS_OK;
 }
 
+int ass_gravity_sym_prepare(ass_sim* s, int rlo, int rhi, int slo, int shi) {
+	if (rhi <= rlo || shi <= slo) return ASS_OK;
+	SymPlan* p = nullptr;
+	return get_plan(s, rlo, rhi, slo, shi, &p);
+}
+
 // a = gravity among particles [lo, hi) (every particle both source and target), pair-once
 int ass_launch_gravity_sym(ass_sim* s, int lo, int hi) { return ass_launch_gravity_sym_pair(s, lo, hi, lo, hi, s->acc, false, nullptr, false); }

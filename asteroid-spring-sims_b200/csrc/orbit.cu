@@ -126,16 +126,6 @@ __global__ void k_drift_bin(const vec4d* __restrict__ posm, vec4d* __restrict__ 
 	vel[p2] = vb;
 }
 
-// rows [lo, hi) packed densely, 10 doubles each (x y z vx vy vz ax ay az m)
-__global__ void k_pack_range(double* __restrict__ out, int lo, int hi, const vec4d* __restrict__ posm, const vec4d* __restrict__ vel,
-		const vec4d* __restrict__ acc) {
-	const int i = lo + blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= hi) return;
-	const vec4d p = posm[i], v = vel[i], a = acc[i];
-	double* r = out + (size_t) (i - lo) * 10;
-	r[0] = p.x; r[1] = p.y; r[2] = p.z; r[3] = v.x; r[4] = v.y; r[5] = v.z; r[6] = a.x; r[7] = a.y; r[8] = a.z; r[9] = p.w;
-}
-
 }  // namespace
 
 #define ENTER_ORB(s)                                                                      \
@@ -211,34 +201,3 @@ extern "C" int ass_sum_mass(ass_sim* s, int i_low, int i_high, double* out) {
 	return ASS_OK;
 }
 
-extern "C" int ass_download_range(ass_sim* s, void* base, size_t stride, int i_low, int i_high, unsigned fields) {
-	REQUIRE(s, ASS_EINVAL, "null sim");
-	REQUIRE(s->have_state, ASS_ESTATE, "no particle state on the device");
-	REQUIRE(!s->predrifted, ASS_ESTATE, "internal: positions are mid-step");
-	REQUIRE(i_low >= 0 && i_high <= s->n && i_low <= i_high, ASS_EINVAL, "bad particle range");
-	REQUIRE(stride >= 10 * sizeof(double) && stride % sizeof(double) == 0, ASS_EINVAL, "stride must hold the 10 leading doubles and be 8-byte aligned");
-	REQUIRE((fields & ~ASS_F_ALL) == 0 && fields != 0, ASS_EINVAL, "bad field mask");
-	if (i_low == i_high) return ASS_OK;
-	REQUIRE(base, ASS_EINVAL, "null particle array");
-	int rc = ass_ensure_device();
-	if (rc) return rc;
-	const int cnt = i_high - i_low;
-	const size_t dense = (size_t) cnt * 10 * sizeof(double);
-	if ((rc = ass_buf_reserve(s->stage, dense))) return rc;
-	std::vector<double> host((size_t) cnt * 10);
-	ass_tic(s, ASS_K_XFER);
-	k_pack_range<<<(cnt + 255) / 256, 256, 0, s->stream>>>((double*) s->stage.p, i_low, i_high, s->posm, s->vel, s->acc);
-	LAUNCH_CHECK();
-	CU_TRY(cudaMemcpyAsync(host.data(), s->stage.p, dense, cudaMemcpyDeviceToHost, s->stream));
-	ass_toc(s, ASS_K_XFER);
-	CU_TRY(cudaStreamSynchronize(s->stream));
-	for (int i = 0; i < cnt; i++) {
-		double* r = (double*) ((unsigned char*) base + (size_t) (i_low + i) * stride);
-		const double* q = host.data() + (size_t) i * 10;
-		if (fields & ASS_F_POS) { r[0] = q[0]; r[1] = q[1]; r[2] = q[2]; }
-		if (fields & ASS_F_VEL) { r[3] = q[3]; r[4] = q[4]; r[5] = q[5]; }
-		if (fields & ASS_F_ACC) { r[6] = q[6]; r[7] = q[7]; r[8] = q[8]; }
-		if (fields & ASS_F_MASS) r[9] = q[9];
-	}
-	return ASS_OK;
-}

@@ -13,25 +13,35 @@
 //                                          lower rank takes its own lower half against the whole other slab, the higher
 //                                          rank its whole slab against the other's upper half)
 // and trailing point masses (params.n_perts) are handled one-sidedly by whoever owns the targets.  The partials for
-// foreign slabs are left in an exported buffer; their owners pull and add them in a fixed order.
+// foreign slabs are left in the exported window; their owners pull and add them in a fixed order.
 //
-// Exchange.  posm, vel and the partial-acceleration buffer live in ONE exportable allocation (the "window").  Peers map
-// it (CUDA IPC across processes, or the raw pointer inside one process); every transfer is a PULL by the copy engines on
-// a side stream: the peers' slabs while the SMs already run the own-slab triangle, the partials before the springs.
+// THE HOST IS NOT IN THE STEP.  ass_shard_step queues nsteps whole steps on the rank's two streams and returns; ranks
+// meet on the DEVICE through 64-bit epoch flags that live in every rank's window and are written by the producers
+// straight into their peers' memory (st.release.sys over NVLink) and polled locally by the consumers (ld.acquire.sys):
+//     POS[r]  = e   rank r's slab carries the (drifted) positions and velocities of step e
+//     PART[r] = e   rank r's partial accelerations of step e for the other slabs are complete
+// The window is ONE exportable allocation  [posm0 | vel0 | posm1 | vel1 | partials | flags]  mapped by every peer (CUDA
+// IPC across processes, the raw pointer inside one process).  Everything that belongs to step e lives in buffer e & 1
+// and the kick of step e writes the own slab of buffer (e+1) & 1 (the ping-pong the unsharded fused loop uses too), so a
+// rank that runs ahead never overwrites what a slower peer still reads: buffer b is next written during step e+1, which
+// cannot start anywhere before every rank has published POS(e+1), i.e. has finished step e and with it every read of
+// buffer b's previous contents.  The partial buffer is single: it is rewritten by the rectangles of step e+1, which wait
+// for POS(e+1) of the slab's owner, set after that owner pulled the partials of step e.
+// One step of rank g, epoch e, buffer b = e & 1:
+//     main stream                                            copy stream
+//     [part1 on the own slab, if not pre-drifted]
+//     POS[g] := e  (into every window)
+//     triangle of the own slab                               wait POS[q] >= e for all q; pull slab q of posm_b, vel_b
+//     wait for the pulls                                       from q's window (copy engines: one all-gather)
+//     rectangles, antipodal half, point masses
+//     PART[g] := e (into every window)
+//     wait PART[q] >= e for the ranks that worked for me; pull their partials, add them in a fixed order
+//     mirror; springs + kick + drift (+ next part1) for the own slab -> buffer b ^ 1
+// With params.n_active restricting the sources the pair-once division does not apply and the ranks fall back to
+// one-sided sums over all sources (own slab first, the rest after the pulls); the PART phase is then empty.
 // (Reading remote tiles from inside the gravity kernel would be the literal "fused" form, but peer loads bypass the
 // local L2: every tile would re-fetch remote particles over NVLink, hundreds of times the bytes of one gather.)
-//
-// A step is four calls separated by three barriers that the launcher owns (torch.distributed; launcher.py):
-//   ass_shard_begin     part1 on the own slab unless the previous finish already pre-drifted it; sync.
-//   --- barrier ---     every slab is final
-//   ass_shard_exchange  start the pulls + launch the own-slab triangle; returns when the pulls have landed.
-//   --- barrier ---     nobody is still reading my slab
-//   ass_shard_gravity   the rectangles, the antipodal half, the point masses; sync (my partials are complete).
-//   --- barrier ---     every partial is complete
-//   ass_shard_finish    pull + add the partials for the own slab, [zero_accel], spring_forces on the own slab,
-//                       part2 (+ next part1) on the own slab; sync.
-// With params.n_active restricting the sources the pair-once division does not apply and the ranks fall back to
-// one-sided sums over all sources (own slab first, the rest after the pulls).
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -40,28 +50,255 @@
 
 #include "common.cuh"
 
-static int n_sources(const ass_sim* s) { return (s->prm.n_active == -1) ? s->n : std::max(0, std::min(s->prm.n_active, s->n)); }
+namespace {
+
+constexpr unsigned long long SPIN_LIMIT_NS = 30ULL * 1000000000ULL;  // a peer that never arrives: give up, flag the error
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+	unsigned long long v;
+	asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+	return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+	asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+	unsigned long long t;
+	asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+	return t;
+}
+
+struct FlagPtrs {
+	unsigned long long* w[ASS_SHARD_MAX_RANKS];  // every rank's flag block (own included), as mapped here
+};
+
+// thread q publishes  flags_of_rank_q[phase][me] = epoch.  Everything this stream did before is complete (stream order)
+// and made visible system-wide by the fence before the releasing store.
+__global__ void k_flag_set(FlagPtrs fp, int nranks, int phase, int me, unsigned long long epoch) {
+	const int q = threadIdx.x;
+	if (q >= nranks || !fp.w[q]) return;
+	__threadfence_system();
+	st_release_sys(fp.w[q] + phase * ASS_SHARD_MAX_RANKS + me, epoch);
+}
+
+// thread q waits until  my_flags[phase][q] >= epoch  for every q in `mask`; polls local memory only
+__global__ void k_flag_wait(const unsigned long long* flags, unsigned mask, int phase, unsigned long long epoch, int* err) {
+	const int q = threadIdx.x;
+	if (!((mask >> q) & 1u)) return;
+	const unsigned long long* f = flags + phase * ASS_SHARD_MAX_RANKS + q;
+	const unsigned long long t0 = global_ns();
+	while (ld_acquire_sys(f) < epoch) {
+		__nanosleep(100);
+		if (global_ns() - t0 > SPIN_LIMIT_NS) { atomicExch(err, 1 + phase); return; }
+	}
+}
+
+// Slab transfers between ranks of ONE process on ONE device (tests, several ass_sim per GPU) are done by a kernel: the
+// copy engines of a device serve their queue in order, and a copy of rank A that waits (stream order) behind A's flag
+// wait would hold up the copy of rank B that A is waiting for.  Ranks in different processes own their GPU's copy
+// engines, whose queue then only ever holds work that depends on the PEERS' progress: no cycle.
+__global__ void k_copy_vec4d(vec4d* __restrict__ dst, const vec4d* __restrict__ src, size_t n) {
+	const size_t stride = (size_t) gridDim.x * blockDim.x;
+	for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = src[i];
+}
+
+__global__ void k_add_partial(vec4d* __restrict__ acc, const vec4d* __restrict__ part, int lo, int hi) {
+	const int i = lo + blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= hi) return;
+	vec4d a = acc[i];
+	const vec4d b = part[i - lo];
+	a.x += b.x; a.y += b.y; a.z += b.z;
+	acc[i] = a;
+}
+
+// reb_integrator_leapfrog_part2 (src/integrator_leapfrog.c:52-67) for bodies without springs: out of buffer b into b ^ 1
+__global__ void k_part2_pingpong(const vec4d* __restrict__ posm, const vec4d* __restrict__ vel, const vec4d* __restrict__ acc,
+		vec4d* __restrict__ posm_out, vec4d* __restrict__ vel_out, int lo, int hi, double dt, int pre_drift_next) {
+	const int i = lo + blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= hi) return;
+	const double h = __dmul_rn(0.5, dt);
+	vec4d p = posm[i];
+	vec4d v = vel[i];
+	const vec4d a = acc[i];
+	v.x = __dadd_rn(v.x, __dmul_rn(dt, a.x));
+	v.y = __dadd_rn(v.y, __dmul_rn(dt, a.y));
+	v.z = __dadd_rn(v.z, __dmul_rn(dt, a.z));
+	p.x = __dadd_rn(p.x, __dmul_rn(h, v.x));
+	p.y = __dadd_rn(p.y, __dmul_rn(h, v.y));
+	p.z = __dadd_rn(p.z, __dmul_rn(h, v.z));
+	if (pre_drift_next) {
+		p.x = __dadd_rn(p.x, __dmul_rn(h, v.x));
+		p.y = __dadd_rn(p.y, __dmul_rn(h, v.y));
+		p.z = __dadd_rn(p.z, __dmul_rn(h, v.z));
+	}
+	vel_out[i] = v;
+	posm_out[i] = p;
+}
+
+int n_sources(const ass_sim* s) { return (s->prm.n_active == -1) ? s->n : std::max(0, std::min(s->prm.n_active, s->n)); }
+// does the pair-once division apply?  (every particle a source; gravity on and not zeroed again by zero_accel)
+bool gravity_on(const ass_sim* s) { return s->prm.gravity == 1 && s->prm.additional_forces != 2; }
+bool pairwise(const ass_sim* s) { return gravity_on(s) && n_sources(s) == s->n; }
+// body part of rank r's slab: trailing point masses [N - n_perts, N) are kept out of the pair-once kernels
+void body_slab(const ass_sim* s, int r, int* lo, int* hi) {
+	const int nb = s->n - std::max(0, std::min(s->prm.n_perts, s->n));
+	*lo = std::min(s->shard.bounds[r], nb);
+	*hi = std::min(s->shard.bounds[r + 1], nb);
+}
+// where an antipodal pair cuts the lower rank's slab
+int half_point(int lo, int hi) { return lo + (hi - lo) / 2; }
+
+// layout of the window, in vec4d units
+size_t win_posm(const ass_sim* s, int b) { return (size_t) b * 2 * (size_t) s->n; }
+size_t win_vel(const ass_sim* s, int b) { return ((size_t) b * 2 + 1) * (size_t) s->n; }
+size_t win_part(const ass_sim* s) { return 4 * (size_t) s->n; }
+size_t win_flags(const ass_sim* s) { return 5 * (size_t) std::max(s->n, 1); }
+constexpr size_t FLAG_VEC4 = (ASS_SHARD_PHASES * ASS_SHARD_MAX_RANKS * sizeof(unsigned long long) + 64 + sizeof(vec4d) - 1) / sizeof(vec4d);
+unsigned long long* flags_of(const ass_sim* s, vec4d* window) { return (unsigned long long*) (window + win_flags(s)); }
+int* err_of(const ass_sim* s, vec4d* window) { return (int*) (flags_of(s, window) + ASS_SHARD_PHASES * ASS_SHARD_MAX_RANKS); }
+
+// (rank, first particle) of every partial the peers compute for rank g's slab, in the order they are added
+void partial_sources(const ass_sim* s, std::vector<std::pair<int, int>>& from) {
+	const ShardInfo& sh = s->shard;
+	const int R = sh.nranks, g = sh.rank, D = (R - 1) / 2;
+	int lo, hi;
+	body_slab(s, g, &lo, &hi);
+	from.clear();
+	for (int d = 1; d <= D; d++) from.push_back({ ((g - d) % R + R) % R, lo });
+	if (R % 2 == 0 && R > 1) {
+		const int h = (g + R / 2) % R;
+		from.push_back({ h, g < h ? half_point(lo, hi) : lo });  // the higher rank covered only my upper half
+	}
+}
+
+// dst (mine) <- src (in peer r's window): cnt vec4d
+int pull(ass_sim* s, cudaStream_t st, int r, vec4d* dst, const vec4d* src, size_t cnt) {
+	if (!cnt) return ASS_OK;
+	if (s->shard.peer_is_ipc[r]) {
+		CU_TRY(cudaMemcpyAsync(dst, src, sizeof(vec4d) * cnt, cudaMemcpyDeviceToDevice, st));
+	} else {
+		const unsigned grid = (unsigned) std::min<size_t>((cnt + 255) / 256, (size_t) ass_sm_count() * 4);
+		k_copy_vec4d<<<grid, 256, 0, st>>>(dst, src, cnt);
+		LAUNCH_CHECK();
+	}
+	return ASS_OK;
+}
+
+int launch_flag_set(ass_sim* s, cudaStream_t st, int phase, unsigned long long epoch) {
+	ShardInfo& sh = s->shard;
+	FlagPtrs fp;
+	memset(&fp, 0, sizeof(fp));
+	for (int q = 0; q < sh.nranks; q++) {
+		vec4d* w = (q == sh.rank) ? sh.window : sh.peer_window[q];
+		REQUIRE(w, ASS_ESTATE, "a peer window has not been imported");
+		fp.w[q] = flags_of(s, w);
+	}
+	k_flag_set<<<1, 32, 0, st>>>(fp, sh.nranks, phase, sh.rank, epoch);
+	LAUNCH_CHECK();
+	return ASS_OK;
+}
+
+int launch_flag_wait(ass_sim* s, cudaStream_t st, unsigned mask, int phase, unsigned long long epoch) {
+	if (!mask) return ASS_OK;
+	k_flag_wait<<<1, 32, 0, st>>>(flags_of(s, s->shard.window), mask, phase, epoch, err_of(s, s->shard.window));
+	LAUNCH_CHECK();
+	return ASS_OK;
+}
+
+// Everything a step may have to allocate or synchronise for -- pair-once plans (tile tables, mass check), scratch rows,
+// the springs' equal-mass verdict -- BEFORE anything of the step is queued: a step in flight waits on peers, and a host
+// that blocks on its own stream at that point would deadlock ranks that share the host thread (tests) and stall the
+// others.
+int shard_prepare(ass_sim* s) {
+	ShardInfo& sh = s->shard;
+	int rc;
+	const int n = s->n;
+	size_t scratch_rows_bytes = 0;
+	if (pairwise(s)) {
+		const int P = sh.nranks, g = sh.rank, D = (P - 1) / 2;
+		const int nb = n - std::max(0, std::min(s->prm.n_perts, n));
+		int lo, hi;
+		body_slab(s, g, &lo, &hi);
+		if (hi > lo && (rc = ass_gravity_sym_prepare(s, lo, hi, lo, hi))) return rc;
+		for (int d = 1; d <= D; d++) {
+			int plo, phi;
+			body_slab(s, (g + d) % P, &plo, &phi);
+			if (hi > lo && phi > plo && (rc = ass_gravity_sym_prepare(s, lo, hi, plo, phi))) return rc;
+		}
+		if (P % 2 == 0 && P > 1) {
+			const int h = (g + P / 2) % P;
+			int plo, phi;
+			body_slab(s, h, &plo, &phi);
+			if (g < h) { if (half_point(lo, hi) > lo && phi > plo && (rc = ass_gravity_sym_prepare(s, lo, half_point(lo, hi), plo, phi))) return rc; }
+			else if (hi > lo && phi > half_point(plo, phi) && (rc = ass_gravity_sym_prepare(s, lo, hi, half_point(plo, phi), phi))) return rc;
+		}
+		const int rows = std::max(ass_gravity_rows(hi - lo, n - nb), ass_gravity_rows(sh.hi - std::max(sh.lo, nb), n));
+		scratch_rows_bytes = sizeof(vec4d) * (size_t) std::max(rows, 1) * (size_t) n;
+		std::vector<std::pair<int, int>> from;
+		partial_sources(s, from);
+		scratch_rows_bytes += sizeof(vec4d) * (size_t) std::max(hi - lo, 0) * from.size();
+	} else if (gravity_on(s)) {
+		const int ns = n_sources(s);
+		const int a = std::min(sh.lo, ns), b = std::min(sh.hi, ns);
+		const int rows = ass_gravity_rows(sh.hi - sh.lo, b - a) + ass_gravity_rows(sh.hi - sh.lo, a) + ass_gravity_rows(sh.hi - sh.lo, ns - b);
+		scratch_rows_bytes = sizeof(vec4d) * (size_t) std::max(rows, 1) * (size_t) n;
+	}
+	if (scratch_rows_bytes && (rc = ass_buf_reserve(s->grav_partial, scratch_rows_bytes))) return rc;
+	if (s->prm.additional_forces != 0 && s->ns > 0 && (rc = ass_springs_prepare(s))) return rc;
+	return ASS_OK;
+}
+
+// one-sided: acc[t_lo, t_hi) += pull of sources [s_lo, s_hi); scratch rows reserved by shard_prepare
+int one_sided_add(ass_sim* s, int s_lo, int s_hi, int t_lo, int t_hi) {
+	if (t_hi <= t_lo || s_hi <= s_lo) return ASS_OK;
+	int used = 0, rc;
+	if ((rc = ass_launch_gravity_partial(s, s->posm, s_lo, s_hi, t_lo, t_hi, 0, &used))) return rc;
+	return ass_launch_gravity_reduce(s, t_lo, t_hi, used, true);
+}
+
+// posm / vel follow the current buffer, the alt pointers the other one
+void point_at(ass_sim* s, int b) {
+	ShardInfo& sh = s->shard;
+	sh.cur = b;
+	s->posm = sh.window + win_posm(s, b);
+	s->vel = sh.window + win_vel(s, b);
+	s->posm_alt = sh.window + win_posm(s, b ^ 1);
+	s->vel_alt = sh.window + win_vel(s, b ^ 1);
+}
+
+int check_device_error(ass_sim* s) {
+	int e = 0;
+	CU_TRY(cudaMemcpy(&e, err_of(s, s->shard.window), sizeof(int), cudaMemcpyDeviceToHost));
+	if (e) {
+		ass_set_error("sharded step: rank %d waited more than %llu s for a peer's %s flag (a rank died, or the ranks did not call ass_shard_step with the same step counts)",
+				s->shard.rank, SPIN_LIMIT_NS / 1000000000ULL, e == 1 + ASS_SHARD_POS ? "positions" : e == 1 + ASS_SHARD_PART ? "partials" : "gather");
+		return ASS_ECOMM;
+	}
+	return ASS_OK;
+}
+
+}  // namespace
 
 extern "C" int ass_shard_setup(ass_sim* s, int rank, int nranks, const int* bounds) {
 	REQUIRE(s && bounds, ASS_EINVAL, "null argument");
 	REQUIRE(s->have_state, ASS_ESTATE, "upload the full body on every rank before sharding");
 	REQUIRE(!s->shard.active, ASS_ESTATE, "already sharded");
-	REQUIRE(nranks >= 1 && rank >= 0 && rank < nranks, ASS_EINVAL, "bad rank");
+	REQUIRE(nranks >= 1 && nranks <= ASS_SHARD_MAX_RANKS && rank >= 0 && rank < nranks, ASS_EINVAL, "bad rank (at most 16 ranks)");
 	REQUIRE(bounds[0] == 0 && bounds[nranks] == s->n, ASS_EINVAL, "bounds must run from 0 to N");
 	for (int r = 0; r < nranks; r++) REQUIRE(bounds[r] <= bounds[r + 1], ASS_EINVAL, "bounds must be non-decreasing");
 	int rc = ass_ensure_device();
 	if (rc) return rc;
 	ShardInfo& sh = s->shard;
 	const size_t n = (size_t) s->n;
-	CU_TRY(cudaMalloc(&sh.window, sizeof(vec4d) * 3 * std::max<size_t>(n, 1)));  // posm | vel | partial accelerations
-	CU_TRY(cudaMemsetAsync(sh.window + 2 * n, 0, sizeof(vec4d) * n, s->stream));
-	CU_TRY(cudaMemcpyAsync(sh.window, s->posm, sizeof(vec4d) * n, cudaMemcpyDeviceToDevice, s->stream));
-	CU_TRY(cudaMemcpyAsync(sh.window + n, s->vel, sizeof(vec4d) * n, cudaMemcpyDeviceToDevice, s->stream));
+	const size_t total = win_flags(s) + FLAG_VEC4;
+	CU_TRY(cudaMalloc(&sh.window, sizeof(vec4d) * total));
+	CU_TRY(cudaMemsetAsync(sh.window, 0, sizeof(vec4d) * total, s->stream));
+	for (int b = 0; b < 2; b++) {
+		CU_TRY(cudaMemcpyAsync(sh.window + win_posm(s, b), s->posm, sizeof(vec4d) * n, cudaMemcpyDeviceToDevice, s->stream));
+		CU_TRY(cudaMemcpyAsync(sh.window + win_vel(s, b), s->vel, sizeof(vec4d) * n, cudaMemcpyDeviceToDevice, s->stream));
+	}
 	CU_TRY(cudaStreamSynchronize(s->stream));
 	cudaFree(s->posm); cudaFree(s->vel); cudaFree(s->posm_alt); cudaFree(s->vel_alt);
-	s->posm = sh.window;
-	s->vel = sh.window + n;
-	s->posm_alt = s->vel_alt = nullptr;  // the fused ping-pong loop is not used by sharded simulations
 	s->cap = s->n;
 	CU_TRY(cudaStreamCreateWithFlags(&sh.copy_stream, cudaStreamNonBlocking));
 	CU_TRY(cudaEventCreateWithFlags(&sh.pulled, cudaEventDisableTiming));
@@ -70,7 +307,10 @@ extern "C" int ass_shard_setup(ass_sim* s, int rank, int nranks, const int* boun
 	sh.lo = bounds[rank]; sh.hi = bounds[rank + 1];
 	sh.peer_window.assign(nranks, nullptr);
 	sh.peer_is_ipc.assign(nranks, 0);
+	sh.epoch = 0;
+	sh.gather_epoch = 0;
 	sh.active = true;
+	point_at(s, 0);
 	s->predrifted = false;
 	return ASS_OK;
 }
@@ -111,216 +351,192 @@ extern "C" int ass_shard_import_local(ass_sim* s, int peer, ass_sim* peer_sim) {
 	REQUIRE(s->shard.active && peer_sim->shard.active, ASS_ESTATE, "call ass_shard_setup on both first");
 	REQUIRE(peer >= 0 && peer < s->shard.nranks && peer != s->shard.rank, ASS_EINVAL, "bad peer rank");
 	REQUIRE(peer_sim->n == s->n, ASS_EINVAL, "peer holds a different body");
+	// With lazy module loading (the CUDA 12 default) the FIRST launch of a kernel loads it, and loading synchronises the
+	// context: it would wait for every rank's flag waits already in flight -- which wait for ranks the same host thread
+	// has not queued yet.  Ranks in separate processes are immune (a load only ever waits for the peers' own progress).
+	const char* ml = getenv("CUDA_MODULE_LOADING");
+	REQUIRE(ml && strcmp(ml, "EAGER") == 0, ASS_ESTATE,
+	        "same-process ranks need CUDA_MODULE_LOADING=EAGER in the environment before CUDA starts (a lazily loaded kernel's first launch synchronises the context and would deadlock against a peer's flag wait)");
 	s->shard.peer_window[peer] = peer_sim->shard.window;
 	s->shard.peer_is_ipc[peer] = 0;
 	return ASS_OK;
 }
 
-extern "C" int ass_shard_begin(ass_sim* s) {
-	REQUIRE(s, ASS_EINVAL, "null sim");
-	REQUIRE(s->shard.active, ASS_ESTATE, "not sharded");
-	int rc = ass_ensure_device();
-	if (rc) return rc;
-	const double dt = s->prm.dt;
-	if (!s->predrifted) {
-		if ((rc = ass_launch_part1_range(s, dt, s->shard.lo, s->shard.hi))) return rc;
-	}
-	s->predrifted = false;
-	s->prm.t += dt / 2.;  // integrator_leapfrog.c:50
-	CU_TRY(cudaStreamSynchronize(s->stream));
-	return ASS_OK;
-}
-
-// does the pair-once division apply?  (every particle a source; gravity on and not zeroed again by zero_accel)
-static bool gravity_on(const ass_sim* s) { return s->prm.gravity == 1 && s->prm.additional_forces != 2; }
-static bool pairwise(const ass_sim* s) { return gravity_on(s) && n_sources(s) == s->n; }
-// body part of rank r's slab: trailing point masses [N - n_perts, N) are kept out of the pair-once kernels
-static void body_slab(const ass_sim* s, int r, int* lo, int* hi) {
-	const int nb = s->n - std::max(0, std::min(s->prm.n_perts, s->n));
-	*lo = std::min(s->shard.bounds[r], nb);
-	*hi = std::min(s->shard.bounds[r + 1], nb);
-}
-
-extern "C" int ass_shard_exchange(ass_sim* s) {
+// reb_step x nsteps for the own slab; queued, not awaited (ass_sync / ass_shard_gather / a download wait for it).
+// Collective: every rank calls it with the same nsteps and pre_drift_last.  pre_drift_last != 0 leaves the positions with
+// the following step's first half-drift already applied (only stepping may follow).
+extern "C" int ass_shard_step(ass_sim* s, int nsteps, int pre_drift_last) {
 	REQUIRE(s, ASS_EINVAL, "null sim");
 	ShardInfo& sh = s->shard;
 	REQUIRE(sh.active, ASS_ESTATE, "not sharded");
+	REQUIRE(nsteps >= 0, ASS_EINVAL, "negative step count");
 	int rc = ass_ensure_device();
 	if (rc) return rc;
-	const size_t n = (size_t) s->n;
-	// 1. pull every peer slab (posm and vel) with the copy engines
-	for (int r = 0; r < sh.nranks; r++) {
-		if (r == sh.rank) continue;
-		const size_t lo = (size_t) sh.bounds[r], cnt = (size_t) (sh.bounds[r + 1] - sh.bounds[r]);
-		if (!cnt) continue;
-		REQUIRE(sh.peer_window[r], ASS_ESTATE, "a peer window has not been imported");
-		CU_TRY(cudaMemcpyAsync(sh.window + lo, sh.peer_window[r] + lo, sizeof(vec4d) * cnt, cudaMemcpyDeviceToDevice, sh.copy_stream));
-		CU_TRY(cudaMemcpyAsync(sh.window + n + lo, sh.peer_window[r] + n + lo, sizeof(vec4d) * cnt, cudaMemcpyDeviceToDevice, sh.copy_stream));
-	}
-	CU_TRY(cudaEventRecord(sh.pulled, sh.copy_stream));
-	// 2. meanwhile: the part of gravity that needs the own slab only
-	sh.rows_local = 0;
-	if (pairwise(s)) {
-		int lo, hi;
-		body_slab(s, sh.rank, &lo, &hi);
-		// a = triangle of the own slab; slabs too small for the pair-once tiles still go through it (forced), so that
-		// every rank evaluates exactly the pairs the division assigns to it
-		if (hi > lo) {
-			if ((rc = ass_launch_gravity_sym(s, lo, hi))) return rc;
+	for (int q = 0; q < sh.nranks; q++) REQUIRE(q == sh.rank || sh.peer_window[q], ASS_ESTATE, "a peer window has not been imported");
+	if (nsteps == 0) return ASS_OK;
+	if ((rc = shard_prepare(s))) return rc;
+	const int P = sh.nranks, g = sh.rank, D = (P - 1) / 2;
+	const int n = s->n;
+	const unsigned all_others = ((1u << P) - 1u) & ~(1u << g);
+	const bool have_springs = s->prm.additional_forces != 0 && s->ns > 0;
+	std::vector<std::pair<int, int>> from;
+	for (int step = 0; step < nsteps; step++) {
+		const double dt = s->prm.dt;
+		const bool pre = (step < nsteps - 1) || pre_drift_last != 0;
+		const unsigned long long e = ++sh.epoch;
+		const int b = sh.cur;
+		if (sh.gather_pending) {  // a peer may still be pulling my slab for the last gather: it must not move yet
+			if ((rc = launch_flag_wait(s, s->stream, all_others, ASS_SHARD_GATHER, sh.gather_pending))) return rc;
+			sh.gather_pending = 0;
 		}
-		// own particles outside the body part (point masses) start from zero
-		if ((rc = ass_launch_zero_accel_range(s, std::max(sh.lo, hi), sh.hi))) return rc;
-	} else if (gravity_on(s)) {
-		const int ns = n_sources(s);
-		const int a = std::min(sh.lo, ns), b = std::min(sh.hi, ns);
-		const int rows = ass_gravity_rows(sh.hi - sh.lo, b - a) + ass_gravity_rows(sh.hi - sh.lo, a) + ass_gravity_rows(sh.hi - sh.lo, ns - b);
-		if ((rc = ass_buf_reserve(s->grav_partial, sizeof(vec4d) * (size_t) std::max(rows, 1) * n))) return rc;
-		if ((rc = ass_launch_gravity_partial(s, s->posm, a, b, sh.lo, sh.hi, 0, &sh.rows_local))) return rc;
-	}
-	// 3. the caller may enter its barrier once the peers' data has landed here
-	CU_TRY(cudaStreamSynchronize(sh.copy_stream));
-	return ASS_OK;
-}
-
-// where an antipodal pair cuts the lower rank's slab
-static int half_point(int lo, int hi) { return lo + (hi - lo) / 2; }
-
-// one-sided: acc[t_lo, t_hi) += pull of sources [s_lo, s_hi)
-static int one_sided_add(ass_sim* s, int s_lo, int s_hi, int t_lo, int t_hi) {
-	if (t_hi <= t_lo || s_hi <= s_lo) return ASS_OK;
-	int rc = ass_buf_reserve(s->grav_partial, sizeof(vec4d) * (size_t) std::max(ass_gravity_rows(t_hi - t_lo, s_hi - s_lo), 1) * (size_t) s->n);
-	if (rc) return rc;
-	int used = 0;
-	if ((rc = ass_launch_gravity_partial(s, s->posm, s_lo, s_hi, t_lo, t_hi, 0, &used))) return rc;
-	return ass_launch_gravity_reduce(s, t_lo, t_hi, used, true);
-}
-
-extern "C" int ass_shard_gravity(ass_sim* s) {
-	REQUIRE(s, ASS_EINVAL, "null sim");
-	ShardInfo& sh = s->shard;
-	REQUIRE(sh.active, ASS_ESTATE, "not sharded");
-	int rc = ass_ensure_device();
-	if (rc) return rc;
-	CU_TRY(cudaStreamWaitEvent(s->stream, sh.pulled, 0));
-	if (pairwise(s)) {
-		const int P = sh.nranks, g = sh.rank, D = (P - 1) / 2;
-		const int n = s->n, nb = n - std::max(0, std::min(s->prm.n_perts, n));
-		vec4d* fpart = sh.window + 2 * (size_t) n;
-		int lo, hi;
-		body_slab(s, g, &lo, &hi);
-		for (int d = 1; d <= D; d++) {  // rectangles: both sides of every pair
-			int plo, phi;
-			body_slab(s, (g + d) % P, &plo, &phi);
-			if ((rc = ass_launch_gravity_sym_pair(s, lo, hi, plo, phi, s->acc, true, fpart, false))) return rc;
+		// ---- drifted positions of the own slab, published ----
+		if (!s->predrifted && (rc = ass_launch_part1_range(s, dt, sh.lo, sh.hi))) return rc;
+		s->predrifted = false;
+		s->prm.t += dt / 2.;  // integrator_leapfrog.c:50
+		if ((rc = launch_flag_set(s, s->stream, ASS_SHARD_POS, e))) return rc;
+		// ---- copy stream: the other slabs of this step, as soon as their owners have published them ----
+		if ((rc = launch_flag_wait(s, sh.copy_stream, all_others, ASS_SHARD_POS, e))) return rc;
+		for (int r = 0; r < P; r++) {
+			if (r == g) continue;
+			const size_t lo = (size_t) sh.bounds[r], cnt = (size_t) (sh.bounds[r + 1] - sh.bounds[r]);
+			if (!cnt) continue;
+			if ((rc = pull(s, sh.copy_stream, r, sh.window + win_posm(s, b) + lo, sh.peer_window[r] + win_posm(s, b) + lo, cnt))) return rc;
+			if ((rc = pull(s, sh.copy_stream, r, sh.window + win_vel(s, b) + lo, sh.peer_window[r] + win_vel(s, b) + lo, cnt))) return rc;
 		}
-		if (P % 2 == 0) {  // antipodal slab: the pair's rectangle is split between its two ranks
-			const int h = (g + P / 2) % P;
-			int plo, phi;
-			body_slab(s, h, &plo, &phi);
-			if (g < h) rc = ass_launch_gravity_sym_pair(s, lo, half_point(lo, hi), plo, phi, s->acc, true, fpart, false);
-			else rc = ass_launch_gravity_sym_pair(s, lo, hi, half_point(plo, phi), phi, s->acc, true, fpart, false);
-			if (rc) return rc;
+		CU_TRY(cudaEventRecord(sh.pulled, sh.copy_stream));
+		// ---- meanwhile: the part of gravity that needs the own slab only ----
+		int rows_local = 0;
+		if (pairwise(s)) {
+			int lo, hi;
+			body_slab(s, g, &lo, &hi);
+			// a = triangle of the own slab; slabs too small for the pair-once tiles still go through it (forced), so that
+			// every rank evaluates exactly the pairs the division assigns to it
+			if (hi > lo && (rc = ass_launch_gravity_sym(s, lo, hi))) return rc;
+			// own particles outside the body part (point masses) start from zero
+			if ((rc = ass_launch_zero_accel_range(s, std::max(sh.lo, hi), sh.hi))) return rc;
+		} else if (gravity_on(s)) {
+			const int ns = n_sources(s);
+			const int a = std::min(sh.lo, ns), c = std::min(sh.hi, ns);
+			if ((rc = ass_launch_gravity_partial(s, s->posm, a, c, sh.lo, sh.hi, 0, &rows_local))) return rc;
 		}
-		// point masses: they pull on my body particles; whoever owns them sums everything onto them
-		if ((rc = one_sided_add(s, nb, n, lo, hi))) return rc;
-		if ((rc = one_sided_add(s, 0, n, std::max(sh.lo, nb), sh.hi))) return rc;
-	}
-	CU_TRY(cudaStreamSynchronize(s->stream));  // my partials for other slabs are complete
-	return ASS_OK;
-}
-
-__global__ void k_add_partial(vec4d* __restrict__ acc, const vec4d* __restrict__ part, int lo, int hi) {
-	const int i = lo + blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= hi) return;
-	vec4d a = acc[i];
-	const vec4d b = part[i - lo];
-	a.x += b.x; a.y += b.y; a.z += b.z;
-	acc[i] = a;
-}
-
-extern "C" int ass_shard_finish(ass_sim* s, int pre_drift_next) {
-	REQUIRE(s, ASS_EINVAL, "null sim");
-	ShardInfo& sh = s->shard;
-	REQUIRE(sh.active, ASS_ESTATE, "not sharded");
-	int rc = ass_ensure_device();
-	if (rc) return rc;
-	const ass_params& P = s->prm;
-	const double dt = P.dt;
-	CU_TRY(cudaStreamWaitEvent(s->stream, sh.pulled, 0));
-	if (pairwise(s)) {
-		// the partials other ranks computed for my slab, pulled and added in a fixed order (d = 1..D)
-		const int R = sh.nranks, g = sh.rank, D = (R - 1) / 2;
-		int lo, hi;
-		body_slab(s, g, &lo, &hi);
-		const size_t cnt = (size_t) std::max(hi - lo, 0), n = (size_t) s->n;
-		// (rank, first particle) of every contribution, in the order they are added
-		std::vector<std::pair<int, int>> from;
-		for (int d = 1; d <= D; d++) from.push_back({ ((g - d) % R + R) % R, lo });
-		if (R % 2 == 0) {
-			const int h = (g + R / 2) % R;
-			from.push_back({ h, g < h ? half_point(lo, hi) : lo });  // the higher rank covered only my upper half
-		}
-		if (cnt && !from.empty()) {
-			if ((rc = ass_buf_reserve(s->grav_partial, sizeof(vec4d) * cnt * from.size()))) return rc;
-			vec4d* land = (vec4d*) s->grav_partial.p;
-			for (size_t q = 0; q < from.size(); q++) {
-				const int r = from[q].first, first = from[q].second;
-				if (hi <= first) continue;
-				REQUIRE(sh.peer_window[r], ASS_ESTATE, "a peer window has not been imported");
-				CU_TRY(cudaMemcpyAsync(land + q * cnt, sh.peer_window[r] + 2 * n + (size_t) first, sizeof(vec4d) * (size_t) (hi - first), cudaMemcpyDeviceToDevice, s->stream));
+		CU_TRY(cudaStreamWaitEvent(s->stream, sh.pulled, 0));
+		// ---- gravity against the other slabs ----
+		if (pairwise(s)) {
+			const int nb = n - std::max(0, std::min(s->prm.n_perts, n));
+			vec4d* fpart = sh.window + win_part(s);
+			int lo, hi;
+			body_slab(s, g, &lo, &hi);
+			for (int d = 1; d <= D; d++) {  // rectangles: both sides of every pair
+				int plo, phi;
+				body_slab(s, (g + d) % P, &plo, &phi);
+				if ((rc = ass_launch_gravity_sym_pair(s, lo, hi, plo, phi, s->acc, true, fpart, false))) return rc;
 			}
-			ass_tic(s, ASS_K_GRAVITY);
-			for (size_t q = 0; q < from.size(); q++) {
-				const int first = from[q].second;
-				if (hi <= first) continue;
-				k_add_partial<<<(unsigned) ((hi - first + 255) / 256), 256, 0, s->stream>>>(s->acc, land + q * cnt, first, hi);
+			if (P % 2 == 0 && P > 1) {  // antipodal slab: the pair's rectangle is split between its two ranks
+				const int h = (g + P / 2) % P;
+				int plo, phi;
+				body_slab(s, h, &plo, &phi);
+				if (g < h) rc = ass_launch_gravity_sym_pair(s, lo, half_point(lo, hi), plo, phi, s->acc, true, fpart, false);
+				else rc = ass_launch_gravity_sym_pair(s, lo, hi, half_point(plo, phi), phi, s->acc, true, fpart, false);
+				if (rc) return rc;
+			}
+			// point masses: they pull on my body particles; whoever owns them sums everything onto them
+			if ((rc = one_sided_add(s, nb, n, lo, hi))) return rc;
+			if ((rc = one_sided_add(s, 0, n, std::max(sh.lo, nb), sh.hi))) return rc;
+			if ((rc = launch_flag_set(s, s->stream, ASS_SHARD_PART, e))) return rc;
+			// the partials other ranks computed for my slab, pulled and added in a fixed order (d = 1..D, then the antipode)
+			partial_sources(s, from);
+			const size_t cnt = (size_t) std::max(hi - lo, 0);
+			if (cnt && !from.empty()) {
+				unsigned need = 0;
+				for (auto& f : from) need |= 1u << f.first;
+				if ((rc = launch_flag_wait(s, s->stream, need, ASS_SHARD_PART, e))) return rc;
+				// landing rows sit behind the one-sided scratch rows (reserved together by shard_prepare)
+				const int rows = std::max(ass_gravity_rows(hi - lo, n - nb), ass_gravity_rows(sh.hi - std::max(sh.lo, nb), n));
+				vec4d* land = (vec4d*) s->grav_partial.p + (size_t) std::max(rows, 1) * (size_t) n;
+				ass_tic(s, ASS_K_XFER);
+				for (size_t q = 0; q < from.size(); q++) {
+					const int r = from[q].first, first = from[q].second;
+					if (hi <= first) continue;
+					if ((rc = pull(s, s->stream, r, land + q * cnt, sh.peer_window[r] + win_part(s) + (size_t) first, (size_t) (hi - first)))) return rc;
+				}
+				ass_toc(s, ASS_K_XFER);
+				ass_tic(s, ASS_K_GRAVITY);
+				for (size_t q = 0; q < from.size(); q++) {
+					const int first = from[q].second;
+					if (hi <= first) continue;
+					k_add_partial<<<(unsigned) ((hi - first + 255) / 256), 256, 0, s->stream>>>(s->acc, land + q * cnt, first, hi);
+					LAUNCH_CHECK();
+				}
+				ass_toc(s, ASS_K_GRAVITY);
+			}
+		} else if (gravity_on(s)) {
+			const int ns = n_sources(s);
+			const int a = std::min(sh.lo, ns), c = std::min(sh.hi, ns);
+			int rows = rows_local, used = 0;
+			if ((rc = ass_launch_gravity_partial(s, s->posm, 0, a, sh.lo, sh.hi, rows, &used))) return rc;
+			rows += used;
+			if ((rc = ass_launch_gravity_partial(s, s->posm, c, ns, sh.lo, sh.hi, rows, &used))) return rc;
+			rows += used;
+			if ((rc = ass_launch_gravity_reduce(s, sh.lo, sh.hi, rows))) return rc;
+		}
+		// ---- springs, kick, drift(s) for the own slab: out of buffer b into buffer b ^ 1 ----
+		if (have_springs) {
+			if ((rc = ass_launch_spring_kick_drift_range(s, s->prm.additional_forces == 2, dt, pre, sh.lo, sh.hi))) return rc;
+		} else {
+			if (s->prm.additional_forces == 2 && (rc = ass_launch_zero_accel_range(s, sh.lo, sh.hi))) return rc;
+			if (sh.hi > sh.lo) {
+				ass_tic(s, ASS_K_LEAPFROG);
+				k_part2_pingpong<<<(sh.hi - sh.lo + 255) / 256, 256, 0, s->stream>>>(s->posm, s->vel, s->acc, s->posm_alt, s->vel_alt, sh.lo, sh.hi, dt, pre ? 1 : 0);
 				LAUNCH_CHECK();
+				ass_toc(s, ASS_K_LEAPFROG);
 			}
-			ass_toc(s, ASS_K_GRAVITY);
 		}
-	} else if (gravity_on(s)) {
-		const int ns = n_sources(s);
-		const int a = std::min(sh.lo, ns), b = std::min(sh.hi, ns);
-		int rows = sh.rows_local, used = 0;
-		if ((rc = ass_launch_gravity_partial(s, s->posm, 0, a, sh.lo, sh.hi, rows, &used))) return rc;
-		rows += used;
-		if ((rc = ass_launch_gravity_partial(s, s->posm, b, ns, sh.lo, sh.hi, rows, &used))) return rc;
-		rows += used;
-		if ((rc = ass_launch_gravity_reduce(s, sh.lo, sh.hi, rows))) return rc;
+		point_at(s, b ^ 1);
+		s->predrifted = pre;
+		s->prm.t += dt / 2.;  // integrator_leapfrog.c:65-66
+		s->prm.dt_last_done = dt;
 	}
-	if (P.additional_forces != 0 && s->ns > 0) {
-		if ((rc = ass_launch_spring_forces_range(s, P.additional_forces == 2, sh.lo, sh.hi))) return rc;
-	} else if (P.additional_forces == 2) {
-		if ((rc = ass_launch_zero_accel_range(s, sh.lo, sh.hi))) return rc;
-	}
-	if ((rc = ass_launch_part2_range(s, dt, pre_drift_next != 0, sh.lo, sh.hi))) return rc;
-	s->predrifted = pre_drift_next != 0;
-	s->prm.t += dt / 2.;  // integrator_leapfrog.c:65-66
-	s->prm.dt_last_done = dt;
-	CU_TRY(cudaStreamSynchronize(s->stream));
 	return ASS_OK;
 }
 
 // Bring every slab home (positions, velocities) so that ass_download_particles returns the whole body; accelerations of
 // foreign slabs are pulled by the caller rank-by-rank if it wants them (each rank only ever computes its own).
+// Collective, queued like a step: GATHER[g] = 2c - 1 says "my slab is final", the pulls wait for that from every
+// peer, GATHER[g] = 2c says "I have pulled everybody's"; the next ass_shard_step starts by waiting for 2c from every
+// peer, because its first kernel moves the own slab in place.  A download (or ass_sync) waits for the pulls.
 extern "C" int ass_shard_gather(ass_sim* s) {
 	REQUIRE(s, ASS_EINVAL, "null sim");
 	ShardInfo& sh = s->shard;
 	REQUIRE(sh.active, ASS_ESTATE, "not sharded");
-	REQUIRE(!s->predrifted, ASS_ESTATE, "finish the step without pre_drift_next before gathering");
+	REQUIRE(!s->predrifted, ASS_ESTATE, "finish the steps without pre_drift_last before gathering");
 	int rc = ass_ensure_device();
 	if (rc) return rc;
-	const size_t n = (size_t) s->n;
-	for (int r = 0; r < sh.nranks; r++) {
-		if (r == sh.rank) continue;
+	const int P = sh.nranks, g = sh.rank, b = sh.cur;
+	const unsigned all_others = ((1u << P) - 1u) & ~(1u << g);
+	for (int q = 0; q < P; q++) REQUIRE(q == g || sh.peer_window[q], ASS_ESTATE, "a peer window has not been imported");
+	const unsigned long long c = ++sh.gather_epoch;
+	if ((rc = launch_flag_set(s, s->stream, ASS_SHARD_GATHER, 2 * c - 1))) return rc;
+	if ((rc = launch_flag_wait(s, s->stream, all_others, ASS_SHARD_GATHER, 2 * c - 1))) return rc;
+	ass_tic(s, ASS_K_XFER);
+	for (int r = 0; r < P; r++) {
+		if (r == g) continue;
 		const size_t lo = (size_t) sh.bounds[r], cnt = (size_t) (sh.bounds[r + 1] - sh.bounds[r]);
 		if (!cnt) continue;
-		REQUIRE(sh.peer_window[r], ASS_ESTATE, "a peer window has not been imported");
-		CU_TRY(cudaMemcpyAsync(sh.window + lo, sh.peer_window[r] + lo, sizeof(vec4d) * cnt, cudaMemcpyDeviceToDevice, sh.copy_stream));
-		CU_TRY(cudaMemcpyAsync(sh.window + n + lo, sh.peer_window[r] + n + lo, sizeof(vec4d) * cnt, cudaMemcpyDeviceToDevice, sh.copy_stream));
+		if ((rc = pull(s, s->stream, r, sh.window + win_posm(s, b) + lo, sh.peer_window[r] + win_posm(s, b) + lo, cnt))) return rc;
+		if ((rc = pull(s, s->stream, r, sh.window + win_vel(s, b) + lo, sh.peer_window[r] + win_vel(s, b) + lo, cnt))) return rc;
 	}
-	CU_TRY(cudaStreamSynchronize(sh.copy_stream));
+	ass_toc(s, ASS_K_XFER);
+	if ((rc = launch_flag_set(s, s->stream, ASS_SHARD_GATHER, 2 * c))) return rc;
+	sh.gather_pending = 2 * c;
 	return ASS_OK;
+}
+
+// ass_sync for a sharded simulation: both streams, then the device-side error flag of the waits
+int ass_shard_sync(ass_sim* s) {
+	ShardInfo& sh = s->shard;
+	CU_TRY(cudaStreamSynchronize(s->stream));
+	CU_TRY(cudaStreamSynchronize(sh.copy_stream));
+	return check_device_error(s);
 }
 
 void ass_shard_release(ass_sim* s) {
@@ -328,11 +544,11 @@ void ass_shard_release(ass_sim* s) {
 	if (!sh.active) return;
 	for (int r = 0; r < (int) sh.peer_window.size(); r++)
 		if (sh.peer_window[r] && sh.peer_is_ipc[r]) cudaIpcCloseMemHandle(sh.peer_window[r]);
-	if (sh.copy_stream) cudaStreamDestroy(sh.copy_stream);
+	if (sh.copy_stream) { cudaStreamSynchronize(sh.copy_stream); cudaStreamDestroy(sh.copy_stream); }
 	if (sh.pulled) cudaEventDestroy(sh.pulled);
-	// posm / vel alias the window: free it once and clear the aliases
+	// posm / vel and their alt twins alias the window: free it once and clear the aliases
 	cudaFree(sh.window);
-	s->posm = s->vel = nullptr;
+	s->posm = s->vel = s->posm_alt = s->vel_alt = nullptr;
 	sh.window = nullptr;
 	sh.active = false;
 }

@@ -12,6 +12,7 @@
 // 35 B x NS of half-edge stream (two 16-byte records per spring, + 11 % padding) + ~150 B x N of mirror, acc and outputs;
 // the 48 B gathered per half-edge come out of shared memory, the tables are filled from L2 (~3 x 56 B x N).
 #include <stdlib.h>
+#include <string.h>
 
 #include <algorithm>
 
@@ -122,16 +123,39 @@ __global__ void __launch_bounds__(BLOCK) k_spring_forces(const GlobalNodes nodes
 // known in advance, was built and measured slower -- 32 us against 28 at C3: the polling and the fixed shares cost more
 // than the deeper prefetch saves.)
 // ---------------------------------------------------------------------------------------------------
-constexpr int TL_THREADS = 512;
+#ifndef ASS_TILE_THREADS
+#define ASS_TILE_THREADS 512
+#endif
+#ifndef ASS_TILE_CHAINS
+#define ASS_TILE_CHAINS 2
+#endif
+constexpr int TL_THREADS = ASS_TILE_THREADS;  // 512 with two interleaved chains per lane, or 1024 with one (half the registers)
+constexpr int TL_CHAINS = ASS_TILE_CHAINS;
+constexpr int TL_WARPS = TL_THREADS / 32;
 constexpr int GPW = 32 / SPRING_LANES;
+constexpr int TL_AHEAD = 2 * TL_WARPS;  // how many slices ahead of the one a warp starts its records are requested into L2
+constexpr int TL_FILL = (2944 + TL_THREADS - 1) / TL_THREADS;  // table slots per thread (TILE_SLOTS_LIMIT below)
 struct TileDesc {
 	int s0, s1, tab_off, n_slots;
 };
 static_assert(sizeof(TileDesc) == sizeof(int4), "TileDesc is uploaded as int4");
+// What a CTA needs before it can request anything, as KERNEL PARAMETERS: with the descriptors in global memory a launch
+// began with a chain of dependent cold misses (tile range -> tile descriptor -> table -> mirror), ~1 us each after an L2 flush.
+constexpr int TL_MAX_CTAS = 160;
+struct CtaHead {
+	int tile0, ntiles;  // this CTA's tiles
+	TileDesc first;     // descriptor of the first one
+	int sl_end;         // one past the CTA's last slice (bounds the look-ahead requests)
+	int pad;
+};
+struct TilesParams {
+	CtaHead h[TL_MAX_CTAS];
+};
+static_assert(sizeof(TilesParams) <= 8192, "per-CTA heads travel as kernel parameters");
 
 template <bool ZERO_FIRST, bool KICK, bool UNI, bool PAL1>
-__global__ void __launch_bounds__(TL_THREADS, 1) k_spring_tiles(const GlobalNodes mir, vec4d* __restrict__ acc, const TileDesc* __restrict__ tiles,
-		const int* __restrict__ cta_tile, const int* __restrict__ tab, const int4* __restrict__ grpT, const int* __restrict__ warp_off,
+__global__ void __launch_bounds__(TL_THREADS, 1) k_spring_tiles(const __grid_constant__ TilesParams heads, const GlobalNodes mir, vec4d* __restrict__ acc,
+		const TileDesc* __restrict__ tiles, const int* __restrict__ tab, const int4* __restrict__ grpT, const int* __restrict__ warp_off,
 		const HalfEdge* __restrict__ heL, const double2* __restrict__ palf, int cap, int max_slices, vec4d* __restrict__ posm_out,
 		vec4d* __restrict__ vel_out, const SpringMirror out, double dt, int pre_drift_next) {
 	extern __shared__ __align__(128) unsigned char tile_smem[];  // [table: xy | zv | vxy | m, cap slots each][headers: groups | record offsets]
@@ -143,34 +167,70 @@ __global__ void __launch_bounds__(TL_THREADS, 1) k_spring_tiles(const GlobalNode
 	int4* s_grp = (int4*) (s_m + cap);                 // max_slices * GPW
 	int* s_off = (int*) (s_grp + (size_t) max_slices * GPW);  // max_slices + 1
 	const SharedNodes nodes{ s_xy, s_zv, s_vxy, s_m };
-	const int tid = threadIdx.x, lane = tid & 31, sub = lane & (SPRING_LANES - 1);
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, sub = lane & (SPRING_LANES - 1);
+	const CtaHead& H = heads.h[blockIdx.x];
+	const int sl_end = H.sl_end;
 	double2 nkg1 = make_double2(0.0, 0.0);
 	if (PAL1) nkg1 = __ldg(palf);
-	for (int t = cta_tile[blockIdx.x]; t < cta_tile[blockIdx.x + 1]; t++) {
-		const TileDesc T = tiles[t];
+	// ask L2 for the records of slice g (at most 4 KB = 32 lines; longer rows are caught up by the loop's own look-ahead)
+	auto request = [&](int g) {
+		if (g < sl_end) {
+			const int o0 = __ldg(warp_off + g), o1 = __ldg(warp_off + g + 1);
+			if (lane * 8 < o1 - o0) asm volatile("prefetch.global.L2 [%0];" ::"l"(heL + o0 + lane * 8));
+		}
+	};
+	for (int t = H.tile0; t < H.tile0 + H.ntiles; t++) {
+		const TileDesc T = (t == H.tile0) ? H.first : tiles[t];
 		const int n_sl = T.s1 - T.s0;
 		__syncthreads();  // everyone has left the previous tile (its table, headers and s_next)
-		for (int i = tid; i < T.n_slots; i += TL_THREADS) {
-			const int r = __ldg(tab + T.tab_off + i);
-			double2 a = make_double2(0.0, 0.0), b = a, c = a;
-			double m = 1.0;
-			if (r >= 0) { a = __ldcg(mir.xy + r); b = __ldcg(mir.zv + r); c = __ldcg(mir.vxy + r); m = __ldcg(mir.m + r); }
-			s_xy[i] = a; s_zv[i] = b; s_vxy[i] = c; s_m[i] = m;
+		// ---- before the table exists: this warp's first slice is slice `warp`; its header and first records are requested
+		//      now and arrive while the table is being filled ----
+		int sw = warp;
+		int4 gi = make_int4(-1, -1, 0, 0);
+		int off = 0, P = 0;
+		int4 r0 = make_int4(0, 0, 0, 0), r1 = r0;
+		if (sw < n_sl) {
+			gi = __ldg(grpT + (size_t) (T.s0 + sw) * GPW + lane / SPRING_LANES);
+			off = __ldg(warp_off + T.s0 + sw);
+			P = (__ldg(warp_off + T.s0 + sw + 1) - off) >> 6;
+			if (P > 0) { r0 = __ldcg((const int4*) heL + off + lane); r1 = __ldcg((const int4*) heL + off + lane + 32); }
+		}
+		if (t == H.tile0) {  // the stream's head start: the slices the warps will take next
+			request(T.s0 + TL_WARPS + warp);
+			request(T.s0 + 2 * TL_WARPS + warp);
+		}
+		// ---- the table: every request of a thread is in flight before its first store ----
+		{
+			int r[TL_FILL];
+#pragma unroll
+			for (int q = 0; q < TL_FILL; q++) {
+				const int i = tid + q * TL_THREADS;
+				r[q] = (i < T.n_slots) ? __ldg(tab + T.tab_off + i) : -1;
+			}
+			double2 a[TL_FILL], b[TL_FILL], c[TL_FILL];
+			double m[TL_FILL];
+#pragma unroll
+			for (int q = 0; q < TL_FILL; q++) {
+				a[q] = make_double2(0.0, 0.0); b[q] = a[q]; c[q] = a[q]; m[q] = 1.0;
+				if (r[q] >= 0) { a[q] = __ldcg(mir.xy + r[q]); b[q] = __ldcg(mir.zv + r[q]); c[q] = __ldcg(mir.vxy + r[q]); m[q] = __ldcg(mir.m + r[q]); }
+			}
+#pragma unroll
+			for (int q = 0; q < TL_FILL; q++) {
+				const int i = tid + q * TL_THREADS;
+				if (i < T.n_slots) { s_xy[i] = a[q]; s_zv[i] = b[q]; s_vxy[i] = c[q]; s_m[i] = m[q]; }
+			}
 		}
 		for (int i = tid; i < n_sl * GPW; i += TL_THREADS) s_grp[i] = __ldg(grpT + (size_t) T.s0 * GPW + i);
 		for (int i = tid; i <= n_sl; i += TL_THREADS) s_off[i] = __ldg(warp_off + T.s0 + i);
-		if (tid == 0) s_next = 0;
+		if (tid == 0) s_next = TL_WARPS;
 		__syncthreads();
-		while (true) {
-			int sw = 0;
-			if (lane == 0) sw = atomicAdd(&s_next, 1);
-			sw = __shfl_sync(0xffffffffu, sw, 0);
-			if (sw >= n_sl) break;
-			const int4 gi = s_grp[sw * GPW + lane / SPRING_LANES];  // (slot, rank, degree, node); slot < 0: padding group
-			const int off = s_off[sw];
-			const int P = (s_off[sw + 1] - off) >> 6;
-			// ask for the next slice's records (at most 4 KB = 32 lines; the counter hands it out next, to some warp of this CTA)
-			if (sw + 1 < n_sl && lane * 8 < s_off[sw + 2] - s_off[sw + 1]) asm volatile("prefetch.global.L2 [%0];" ::"l"(heL + s_off[sw + 1] + lane * 8));
+		while (sw < n_sl) {
+			// the slice after this one: taken from the counter now, so its header and first records are on their way
+			// long before this slice's last pair
+			int nx = 0;
+			if (lane == 0) nx = atomicAdd(&s_next, 1);
+			nx = __shfl_sync(0xffffffffu, nx, 0);
+			request(T.s0 + nx + TL_AHEAD);
 			const bool live = gi.x >= 0;
 			const int slot = live ? gi.x : 0;
 			const int nt = (gi.z - sub + SPRING_LANES - 1) / SPRING_LANES;  // entries sub, sub + SPRING_LANES, ... of the row are this lane's
@@ -178,8 +238,17 @@ __global__ void __launch_bounds__(TL_THREADS, 1) k_spring_tiles(const GlobalNode
 			a_old.x = 0.0; a_old.y = 0.0; a_old.z = 0.0; a_old.w = 0.0;
 			if (!ZERO_FIRST && live && sub == 0) a_old = acc[gi.w];  // needed after the sum: requested now
 			const NodeState ni = nodes.get<false>(slot);
-			const Force3 F = lane_spring_sum<UNI, PAL1, false>((const int4*) heL + off + lane, P, nt, ni, nodes, palf, nkg1);
+			int4 gi_n = make_int4(-1, -1, 0, 0);
+			int off_n = 0, P_n = 0;
+			if (nx < n_sl) {
+				gi_n = s_grp[nx * GPW + lane / SPRING_LANES];  // (slot, rank, degree, node); slot < 0: padding group
+				off_n = s_off[nx];
+				P_n = (s_off[nx + 1] - off_n) >> 6;
+			}
+			const Force3 F = lane_spring_sum_x<UNI, PAL1, TL_CHAINS>((const int4*) heL + off + lane, P, nt, ni, nodes, palf, nkg1, r0, r1,
+					P_n > 0 ? (const int4*) heL + off_n + lane : nullptr);
 			if (live && sub == 0) finish_node<KICK>(F, gi.z > 0, a_old, ni, gi.w, gi.y, acc, posm_out, vel_out, out, dt, pre_drift_next);
+			sw = nx; gi = gi_n; off = off_n; P = P_n;
 		}
 	}
 }
@@ -362,7 +431,7 @@ int ass_build_spring_tiles(ass_sim* s, const SpringLayout& lay) {
 	const int ns = (int) lay.warp_off.size() - 1;
 	if (ns <= 0 || lay.heT.empty()) return ASS_OK;
 	// small bodies: at least ~4 slices per CTA, so that a few thousand nodes already spread over the whole machine
-	int grid = std::max(1, std::min((ns + 3) / 4, ass_sm_count()));
+	int grid = std::max(1, std::min(std::min((ns + 3) / 4, ass_sm_count()), TL_MAX_CTAS));
 	int slots_limit = TILE_SLOTS_LIMIT;
 	// test hooks: fewer CTAs / smaller tables, so that a small body exercises several tiles per CTA
 	if (const char* e = getenv("ASS_TILE_GRID")) grid = std::max(1, std::min(grid, atoi(e)));
@@ -374,13 +443,24 @@ int ass_build_spring_tiles(ass_sim* s, const SpringLayout& lay) {
 	if ((rc = tiles_reserve(s->grpT, s->grpT_cap, th.grpT.size(), "tile lane groups"))) return rc;
 	if ((rc = tiles_reserve(s->tile_tab, s->tile_tab_cap, th.tab.size(), "tile table entries"))) return rc;
 	if ((rc = tiles_reserve(s->tile_desc, s->tile_desc_cap, th.tiles.size(), "tile descriptors"))) return rc;
-	if ((rc = tiles_reserve(s->cta_tile, s->cta_tile_cap, th.cta_tile.size(), "tile cuts"))) return rc;
 	CU_TRY(cudaMemcpyAsync(s->heL, th.heL.data(), sizeof(HalfEdge) * th.heL.size(), cudaMemcpyHostToDevice, s->stream));
 	CU_TRY(cudaMemcpyAsync(s->grpT, th.grpT.data(), sizeof(int4) * th.grpT.size(), cudaMemcpyHostToDevice, s->stream));
 	CU_TRY(cudaMemcpyAsync(s->tile_tab, th.tab.data(), sizeof(int) * th.tab.size(), cudaMemcpyHostToDevice, s->stream));
 	CU_TRY(cudaMemcpyAsync(s->tile_desc, th.tiles.data(), sizeof(TileDesc) * th.tiles.size(), cudaMemcpyHostToDevice, s->stream));
-	CU_TRY(cudaMemcpyAsync(s->cta_tile, th.cta_tile.data(), sizeof(int) * th.cta_tile.size(), cudaMemcpyHostToDevice, s->stream));
 	CU_TRY(cudaStreamSynchronize(s->stream));
+	// per-CTA heads: they travel as kernel parameters (k_spring_tiles)
+	s->tile_heads.assign((size_t) grid * (sizeof(CtaHead) / sizeof(int)), 0);
+	for (int c = 0; c < grid; c++) {
+		CtaHead h;
+		memset(&h, 0, sizeof(h));
+		h.tile0 = th.cta_tile[(size_t) c];
+		h.ntiles = th.cta_tile[(size_t) c + 1] - h.tile0;
+		if (h.ntiles > 0) {
+			h.first = th.tiles[(size_t) h.tile0];
+			h.sl_end = th.tiles[(size_t) h.tile0 + h.ntiles - 1].s1;
+		}
+		memcpy(s->tile_heads.data() + (size_t) c * (sizeof(CtaHead) / sizeof(int)), &h, sizeof(h));
+	}
 	s->tiles_grid = grid;
 	s->tile_slots_max = th.slots_max;
 	s->tile_slices_max = th.slices_max;
@@ -501,14 +581,14 @@ extern "C" int ass_selfcheck_spring_layout(const double* pos_xyzm, int n, const 
 template <bool ZERO_FIRST, bool KICK, bool UNI, bool PAL1>
 static int launch_tiles_t(ass_sim* s, double dt, int pre) {
 	auto kern = k_spring_tiles<ZERO_FIRST, KICK, UNI, PAL1>;
-	static size_t smem_set = 0;  // per instantiation
 	const size_t smem = TILE_SLOT_BYTES * (size_t) s->tile_slots_max + (size_t) s->tile_slices_max * GPW * sizeof(int4) + sizeof(int) * ((size_t) s->tile_slices_max + 2);
-	if (smem > smem_set) {
-		CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-		smem_set = smem;
-	}
-	kern<<<s->tiles_grid, TL_THREADS, smem, s->stream>>>(mirror_nodes(s), s->acc, (const TileDesc*) s->tile_desc, s->cta_tile, s->tile_tab, s->grpT,
-			s->warp_off, s->heL, s->palf, s->tile_slots_max, s->tile_slices_max, KICK ? s->posm_alt : nullptr, KICK ? s->vel_alt : nullptr, s->mir_alt, dt, pre);
+	// the opt-in above 48 KB is per function AND per device: set on every launch (a host-side table lookup) rather than
+	// remembered per process
+	CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+	TilesParams P;
+	memcpy(&P, s->tile_heads.data(), std::min(sizeof(P), s->tile_heads.size() * sizeof(int)));
+	kern<<<s->tiles_grid, TL_THREADS, smem, s->stream>>>(P, mirror_nodes(s), s->acc, (const TileDesc*) s->tile_desc, s->tile_tab, s->grpT, s->warp_off, s->heL,
+			s->palf, s->tile_slots_max, s->tile_slices_max, KICK ? s->posm_alt : nullptr, KICK ? s->vel_alt : nullptr, s->mir_alt, dt, pre);
 	return ASS_OK;
 }
 
@@ -542,6 +622,26 @@ int ass_launch_spring_forces_range(ass_sim* s, bool zero_first, int lo, int hi) 
 	ass_tic(s, ASS_K_SPRINGS);
 	if ((rc = launch_mirror(s))) return rc;
 	launch_csr<false, true>(s, zero_first, uni, lo, hi, 0.0, 0);
+	LAUNCH_CHECK();
+	ass_toc(s, ASS_K_SPRINGS);
+	return ASS_OK;
+}
+
+int ass_springs_prepare(ass_sim* s) {
+	bool uni;
+	return springs_uniform_mass(s, &uni);
+}
+
+// springs + kick + drift(s) for NODES [lo, hi) of a sharded body (shard.cu): gathers from the mirror of posm / vel (all
+// nodes of the current buffer), writes the own nodes of posm_alt / vel_alt (the other buffer).  The caller swaps.
+int ass_launch_spring_kick_drift_range(ass_sim* s, bool zero_first, double dt, bool pre_drift_next, int lo, int hi) {
+	if (hi <= lo) return ASS_OK;
+	bool uni;
+	int rc = springs_uniform_mass(s, &uni);  // cached: shard_prepare asked before the step was queued
+	if (rc) return rc;
+	ass_tic(s, ASS_K_SPRINGS);
+	if ((rc = launch_mirror(s))) return rc;
+	launch_csr<true, true>(s, zero_first, uni, lo, hi, dt, pre_drift_next ? 1 : 0);
 	LAUNCH_CHECK();
 	ass_toc(s, ASS_K_SPRINGS);
 	return ASS_OK;

@@ -285,6 +285,43 @@ extern "C" int ass_mark_end(ass_sim* s, double* ms) {
 	return ASS_OK;
 }
 
+// Lap timer: event pairs on the simulation's stream, recorded without waiting for anything, summed when collected.  For
+// loops whose iterations must stay queued back to back (a sharded body's steps: a host that waited for every step
+// would be in the loop it is supposed to stay out of) but whose timed region excludes something between the iterations
+// (the L2 flush).
+extern "C" int ass_lap_begin(ass_sim* s) {
+	REQUIRE(s, ASS_EINVAL, "null sim");
+	if (s->lap_open >= (int) s->lap_ev.size()) {
+		cudaEvent_t a, b;
+		CU_TRY(cudaEventCreate(&a));
+		CU_TRY(cudaEventCreate(&b));
+		s->lap_ev.push_back({ a, b });
+	}
+	CU_TRY(cudaEventRecord(s->lap_ev[(size_t) s->lap_open].first, s->stream));
+	return ASS_OK;
+}
+extern "C" int ass_lap_end(ass_sim* s) {
+	REQUIRE(s, ASS_EINVAL, "null sim");
+	REQUIRE(s->lap_open < (int) s->lap_ev.size(), ASS_ESTATE, "ass_lap_end without ass_lap_begin");
+	CU_TRY(cudaEventRecord(s->lap_ev[(size_t) s->lap_open].second, s->stream));
+	s->lap_open++;
+	return ASS_OK;
+}
+extern "C" int ass_lap_collect(ass_sim* s, double* total_ms, int* laps) {
+	REQUIRE(s && total_ms, ASS_EINVAL, "null argument");
+	int rc = ass_sync(s);
+	double tot = 0.0;
+	for (int i = 0; i < s->lap_open; i++) {
+		float ms = 0.f;
+		CU_TRY(cudaEventElapsedTime(&ms, s->lap_ev[(size_t) i].first, s->lap_ev[(size_t) i].second));
+		tot += ms;
+	}
+	*total_ms = tot;
+	if (laps) *laps = s->lap_open;
+	s->lap_open = 0;
+	return rc;
+}
+
 __global__ void k_fill(double* p, size_t n, double v) {
 	size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
 	size_t stride = (size_t) gridDim.x * blockDim.x;
@@ -338,7 +375,7 @@ extern "C" int ass_destroy(ass_sim* s) {
 	ass_shard_release(s);  // a sharded simulation's posm / vel alias its exported window
 	ass_sym_plans_free(s);
 	cudaFree(s->slotT); cudaFree(s->warp_off);
-	cudaFree(s->heL); cudaFree(s->grpT); cudaFree(s->tile_tab); cudaFree(s->tile_desc); cudaFree(s->cta_tile);
+	cudaFree(s->heL); cudaFree(s->grpT); cudaFree(s->tile_tab); cudaFree(s->tile_desc);
 	cudaFree(s->order); cudaFree(s->rank); cudaFree(s->mir_block); cudaFree(s->mir_m);
 	cudaFree(s->posm); cudaFree(s->vel); cudaFree(s->acc); cudaFree(s->posm_alt); cudaFree(s->vel_alt);
 	cudaFree(s->he); cudaFree(s->row_ptr); cudaFree(s->slot); cudaFree(s->pal);
@@ -347,6 +384,10 @@ extern "C" int ass_destroy(ass_sim* s) {
 	if (s->h_red) cudaFreeHost(s->h_red);
 	if (s->h_pinned) cudaFreeHost(s->h_pinned);
 	for (auto& e : s->ev_pool) {
+		cudaEventDestroy(e.first);
+		cudaEventDestroy(e.second);
+	}
+	for (auto& e : s->lap_ev) {
 		cudaEventDestroy(e.first);
 		cudaEventDestroy(e.second);
 	}
@@ -360,6 +401,7 @@ extern "C" int ass_destroy(ass_sim* s) {
 
 extern "C" int ass_sync(ass_sim* s) {
 	REQUIRE(s, ASS_EINVAL, "null sim");
+	if (s->shard.active) return ass_shard_sync(s);  // both streams, and the verdict of the device-side waits
 	CU_TRY(cudaStreamSynchronize(s->stream));
 	return ASS_OK;
 }
@@ -473,6 +515,63 @@ static int ensure_pinned(ass_sim* s, size_t bytes) {
 	return ASS_OK;
 }
 
+// rows [lo, hi) of the caller's array <-> particles [lo, hi) of the device state
+static int upload_rows(ass_sim* s, const void* base, size_t stride, int lo, int hi, unsigned fields) {
+	const int cnt = hi - lo;
+	if (cnt <= 0) return ASS_OK;
+	const size_t bytes = (size_t) cnt * stride;
+	int rc = ass_buf_reserve(s->stage, bytes);
+	if (rc) return rc;
+	ass_tic(s, ASS_K_XFER);
+	// One plain copy of the raw rows.  From a range pinned through ass_host_register / ass_host_alloc the copy engine
+	// reads the caller's rows at link rate; from pageable memory (the default: realloc'd by reb_add,
+	// src/particle.c:53-56) the driver stages it.
+	CU_TRY(cudaMemcpyAsync(s->stage.p, (const unsigned char*) base + (size_t) lo * stride, bytes, cudaMemcpyHostToDevice, s->stream));
+	k_unpack_rows<<<(cnt + 255) / 256, 256, 0, s->stream>>>((const unsigned char*) s->stage.p, stride, cnt, fields, s->posm + lo, s->vel + lo, s->acc + lo);
+	LAUNCH_CHECK();
+	ass_toc(s, ASS_K_XFER);
+	// pageable source: the copy has been staged when cudaMemcpyAsync returns, but keep the contract simple
+	CU_TRY(cudaStreamSynchronize(s->stream));
+	return ASS_OK;
+}
+
+static int download_rows(ass_sim* s, void* base, size_t stride, int lo, int hi, unsigned fields) {
+	const int cnt = hi - lo;
+	if (cnt <= 0) return ASS_OK;
+	int rc;
+	unsigned char* first = (unsigned char*) base + (size_t) lo * stride;
+	// Only the requested doubles may change on the host (the rows also hold pointers, hash, r, ...).
+	if (unsigned char* alias = pinned_alias(first, (size_t) (cnt - 1) * stride + 10 * sizeof(double))) {
+		ass_tic(s, ASS_K_XFER);
+		const long long threads = 16LL * cnt;
+		k_pack_rows_direct<<<(unsigned) ((threads + 255) / 256), 256, 0, s->stream>>>(alias, stride, cnt, fields, s->posm + lo, s->vel + lo, s->acc + lo);
+		LAUNCH_CHECK();
+		ass_toc(s, ASS_K_XFER);
+		CU_TRY(cudaStreamSynchronize(s->stream));
+		return ASS_OK;
+	}
+	// pageable rows: pack the fields densely on the device, copy that, and scatter into the caller's rows here
+	const size_t dense = (size_t) cnt * 10 * sizeof(double);
+	if ((rc = ass_buf_reserve(s->stage, dense))) return rc;
+	if ((rc = ensure_pinned(s, dense))) return rc;
+	ass_tic(s, ASS_K_XFER);
+	k_pack_rows<<<(cnt + 255) / 256, 256, 0, s->stream>>>((unsigned char*) s->stage.p, 10 * sizeof(double), cnt, fields, s->posm + lo, s->vel + lo, s->acc + lo);
+	LAUNCH_CHECK();
+	CU_TRY(cudaMemcpyAsync(s->h_pinned, s->stage.p, dense, cudaMemcpyDeviceToHost, s->stream));
+	ass_toc(s, ASS_K_XFER);
+	CU_TRY(cudaStreamSynchronize(s->stream));
+	const double* src = (const double*) s->h_pinned;
+	for (int i = 0; i < cnt; i++) {
+		double* r = (double*) (first + (size_t) i * stride);
+		const double* q = src + (size_t) i * 10;
+		if (fields & ASS_F_POS) { r[0] = q[0]; r[1] = q[1]; r[2] = q[2]; }
+		if (fields & ASS_F_VEL) { r[3] = q[3]; r[4] = q[4]; r[5] = q[5]; }
+		if (fields & ASS_F_ACC) { r[6] = q[6]; r[7] = q[7]; r[8] = q[8]; }
+		if (fields & ASS_F_MASS) r[9] = q[9];
+	}
+	return ASS_OK;
+}
+
 extern "C" int ass_upload_particles(ass_sim* s, const void* base, size_t stride, int n, unsigned fields) {
 	REQUIRE(s, ASS_EINVAL, "null sim");
 	REQUIRE(n >= 0, ASS_EINVAL, "negative particle count");
@@ -484,31 +583,37 @@ extern "C" int ass_upload_particles(ass_sim* s, const void* base, size_t stride,
 	if (n != s->n) {
 		// a different particle count is a new body: everything must come from the host
 		REQUIRE(fields == ASS_F_ALL, ASS_ESTATE, "particle count changed: upload ASS_F_ALL");
+		REQUIRE(!s->shard.active, ASS_ESTATE, "a sharded simulation keeps its particle count");
 		if ((rc = ensure_particles(s, n))) return rc;
-		if (n != s->n) { s->ns = 0; s->n_he = 0; ass_sym_plans_free(s); }  // springs and gravity plans refer to the old body
+		if (n != s->n) { s->ns = 0; s->n_he = 0; s->tiles_grid = 0; ass_sym_plans_free(s); }  // springs and gravity plans refer to the old body
 		s->n = n;
 	}
-	// a pre-drifted body (ass_shard_finish(pre_drift_next = 1)) may only be REPLACED: patching positions or velocities
+	// a pre-drifted body (ass_shard_step(..., pre_drift_last = 1)) may only be REPLACED: patching positions or velocities
 	// into a half-drifted state would be applied to the wrong instant
 	REQUIRE(!s->predrifted || (fields & (ASS_F_POS | ASS_F_VEL)) == (ASS_F_POS | ASS_F_VEL), ASS_ESTATE,
-	        "positions are pre-drifted: upload positions and velocities together, or finish a step without pre_drift_next first");
+	        "positions are pre-drifted: upload positions and velocities together, or finish a step without pre_drift_last first");
 	s->predrifted = false;
 	if (fields & ASS_F_MASS) s->mass_epoch++;
-	if (n == 0) { s->have_state = true; return ASS_OK; }
-	const size_t bytes = (size_t) n * stride;
-	if ((rc = ass_buf_reserve(s->stage, bytes))) return rc;
-	ass_tic(s, ASS_K_XFER);
-	// One plain copy of the raw rows.  From a range pinned through ass_host_register / ass_host_alloc the copy engine
-	// reads the caller's rows at link rate; from pageable memory (the default: realloc'd by reb_add,
-	// src/particle.c:53-56) the driver stages it.
-	CU_TRY(cudaMemcpyAsync(s->stage.p, base, bytes, cudaMemcpyHostToDevice, s->stream));
-	k_unpack_rows<<<(n + 255) / 256, 256, 0, s->stream>>>((const unsigned char*) s->stage.p, stride, n, fields, s->posm, s->vel, s->acc);
-	LAUNCH_CHECK();
-	ass_toc(s, ASS_K_XFER);
-	// pageable source: the copy has been staged when cudaMemcpyAsync returns, but keep the contract simple
-	CU_TRY(cudaStreamSynchronize(s->stream));
+	if ((rc = upload_rows(s, base, stride, 0, n, fields))) return rc;
 	s->have_state = true;
 	return ASS_OK;
+}
+
+// ass_upload_particles for rows [i_low, i_high) only (`base` is row 0 of the caller's array): a rank of a sharded body
+// refreshing its own slab, or a module that moved a few particles on the host.
+extern "C" int ass_upload_range(ass_sim* s, const void* base, size_t stride, int i_low, int i_high, unsigned fields) {
+	REQUIRE(s, ASS_EINVAL, "null sim");
+	REQUIRE(s->have_state, ASS_ESTATE, "upload the whole body first");
+	REQUIRE(i_low >= 0 && i_high <= s->n && i_low <= i_high, ASS_EINVAL, "bad particle range");
+	REQUIRE(stride >= 10 * sizeof(double) && stride % sizeof(double) == 0, ASS_EINVAL, "stride must hold the 10 leading doubles and be 8-byte aligned");
+	REQUIRE((fields & ~ASS_F_ALL) == 0 && fields != 0, ASS_EINVAL, "bad field mask");
+	REQUIRE(!s->predrifted, ASS_ESTATE, "positions are pre-drifted: finish a step without pre_drift_last first");
+	if (i_low == i_high) return ASS_OK;
+	REQUIRE(base, ASS_EINVAL, "null particle array");
+	int rc = ass_ensure_device();
+	if (rc) return rc;
+	if (fields & ASS_F_MASS) s->mass_epoch++;
+	return upload_rows(s, base, stride, i_low, i_high, fields);
 }
 
 extern "C" int ass_download_particles(ass_sim* s, void* base, size_t stride, int n, unsigned fields) {
@@ -522,37 +627,23 @@ extern "C" int ass_download_particles(ass_sim* s, void* base, size_t stride, int
 	if (n == 0) return ASS_OK;
 	int rc = ass_ensure_device();
 	if (rc) return rc;
-	// Only the requested doubles may change on the host (the rows also hold pointers, hash, r, ...): pack the
-	// fields densely on the device, copy that, and scatter into the caller's rows here.
-	if (unsigned char* alias = pinned_alias(base, (size_t) (n - 1) * stride + 10 * sizeof(double))) {
-		ass_tic(s, ASS_K_XFER);
-		const long long threads = 16LL * n;
-		k_pack_rows_direct<<<(unsigned) ((threads + 255) / 256), 256, 0, s->stream>>>(alias, stride, n, fields, s->posm, s->vel, s->acc);
-		LAUNCH_CHECK();
-		ass_toc(s, ASS_K_XFER);
-		CU_TRY(cudaStreamSynchronize(s->stream));
-		return ASS_OK;
-	}
-	const size_t dense = (size_t) n * 10 * sizeof(double);
-	if ((rc = ass_buf_reserve(s->stage, dense))) return rc;
-	if ((rc = ensure_pinned(s, dense))) return rc;
-	ass_tic(s, ASS_K_XFER);
-	k_pack_rows<<<(n + 255) / 256, 256, 0, s->stream>>>((unsigned char*) s->stage.p, 10 * sizeof(double), n, fields, s->posm, s->vel, s->acc);
-	LAUNCH_CHECK();
-	CU_TRY(cudaMemcpyAsync(s->h_pinned, s->stage.p, dense, cudaMemcpyDeviceToHost, s->stream));
-	ass_toc(s, ASS_K_XFER);
-	CU_TRY(cudaStreamSynchronize(s->stream));
-	const double* src = (const double*) s->h_pinned;
-	unsigned char* dst = (unsigned char*) base;
-	for (int i = 0; i < n; i++) {
-		double* r = (double*) (dst + (size_t) i * stride);
-		const double* q = src + (size_t) i * 10;
-		if (fields & ASS_F_POS) { r[0] = q[0]; r[1] = q[1]; r[2] = q[2]; }
-		if (fields & ASS_F_VEL) { r[3] = q[3]; r[4] = q[4]; r[5] = q[5]; }
-		if (fields & ASS_F_ACC) { r[6] = q[6]; r[7] = q[7]; r[8] = q[8]; }
-		if (fields & ASS_F_MASS) r[9] = q[9];
-	}
-	return ASS_OK;
+	return download_rows(s, base, stride, 0, n, fields);
+}
+
+// ass_download_particles for rows [i_low, i_high) only: `base` is row 0 of the caller's array (e.g. to read one point mass
+// for output while the body stays resident, or a rank's own slab of a sharded body).
+extern "C" int ass_download_range(ass_sim* s, void* base, size_t stride, int i_low, int i_high, unsigned fields) {
+	REQUIRE(s, ASS_EINVAL, "null sim");
+	REQUIRE(s->have_state, ASS_ESTATE, "no particle state on the device");
+	REQUIRE(!s->predrifted, ASS_ESTATE, "internal: positions are mid-step");
+	REQUIRE(i_low >= 0 && i_high <= s->n && i_low <= i_high, ASS_EINVAL, "bad particle range");
+	REQUIRE(stride >= 10 * sizeof(double) && stride % sizeof(double) == 0, ASS_EINVAL, "stride must hold the 10 leading doubles and be 8-byte aligned");
+	REQUIRE((fields & ~ASS_F_ALL) == 0 && fields != 0, ASS_EINVAL, "bad field mask");
+	if (i_low == i_high) return ASS_OK;
+	REQUIRE(base, ASS_EINVAL, "null particle array");
+	int rc = ass_ensure_device();
+	if (rc) return rc;
+	return download_rows(s, base, stride, i_low, i_high, fields);
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -1,24 +1,33 @@
 #!/usr/bin/env python
 """bench.py -- node-steps/s of the per-step hot path (springs + direct-sum self-gravity + leapfrog kick/drift).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C1|C2|C3|C4|C5] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C1|C2|C3|C4|C5] [--impl reference] [--no-sub]
 
-Prints ONE JSON line (rank 0).  Default workload: BASELINE config C3 -- a wobble_bennu2-style tumbling viscoelastic
-body, synthetic N ~ 1e5 nodes, REB_GRAVITY_BASIC + spring_forces + leapfrog -- the size north_star quotes its target on.
-With --gpus N > 1 (launched by torchrun, one process per GPU) the default is N independent C3 ensemble members with a
-swept spin rate, one per GPU, no data-path collective ("scaling": "weak"); --workload C4 runs the N = 1e6 body sharded
-over the ranks instead ("strong"), --workload C5 the 4096 x 1k-node ensemble.
+Prints ONE JSON line (rank 0).  The main record is always BASELINE config C3 -- a wobble_bennu2-style tumbling
+viscoelastic body, synthetic N ~ 1e5 nodes, REB_GRAVITY_BASIC + spring_forces + leapfrog -- the size north_star quotes
+its target on:
+    --gpus 1      the body on one GPU (fused step loop);
+    --gpus N > 1  THE SAME body cut into N particle slabs, one rank per GPU under torchrun ("scaling": "strong"): gravity
+                  divided by pairs of slabs, slabs exchanged by copy-engine pulls over CUDA-IPC windows, ranks meeting
+                  on the device through epoch flags (no host barrier inside the step loop).
+The same line carries two sub-records, measured in the same run on the same ranks, each with its own ms_per_step, clock
+samples and parity check:
+    c4_sharded    BASELINE config C4: N ~ 1e6 + a Mars-like point mass, slab-sharded over the N ranks (N = 1: unsharded);
+    c5_ensemble   BASELINE config C5: 4096 independent ~1k-node bodies, dealt to the ranks by cost, no collective.
+--workload X makes X the (only) record instead.
 
 value      whole-job node-steps/s, state resident in HBM, device-timed (CUDA events on the simulation's stream),
-           max over ranks; L2 flushed between steps.
-e2e        the same through the host-facing call sequence a drop-in reb_step makes in its always-coherent mode:
-           every step uploads the host `struct reb_particle`-strided array, steps once, downloads x, v, a.
+           max over ranks; L2 flushed between steps (outside the timed laps).
+e2e        the same through host buffers: every step uploads the host `struct reb_particle`-strided rows from pinned
+           memory, steps once, downloads x, v, a (sharded: every rank its own slab).
 roofline   the dominant kernel (gravity at C2..C4, springs at C1/C5) against the FP64 DFMA peak measured in this run /
            the HBM copy peak of MEASURED_PEAKS.json.
+parity     in-run check of the result against the CPU oracle (a 256-target slab of accelerations after one step) and,
+           for sharded runs, of x, v against the unsharded path on rank 0's GPU.
 cpu_baseline  the UNMODIFIED reference (oracle/_ref, built from /root/reference by oracle/Makefile) timed on this
            box's host on a bounded sample of the same step, serial as shipped.
 --impl reference  the reference's own CPU implementation with every host thread it can correctly use (OpenMP on
-           gravity.c / integrator_leapfrog.c only; its src_spring pragmas are racy).
+           gravity.c / integrator_leapfrog.c only; its src_spring pragmas are racy), on the same body.
 """
 import argparse
 import json
@@ -27,6 +36,7 @@ import subprocess
 import sys
 import threading
 import time
+import traceback
 
 import numpy as np
 
@@ -36,6 +46,7 @@ sys.path.insert(0, ROOT)
 SEED = 12345
 ABC = (1.0, 0.7, 0.5)
 K_SPRING, GAMMA = 0.08, 5.0          # modules/wobble_bennu2/problem.cfg
+ACC_TOL, POS_TOL = 1e-12, 1e-13      # parity bars of tests/test_gpu_parity.py
 
 # name -> (min_dist d, dt, gravity, additional_forces mode, omega)       SURVEY 8d synthetic inputs
 WORKLOADS = {
@@ -55,7 +66,9 @@ def read_json(path):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks / throttle reasons sampled DURING the run (B200_PROFILING.md recipe).  start() returns once the
+    first sample has arrived, so that even a sub-millisecond timed region is bracketed by samples; callers start it
+    before the warm-up steps: the samples then cover warm-up + timed region, i.e. the GPU under this load."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index):
@@ -63,14 +76,18 @@ class ClockSampler:
         self.proc = None
         self.lines = []
 
-    def start(self):
+    def start(self, wait_s=3.0):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "25"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
+            t0 = time.perf_counter()
+            while not self.lines and time.perf_counter() - t0 < wait_s:
+                time.sleep(0.01)
         except Exception:
             self.proc = None
+        return self
 
     def _read(self):
         for line in self.proc.stdout:
@@ -79,7 +96,7 @@ class ClockSampler:
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
@@ -136,9 +153,34 @@ def sum_over_ranks(dist, x, local):
     return launcher.reduce_sum(dist, x, None if dist is None else "cuda:%d" % local)
 
 
+def all_ranks(dist, x):
+    """The value of every rank, as a list (rank order)."""
+    if dist is None:
+        return [x]
+    out = [None] * dist.get_world_size()
+    dist.all_gather_object(out, x)
+    return out
+
+
+def config_of(name, cfg, n, ns, world, mode):
+    """The `config` object -- built by this one function for both arms, so the two lines carry identical keys and values."""
+    if mode == "ensemble":
+        par = "ensemble members dealt to %d GPU(s) by cost, no collective" % world
+    elif world > 1:
+        par = "particle slabs x%d (strong scaling: one body)" % world
+    else:
+        par = "one GPU"
+    return {"workload": "%s: %s" % (name, cfg["desc"]), "N": int(n), "NS": int(ns), "seed": SEED,
+            "generator": "rand_ellipsoid(d=%g, 1, 0.7, 0.5)" % cfg["d"], "max_spring_dist": 2.3 * cfg["d"], "k": K_SPRING, "gamma": GAMMA,
+            "dt": cfg["dt"], "softening": cfg["d"] / 100.0, "gravity": "REB_GRAVITY_BASIC" if cfg["gravity"] else "REB_GRAVITY_NONE",
+            "l2": "b200 arm: flushed between steps (256 MiB fill, outside the device-timed laps); reference arm: host caches as they come",
+            "parallelism": "b200 arm: %s; reference arm: OpenMP over the host cores (gravity, leapfrog)" % par}
+
+
 def build_body(A, cfg, omega, with_point_mass=False):
     """Synthesise a BASELINE config from the module's code path: rand_ellipsoid -> connect_springs_dist ->
-    subtract_com/cov -> spin_body (modules/wobble_bennu2/problem.cpp:63-333), everything through the product."""
+    subtract_com/cov -> spin_body (modules/wobble_bennu2/problem.cpp:63-333), everything through the product.
+    Returns (sim, p0, springs, setup): p0 is the host copy of the initial state."""
     t0 = time.perf_counter()
     A.srand(SEED)
     p = A.rand_ellipsoid(cfg["d"], *ABC, 1.0)
@@ -163,12 +205,411 @@ def build_body(A, cfg, omega, with_point_mass=False):
         p = np.vstack([p, pm])
         n_perts = 1
         sim.upload(p)
+    t0 = time.perf_counter()
     sim.set_springs(springs)
+    t_layout = time.perf_counter() - t0
     sim.set_params(t=0.0, dt=cfg["dt"], G=1.0, softening=cfg["d"] / 100.0, gravity=cfg["gravity"], n_active=-1,
                    n_perts=n_perts, additional_forces=cfg["af"], heartbeat=0)
-    return sim, p, springs, {"gen_s": t_gen, "connect_s": t_connect}
+    return sim, p, springs, {"gen_s": t_gen, "connect_s": t_connect, "set_springs_s": t_layout}
 
 
+# ---------------------------------------------------------------------------------------------------
+# parity inside the run
+# ---------------------------------------------------------------------------------------------------
+def oracle_first_step_acc(p0, springs, cfg, n_perts, lo, hi):
+    """Accelerations of particles [lo, hi) at the first step's force evaluation, by the CPU oracle: part1, then
+    REB_GRAVITY_BASIC for those targets over all sources, then spring_forces (a checker; never the thing measured)."""
+    from oracle.bindings import Oracle, make_sim
+    orc = Oracle()
+    q = np.ascontiguousarray(p0[:, :11]).copy()
+    sim = make_sim(dt=cfg["dt"], G=1.0, softening=cfg["d"] / 100.0, gravity_basic=cfg["gravity"], zero_first=(cfg["af"] == 2), n_perts=n_perts)
+    orc.leapfrog_part1(q, sim)
+    if cfg["gravity"] and cfg["af"] != 2:
+        orc.gravity_basic(q, G=1.0, softening=cfg["d"] / 100.0, i_lo=lo, i_hi=hi)
+    else:
+        q[:, 6:9] = 0.0 if cfg["af"] == 2 else q[:, 6:9]
+    orc.spring_forces(q, springs)
+    return q[lo:hi, 6:9].copy()
+
+
+def parity_of_sim(A, dist, sim, p0, springs, cfg, n_perts, rank, world, bounds):
+    """Re-run the body from its initial state: one step -> accelerations of a 256-target slab against the oracle;
+    a second step -> x, v (sharded: of the gathered body) against the unsharded path on this rank's GPU (rank 0).
+    Returns the parity object (rank 0) after every rank has taken part in the collective calls."""
+    n = len(p0)
+    sharded = bounds is not None
+    lo, hi = (bounds[rank], bounds[rank + 1]) if sharded else (0, n)
+    prm = dict(t=0.0, dt=cfg["dt"])
+    out1 = p0.copy()
+    out2 = p0.copy()
+    sim.upload(p0)
+    sim.set_params(**prm)
+    if sharded:
+        sim.shard_step(1); sim.shard_gather(); sim.sync()
+        sim.download(out1)
+        sim.shard_step(1); sim.shard_gather(); sim.sync()
+        sim.download(out2)
+    else:
+        sim.step(1); sim.download(out1)
+        sim.step(1); sim.download(out2)
+    res = None
+    if rank == 0:
+        t_lo = lo + max(0, (hi - lo) // 2 - 128)
+        t_hi = min(hi, t_lo + 256)
+        res = {"steps": 2, "targets": [int(t_lo), int(t_hi)]}
+        try:
+            want = oracle_first_step_acc(p0, springs, cfg, n_perts, t_lo, t_hi)
+            amax = float(np.abs(want).max())
+            res["acc_vs_oracle"] = float(np.abs(out1[t_lo:t_hi, 6:9] - want).max() / max(amax, 1e-300))
+            res["acc_tol"] = ACC_TOL
+        except Exception as e:  # oracle library missing on this box
+            res["acc_vs_oracle"] = None
+            res["oracle_error"] = repr(e)
+        if sharded:
+            with A.Sim() as u:
+                u.upload(p0); u.set_springs(springs)
+                u.set_params(t=0.0, dt=cfg["dt"], G=1.0, softening=cfg["d"] / 100.0, gravity=cfg["gravity"], n_active=-1, n_perts=n_perts,
+                             additional_forces=cfg["af"], heartbeat=0)
+                u.step(1); w1 = u.download(p0.copy())
+                u.step(1); w2 = u.download(p0.copy())
+            amax = float(np.abs(w1[:, 6:9]).max())
+            res["acc_own_slab_vs_1gpu"] = float(np.abs(out1[lo:hi, 6:9] - w1[lo:hi, 6:9]).max() / max(amax, 1e-300))
+            res["xv_vs_1gpu_max_abs"] = float(np.abs(out2[:, :6] - w2[:, :6]).max())
+            res["xv_tol"] = POS_TOL
+        checks = [res.get("acc_vs_oracle") is not None and res["acc_vs_oracle"] <= ACC_TOL]
+        if sharded:
+            checks += [res["acc_own_slab_vs_1gpu"] <= ACC_TOL, res["xv_vs_1gpu_max_abs"] <= POS_TOL]
+        res["ok"] = bool(all(checks))
+    return res
+
+
+# ---------------------------------------------------------------------------------------------------
+# one body on one GPU
+# ---------------------------------------------------------------------------------------------------
+def run_single(args, A, name, cfg, local, want_e2e=True, want_cpu=True, steps=None, warmup=None):
+    steps = steps or args.steps
+    warmup = warmup or args.warmup
+    sim, p0, springs, setup = build_body(A, cfg, cfg["omega"], with_point_mass=(name == "C4"))
+    n, ns = len(p0), len(springs)
+    n_perts = 1 if name == "C4" else 0
+    clocks = ClockSampler(local).start()
+    sim.step(warmup)
+    sim.sync()
+    fp64_peak, _ = A.probe_fp64_peak(1 << 13)
+    sim.timing(True)
+    sim.timing_reset()
+    launches0 = A.launch_count()
+    sim.sync()
+    t_wall0 = time.perf_counter()
+    dev_ms = 0.0
+    for _ in range(steps):
+        sim.l2_flush()
+        sim.mark_begin()
+        sim.step(1)
+        dev_ms += sim.mark_end()
+    sim.sync()
+    t_wall = time.perf_counter() - t_wall0
+    clk = clocks.stop()
+    launches = A.launch_count() - launches0
+    kt = sim.timing_get()
+    sim.timing(False)
+    value = n * steps / (dev_ms * 1e-3)
+
+    # ---- end to end through host buffers (the drop-in's always-coherent reb_step) ----
+    e2e = None
+    if want_e2e and not args.no_e2e:
+        # 128-byte rows == sizeof(struct reb_particle), in page-locked host memory (ass_host_alloc): what the drop-in's
+        # reb_integrate gives the module's own r->particles by pinning it in place (ass_host_register)
+        pinned = A.PinnedRows(n, 16)
+        host = pinned.a
+        host[:] = 0.0
+        sim.download(host)
+        for _ in range(2):
+            sim.upload(host); sim.step(1); sim.download(host, A.F_POS | A.F_VEL | A.F_ACC)
+        k = min(steps, 20)
+        t0 = time.perf_counter()
+        for _ in range(k):
+            sim.upload(host)
+            sim.step(1)
+            sim.download(host, A.F_POS | A.F_VEL | A.F_ACC)
+        t_e2e = time.perf_counter() - t0
+        e2e = {"value": n * k / t_e2e, "unit": "node-steps/s", "h2d_bytes_per_step": int(n * 128), "d2h_bytes_per_step": int(n * 72),
+               "host_memory": "pinned (ass_host_alloc)", "steps": k}
+        del host
+        pinned.close()
+
+    parity = parity_of_sim(A, None, sim, p0, springs, cfg, n_perts, 0, 1, None)
+
+    # ---- roofline of the dominant kernel ----
+    peaks = read_json(os.path.join(ROOT, "MEASURED_PEAKS.json")) or {}
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    hbm_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+    traffic = (read_json(os.path.join(ROOT, "profiles", "traffic.json")) or {}).get(name, {})
+    g_ms, g_n = kt["gravity"]
+    s_ms, s_n = kt["springs"]
+    roof_g = roof_s = None
+    if g_n:
+        # one gravity evaluation per step = the pair kernel + its fixed-order row reduction (both inside the timer)
+        ach = 20.0 * n * n * steps / (g_ms * 1e-3) / 1e12    # SURVEY 8d: 20 flop per ordered pair
+        nominal = 148 * 128 * 1.965e9 / 1e12                 # 148 SMs x 64 DFMA lanes x 2 flop x 1.965 GHz
+        roof_g = {"kernel": "k_gravity_sym (+ its row reduction)", "bound": "fp64", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach / fp64_peak,
+                  "frac_of_nominal_37.2": ach / nominal,
+                  "traffic": traffic.get("gravity"), "peak_source": "DFMA microbenchmark measured in this run (ass_probe_fp64_peak); MEASURED_PEAKS.json has no FP64 figure",
+                  "pairs_per_s": n * n * steps / (g_ms * 1e-3), "ms_per_evaluation": g_ms / steps}
+    if s_n:
+        alg = 32.0 * ns + 80.0 * n                                    # SURVEY 8d
+        ach = alg * s_n / (s_ms * 1e-3) / 1e9
+        roof_s = {"kernel": "k_spring_tiles<KICK> (springs + kick + drift)", "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+                  "traffic": traffic.get("springs"), "peak_source": hbm_src, "algorithmic_bytes_per_launch": alg, "ms_per_launch": s_ms / s_n}
+    dominant = roof_g if (roof_g and g_ms >= s_ms) else roof_s
+
+    # ---- CPU baseline: the unmodified reference on this host, bounded sample ----
+    cpu = None
+    if want_cpu and not args.no_cpu_baseline:
+        try:
+            v, sample, cores, detail = reference_arm_value(cfg, np.ascontiguousarray(p0[:, :11]), springs, budget_s=12.0, omp=False)
+            cpu = {"value": v, "unit": "node-steps/s", "cores": cores, "host_cores": os.cpu_count(), "kind": "reference",
+                   "sample": sample + "; built -O3 -march=x86-64-v3 (no AVX-512: the path is scalar sqrt/div)"}
+        except FileNotFoundError as e:
+            cpu = {"value": None, "unit": "node-steps/s", "cores": 0, "kind": "reference", "sample": "unavailable: %s" % e}
+    sim.close()
+    return {
+        "metric": "node-steps/s", "value": value, "unit": "node-steps/s", "n_gpus": 1, "steps": steps, "warmup": warmup,
+        "ms_per_step": dev_ms / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic", "config": config_of(name, cfg, n, ns, 1, "single"),
+        "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "parity": parity,
+        "roofline": dominant, "roofline_gravity": roof_g, "roofline_springs": roof_s, "cpu_baseline": cpu,
+        "kernel_ms": {k: {"ms": v[0], "launches": v[1]} for k, v in kt.items()},
+        "wall_ms_per_step_incl_flush": 1e3 * t_wall / steps, "setup": setup, "fp64_peak_tflops_measured": fp64_peak,
+    }
+
+
+# ---------------------------------------------------------------------------------------------------
+# one body sharded by particle slabs over the ranks
+# ---------------------------------------------------------------------------------------------------
+def run_sharded(args, A, name, cfg, rank, world, local, dist, want_e2e=True, steps=None, warmup=None):
+    steps = steps or args.steps
+    warmup = warmup or args.warmup
+    with_pm = name == "C4"
+    sim, p0, springs, setup = build_body(A, cfg, cfg["omega"], with_point_mass=with_pm)
+    n, ns = len(p0), len(springs)
+    n_perts = 1 if with_pm else 0
+    bounds = A.slab_bounds(n, world)
+    lo, hi = bounds[rank], bounds[rank + 1]
+    sim.shard_setup(rank, world, bounds)
+    A.launcher.exchange_windows(dist, sim, rank, world)
+    clocks = ClockSampler(local).start()
+    sim.shard_step(warmup, pre_drift_last=True)
+    sim.sync()
+    fp64_peak, _ = A.probe_fp64_peak(1 << 13)
+    # device-timed laps, one per step, queued back to back: the host never waits inside the loop
+    dist.barrier()
+    launches0 = A.launch_count()
+    sim.timing(True); sim.timing_reset()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        sim.l2_flush()
+        sim.lap_begin()
+        sim.shard_step(1, pre_drift_last=True)
+        sim.lap_end()
+    t_queue = time.perf_counter() - t0          # how long the host needed to queue the whole loop
+    dev_ms, laps = sim.lap_collect()
+    t_wall = time.perf_counter() - t0
+    kt = sim.timing_get()
+    sim.timing(False)
+    launches = A.launch_count() - launches0
+    dist.barrier()
+    clk = clocks.stop()
+    per_rank_ms = all_ranks(dist, dev_ms / steps)
+    dev_ms_max = max_over_ranks(dist, dev_ms, local)
+    g_ms = max_over_ranks(dist, kt["gravity"][0], local)
+    s_ms = max_over_ranks(dist, kt["springs"][0], local)
+    value = n * steps / (dev_ms_max * 1e-3)
+
+    # ---- end to end: every rank refreshes its own slab from pinned host rows, steps, reads its slab's x, v, a back ----
+    e2e = None
+    if want_e2e and not args.no_e2e:
+        sim.upload(p0)                      # leave the pre-drifted state of the timed loop
+        sim.set_params(t=0.0)
+        pinned = A.PinnedRows(n, 16)
+        host = pinned.a
+        host[:] = 0.0
+        host[:, :11] = p0[:, :11]
+        k = min(steps, 20)
+        for _ in range(2):
+            sim.upload_range(host, lo, hi); sim.shard_step(1); sim.download_range(host, lo, hi, A.F_POS | A.F_VEL | A.F_ACC)
+        dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(k):
+            sim.upload_range(host, lo, hi)
+            sim.shard_step(1)
+            sim.download_range(host, lo, hi, A.F_POS | A.F_VEL | A.F_ACC)
+        t_mine = time.perf_counter() - t0
+        dist.barrier()
+        t_e2e = max_over_ranks(dist, t_mine, local)
+        e2e = {"value": n * k / t_e2e, "unit": "node-steps/s", "h2d_bytes_per_step": int(n * 128), "d2h_bytes_per_step": int(n * 72),
+               "host_memory": "pinned (ass_host_alloc); bytes are the sum over ranks: every rank moves its own slab", "steps": k}
+        del host
+        pinned.close()
+
+    parity = parity_of_sim(A, dist, sim, p0, springs, cfg, n_perts, rank, world, bounds)
+    dist.barrier()
+    sim.close()
+    if rank != 0:
+        return None
+    pairs = float(n) * float(n) / world
+    ach = 20.0 * pairs * steps / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0
+    own = bounds[1] - bounds[0]
+    return {
+        "metric": "node-steps/s", "value": value, "unit": "node-steps/s", "n_gpus": world, "steps": steps, "warmup": warmup,
+        "ms_per_step": dev_ms_max / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": config_of(name, cfg, n, ns, world, "slabs"),
+        "sharding": {"bounds": [int(b) for b in bounds],
+                     "exchange": "per step and rank: copy-engine pulls of the other slabs' x and v (%.2f MB, overlapped with the own-slab gravity triangle) and of the partial accelerations %d peers computed for this slab (%.2f MB) over CUDA-IPC peer mappings" % (
+                         64e-6 * (n - own), (world - 1) // 2 + (1 if world % 2 == 0 else 0), 32e-6 * own * ((world - 1) // 2 + (1 if world % 2 == 0 else 0))),
+                     "synchronisation": "device-side epoch flags in the peer-mapped windows (st.release.sys / ld.acquire.sys); no host barrier or stream synchronisation inside the step loop",
+                     "gravity": "divided by pairs of slabs: every unordered particle pair evaluated once, the same work on every rank",
+                     "per_rank_ms_per_step": per_rank_ms, "host_queue_ms_per_step": 1e3 * t_queue / steps},
+        "clocks": clk, "gpu_launches": int(launches), "e2e": e2e, "parity": parity,
+        "roofline": {"kernel": "k_gravity_sym (triangle + rectangles + reductions)", "bound": "fp64", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s",
+                     "frac": ach / fp64_peak if fp64_peak else None, "traffic": None,
+                     "note": "per GPU: 20 flop x N x N/%d ordered pairs per step (SURVEY 8d convention) over the gravity kernels' device time (max over ranks)" % world,
+                     "gravity_ms_per_step": g_ms / steps, "springs_ms_per_step": s_ms / steps},
+        "cpu_baseline": None,
+        "kernel_ms": {k: {"ms": v[0], "launches": v[1]} for k, v in kt.items()},
+        "wall_ms_per_step_incl_flush": 1e3 * t_wall / steps, "setup": setup, "fp64_peak_tflops_measured": fp64_peak,
+    }
+
+
+# ---------------------------------------------------------------------------------------------------
+# the ensemble
+# ---------------------------------------------------------------------------------------------------
+def run_c5(args, A, rank, world, local, dist, steps=None, warmup=None):
+    """BASELINE config 5: 4096 independent ~1k-node bodies (C1 generator), omega_z swept 0.1 -> 0.9, k in
+    {0.02, 0.04, 0.08, 0.16}, GRAVITY_NONE + zero_accel + springs; members dealt to the ranks by cost, no collective."""
+    steps = steps or args.steps
+    warmup = warmup or args.warmup
+    total = int(os.environ.get("ASS_C5_BODIES", "4096"))
+    distinct = int(os.environ.get("ASS_C5_DISTINCT_SEEDS", "64"))   # bodies are regenerated per seed; 64 shapes x sweeps
+    d = WORKLOADS["C1"]["d"]
+    t0 = time.perf_counter()
+    shapes = {}
+    for sd in range(min(distinct, total)):
+        A.srand(SEED + sd)
+        p = A.rand_ellipsoid(d, *ABC, 1.0)
+        with A.Sim() as s:
+            s.upload(p)
+            sp = s.connect_springs_dist(2.3 * d, 0, len(p), 1.0, GAMMA)
+            s.subtract_com(0, len(p)); s.subtract_cov(0, len(p))
+            s.download(p)
+        shapes[sd] = (p, sp)
+    # a member's cost is its spring count (the spring phase is the step): longest-processing-time-first dealing
+    costs = [len(shapes[b % distinct][1]) for b in range(total)]
+    mine = A.launcher.deal_members_by_cost(costs, world, rank)
+
+    def member(b):
+        p, sp = shapes[b % distinct]
+        wz = 0.1 + 0.8 * b / max(total - 1, 1)
+        k = (0.02, 0.04, 0.08, 0.16)[b % 4]
+        q = p.copy()
+        q[:, 3] = -wz * q[:, 1]; q[:, 4] = wz * q[:, 0]; q[:, 5] = 0.0      # spin_body about z for a centred body
+        s2 = sp.copy(); s2["k"] = k
+        return q, s2
+    bodies, springs, params = [], [], []
+    for b in mine:
+        q, s2 = member(b)
+        bodies.append(q); springs.append(s2)
+        params.append(dict(dt=WORKLOADS["C1"]["dt"], gravity=0, additional_forces=2, heartbeat=0))
+    setup_s = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    ens = A.Ensemble(bodies, springs, params)
+    create_s = time.perf_counter() - t0
+    nodes = ens.total_nodes
+    clocks = ClockSampler(local).start()
+    ens.step(warmup)
+    ens.sync()
+    barrier(dist)
+    launches0 = A.launch_count()
+    ms = ens.step(steps, timed=True)
+    barrier(dist)
+    clk = clocks.stop()
+    launches = A.launch_count() - launches0
+    ms_max = max_over_ranks(dist, ms, local)
+    per_rank_ms = all_ranks(dist, ms / steps)
+    per_rank_members = all_ranks(dist, len(mine))
+    total_nodes = sum_over_ranks(dist, float(nodes), local)
+    total_springs = sum_over_ranks(dist, float(ens.total_springs), local)
+    value = total_nodes * steps / (ms_max * 1e-3)
+    # e2e: state is resident by design (that is the point of the ensemble kernel); every step's result is read back
+    barrier(dist)
+    k_e2e = min(steps, 20)
+    t0 = time.perf_counter()
+    for _ in range(k_e2e):
+        ens.step(1)
+        ens.download(A.F_POS | A.F_VEL | A.F_ACC)
+    t_mine = time.perf_counter() - t0
+    barrier(dist)
+    t_e2e = max_over_ranks(dist, t_mine, local)
+    # parity: this rank's first member, re-run from its initial state -- bit for bit against the single-body path, and
+    # against the oracle within the usual bars
+    parity = None
+    if rank == 0:
+        parity = {"member": int(mine[0]), "steps": 3}
+        try:
+            q, s2 = member(mine[0])
+            with A.Ensemble([q], [s2], [params[0]]) as e1:
+                e1.step(3)
+                got = e1.download()[0]
+            with A.Sim() as s:
+                s.upload(q); s.set_springs(s2); s.set_params(dt=WORKLOADS["C1"]["dt"], gravity=0, additional_forces=2, heartbeat=0)
+                s.step(3)
+                one = s.download(q.copy())
+            parity["bitwise_equal_to_single_body_path"] = bool(np.array_equal(got[:, :10].view(np.uint64), one[:, :10].view(np.uint64)))
+            from oracle.bindings import Oracle, make_sim
+            ref = np.ascontiguousarray(q[:, :11]).copy()
+            Oracle().step(ref, s2, make_sim(dt=WORKLOADS["C1"]["dt"], gravity_basic=0, zero_first=1), 3)
+            parity["acc_vs_oracle"] = float(np.abs(got[:, 6:9] - ref[:, 6:9]).max() / np.abs(ref[:, 6:9]).max())
+            parity["xv_vs_oracle_max_abs"] = float(np.abs(got[:, :6] - ref[:, :6]).max())
+            parity["ok"] = bool(parity["bitwise_equal_to_single_body_path"] and parity["acc_vs_oracle"] <= 1e-11 and parity["xv_vs_oracle_max_abs"] <= POS_TOL)
+        except Exception as e:
+            parity["error"] = repr(e)
+            parity["ok"] = False
+    ens.close()
+    if rank != 0:
+        return None
+    peaks = read_json(os.path.join(ROOT, "MEASURED_PEAKS.json")) or {}
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    alg = (32.0 * total_springs + 80.0 * total_nodes) / world              # per GPU per step (SURVEY 8d)
+    ach = alg * steps / (ms_max * 1e-3) / 1e9
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        try:
+            cfg1 = dict(WORKLOADS["C1"])
+            v, sample, cores, _ = reference_arm_value(cfg1, np.ascontiguousarray(bodies[0][:, :11]), springs[0], budget_s=5.0, omp=False)
+            cpu = {"value": v, "unit": "node-steps/s", "cores": cores, "host_cores": os.cpu_count(), "kind": "reference",
+                   "sample": "one member of the ensemble (N=%d) stepped by the reference; the ensemble is that x %d" % (len(bodies[0]), total)}
+        except FileNotFoundError as e:
+            cpu = {"value": None, "unit": "node-steps/s", "cores": 0, "kind": "reference", "sample": "unavailable: %s" % e}
+    return {"metric": "node-steps/s", "value": value, "unit": "node-steps/s", "n_gpus": world, "steps": steps, "warmup": warmup,
+            "ms_per_step": ms_max / steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "C5: ensemble spin-rate/material sweep, %d independent ~1k-node bodies (C1 generator, %d distinct seeds), GRAVITY_NONE + zero_accel + springs" % (total, distinct),
+                       "bodies": total, "nodes_total": int(total_nodes), "springs_total": int(total_springs),
+                       "l2": "inputs larger than L2: %.0f MB of half-edge records per GPU streamed every step" % (64.0 * total_springs / world / 1e6),
+                       "parallelism": "ensemble members dealt to %d GPU(s) by cost (longest-processing-time first), no collective" % world},
+            "dealing": {"members_per_gpu": per_rank_members, "per_gpu_ms_per_step": per_rank_ms},
+            "clocks": clk,
+            "e2e": {"value": total_nodes * k_e2e / t_e2e, "unit": "node-steps/s", "h2d_bytes_per_step": 0,
+                    "d2h_bytes_per_step": int(total_nodes * 80), "note": "state resident (the point of the ensemble kernel); every step's x, v, a read back", "steps": k_e2e},
+            "gpu_launches": int(launches), "parity": parity,
+            "roofline": {"kernel": "k_ensemble (spring phase)", "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+                         "traffic": None, "algorithmic_bytes_per_step_per_gpu": alg},
+            "cpu_baseline": cpu, "setup": {"build_bodies_s": setup_s, "ensemble_create_s": create_s}}
+
+
+# ---------------------------------------------------------------------------------------------------
+# the reference arm
+# ---------------------------------------------------------------------------------------------------
 def reference_arm_value(cfg, p, springs, budget_s, omp):
     """Time the UNMODIFIED reference's reb_step on this host.  Gravity is O(N^2): to stay inside the budget it is
     timed with N_active = N/f sources (the reference's own loop bound, gravity.c:64,89) and scaled by f; springs and
@@ -211,20 +652,28 @@ def reference_arm_value(cfg, p, springs, budget_s, omp):
 
 
 def run_reference(args, rank, world):
-    """--impl reference: the reference's own CPU path, all host threads it can correctly use. Rank 0 only."""
+    """--impl reference: the reference's own CPU path, all host threads it can correctly use. Rank 0 only.  The body is
+    the one the b200 arm steps (at every N: the b200 arm is strong-scaled), built by the CPU oracle's generator and
+    connector -- nothing of libass_b200.so is loaded in this arm."""
     if rank != 0:
         return
     # torchrun pins OMP_NUM_THREADS=1 for its children; the reference arm is meant to use every host thread it can
     os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
-    import asteroid_spring_sims_b200 as A  # host-side generator only (no GPU needed): builds the same body
     name = args.workload or "C3"
+    if name == "C5":
+        name = "C1"
     cfg = WORKLOADS[name]
-    A.srand(SEED)
-    p = A.rand_ellipsoid(cfg["d"], *ABC, 1.0)
     from oracle.bindings import Oracle
     orc = Oracle()
-    springs = orc.connect_springs_dist(p, 2.3 * cfg["d"], 0, len(p), K_SPRING, GAMMA)
-    orc.subtract_com(p, 0, len(p)); orc.subtract_cov(p, 0, len(p)); orc.spin_body(p, 0, len(p), cfg["omega"])
+    orc.srand(SEED)
+    p = orc.rand_ellipsoid(cfg["d"], *ABC, 1.0)
+    n_body = len(p)
+    springs = orc.connect_springs_dist(p, 2.3 * cfg["d"], 0, n_body, K_SPRING, GAMMA)
+    orc.subtract_com(p, 0, n_body); orc.subtract_cov(p, 0, n_body); orc.spin_body(p, 0, n_body, cfg["omega"])
+    if name == "C4":
+        pm = np.zeros((1, p.shape[1]))
+        pm[0, 0] = 7.0; pm[0, 4] = np.sqrt(2.0 / 7.0); pm[0, 9] = 1.0
+        p = np.ascontiguousarray(np.vstack([p, pm]))
     total = args.steps + args.warmup
     budget = max(2.0, min(20.0, 150.0 / max(total, 1)))
     vals = []
@@ -236,167 +685,13 @@ def run_reference(args, rank, world):
     value = len(p) * len(vals) / sum(len(p) / v for v in vals)
     out = {"impl": "reference", "metric": "node-steps/s", "value": value, "unit": "node-steps/s", "n_gpus": args.gpus,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * len(p) / value, "higher_is_better": True,
-           "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "config": {"workload": "%s: %s" % (name, cfg["desc"]), "N": len(p), "NS": len(springs)},
-           "cpu_baseline": {"value": value, "unit": "node-steps/s", "cores": cores, "kind": "reference", "sample": sample},
+           "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": config_of(name, cfg, len(p), len(springs), max(args.gpus, 1), "slabs" if args.gpus > 1 else "single"),
+           "cpu_baseline": {"value": value, "unit": "node-steps/s", "cores": cores, "kind": "reference",
+                            "sample": sample + "; built -O3 -march=x86-64-v3 (no AVX-512: the path is scalar sqrt/div)"},
            "e2e": {"value": value, "unit": "node-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "detail": detail}
     emit(out)
-
-
-def finish_line(out, dist):
-    emit(out)
-    if dist is not None:
-        dist.destroy_process_group()
-
-
-def run_c5(args, A, rank, world, local, dist):
-    """BASELINE config 5: 4096 independent ~1k-node bodies (C1 generator), omega_z swept 0.1 -> 0.9, k in
-    {0.02, 0.04, 0.08, 0.16}, GRAVITY_NONE + zero_accel + springs; members dealt round-robin to the ranks, no collective."""
-    total = int(os.environ.get("ASS_C5_BODIES", "4096"))
-    distinct = int(os.environ.get("ASS_C5_DISTINCT_SEEDS", "64"))   # bodies are regenerated per seed; 64 shapes x sweeps
-    d = WORKLOADS["C1"]["d"]
-    mine = A.launcher.deal_members(total, world, rank)
-    t0 = time.perf_counter()
-    shapes = {}
-    for sd in sorted({b % distinct for b in mine}):
-        A.srand(SEED + sd)
-        p = A.rand_ellipsoid(d, *ABC, 1.0)
-        with A.Sim() as s:
-            s.upload(p)
-            sp = s.connect_springs_dist(2.3 * d, 0, len(p), 1.0, GAMMA)
-            s.subtract_com(0, len(p)); s.subtract_cov(0, len(p))
-            s.download(p)
-        shapes[sd] = (p, sp)
-    bodies, springs, params = [], [], []
-    for b in mine:
-        p, sp = shapes[b % distinct]
-        wz = 0.1 + 0.8 * b / max(total - 1, 1)
-        k = (0.02, 0.04, 0.08, 0.16)[b % 4]
-        q = p.copy()
-        q[:, 3] = -wz * q[:, 1]; q[:, 4] = wz * q[:, 0]; q[:, 5] = 0.0      # spin_body about z for a centred body
-        s2 = sp.copy(); s2["k"] = k
-        bodies.append(q); springs.append(s2)
-        params.append(dict(dt=WORKLOADS["C1"]["dt"], gravity=0, additional_forces=2, heartbeat=0))
-    setup_s = time.perf_counter() - t0
-    ens = A.Ensemble(bodies, springs, params)
-    nodes = ens.total_nodes
-    ens.step(args.warmup)
-    ens.sync()
-    clocks = ClockSampler(local)
-    barrier(dist)
-    launches0 = A.launch_count()
-    clocks.start()
-    ms = ens.step(args.steps, timed=True)
-    barrier(dist)
-    clk = clocks.stop()
-    launches = A.launch_count() - launches0
-    ms_max = max_over_ranks(dist, ms, local)
-    total_nodes = sum_over_ranks(dist, float(nodes), local)
-    total_springs = sum_over_ranks(dist, float(ens.total_springs), local)
-    value = total_nodes * args.steps / (ms_max * 1e-3)
-    # e2e: state is resident by design (that is the point of the ensemble kernel); every step's result is read back
-    barrier(dist)
-    t0 = time.perf_counter()
-    for _ in range(min(args.steps, 20)):
-        ens.step(1)
-        ens.download(A.F_POS | A.F_VEL | A.F_ACC)
-    barrier(dist)
-    t_e2e = max_over_ranks(dist, time.perf_counter() - t0, local)
-    if rank != 0:
-        return
-    peaks = read_json(os.path.join(ROOT, "MEASURED_PEAKS.json")) or {}
-    hbm_peak = peaks.get("hbm_gbs", 6650.0)
-    alg = (32.0 * total_springs + 80.0 * total_nodes) / world              # per GPU per step (SURVEY 8d)
-    ach = alg * args.steps / (ms_max * 1e-3) / 1e9
-    cpu = None
-    if not args.no_cpu_baseline:
-        try:
-            cfg1 = dict(WORKLOADS["C1"])
-            v, sample, cores, _ = reference_arm_value(cfg1, np.ascontiguousarray(bodies[0]), springs[0], budget_s=5.0, omp=False)
-            cpu = {"value": v, "unit": "node-steps/s", "cores": cores, "host_cores": os.cpu_count(), "kind": "reference",
-                   "sample": "one member of the ensemble (N=%d) stepped by the reference; the ensemble is that x %d" % (len(bodies[0]), total)}
-        except FileNotFoundError as e:
-            cpu = {"value": None, "unit": "node-steps/s", "cores": 0, "kind": "reference", "sample": "unavailable: %s" % e}
-    out = {"metric": "node-steps/s", "value": value, "unit": "node-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-           "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "strong",
-           "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "config": {"workload": "C5: ensemble spin-rate/material sweep, %d independent ~1k-node bodies (C1 generator, %d distinct seeds), GRAVITY_NONE + zero_accel + springs" % (total, distinct),
-                      "bodies": total, "bodies_per_gpu": len(mine), "nodes_total": int(total_nodes), "springs_total": int(total_springs),
-                      "l2": "inputs larger than L2: %.0f MB of half-edge records per GPU streamed every step" % (64.0 * total_springs / world / 1e6),
-                      "parallelism": "ensemble x%d, no collective" % world},
-           "clocks": clk,
-           "e2e": {"value": total_nodes * min(args.steps, 20) / t_e2e, "unit": "node-steps/s", "h2d_bytes_per_step": 0,
-                   "d2h_bytes_per_step": int(nodes * 80), "note": "state resident (the point of the ensemble kernel); every step's x, v, a read back"},
-           "gpu_launches": int(launches),
-           "roofline": {"kernel": "k_ensemble (spring phase)", "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-                        "traffic": None, "algorithmic_bytes_per_step_per_gpu": alg},
-           "cpu_baseline": cpu, "setup": {"build_bodies_s": setup_s}}
-    finish_line(out, dist)
-
-
-def run_c4_sharded(args, A, rank, world, local, dist):
-    """BASELINE config 4: one N ~ 1e6 body (+ a Mars-like point mass) split into particle slabs over the ranks; the only
-    exchange is the per-step pull of the other slabs' x and v through CUDA-IPC peer mappings (strong scaling)."""
-    cfg = dict(WORKLOADS["C4"])
-    if os.environ.get("ASS_C4_D"):
-        cfg["d"] = float(os.environ["ASS_C4_D"])
-    sim, p, springs, setup = build_body(A, cfg, cfg["omega"], with_point_mass=True)
-    n, ns = len(p), len(springs)
-    bounds = A.slab_bounds(n, world)
-    sim.shard_setup(rank, world, bounds)
-    A.launcher.exchange_windows(dist, sim, rank, world)
-
-    def run(nsteps):
-        A.launcher.sharded_steps(dist, sim, nsteps)
-
-    run(args.warmup)
-    fp64_peak, _ = A.probe_fp64_peak(1 << 13)
-    sim.timing(True); sim.timing_reset()
-    clocks = ClockSampler(local)
-    dist.barrier()
-    launches0 = A.launch_count()
-    clocks.start()
-    sim.sync()
-    t0 = time.perf_counter()
-    run(args.steps)
-    sim.sync()
-    dist.barrier()
-    t_wall = max_over_ranks(dist, time.perf_counter() - t0, local)
-    clk = clocks.stop()
-    launches = A.launch_count() - launches0
-    kt = sim.timing_get()
-    sim.timing(False)
-    g_ms = max_over_ranks(dist, kt["gravity"][0], local)
-    value = n * args.steps / t_wall
-    # e2e: the sharded body's natural host interaction is a gather + download at print cadence; per step that is
-    # x, v of the own slab (the module's heartbeat) -- measured as one full download every step
-    host = np.zeros((n, 16))
-    dist.barrier()
-    t0 = time.perf_counter()
-    for s in range(min(args.steps, 3)):
-        A.launcher.sharded_steps(dist, sim, 1, pre_drift=False)
-        sim.download(host, A.F_POS | A.F_VEL | A.F_ACC)
-    dist.barrier()
-    t_e2e = max_over_ranks(dist, time.perf_counter() - t0, local)
-    if rank != 0:
-        return
-    pairs = float(n) * float(n) / world
-    ach = 20.0 * pairs * args.steps / (g_ms * 1e-3) / 1e12
-    out = {"metric": "node-steps/s", "value": value, "unit": "node-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-           "ms_per_step": 1e3 * t_wall / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "config": {"workload": "C4: %s, slabs over %d GPUs" % (cfg["desc"], world), "N": n, "NS": ns, "bounds": bounds,
-                      "exchange": "per step: pull of the other slabs' x and v (%.1f MB, overlapped with the own-slab gravity triangle) and of the partial accelerations the peers computed for this slab (%.1f MB) over CUDA-IPC peer mappings, copy engines; 3 host barriers" % (
-                          64e-6 * (n - (bounds[1] - bounds[0])), 32e-6 * (bounds[1] - bounds[0]) * (world // 2)),
-                      "gravity": "divided by pairs of slabs: every unordered particle pair evaluated once, the same work on every rank",
-                      "l2": "inputs larger than L2 (half-edges %.0f MB)" % (64e-6 * ns), "parallelism": "particle slabs x%d" % world},
-           "clocks": clk, "gpu_launches": int(launches),
-           "e2e": {"value": n * min(args.steps, 3) / t_e2e, "unit": "node-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": int(n * 80)},
-           "roofline": {"kernel": "k_gravity", "bound": "fp64", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach / fp64_peak, "traffic": None,
-                        "note": "per GPU: 20 flop x N x N/%d ordered pairs per step (SURVEY 8d convention; the pair-once kernels execute 9.5 FP64 instructions per ordered pair) over the gravity kernels' device time (max over ranks)" % world},
-           "cpu_baseline": None,
-           "kernel_ms": {k: {"ms": v[0], "launches": v[1]} for k, v in kt.items()}, "setup": setup}
-    finish_line(out, dist)
 
 
 _REAL_STDOUT = None
@@ -421,6 +716,18 @@ def emit(obj):
         os.write(_REAL_STDOUT, line)
 
 
+def sub_record(fn, rank, dist, label):
+    """A sub-record must never take the main record down with it: failures are reported inside the sub-record.
+    Every rank takes part (the calls are collective); rank 0 returns the record."""
+    try:
+        rec = fn()
+    except Exception as e:
+        traceback.print_exc()
+        rec = {"error": "%s failed on rank %d: %r" % (label, rank, e)}
+        # the other ranks may be inside a collective: nothing sensible can be salvaged from this sub-record
+    return rec
+
+
 def main():
     quiet_stdout()
     ap = argparse.ArgumentParser()
@@ -431,6 +738,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-sub", action="store_true", help="main record only (skip the c4_sharded / c5_ensemble sub-records)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -444,120 +752,29 @@ def main():
     import asteroid_spring_sims_b200 as A
     A.init(local)
     name = args.workload or "C3"
+
+    def body_record(nm, **kw):
+        cfg = dict(WORKLOADS[nm])
+        if nm == "C4" and os.environ.get("ASS_C4_D"):
+            cfg["d"] = float(os.environ["ASS_C4_D"])      # a smaller body of the same kind, for quick checks
+        if world > 1:
+            return run_sharded(args, A, nm, cfg, rank, world, local, dist, **kw)
+        return run_single(args, A, nm, cfg, local, **kw)
+
     if name == "C5":
-        return run_c5(args, A, rank, world, local, dist)
-    if name == "C4" and world > 1:
-        return run_c4_sharded(args, A, rank, world, local, dist)
-    cfg = dict(WORKLOADS[name])
-    if name == "C4" and os.environ.get("ASS_C4_D"):
-        cfg["d"] = float(os.environ["ASS_C4_D"])      # a smaller body of the same kind, for quick checks
-    # ensemble member `rank`: spin rate swept across members (BASELINE config 5's sweep, applied to bodies of this size)
-    omega = tuple(np.array(cfg["omega"]) * (1.0 + 0.1 * rank))
-    sim, p, springs, setup = build_body(A, cfg, omega, with_point_mass=(name == "C4"))
-    n, ns = len(p), len(springs)
-
-    # ---- device-resident throughput ----
-    sim.step(args.warmup)
-    sim.sync()
-    fp64_peak, _ = A.probe_fp64_peak(1 << 13)
-    sim.timing(True)
-    sim.timing_reset()
-    clocks = ClockSampler(local)
-    barrier(dist)
-    launches0 = A.launch_count()
-    clocks.start()
-    sim.sync()
-    t_wall0 = time.perf_counter()
-    dev_ms = 0.0
-    for _ in range(args.steps):
-        sim.l2_flush()
-        sim.mark_begin()
-        sim.step(1)
-        dev_ms += sim.mark_end()
-    sim.sync()
-    barrier(dist)
-    t_wall = time.perf_counter() - t_wall0
-    clk = clocks.stop()
-    launches = A.launch_count() - launches0
-    kt = sim.timing_get()
-    sim.timing(False)
-    dev_ms_max = max_over_ranks(dist, dev_ms, local)
-    total_nodes = sum_over_ranks(dist, float(n), local)
-    value = total_nodes * args.steps / (dev_ms_max * 1e-3)
-
-    # ---- end to end through host buffers (the drop-in's always-coherent reb_step) ----
-    e2e = None
-    if not args.no_e2e:
-        # 128-byte rows == sizeof(struct reb_particle), in page-locked host memory (ass_host_alloc): what the drop-in's
-        # reb_integrate gives the module's own r->particles by pinning it in place (ass_host_register)
-        pinned = A.PinnedRows(n, 16)
-        host = pinned.a
-        host[:] = 0.0
-        sim.download(host)
-        for _ in range(2):
-            sim.upload(host); sim.step(1); sim.download(host, A.F_POS | A.F_VEL | A.F_ACC)
-        barrier(dist)
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            sim.upload(host)
-            sim.step(1)
-            sim.download(host, A.F_POS | A.F_VEL | A.F_ACC)
-        barrier(dist)
-        t_e2e = max_over_ranks(dist, time.perf_counter() - t0, local)
-        e2e = {"value": total_nodes * args.steps / t_e2e, "unit": "node-steps/s",
-               "h2d_bytes_per_step": int(n * 128), "d2h_bytes_per_step": int(n * 72), "host_memory": "pinned (ass_host_alloc)"}
-        del host
-        pinned.close()
-
-    if rank != 0:
-        return
-
-    # ---- roofline of the dominant kernel ----
-    peaks = read_json(os.path.join(ROOT, "MEASURED_PEAKS.json")) or {}
-    hbm_peak = peaks.get("hbm_gbs", 6650.0)
-    hbm_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
-    traffic = (read_json(os.path.join(ROOT, "profiles", "traffic.json")) or {}).get(name, {})
-    g_ms, g_n = kt["gravity"]
-    s_ms, s_n = kt["springs"]
-    roof_g = roof_s = None
-    if g_n:
-        n_src = n
-        # one gravity evaluation per step = the pair kernel + its fixed-order row reduction (both inside the timer)
-        ach = 20.0 * n * n_src * args.steps / (g_ms * 1e-3) / 1e12    # 20 flop per ordered pair
-        roof_g = {"kernel": "k_gravity (+k_gravity_reduce)", "bound": "fp64", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach / fp64_peak,
-                  "traffic": traffic.get("gravity"), "peak_source": "DFMA microbenchmark measured in this run (ass_probe_fp64_peak); MEASURED_PEAKS.json has no FP64 figure",
-                  "pairs_per_s": n * n_src * args.steps / (g_ms * 1e-3), "ms_per_evaluation": g_ms / args.steps}
-    if s_n:
-        alg = 32.0 * ns + 80.0 * n
-        ach = alg * s_n / (s_ms * 1e-3) / 1e9
-        roof_s = {"kernel": "k_spring_tiles<KICK> (springs + kick + drift)", "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-                  "traffic": traffic.get("springs"), "peak_source": hbm_src, "algorithmic_bytes_per_launch": alg, "ms_per_launch": s_ms / s_n}
-    dominant = roof_g if (roof_g and g_ms >= s_ms) else roof_s
-
-    # ---- CPU baseline: the unmodified reference on this host, bounded sample ----
-    cpu = None
-    if not args.no_cpu_baseline:
-        try:
-            v, sample, cores, detail = reference_arm_value(cfg, np.ascontiguousarray(p), springs, budget_s=12.0, omp=False)
-            cpu = {"value": v, "unit": "node-steps/s", "cores": cores, "host_cores": os.cpu_count(), "kind": "reference", "sample": sample}
-        except FileNotFoundError as e:
-            cpu = {"value": None, "unit": "node-steps/s", "cores": 0, "kind": "reference", "sample": "unavailable: %s" % e}
-
-    out = {
-        "metric": "node-steps/s", "value": value, "unit": "node-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "%s: %s%s" % (name, cfg["desc"], "" if world == 1 else " x %d independent ensemble members, one per GPU (swept spin rate)" % world),
-                   "N_per_gpu": n, "NS_per_gpu": ns, "seed": SEED, "generator": "rand_ellipsoid(d=%g, 1, 0.7, 0.5)" % cfg["d"],
-                   "max_spring_dist": 2.3 * cfg["d"], "k": K_SPRING, "gamma": GAMMA, "dt": cfg["dt"], "softening": cfg["d"] / 100.0,
-                   "l2": "flushed between steps (256 MiB fill, outside the device-timed bracket)", "parallelism": "ensemble x%d" % world},
-        "clocks": clk, "e2e": e2e, "gpu_launches": int(launches),
-        "roofline": dominant, "roofline_gravity": roof_g, "roofline_springs": roof_s, "cpu_baseline": cpu,
-        "kernel_ms": {k: {"ms": v[0], "launches": v[1]} for k, v in kt.items()},
-        "wall_ms_per_step_incl_flush": 1e3 * t_wall / args.steps, "setup": setup, "fp64_peak_tflops_measured": fp64_peak,
-    }
-    emit(out)
+        out = run_c5(args, A, rank, world, local, dist)
+    else:
+        out = body_record(name)
+        if args.workload is None and not args.no_sub:
+            c4 = sub_record(lambda: body_record("C4", want_e2e=False, **({} if world > 1 else {"want_cpu": False})), rank, dist, "c4_sharded")
+            c5 = sub_record(lambda: run_c5(args, A, rank, world, local, dist), rank, dist, "c5_ensemble")
+            if rank == 0:
+                out["c4_sharded"] = c4
+                out["c5_ensemble"] = c5
+    if rank == 0:
+        emit(out)
     if dist is not None:
+        dist.barrier()
         dist.destroy_process_group()
 
 

@@ -205,22 +205,29 @@ int ass_ensemble_destroy(ass_ensemble* e);
  *      BASELINE C4).  Every rank uploads the whole body and the whole spring list, then calls ass_shard_setup.  Rank g
  *      integrates, and sums the springs onto, particles [bounds[g], bounds[g+1]) only.  Gravity is divided by pairs of
  *      slabs so that every unordered particle pair is evaluated once and every rank does the same work; a rank leaves
- *      the partial accelerations it computed for other slabs in an exported buffer.  All transfers are pulls through
+ *      the partial accelerations it computed for other slabs in its exported window.  All transfers are pulls through
  *      peer-mapped memory (CUDA IPC over NVLink) by the copy engines: the peers' x and v while the SMs already work on
  *      the own slab (the analogue of one all-gather), the partials before the springs (one reduce-scatter).
- *      The launcher owns three barriers per step (torch.distributed; asteroid-spring-sims_b200/launcher.py):
- *          ass_shard_begin -> barrier -> ass_shard_exchange -> barrier -> ass_shard_gravity -> barrier -> ass_shard_finish ---- */
+ *      The host is not in the step: ass_shard_step queues whole steps and returns; the ranks meet on the device through
+ *      64-bit epoch flags that producers store into their peers' windows and consumers poll locally (csrc/shard.cu).
+ *      The launcher (asteroid-spring-sims_b200/launcher.py) only swaps the window handles once. ---- */
 #define ASS_IPC_HANDLE_BYTES 64
-int ass_shard_setup(ass_sim* sim, int rank, int nranks, const int* bounds /* nranks + 1 */);
+int ass_shard_setup(ass_sim* sim, int rank, int nranks /* <= 16 */, const int* bounds /* nranks + 1 */);
 int ass_shard_export(ass_sim* sim, unsigned char handle[ASS_IPC_HANDLE_BYTES]);
 int ass_shard_import(ass_sim* sim, int peer_rank, const unsigned char handle[ASS_IPC_HANDLE_BYTES]);
 /* same-process peers (several ass_sim in one process): share the pointer instead of an IPC handle */
 int ass_shard_import_local(ass_sim* sim, int peer_rank, ass_sim* peer);
-int ass_shard_begin(ass_sim* sim);                        /* part1 on the own slab (if not pre-drifted); synchronises */
-int ass_shard_exchange(ass_sim* sim);                     /* pulls + gravity within the own slab; returns when pulls landed */
-int ass_shard_gravity(ass_sim* sim);                      /* gravity between slabs; synchronises (partials complete) */
-int ass_shard_finish(ass_sim* sim, int pre_drift_next);   /* add the peers' partials, springs, part2 on the own slab */
-int ass_shard_gather(ass_sim* sim);                       /* bring every slab's x, v home (before a full download) */
+/* reb_step (src/rebound.c:69-144) x nsteps for the own slab, with the built-in additional_forces of
+ * params.additional_forces.  Collective: every rank calls it with the same arguments.  Queued, not awaited: ass_sync,
+ * a download or ass_get_params after ass_sync see the result.  pre_drift_last != 0 leaves the positions with the next
+ * step's first half-drift (src/integrator_leapfrog.c:45-47) already applied: only more stepping may follow.
+ * A peer that does not arrive within 30 s makes the next ass_sync / download fail with ASS_ECOMM instead of hanging. */
+int ass_shard_step(ass_sim* sim, int nsteps, int pre_drift_last);
+/* bring every slab's x, v home (before a full download).  Collective, queued; the next ass_shard_step waits on the
+ * device until every peer has taken its copy. */
+int ass_shard_gather(ass_sim* sim);
+/* ass_upload_particles for rows [i_low, i_high) only: `base` is row 0 of the caller's array */
+int ass_upload_range(ass_sim* sim, const void* base, size_t stride_bytes, int i_low, int i_high, unsigned fields);
 
 /* ---- measurement ---- */
 /* Kernel classes for the per-kernel CUDA-event timers */
@@ -232,6 +239,11 @@ int ass_timing_get(ass_sim* sim, double ms[ASS_K_COUNT], long long launches[ASS_
 /* stream-ordered stopwatch on the simulation's stream: returns device ms between the two marks (synchronises) */
 int ass_mark_begin(ass_sim* sim);
 int ass_mark_end(ass_sim* sim, double* ms);
+/* lap timer on the simulation's stream: begin / end only record events (nothing waits), collect synchronises and
+ * returns the sum of all laps since the last collect.  For loops that must stay queued (sharded steps). */
+int ass_lap_begin(ass_sim* sim);
+int ass_lap_end(ass_sim* sim);
+int ass_lap_collect(ass_sim* sim, double* total_ms, int* laps);
 int ass_l2_flush(ass_sim* sim);                    /* overwrite a buffer larger than L2 */
 /* DFMA-only microbenchmark: the FP64 roofline denominator (MEASURED_PEAKS.json has none). iters ~ 1<<14. */
 int ass_probe_fp64_peak(int iters, double* tflops, double* ms);

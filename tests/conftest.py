@@ -8,6 +8,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 GOLDEN = os.path.join(ROOT, "tests", "golden")
+# The in-process sharding tests drive up to 8 "ranks" x 2 streams on one GPU, and a rank's stream may sit in a kernel that
+# waits for another rank's flag: with the default 8 hardware queues two such streams could share one and block each other.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+# ... and all of them are queued by ONE host thread: a lazily loaded kernel's first launch synchronises the context, which
+# would wait for a flag wait whose producer this thread has not queued yet (ass_shard_import_local insists on this)
+os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
 
 
 def pytest_configure(config):

@@ -2,9 +2,11 @@
 
 Ensemble members must reproduce what the single-body path gives the same body (bit for bit without gravity: same
 arithmetic, same lane order), which the other tests already tie to the reference.  The sharded path is run as a
-two-rank protocol inside one process (two ass_sim objects exchanging through same-process peer pointers): no kernel
-waits on another, the "barriers" are just the order of the host calls.  The real multi-process IPC path is exercised
-by tests/test_gpu_multi.py::test_ipc_two_ranks when two GPUs are visible and by bench.py --workload C4 under torchrun.
+P-rank protocol inside one process (P ass_sim objects exchanging through same-process peer pointers, all on one GPU):
+every rank's steps are queued up front by the one host thread and the ranks then meet through the same device-side
+epoch flags as real ranks do -- the host cannot order anything, so a missing wait shows up as a wrong result.  The
+multi-process CUDA-IPC path is exercised by test_ipc_two_ranks when two GPUs are visible and by bench.py --gpus N under
+torchrun (which checks parity inside the run).
 """
 import os
 import subprocess
@@ -105,7 +107,7 @@ def test_ensemble_errors(gpu):
     assert "shared memory" in str(e.value)
 
 
-@pytest.mark.parametrize("nranks", [1, 2, 3, 4, 5])
+@pytest.mark.parametrize("nranks", [1, 2, 3, 4, 5, 8])
 def test_sharded_body_in_process(gpu, oracle, body010, nranks):
     """C4's protocol at small size: every 'rank' is an ass_sim of this process; result = the unsharded path's."""
     g = body010
@@ -128,12 +130,11 @@ def test_sharded_body_in_process(gpu, oracle, body010, nranks):
             if q != r:
                 sims[r].shard_import_local(q, sims[q])
     nsteps = 4
-    for step in range(nsteps):
-        for s in sims: s.shard_begin()
-        for s in sims: s.shard_exchange()
-        for s in sims: s.shard_gravity()
-        for s in sims: s.shard_finish(pre_drift_next=(step < nsteps - 1))
+    # two batches, the first one ending pre-drifted: everything is queued before any rank has run a single kernel
+    for s in sims: s.shard_step(3, pre_drift_last=True)
+    for s in sims: s.shard_step(nsteps - 3)
     for s in sims: s.shard_gather()
+    for s in sims: s.sync()
     # reference: the oracle, and the unsharded GPU path
     ref = p.copy()
     sim = make_sim(dt=2e-3, softening=d / 100.0, gravity_basic=1, zero_first=0, n_perts=1)
@@ -173,9 +174,13 @@ handles = [None] * world
 dist.all_gather_object(handles, s.shard_export())
 for q in range(world):
     if q != rank: s.shard_import(q, handles[q])
-for step in range(4):
-    s.shard_begin(); dist.barrier(); s.shard_exchange(); dist.barrier(); s.shard_gravity(); dist.barrier(); s.shard_finish(step < 3)
-dist.barrier(); s.shard_gather(); dist.barrier()
+if rank == 1:
+    for _ in range(40): s.l2_flush()      # one rank starts late: the others must wait on the device, not run ahead
+s.shard_step(2, pre_drift_last=True)
+if rank == 0:
+    for _ in range(40): s.l2_flush()      # ... and the other one falls behind between batches
+s.shard_step(2)
+s.shard_gather(); s.sync()
 out = s.download(p.copy())
 u = A.Sim(); u.upload(p); u.set_springs(sp); u.set_params(**prm); u.step(4); want = u.download(p.copy())
 lo, hi = bounds[rank], bounds[rank + 1]
@@ -187,7 +192,8 @@ dist.barrier(); s.close(); dist.destroy_process_group()
 
 
 def test_ipc_two_ranks(gpu, tmp_path):
-    """The real thing: two processes, two GPUs, CUDA IPC windows, torch.distributed barriers."""
+    """The real thing: two processes, two GPUs, CUDA IPC windows, device-side flags; the host never synchronises the ranks
+    inside the run (torch.distributed only swaps the window handles)."""
     if gpu.device_count() < 2:
         pytest.skip("needs two GPUs")
     script = tmp_path / "worker.py"
