@@ -280,11 +280,46 @@ class Sim:
         w = (C.c_double * 3)(*omega)
         _chk(lib().ass_spin_body(self._h, C.c_int(lo), C.c_int(hi), w))
 
+    def transform_body(self, lo, hi, R, about_com=True):
+        """x <- R (x - c) + c, v <- R (v - u) + u: rotate_body (about the range's CoM / CoV) or rotate_origin / rotate_to_principal."""
+        m = (C.c_double * 9)(*[float(v) for v in np.asarray(R, dtype=np.float64).reshape(9)])
+        _chk(lib().ass_transform_body(self._h, C.c_int(lo), C.c_int(hi), m, C.c_int(int(about_com))))
+
     def diagnostics(self, lo=0, hi=None, want_gpe=False):
         hi = self.n if hi is None else hi
         out = (C.c_double * 20)()
         _chk(lib().ass_diagnostics(self._h, C.c_int(lo), C.c_int(hi), C.c_int(int(want_gpe)), out))
         return np.array(out[:])
+
+    # -- stress (stress.cpp) and the masked force terms of the bennu2 / cube modules --
+    def stress(self):
+        """(N x 3 x 3 stress tensors, max_force, max_force_spring): the first half of update_stress."""
+        n = self.n
+        T = np.zeros((n, 9)); F = np.zeros(n); S = np.zeros(n, dtype=np.int32)
+        _chk(lib().ass_stress(self._h, T.ctypes.data_as(C.c_void_p), F.ctypes.data_as(C.c_void_p), S.ctypes.data_as(C.c_void_p)))
+        return T.reshape(n, 3, 3), F, S
+
+    def set_node_mask(self, mask_id, mask):
+        m = np.ascontiguousarray(mask, dtype=np.uint8)
+        assert len(m) == self.n
+        _chk(lib().ass_set_node_mask(self._h, C.c_int(mask_id), m.ctypes.data_as(C.c_void_p)))
+
+    def mask_from_plane(self, mask_id, lo, hi, axis, threshold, greater=True):
+        c = C.c_int()
+        _chk(lib().ass_mask_from_plane(self._h, C.c_int(mask_id), C.c_int(lo), C.c_int(hi), C.c_int(axis), C.c_double(threshold), C.c_int(int(greater)), C.byref(c)))
+        return c.value
+
+    def apply_radial_impulse(self, mask_id, lo, hi, lat, longi, dangle, force, envelope, want_count=True):
+        c = C.c_int()
+        _chk(lib().ass_apply_radial_impulse(self._h, C.c_int(mask_id), C.c_int(lo), C.c_int(hi), C.c_double(lat), C.c_double(longi), C.c_double(dangle),
+                                            C.c_double(force), C.c_double(envelope), C.byref(c) if want_count else None))
+        return c.value
+
+    def plane_push(self, mask_id, axis, per_node_force):
+        _chk(lib().ass_plane_push(self._h, C.c_int(mask_id), C.c_int(axis), C.c_double(per_node_force)))
+
+    def plane_constraint(self, mask_id, axis):
+        _chk(lib().ass_plane_constraint(self._h, C.c_int(mask_id), C.c_int(axis)))
 
     # -- phobos* terms (orb.cpp) --
     def quadrupole_accel(self, J2, R, phi, theta, i_p):
@@ -497,3 +532,36 @@ def hcp_ellipsoid(min_dist, a, b, c, total_mass, existing=None):
 
 def cubic_ellipsoid(min_dist, a, b, c, total_mass, existing=None):
     return _gen(lib().ass_cubic_ellipsoid, min_dist, a, b, c, total_mass, existing)
+
+
+def rand_rectangle(min_dist, x, y, z, total_mass, existing=None):
+    return _gen(lib().ass_rand_rectangle, min_dist, x, y, z, total_mass, existing)
+
+
+def _gen2(fn, args, existing):
+    libc = C.CDLL(None)
+    libc.malloc.restype = C.c_void_p
+    n0 = 0 if existing is None else len(existing)
+    ptr = C.c_void_p(None)
+    cap = C.c_int(n0)
+    if n0:
+        existing = np.ascontiguousarray(existing, dtype=np.float64)
+        assert existing.shape[1] == 11
+        ptr = C.c_void_p(libc.malloc(C.c_size_t(existing.nbytes)))
+        C.memmove(ptr, existing.ctypes.data, existing.nbytes)
+    n = _chk(fn(C.byref(ptr), C.byref(cap), C.c_int(n0), *[C.c_double(a) for a in args]))
+    out = np.empty((n, 11), dtype=np.float64)
+    if n:
+        C.memmove(out.ctypes.data, ptr, out.nbytes)
+    if ptr.value:
+        lib().ass_free(ptr)
+    return out
+
+
+def rand_cone(min_dist, radius, height, total_mass, existing=None):
+    return _gen2(lib().ass_rand_cone, (min_dist, radius, height, total_mass), existing)
+
+
+def rand_shape(vertices, min_dist, total_mass):
+    """vertices: (V, 11) rows of the shape model; returns vertices followed by the new particles (as the reference does)."""
+    return _gen2(lib().ass_rand_shape, (min_dist, total_mass), vertices)

@@ -41,6 +41,7 @@ static_assert(sizeof(ass_spring) == 32, "ass_spring must match struct spring (32
 #endif
 constexpr int SPRING_LANES = ASS_SPRING_LANES;  // lanes cooperating on one node's half-edge list (2, 4 or 8)
 static_assert(SPRING_LANES == 2 || SPRING_LANES == 4 || SPRING_LANES == 8, "SPRING_LANES must be 2, 4 or 8");
+#define ASS_MAX_MASKS 4
 #define ASS_SORT_BLOCK 256  // ranks per block inside which nodes are dealt to lane groups by degree (ass_sim::grp)
 
 // ---------------------------------------------------------------------------------------------------
@@ -121,6 +122,7 @@ struct ass_sim {
 	bool have_state = false;
 	bool predrifted = false;  // positions already carry the next step's first half-drift (fused loop only)
 	bool sum_sequential = true;  // CoM / CoV sums in the reference's particle order (bit-exact) or as a parallel tree
+	bool sum_order_forced = false;  // ass_set_sum_order was called: otherwise the built-in per-step heartbeat uses the tree
 	int gravity_kernel = 0;      // 0 auto, 1 one-sided tiles (gravity.cu), 2 pair-once (gravity_sym.cu)
 	std::vector<struct SymPlan*> sym_plans;  // CTA tables + scratch rows of the pair-once kernel, one per (resident, streamed) range pair
 
@@ -171,6 +173,10 @@ struct ass_sim {
 	int n_pal = 0;
 	size_t he_cap = 0, row_cap = 0, pal_cap = 0;
 	int max_degree = 0;
+
+	// node masks for the masked force terms (stress.cu: apply_impact's surface nodes, the cube module's top / bottom faces)
+	unsigned char* masks = nullptr;  // ASS_MAX_MASKS x mask_cap
+	size_t mask_cap = 0;
 
 	// scratch
 	DevBuf stage;             // raw host rows on the device

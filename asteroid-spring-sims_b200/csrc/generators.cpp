@@ -185,6 +185,189 @@ extern "C" int ass_rand_ellipsoid(double** rows, int* cap_rows, int n0, double m
 	return R.n;
 }
 
+// The common loop of rand_rectangle / rand_cone / rand_shape (shapes.cpp:66-208, 435-516): n_candidates darts, each
+// x = U(lo0, hi0), y = U(lo1, hi1), z = U(lo2, hi2) in that order from libc rand(); kept if `inside` says so and no
+// particle created by this call lies within min_dist (strict <, Vector::len); m = 1 and r = `radius` until the end,
+// then m = total_mass / count.  The "too near" scan of the reference is linear in the particles created so far; here
+// it is a 27-cell lookup -- same answer.
+extern "C" int ass_rand_fill(double** rows, int* cap_rows, int n0, long long n_candidates, const double lo[3], const double hi[3],
+		ass_inside_fn inside, void* ctx, double min_dist, double radius, double total_mass) {
+	if (!rows || !cap_rows || n0 < 0 || !lo || !hi || !(min_dist > 0.0) || n_candidates < 0) {
+		ass_set_error("ass_rand_fill: bad argument");
+		return ASS_EINVAL;
+	}
+	Rows R{ rows, cap_rows, n0 };
+	const int i_0 = n0;
+	BucketGrid grid(lo, hi, min_dist, 2.5e8);
+	for (long long t = 0; t < n_candidates; t++) {
+		double p[3];
+		p[0] = random_uniform(lo[0], hi[0]);
+		p[1] = random_uniform(lo[1], hi[1]);
+		p[2] = random_uniform(lo[2], hi[2]);
+		if (inside && !inside(ctx, p[0], p[1], p[2])) continue;
+		const double* base = *rows;
+		const bool too_near = grid.any_neighbour(p, [&](int id) {
+			const double* q = base + (size_t) (i_0 + id) * STRIDE;
+			return vlen(p[0] - q[0], p[1] - q[1], p[2] - q[2]) < min_dist;
+		});
+		if (too_near) continue;
+		if (!R.push(p[0], p[1], p[2], 1.0, radius)) {
+			ass_set_error("ass_rand_fill: out of memory");
+			return ASS_ENOMEM;
+		}
+		grid.insert(p, R.n - 1 - i_0);
+	}
+	if (R.n > i_0) {
+		const double particle_mass = total_mass / (R.n - i_0);
+		for (int i = i_0; i < R.n; i++) (*rows)[(size_t) i * STRIDE + 9] = particle_mass;
+	}
+	return R.n;
+}
+
+// rand_rectangle, shapes.cpp:66-128: box of edge lengths x, y, z about the origin
+extern "C" int ass_rand_rectangle(double** rows, int* cap_rows, int n0, double min_dist, double x, double y, double z, double total_mass) {
+	if (!(x > 0.0) || !(y > 0.0) || !(z > 0.0) || !(min_dist > 0.0)) {
+		ass_set_error("ass_rand_rectangle: bad argument");
+		return ASS_EINVAL;
+	}
+	const int n_part = 40.0 * x * y * z / pow(min_dist, 3.0);  // :70 (double -> int truncation)
+	const double lo[3] = { -x / 2, -y / 2, -z / 2 }, hi[3] = { x / 2, y / 2, z / 2 };
+	return ass_rand_fill(rows, cap_rows, n0, n_part, lo, hi, nullptr, nullptr, min_dist, (min_dist / 2.0) / 3.0, total_mass);  // r: :83-84
+}
+
+namespace {
+struct Cone { double radius, height, slope; };
+int inside_cone(void* ctx, double x, double y, double z) {  // shapes.cpp:168-173, with the contractions gcc applies in GNU C++ mode
+	const Cone* c = (const Cone*) ctx;
+	const double cur_rad = sqrt(fma(x, x, y * y));           // gcc contracts pt.x*pt.x + pt.y*pt.y into fma(x, x, y*y)
+	const double max_height = fma(-cur_rad, c->slope, c->height);  // height - cur_rad * slope, contracted
+	return (cur_rad < c->radius) && (z < max_height);
+}
+}  // namespace
+
+// rand_cone, shapes.cpp:132-206: base radius and height, apex up, base in the plane z = 0
+extern "C" int ass_rand_cone(double** rows, int* cap_rows, int n0, double min_dist, double radius, double height, double total_mass) {
+	if (!(radius > 0.0) || !(height > 0.0) || !(min_dist > 0.0)) {
+		ass_set_error("ass_rand_cone: bad argument");
+		return ASS_EINVAL;
+	}
+	Cone c{ radius, height, height / radius };  // :136
+	const int n_part = 40 * pow(2.0 * radius / min_dist, 3.0);  // :139
+	const double lo[3] = { -radius, -radius, 0.0 }, hi[3] = { radius, radius, height };
+	return ass_rand_fill(rows, cap_rows, n0, n_part, lo, hi, inside_cone, &c, min_dist, (min_dist / 2.0) / 2.0, total_mass);  // r: :153-154
+}
+
+namespace {
+// within_shape (shapes.cpp:720-748) over the vertex rows [0, n_shape): inside the smallest vertex radius -> in; outside
+// the largest -> out; otherwise compare with the radius of the NEAREST vertex (nearest_to_point, :752-774: first index
+// of the strictly smallest distance).  The nearest vertex is found through a bucket grid over the vertices instead of a
+// scan over all of them: cells are visited in shells around the point until no closer vertex can exist, ties go to the
+// lowest index -- the vertex the linear scan returns.
+struct Shape {
+	const double* rows;
+	int n;
+	double r_min, r_max, h, lo[3];
+	int dim[3];
+	std::vector<int> start, ids;
+	int cell(const double p[3], int c[3]) const {
+		for (int d = 0; d < 3; d++) {
+			int v = (int) floor((p[d] - lo[d]) / h);
+			c[d] = v < 0 ? 0 : (v >= dim[d] ? dim[d] - 1 : v);
+		}
+		return (c[2] * dim[1] + c[1]) * dim[0] + c[0];
+	}
+	int nearest(double x, double y, double z) const {
+		const double p[3] = { x, y, z };
+		int c[3];
+		cell(p, c);
+		double best = DBL_MAX;
+		int best_i = -1;
+		const int max_shell = std::max(dim[0], std::max(dim[1], dim[2]));
+		for (int sh = 0; sh <= max_shell; sh++) {
+			// every vertex in a cell of shell `sh` is at least (sh - 1) * h away: along some axis its cell index differs by sh
+			// from the point's (clamped) cell, and a point outside the box is only farther from that side
+			if (best_i >= 0 && (sh - 1) * h > best) break;
+			for (int k = c[2] - sh; k <= c[2] + sh; k++) {
+				if (k < 0 || k >= dim[2]) continue;
+				for (int j = c[1] - sh; j <= c[1] + sh; j++) {
+					if (j < 0 || j >= dim[1]) continue;
+					const bool edge_kj = (k == c[2] - sh || k == c[2] + sh || j == c[1] - sh || j == c[1] + sh);
+					for (int i = c[0] - sh; i <= c[0] + sh; i += (edge_kj ? 1 : std::max(1, 2 * sh))) {
+						if (i < 0 || i >= dim[0]) continue;
+						const int cc = (k * dim[1] + j) * dim[0] + i;
+						for (int q = start[cc]; q < start[cc + 1]; q++) {
+							const int id = ids[q];
+							const double* v = rows + (size_t) id * STRIDE;
+							const double r = vlen(v[0] - x, v[1] - y, v[2] - z);  // Vector dx = part_pos - pos; dx.len()
+							if (r < best || (r == best && id < best_i)) { best = r; best_i = id; }
+						}
+					}
+				}
+			}
+		}
+		return best_i;
+	}
+};
+int inside_shape(void* ctx, double x, double y, double z) {
+	const Shape* S = (const Shape*) ctx;
+	const double rad = vlen(x, y, z);
+	if (rad < S->r_min) return 1;
+	if (rad > S->r_max) return 0;
+	const int i = S->nearest(x, y, z);
+	const double* v = S->rows + (size_t) i * STRIDE;
+	return !(rad > vlen(v[0], v[1], v[2]));
+}
+}  // namespace
+
+// rand_shape, shapes.cpp:435-516: rows [0, n0) are the vertices of the shape model (already "read in"); new particles are
+// appended after them.
+extern "C" int ass_rand_shape(double** rows, int* cap_rows, int n0, double min_dist, double total_mass) {
+	if (!rows || !cap_rows || n0 <= 0 || !*rows || !(min_dist > 0.0)) {
+		ass_set_error("ass_rand_shape: needs the shape's vertices as rows [0, n0) and a positive min_dist");
+		return ASS_EINVAL;
+	}
+	// the vertex rows may move when the array grows: work on a copy
+	std::vector<double> verts(*rows, *rows + (size_t) n0 * STRIDE);
+	Shape S;
+	S.rows = verts.data();
+	S.n = n0;
+	S.r_min = DBL_MAX;  // min_radius / max_radius, shapes.cpp:777-811
+	S.r_max = 0.0;
+	double bl[3] = { DBL_MAX, DBL_MAX, DBL_MAX }, bh[3] = { -DBL_MAX, -DBL_MAX, -DBL_MAX };
+	for (int i = 0; i < n0; i++) {
+		const double* v = verts.data() + (size_t) i * STRIDE;
+		const double r = vlen(v[0], v[1], v[2]);
+		if (r < S.r_min) S.r_min = r;
+		if (r > S.r_max) S.r_max = r;
+		for (int d = 0; d < 3; d++) { bl[d] = std::min(bl[d], v[d]); bh[d] = std::max(bh[d], v[d]); }
+	}
+	// ~2 vertices per cell
+	double vol = 1.0;
+	for (int d = 0; d < 3; d++) vol *= std::max(bh[d] - bl[d], 1e-300);
+	S.h = std::max(cbrt(vol * 2.0 / n0), 1e-12 * S.r_max + 1e-300);
+	for (int d = 0; d < 3; d++) {
+		S.lo[d] = bl[d];
+		S.dim[d] = std::min(1024, (int) floor((bh[d] - bl[d]) / S.h) + 1);
+	}
+	const size_t nc = (size_t) S.dim[0] * S.dim[1] * S.dim[2];
+	S.start.assign(nc + 1, 0);
+	std::vector<int> cell_of((size_t) n0);
+	for (int i = 0; i < n0; i++) {
+		int c[3];
+		cell_of[(size_t) i] = S.cell(verts.data() + (size_t) i * STRIDE, c);
+		S.start[(size_t) cell_of[(size_t) i] + 1]++;
+	}
+	for (size_t c = 0; c < nc; c++) S.start[c + 1] += S.start[c];
+	S.ids.resize((size_t) n0);
+	{
+		std::vector<int> fill(S.start.begin(), S.start.end() - 1);
+		for (int i = 0; i < n0; i++) S.ids[(size_t) fill[(size_t) cell_of[(size_t) i]]++] = i;
+	}
+	const int n_part = 40 * pow(2.0 * S.r_max / min_dist, 3.0);  // :447
+	const double lo[3] = { -S.r_max, -S.r_max, -S.r_max }, hi[3] = { S.r_max, S.r_max, S.r_max };
+	return ass_rand_fill(rows, cap_rows, n0, n_part, lo, hi, inside_shape, &S, min_dist, min_dist / 4.0, total_mass);  // r: :462
+}
+
 extern "C" int ass_hcp_ellipsoid(double** rows, int* cap_rows, int n0, double min_dist, double a, double b, double c, double total_mass) {
 	if (!rows || !cap_rows || n0 < 0 || !(min_dist > 0.0) || !(a > 0.0) || !(b > 0.0) || !(c > 0.0)) {
 		ass_set_error("ass_hcp_ellipsoid: bad argument");

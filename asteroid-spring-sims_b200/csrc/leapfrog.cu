@@ -150,8 +150,21 @@ extern "C" int ass_leapfrog_part2(ass_sim* s) {
 //     gravity(x)                               -> acc            (only if gravity is on and its result survives)
 //     springs + kick + drift [+ next part1]    -> posm', vel', acc   one kernel, ping-pong buffers
 //     [heartbeat: CoM reduce ; shift + next part1]
+// The built-in heartbeat (center_sim every step) sums as a parallel tree unless the caller asked for an order: the
+// reference-order sum is one CTA walking all N particles (0.7 ms at N = 1e5, 25 x the spring kernel) and is meant for
+// set-up helpers, where an ulp of position ends up in rs0.
+struct HeartbeatSumOrder {
+	ass_sim* s;
+	bool saved;
+	explicit HeartbeatSumOrder(ass_sim* s_) : s(s_), saved(s_->sum_sequential) {
+		if (!s->sum_order_forced) s->sum_sequential = false;
+	}
+	~HeartbeatSumOrder() { s->sum_sequential = saved; }
+};
+
 static int step_loop(ass_sim* s, int nsteps, bool with_hb) {
 	const ass_params& P = s->prm;
+	HeartbeatSumOrder order_scope(s);
 	const int af = P.additional_forces;
 	const bool hb = with_hb && P.heartbeat == 1;
 	const bool have_springs = s->ns > 0 && af != 0;
@@ -251,6 +264,7 @@ extern "C" int ass_integrate(ass_sim* s, double tmax) {
 	s->prm.dt_last_done = 0.;            // :630
 	s->prm.status = -1;                  // :632 REB_RUNNING
 	if (s->prm.heartbeat == 1) {         // :633 heartbeat at t = 0
+		HeartbeatSumOrder order_scope(s);
 		const int hi = s->n - s->prm.n_perts;
 		if ((rc = ass_launch_com(s, 0, hi, false, s->d_red))) return rc;
 		if ((rc = ass_launch_shift(s, 0, s->n, s->d_red, false, -1.0, 0.0))) return rc;

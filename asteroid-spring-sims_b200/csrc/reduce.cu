@@ -178,6 +178,30 @@ __global__ void k_spin(const vec4d* __restrict__ posm, vec4d* __restrict__ vel, 
 	vel[i] = v;
 }
 
+// x <- R (x - c) + c, v <- R (v - u) + u for a 3x3 matrix R (row-major): rotate_body (c = CoM, u = CoV of the range),
+// rotate_origin and rotate_to_principal (c = u = 0), physics.cpp:249-385.  Matrix * Vector as gcc compiles
+// matrix_math.cpp:442-450: res = a0*v0, then two fused multiply-adds, in index order.
+__global__ void k_transform(vec4d* __restrict__ posm, vec4d* __restrict__ vel, int lo, int hi, const double* __restrict__ com,
+		const double* __restrict__ cov, double r00, double r01, double r02, double r10, double r11, double r12, double r20, double r21, double r22) {
+	const int i = lo + blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= hi) return;
+	const double cx = com ? com[0] : 0.0, cy = com ? com[1] : 0.0, cz = com ? com[2] : 0.0;
+	const double ux = cov ? cov[0] : 0.0, uy = cov ? cov[1] : 0.0, uz = cov ? cov[2] : 0.0;
+	vec4d p = posm[i], v = vel[i];
+	const double x = com ? __dsub_rn(p.x, cx) : p.x, y = com ? __dsub_rn(p.y, cy) : p.y, z = com ? __dsub_rn(p.z, cz) : p.z;
+	const double a = cov ? __dsub_rn(v.x, ux) : v.x, b = cov ? __dsub_rn(v.y, uy) : v.y, c = cov ? __dsub_rn(v.z, uz) : v.z;
+	const double X = __fma_rn(r02, z, __fma_rn(r01, y, __dmul_rn(r00, x)));
+	const double Y = __fma_rn(r12, z, __fma_rn(r11, y, __dmul_rn(r10, x)));
+	const double Z = __fma_rn(r22, z, __fma_rn(r21, y, __dmul_rn(r20, x)));
+	const double A = __fma_rn(r02, c, __fma_rn(r01, b, __dmul_rn(r00, a)));
+	const double B = __fma_rn(r12, c, __fma_rn(r11, b, __dmul_rn(r10, a)));
+	const double C = __fma_rn(r22, c, __fma_rn(r21, b, __dmul_rn(r20, a)));
+	p.x = com ? __dadd_rn(X, cx) : X; p.y = com ? __dadd_rn(Y, cy) : Y; p.z = com ? __dadd_rn(Z, cz) : Z;
+	v.x = cov ? __dadd_rn(A, ux) : A; v.y = cov ? __dadd_rn(B, uy) : B; v.z = cov ? __dadd_rn(C, uz) : C;
+	posm[i] = p;
+	vel[i] = v;
+}
+
 // node sums needing CoM and CoV: L (3), KE (1), inertia (6)  -> 10 values
 __global__ void __launch_bounds__(RB) k_node_diag(const vec4d* __restrict__ posm, const vec4d* __restrict__ vel, int lo, int hi,
 		const double* __restrict__ com, const double* __restrict__ cov, double* __restrict__ part) {
@@ -334,6 +358,7 @@ static int fetch(ass_sim* s, int count) {
 extern "C" int ass_set_sum_order(ass_sim* s, int sequential) {
 	REQUIRE(s, ASS_EINVAL, "null sim");
 	s->sum_sequential = sequential != 0;
+	s->sum_order_forced = true;
 	return ASS_OK;
 }
 
@@ -391,6 +416,22 @@ extern "C" int ass_spin_body(ass_sim* s, int lo, int hi, const double omega[3]) 
 	if (rc || (rc = ass_launch_com(s, lo, hi, true, s->d_red + 4))) return rc;
 	ass_tic(s, ASS_K_REDUCE);
 	k_spin<<<(hi - lo + 255) / 256, 256, 0, s->stream>>>(s->posm, s->vel, lo, hi, s->d_red, s->d_red + 4, omega[0], omega[1], omega[2]);
+	LAUNCH_CHECK();
+	ass_toc(s, ASS_K_REDUCE);
+	return ASS_OK;
+}
+
+extern "C" int ass_transform_body(ass_sim* s, int lo, int hi, const double R[9], int about_com) {
+	ENTER_RANGE(s, lo, hi);
+	REQUIRE(R, ASS_EINVAL, "null matrix");
+	if (hi == lo) return ASS_OK;
+	int rc;
+	if (about_com) {
+		if ((rc = ass_launch_com(s, lo, hi, false, s->d_red)) || (rc = ass_launch_com(s, lo, hi, true, s->d_red + 4))) return rc;
+	}
+	ass_tic(s, ASS_K_REDUCE);
+	k_transform<<<(hi - lo + 255) / 256, 256, 0, s->stream>>>(s->posm, s->vel, lo, hi, about_com ? s->d_red : nullptr, about_com ? s->d_red + 4 : nullptr, R[0],
+			R[1], R[2], R[3], R[4], R[5], R[6], R[7], R[8]);
 	LAUNCH_CHECK();
 	ass_toc(s, ASS_K_REDUCE);
 	return ASS_OK;

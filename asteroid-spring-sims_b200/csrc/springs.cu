@@ -133,8 +133,7 @@ constexpr int TL_THREADS = ASS_TILE_THREADS;  // 512 with two interleaved chains
 constexpr int TL_CHAINS = ASS_TILE_CHAINS;
 constexpr int TL_WARPS = TL_THREADS / 32;
 constexpr int GPW = 32 / SPRING_LANES;
-constexpr int TL_AHEAD = 2 * TL_WARPS;  // how many slices ahead of the one a warp starts its records are requested into L2
-constexpr int TL_FILL = (2944 + TL_THREADS - 1) / TL_THREADS;  // table slots per thread (TILE_SLOTS_LIMIT below)
+constexpr int TL_FILL = 3;  // table slots a thread has in flight at a time while the table is filled
 struct TileDesc {
 	int s0, s1, tab_off, n_slots;
 };
@@ -169,16 +168,8 @@ __global__ void __launch_bounds__(TL_THREADS, 1) k_spring_tiles(const __grid_con
 	const SharedNodes nodes{ s_xy, s_zv, s_vxy, s_m };
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, sub = lane & (SPRING_LANES - 1);
 	const CtaHead& H = heads.h[blockIdx.x];
-	const int sl_end = H.sl_end;
 	double2 nkg1 = make_double2(0.0, 0.0);
 	if (PAL1) nkg1 = __ldg(palf);
-	// ask L2 for the records of slice g (at most 4 KB = 32 lines; longer rows are caught up by the loop's own look-ahead)
-	auto request = [&](int g) {
-		if (g < sl_end) {
-			const int o0 = __ldg(warp_off + g), o1 = __ldg(warp_off + g + 1);
-			if (lane * 8 < o1 - o0) asm volatile("prefetch.global.L2 [%0];" ::"l"(heL + o0 + lane * 8));
-		}
-	};
 	for (int t = H.tile0; t < H.tile0 + H.ntiles; t++) {
 		const TileDesc T = (t == H.tile0) ? H.first : tiles[t];
 		const int n_sl = T.s1 - T.s0;
@@ -188,23 +179,19 @@ __global__ void __launch_bounds__(TL_THREADS, 1) k_spring_tiles(const __grid_con
 		int sw = warp;
 		int4 gi = make_int4(-1, -1, 0, 0);
 		int off = 0, P = 0;
-		int4 r0 = make_int4(0, 0, 0, 0), r1 = r0;
+		int4 r0 = make_int4(0, 0, 0, 0), r1 = r0;  // the stream's first pair of steps
 		if (sw < n_sl) {
 			gi = __ldg(grpT + (size_t) (T.s0 + sw) * GPW + lane / SPRING_LANES);
 			off = __ldg(warp_off + T.s0 + sw);
 			P = (__ldg(warp_off + T.s0 + sw + 1) - off) >> 6;
 			if (P > 0) { r0 = __ldcg((const int4*) heL + off + lane); r1 = __ldcg((const int4*) heL + off + lane + 32); }
 		}
-		if (t == H.tile0) {  // the stream's head start: the slices the warps will take next
-			request(T.s0 + TL_WARPS + warp);
-			request(T.s0 + 2 * TL_WARPS + warp);
-		}
 		// ---- the table: every request of a thread is in flight before its first store ----
-		{
+		for (int base = 0; base < T.n_slots; base += TL_FILL * TL_THREADS) {
 			int r[TL_FILL];
 #pragma unroll
 			for (int q = 0; q < TL_FILL; q++) {
-				const int i = tid + q * TL_THREADS;
+				const int i = base + tid + q * TL_THREADS;
 				r[q] = (i < T.n_slots) ? __ldg(tab + T.tab_off + i) : -1;
 			}
 			double2 a[TL_FILL], b[TL_FILL], c[TL_FILL];
@@ -216,7 +203,7 @@ __global__ void __launch_bounds__(TL_THREADS, 1) k_spring_tiles(const __grid_con
 			}
 #pragma unroll
 			for (int q = 0; q < TL_FILL; q++) {
-				const int i = tid + q * TL_THREADS;
+				const int i = base + tid + q * TL_THREADS;
 				if (i < T.n_slots) { s_xy[i] = a[q]; s_zv[i] = b[q]; s_vxy[i] = c[q]; s_m[i] = m[q]; }
 			}
 		}
@@ -230,7 +217,6 @@ __global__ void __launch_bounds__(TL_THREADS, 1) k_spring_tiles(const __grid_con
 			int nx = 0;
 			if (lane == 0) nx = atomicAdd(&s_next, 1);
 			nx = __shfl_sync(0xffffffffu, nx, 0);
-			request(T.s0 + nx + TL_AHEAD);
 			const bool live = gi.x >= 0;
 			const int slot = live ? gi.x : 0;
 			const int nt = (gi.z - sub + SPRING_LANES - 1) / SPRING_LANES;  // entries sub, sub + SPRING_LANES, ... of the row are this lane's
@@ -244,6 +230,8 @@ __global__ void __launch_bounds__(TL_THREADS, 1) k_spring_tiles(const __grid_con
 				gi_n = s_grp[nx * GPW + lane / SPRING_LANES];  // (slot, rank, degree, node); slot < 0: padding group
 				off_n = s_off[nx];
 				P_n = (s_off[nx + 1] - off_n) >> 6;
+				// the rest of that slice's records (at most 4 KB = 32 lines): into L2 now, a slice ahead of their use
+				if (lane * 8 < s_off[nx + 1] - off_n) asm volatile("prefetch.global.L2 [%0];" ::"l"(heL + off_n + lane * 8));
 			}
 			const Force3 F = lane_spring_sum_x<UNI, PAL1, TL_CHAINS>((const int4*) heL + off + lane, P, nt, ni, nodes, palf, nkg1, r0, r1,
 					P_n > 0 ? (const int4*) heL + off_n + lane : nullptr);
@@ -582,9 +570,15 @@ template <bool ZERO_FIRST, bool KICK, bool UNI, bool PAL1>
 static int launch_tiles_t(ass_sim* s, double dt, int pre) {
 	auto kern = k_spring_tiles<ZERO_FIRST, KICK, UNI, PAL1>;
 	const size_t smem = TILE_SLOT_BYTES * (size_t) s->tile_slots_max + (size_t) s->tile_slices_max * GPW * sizeof(int4) + sizeof(int) * ((size_t) s->tile_slices_max + 2);
-	// the opt-in above 48 KB is per function AND per device: set on every launch (a host-side table lookup) rather than
-	// remembered per process
-	CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+	// the opt-in above 48 KB is per function AND per device: remembered per device (a process may drive several), set to
+	// the most a tile can need so that it never has to be raised again
+	static bool opted[64] = {};
+	int dev = 0;
+	CU_TRY(cudaGetDevice(&dev));
+	if (dev < 0 || dev >= 64 || !opted[dev]) {
+		CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
+		if (dev >= 0 && dev < 64) opted[dev] = true;
+	}
 	TilesParams P;
 	memcpy(&P, s->tile_heads.data(), std::min(sizeof(P), s->tile_heads.size() * sizeof(int)));
 	kern<<<s->tiles_grid, TL_THREADS, smem, s->stream>>>(P, mirror_nodes(s), s->acc, (const TileDesc*) s->tile_desc, s->tile_tab, s->grpT, s->warp_off, s->heL,

@@ -380,7 +380,7 @@ extern "C" int ass_destroy(ass_sim* s) {
 	cudaFree(s->posm); cudaFree(s->vel); cudaFree(s->acc); cudaFree(s->posm_alt); cudaFree(s->vel_alt);
 	cudaFree(s->he); cudaFree(s->row_ptr); cudaFree(s->slot); cudaFree(s->pal);
 	cudaFree(s->stage.p); cudaFree(s->grav_partial.p); cudaFree(s->red_partial.p); cudaFree(s->flush.p);
-	cudaFree(s->d_red);
+	cudaFree(s->d_red); cudaFree(s->masks);
 	if (s->h_red) cudaFreeHost(s->h_red);
 	if (s->h_pinned) cudaFreeHost(s->h_pinned);
 	for (auto& e : s->ev_pool) {

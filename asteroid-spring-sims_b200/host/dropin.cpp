@@ -61,10 +61,17 @@ struct Dropin {
 	bool topo_stale = true, prop_stale = true;
 	size_t sp_size = 0;
 	const spring* sp_ptr = nullptr;
-	uint64_t sp_probe = 0;
 	// r->particles page-locked for the length of a reb_integrate (uploads / downloads at PCIe link rate)
 	void* pinned = nullptr;
 	size_t pinned_bytes = 0;
+	// diagnostics of one device state, shared by the functions write_resolved_with_E calls one after another
+	uint64_t version = 1;        // bumped whenever the device state or the spring list may have changed
+	uint64_t diag_version = 0;
+	int diag_lo = -1, diag_hi = -1;
+	bool diag_gpe = false;
+	double diag[20];
+	// fingerprints of the module's spring list: wiring (particle_1, particle_2) and properties (k, rs0, gamma) apart
+	uint64_t sp_probe_topo = 0, sp_probe_prop = 0;
 };
 
 std::mutex g_mu;
@@ -137,6 +144,7 @@ void ensure_dev(reb_simulation* r, Dropin& d) {
 	if (d.dev_fresh && ass_num_particles(d.sim) == r->N) return;
 	if (d.in_run) pin_particles(r, d);
 	OK(ass_upload_particles(d.sim, r->particles, sizeof(reb_particle), r->N, ASS_F_ALL));
+	d.version++;
 	d.dev_fresh = true;
 	d.host_fresh = true;
 	d.pending = 0;
@@ -151,6 +159,7 @@ void flush_host(reb_simulation* r, Dropin& d) {
 
 // a device operation wrote `fields`
 void wrote(reb_simulation* r, Dropin& d, unsigned fields) {
+	d.version++;
 	d.pending |= fields;
 	d.host_fresh = false;
 	if (resident() && d.in_run) return;  // the device copy is the truth until someone asks for the host arrays
@@ -171,36 +180,43 @@ struct Sequence {  // several kernels of ours back to back: transfer once at the
 	}
 };
 
-uint64_t probe_springs() {
-	// cheap fingerprint of the module's list: catches add/del/set_gamma done by code we did not intercept
+// cheap fingerprints of the module's list: they catch add / del / direct writes to springs[i] done by code this layer
+// did not intercept.  Wiring and properties are hashed apart, so a direct `springs[i].k = ...` costs a property update
+// (one kernel), not a rebuild of the layout (seconds of host time at 1e5 nodes).
+void probe_springs(uint64_t* topo, uint64_t* prop) {
 	const size_t n = springs.size();
-	uint64_t h = 1469598103934665603ULL ^ n;
-	if (!n) return h;
+	uint64_t ht = 1469598103934665603ULL ^ n, hp = 1469598103934665603ULL;
 	const size_t step = n > 4096 ? n / 1024 : 1;
-	auto mix = [&](const spring& s) {
+	auto mix = [&](const spring& sp) {
 		uint64_t w[4];
-		memcpy(w, &s, sizeof(w));
-		for (int q = 0; q < 4; q++) { h ^= w[q]; h *= 1099511628211ULL; }
+		memcpy(w, &sp, sizeof(w));  // {k, rs0, gamma, (particle_1, particle_2)}
+		for (int q = 0; q < 3; q++) { hp ^= w[q]; hp *= 1099511628211ULL; }
+		ht ^= w[3]; ht *= 1099511628211ULL;
 	};
 	for (size_t i = 0; i < n; i += step) mix(springs[i]);
-	mix(springs[n - 1]);
-	return h;
+	if (n) mix(springs[n - 1]);
+	*topo = ht;
+	*prop = hp;
 }
 
 void ensure_springs(Dropin& d) {
 	if (num_springs != (int) springs.size()) throw "Spring count and size of spring array don't match.\n";  // springs.cpp:38-40,99-101
-	const uint64_t pr = probe_springs();
-	if (springs.size() != d.sp_size || springs.data() != d.sp_ptr) d.topo_stale = true;
-	else if (pr != d.sp_probe) d.topo_stale = true;  // cannot tell a property edit from a re-wiring: rebuild
+	uint64_t pt, pp;
+	probe_springs(&pt, &pp);
+	if (springs.size() != d.sp_size || springs.data() != d.sp_ptr || pt != d.sp_probe_topo) d.topo_stale = true;
+	else if (pp != d.sp_probe_prop) d.prop_stale = true;
 	if (d.topo_stale) {
 		OK(ass_set_springs(d.sim, (const ass_spring*) springs.data(), (int) springs.size()));
+		d.version++;
 	} else if (d.prop_stale) {
 		OK(ass_update_spring_props(d.sim, (const ass_spring*) springs.data(), (int) springs.size()));
+		d.version++;
 	}
 	d.topo_stale = d.prop_stale = false;
 	d.sp_size = springs.size();
 	d.sp_ptr = springs.data();
-	d.sp_probe = pr;
+	d.sp_probe_topo = pt;
+	d.sp_probe_prop = pp;
 }
 
 void props_changed() {
@@ -550,6 +566,155 @@ double sum_mass(reb_simulation* const r, int i_low, int i_high) {
 	return m;
 }
 
+// src_spring/stress.cpp:32-98.  The O(NS) part -- every node's sum of +-outer(F, L) and its strongest spring -- runs on the
+// device and comes back with the reference's bits; the 3x3 eigenvalues stay the reference's own code, including its
+// behaviour on tensors that are not exactly symmetric (eigenvalues() throws a `const char*` that the `catch (char*)`
+// below, copied from the reference, does not match: the exception leaves update_stress, as it does there).
+void update_stress(reb_simulation* const r) {
+	Dropin& d = get(r);
+	ensure_dev(r, d);
+	ensure_springs(d);
+	const int N = r->N;
+	if (!stresses.size()) stresses.resize(N);
+	std::vector<double> T((size_t) 9 * N), F((size_t) N);
+	std::vector<int> S((size_t) N);
+	OK(ass_stress(d.sim, T.data(), F.data(), S.data()));
+	for (int i = 0; i < N; i++) {
+		const double* t = T.data() + (size_t) 9 * i;
+		stresses[i].stress = Matrix({ { t[0], t[1], t[2] }, { t[3], t[4], t[5] }, { t[6], t[7], t[8] } });
+		stresses[i].eigs[0] = 0.0; stresses[i].eigs[1] = 0.0; stresses[i].eigs[2] = 0.0;
+		stresses[i].max_force = F[(size_t) i];
+		stresses[i].max_force_spring = S[(size_t) i];
+		stresses[i].failing = false;
+	}
+	for (int i = 0; i < N; i++) {
+		try {
+			eigenvalues(stresses[i].stress, stresses[i].eigs);
+		} catch (char* str) {
+			std::cerr << "Error: " << str << " Exiting." << std::endl;
+			exit(1);
+		}
+	}
+}
+
+// ---------------------------------------------------------------------------------------------------
+// the rest of src_spring/physics.cpp that set-up code and write_resolved_with_E (output_spring.cpp:112-192) call
+// ---------------------------------------------------------------------------------------------------
+namespace {
+// out[20] of ass_diagnostics for the current device state; one evaluation serves measure_L, compute_rot_kin,
+// spring_potential_energy, dEdt_total and mom_inertia when they are called back to back on an unchanged state
+const double* diagnostics(reb_simulation* r, int i_low, int i_high, bool want_gpe) {
+	Dropin& d = get(r);
+	ensure_dev(r, d);
+	if (num_springs > 0 || springs.size() > 0) ensure_springs(d);
+	if (d.diag_version == d.version && d.diag_lo == i_low && d.diag_hi == i_high && (d.diag_gpe || !want_gpe)) return d.diag;
+	push_params(r, d);
+	OK(ass_diagnostics(d.sim, i_low, i_high, want_gpe ? 1 : 0, d.diag));
+	d.diag_version = d.version; d.diag_lo = i_low; d.diag_hi = i_high; d.diag_gpe = want_gpe;
+	return d.diag;
+}
+// spring sums do not depend on the particle range: reuse whatever range was evaluated last
+const double* spring_diagnostics(reb_simulation* r) {
+	Dropin& d = get(r);
+	if (d.diag_version == d.version && d.diag_lo >= 0) {
+		ensure_dev(r, d);
+		ensure_springs(d);
+		if (d.diag_version == d.version) return d.diag;
+	}
+	return diagnostics(r, 0, r->N - num_perts > 0 ? r->N - num_perts : r->N, false);
+}
+}  // namespace
+
+// physics.cpp:184-210
+void spin_body(reb_simulation* const r, int i_low, int i_high, Vector omega) {
+	Dropin& d = get(r);
+	ensure_dev(r, d);
+	const double w[3] = { omega.getX(), omega.getY(), omega.getZ() };
+	OK(ass_spin_body(d.sim, i_low, i_high, w));
+	wrote(r, d, ASS_F_VEL);
+}
+
+// physics.cpp:136-162
+Vector measure_L(reb_simulation* const r, int i_low, int i_high) {
+	if (i_high <= i_low) return Vector(zero_vec);
+	const double* q = diagnostics(r, i_low, i_high, false);
+	return Vector({ q[6], q[7], q[8] });
+}
+
+// physics.cpp:116-134
+Matrix mom_inertia(reb_simulation* const r, int i_low, int i_high) {
+	if (i_high <= i_low) return Matrix(zero_mat);
+	const double* q = diagnostics(r, i_low, i_high, false);  // [13..18] xx yy zz xy xz yz
+	return Matrix({ { q[13], q[16], q[17] }, { q[16], q[14], q[18] }, { q[17], q[18], q[15] } });
+}
+
+// physics.cpp:164-181
+Vector body_spin(reb_simulation* const r, int i_low, int i_high) {
+	Matrix inv_mom_inert = inverse(mom_inertia(r, i_low, i_high));
+	return inv_mom_inert * measure_L(r, i_low, i_high);
+}
+
+// physics.cpp:508-528
+double compute_rot_kin(reb_simulation* const r, int i_low, int i_high) {
+	if (i_high <= i_low) return 0.0;
+	return diagnostics(r, i_low, i_high, false)[9];
+}
+
+// physics.cpp:457-476
+double spring_potential_energy(reb_simulation* const r) {
+	if (num_springs <= 0 || r->N <= 0) return 0.0;
+	return spring_diagnostics(r)[10];
+}
+
+// physics.cpp:409-454
+double dEdt_total(reb_simulation* const r) {
+	if (num_springs <= 0 || r->N <= 0) return 0.0;
+	return spring_diagnostics(r)[12];
+}
+
+// physics.cpp:479-504 -- O(N^2): as expensive as a force evaluation; on the device it reuses the gravity tiling
+double grav_potential_energy(reb_simulation* const r, int i_low, int i_high) {
+	if (i_high <= i_low) return 0.0;
+	return diagnostics(r, i_low, i_high, true)[11];
+}
+
+// physics.cpp:249-290
+void rotate_body(reb_simulation* const r, int i_low, int i_high, double alpha, double beta, double gamma) {
+	Dropin& d = get(r);
+	ensure_dev(r, d);
+	// Rz2 * Rx * Rz1, composed by the reference's own Matrix arithmetic (left to right, as in :274)
+	const Matrix R = getRotMatZ(gamma) * getRotMatX(beta) * getRotMatZ(alpha);
+	const double m[9] = { R.getXX(), R.getXY(), R.getXZ(), R.getYX(), R.getYY(), R.getYZ(), R.getZX(), R.getZY(), R.getZZ() };
+	OK(ass_transform_body(d.sim, i_low, i_high, m, 1));
+	wrote(r, d, ASS_F_POS | ASS_F_VEL);
+}
+
+// physics.cpp:294-331
+void rotate_origin(reb_simulation* const r, int i_low, int i_high, double alpha, double beta, double gamma) {
+	Dropin& d = get(r);
+	ensure_dev(r, d);
+	const Matrix R = getRotMatZ(gamma) * getRotMatX(beta) * getRotMatZ(alpha);
+	const double m[9] = { R.getXX(), R.getXY(), R.getXZ(), R.getYX(), R.getYY(), R.getYZ(), R.getZX(), R.getZY(), R.getZZ() };
+	OK(ass_transform_body(d.sim, i_low, i_high, m, 0));
+	wrote(r, d, ASS_F_POS | ASS_F_VEL);
+}
+
+// physics.cpp:334-385: the 3x3 eigenproblem stays the reference's own code (matrix_math.cpp); the O(N) rotation runs on the device
+void rotate_to_principal(reb_simulation* const r, int i_low, int i_high) {
+	Matrix inertia_mat = mom_inertia(r, i_low, i_high);
+	double eigs[3];
+	eigenvalues(inertia_mat, eigs);
+	Vector eigvec1 = eigenvector(inertia_mat, eigs[2]);  // note the order (:346-349)
+	Vector eigvec2 = eigenvector(inertia_mat, eigs[1]);
+	Vector eigvec3 = eigenvector(inertia_mat, eigs[0]);
+	Matrix R = { eigvec1, eigvec2, eigvec3 };
+	const double m[9] = { R.getXX(), R.getXY(), R.getXZ(), R.getYX(), R.getYY(), R.getYZ(), R.getZX(), R.getZY(), R.getZZ() };
+	Dropin& d = get(r);
+	ensure_dev(r, d);
+	OK(ass_transform_body(d.sim, i_low, i_high, m, 0));
+	wrote(r, d, ASS_F_POS | ASS_F_VEL);
+}
+
 // src_spring/shapes.cpp:814-833
 double mindist(reb_simulation* const r, int i_low, int i_high) {
 	Dropin& d = get(r);
@@ -557,6 +722,114 @@ double mindist(reb_simulation* const r, int i_low, int i_high) {
 	double out = 0.0;
 	OK(ass_mindist(d.sim, i_low, i_high, &out));
 	return out;
+}
+
+namespace {
+// append packed generator rows [n0, n_new) to the simulation, as the reference's reb_add loop does
+void add_rows(reb_simulation* r, const double* rows, int n_from, int n_to) {
+	for (int i = n_from; i < n_to; i++) {
+		reb_particle pt;
+		memset(&pt, 0, sizeof(pt));
+		const double* q = rows + (size_t) i * 11;
+		pt.x = q[0]; pt.y = q[1]; pt.z = q[2];
+		pt.m = q[9]; pt.r = q[10];
+		reb_add(r, pt);
+	}
+}
+// existing particles as packed rows (rand_shape reads the shape model's vertices from the simulation)
+double* rows_of(reb_simulation* r, int n, int* cap) {
+	*cap = n > 0 ? n : 1;
+	double* rows = (double*) calloc((size_t) *cap * 11, sizeof(double));
+	for (int i = 0; i < n; i++) {
+		const reb_particle& p = r->particles[i];
+		double* q = rows + (size_t) i * 11;
+		q[0] = p.x; q[1] = p.y; q[2] = p.z; q[3] = p.vx; q[4] = p.vy; q[5] = p.vz; q[9] = p.m; q[10] = p.r;
+	}
+	return rows;
+}
+}  // namespace
+
+// src_spring/shapes.cpp:66-128
+void rand_rectangle(reb_simulation* const r, double min_dist, double x, double y, double z, double total_mass) {
+	const int n_part = 40.0 * x * y * z / pow(min_dist, 3.0);
+	std::cout << "rand_rectangle: Trying to create " << n_part << " particles." << std::endl;
+	ass_dropin_sync_host(r);
+	double* rows = nullptr;
+	int cap = 0;
+	const int n_new = ass_rand_rectangle(&rows, &cap, 0, min_dist, x, y, z, total_mass);
+	if (n_new < 0) fatal("ass_rand_rectangle");
+	const int i_0 = r->N;
+	add_rows(r, rows, 0, n_new);
+	ass_free(rows);
+	ass_dropin_host_modified(r);
+	const double min_d = mindist(r, i_0, r->N);
+	std::cout << "rand_rectangle: Created " << r->N - i_0 << " particles separated by minimum distance " << min_d << std::endl;
+}
+
+// src_spring/shapes.cpp:132-206
+void rand_cone(reb_simulation* const r, double min_dist, double radius, double height, double total_mass) {
+	const int n_part = 40 * pow(2.0 * radius / min_dist, 3.0);
+	std::cout << "rand_cone: Trying to create " << n_part << " particles." << std::endl;
+	ass_dropin_sync_host(r);
+	double* rows = nullptr;
+	int cap = 0;
+	const int n_new = ass_rand_cone(&rows, &cap, 0, min_dist, radius, height, total_mass);
+	if (n_new < 0) fatal("ass_rand_cone");
+	const int i_0 = r->N;
+	add_rows(r, rows, 0, n_new);
+	ass_free(rows);
+	ass_dropin_host_modified(r);
+	const double min_d = mindist(r, i_0, r->N);
+	std::cout << "rand_cone: Created " << r->N - i_0 << " particles separated by minimum distance " << min_d << std::endl;
+}
+
+// src_spring/shapes.cpp:435-516: the shape model's vertices are particles [0, N) already
+void rand_shape(reb_simulation* const r, double min_dist, double total_mass) {
+	ass_dropin_sync_host(r);
+	const int N_shape = r->N;
+	const double max_r_shape = max_radius(r, 0, N_shape);
+	const int n_part = 40 * pow(2.0 * max_r_shape / min_dist, 3.0);
+	std::cout << "rand_shape: Trying to create " << n_part << " particles." << std::endl;
+	int cap = 0;
+	double* rows = rows_of(r, N_shape, &cap);
+	const int n_new = ass_rand_shape(&rows, &cap, N_shape, min_dist, total_mass);
+	if (n_new < 0) fatal("ass_rand_shape");
+	add_rows(r, rows, N_shape, n_new);
+	free(rows);
+	ass_dropin_host_modified(r);
+	const double min_d = mindist(r, N_shape, r->N);
+	std::cout << "rand_shape: Created " << r->N - N_shape << " particles separated by a minimum of " << min_d << std::endl;
+}
+
+// src_spring/shapes.cpp:282-352
+void hcp_ellipsoid(reb_simulation* r, double min_dist, double x, double y, double z, double total_mass) {
+	ass_dropin_sync_host(r);
+	double* rows = nullptr;
+	int cap = 0;
+	const int n_new = ass_hcp_ellipsoid(&rows, &cap, 0, min_dist, x, y, z, total_mass);
+	if (n_new < 0) fatal("ass_hcp_ellipsoid");
+	const int i_0 = r->N;
+	add_rows(r, rows, 0, n_new);
+	const double min_d = n_new > 0 ? rows[10] * 4.0 : 0.0;  // r = min_d / 4 (:342)
+	ass_free(rows);
+	ass_dropin_host_modified(r);
+	std::cout << "hcp_ellipsoid: Created " << r->N - i_0 << " particles with lattice spacing " << 1.08 * min_dist
+	          << ", separated by minimum distance " << (n_new > 1 ? mindist(r, i_0, r->N) : min_d) << std::endl;
+}
+
+// src_spring/shapes.cpp:356-431
+void cubic_ellipsoid(reb_simulation* r, double min_dist, double x, double y, double z, double total_mass) {
+	ass_dropin_sync_host(r);
+	double* rows = nullptr;
+	int cap = 0;
+	const int n_new = ass_cubic_ellipsoid(&rows, &cap, 0, min_dist, x, y, z, total_mass);
+	if (n_new < 0) fatal("ass_cubic_ellipsoid");
+	const int i_0 = r->N;
+	add_rows(r, rows, 0, n_new);
+	ass_free(rows);
+	ass_dropin_host_modified(r);
+	std::cout << "cubic_ellipsoid: Created " << r->N - i_0 << " particles, separated by minimum distance "
+	          << (n_new > 1 ? mindist(r, i_0, r->N) : 0.0) << std::endl;
 }
 
 // src_spring/shapes.cpp:210-278
@@ -569,14 +842,7 @@ void rand_ellipsoid(reb_simulation* const r, double min_dist, double x, double y
 	const int n_new = ass_rand_ellipsoid(&rows, &cap, 0, min_dist, x, y, z, total_mass);
 	if (n_new < 0) fatal("ass_rand_ellipsoid");
 	const int i_0 = r->N;
-	for (int i = 0; i < n_new; i++) {
-		reb_particle pt;
-		memset(&pt, 0, sizeof(pt));
-		const double* q = rows + (size_t) i * 11;
-		pt.x = q[0]; pt.y = q[1]; pt.z = q[2];
-		pt.m = q[9]; pt.r = q[10];
-		reb_add(r, pt);
-	}
+	add_rows(r, rows, 0, n_new);
 	ass_free(rows);
 	ass_dropin_host_modified(r);
 	const double min_d = mindist(r, i_0, r->N);

@@ -339,6 +339,12 @@ def run_single(args, A, name, cfg, local, want_e2e=True, want_cpu=True, steps=No
         pinned.close()
 
     parity = parity_of_sim(A, None, sim, p0, springs, cfg, n_perts, 0, 1, None)
+    dropin = None
+    if want_e2e and not args.no_e2e and not args.no_dropin and name == "C3":
+        try:
+            dropin = run_dropin_e2e(p0, springs, cfg)
+        except Exception as e:
+            dropin = {"error": repr(e)}
 
     # ---- roofline of the dominant kernel ----
     peaks = read_json(os.path.join(ROOT, "MEASURED_PEAKS.json")) or {}
@@ -377,7 +383,7 @@ def run_single(args, A, name, cfg, local, want_e2e=True, want_cpu=True, steps=No
         "metric": "node-steps/s", "value": value, "unit": "node-steps/s", "n_gpus": 1, "steps": steps, "warmup": warmup,
         "ms_per_step": dev_ms / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic", "config": config_of(name, cfg, n, ns, 1, "single"),
-        "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "parity": parity,
+        "clocks": clk, "e2e": e2e, "dropin_e2e": dropin, "gpu_launches": int(launches), "parity": parity,
         "roofline": dominant, "roofline_gravity": roof_g, "roofline_springs": roof_s, "cpu_baseline": cpu,
         "kernel_ms": {k: {"ms": v[0], "launches": v[1]} for k, v in kt.items()},
         "wall_ms_per_step_incl_flush": 1e3 * t_wall / steps, "setup": setup, "fp64_peak_tflops_measured": fp64_peak,
@@ -694,6 +700,76 @@ def run_reference(args, rank, world):
     emit(out)
 
 
+# ---------------------------------------------------------------------------------------------------
+# the drop-in itself: ONE module source linked against the reference and against the drop-in (tests/dropin)
+# ---------------------------------------------------------------------------------------------------
+def run_dropin_e2e(p0, springs, cfg, steps_b200=50):
+    """Wall time of reb_integrate inside tests/dropin/_build/synth_ref (the unmodified reference, serial as shipped) and
+    synth_b200 (the same module source on the drop-in) on the body of the main record, read from the reference's own
+    restart files (modules/asteroid_spin's path: read_particles / read_springs).  One print at t = 0 (write_resolved_with_E
+    with its O(N^2) potential energy) + the step loop.  The reference runs ONE step (it needs about a minute per step at
+    this size); the drop-in runs `steps_b200` in coherent (every call self-contained: upload, run, download) and resident
+    mode.  Returns None where the binaries are absent."""
+    import shutil
+    import tempfile
+    build = os.path.join(ROOT, "tests", "dropin", "_build")
+    bins = {k: os.path.join(build, k) for k in ("synth_ref", "synth_b200")}
+    if not all(os.path.exists(b) for b in bins.values()):
+        return {"unavailable": "tests/dropin/_build/synth_ref / synth_b200 not built (needs the reference tree at build time)"}
+    n, ns = len(p0), len(springs)
+    work = tempfile.mkdtemp(prefix="ass_dropin_")
+    try:
+        with open(os.path.join(work, "body_000000_particles.txt"), "w") as f:
+            for r in p0:   # x y z vx vy vz r m (input_spring.cpp:108-136)
+                f.write("%.17g %.17g %.17g %.17g %.17g %.17g %.17g %.17g\n" % (r[0], r[1], r[2], r[3], r[4], r[5], r[10] if p0.shape[1] > 10 else 0.0, r[9]))
+        with open(os.path.join(work, "body_000000_springs.txt"), "w") as f:
+            for q in springs:   # i j k rs0 gamma (input_spring.cpp:77-105)
+                f.write("%d %d %.17g %.17g %.17g\n" % (q["particle_1"], q["particle_2"], q["k"], q["rs0"], q["gamma"]))
+        base = open(os.path.join(ROOT, "tests", "dropin", "problem.cfg")).read()
+
+        def run(binary, nsteps, env_extra):
+            d = os.path.join(work, binary + "_" + env_extra.get("ASS_RESIDENT", "x"))
+            os.makedirs(d, exist_ok=True)
+            c = base
+            for key, val in (("dt", "%.17g" % cfg["dt"]), ("t_max", "%.17g" % (nsteps * cfg["dt"])), ("print_interval", "1e9"),
+                             ("min_particle_distance", "%.17g" % cfg["d"]), ("max_spring_dist", "%.17g" % (2.3 * cfg["d"])),
+                             ("k", "%.17g" % K_SPRING), ("gamma", "%.17g" % GAMMA), ("damp_fac", "1.0"), ("t_damp", "1e9"),
+                             ("gravity", "%d" % cfg["gravity"]), ("restart_index", "0")):
+                c = __import__("re").sub(r"(?m)^%s = [^;]*;" % key, "%s = %s;" % (key, val), c)
+            c = c.replace('restart_root = "";', 'restart_root = "%s";' % os.path.join(work, "body"))
+            open(os.path.join(d, "problem.cfg"), "w").write(c)
+            env = dict(os.environ)
+            env.update(env_extra)
+            t0 = time.perf_counter()
+            pr = subprocess.run([bins[binary]], cwd=d, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
+            wall = time.perf_counter() - t0
+            if pr.returncode != 0:
+                return {"error": pr.stdout[-400:]}
+            tm = dict(ln.split() for ln in open(os.path.join(d, "synth_timing.txt")).read().strip().split("\n"))
+            return {"steps": nsteps, "integrate_s": float(tm["integrate_s"]), "process_wall_s": wall,
+                    "res_row": open(os.path.join(d, "synth_res.txt")).read().strip().split("\n")[-1].split()}
+        out = {"body": {"N": int(n), "NS": int(ns)}, "what": "reb_integrate of tests/dropin/problem.cpp: heartbeat print at t = 0 (write_resolved_with_E incl. grav_potential_energy) + the steps"}
+        out["reference"] = run("synth_ref", 1, {})
+        out["b200_same_call"] = run("synth_b200", 1, {"ASS_RESIDENT": "1"})       # the reference's call, like for like
+        out["b200_coherent"] = run("synth_b200", steps_b200, {"ASS_RESIDENT": "0"})
+        out["b200_resident"] = run("synth_b200", steps_b200, {"ASS_RESIDENT": "1"})
+        try:
+            out["speedup_same_call"] = out["reference"]["integrate_s"] / out["b200_same_call"]["integrate_s"]
+            for k in ("b200_coherent", "b200_resident"):   # steady state: the t = 0 print amortised over the steps
+                out[k]["ms_per_step"] = 1e3 * (out[k]["integrate_s"] - out["b200_same_call"]["integrate_s"]) / max(out[k]["steps"] - 1, 1)
+            # the t = 0 print must agree: Etot column (22) of the history file
+            e_ref = float(out["reference"]["res_row"][22]); e_gpu = float(out["b200_same_call"]["res_row"][22])
+            out["etot_t0_rel_diff"] = abs(e_gpu - e_ref) / max(abs(e_ref), 1e-300)
+        except Exception as e:
+            out["note"] = "incomplete: %r" % e
+        for k in ("reference", "b200_same_call", "b200_coherent", "b200_resident"):
+            if isinstance(out.get(k), dict):
+                out[k].pop("res_row", None)
+        return out
+    finally:
+        shutil.rmtree(work, ignore_errors=True)
+
+
 _REAL_STDOUT = None
 
 
@@ -739,6 +815,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-sub", action="store_true", help="main record only (skip the c4_sharded / c5_ensemble sub-records)")
+    ap.add_argument("--no-dropin", action="store_true", help="skip the dropin_e2e record (one reference step: about a minute)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 

@@ -134,8 +134,10 @@ int ass_step(ass_sim* sim, int nsteps, int with_heartbeat);
 int ass_integrate(ass_sim* sim, double tmax);
 
 /* ---- per-step heartbeat helpers (src_spring/physics.cpp) ---- */
-/* How the mass-weighted sums behind compute_com / compute_cov (and everything built on them) are accumulated:
- * sequential != 0 (default): in the reference's particle order, one rounding per operation -> bit-identical CoM / CoV,
+/* How the mass-weighted sums behind compute_com / compute_cov (and everything built on them) are accumulated.  Until this
+ * is called the helpers below sum sequentially and the BUILT-IN per-step heartbeat of ass_step / ass_integrate uses the
+ * tree; a call fixes one order for both.
+ * sequential != 0 (default for the helpers): in the reference's particle order, one rounding per operation -> bit-identical CoM / CoV,
  *                            hence bit-identical subtract_com / subtract_cov / spin_body / center_sim results.  One CTA,
  *                            ~8 cycles per particle: meant for set-up, where an ulp of position changes rs0 bits.
  * sequential == 0:           fixed-order parallel tree; equal to rounding; for per-step heartbeats at large N. */
@@ -147,10 +149,37 @@ int ass_move_resolved(ass_sim* sim, const double dx[3], const double dv[3], int 
 int ass_compute_com(ass_sim* sim, int i_low, int i_high, double out[3]); /* physics.cpp:41-57 */
 int ass_compute_cov(ass_sim* sim, int i_low, int i_high, double out[3]); /* physics.cpp:60-74 */
 int ass_spin_body(ass_sim* sim, int i_low, int i_high, const double omega[3]); /* physics.cpp:184-210 */
+/* x <- R (x - c) + c, v <- R (v - u) + u for particles [i_low, i_high), R a row-major 3x3 matrix: about_com != 0 takes
+ * c, u = CoM, CoV of the range (rotate_body, physics.cpp:249-290), about_com == 0 the origin (rotate_origin :294-331,
+ * rotate_to_principal :334-385: the host composes R -- Euler matrices, eigenvectors -- the device applies it). */
+int ass_transform_body(ass_sim* sim, int i_low, int i_high, const double R[9], int about_com);
 /* out[20]: [0..2] CoM, [3..5] CoV, [6..8] L = measure_L (physics.cpp:136-162), [9] compute_rot_kin (:508-528),
  * [10] spring_potential_energy (:457-476), [11] grav_potential_energy (:479-504; 0 unless want_gpe),
  * [12] dEdt_total (:409-454), [13..18] mom_inertia xx yy zz xy xz yz (:116-134), [19] sum_mass (orb.cpp:438-449) */
 int ass_diagnostics(ass_sim* sim, int i_low, int i_high, int want_gpe, double out[20]);
+
+/* ---- stress (src_spring/stress.cpp) ---- */
+/* The first half of update_stress, stress.cpp:32-85: per node the sum of +outer(F, L) (node is particle_1) / -outer(F, L)
+ * (particle_2) over its springs in spring-index order, F = spring_i_force (springs.cpp:350-392), L = spring_r, divided
+ * by the node volume 4 pi / (3 N); and the strongest spring per node (first index of the largest |F|; -1: none).
+ * tensors: N x 9 row-major.  The eigenvalue stage (:88-97) is 3x3 host work and stays the caller's. */
+int ass_stress(ass_sim* sim, double* tensors, double* max_force, int* max_force_spring);
+
+/* ---- masked force terms of two modules' own additional_forces (module-local code, offered so that resident mode
+ *      covers them): node masks 0..3 live on the device ---- */
+int ass_set_node_mask(ass_sim* sim, int mask_id, const unsigned char* mask /* N bytes, non-zero = member */);
+/* mask = particles of [i_low, i_high) with coordinate `axis` > threshold (greater != 0) or < threshold; *count = members
+ * (modules/cube/problem.cpp:217-227, 247-257: the top / bottom faces, marked once) */
+int ass_mask_from_plane(ass_sim* sim, int mask_id, int i_low, int i_high, int axis, double threshold, int greater, int* count);
+/* apply_impact, modules/bennu2/problem.cpp:366-460 (force part): masked particles of [i_low, i_high) within angle
+ * `dangle` of the direction (lat, longi) get  a -= force * x_hat / (m * num_pushed * |x|) * envelope, num_pushed
+ * counted first; the caller passes envelope = 1 - cos(2 pi t / tau).  *num_pushed may be NULL (no host round trip). */
+int ass_apply_radial_impulse(ass_sim* sim, int mask_id, int i_low, int i_high, double lat, double longi, double dangle, double force,
+		double envelope, int* num_pushed);
+/* top_push, modules/cube/problem.cpp:230-234: a[axis] -= per_node_force / m for masked particles (per_node_force =
+ * pressure / N_surf);  table_top, :259-263: a[axis] = 0 for masked particles */
+int ass_plane_push(ass_sim* sim, int mask_id, int axis, double per_node_force);
+int ass_plane_constraint(ass_sim* sim, int mask_id, int axis);
 
 /* ---- the other per-step terms of the phobos / phobos_deimos modules (src_spring/orb.cpp) ---- */
 /* quadrupole_accel, orb.cpp:311-366: a += J2 acceleration from particle i_p (with params.G), reaction onto i_p.
@@ -184,6 +213,15 @@ void ass_free(void* p);
 int ass_rand_ellipsoid(double** rows, int* cap_rows, int n0, double min_dist, double a, double b, double c, double total_mass);
 int ass_hcp_ellipsoid(double** rows, int* cap_rows, int n0, double min_dist, double a, double b, double c, double total_mass);
 int ass_cubic_ellipsoid(double** rows, int* cap_rows, int n0, double min_dist, double a, double b, double c, double total_mass);
+/* rand_rectangle (shapes.cpp:66-128), rand_cone (:132-206), rand_shape (:435-516; rows [0, n0) hold the shape model's
+ * vertices).  They share one loop, also exported: n_candidates darts over the box [lo, hi] (x, y, z drawn in that order
+ * from libc rand()), kept if `inside` (NULL: always) accepts them and no particle made by this call is within min_dist. */
+typedef int (*ass_inside_fn)(void* ctx, double x, double y, double z);
+int ass_rand_fill(double** rows, int* cap_rows, int n0, long long n_candidates, const double lo[3], const double hi[3],
+		ass_inside_fn inside, void* ctx, double min_dist, double radius, double total_mass);
+int ass_rand_rectangle(double** rows, int* cap_rows, int n0, double min_dist, double x, double y, double z, double total_mass);
+int ass_rand_cone(double** rows, int* cap_rows, int n0, double min_dist, double radius, double height, double total_mass);
+int ass_rand_shape(double** rows, int* cap_rows, int n0, double min_dist, double total_mass);
 
 /* ---- ensembles: B independent small bodies, one CTA per body, no collective (BASELINE C5) ---- */
 typedef struct ass_ensemble ass_ensemble;

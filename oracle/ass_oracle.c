@@ -833,3 +833,204 @@ void orc_drift_bin(double* p, double G, double timestep, double inv_tau_a, doubl
 		P(part_2, ORC_VX + c) -= m2 * dv[c] / (m1 + m2);
 	}
 }
+
+/* ------------------------------------------------------------------------------------------------ */
+/* generator variants: literal restatements of shapes.cpp (one libc rand() stream, linear "too near" scan) */
+/* ------------------------------------------------------------------------------------------------ */
+typedef int (*inside_fn)(const void* ctx, const double* p, double x, double y, double z);
+
+static int rand_fill_n2(double** pp, int n0, int n_part, const double* lo, const double* hi, inside_fn inside, const void* ctx,
+		double min_dist, double radius, double total_mass) {
+	double* p = *pp;
+	int cap = n0, n = n0;
+	const int i_0 = n0;
+	for (int t = 0; t < n_part; t++) {
+		const double x = orc_random_uniform(lo[0], hi[0]);
+		const double y = orc_random_uniform(lo[1], hi[1]);
+		const double z = orc_random_uniform(lo[2], hi[2]);
+		if (inside && !inside(ctx, p, x, y, z)) continue;
+		int too_near = 0;
+		for (int j = i_0; !too_near && j < n; j++)
+			if (len3(x - P(j, ORC_X), y - P(j, ORC_Y), z - P(j, ORC_Z)) < min_dist) too_near = 1;
+		if (too_near) continue;
+		p = grow_rows(p, &cap, n + 1);
+		memset(&P(n, 0), 0, sizeof(double) * ORC_STRIDE);
+		P(n, ORC_X) = x; P(n, ORC_Y) = y; P(n, ORC_Z) = z;
+		P(n, ORC_M) = 1.0; P(n, ORC_R) = radius;
+		n++;
+	}
+	if (n > i_0) finish_masses(p, i_0, n, total_mass);
+	*pp = p;
+	return n;
+}
+
+int orc_rand_rectangle_n2(double** pp, int n0, double min_dist, double x, double y, double z, double total_mass) { /* shapes.cpp:66-128 */
+	const int n_part = 40.0 * x * y * z / pow(min_dist, 3.0);
+	const double lo[3] = { -x / 2, -y / 2, -z / 2 }, hi[3] = { x / 2, y / 2, z / 2 };
+	return rand_fill_n2(pp, n0, n_part, lo, hi, NULL, NULL, min_dist, (min_dist / 2.0) / 3.0, total_mass);
+}
+
+typedef struct { double radius, height, slope; } cone_t;
+static int in_cone(const void* ctx, const double* p, double x, double y, double z) { /* shapes.cpp:168-173, GNU C++: contracted */
+	(void) p;
+	const cone_t* c = (const cone_t*) ctx;
+	const double cur_rad = sqrt(fma(x, x, y * y));
+	const double max_height = fma(-cur_rad, c->slope, c->height);
+	return (cur_rad < c->radius) && (z < max_height);
+}
+int orc_rand_cone_n2(double** pp, int n0, double min_dist, double radius, double height, double total_mass) { /* shapes.cpp:132-206 */
+	cone_t c = { radius, height, height / radius };
+	const int n_part = 40 * pow(2.0 * radius / min_dist, 3.0);
+	const double lo[3] = { -radius, -radius, 0.0 }, hi[3] = { radius, radius, height };
+	return rand_fill_n2(pp, n0, n_part, lo, hi, in_cone, &c, min_dist, (min_dist / 2.0) / 2.0, total_mass);
+}
+
+typedef struct { int n_shape; double r_min, r_max; } shape_t;
+static int in_shape(const void* ctx, const double* p, double x, double y, double z) { /* within_shape + nearest_to_point, shapes.cpp:720-774 */
+	const shape_t* s = (const shape_t*) ctx;
+	const double rad = len3(x, y, z);
+	if (rad < s->r_min) return 1;
+	if (rad > s->r_max) return 0;
+	double dist = DBL_MAX;
+	int i_0 = -1;
+	for (int i = 0; i < s->n_shape; i++) {
+		const double r = len3(P(i, ORC_X) - x, P(i, ORC_Y) - y, P(i, ORC_Z) - z);
+		if (r < dist) { i_0 = i; dist = r; }
+	}
+	return !(rad > len3(P(i_0, ORC_X), P(i_0, ORC_Y), P(i_0, ORC_Z)));
+}
+int orc_rand_shape_n2(double** pp, int n0, double min_dist, double total_mass) { /* shapes.cpp:435-516 */
+	const double* p = *pp;
+	shape_t s = { n0, DBL_MAX, 0.0 };
+	for (int i = 0; i < n0; i++) { /* min_radius / max_radius, shapes.cpp:777-811 */
+		const double r = len3(P(i, ORC_X), P(i, ORC_Y), P(i, ORC_Z));
+		if (r < s.r_min) s.r_min = r;
+		if (r > s.r_max) s.r_max = r;
+	}
+	const int n_part = 40 * pow(2.0 * s.r_max / min_dist, 3.0);
+	const double lo[3] = { -s.r_max, -s.r_max, -s.r_max }, hi[3] = { s.r_max, s.r_max, s.r_max };
+	return rand_fill_n2(pp, n0, n_part, lo, hi, in_shape, &s, min_dist, min_dist / 4.0, total_mass);
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* set-up rotations, physics.cpp:249-331; Matrix arithmetic as gcc compiles matrix_math.cpp:442-450, 582-592 (res += a*b  */
+/* chains contracted into fused multiply-adds, the first product plain)                                                    */
+/* ------------------------------------------------------------------------------------------------ */
+static void mat_mul(const double* a, const double* b, double* out) {
+	for (int i = 0; i < 3; i++)
+		for (int j = 0; j < 3; j++) out[3 * i + j] = fma(a[3 * i + 2], b[6 + j], fma(a[3 * i + 1], b[3 + j], a[3 * i] * b[j]));
+}
+static void mat_vec(const double* a, const double* v, double* out) {
+	for (int i = 0; i < 3; i++) out[i] = fma(a[3 * i + 2], v[2], fma(a[3 * i + 1], v[1], a[3 * i] * v[0]));
+}
+void orc_euler_matrix(double alpha, double beta, double gamma, double* out9) {
+	const double Rz1[9] = { cos(alpha), -sin(alpha), 0, sin(alpha), cos(alpha), 0, 0, 0, 1 };
+	const double Rx[9] = { 1, 0, 0, 0, cos(beta), -sin(beta), 0, sin(beta), cos(beta) };
+	const double Rz2[9] = { cos(gamma), -sin(gamma), 0, sin(gamma), cos(gamma), 0, 0, 0, 1 };
+	double t[9];
+	mat_mul(Rz2, Rx, t);     /* Rz2 * Rx * Rz1 associates left to right (physics.cpp:274) */
+	mat_mul(t, Rz1, out9);
+}
+static void rotate_about(double* p, int i_low, int i_high, const double* R, const double* c, const double* u) {
+	for (int i = i_low; i < i_high; i++) {
+		const double x0[3] = { P(i, ORC_X) - c[0], P(i, ORC_Y) - c[1], P(i, ORC_Z) - c[2] };
+		const double v0[3] = { P(i, ORC_VX) - u[0], P(i, ORC_VY) - u[1], P(i, ORC_VZ) - u[2] };
+		double xr[3], vr[3];
+		mat_vec(R, x0, xr);
+		mat_vec(R, v0, vr);
+		P(i, ORC_X) = xr[0] + c[0]; P(i, ORC_Y) = xr[1] + c[1]; P(i, ORC_Z) = xr[2] + c[2];
+		P(i, ORC_VX) = vr[0] + u[0]; P(i, ORC_VY) = vr[1] + u[1]; P(i, ORC_VZ) = vr[2] + u[2];
+	}
+}
+void orc_rotate_body(double* p, int i_low, int i_high, double alpha, double beta, double gamma) { /* physics.cpp:249-290 */
+	double com[3], cov[3], R[9];
+	orc_compute_com(p, i_low, i_high, com);
+	orc_compute_cov(p, i_low, i_high, cov);
+	orc_euler_matrix(alpha, beta, gamma, R);
+	rotate_about(p, i_low, i_high, R, com, cov);
+}
+void orc_rotate_origin(double* p, int i_low, int i_high, double alpha, double beta, double gamma) { /* physics.cpp:294-331 */
+	double R[9];
+	const double zero[3] = { 0.0, 0.0, 0.0 };
+	orc_euler_matrix(alpha, beta, gamma, R);
+	for (int i = i_low; i < i_high; i++) { /* no centre: nothing is subtracted or added back */
+		const double x0[3] = { P(i, ORC_X), P(i, ORC_Y), P(i, ORC_Z) }, v0[3] = { P(i, ORC_VX), P(i, ORC_VY), P(i, ORC_VZ) };
+		double xr[3], vr[3];
+		mat_vec(R, x0, xr);
+		mat_vec(R, v0, vr);
+		P(i, ORC_X) = xr[0]; P(i, ORC_Y) = xr[1]; P(i, ORC_Z) = xr[2];
+		P(i, ORC_VX) = vr[0]; P(i, ORC_VY) = vr[1]; P(i, ORC_VZ) = vr[2];
+	}
+	(void) zero;
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* stress tensors, stress.cpp:32-85 with spring_i_force (springs.cpp:350-392)                         */
+/* ------------------------------------------------------------------------------------------------ */
+void orc_stress(const double* p, int n, const orc_spring* s, int ns, double* tensors, double* max_force, int* max_spring) {
+	for (int i = 0; i < n; i++) {
+		for (int q = 0; q < 9; q++) tensors[9 * (size_t) i + q] = 0.0;
+		max_force[i] = 0.0;
+		max_spring[i] = -1;
+	}
+	for (int k = 0; k < ns; k++) {
+		const int i = s[k].particle_1, j = s[k].particle_2;
+		const double L[3] = { P(i, ORC_X) - P(j, ORC_X), P(i, ORC_Y) - P(j, ORC_Y), P(i, ORC_Z) - P(j, ORC_Z) };
+		const double len = len3(L[0], L[1], L[2]);
+		const double hat[3] = { L[0] / len, L[1] / len, L[2] / len };
+		const double c = -s[k].k * (len - s[k].rs0);
+		double F[3] = { hat[0] * c, hat[1] * c, hat[2] * c };
+		if (s[k].gamma > 0.0) {
+			const double dv[3] = { P(i, ORC_VX) - P(j, ORC_VX), P(i, ORC_VY) - P(j, ORC_VY), P(i, ORC_VZ) - P(j, ORC_VZ) };
+			const double strain_rate = fma(dv[2], hat[2], fma(dv[0], hat[0], dv[1] * hat[1])) / len;
+			const double m_red = P(i, ORC_M) * P(j, ORC_M) / (P(i, ORC_M) + P(j, ORC_M));
+			const double g = s[k].gamma * m_red * strain_rate;
+			for (int a = 0; a < 3; a++) F[a] -= hat[a] * g;
+		}
+		for (int a = 0; a < 3; a++)
+			for (int b = 0; b < 3; b++) {
+				const double o = F[a] * L[b];
+				tensors[9 * (size_t) i + 3 * a + b] += o;
+				tensors[9 * (size_t) j + 3 * a + b] -= o;
+			}
+		const double F_mag = len3(F[0], F[1], F[2]);
+		if (F_mag > max_force[i]) { max_force[i] = F_mag; max_spring[i] = k; }
+		if (F_mag > max_force[j]) { max_force[j] = F_mag; max_spring[j] = k; }
+	}
+	const double vol = 4.0 * M_PI / (3.0 * (double) n);
+	for (int i = 0; i < n; i++)
+		for (int q = 0; q < 9; q++) tensors[9 * (size_t) i + q] /= vol;
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* module-local force terms                                                                          */
+/* ------------------------------------------------------------------------------------------------ */
+int orc_apply_impact(double* p, int n_body, const unsigned char* is_surf, double lat, double longi, double dangle, double force, double envelope) {
+	/* modules/bennu2/problem.cpp:386-447 without the display-radius bookkeeping; envelope = 1 - cos(2 pi t / tau) */
+	const double x0[3] = { cos(longi) * cos(lat), sin(longi) * cos(lat), sin(lat) };
+	int num_pushed = 0;
+	for (int pass = 0; pass < 2; pass++)
+		for (int i = 0; i < n_body; i++) {
+			if (!is_surf[i]) continue;
+			const double len = len3(P(i, ORC_X), P(i, ORC_Y), P(i, ORC_Z));
+			const double hat[3] = { P(i, ORC_X) / len, P(i, ORC_Y) / len, P(i, ORC_Z) / len };
+			const double projection = fma(x0[2], hat[2], fma(x0[0], hat[0], x0[1] * hat[1]));
+			if (!(acos(projection) < dangle)) continue;
+			if (pass == 0) { num_pushed++; continue; }
+			const double den = P(i, ORC_M) * num_pushed * len;
+			P(i, ORC_AX) -= hat[0] * force / den * envelope;
+			P(i, ORC_AY) -= hat[1] * force / den * envelope;
+			P(i, ORC_AZ) -= hat[2] * force / den * envelope;
+		}
+	return num_pushed;
+}
+void orc_top_push(double* p, int n, const unsigned char* top, double pressure) { /* modules/cube/problem.cpp:230-234 */
+	int n_surf = 0;
+	for (int i = 0; i < n; i++) n_surf += top[i] ? 1 : 0;
+	for (int i = 0; i < n; i++)
+		if (top[i]) P(i, ORC_AY) -= pressure / n_surf / P(i, ORC_M);
+}
+void orc_table_top(double* p, int n, const unsigned char* bottom) { /* modules/cube/problem.cpp:259-263 */
+	for (int i = 0; i < n; i++)
+		if (bottom[i]) P(i, ORC_AY) = 0.0;
+}

@@ -91,6 +91,26 @@ void orc_quadrupole_accel(double* p, int n, double G, double J2, double R, doubl
 void orc_drift_resolved(double* p, double G, double timestep, double inv_tau_a, double inv_tau_e, int i_part, int i_low, int i_high); /* orb.cpp:253-302 */
 void orc_drift_bin(double* p, double G, double timestep, double inv_tau_a, double inv_tau_e, int part_1, int part_2);                 /* orb.cpp:198-250 */
 
+/* ---- generator variants (shapes.cpp), literal O(candidates x N) restatements ---- */
+int orc_rand_rectangle_n2(double** p, int n0, double min_dist, double x, double y, double z, double total_mass);  /* shapes.cpp:66-128 */
+int orc_rand_cone_n2(double** p, int n0, double min_dist, double radius, double height, double total_mass);       /* shapes.cpp:132-206 */
+int orc_rand_shape_n2(double** p, int n0, double min_dist, double total_mass);                                    /* shapes.cpp:435-516; rows [0, n0) = vertices */
+
+/* ---- set-up rotations (physics.cpp:249-331) ---- */
+void orc_euler_matrix(double alpha, double beta, double gamma, double* out9);  /* getRotMatZ(gamma) * getRotMatX(beta) * getRotMatZ(alpha) */
+void orc_rotate_body(double* p, int i_low, int i_high, double alpha, double beta, double gamma);
+void orc_rotate_origin(double* p, int i_low, int i_high, double alpha, double beta, double gamma);
+
+/* ---- stress (stress.cpp:32-85): tensors n x 9, max_force n, max_spring n ---- */
+void orc_stress(const double* p, int n, const orc_spring* s, int ns, double* tensors, double* max_force, int* max_spring);
+
+/* ---- module-local per-step force terms (not library symbols): restated from the two modules that define them ---- */
+/* apply_impact, modules/bennu2/problem.cpp:366-460 (force part); is_surf: n bytes; returns num_pushed */
+int orc_apply_impact(double* p, int n_body, const unsigned char* is_surf, double lat, double longi, double dangle, double force, double envelope);
+/* top_push / table_top, modules/cube/problem.cpp:205-264, with the faces already marked */
+void orc_top_push(double* p, int n, const unsigned char* top, double pressure);
+void orc_table_top(double* p, int n, const unsigned char* bottom);
+
 #ifdef __cplusplus
 }
 #endif

@@ -166,6 +166,62 @@ class Oracle:
     def cubic_ellipsoid(self, min_dist, a, b, c, total_mass, existing=None):
         return self._gen(self.lib.orc_cubic_ellipsoid, min_dist, a, b, c, total_mass, existing)
 
+    def rand_rectangle(self, min_dist, x, y, z, total_mass, existing=None):
+        return self._gen(self.lib.orc_rand_rectangle_n2, min_dist, x, y, z, total_mass, existing)
+
+    def _gen_n(self, fn, args, existing=None):
+        self.libc.malloc.restype = C.c_void_p
+        n0 = 0 if existing is None else len(existing)
+        ptr = C.c_void_p(None)
+        if n0:
+            existing = np.ascontiguousarray(existing, dtype=np.float64)
+            ptr = C.c_void_p(self.libc.malloc(C.c_size_t(existing.nbytes)))
+            C.memmove(ptr, existing.ctypes.data, existing.nbytes)
+        n = fn(C.byref(ptr), C.c_int(n0), *[C.c_double(a) for a in args])
+        assert n >= 0
+        out = np.empty((n, STRIDE), dtype=np.float64)
+        if n:
+            C.memmove(out.ctypes.data, ptr, out.nbytes)
+        if ptr.value:
+            self.lib.orc_free(ptr)
+        return out
+
+    def rand_cone(self, min_dist, radius, height, total_mass):
+        return self._gen_n(self.lib.orc_rand_cone_n2, (min_dist, radius, height, total_mass))
+
+    def rand_shape(self, vertices, min_dist, total_mass):
+        return self._gen_n(self.lib.orc_rand_shape_n2, (min_dist, total_mass), vertices)
+
+    def euler_matrix(self, alpha, beta, gamma):
+        out = (C.c_double * 9)()
+        self.lib.orc_euler_matrix(C.c_double(alpha), C.c_double(beta), C.c_double(gamma), out)
+        return np.array(out[:])
+
+    def rotate_body(self, p, lo, hi, alpha, beta, gamma):
+        self.lib.orc_rotate_body(self._p(p), C.c_int(lo), C.c_int(hi), C.c_double(alpha), C.c_double(beta), C.c_double(gamma))
+
+    def rotate_origin(self, p, lo, hi, alpha, beta, gamma):
+        self.lib.orc_rotate_origin(self._p(p), C.c_int(lo), C.c_int(hi), C.c_double(alpha), C.c_double(beta), C.c_double(gamma))
+
+    def stress(self, p, s):
+        n = len(p)
+        T = np.zeros((n, 9)); F = np.zeros(n); S = np.zeros(n, dtype=np.int32)
+        self.lib.orc_stress(self._p(p), C.c_int(n), self._s(s), C.c_int(len(s)), T.ctypes.data_as(C.c_void_p), F.ctypes.data_as(C.c_void_p), S.ctypes.data_as(C.c_void_p))
+        return T.reshape(n, 3, 3), F, S
+
+    def apply_impact(self, p, n_body, is_surf, lat, longi, dangle, force, envelope):
+        m = np.ascontiguousarray(is_surf, dtype=np.uint8)
+        return self.lib.orc_apply_impact(self._p(p), C.c_int(n_body), m.ctypes.data_as(C.c_void_p), C.c_double(lat), C.c_double(longi), C.c_double(dangle),
+                                         C.c_double(force), C.c_double(envelope))
+
+    def top_push(self, p, top, pressure):
+        m = np.ascontiguousarray(top, dtype=np.uint8)
+        self.lib.orc_top_push(self._p(p), C.c_int(len(p)), m.ctypes.data_as(C.c_void_p), C.c_double(pressure))
+
+    def table_top(self, p, bottom):
+        m = np.ascontiguousarray(bottom, dtype=np.uint8)
+        self.lib.orc_table_top(self._p(p), C.c_int(len(p)), m.ctypes.data_as(C.c_void_p))
+
     def mindist(self, p, lo=0, hi=None, n2=False):
         hi = len(p) if hi is None else hi
         fn = self.lib.orc_mindist_n2 if n2 else self.lib.orc_mindist
@@ -262,6 +318,36 @@ class Ref:
 
     def cubic_ellipsoid(self, d, a, b, c, M):
         return self.lib.ref_cubic_ellipsoid(self.h, C.c_double(d), C.c_double(a), C.c_double(b), C.c_double(c), C.c_double(M))
+
+    def stress(self):
+        """(N x 3 x 3 tensors, max_force, max_force_spring, threw) of update_stress (stress.cpp:32-98)."""
+        n = self.n
+        T = np.zeros((n, 9)); F = np.zeros(n); S = np.zeros(n, dtype=np.int32)
+        threw = self.lib.ref_stress(self.h, T.ctypes.data_as(C.c_void_p), F.ctypes.data_as(C.c_void_p), S.ctypes.data_as(C.c_void_p))
+        return T.reshape(n, 3, 3), F, S, int(threw)
+
+    def rand_rectangle(self, d, x, y, z, M):
+        return self.lib.ref_rand_rectangle(self.h, C.c_double(d), C.c_double(x), C.c_double(y), C.c_double(z), C.c_double(M))
+
+    def rand_cone(self, d, radius, height, M):
+        return self.lib.ref_rand_cone(self.h, C.c_double(d), C.c_double(radius), C.c_double(height), C.c_double(M))
+
+    def rand_shape(self, d, M):
+        return self.lib.ref_rand_shape(self.h, C.c_double(d), C.c_double(M))
+
+    def rotate_body(self, lo, hi, alpha, beta, gamma):
+        self.lib.ref_rotate_body(self.h, C.c_int(lo), C.c_int(hi), C.c_double(alpha), C.c_double(beta), C.c_double(gamma))
+
+    def rotate_origin(self, lo, hi, alpha, beta, gamma):
+        self.lib.ref_rotate_origin(self.h, C.c_int(lo), C.c_int(hi), C.c_double(alpha), C.c_double(beta), C.c_double(gamma))
+
+    def rotate_to_principal(self, lo, hi):
+        self.lib.ref_rotate_to_principal(self.h, C.c_int(lo), C.c_int(hi))
+
+    def euler_matrix(self, alpha, beta, gamma):
+        out = (C.c_double * 9)()
+        self.lib.ref_euler_matrix(C.c_double(alpha), C.c_double(beta), C.c_double(gamma), out)
+        return np.array(out[:])
 
     def mindist(self, lo, hi):
         return self.lib.ref_mindist(self.h, C.c_int(lo), C.c_int(hi))

@@ -117,6 +117,18 @@ int ref_cubic_ellipsoid(void* h, double min_dist, double a, double b, double c, 
 	cubic_ellipsoid((reb_simulation*) h, min_dist, a, b, c, total_mass);
 	return ((reb_simulation*) h)->N;
 }
+int ref_rand_rectangle(void* h, double min_dist, double x, double y, double z, double total_mass) {
+	rand_rectangle((reb_simulation*) h, min_dist, x, y, z, total_mass);   // shapes.cpp:66-128
+	return ((reb_simulation*) h)->N;
+}
+int ref_rand_cone(void* h, double min_dist, double radius, double height, double total_mass) {
+	rand_cone((reb_simulation*) h, min_dist, radius, height, total_mass);   // shapes.cpp:132-206
+	return ((reb_simulation*) h)->N;
+}
+int ref_rand_shape(void* h, double min_dist, double total_mass) {
+	rand_shape((reb_simulation*) h, min_dist, total_mass);   // shapes.cpp:435-516; the vertices are the particles already added
+	return ((reb_simulation*) h)->N;
+}
 double ref_mindist(void* h, int lo, int hi) { return mindist((reb_simulation*) h, lo, hi); }
 
 int ref_add_particle(void* h, const double* p /* x y z vx vy vz ax ay az m r */) {
@@ -202,6 +214,20 @@ void ref_move_resolved(void* h, const double* dx, const double* dv, int lo, int 
 void ref_spin_body(void* h, int lo, int hi, double ox, double oy, double oz) {
 	spin_body((reb_simulation*) h, lo, hi, Vector({ ox, oy, oz }));
 }
+void ref_rotate_body(void* h, int lo, int hi, double alpha, double beta, double gamma) {
+	rotate_body((reb_simulation*) h, lo, hi, alpha, beta, gamma);   // physics.cpp:249-290
+}
+void ref_rotate_origin(void* h, int lo, int hi, double alpha, double beta, double gamma) {
+	rotate_origin((reb_simulation*) h, lo, hi, alpha, beta, gamma);   // physics.cpp:294-331
+}
+void ref_rotate_to_principal(void* h, int lo, int hi) { rotate_to_principal((reb_simulation*) h, lo, hi); }   // physics.cpp:334-385
+// the matrix rotate_body / rotate_origin apply (Rz2 * Rx * Rz1, left to right), row-major
+void ref_euler_matrix(double alpha, double beta, double gamma, double* out9) {
+	Matrix R = getRotMatZ(gamma) * getRotMatX(beta) * getRotMatZ(alpha);
+	out9[0] = R.getXX(); out9[1] = R.getXY(); out9[2] = R.getXZ();
+	out9[3] = R.getYX(); out9[4] = R.getYY(); out9[5] = R.getYZ();
+	out9[6] = R.getZX(); out9[7] = R.getZY(); out9[8] = R.getZZ();
+}
 // out[0..2] CoM, [3..5] CoV, [6..8] L (measure_L), [9] KE (compute_rot_kin), [10] SPE,
 // [11] GPE (only if want_gpe, else 0), [12] dEdt_total, [13..18] I xx yy zz xy xz yz, [19] sum_mass
 void ref_diagnostics(void* h, int lo, int hi, int want_gpe, double* out) {
@@ -248,6 +274,31 @@ int ref_update_stress(void* h, double* out) {
 		out[4 * i + 3] = stresses[i].max_force;
 	}
 	return 0;
+}
+
+// The per-node stress tensors (stress.cpp:32-85: sum of +-outer(F, L) over the node's springs, divided by the node
+// volume) and the strongest spring per node, whether or not the eigenvalue stage that follows them threw.
+// tensors: N x 9 row-major; returns 1 if update_stress threw.
+int ref_stress(void* h, double* tensors, double* max_force, int* max_spring) {
+	reb_simulation* r = (reb_simulation*) h;
+	extern std::vector<stress_tensor> stresses;
+	stresses.clear();
+	int threw = 0;
+	try {
+		update_stress(r);
+	} catch (const char*) {
+		threw = 1;
+	}
+	for (int i = 0; i < r->N; i++) {
+		const Matrix& m = stresses[i].stress;
+		double* t = tensors + 9 * (size_t) i;
+		t[0] = m.getXX(); t[1] = m.getXY(); t[2] = m.getXZ();
+		t[3] = m.getYX(); t[4] = m.getYY(); t[5] = m.getYZ();
+		t[6] = m.getZX(); t[7] = m.getZY(); t[8] = m.getZZ();
+		max_force[i] = stresses[i].max_force;
+		max_spring[i] = stresses[i].max_force_spring;
+	}
+	return threw;
 }
 
 }  // extern "C"

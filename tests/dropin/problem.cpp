@@ -12,6 +12,7 @@
 #define restrict __restrict__
 #endif
 
+#include <chrono>
 #include <cmath>
 #include <cstdlib>
 #include <fstream>
@@ -31,6 +32,7 @@ extern "C" {
 #include "kepcart.h"
 #include "orb.h"
 #include "input_spring.h"
+#include "output_spring.h"
 
 using namespace libconfig;
 using std::string;
@@ -47,6 +49,11 @@ double mass_scale, time_scale, length_scale, temp_scale, omega_scale, vel_scale,
 int use_gravity = 0;
 // phobos / phobos_deimos shape (modules/phobos_deimos/problem.cpp): one central point mass with a J2, migration drift
 int point_mass = 0;
+int shape = 0;   // 0 rand_ellipsoid, 1 hcp_ellipsoid, 2 cubic_ellipsoid, 3 rand_rectangle, 4 rand_cone
+int restart_index = -1;  // >= 0: read <restart_root>_<index>_particles.txt / _springs.txt (modules/asteroid_spin/problem.cpp:104-118)
+string restart_root;
+int stress = 0;  // 1: update_stress after the run, tensors written to <fileroot>_stress.txt
+int rotate = 0;  // 1: rotate_body + rotate_to_principal between spin-up and the run (modules/wobble_bennu2/problem.cpp:300-312)
 double J2_plus = 1.96e-3, R_plus = 0.5, theta_plus = 0.4, phi_plus = 0.3, inv_tau_a = 1e-2, inv_tau_e = 3e-2;
 
 void additional_forces(reb_simulation *n_body_sim);
@@ -72,6 +79,11 @@ int main(int argc, char *argv[]) {
 	cfg.lookupValue("seed", seed);
 	cfg.lookupValue("gravity", use_gravity);
 	cfg.lookupValue("point_mass", point_mass);
+	cfg.lookupValue("shape", shape);
+	cfg.lookupValue("rotate", rotate);
+	cfg.lookupValue("stress", stress);
+	cfg.lookupValue("restart_index", restart_index);
+	cfg.lookupValue("restart_root", restart_root);
 	Vector omega(omega_in);
 
 	reb_simulation *const n_body_sim = reb_create_simulation();
@@ -91,12 +103,29 @@ int main(int argc, char *argv[]) {
 	default_spring.gamma = gamma_fac * def_gamma;
 	default_spring.k = k;
 
-	rand_ellipsoid(n_body_sim, min_dist, r_ball, r_ball * ratio1, r_ball * ratio2, mass_ball);
+	if (restart_index >= 0) {
+		// asteroid_spin's restart path: a body and its springs from the reference's own text dumps
+		read_particles(n_body_sim, restart_root, restart_index);
+		read_springs(restart_root, restart_index);
+	} else
+	switch (shape) {
+	case 1: hcp_ellipsoid(n_body_sim, min_dist, r_ball, r_ball * ratio1, r_ball * ratio2, mass_ball); break;
+	case 2: cubic_ellipsoid(n_body_sim, min_dist, r_ball, r_ball * ratio1, r_ball * ratio2, mass_ball); break;
+	case 3: rand_rectangle(n_body_sim, min_dist, 2.0 * r_ball, 2.0 * r_ball * ratio1, 2.0 * r_ball * ratio2, mass_ball); break;  // modules/cube
+	case 4: rand_cone(n_body_sim, min_dist, r_ball, 1.5 * r_ball, mass_ball); break;
+	default: rand_ellipsoid(n_body_sim, min_dist, r_ball, r_ball * ratio1, r_ball * ratio2, mass_ball);
+	}
 	const int i_low = 0, i_high = n_body_sim->N;
-	subtract_com(n_body_sim, i_low, i_high);
-	subtract_cov(n_body_sim, i_low, i_high);
-	spin_body(n_body_sim, i_low, i_high, omega);
-	connect_springs_dist(n_body_sim, max_spring_dist, i_low, i_high, default_spring);
+	if (restart_index < 0) {
+		subtract_com(n_body_sim, i_low, i_high);
+		subtract_cov(n_body_sim, i_low, i_high);
+		spin_body(n_body_sim, i_low, i_high, omega);
+		connect_springs_dist(n_body_sim, max_spring_dist, i_low, i_high, default_spring);
+	}
+	if (rotate) {
+		rotate_body(n_body_sim, i_low, i_high, 0.3, -0.2, 1.1);
+		rotate_to_principal(n_body_sim, i_low, i_high);
+	}
 	if (point_mass) {
 		// modules/phobos_deimos/problem.cpp:246-262: a Mars-like mass on a slightly eccentric, inclined orbit about the body
 		OrbitalElements orb_el;
@@ -106,15 +135,20 @@ int main(int argc, char *argv[]) {
 	}
 
 	std::ofstream runfile(fileroot + "_run.txt", std::ios::out | std::ios::trunc);
-	runfile << std::hexfloat << "N " << n_body_sim->N << "\nNS " << num_springs << "\nmean_rs0 " << mean_spring_length()
-			<< "\nmindist " << mindist(n_body_sim, i_low, i_high) << "\n";
-	for (int i = 0; i < num_springs; i++)
-		runfile << springs[i].particle_1 << " " << springs[i].particle_2 << " " << springs[i].rs0 << "\n";
+	runfile << std::hexfloat << "N " << n_body_sim->N << "\nNS " << num_springs << "\nmean_rs0 " << mean_spring_length() << "\n";
+	if (restart_index < 0) {  // (the reference's mindist is O(N^2): not on a body of restart size)
+		runfile << "mindist " << mindist(n_body_sim, i_low, i_high) << "\n";
+		for (int i = 0; i < num_springs; i++)
+			runfile << springs[i].particle_1 << " " << springs[i].particle_2 << " " << springs[i].rs0 << "\n";
+	}
 	runfile.close();
 	std::ofstream(fileroot + "_ext.txt", std::ios::out | std::ios::trunc).close();
 
 	if (t_max == 0.0) t_max = INFINITY;
+	const auto wall0 = std::chrono::steady_clock::now();
 	reb_integrate(n_body_sim, t_max);
+	const double wall_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - wall0).count();
+	std::ofstream(fileroot + "_timing.txt", std::ios::out | std::ios::trunc) << "integrate_s " << wall_s << "\nN " << n_body_sim->N << "\nt " << n_body_sim->t << "\n";
 
 	std::ofstream fin(fileroot + "_final.txt", std::ios::out | std::ios::trunc);
 	fin << std::hexfloat << "t " << n_body_sim->t << "\ndt " << n_body_sim->dt << "\nstatus " << n_body_sim->status << "\n";
@@ -122,6 +156,25 @@ int main(int argc, char *argv[]) {
 		const reb_particle &p = n_body_sim->particles[i];
 		fin << p.x << " " << p.y << " " << p.z << " " << p.vx << " " << p.vy << " " << p.vz << " " << p.ax << " " << p.ay
 				<< " " << p.az << " " << p.m << "\n";
+	}
+	if (stress) {
+		// update_stress (stress.cpp:32-98) throws out of its eigenvalue stage on any real body (a tensor summed in floating
+		// point is not EXACTLY symmetric, matrix_math.cpp:273-276); the tensors themselves are complete by then
+		extern vector<stress_tensor> stresses;
+		int threw = 0;
+		try {
+			update_stress(n_body_sim);
+		} catch (const char *) {
+			threw = 1;
+		}
+		std::ofstream sf(fileroot + "_stress.txt", std::ios::out | std::ios::trunc);
+		sf << std::hexfloat << "threw " << threw << "\n";
+		for (int i = 0; i < n_body_sim->N; i++) {
+			const Matrix &m = stresses[i].stress;
+			sf << m.getXX() << " " << m.getXY() << " " << m.getXZ() << " " << m.getYX() << " " << m.getYY() << " " << m.getYZ() << " "
+					<< m.getZX() << " " << m.getZY() << " " << m.getZZ() << " " << stresses[i].max_force << " " << stresses[i].max_force_spring
+					<< "\n";
+		}
 	}
 	return 0;
 }
@@ -155,5 +208,8 @@ void heartbeat(reb_simulation *const n_body_sim) {
 		std::ofstream out(extendedfile, std::ios::out | std::ios::app);
 		out << std::setprecision(17) << n_body_sim->t << " " << L.getX() << " " << L.getY() << " " << L.getZ() << " " << KE
 				<< " " << SPE << " " << GPE << " " << dEdt_total(n_body_sim) << "\n";
+		// the module's own history file, through the reference's writer (output_spring.cpp:112-192): t, CoM, CoV, omega, L, I,
+		// KErot, PEspr, PEgrav, Etot, dE/dt -- every number of it comes from a function the drop-in replaces
+		write_resolved_with_E(n_body_sim, i_low, i_high, fileroot + "_res.txt", 0.0);
 	}
 }

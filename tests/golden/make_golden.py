@@ -189,6 +189,75 @@ def orb():
     print("orb", {k: v.shape for k, v in out.items()})
 
 
+def shape_vertices():
+    """A deterministic closed surface of 162 vertices: a lumpy ellipsoid (what a .tab shape model is to rand_shape)."""
+    v = []
+    for i in range(9):
+        th = np.pi * (i + 0.5) / 9
+        for j in range(18):
+            ph = 2 * np.pi * j / 18
+            rr = 1.0 + 0.15 * np.sin(3 * th) * np.cos(2 * ph)
+            v.append((rr * 1.0 * np.sin(th) * np.cos(ph), rr * 0.8 * np.sin(th) * np.sin(ph), rr * 0.6 * np.cos(th)))
+    P = np.zeros((len(v), 11))
+    P[:, :3] = np.array(v)
+    P[:, 9] = 1.0
+    return P
+
+
+def extras():
+    """Generator variants (shapes.cpp:66-206, 435-516) and the set-up rotations (physics.cpp:249-385), run by the reference."""
+    out = {}
+    with Ref() as r:
+        r.seed(SEED)
+        r.rand_rectangle(0.2, 2.0, 1.4, 1.0, 1.0)
+        out["rect"] = r.get()
+    with Ref() as r:
+        r.seed(SEED)
+        r.rand_cone(0.2, 1.0, 1.5, 1.0)
+        out["cone"] = r.get()
+    V = shape_vertices()
+    out["shape_vertices"] = V
+    with Ref() as r:
+        r.add_particles(V)
+        r.seed(SEED)
+        r.rand_shape(0.2, 1.0)
+        out["shape"] = r.get()
+    g = np.load(os.path.join(HERE, "ellipsoid_d015.npz"))
+    start = g["start"]
+    n = len(start)
+    with Ref() as r:
+        r.add_particles(start)
+        r.rotate_body(0, n, 0.3, -0.2, 1.1)
+        out["rot_body"] = r.get()
+        r.rotate_origin(0, n, -0.7, 0.4, 0.25)
+        out["rot_origin"] = r.get()
+        r.rotate_to_principal(0, n)
+        out["rot_principal"] = r.get()
+        out["euler"] = r.euler_matrix(0.3, -0.2, 1.1)
+        out["euler2"] = r.euler_matrix(-0.7, 0.4, 0.25)
+    # the stress tensor of every node (stress.cpp:32-85) on a real body: update_stress itself throws in its eigenvalue
+    # stage there (SURVEY), the tensors and the strongest spring per node are complete by then
+    with Ref() as r:
+        r.add_particles(start)
+        r.set_springs(g["springs"])
+        T, F, S, threw = r.stress()
+        out["stress"] = T; out["stress_max_force"] = F; out["stress_max_spring"] = S; out["stress_threw"] = np.array([threw])
+    # StressTest's fixture (modules/tests/tests.cpp:1452-1644): 3 particles, zero velocities, particle 0 moved to (1,1,4)
+    P = np.zeros((3, 11))
+    P[0, :3] = (0, 0, 0); P[1, :3] = (1, 2, 2); P[2, :3] = (2, 3, 6)
+    P[:, 9] = (1, 2, 3)
+    with Ref() as r:
+        r.add_particles(P)
+        r.connect_springs_dist(100.0, 0, 3, 11.0, 35.0)
+        Q = r.get(); Q[0, :3] = (1, 1, 4); r.set(Q)
+        out["kat_stress_in"] = r.get()
+        out["kat_stress_springs"] = r.springs()
+        T, F, S, threw = r.stress()
+        out["kat_stress"] = T; out["kat_stress_max_force"] = F; out["kat_stress_max_spring"] = S; out["kat_stress_threw"] = np.array([threw])
+    np.savez_compressed(os.path.join(HERE, "extras.npz"), **out)
+    print("extras", {k: v.shape for k, v in out.items()})
+
+
 def c2():
     """BASELINE config C2: d = 0.0474 -> N = 9327, NS = 134162.  ~90 s of reference time (its O(N^2) paths)."""
     d = 0.0474
@@ -214,5 +283,6 @@ if __name__ == "__main__":
     body("ellipsoid_d015", 0.15, 20, 200, 10)
     body("c1_d010", 0.10, 20, 200, 20)
     orb()
+    extras()
     if "--c2" in sys.argv:
         c2()

@@ -27,11 +27,14 @@ def build():
         pytest.skip("tests/dropin/_build not built and /root/reference absent")
 
 
-def run(binary, workdir, gravity, env_extra=None, expect_ok=True, point_mass=0):
+def run(binary, workdir, gravity, env_extra=None, expect_ok=True, point_mass=0, shape=0, rotate=0, stress=0):
     os.makedirs(workdir, exist_ok=True)
     cfg = open(os.path.join(DROPIN, "problem.cfg")).read()
     cfg = re.sub(r"gravity = \d;", "gravity = %d;" % gravity, cfg)
     cfg = re.sub(r"point_mass = \d;", "point_mass = %d;" % point_mass, cfg)
+    cfg = re.sub(r"shape = \d;", "shape = %d;" % shape, cfg)
+    cfg = re.sub(r"rotate = \d;", "rotate = %d;" % rotate, cfg)
+    cfg = re.sub(r"stress = \d;", "stress = %d;" % stress, cfg)
     open(os.path.join(workdir, "problem.cfg"), "w").write(cfg)
     env = dict(os.environ)
     env.update(env_extra or {})
@@ -50,6 +53,40 @@ def parse(workdir):
     return run_lines, ext, head, state
 
 
+def parse_res(workdir):
+    """<fileroot>_res.txt as written by the reference's write_resolved_with_E (output_spring.cpp:112-192): 25 columns of
+    width 14.  A value that needs more than 13 characters (rounding noise such as 1.348378703e-32 in the power column at
+    t = 0) runs into its neighbour -- in the reference's own output too -- so rows that do not split into 25 numbers are
+    returned as NaN rows."""
+    rows = []
+    for ln in open(os.path.join(workdir, "synth_res.txt")):
+        if ln.startswith("#") or not ln.strip():
+            continue
+        tok = ln.split()
+        try:
+            rows.append([float(x) for x in tok] if len(tok) == 25 else [float(tok[0])] + [np.nan] * 24)
+        except ValueError:
+            rows.append([np.nan] * 25)
+    return np.array(rows, ndmin=2)
+
+
+def compare_res(g, r):
+    """Printed with 4-10 significant digits: equal to within a unit of the last printed digit, quantities that are zero
+    up to rounding (the centred body's CoM / CoV columns) to an absolute bar."""
+    assert g.shape == r.shape and r.shape[1] == 25
+    ok = ~(np.isnan(g).any(axis=1) | np.isnan(r).any(axis=1))
+    assert ok.sum() >= max(1, len(r) // 2), "too few rows of the history file could be parsed"
+    g, r = g[ok], r[ok]
+    assert np.array_equal(g[:, 0], r[:, 0])
+    scale = np.maximum(np.abs(r), 1e-12)
+    rel = np.abs(g - r) / scale
+    big = np.abs(r) > 1e-9
+    assert np.all(rel[big] <= 2e-4), rel[big].max()           # the coarsest columns carry 4 digits
+    assert np.all(np.abs(g[~big]) <= 1e-9)
+    # the energy columns carry 10 digits: KErot + PEspr + PEgrav == Etot as printed by both
+    assert np.all(np.abs(g[:, 22] - r[:, 22]) <= 1e-8 * np.maximum(np.abs(r[:, 22]), 1e-30))
+
+
 def test_module_links_both_ways_and_reference_runs(tmp_path):
     build()
     run("synth_ref", str(tmp_path / "ref"), 1)
@@ -63,6 +100,30 @@ def test_module_links_both_ways_and_reference_runs(tmp_path):
               "_Z16quadrupole_accelP14reb_simulationddddi", "_Z14drift_resolvedP14reb_simulationdddiii", "_Z9drift_binP14reb_simulationdddii",
               "_Z8sum_massP14reb_simulationii"):
         assert re.search(r" T %s$" % re.escape(s), syms, re.M), s
+    # ... and, demangled, everything set-up code and write_resolved_with_E reach for
+    dem = subprocess.run(["nm", "-C", "--defined-only", os.path.join(BUILD, "dropin.o")], stdout=subprocess.PIPE, text=True).stdout
+    for name in ("spin_body(", "measure_L(", "mom_inertia(", "body_spin(", "compute_rot_kin(", "spring_potential_energy(", "grav_potential_energy(",
+                 "dEdt_total(", "rotate_body(", "rotate_origin(", "rotate_to_principal(", "hcp_ellipsoid(", "cubic_ellipsoid(", "rand_rectangle(",
+                 "rand_cone(", "rand_shape(", "update_stress("):
+        assert re.search(r" T %s" % re.escape(name), dem), name
+
+
+def test_every_reference_module_links_against_the_dropin():
+    """'Modules compile unchanged': each shipped modules/<name>/problem.cpp, compiled where it lies, links against the
+    drop-in plus the reference objects whose same-named symbols were weakened."""
+    if not HAVE_REF:
+        pytest.skip("/root/reference absent")
+    build()
+    subprocess.check_call(["make", "-s", "-C", DROPIN, "-j8", "modules"])
+    names = sorted(d for d in os.listdir("/root/reference/modules")
+                   if d != "tests" and os.path.exists(os.path.join("/root/reference/modules", d, "problem.cpp")))
+    assert len(names) == 12, names
+    for nm_ in names:
+        path = os.path.join(BUILD, "mod_%s_b200" % nm_)
+        assert os.path.exists(path), nm_
+        syms = subprocess.run(["nm", "--defined-only", path], stdout=subprocess.PIPE, text=True).stdout
+        # the step loop and the force routine are the drop-in's strong definitions, the reference's are weak (W) or gone
+        assert re.search(r" T reb_integrate$", syms, re.M) and re.search(r" T _Z13spring_forcesP14reb_simulation$", syms, re.M), nm_
 
 
 def test_dropin_fails_loudly_without_a_gpu(tmp_path):
@@ -100,6 +161,35 @@ def test_dropin_matches_reference(tmp_path, gravity, resident):
     e_g = g_ext[:, 4] + g_ext[:, 5] + g_ext[:, 6]
     assert np.all(np.abs(e_g - e_r) <= 1e-9 * np.abs(e_r))
     assert np.abs(g_ext[:, 1:4] - r_ext[:, 1:4]).max() <= 1e-9 * np.abs(r_ext[:, 1:4]).max()
+    # the module's own history file, through the reference's writer on top of the drop-in's diagnostics
+    compare_res(parse_res(gpu_dir), parse_res(ref_dir))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [1, 2, 3, 4])
+def test_dropin_other_shapes_rotations_and_stress(tmp_path, shape):
+    """hcp / cubic lattices, the cube module's box, a cone; rotate_body + rotate_to_principal after the springs are
+    connected; update_stress after the run.  Generator output and spring list bit-exact, the rest to the usual bars;
+    the stress tensors are the reference's bits."""
+    build()
+    ref_dir, gpu_dir = str(tmp_path / "ref"), str(tmp_path / "b200")
+    run("synth_ref", ref_dir, 1, shape=shape, rotate=1, stress=1)
+    run("synth_b200", gpu_dir, 1, {"ASS_RESIDENT": "1"}, shape=shape, rotate=1, stress=1)
+    r_run, r_ext, r_head, r_state = parse(ref_dir)
+    g_run, g_ext, g_head, g_state = parse(gpu_dir)
+    assert g_run == r_run and g_head == r_head
+    amax = np.abs(r_state[:, 6:9]).max()
+    assert np.abs(g_state[:, 6:9] - r_state[:, 6:9]).max() <= 1e-10 * amax
+    assert np.allclose(g_state[:, :6], r_state[:, :6], rtol=0, atol=1e-12)
+    compare_res(parse_res(gpu_dir), parse_res(ref_dir))
+    # stress: both threw (or neither); tensors of the final state agree to rounding of that state
+    rs = open(os.path.join(ref_dir, "synth_stress.txt")).read().split("\n")
+    gs = open(os.path.join(gpu_dir, "synth_stress.txt")).read().split("\n")
+    assert rs[0] == gs[0] and len(rs) == len(gs)
+    R = np.array([[float.fromhex(x) for x in ln.split()[:10]] for ln in rs[1:] if ln.strip()])
+    G = np.array([[float.fromhex(x) for x in ln.split()[:10]] for ln in gs[1:] if ln.strip()])
+    assert np.abs(G - R).max() <= 1e-9 * np.abs(R).max()
+    assert [ln.split()[10] for ln in rs[1:] if ln.strip()] == [ln.split()[10] for ln in gs[1:] if ln.strip()]
 
 
 @pytest.mark.gpu
