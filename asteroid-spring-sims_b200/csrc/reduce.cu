@@ -114,6 +114,39 @@ __global__ void __launch_bounds__(256) k_moment_seq(const vec4d* __restrict__ po
 	if (threadIdx.x == 3) out[3] = tot[3];
 }
 
+// mom_inertia (physics.cpp:116-134) summed in the reference's particle order, one rounding per operation:
+//     inertia += m * pow(|dx|, 2) * I ;  inertia -= m * outer(dx, dx)        (dx = x - CoM)
+// i.e. per particle  I_aa = (I_aa + m |dx|^2) - (dx_a dx_a) m  and  I_ab = I_ab - (dx_a dx_b) m.  Same staging as
+// k_moment_seq: all threads prepare a chunk, six threads run the six dependent chains (xx yy zz xy xz yz).  For set-up:
+// rotate_to_principal takes eigenvectors of this tensor, and their signs hang on its last bits.
+__global__ void __launch_bounds__(256) k_inertia_seq(const vec4d* __restrict__ posm, int lo, int hi, const double* __restrict__ com, double* __restrict__ out6) {
+	__shared__ double sub[6][SEQ_CHUNK / 2];  // what is subtracted: (dx_a dx_b) m
+	__shared__ double add[SEQ_CHUNK / 2];     // what the diagonal gains first: m |dx|^2
+	double acc = 0.0;
+	const double cx = com[0], cy = com[1], cz = com[2];
+	const int t = threadIdx.x;
+	const int ia[6] = { 0, 1, 2, 0, 0, 1 }, ib[6] = { 0, 1, 2, 1, 2, 2 };
+	for (int base = lo; base < hi; base += SEQ_CHUNK / 2) {
+		const int cnt = min(SEQ_CHUNK / 2, hi - base);
+		for (int k = t; k < cnt; k += blockDim.x) {
+			const vec4d p = posm[base + k];
+			const double d[3] = { __dsub_rn(p.x, cx), __dsub_rn(p.y, cy), __dsub_rn(p.z, cz) };
+			const double len = ref_len(d[0], d[1], d[2]);
+			add[k] = __dmul_rn(p.w, __dmul_rn(len, len));  // m * pow(len, 2.0): pow(x, 2) is the correctly rounded square
+#pragma unroll
+			for (int q = 0; q < 6; q++) sub[q][k] = __dmul_rn(__dmul_rn(d[ia[q]], d[ib[q]]), p.w);
+		}
+		__syncthreads();
+		if (t < 6) {
+			const double* sb = sub[t];
+			if (t < 3) for (int k = 0; k < cnt; k++) acc = __dsub_rn(__dadd_rn(acc, add[k]), sb[k]);
+			else for (int k = 0; k < cnt; k++) acc = __dsub_rn(acc, sb[k]);  // (+ m |dx|^2 * 0 leaves an off-diagonal sum unchanged)
+		}
+		__syncthreads();
+	}
+	if (t < 6) out6[t] = acc;
+}
+
 // out[0..2] = sums / mass ; out[3] = mass
 __global__ void k_fold_com(const double* __restrict__ part, int nblk, double* __restrict__ out) {
 	__shared__ double sm[4];
@@ -454,6 +487,10 @@ extern "C" int ass_diagnostics(ass_sim* s, int lo, int hi, int want_gpe, double 
 	LAUNCH_CHECK();
 	k_fold<10><<<1, RB, 0, s->stream>>>(part, grid, d + 8);
 	LAUNCH_CHECK();
+	if (s->sum_sequential) {  // set-up: the inertia tensor in the reference's order (its eigenvectors feed rotate_to_principal)
+		k_inertia_seq<<<1, 256, 0, s->stream>>>(s->posm, lo, hi, d, d + 12);
+		LAUNCH_CHECK();
+	}
 	if (s->ns > 0) {
 		const int g2 = reduce_grid(s->n);
 		k_spring_diag<<<g2, RB, 0, s->stream>>>(s->posm, s->vel, s->order, s->row_ptr, s->he, s->pal, s->n, part);

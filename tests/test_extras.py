@@ -163,3 +163,24 @@ def test_masked_force_terms_match_oracle(gpu, oracle, body015):
         s.plane_constraint(2, 1)
         out = s.download(q.copy())
     assert same_bits(out, want)
+
+
+@pytest.mark.gpu
+def test_inertia_tensor_in_reference_order_is_bit_exact(gpu, body015, kat3):
+    """Set-up mode (sequential sums, the default outside the step loop): mom_inertia carries the reference's bits, so the
+    eigenvectors rotate_to_principal takes from it -- whose signs hang on the last bits of a nearly diagonal tensor --
+    are the reference's.  The tree order agrees to rounding."""
+    start = body015["start"]
+    n = len(start)
+    want = body015["hist_none"][0]            # ref_diagnostics of the same state: [13..18] = I xx yy zz xy xz yz
+    with gpu.Sim() as s:
+        s.upload(start)
+        d = s.diagnostics(0, n)
+        assert same_bits(d[13:19], want[13:19])
+        s.set_sum_order(False)
+        t = s.diagnostics(0, n)
+        assert np.allclose(t[13:19], want[13:19], rtol=1e-13, atol=1e-16) 
+    P = kat3["force_in"].copy(); P[:, 6:9] = 0
+    with gpu.Sim() as s:
+        s.upload(P)
+        assert same_bits(s.diagnostics(0, 3)[13:19], kat3["diag_g1"][13:19])
