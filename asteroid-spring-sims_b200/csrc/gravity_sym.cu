@@ -33,9 +33,16 @@
 
 namespace {
 
+#ifndef ASS_SYM_RESIDENTS
+#define ASS_SYM_RESIDENTS 4
+#endif
+#ifndef ASS_SYM_CTAS_PER_SM
+#define ASS_SYM_CTAS_PER_SM 2
+#endif
 constexpr int SG_T = 256;            // threads per CTA
 constexpr int SG_W = SG_T / 32;      // warps
-constexpr int SG_R = 4;              // resident particles per thread
+constexpr int SG_R = ASS_SYM_RESIDENTS;  // resident particles per thread (4 with 2 CTAs per SM; 3 with 3 was measured: profiles/r2_gravity_variants.md)
+constexpr int SG_OCC = ASS_SYM_CTAS_PER_SM;
 constexpr int SG_P = SG_T * SG_R;    // particles per block (1024)
 constexpr int SG_TILE = 128;         // streamed particles between block-wide reductions (4 chunks of 32)
 
@@ -137,7 +144,7 @@ __device__ __forceinline__ void meet(const double2 xy, const double2 zm, int sid
 // range and the tiles are its lower triangle incl. the diagonal; rect != 0: the ranges are disjoint (two slabs of a
 // sharded body) and the tiles are the full rectangle, nsb streamed blocks wide.
 template <bool UNI>
-__global__ void __launch_bounds__(SG_T, 2) k_gravity_sym(const vec4d* __restrict__ posm, int rlo, int rhi, int slo, int shi, int rect, int nsb,
+__global__ void __launch_bounds__(SG_T, SG_OCC) k_gravity_sym(const vec4d* __restrict__ posm, int rlo, int rhi, int slo, int shi, int rect, int nsb,
 		const SymCta* __restrict__ ctas, double soft2, double* __restrict__ res, size_t res_plane, double* __restrict__ str, size_t str_plane) {
 	__shared__ double2 s_xy[SG_TILE], s_zm[SG_TILE];
 	__shared__ double s_acc[SG_W][3][SG_TILE];
@@ -345,7 +352,7 @@ static int get_plan(ass_sim* s, int rlo, int rhi, int slo, int shi, SymPlan** ou
 	plan->nrb = nrb; plan->nsb = nsb;
 	const long long tiles = plan->rect ? (long long) nrb * nsb : (long long) nrb * (nrb + 1) / 2;
 	// tiles per CTA: enough CTAs (>= ~16 per resident slot) for the block scheduler to balance, few enough rows
-	const long long slots = 2LL * ass_sm_count();
+	const long long slots = (long long) SG_OCC * ass_sm_count();
 	int U = (int) std::max(1LL, tiles / (slots * 16));
 	// few tiles (N ~ 1e4): cut every tile's streamed side into `cut` pieces so that ~2 CTAs per slot exist
 	int cut = 1;

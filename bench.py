@@ -274,7 +274,11 @@ def parity_of_sim(A, dist, sim, p0, springs, cfg, n_perts, rank, world, bounds):
                 u.step(1); w2 = u.download(p0.copy())
             amax = float(np.abs(w1[:, 6:9]).max())
             res["acc_own_slab_vs_1gpu"] = float(np.abs(out1[lo:hi, 6:9] - w1[lo:hi, 6:9]).max() / max(amax, 1e-300))
-            res["xv_vs_1gpu_max_abs"] = float(np.abs(out2[:, :6] - w2[:, :6]).max())
+            dev = np.abs(out2[:, :6] - w2[:, :6])
+            worst = np.unravel_index(int(np.argmax(dev)), dev.shape)
+            res["xv_vs_1gpu_max_abs"] = float(dev.max())
+            res["xv_worst"] = {"particle": int(worst[0]), "column": "x y z vx vy vz".split()[int(worst[1])], "value_1gpu": float(w2[worst]),
+                               "body_max_abs": float(dev[:n - n_perts].max()) if n > n_perts else None}
             res["xv_tol"] = POS_TOL
         checks = [res.get("acc_vs_oracle") is not None and res["acc_vs_oracle"] <= ACC_TOL]
         if sharded:
