@@ -735,9 +735,10 @@ def run_dropin_e2e(p0, springs, cfg, steps_b200=50):
             d = os.path.join(work, binary + "_" + env_extra.get("ASS_RESIDENT", "x"))
             os.makedirs(d, exist_ok=True)
             c = base
-            for key, val in (("dt", "%.17g" % cfg["dt"]), ("t_max", "%.17g" % (nsteps * cfg["dt"])), ("print_interval", "1e9"),
-                             ("min_particle_distance", "%.17g" % cfg["d"]), ("max_spring_dist", "%.17g" % (2.3 * cfg["d"])),
-                             ("k", "%.17g" % K_SPRING), ("gamma", "%.17g" % GAMMA), ("damp_fac", "1.0"), ("t_damp", "1e9"),
+            fl = lambda x: repr(float(x))   # libconfig reads "5" as an int and refuses it to a double lookup: always "5.0"
+            for key, val in (("dt", fl(cfg["dt"])), ("t_max", fl(nsteps * cfg["dt"])), ("print_interval", "1.0e9"),
+                             ("min_particle_distance", fl(cfg["d"])), ("max_spring_dist", fl(2.3 * cfg["d"])),
+                             ("k", fl(K_SPRING)), ("gamma", fl(GAMMA)), ("damp_fac", "1.0"), ("t_damp", "1.0e9"),
                              ("gravity", "%d" % cfg["gravity"]), ("restart_index", "0")):
                 c = __import__("re").sub(r"(?m)^%s = [^;]*;" % key, "%s = %s;" % (key, val), c)
             c = c.replace('restart_root = "";', 'restart_root = "%s";' % os.path.join(work, "body"))
