@@ -244,6 +244,12 @@ class Sim:
     def step(self, nsteps=1, heartbeat=False):
         _chk(lib().ass_step(self._h, C.c_int(nsteps), C.c_int(int(heartbeat))))
 
+    def step_timed(self, nsteps=1, heartbeat=False):
+        """ass_step with an L2 flush before and a device-timed lap around every step; returns the sum of the laps in ms."""
+        ms = C.c_double()
+        _chk(lib().ass_step_timed(self._h, C.c_int(nsteps), C.c_int(int(heartbeat)), C.byref(ms)))
+        return ms.value
+
     def integrate(self, tmax):
         return _chk(lib().ass_integrate(self._h, C.c_double(tmax)))
 

@@ -197,6 +197,7 @@ struct ass_sim {
 	cudaEvent_t mark0 = nullptr, mark1 = nullptr;
 	std::vector<std::pair<cudaEvent_t, cudaEvent_t>> lap_ev;  // ass_lap_begin / ass_lap_end
 	int lap_open = 0;
+	bool lap_flush = false;  // ass_step_timed: flush L2 and lap every step of the fused loop
 
 	ShardInfo shard;
 };

@@ -178,6 +178,9 @@ static int step_loop(ass_sim* s, int nsteps, bool with_hb) {
 	for (int step = 0; step < nsteps; step++) {
 		const double dt = s->prm.dt;
 		const bool last = (step == nsteps - 1);
+		if (s->lap_flush) {  // measurement only (ass_step_timed): cold L2 for every step, the flush outside the lap
+			if ((rc = ass_l2_flush(s)) || (rc = ass_lap_begin(s))) return rc;
+		}
 		if (!s->predrifted) {
 			if ((rc = have_springs ? ass_launch_part1_mirrored(s, dt) : ass_launch_part1(s, dt))) return rc;
 			mirror_fresh = have_springs;
@@ -212,6 +215,7 @@ static int step_loop(ass_sim* s, int nsteps, bool with_hb) {
 			s->predrifted = !last;
 			mirror_fresh = false;
 		}
+		if (s->lap_flush && (rc = ass_lap_end(s))) return rc;
 	}
 	return ASS_OK;
 }
@@ -221,6 +225,26 @@ extern "C" int ass_step(ass_sim* s, int nsteps, int with_heartbeat) {
 	REQUIRE(nsteps >= 0, ASS_EINVAL, "negative step count");
 	REQUIRE(!s->shard.active, ASS_ESTATE, "sharded simulations step through ass_leapfrog_part1 / ass_shard_publish / ... (host-driven)");
 	return step_loop(s, nsteps, with_heartbeat != 0);
+}
+
+// ass_step as the product runs it -- the fused loop, positions pre-drifted from one step into the next, nothing between
+// the steps on the host -- but measured step by step: before every step the L2 is overwritten, and a pair of events
+// brackets the step's own kernels (the flush stays outside).  Returns the sum of the laps.  For bench.py: a body whose
+// working set fits in L2 has to be flushed between timed iterations, and doing that from the host would put a
+// synchronisation and the launch latency of a cold queue into every step.
+extern "C" int ass_step_timed(ass_sim* s, int nsteps, int with_heartbeat, double* device_ms) {
+	ENTER(s);
+	REQUIRE(nsteps >= 0 && device_ms, ASS_EINVAL, "bad argument");
+	REQUIRE(!s->shard.active, ASS_ESTATE, "sharded simulations are timed by the caller around ass_shard_step");
+	double dummy;
+	int laps = 0;
+	int rc = ass_lap_collect(s, &dummy, &laps);  // drop laps somebody left open
+	if (rc) return rc;
+	s->lap_flush = true;
+	rc = step_loop(s, nsteps, with_heartbeat != 0);
+	s->lap_flush = false;
+	if (rc) return rc;
+	return ass_lap_collect(s, device_ms, &laps);
 }
 
 // reb_check_exit, src/rebound.c:509-569, for the leapfrog case (reb_integrator_synchronize is a no-op for leapfrog,

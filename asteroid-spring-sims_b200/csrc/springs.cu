@@ -42,7 +42,8 @@ __global__ void k_mirror(const vec4d* __restrict__ posm, const vec4d* __restrict
 // step's part1) -- the epilogue shared by both kernels below; executed by one lane.
 template <bool KICK>
 __device__ __forceinline__ void finish_node(const Force3 F, const bool has_springs, vec4d a, const NodeState& ni, const int node, const int k,
-		vec4d* __restrict__ acc, vec4d* __restrict__ posm_out, vec4d* __restrict__ vel_out, const SpringMirror out, const double dt, const int pre_drift_next) {
+		vec4d* __restrict__ acc, vec4d* __restrict__ posm_out, vec4d* __restrict__ vel_out, const SpringMirror out, const double dt, const int pre_drift_next,
+		const bool write_state = true) {
 	// a node without springs (e.g. a point-mass perturber, possibly massless) is left untouched
 	const double inv_m = has_springs ? fast_rcp(ni.m) : 0.0;
 	a.x = fma(F.x, inv_m, a.x);
@@ -70,8 +71,10 @@ __device__ __forceinline__ void finish_node(const Force3 F, const bool has_sprin
 			out.zv[k] = make_double2(p.z, v.z);
 			out.vxy[k] = make_double2(v.x, v.y);
 		}
-		vel_out[node] = v;
-		posm_out[node] = p;
+		if (write_state) {  // (the persistent multi-step kernel keeps intermediate steps in the mirror only)
+			vel_out[node] = v;
+			posm_out[node] = p;
+		}
 	}
 }
 
@@ -152,14 +155,13 @@ struct TilesParams {
 };
 static_assert(sizeof(TilesParams) <= 8192, "per-CTA heads travel as kernel parameters");
 
+// One pass of a CTA over its tiles: the body of both kernels below.
 template <bool ZERO_FIRST, bool KICK, bool UNI, bool PAL1>
-__global__ void __launch_bounds__(TL_THREADS, 1) k_spring_tiles(const __grid_constant__ TilesParams heads, const GlobalNodes mir, vec4d* __restrict__ acc,
+__device__ __forceinline__ void tiles_pass(const CtaHead& H, unsigned char* tile_smem, int* s_next, const GlobalNodes mir, vec4d* __restrict__ acc,
 		const TileDesc* __restrict__ tiles, const int* __restrict__ tab, const int4* __restrict__ grpT, const int* __restrict__ warp_off,
-		const HalfEdge* __restrict__ heL, const double2* __restrict__ palf, int cap, int max_slices, vec4d* __restrict__ posm_out,
-		vec4d* __restrict__ vel_out, const SpringMirror out, double dt, int pre_drift_next) {
-	extern __shared__ __align__(128) unsigned char tile_smem[];  // [table: xy | zv | vxy | m, cap slots each][headers: groups | record offsets]
-	__shared__ int s_next;
-	double2* s_xy = (double2*) tile_smem;
+		const HalfEdge* __restrict__ heL, const double2* __restrict__ palf, const double2 nkg1, int cap, int max_slices, vec4d* __restrict__ posm_out,
+		vec4d* __restrict__ vel_out, const SpringMirror out, double dt, int pre_drift_next, bool write_state) {
+	double2* s_xy = (double2*) tile_smem;  // [table: xy | zv | vxy | m, cap slots each][headers: groups | record offsets]
 	double2* s_zv = s_xy + cap;
 	double2* s_vxy = s_zv + cap;
 	double* s_m = (double*) (s_vxy + cap);
@@ -167,9 +169,6 @@ __global__ void __launch_bounds__(TL_THREADS, 1) k_spring_tiles(const __grid_con
 	int* s_off = (int*) (s_grp + (size_t) max_slices * GPW);  // max_slices + 1
 	const SharedNodes nodes{ s_xy, s_zv, s_vxy, s_m };
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, sub = lane & (SPRING_LANES - 1);
-	const CtaHead& H = heads.h[blockIdx.x];
-	double2 nkg1 = make_double2(0.0, 0.0);
-	if (PAL1) nkg1 = __ldg(palf);
 	for (int t = H.tile0; t < H.tile0 + H.ntiles; t++) {
 		const TileDesc T = (t == H.tile0) ? H.first : tiles[t];
 		const int n_sl = T.s1 - T.s0;
@@ -209,13 +208,13 @@ __global__ void __launch_bounds__(TL_THREADS, 1) k_spring_tiles(const __grid_con
 		}
 		for (int i = tid; i < n_sl * GPW; i += TL_THREADS) s_grp[i] = __ldg(grpT + (size_t) T.s0 * GPW + i);
 		for (int i = tid; i <= n_sl; i += TL_THREADS) s_off[i] = __ldg(warp_off + T.s0 + i);
-		if (tid == 0) s_next = TL_WARPS;
+		if (tid == 0) *s_next = TL_WARPS;
 		__syncthreads();
 		while (sw < n_sl) {
 			// the slice after this one: taken from the counter now, so its header and first records are on their way
 			// long before this slice's last pair
 			int nx = 0;
-			if (lane == 0) nx = atomicAdd(&s_next, 1);
+			if (lane == 0) nx = atomicAdd(s_next, 1);
 			nx = __shfl_sync(0xffffffffu, nx, 0);
 			const bool live = gi.x >= 0;
 			const int slot = live ? gi.x : 0;
@@ -235,9 +234,61 @@ __global__ void __launch_bounds__(TL_THREADS, 1) k_spring_tiles(const __grid_con
 			}
 			const Force3 F = lane_spring_sum_x<UNI, PAL1, TL_CHAINS>((const int4*) heL + off + lane, P, nt, ni, nodes, palf, nkg1, r0, r1,
 					P_n > 0 ? (const int4*) heL + off_n + lane : nullptr);
-			if (live && sub == 0) finish_node<KICK>(F, gi.z > 0, a_old, ni, gi.w, gi.y, acc, posm_out, vel_out, out, dt, pre_drift_next);
+			if (live && sub == 0) finish_node<KICK>(F, gi.z > 0, a_old, ni, gi.w, gi.y, acc, posm_out, vel_out, out, dt, pre_drift_next, write_state);
 			sw = nx; gi = gi_n; off = off_n; P = P_n;
 		}
+	}
+}
+
+template <bool ZERO_FIRST, bool KICK, bool UNI, bool PAL1>
+__global__ void __launch_bounds__(TL_THREADS, 1) k_spring_tiles(const __grid_constant__ TilesParams heads, const GlobalNodes mir, vec4d* __restrict__ acc,
+		const TileDesc* __restrict__ tiles, const int* __restrict__ tab, const int4* __restrict__ grpT, const int* __restrict__ warp_off,
+		const HalfEdge* __restrict__ heL, const double2* __restrict__ palf, int cap, int max_slices, vec4d* __restrict__ posm_out,
+		vec4d* __restrict__ vel_out, const SpringMirror out, double dt, int pre_drift_next) {
+	extern __shared__ __align__(128) unsigned char tile_smem[];
+	__shared__ int s_next;
+	double2 nkg1 = make_double2(0.0, 0.0);
+	if (PAL1) nkg1 = __ldg(palf);
+	tiles_pass<ZERO_FIRST, KICK, UNI, PAL1>(heads.h[blockIdx.x], tile_smem, &s_next, mir, acc, tiles, tab, grpT, warp_off, heL, palf, nkg1, cap, max_slices,
+			posm_out, vel_out, out, dt, pre_drift_next, true);
+}
+
+// The persistent multi-step form for bodies without a force term between the spring evaluations (REB_GRAVITY_NONE, or
+// zero_accel right after gravity: every shipped module): nsteps x [springs + kick + drift + next half-drift] in ONE
+// launch, the CTAs meeting at a grid-wide barrier after every step.  The state of the intermediate steps lives in the two
+// rank-ordered mirrors only (step s reads mirror s & 1 and writes the other one); posm / vel are written by the last step.
+// A launch, the parameter fetch and the cold chain tile table -> mirror cost ~8 us per evaluation (12 us of a 1k-node
+// body's step are this fixed part); here they are paid once per batch.  Launched cooperatively (all CTAs resident: the
+// barrier spins).  bar: a zeroed counter; arrival s of a CTA waits for (s + 1) * gridDim.x.
+__device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned target) {
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		__threadfence();  // this CTA's mirror / acc writes before its arrival
+		atomicAdd(bar, 1u);
+		unsigned v;
+		do {
+			asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
+		} while (v < target);
+	}
+	__syncthreads();
+}
+
+template <bool ZERO_FIRST, bool UNI, bool PAL1>
+__global__ void __launch_bounds__(TL_THREADS, 1) k_spring_steps(const __grid_constant__ TilesParams heads, const GlobalNodes mirA, const GlobalNodes mirB,
+		vec4d* __restrict__ acc, const TileDesc* __restrict__ tiles, const int* __restrict__ tab, const int4* __restrict__ grpT,
+		const int* __restrict__ warp_off, const HalfEdge* __restrict__ heL, const double2* __restrict__ palf, int cap, int max_slices,
+		vec4d* __restrict__ posm_out, vec4d* __restrict__ vel_out, double dt, int nsteps, unsigned* __restrict__ bar) {
+	extern __shared__ __align__(128) unsigned char tile_smem[];
+	__shared__ int s_next;
+	double2 nkg1 = make_double2(0.0, 0.0);
+	if (PAL1) nkg1 = __ldg(palf);
+	const SpringMirror outA{ (double2*) mirA.xy, (double2*) mirA.zv, (double2*) mirA.vxy }, outB{ (double2*) mirB.xy, (double2*) mirB.zv, (double2*) mirB.vxy };
+	for (int step = 0; step < nsteps; step++) {
+		const bool last = step == nsteps - 1;
+		const bool even = (step & 1) == 0;
+		tiles_pass<ZERO_FIRST, true, UNI, PAL1>(heads.h[blockIdx.x], tile_smem, &s_next, even ? mirA : mirB, acc, tiles, tab, grpT, warp_off, heL, palf, nkg1,
+				cap, max_slices, posm_out, vel_out, even ? outB : outA, dt, last ? 0 : 1, last);
+		if (!last) grid_barrier(bar, (unsigned) (step + 1) * gridDim.x);
 	}
 }
 

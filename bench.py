@@ -305,12 +305,9 @@ def run_single(args, A, name, cfg, local, want_e2e=True, want_cpu=True, steps=No
     launches0 = A.launch_count()
     sim.sync()
     t_wall0 = time.perf_counter()
-    dev_ms = 0.0
-    for _ in range(steps):
-        sim.l2_flush()
-        sim.mark_begin()
-        sim.step(1)
-        dev_ms += sim.mark_end()
+    # the fused loop as the product runs it (pre-drifted from step to step, the host queues the batch and waits once), the L2
+    # overwritten before every step and a device-timed lap around every step's own kernels
+    dev_ms = sim.step_timed(steps)
     sim.sync()
     t_wall = time.perf_counter() - t_wall0
     clk = clocks.stop()
@@ -345,8 +342,18 @@ def run_single(args, A, name, cfg, local, want_e2e=True, want_cpu=True, steps=No
     parity = parity_of_sim(A, None, sim, p0, springs, cfg, n_perts, 0, 1, None)
     dropin = None
     if want_e2e and not args.no_e2e and not args.no_dropin and name == "C3":
+        # One reb_integrate of the unmodified reference at C3 size takes ~5.5 minutes (its write_resolved_with_E alone spends
+        # ~4 of them in grav_potential_energy): the default run times the drop-in against the reference on the C2 body
+        # (N = 9 327, same code path, ~10 s) and `--dropin-c3` on the body of the main record
+        # (profiles/r2_dropin_e2e_c3.json holds that measurement: 334.7 s against 1.24 s for the same call).
         try:
-            dropin = run_dropin_e2e(p0, springs, cfg)
+            if args.dropin_c3:
+                dropin = run_dropin_e2e(p0, springs, cfg, label="C3")
+            else:
+                cfg2 = dict(WORKLOADS["C2"])
+                sim2, p2, sp2, _ = build_body(A, cfg2, cfg2["omega"])
+                sim2.close()
+                dropin = run_dropin_e2e(p2, sp2, cfg2, steps_b200=200, label="C2")
         except Exception as e:
             dropin = {"error": repr(e)}
 
@@ -707,7 +714,7 @@ def run_reference(args, rank, world):
 # ---------------------------------------------------------------------------------------------------
 # the drop-in itself: ONE module source linked against the reference and against the drop-in (tests/dropin)
 # ---------------------------------------------------------------------------------------------------
-def run_dropin_e2e(p0, springs, cfg, steps_b200=50):
+def run_dropin_e2e(p0, springs, cfg, steps_b200=50, label=""):
     """Wall time of reb_integrate inside tests/dropin/_build/synth_ref (the unmodified reference, serial as shipped) and
     synth_b200 (the same module source on the drop-in) on the body of the main record, read from the reference's own
     restart files (modules/asteroid_spin's path: read_particles / read_springs).  One print at t = 0 (write_resolved_with_E
@@ -752,8 +759,8 @@ def run_dropin_e2e(p0, springs, cfg, steps_b200=50):
                 return {"error": pr.stdout[-400:]}
             tm = dict(ln.split() for ln in open(os.path.join(d, "synth_timing.txt")).read().strip().split("\n"))
             return {"steps": nsteps, "integrate_s": float(tm["integrate_s"]), "process_wall_s": wall,
-                    "res_row": open(os.path.join(d, "synth_res.txt")).read().strip().split("\n")[-1].split()}
-        out = {"body": {"N": int(n), "NS": int(ns)}, "what": "reb_integrate of tests/dropin/problem.cpp: heartbeat print at t = 0 (write_resolved_with_E incl. grav_potential_energy) + the steps"}
+                    "res_row": open(os.path.join(d, "synth_res.txt")).read().rstrip("\n").split("\n")[1]}
+        out = {"body": {"N": int(n), "NS": int(ns), "workload": label}, "what": "reb_integrate of tests/dropin/problem.cpp: heartbeat print at t = 0 (write_resolved_with_E incl. grav_potential_energy) + the steps"}
         out["reference"] = run("synth_ref", 1, {})
         out["b200_same_call"] = run("synth_b200", 1, {"ASS_RESIDENT": "1"})       # the reference's call, like for like
         out["b200_coherent"] = run("synth_b200", steps_b200, {"ASS_RESIDENT": "0"})
@@ -763,7 +770,8 @@ def run_dropin_e2e(p0, springs, cfg, steps_b200=50):
             for k in ("b200_coherent", "b200_resident"):   # steady state: the t = 0 print amortised over the steps
                 out[k]["ms_per_step"] = 1e3 * (out[k]["integrate_s"] - out["b200_same_call"]["integrate_s"]) / max(out[k]["steps"] - 1, 1)
             # the t = 0 print must agree: Etot column (22) of the history file
-            e_ref = float(out["reference"]["res_row"][22]); e_gpu = float(out["b200_same_call"]["res_row"][22])
+            # (columns are 14 wide; the power column after Etot overflows its width and runs into it: cut by position)
+            e_ref = float(out["reference"]["res_row"][14 * 22:14 * 23]); e_gpu = float(out["b200_same_call"]["res_row"][14 * 22:14 * 23])
             out["etot_t0_rel_diff"] = abs(e_gpu - e_ref) / max(abs(e_ref), 1e-300)
         except Exception as e:
             out["note"] = "incomplete: %r" % e
@@ -820,7 +828,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-sub", action="store_true", help="main record only (skip the c4_sharded / c5_ensemble sub-records)")
-    ap.add_argument("--no-dropin", action="store_true", help="skip the dropin_e2e record (one reference step: about a minute)")
+    ap.add_argument("--no-dropin", action="store_true", help="skip the dropin_e2e record")
+    ap.add_argument("--dropin-c3", action="store_true", help="time the drop-in against the reference on the C3 body (the reference needs ~5.5 minutes)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 

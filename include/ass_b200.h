@@ -283,6 +283,9 @@ int ass_lap_begin(ass_sim* sim);
 int ass_lap_end(ass_sim* sim);
 int ass_lap_collect(ass_sim* sim, double* total_ms, int* laps);
 int ass_l2_flush(ass_sim* sim);                    /* overwrite a buffer larger than L2 */
+/* ass_step, measured: the same fused loop, with the L2 overwritten before every step and a lap around every step's own
+ * kernels (the flush outside); *device_ms = sum of the laps.  The host queues the whole batch and waits once. */
+int ass_step_timed(ass_sim* sim, int nsteps, int with_heartbeat, double* device_ms);
 /* DFMA-only microbenchmark: the FP64 roofline denominator (MEASURED_PEAKS.json has none). iters ~ 1<<14. */
 int ass_probe_fp64_peak(int iters, double* tflops, double* ms);
 /* device copy bandwidth (read+write bytes / time) for a buffer of `bytes` */
