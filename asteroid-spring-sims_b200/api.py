@@ -131,6 +131,11 @@ def selfcheck_sqrt(samples=1 << 28, exp_lo=-200, exp_hi=200):
     return bad.value, first.value
 
 
+def spring_lanes():
+    """Lanes sharing one node's row in the spring kernels; a slice of the lane-transposed list holds 32 // lanes nodes."""
+    return int(lib().ass_spring_lanes())
+
+
 def selfcheck_spring_layout(p, springs, grid=148, slots=1 << 20):
     """Host-only check of what ass_set_springs builds (ranking, CSR and lane-transposed half-edge copies, tile cut for
     `grid` CTAs with tables of at most `slots` entries); needs no GPU.  Returns a dict of counts; 'violations' must be 0."""

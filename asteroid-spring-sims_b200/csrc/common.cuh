@@ -37,10 +37,10 @@ static_assert(sizeof(ass_spring) == 32, "ass_spring must match struct spring (32
 #define ASS_L_EPS 1e-6  // src_spring/springs.cpp:28
 #define ASS_LEN2_TINY 1e-280  // squared spring lengths at or below this count as coincident endpoints (spring_math.cuh)
 #ifndef ASS_SPRING_LANES
-#define ASS_SPRING_LANES 4
+#define ASS_SPRING_LANES 2
 #endif
-constexpr int SPRING_LANES = ASS_SPRING_LANES;  // lanes cooperating on one node's half-edge list (2, 4 or 8)
-static_assert(SPRING_LANES == 2 || SPRING_LANES == 4 || SPRING_LANES == 8, "SPRING_LANES must be 2, 4 or 8");
+constexpr int SPRING_LANES = ASS_SPRING_LANES;  // lanes cooperating on one node's half-edge list (1, 2, 4 or 8)
+static_assert(SPRING_LANES == 1 || SPRING_LANES == 2 || SPRING_LANES == 4 || SPRING_LANES == 8, "SPRING_LANES must be 1, 2, 4 or 8");
 #define ASS_MAX_MASKS 4
 #define ASS_SORT_BLOCK 256  // ranks per block inside which nodes are dealt to lane groups by degree (ass_sim::grp)
 
@@ -167,6 +167,7 @@ struct ass_sim {
 	int4* tile_desc = nullptr;  // (first slice, end slice, offset into tile_tab, slots)
 	std::vector<int> tile_heads;  // per CTA: (first tile, tile count, first tile's descriptor, last slice): kernel parameters
 	int tiles_grid = 0, tile_slots_max = 0, tile_slices_max = 0;
+	size_t tile_bytes_max = 0;  // shared memory of the largest tile (table + slice headers)
 	size_t heL_cap = 0, grpT_cap = 0, tile_tab_cap = 0, tile_desc_cap = 0;
 	double2* pal = nullptr;   // palette of distinct (k, gamma) pairs
 	double2* palf = nullptr;  // the same entries as the force kernels want them: (-k, -max(gamma, 0)); lives behind pal
@@ -309,6 +310,30 @@ __device__ __forceinline__ double rsqrt_cubed(double a) {
 	const double q = eps * fma(1.875, eps, 1.5);
 	return fma(c, q, c);
 }
+
+// ---- per-thread asynchronous copies global -> shared (LDGSTS): no registers, any number in flight ----
+__device__ __forceinline__ void cp_async_16(void* dst_smem, const void* src) {  // past L1
+	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned) __cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_8(void* dst_smem, const void* src) {
+	asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned) __cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_4(void* dst_smem, const void* src) {
+	asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned) __cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+}
+// the same with the destination as a 32-bit shared-memory address, groups, and a plain 16-byte shared-memory load
+__device__ __forceinline__ void cp_async_16s(unsigned dst_smem, const void* src) {
+	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ int4 lds_128(unsigned src_smem) {
+	int4 v;
+	asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(src_smem) : "memory");
+	return v;
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 // ---- bulk-copy engine (TMA, 1-D, no tensor map) + mbarrier: global -> shared staging with completion by byte count ----
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t) __cvta_generic_to_shared(p); }

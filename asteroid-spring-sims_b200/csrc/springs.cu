@@ -78,6 +78,41 @@ __device__ __forceinline__ void finish_node(const Force3 F, const bool has_sprin
 	}
 }
 
+// The same epilogue spread over the node's lane group (SPRING_LANES >= 4): after fold_lanes every lane of the group holds
+// the node's sum, so lane 0 / 1 / 2 takes the x / y / z component through kick and drift(s) and lane 3 the fourth word of
+// every vector -- a third of the dependent FP64 instructions per slice, all lanes of a quarter warp storing one 32-byte
+// vector together.  Operation for operation what finish_node does for the component: the same bits.
+// a_c: the lane's component of the old acceleration (0 with zero_accel fused in; lane 3: the fourth word, carried through).
+template <bool KICK>
+__device__ __forceinline__ void finish_node_lanes(const Force3 F, const bool has_springs, const double a_c, const NodeState& ni, const int node,
+		const int k, const int sub, vec4d* __restrict__ acc, vec4d* __restrict__ posm_out, vec4d* __restrict__ vel_out, const SpringMirror out,
+		const double dt, const int pre_drift_next, const bool write_state) {
+	const double inv_m = has_springs ? fast_rcp(ni.m) : 0.0;
+	const double Fc = sub == 0 ? F.x : (sub == 1 ? F.y : (sub == 2 ? F.z : 0.0));
+	const double a = sub == 3 ? a_c : fma(Fc, inv_m, a_c);
+	((double*) (acc + node))[sub] = a;
+	if (KICK) {
+		const double h = __dmul_rn(0.5, dt);
+		const double pc = sub == 0 ? ni.xy.x : (sub == 1 ? ni.xy.y : ni.zv.x);
+		const double vc = sub == 0 ? ni.vxy.x : (sub == 1 ? ni.vxy.y : ni.zv.y);
+		double v = __dadd_rn(vc, __dmul_rn(dt, a));
+		double p = __dadd_rn(pc, __dmul_rn(h, v));
+		if (pre_drift_next) {
+			p = __dadd_rn(p, __dmul_rn(h, v));
+			if (sub < 3) {
+				double* const pd = sub == 0 ? &out.xy[k].x : (sub == 1 ? &out.xy[k].y : &out.zv[k].x);
+				double* const vd = sub == 0 ? &out.vxy[k].x : (sub == 1 ? &out.vxy[k].y : &out.zv[k].y);
+				*pd = p;
+				*vd = v;
+			}
+		}
+		if (write_state) {
+			((double*) (vel_out + node))[sub] = sub == 3 ? 0.0 : v;
+			((double*) (posm_out + node))[sub] = sub == 3 ? ni.m : p;
+		}
+	}
+}
+
 // The CSR kernel: one group of SPRING_LANES lanes per node, rows read from the CSR copy of the half-edge list.
 // ZERO_FIRST  false: acc += springs (spring_forces);  true: acc = springs (zero_accel + spring_forces)
 // KICK        additionally v += dt*a ; x += (dt/2)*v [; x += (dt/2)*v again = next step's part1] into the alt buffers
@@ -135,8 +170,14 @@ __global__ void __launch_bounds__(BLOCK) k_spring_forces(const GlobalNodes nodes
 constexpr int TL_THREADS = ASS_TILE_THREADS;  // 512 with two interleaved chains per lane, or 1024 with one (half the registers)
 constexpr int TL_CHAINS = ASS_TILE_CHAINS;
 constexpr int TL_WARPS = TL_THREADS / 32;
+#ifndef ASS_TILE_RING
+#define ASS_TILE_RING 4
+#endif
+constexpr int TL_RING = ASS_TILE_RING;                    // pairs of steps (1 KB each) per warp in the record ring (spring_math.cuh: RecordStream)
+constexpr int TL_RING_BYTES = TL_WARPS * TL_RING * 1024;  // 64 KB
 constexpr int GPW = 32 / SPRING_LANES;
-constexpr int TL_FILL = 3;  // table slots a thread has in flight at a time while the table is filled
+constexpr int TILE_SLOTS_LIMIT = 2944;  // the table's share of the SM's 227 KB (checked below, next to the launcher)
+constexpr int TL_FILL = (TILE_SLOTS_LIMIT + TL_THREADS - 1) / TL_THREADS;  // table slots per thread, all in flight at once while the table is filled
 struct TileDesc {
 	int s0, s1, tab_off, n_slots;
 };
@@ -159,55 +200,58 @@ static_assert(sizeof(TilesParams) <= 8192, "per-CTA heads travel as kernel param
 template <bool ZERO_FIRST, bool KICK, bool UNI, bool PAL1>
 __device__ __forceinline__ void tiles_pass(const CtaHead& H, unsigned char* tile_smem, int* s_next, const GlobalNodes mir, vec4d* __restrict__ acc,
 		const TileDesc* __restrict__ tiles, const int* __restrict__ tab, const int4* __restrict__ grpT, const int* __restrict__ warp_off,
-		const HalfEdge* __restrict__ heL, const double2* __restrict__ palf, const double2 nkg1, int cap, int max_slices, vec4d* __restrict__ posm_out,
+		const HalfEdge* __restrict__ heL, const double2* __restrict__ palf, const double2 nkg1, vec4d* __restrict__ posm_out,
 		vec4d* __restrict__ vel_out, const SpringMirror out, double dt, int pre_drift_next, bool write_state) {
-	double2* s_xy = (double2*) tile_smem;  // [table: xy | zv | vxy | m, cap slots each][headers: groups | record offsets]
-	double2* s_zv = s_xy + cap;
-	double2* s_vxy = s_zv + cap;
-	double* s_m = (double*) (s_vxy + cap);
-	int4* s_grp = (int4*) (s_m + cap);                 // max_slices * GPW
-	int* s_off = (int*) (s_grp + (size_t) max_slices * GPW);  // max_slices + 1
-	const SharedNodes nodes{ s_xy, s_zv, s_vxy, s_m };
+	// [record rings: TL_RING KB per warp][table: xy | zv | vxy | m, one entry per slot of THIS tile][headers: groups | record offsets]
+	double2* const s_xy = (double2*) (tile_smem + TL_RING_BYTES);
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, sub = lane & (SPRING_LANES - 1);
+	RecordStream<TL_RING> rs;  // this warp's record stream (spring_math.cuh)
+	rs.ring = (unsigned) __cvta_generic_to_shared(tile_smem) + (unsigned) (warp * TL_RING * 1024 + lane * 16);
 	for (int t = H.tile0; t < H.tile0 + H.ntiles; t++) {
 		const TileDesc T = (t == H.tile0) ? H.first : tiles[t];
 		const int n_sl = T.s1 - T.s0;
+		double2* const s_zv = s_xy + T.n_slots;
+		double2* const s_vxy = s_zv + T.n_slots;
+		double* const s_m = (double*) (s_vxy + T.n_slots);
+		int4* const s_grp = (int4*) (s_m + T.n_slots);      // n_sl * GPW
+		int* const s_off = (int*) (s_grp + (size_t) n_sl * GPW);  // n_sl + 1
+		const SharedNodes nodes{ s_xy, s_zv, s_vxy, s_m };
 		__syncthreads();  // everyone has left the previous tile (its table, headers and s_next)
 		// ---- before the table exists: this warp's first slice is slice `warp`; its header and first records are requested
 		//      now and arrive while the table is being filled ----
 		int sw = warp;
 		int4 gi = make_int4(-1, -1, 0, 0);
-		int off = 0, P = 0;
-		int4 r0 = make_int4(0, 0, 0, 0), r1 = r0;  // the stream's first pair of steps
+		int off = 0, off1 = 0;
 		if (sw < n_sl) {
 			gi = __ldg(grpT + (size_t) (T.s0 + sw) * GPW + lane / SPRING_LANES);
 			off = __ldg(warp_off + T.s0 + sw);
-			P = (__ldg(warp_off + T.s0 + sw + 1) - off) >> 6;
-			if (P > 0) { r0 = __ldcg((const int4*) heL + off + lane); r1 = __ldcg((const int4*) heL + off + lane + 32); }
+			off1 = __ldg(warp_off + T.s0 + sw + 1);
 		}
-		// ---- the table: every request of a thread is in flight before its first store ----
-		for (int base = 0; base < T.n_slots; base += TL_FILL * TL_THREADS) {
-			int r[TL_FILL];
+		// ---- the table, in TWO dependent round trips (after an L2 flush each costs ~1.5 us): (1) every table entry of this
+		//      thread (slot -> rank) together with the slice headers; (2) the state of those ranks, copied global -> shared
+		//      without passing through registers (cp.async: all slots of a thread in flight at once), together with the
+		//      first records of this warp's slice ----
+		int rk[TL_FILL];
 #pragma unroll
-			for (int q = 0; q < TL_FILL; q++) {
-				const int i = base + tid + q * TL_THREADS;
-				r[q] = (i < T.n_slots) ? __ldg(tab + T.tab_off + i) : -1;
-			}
-			double2 a[TL_FILL], b[TL_FILL], c[TL_FILL];
-			double m[TL_FILL];
+		for (int q = 0; q < TL_FILL; q++) {
+			const int i = tid + q * TL_THREADS;
+			rk[q] = (i < T.n_slots) ? __ldg(tab + T.tab_off + i) : -2;
+		}
+		for (int i = tid; i < n_sl * GPW; i += TL_THREADS) cp_async_16(s_grp + i, grpT + (size_t) T.s0 * GPW + i);
+		for (int i = tid; i <= n_sl; i += TL_THREADS) cp_async_4(s_off + i, warp_off + T.s0 + i);
 #pragma unroll
-			for (int q = 0; q < TL_FILL; q++) {
-				a[q] = make_double2(0.0, 0.0); b[q] = a[q]; c[q] = a[q]; m[q] = 1.0;
-				if (r[q] >= 0) { a[q] = __ldcg(mir.xy + r[q]); b[q] = __ldcg(mir.zv + r[q]); c[q] = __ldcg(mir.vxy + r[q]); m[q] = __ldcg(mir.m + r[q]); }
-			}
-#pragma unroll
-			for (int q = 0; q < TL_FILL; q++) {
-				const int i = base + tid + q * TL_THREADS;
-				if (i < T.n_slots) { s_xy[i] = a[q]; s_zv[i] = b[q]; s_vxy[i] = c[q]; s_m[i] = m[q]; }
+		for (int q = 0; q < TL_FILL; q++) {
+			const int i = tid + q * TL_THREADS;
+			if (rk[q] >= 0) {
+				cp_async_16(s_xy + i, mir.xy + rk[q]); cp_async_16(s_zv + i, mir.zv + rk[q]); cp_async_16(s_vxy + i, mir.vxy + rk[q]); cp_async_8(s_m + i, mir.m + rk[q]);
+			} else if (rk[q] == -1) {  // a slot without a rank (classes are padded to the fullest): finite values, never a live operand
+				s_xy[i] = make_double2(0.0, 0.0); s_zv[i] = make_double2(0.0, 0.0); s_vxy[i] = make_double2(0.0, 0.0); s_m[i] = 1.0;
 			}
 		}
-		for (int i = tid; i < n_sl * GPW; i += TL_THREADS) s_grp[i] = __ldg(grpT + (size_t) T.s0 * GPW + i);
-		for (int i = tid; i <= n_sl; i += TL_THREADS) s_off[i] = __ldg(warp_off + T.s0 + i);
+		int P = (off1 - off) >> 6;  // first use of the headers: after every table request
+		rs.begin((const int4*) heL + off + lane, P);
+		rs.top_up();
+		cp_async_wait_all();
 		if (tid == 0) *s_next = TL_WARPS;
 		__syncthreads();
 		while (sw < n_sl) {
@@ -218,24 +262,27 @@ __device__ __forceinline__ void tiles_pass(const CtaHead& H, unsigned char* tile
 			nx = __shfl_sync(0xffffffffu, nx, 0);
 			const bool live = gi.x >= 0;
 			const int slot = live ? gi.x : 0;
-			const int nt = (gi.z - sub + SPRING_LANES - 1) / SPRING_LANES;  // entries sub, sub + SPRING_LANES, ... of the row are this lane's
+			// the old acceleration is needed after the sum: requested now (SPRING_LANES >= 4: one word per lane, see finish_node_lanes)
 			vec4d a_old;
 			a_old.x = 0.0; a_old.y = 0.0; a_old.z = 0.0; a_old.w = 0.0;
-			if (!ZERO_FIRST && live && sub == 0) a_old = acc[gi.w];  // needed after the sum: requested now
+			double a_old_c = 0.0;
+			if (SPRING_LANES >= 4) {
+				if (!ZERO_FIRST && live && sub < 4) a_old_c = ((const double*) (acc + gi.w))[sub];
+			} else if (!ZERO_FIRST && live && sub == 0) a_old = acc[gi.w];
 			const NodeState ni = nodes.get<false>(slot);
 			int4 gi_n = make_int4(-1, -1, 0, 0);
-			int off_n = 0, P_n = 0;
+			int P_n = 0;
 			if (nx < n_sl) {
 				gi_n = s_grp[nx * GPW + lane / SPRING_LANES];  // (slot, rank, degree, node); slot < 0: padding group
-				off_n = s_off[nx];
+				const int off_n = s_off[nx];
 				P_n = (s_off[nx + 1] - off_n) >> 6;
-				// the rest of that slice's records (at most 4 KB = 32 lines): into L2 now, a slice ahead of their use
-				if (lane * 8 < s_off[nx + 1] - off_n) asm volatile("prefetch.global.L2 [%0];" ::"l"(heL + off_n + lane * 8));
+				rs.next_slice((const int4*) heL + off_n + lane, P_n);  // the stream walks on into it when this slice's records are out
 			}
-			const Force3 F = lane_spring_sum_x<UNI, PAL1, TL_CHAINS>((const int4*) heL + off + lane, P, nt, ni, nodes, palf, nkg1, r0, r1,
-					P_n > 0 ? (const int4*) heL + off_n + lane : nullptr);
-			if (live && sub == 0) finish_node<KICK>(F, gi.z > 0, a_old, ni, gi.w, gi.y, acc, posm_out, vel_out, out, dt, pre_drift_next, write_state);
-			sw = nx; gi = gi_n; off = off_n; P = P_n;
+			const Force3 F = lane_spring_sum_ring<UNI, PAL1, TL_CHAINS>(rs, P, ni, nodes, palf, nkg1);
+			if (SPRING_LANES >= 4) {
+				if (live && sub < 4) finish_node_lanes<KICK>(F, gi.z > 0, a_old_c, ni, gi.w, gi.y, sub, acc, posm_out, vel_out, out, dt, pre_drift_next, write_state);
+			} else if (live && sub == 0) finish_node<KICK>(F, gi.z > 0, a_old, ni, gi.w, gi.y, acc, posm_out, vel_out, out, dt, pre_drift_next, write_state);
+			sw = nx; gi = gi_n; P = P_n;
 		}
 	}
 }
@@ -243,14 +290,13 @@ __device__ __forceinline__ void tiles_pass(const CtaHead& H, unsigned char* tile
 template <bool ZERO_FIRST, bool KICK, bool UNI, bool PAL1>
 __global__ void __launch_bounds__(TL_THREADS, 1) k_spring_tiles(const __grid_constant__ TilesParams heads, const GlobalNodes mir, vec4d* __restrict__ acc,
 		const TileDesc* __restrict__ tiles, const int* __restrict__ tab, const int4* __restrict__ grpT, const int* __restrict__ warp_off,
-		const HalfEdge* __restrict__ heL, const double2* __restrict__ palf, int cap, int max_slices, vec4d* __restrict__ posm_out,
+		const HalfEdge* __restrict__ heL, const double2* __restrict__ palf, vec4d* __restrict__ posm_out,
 		vec4d* __restrict__ vel_out, const SpringMirror out, double dt, int pre_drift_next) {
 	extern __shared__ __align__(128) unsigned char tile_smem[];
 	__shared__ int s_next;
 	double2 nkg1 = make_double2(0.0, 0.0);
 	if (PAL1) nkg1 = __ldg(palf);
-	tiles_pass<ZERO_FIRST, KICK, UNI, PAL1>(heads.h[blockIdx.x], tile_smem, &s_next, mir, acc, tiles, tab, grpT, warp_off, heL, palf, nkg1, cap, max_slices,
-			posm_out, vel_out, out, dt, pre_drift_next, true);
+	tiles_pass<ZERO_FIRST, KICK, UNI, PAL1>(heads.h[blockIdx.x], tile_smem, &s_next, mir, acc, tiles, tab, grpT, warp_off, heL, palf, nkg1, posm_out, vel_out, out, dt, pre_drift_next, true);
 }
 
 // The persistent multi-step form for bodies without a force term between the spring evaluations (REB_GRAVITY_NONE, or
@@ -276,7 +322,7 @@ __device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned target) {
 template <bool ZERO_FIRST, bool UNI, bool PAL1>
 __global__ void __launch_bounds__(TL_THREADS, 1) k_spring_steps(const __grid_constant__ TilesParams heads, const GlobalNodes mirA, const GlobalNodes mirB,
 		vec4d* __restrict__ acc, const TileDesc* __restrict__ tiles, const int* __restrict__ tab, const int4* __restrict__ grpT,
-		const int* __restrict__ warp_off, const HalfEdge* __restrict__ heL, const double2* __restrict__ palf, int cap, int max_slices,
+		const int* __restrict__ warp_off, const HalfEdge* __restrict__ heL, const double2* __restrict__ palf,
 		vec4d* __restrict__ posm_out, vec4d* __restrict__ vel_out, double dt, int nsteps, unsigned* __restrict__ bar) {
 	extern __shared__ __align__(128) unsigned char tile_smem[];
 	__shared__ int s_next;
@@ -287,7 +333,7 @@ __global__ void __launch_bounds__(TL_THREADS, 1) k_spring_steps(const __grid_con
 		const bool last = step == nsteps - 1;
 		const bool even = (step & 1) == 0;
 		tiles_pass<ZERO_FIRST, true, UNI, PAL1>(heads.h[blockIdx.x], tile_smem, &s_next, even ? mirA : mirB, acc, tiles, tab, grpT, warp_off, heL, palf, nkg1,
-				cap, max_slices, posm_out, vel_out, even ? outB : outA, dt, last ? 0 : 1, last);
+				posm_out, vel_out, even ? outB : outA, dt, last ? 0 : 1, last);
 		if (!last) grid_barrier(bar, (unsigned) (step + 1) * gridDim.x);
 	}
 }
@@ -344,10 +390,11 @@ static void launch_csr(ass_sim* s, bool zero_first, bool uni, int lo, int hi, do
 
 // shared memory per table slot of the tiled kernel: three 16-byte pairs and the mass
 constexpr size_t TILE_SLOT_BYTES = 3 * sizeof(double2) + sizeof(double);
-// the table's share of the SM's 227 KB; the rest holds the slice headers of the tile (a tile of TILE_SLOTS_LIMIT slots has
-// at most that many own nodes, i.e. TILE_SLOTS_LIMIT / GPW slices of 16 GPW + 4 bytes)
-constexpr int TILE_SLOTS_LIMIT = 2944;
-static_assert(TILE_SLOTS_LIMIT * TILE_SLOT_BYTES + (TILE_SLOTS_LIMIT / GPW + 2) * (16 * GPW + 4) + 4096 <= 227 * 1024, "tile does not fit in shared memory");
+// and in bytes, slice headers included (16 GPW + 4 bytes per slice): what is left of the SM's 227 KB next to the record rings
+constexpr size_t TILE_SMEM_MAX = 227 * 1024 - 1024;  // dynamic shared memory the kernels opt in to
+constexpr size_t TILE_BYTES_LIMIT = TILE_SMEM_MAX - TL_RING_BYTES;
+static size_t tile_bytes(int slots, int slices) { return TILE_SLOT_BYTES * (size_t) slots + (size_t) slices * (GPW * sizeof(int4) + sizeof(int)) + 2 * sizeof(int); }
+static_assert(TILE_BYTES_LIMIT >= 64 * 1024, "no room for a table next to the record rings");
 
 template <class T>
 static int tiles_reserve(T*& ptr, size_t& cap, size_t need, const char* what) {
@@ -367,6 +414,7 @@ static int tiles_reserve(T*& ptr, size_t& cap, size_t need, const char* what) {
 // What the tiled kernel reads besides the mirror, as built on the host.
 struct TilesHost {
 	int grid = 0, slots_max = 0, slices_max = 0;
+	size_t bytes_max = 0;  // table + headers of the largest tile
 	std::vector<TileDesc> tiles;
 	std::vector<int> cta_tile, tab;
 	std::vector<HalfEdge> heL;
@@ -376,7 +424,7 @@ struct TilesHost {
 // Cut the slices into one run per CTA (equal weight: pairs of steps + a constant per slice for the boundary work) and
 // every run into tiles whose node tables fit in `slots_limit` slots; renumber the records.  Pure host work,
 // proportional to the half-edge count, done once per spring list.  Returns ASS_EINVAL if a single slice does not fit.
-static int build_tiles_host(const SpringLayout& lay, int grid, int slots_limit, TilesHost& out) {
+static int build_tiles_host(const SpringLayout& lay, int grid, int slots_limit, TilesHost& out, size_t bytes_limit = TILE_BYTES_LIMIT) {
 	const int ns = (int) lay.warp_off.size() - 1;
 	const int n = (int) lay.rank.size();
 	out.grid = grid;
@@ -425,11 +473,12 @@ static int build_tiles_host(const SpringLayout& lay, int grid, int slots_limit, 
 				}
 				for (int at = lay.warp_off[sl]; at < lay.warp_off[(size_t) sl + 1]; at++) touch(lay.heT[(size_t) at].nbr);
 				const int need = 8 * *std::max_element(cnt, cnt + 8);
-				if (need > slots_limit && sl > s0) {  // does not fit any more: take the slice back, close the tile
+				const bool too_big = need > TILE_SLOTS_LIMIT || tile_bytes(need, sl - s0 + 1) > bytes_limit;
+				if ((need > slots_limit || too_big) && sl > s0) {  // does not fit any more: take the slice back, close the tile
 					for (int r : added) { stamp[(size_t) r] = -1; cnt[r & 7]--; }
 					break;
 				}
-				if (need > TILE_SLOTS_LIMIT) return ASS_EINVAL;  // (a lone slice above a test hook's smaller limit is accepted)
+				if (too_big) return ASS_EINVAL;  // (a lone slice above a test hook's smaller limit is accepted)
 				members.insert(members.end(), added.begin(), added.end());
 				sl++;
 			}
@@ -458,6 +507,7 @@ static int build_tiles_host(const SpringLayout& lay, int grid, int slots_limit, 
 			}
 			out.slots_max = std::max(out.slots_max, n_slots);
 			out.slices_max = std::max(out.slices_max, sl - s0);
+			out.bytes_max = std::max(out.bytes_max, tile_bytes(n_slots, sl - s0));
 			tiles.push_back(T);
 		}
 	}
@@ -503,8 +553,11 @@ int ass_build_spring_tiles(ass_sim* s, const SpringLayout& lay) {
 	s->tiles_grid = grid;
 	s->tile_slots_max = th.slots_max;
 	s->tile_slices_max = th.slices_max;
+	s->tile_bytes_max = th.bytes_max;
 	return ASS_OK;
 }
+
+extern "C" int ass_spring_lanes(void) { return SPRING_LANES; }
 
 // Host-only self-check of everything ass_set_springs builds for the spring kernels (include/ass_b200.h): no device
 // is touched, so the CPU test suite can drive it.
@@ -620,20 +673,20 @@ extern "C" int ass_selfcheck_spring_layout(const double* pos_xyzm, int n, const 
 template <bool ZERO_FIRST, bool KICK, bool UNI, bool PAL1>
 static int launch_tiles_t(ass_sim* s, double dt, int pre) {
 	auto kern = k_spring_tiles<ZERO_FIRST, KICK, UNI, PAL1>;
-	const size_t smem = TILE_SLOT_BYTES * (size_t) s->tile_slots_max + (size_t) s->tile_slices_max * GPW * sizeof(int4) + sizeof(int) * ((size_t) s->tile_slices_max + 2);
+	const size_t smem = TL_RING_BYTES + s->tile_bytes_max;
 	// the opt-in above 48 KB is per function AND per device: remembered per device (a process may drive several), set to
 	// the most a tile can need so that it never has to be raised again
 	static bool opted[64] = {};
 	int dev = 0;
 	CU_TRY(cudaGetDevice(&dev));
 	if (dev < 0 || dev >= 64 || !opted[dev]) {
-		CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
+		CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) TILE_SMEM_MAX));
 		if (dev >= 0 && dev < 64) opted[dev] = true;
 	}
 	TilesParams P;
 	memcpy(&P, s->tile_heads.data(), std::min(sizeof(P), s->tile_heads.size() * sizeof(int)));
 	kern<<<s->tiles_grid, TL_THREADS, smem, s->stream>>>(P, mirror_nodes(s), s->acc, (const TileDesc*) s->tile_desc, s->tile_tab, s->grpT, s->warp_off, s->heL,
-			s->palf, s->tile_slots_max, s->tile_slices_max, KICK ? s->posm_alt : nullptr, KICK ? s->vel_alt : nullptr, s->mir_alt, dt, pre);
+			s->palf, KICK ? s->posm_alt : nullptr, KICK ? s->vel_alt : nullptr, s->mir_alt, dt, pre);
 	return ASS_OK;
 }
 

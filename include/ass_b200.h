@@ -300,6 +300,8 @@ int ass_selfcheck_sqrt(long long samples, int exp_lo, int exp_hi, long long* mis
  * [1] padding records, [2] tiles, [3] largest table, [4] gather passes per step summed over all quarter warps and
  * [5] their minimum (one each), [6] violated invariants (must be 0), [7] records in the lane-transposed copy. */
 int ass_selfcheck_spring_layout(const double* pos_xyzm, int n, const ass_spring* springs, int ns, int grid, int slots, long long* stats);
+/* lanes that share one node's half-edge row in the spring kernels (a slice of the lane-transposed list = 32 / lanes nodes) */
+int ass_spring_lanes(void);
 /* total number of kernel launches issued by this library in this process */
 long long ass_launch_count(void);
 

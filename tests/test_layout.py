@@ -26,7 +26,8 @@ def test_layout_invariants_on_reference_bodies(A, body015, body010, grid, slots)
         p, sp = g["start"], g["springs"]
         st = A.selfcheck_spring_layout(p, sp, grid=grid, slots=slots)
         assert st["violations"] == 0
-        assert st["slices"] == (len(p) + 7) // 8                      # 4 lanes per node, 8 nodes per slice
+        per_slice = 32 // A.spring_lanes()                            # nodes per slice (2 lanes per node: 16)
+        assert st["slices"] == (len(p) + per_slice - 1) // per_slice
         assert st["records"] == 2 * len(sp) + st["padding"] and st["records"] % 64 == 0
         assert st["padding"] < 0.45 * 2 * len(sp)                     # small bodies pad most (C3: 11 %)
         assert 1 <= st["tiles"] <= st["slices"]
@@ -50,7 +51,7 @@ def test_layout_edge_cases(A):
     # no springs at all; fewer nodes than one slice; a node count that is not a multiple of the slice size
     for n in (1, 3, 8, 9, 257):
         st = A.selfcheck_spring_layout(body(n), springs_of(A, []))
-        assert st["violations"] == 0 and st["records"] == 0 and st["slices"] == (n + 7) // 8
+        assert st["violations"] == 0 and st["records"] == 0 and st["slices"] == (n + 32 // A.spring_lanes() - 1) // (32 // A.spring_lanes())
     # one spring; a chain; isolated nodes next to connected ones (point-mass perturbers carry no springs)
     assert A.selfcheck_spring_layout(body(2), springs_of(A, [(0, 1)]))["violations"] == 0
     assert A.selfcheck_spring_layout(body(50), springs_of(A, [(i, i + 1) for i in range(30)]))["violations"] == 0
