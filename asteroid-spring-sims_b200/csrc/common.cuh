@@ -185,6 +185,7 @@ struct ass_sim {
 	size_t h_pinned_bytes = 0;
 	DevBuf grav_partial;      // [split][n] vec4d
 	double* d_red = nullptr;  // reduction outputs (device)
+	unsigned* d_step_bar = nullptr;  // arrival counter of the multi-step spring kernel's grid barrier
 	double* h_red = nullptr;  // pinned mirror
 	DevBuf red_partial;
 	DevBuf flush;             // L2 flush target
@@ -226,6 +227,7 @@ int ass_build_spring_layout(const vec4d* pos, int n, const ass_spring* sp, int n
 int ass_build_spring_tiles(ass_sim* s, const SpringLayout& lay);  // springs.cu; queues uploads on s->stream and waits for them
 int ass_ensure_device(void);
 int ass_sm_count(void);
+bool ass_cooperative_launch_ok(void);
 
 // RAII-free timing bracket: tic before a launch, toc after it
 void ass_tic(ass_sim* s, int klass);
@@ -249,6 +251,8 @@ void ass_toc(ass_sim* s, int klass);
 int ass_launch_spring_forces(ass_sim* s, bool zero_first, bool mirror_fresh);
 int ass_launch_spring_forces_range(ass_sim* s, bool zero_first, int lo, int hi);
 int ass_launch_spring_kick_drift(ass_sim* s, bool zero_first, double dt, bool pre_drift_next, bool mirror_fresh);
+bool ass_spring_steps_applicable(const ass_sim* s);
+int ass_launch_spring_steps(ass_sim* s, bool zero_first, double dt, int nsteps);  // a batch of gravity-free steps in one launch
 // the same for NODES [lo, hi) of a sharded body: reads posm / vel (all nodes), writes posm_alt / vel_alt (own nodes); no swap
 int ass_launch_spring_kick_drift_range(ass_sim* s, bool zero_first, double dt, bool pre_drift_next, int lo, int hi);
 int ass_springs_prepare(ass_sim* s);  // the equal-mass verdict (may synchronise), taken before a step is queued

@@ -185,6 +185,20 @@ static int step_loop(ass_sim* s, int nsteps, bool with_hb) {
 			if ((rc = have_springs ? ass_launch_part1_mirrored(s, dt) : ass_launch_part1(s, dt))) return rc;
 			mirror_fresh = have_springs;
 		}
+		// Nothing but springs between here and the end of the batch (REB_GRAVITY_NONE or zero_accel after gravity, no
+		// heartbeat): the remaining steps run as ONE launch, the CTAs meeting at a grid barrier after every step
+		// (springs.cu: k_spring_steps).  Same kernels' code, same bits as one launch per step (tests).
+		if (have_springs && !grav && !hb && !s->lap_flush && nsteps - step >= 2 && mirror_fresh && ass_spring_steps_applicable(s)) {
+			const int batch = nsteps - step;
+			if ((rc = ass_launch_spring_steps(s, af == 2, dt, batch))) return rc;
+			for (int i = 0; i < batch; i++) {  // the clock advances as the reference's does: twice dt/2 per step
+				s->prm.t += dt / 2.;
+				s->prm.t += dt / 2.;
+			}
+			s->prm.dt_last_done = dt;
+			s->predrifted = false;
+			return ASS_OK;
+		}
 		s->predrifted = false;
 		s->prm.t += dt / 2.;
 		if (grav) {

@@ -196,12 +196,34 @@ struct TilesParams {
 };
 static_assert(sizeof(TilesParams) <= 8192, "per-CTA heads travel as kernel parameters");
 
+// Grid-wide barrier of the multi-step kernel (k_spring_steps), split in two: a CTA ARRIVES when its writes of a step are out,
+// then requests everything of the next step that does not depend on other CTAs (table entries, slice headers, the first
+// records of every warp), and only then WAITS for the others -- right before it copies their nodes' new state.
+// bar: a zeroed counter; the wait after step s is for (s + 1) * gridDim.x arrivals.
+__device__ __forceinline__ void grid_arrive(unsigned* bar) {
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		__threadfence();  // this CTA's mirror / acc writes before its arrival
+		atomicAdd(bar, 1u);
+	}
+}
+__device__ __forceinline__ void grid_wait(const unsigned* bar, unsigned target) {
+	if (threadIdx.x == 0) {
+		unsigned v;
+		do {
+			asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
+		} while (v < target);
+	}
+	__syncthreads();
+}
+
 // One pass of a CTA over its tiles: the body of both kernels below.
 template <bool ZERO_FIRST, bool KICK, bool UNI, bool PAL1>
 __device__ __forceinline__ void tiles_pass(const CtaHead& H, unsigned char* tile_smem, int* s_next, const GlobalNodes mir, vec4d* __restrict__ acc,
 		const TileDesc* __restrict__ tiles, const int* __restrict__ tab, const int4* __restrict__ grpT, const int* __restrict__ warp_off,
 		const HalfEdge* __restrict__ heL, const double2* __restrict__ palf, const double2 nkg1, vec4d* __restrict__ posm_out,
-		vec4d* __restrict__ vel_out, const SpringMirror out, double dt, int pre_drift_next, bool write_state) {
+		vec4d* __restrict__ vel_out, const SpringMirror out, double dt, int pre_drift_next, bool write_state, const unsigned* bar = nullptr,
+		unsigned bar_target = 0) {
 	// [record rings: TL_RING KB per warp][table: xy | zv | vxy | m, one entry per slot of THIS tile][headers: groups | record offsets]
 	double2* const s_xy = (double2*) (tile_smem + TL_RING_BYTES);
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, sub = lane & (SPRING_LANES - 1);
@@ -239,6 +261,11 @@ __device__ __forceinline__ void tiles_pass(const CtaHead& H, unsigned char* tile
 		}
 		for (int i = tid; i < n_sl * GPW; i += TL_THREADS) cp_async_16(s_grp + i, grpT + (size_t) T.s0 * GPW + i);
 		for (int i = tid; i <= n_sl; i += TL_THREADS) cp_async_4(s_off + i, warp_off + T.s0 + i);
+		int P = (off1 - off) >> 6;  // first use of the headers: after every table request
+		rs.begin((const int4*) heL + off + lane, P);
+		rs.top_up();
+		// (multi-step kernel) everything above is this CTA's own; what follows reads what the other CTAs wrote last step
+		if (bar && t == H.tile0) grid_wait(bar, bar_target);
 #pragma unroll
 		for (int q = 0; q < TL_FILL; q++) {
 			const int i = tid + q * TL_THREADS;
@@ -248,9 +275,6 @@ __device__ __forceinline__ void tiles_pass(const CtaHead& H, unsigned char* tile
 				s_xy[i] = make_double2(0.0, 0.0); s_zv[i] = make_double2(0.0, 0.0); s_vxy[i] = make_double2(0.0, 0.0); s_m[i] = 1.0;
 			}
 		}
-		int P = (off1 - off) >> 6;  // first use of the headers: after every table request
-		rs.begin((const int4*) heL + off + lane, P);
-		rs.top_up();
 		cp_async_wait_all();
 		if (tid == 0) *s_next = TL_WARPS;
 		__syncthreads();
@@ -305,20 +329,7 @@ __global__ void __launch_bounds__(TL_THREADS, 1) k_spring_tiles(const __grid_con
 // rank-ordered mirrors only (step s reads mirror s & 1 and writes the other one); posm / vel are written by the last step.
 // A launch, the parameter fetch and the cold chain tile table -> mirror cost ~8 us per evaluation (12 us of a 1k-node
 // body's step are this fixed part); here they are paid once per batch.  Launched cooperatively (all CTAs resident: the
-// barrier spins).  bar: a zeroed counter; arrival s of a CTA waits for (s + 1) * gridDim.x.
-__device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned target) {
-	__syncthreads();
-	if (threadIdx.x == 0) {
-		__threadfence();  // this CTA's mirror / acc writes before its arrival
-		atomicAdd(bar, 1u);
-		unsigned v;
-		do {
-			asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
-		} while (v < target);
-	}
-	__syncthreads();
-}
-
+// barrier spins).
 template <bool ZERO_FIRST, bool UNI, bool PAL1>
 __global__ void __launch_bounds__(TL_THREADS, 1) k_spring_steps(const __grid_constant__ TilesParams heads, const GlobalNodes mirA, const GlobalNodes mirB,
 		vec4d* __restrict__ acc, const TileDesc* __restrict__ tiles, const int* __restrict__ tab, const int4* __restrict__ grpT,
@@ -333,8 +344,8 @@ __global__ void __launch_bounds__(TL_THREADS, 1) k_spring_steps(const __grid_con
 		const bool last = step == nsteps - 1;
 		const bool even = (step & 1) == 0;
 		tiles_pass<ZERO_FIRST, true, UNI, PAL1>(heads.h[blockIdx.x], tile_smem, &s_next, even ? mirA : mirB, acc, tiles, tab, grpT, warp_off, heL, palf, nkg1,
-				posm_out, vel_out, even ? outB : outA, dt, last ? 0 : 1, last);
-		if (!last) grid_barrier(bar, (unsigned) (step + 1) * gridDim.x);
+				posm_out, vel_out, even ? outB : outA, dt, last ? 0 : 1, last, step > 0 ? bar : nullptr, (unsigned) step * gridDim.x);
+		if (!last) grid_arrive(bar);
 	}
 }
 
@@ -699,6 +710,38 @@ static int launch_tiles(ass_sim* s, bool zero_first, bool uni, double dt, int pr
 #undef ASS_TILES_U
 }
 
+// nsteps x [springs + kick + drift (+ the next step's part1)] in one cooperative launch (k_spring_steps)
+template <bool ZERO_FIRST, bool UNI, bool PAL1>
+static int launch_steps_t(ass_sim* s, double dt, int nsteps) {
+	auto kern = k_spring_steps<ZERO_FIRST, UNI, PAL1>;
+	size_t smem = TL_RING_BYTES + s->tile_bytes_max;
+	static bool opted[64] = {};
+	int dev = 0;
+	CU_TRY(cudaGetDevice(&dev));
+	if (dev < 0 || dev >= 64 || !opted[dev]) {
+		CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) TILE_SMEM_MAX));
+		if (dev >= 0 && dev < 64) opted[dev] = true;
+	}
+	if (!s->d_step_bar) CU_TRY(cudaMalloc(&s->d_step_bar, sizeof(unsigned)));
+	CU_TRY(cudaMemsetAsync(s->d_step_bar, 0, sizeof(unsigned), s->stream));
+	TilesParams P;
+	memcpy(&P, s->tile_heads.data(), std::min(sizeof(P), s->tile_heads.size() * sizeof(int)));
+	GlobalNodes mirA = mirror_nodes(s);
+	GlobalNodes mirB{ s->mir_alt.xy, s->mir_alt.zv, s->mir_alt.vxy, s->mir_m };
+	vec4d* acc = s->acc;
+	const TileDesc* tiles = (const TileDesc*) s->tile_desc;
+	const int* tab = s->tile_tab;
+	const int4* grpT = s->grpT;
+	const int* warp_off = s->warp_off;
+	const HalfEdge* heL = s->heL;
+	const double2* palf = s->palf;
+	vec4d *posm_out = s->posm_alt, *vel_out = s->vel_alt;
+	unsigned* bar = s->d_step_bar;
+	void* args[] = { &P, &mirA, &mirB, &acc, &tiles, &tab, &grpT, &warp_off, &heL, &palf, &posm_out, &vel_out, &dt, &nsteps, &bar };
+	CU_TRY(cudaLaunchCooperativeKernel((const void*) kern, dim3((unsigned) s->tiles_grid), dim3(TL_THREADS), args, smem, s->stream));
+	return ASS_OK;
+}
+
 // ASS_SPRINGS_NO_STREAM=1 runs the whole-body evaluations on the CSR kernel instead (same bits: tests)
 static bool use_csr_kernel(const ass_sim* s) {
 	const char* e = getenv("ASS_SPRINGS_NO_STREAM");
@@ -774,6 +817,37 @@ int ass_launch_spring_kick_drift(ass_sim* s, bool zero_first, double dt, bool pr
 	std::swap(s->posm, s->posm_alt);
 	std::swap(s->vel, s->vel_alt);
 	if (pre_drift_next) std::swap(s->mir, s->mir_alt);  // the kernel wrote the next evaluation's mirror
+	return ASS_OK;
+}
+
+// Can a batch of steps run as ONE launch?  Needs the tiled kernel (every CTA resident at once: the grid is at most one CTA
+// per SM) and a device that launches cooperatively.  ASS_SPRINGS_NO_MULTISTEP=1 keeps one launch per step (same bits: tests).
+bool ass_spring_steps_applicable(const ass_sim* s) {
+	const char* e = getenv("ASS_SPRINGS_NO_MULTISTEP");
+	if (e && *e && *e != '0') return false;
+	return s->n > 0 && s->ns > 0 && !use_csr_kernel(s) && s->tiles_grid <= ass_sm_count() && ass_cooperative_launch_ok();
+}
+
+// nsteps whole steps without gravity, heartbeat or any other work between the spring evaluations, starting from pre-drifted
+// positions with a fresh mirror: step i = springs + kick + drift, and for all but the last the next step's part1.
+// On return posm / vel / acc hold the end-of-batch state (not pre-drifted); the mirror is stale.
+int ass_launch_spring_steps(ass_sim* s, bool zero_first, double dt, int nsteps) {
+	if (s->n == 0 || nsteps <= 0) return ASS_OK;
+	bool uni;
+	int rc = springs_uniform_mass(s, &uni);
+	if (rc) return rc;
+	const bool pal1 = s->n_pal == 1;
+	ass_tic(s, ASS_K_SPRINGS);
+#define ASS_STEPS_U(Z, U) (pal1 ? launch_steps_t<Z, U, true>(s, dt, nsteps) : launch_steps_t<Z, U, false>(s, dt, nsteps))
+	if (zero_first) rc = uni ? ASS_STEPS_U(true, true) : ASS_STEPS_U(true, false);
+	else rc = uni ? ASS_STEPS_U(false, true) : ASS_STEPS_U(false, false);
+#undef ASS_STEPS_U
+	if (rc) return rc;
+	LAUNCH_CHECK();
+	ass_toc(s, ASS_K_SPRINGS);
+	std::swap(s->posm, s->posm_alt);
+	std::swap(s->vel, s->vel_alt);
+	if ((nsteps - 1) & 1) std::swap(s->mir, s->mir_alt);  // (the mirror written last; stale either way: the last step writes none)
 	return ASS_OK;
 }
 

@@ -76,6 +76,18 @@ int ass_ensure_device(void) {
 
 int ass_sm_count(void) { return g_sm_count > 0 ? g_sm_count : 148; }
 
+// does the current device launch kernels cooperatively (all CTAs resident, grid-wide barriers allowed)?
+bool ass_cooperative_launch_ok(void) {
+	static int ok[64];  // 0 unknown, 1 yes, 2 no
+	int dev = 0;
+	if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return false;
+	if (!ok[dev]) {
+		int v = 0;
+		ok[dev] = (cudaDeviceGetAttribute(&v, cudaDevAttrCooperativeLaunch, dev) == cudaSuccess && v) ? 1 : 2;
+	}
+	return ok[dev] == 1;
+}
+
 extern "C" int ass_device_info(int* sm_count, long long* l2_bytes, long long* mem_bytes, int* sm_clock_khz, int* cc) {
 	int rc = ass_ensure_device();
 	if (rc) return rc;
@@ -380,7 +392,7 @@ extern "C" int ass_destroy(ass_sim* s) {
 	cudaFree(s->posm); cudaFree(s->vel); cudaFree(s->acc); cudaFree(s->posm_alt); cudaFree(s->vel_alt);
 	cudaFree(s->he); cudaFree(s->row_ptr); cudaFree(s->slot); cudaFree(s->pal);
 	cudaFree(s->stage.p); cudaFree(s->grav_partial.p); cudaFree(s->red_partial.p); cudaFree(s->flush.p);
-	cudaFree(s->d_red); cudaFree(s->masks);
+	cudaFree(s->d_red); cudaFree(s->masks); cudaFree(s->d_step_bar);
 	if (s->h_red) cudaFreeHost(s->h_red);
 	if (s->h_pinned) cudaFreeHost(s->h_pinned);
 	for (auto& e : s->ev_pool) {

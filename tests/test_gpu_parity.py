@@ -616,6 +616,39 @@ def test_tiled_spring_kernel_with_many_tiles_per_cta(gpu, body015, monkeypatch):
         assert same_bits(ref[0], o[0]) and same_bits(ref[1], o[1])
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("af", [1, 2])
+def test_batch_of_gravity_free_steps_in_one_launch(gpu, body015, monkeypatch, af):
+    """Without gravity and heartbeat ass_step(n) runs the n steps as ONE cooperative launch (springs.cu: k_spring_steps, the
+    CTAs meeting at a grid barrier after every step): the same bits as one launch per step, for a body that takes one tile per
+    CTA and with the test hooks that give a CTA several, with accelerations accumulating (af = 1: no zero_accel)
+    and not; the clock advances as the reference's does; a following call continues from the batch's end state."""
+    g = body015
+    start = g["start"].copy(); start[:, 6:9] = 0.2
+    sp = g["springs"]
+    runs = {}
+    for name, env in (("per_step", {"ASS_SPRINGS_NO_MULTISTEP": "1"}), ("batch", {}), ("batch_tiles", {"ASS_TILE_GRID": "3", "ASS_TILE_SLOTS": "1000"})):
+        for k in ("ASS_SPRINGS_NO_MULTISTEP", "ASS_TILE_GRID", "ASS_TILE_SLOTS"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        with new_sim(gpu, start, sp, gravity=0, dt=1e-3, additional_forces=af) as s:
+            n0 = gpu.launch_count()
+            s.step(7)
+            launches = gpu.launch_count() - n0
+            mid = s.download(start.copy())
+            t_mid = s.params.t
+            s.step(1); s.step(4)
+            runs[name] = (mid, t_mid, s.download(start.copy()), s.params.t, launches)
+    ref = runs["per_step"]
+    for name in ("batch", "batch_tiles"):
+        r = runs[name]
+        assert same_bits(ref[0], r[0]) and same_bits(ref[2], r[2]), name
+        assert r[1] == ref[1] and r[3] == ref[3]
+        assert r[4] < ref[4]                       # part1 + one launch instead of part1 + seven
+    assert np.isfinite(ref[2][:, :9]).all()
+
+
 def test_hub_body_is_served_by_the_csr_kernel(gpu, oracle):
     """A node with more neighbours than a shared-memory table holds (~2 900) cannot be tiled: ass_set_springs then builds no
     tile cut and whole-body evaluations run on the CSR kernel -- including property updates -- with the usual accuracy."""
