@@ -240,6 +240,20 @@ class Sim:
         """0 = by size (default), 1 = one-sided source tiles, 2 = pair-once (Newton's third law)."""
         _chk(lib().ass_set_gravity_kernel(self._h, C.c_int(int(which))))
 
+    def probe_gravity_pair(self, rlo, rhi, slo, shi, reps=5):
+        """Device time (ms) of pair-once gravity between two particle ranges (identical or disjoint), L2 flushed per repetition."""
+        ms = C.c_double()
+        _chk(lib().ass_probe_gravity_pair(self._h, C.c_int(rlo), C.c_int(rhi), C.c_int(slo), C.c_int(shi), C.c_int(reps), C.byref(ms)))
+        return ms.value
+
+    def probe_gravity_pieces(self, ranges, concurrent, reps=5):
+        """Device time (ms) of several pair-once gravity pieces [(rlo, rhi, slo, shi), ...] per repetition, run one after the
+        other or concurrently (pair kernels on their own streams, reductions afterwards)."""
+        flat = (C.c_int * (4 * len(ranges)))(*[int(v) for r in ranges for v in r])
+        ms = C.c_double()
+        _chk(lib().ass_probe_gravity_pieces(self._h, C.c_int(len(ranges)), flat, C.c_int(int(concurrent)), C.c_int(reps), C.byref(ms)))
+        return ms.value
+
     def leapfrog_part1(self):
         _chk(lib().ass_leapfrog_part1(self._h))
 

@@ -97,6 +97,9 @@ struct ShardInfo {
 	std::vector<char> peer_is_ipc;    // mapped through cudaIpcOpenMemHandle (needs closing) or a same-process pointer
 	cudaStream_t copy_stream = nullptr;
 	cudaEvent_t pulled = nullptr;
+	cudaEvent_t drifted = nullptr;                                // main stream: own slab drifted (and the previous step's reductions queued before it)
+	cudaStream_t grav_stream[3] = { nullptr, nullptr, nullptr };  // pair kernels of the rectangles / the antipodal half, next to the triangle
+	cudaEvent_t grav_done[3] = { nullptr, nullptr, nullptr };
 	bool active = false;
 };
 
@@ -211,6 +214,8 @@ void ass_sym_plans_free(ass_sim* s);
 bool ass_gravity_sym_applicable(int count);
 int ass_launch_gravity_sym(ass_sim* s, int lo, int hi);
 int ass_launch_gravity_sym_pair(ass_sim* s, int rlo, int rhi, int slo, int shi, vec4d* res_out, bool res_add, vec4d* str_out, bool str_add);
+int ass_launch_gravity_sym_main(ass_sim* s, int rlo, int rhi, int slo, int shi, cudaStream_t st);  // the pair kernel alone, on any stream
+int ass_launch_gravity_sym_finish(ass_sim* s, int rlo, int rhi, int slo, int shi, vec4d* res_out, bool res_add, vec4d* str_out, bool str_add);
 // build (or refresh) the plan of a range pair now: whatever allocation and synchronisation it needs happens here, not in the launch
 int ass_gravity_sym_prepare(ass_sim* s, int rlo, int rhi, int slo, int shi);
 int ass_buf_reserve(DevBuf& b, size_t bytes);

@@ -48,7 +48,7 @@ constexpr int SG_TILE = 128;         // streamed particles between block-wide re
 
 struct SymCta {
 	int rb, s0, s1;  // resident block, streamed blocks [s0, s1); a streamed block equal to rb is the diagonal tile
-	int t_lo, t_hi;  // streamed particles [t_lo, t_hi) of each of those blocks (multiples of SG_TILE); the whole block is
+	int t_lo, t_hi;  // streamed particles [t_lo, t_hi) of each of those blocks (multiples of 32); the whole block is
 	                 // [0, SG_P).  Bodies of ~1e4 particles have too few tiles to fill the machine: their tiles are cut.
 };
 
@@ -167,6 +167,7 @@ __global__ void __launch_bounds__(SG_T, SG_OCC) k_gravity_sym(const vec4d* __res
 		const size_t tile_row = (rect ? (size_t) C.rb * (size_t) nsb + (size_t) sb                       // rectangle, row-major
 		                              : (size_t) C.rb * (size_t) (C.rb - 1) / 2 + (size_t) sb) * (size_t) SG_P;  // strict lower triangle
 		for (int t0 = C.t_lo; t0 < C.t_hi; t0 += SG_TILE) {
+			const int cnt = min(SG_TILE, C.t_hi - t0);  // a piece may end inside a tile (multiples of 32)
 			vec4d mine;
 			if (tid < SG_TILE) mine = load_or_dummy(posm, sbase + t0 + tid, shi);
 			__syncthreads();  // the previous tile's fold has finished reading s_acc / nobody still reads s_xy
@@ -177,7 +178,7 @@ __global__ void __launch_bounds__(SG_T, SG_OCC) k_gravity_sym(const vec4d* __res
 			__syncthreads();
 			if (sbase + t0 >= shi) continue;  // a tile of pure padding (uniform across the CTA)
 #pragma unroll 1
-			for (int c0 = 0; c0 < SG_TILE; c0 += 32) {
+			for (int c0 = 0; c0 < cnt; c0 += 32) {
 				double sax = 0.0, say = 0.0, saz = 0.0;
 				if (diag) {
 #pragma unroll 2
@@ -203,8 +204,8 @@ __global__ void __launch_bounds__(SG_T, SG_OCC) k_gravity_sym(const vec4d* __res
 			}
 			if (!diag) {
 				__syncthreads();
-				for (int v = tid; v < 3 * SG_TILE; v += SG_T) {
-					const int comp = v / SG_TILE, q = v - comp * SG_TILE;
+				for (int v = tid; v < 3 * cnt; v += SG_T) {
+					const int comp = v / cnt, q = v - comp * cnt;
 					double a = s_acc[0][comp][q];
 #pragma unroll
 					for (int w = 1; w < SG_W; w++) a += s_acc[w][comp][q];
@@ -317,7 +318,7 @@ void ass_sym_plans_free(ass_sim* s) {
 // a tile can be cut into SG_P / SG_TILE pieces.
 bool ass_gravity_sym_applicable(int count) {
 	const long long nb = (count + SG_P - 1) / SG_P;
-	return nb * (nb + 1) / 2 * (SG_P / SG_TILE) >= 2LL * ass_sm_count();
+	return nb * (nb + 1) / 2 * (SG_P / SG_TILE) >= 2LL * ass_sm_count();  // (threshold as measured with pieces of 128)
 }
 
 static int check_masses(ass_sim* s, SymPlan* plan) {
@@ -359,6 +360,16 @@ static int get_plan(ass_sim* s, int rlo, int rhi, int slo, int shi, SymPlan** ou
 	// resident CTA does not run it twice as fast, so fewer, fatter CTAs lose: C2 gravity 100 -> 116 us)
 	int cut = 1;
 	while (U == 1 && tiles * cut < 2 * slots && cut < SG_P / SG_TILE) cut *= 2;
+	// Round 2: pieces of 64 streamed particles where that saves a whole round of CTAs.  A body of ~1e4 particles has 55
+	// tiles: cut in 8 that is 440 CTAs = 1.49 rounds of the 296 slots, i.e. two rounds of 4 units of 32 streamed particles
+	// where 6 units would do; cut in 16 it is 2.97 rounds of 2 units (measured: 120.5 -> 111.6 us).  A CTA costs about one
+	// unit on top of its pairs (resident block, scratch rows), which is what the comparison charges; a 12 288-particle slab
+	// (2.1 rounds in 8, 4.2 in 16) stays at 8 -- measured slower in 16.  ASS_SYM_MAX_CUT caps the cut (measurements).
+	if (U == 1 && cut == SG_P / SG_TILE) {
+		auto cost = [&](int c) { return (double) ((tiles * c + slots - 1) / slots) * (32.0 / c + 1.0); };
+		if (cost(2 * cut) < 0.92 * cost(cut)) cut *= 2;
+	}
+	if (const char* e = getenv("ASS_SYM_MAX_CUT")) cut = std::max(1, std::min(cut, atoi(e)));
 	const int piece = SG_P / cut;
 	std::vector<std::vector<SymCta>> per_block(nrb);
 	for (int rb = 0; rb < nrb; rb++) {
@@ -401,18 +412,39 @@ static int get_plan(ass_sim* s, int rlo, int rhi, int slo, int shi, SymPlan** ou
 //                      str_out[j] (=|+=) the pull of the resident range on streamed j (Newton's third law)
 int ass_launch_gravity_sym_pair(ass_sim* s, int rlo, int rhi, int slo, int shi, vec4d* res_out, bool res_add, vec4d* str_out, bool str_add) {
 	if (rhi <= rlo || shi <= slo) return ASS_OK;
+	ass_tic(s, ASS_K_GRAVITY);
+	int rc = ass_launch_gravity_sym_main(s, rlo, rhi, slo, shi, s->stream);
+	if (!rc) rc = ass_launch_gravity_sym_finish(s, rlo, rhi, slo, shi, res_out, res_add, str_out, str_add);
+	if (rc) return rc;
+	ass_toc(s, ASS_K_GRAVITY);
+	return ASS_OK;
+}
+
+// The two halves of the above, for callers that run several range pairs at once (shard.cu: a rank's triangle, rectangles and
+// antipodal half on separate streams, so that the last, partly filled round of CTAs of one is topped up with the next one's):
+// the pair kernel into the plan's own scratch rows on ANY stream, and -- on the simulation's stream, after the caller has
+// made it wait for that kernel -- the fixed-order reductions into the output arrays.
+int ass_launch_gravity_sym_main(ass_sim* s, int rlo, int rhi, int slo, int shi, cudaStream_t st) {
+	if (rhi <= rlo || shi <= slo) return ASS_OK;
 	SymPlan* p = nullptr;
 	int rc = get_plan(s, rlo, rhi, slo, shi, &p);
 	if (rc) return rc;
 	const double soft2 = s->prm.softening * s->prm.softening;
-	ass_tic(s, ASS_K_GRAVITY);
 	if (p->uniform)
-		k_gravity_sym<true><<<p->n_cta, SG_T, 0, s->stream>>>(s->posm, rlo, rhi, slo, shi, p->rect ? 1 : 0, p->nsb, p->d_ctas, soft2, p->d_res, p->res_plane,
+		k_gravity_sym<true><<<p->n_cta, SG_T, 0, st>>>(s->posm, rlo, rhi, slo, shi, p->rect ? 1 : 0, p->nsb, p->d_ctas, soft2, p->d_res, p->res_plane,
 				p->d_str, p->str_plane);
 	else
-		k_gravity_sym<false><<<p->n_cta, SG_T, 0, s->stream>>>(s->posm, rlo, rhi, slo, shi, p->rect ? 1 : 0, p->nsb, p->d_ctas, soft2, p->d_res, p->res_plane,
+		k_gravity_sym<false><<<p->n_cta, SG_T, 0, st>>>(s->posm, rlo, rhi, slo, shi, p->rect ? 1 : 0, p->nsb, p->d_ctas, soft2, p->d_res, p->res_plane,
 				p->d_str, p->str_plane);
 	LAUNCH_CHECK();
+	return ASS_OK;
+}
+
+int ass_launch_gravity_sym_finish(ass_sim* s, int rlo, int rhi, int slo, int shi, vec4d* res_out, bool res_add, vec4d* str_out, bool str_add) {
+	if (rhi <= rlo || shi <= slo) return ASS_OK;
+	SymPlan* p = nullptr;
+	int rc = get_plan(s, rlo, rhi, slo, shi, &p);
+	if (rc) return rc;
 	if (!p->rect) {
 		k_gravity_sym_reduce<<<(rhi - rlo + 255) / 256, 256, 0, s->stream>>>(p->d_res, p->res_plane, p->d_str, p->str_plane, p->d_cta_begin, p->nrb, rlo, rhi,
 				s->prm.G, p->uniform, s->posm, res_out, res_add ? 1 : 0);
@@ -425,7 +457,6 @@ int ass_launch_gravity_sym_pair(ass_sim* s, int rlo, int rhi, int slo, int shi, 
 		k_gravity_rect_reduce_str<<<(shi - slo + 255) / 256, 256, 0, s->stream>>>(p->d_str, p->str_plane, p->nrb, p->nsb, slo, shi, Gm, str_out, str_add ? 1 : 0);
 		LAUNCH_CHECK();
 	}
-	ass_toc(s, ASS_K_GRAVITY);
 	return ASS_OK;
 }
 

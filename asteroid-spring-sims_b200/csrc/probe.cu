@@ -152,3 +152,86 @@ extern "C" int ass_selfcheck_sqrt(long long samples, int exp_lo, int exp_hi, lon
 	*mismatches = (long long) bad;
 	return ASS_OK;
 }
+
+// Pair-once gravity between two particle ranges of a simulation, timed on the device (L2 flushed before every repetition):
+// the pieces a rank of a sharded body launches per step (own triangle, rectangles against runs of slabs, half of the
+// antipodal rectangle), measurable on ONE GPU.  Writes the simulation's acceleration array (measurement only).
+extern "C" int ass_probe_gravity_pair(ass_sim* s, int rlo, int rhi, int slo, int shi, int reps, double* ms_avg) {
+	REQUIRE(s && ms_avg && reps > 0, ASS_EINVAL, "bad argument");
+	{
+		int rc0 = ass_ensure_device();
+		if (rc0) return rc0;
+	}
+	REQUIRE(s->have_state && !s->shard.active, ASS_ESTATE, "needs an unsharded simulation with particles");
+	REQUIRE(0 <= rlo && rlo < rhi && rhi <= s->n && 0 <= slo && slo < shi && shi <= s->n, ASS_EINVAL, "bad range");
+	REQUIRE((rlo == slo && rhi == shi) || rhi <= slo || shi <= rlo, ASS_EINVAL, "ranges must be identical or disjoint");
+	vec4d* part = nullptr;
+	CU_TRY(cudaMalloc(&part, sizeof(vec4d) * (size_t) s->n));
+	int rc = ass_launch_gravity_sym_pair(s, rlo, rhi, slo, shi, s->acc, false, part, false);  // builds the plan
+	double total = 0.0;
+	for (int rep = 0; rep < reps && !rc; rep++) {
+		double ms = 0.0;
+		if ((rc = ass_l2_flush(s)) || (rc = ass_mark_begin(s))) break;
+		if ((rc = ass_launch_gravity_sym_pair(s, rlo, rhi, slo, shi, s->acc, false, part, false))) break;
+		if ((rc = ass_mark_end(s, &ms))) break;
+		total += ms;
+	}
+	cudaStreamSynchronize(s->stream);
+	cudaFree(part);
+	if (rc) return rc;
+	*ms_avg = total / reps;
+	return ASS_OK;
+}
+
+// Several range pairs per repetition, as a rank of a sharded body runs them: one after the other on the simulation's
+// stream (concurrent == 0), or each pair kernel on a stream of its own with the reductions afterwards (concurrent != 0).
+// ranges: n_pieces x {rlo, rhi, slo, shi}.
+extern "C" int ass_probe_gravity_pieces(ass_sim* s, int n_pieces, const int* ranges, int concurrent, int reps, double* ms_avg) {
+	REQUIRE(s && ranges && ms_avg && reps > 0 && n_pieces > 0 && n_pieces <= 4, ASS_EINVAL, "bad argument");
+	{
+		int rc0 = ass_ensure_device();
+		if (rc0) return rc0;
+	}
+	REQUIRE(s->have_state && !s->shard.active, ASS_ESTATE, "needs an unsharded simulation with particles");
+	vec4d* part = nullptr;
+	CU_TRY(cudaMalloc(&part, sizeof(vec4d) * (size_t) s->n));
+	cudaStream_t st[4] = {};
+	cudaEvent_t go = nullptr, done[4] = {};
+	cudaEventCreateWithFlags(&go, cudaEventDisableTiming);
+	for (int q = 0; q < n_pieces; q++) { cudaStreamCreateWithFlags(&st[q], cudaStreamNonBlocking); cudaEventCreateWithFlags(&done[q], cudaEventDisableTiming); }
+	int rc = ASS_OK;
+	for (int q = 0; q < n_pieces && !rc; q++) rc = ass_gravity_sym_prepare(s, ranges[4 * q], ranges[4 * q + 1], ranges[4 * q + 2], ranges[4 * q + 3]);
+	double total = 0.0;
+	for (int rep = -1; rep < reps && !rc; rep++) {
+		double ms = 0.0;
+		if ((rc = ass_l2_flush(s)) || (rc = ass_mark_begin(s))) break;
+		if (concurrent) {
+			cudaEventRecord(go, s->stream);
+			for (int q = 0; q < n_pieces && !rc; q++) {
+				const int* r = ranges + 4 * q;
+				cudaStreamWaitEvent(st[q], go, 0);
+				rc = ass_launch_gravity_sym_main(s, r[0], r[1], r[2], r[3], st[q]);
+				cudaEventRecord(done[q], st[q]);
+			}
+			for (int q = 0; q < n_pieces && !rc; q++) {
+				const int* r = ranges + 4 * q;
+				cudaStreamWaitEvent(s->stream, done[q], 0);
+				rc = ass_launch_gravity_sym_finish(s, r[0], r[1], r[2], r[3], s->acc, q > 0, part, false);
+			}
+		} else {
+			for (int q = 0; q < n_pieces && !rc; q++) {
+				const int* r = ranges + 4 * q;
+				rc = ass_launch_gravity_sym_pair(s, r[0], r[1], r[2], r[3], s->acc, q > 0, part, false);
+			}
+		}
+		if (rc || (rc = ass_mark_end(s, &ms))) break;
+		if (rep >= 0) total += ms;
+	}
+	cudaStreamSynchronize(s->stream);
+	for (int q = 0; q < n_pieces; q++) { cudaStreamSynchronize(st[q]); cudaStreamDestroy(st[q]); cudaEventDestroy(done[q]); }
+	cudaEventDestroy(go);
+	cudaFree(part);
+	if (rc) return rc;
+	*ms_avg = total / reps;
+	return ASS_OK;
+}

@@ -347,6 +347,11 @@ extern "C" int ass_shard_setup(ass_sim* s, int rank, int nranks, const int* boun
 	s->cap = s->n;
 	CU_TRY(cudaStreamCreateWithFlags(&sh.copy_stream, cudaStreamNonBlocking));
 	CU_TRY(cudaEventCreateWithFlags(&sh.pulled, cudaEventDisableTiming));
+	CU_TRY(cudaEventCreateWithFlags(&sh.drifted, cudaEventDisableTiming));
+	for (int q = 0; q < 3; q++) {
+		CU_TRY(cudaStreamCreateWithFlags(&sh.grav_stream[q], cudaStreamNonBlocking));
+		CU_TRY(cudaEventCreateWithFlags(&sh.grav_done[q], cudaEventDisableTiming));
+	}
 	sh.rank = rank; sh.nranks = nranks;
 	sh.bounds.assign(bounds, bounds + nranks + 1);
 	sh.lo = bounds[rank]; sh.hi = bounds[rank + 1];
@@ -439,6 +444,7 @@ extern "C" int ass_shard_step(ass_sim* s, int nsteps, int pre_drift_last) {
 		s->predrifted = false;
 		s->prm.t += dt / 2.;  // integrator_leapfrog.c:50
 		if ((rc = launch_flag_set(s, s->stream, ASS_SHARD_POS, e))) return rc;
+		CU_TRY(cudaEventRecord(sh.drifted, s->stream));  // own slab drifted, last step's reductions done: the gravity streams may go
 		// ---- copy stream: the other slabs of this step, as soon as their owners have published them ----
 		if ((rc = launch_flag_wait(s, sh.copy_stream, all_others, ASS_SHARD_POS, e))) return rc;
 		for (int r = 0; r < P; r++) {
@@ -473,15 +479,41 @@ extern "C" int ass_shard_step(ass_sim* s, int nsteps, int pre_drift_last) {
 			body_slab(s, g, &lo, &hi);
 			int run_lo[2], run_hi[2];
 			const int runs = rect_runs(s, run_lo, run_hi);
-			for (int q = 0; q < runs; q++)  // rectangles: both sides of every pair
-				if ((rc = ass_launch_gravity_sym_pair(s, lo, hi, run_lo[q], run_hi[q], s->acc, true, fpart, false))) return rc;
+			// rectangles (both sides of every pair) and, for an even rank count, this rank's half of the antipodal rectangle.
+			// Their pair kernels run on streams of their own, next to the triangle still running on the main stream: each of
+			// these launches ends in a partly filled round of CTAs (a 12 288-particle slab is 2.1 / 2.9 / 1.9 rounds), and the
+			// block scheduler tops a draining kernel up with the next one's CTAs (measured on one GPU, tools/
+			// prof_gravity_pairs.py: 889 -> 815 us per rank and step at C3 / 8).  The fixed-order reductions follow on the
+			// main stream.  ASS_SHARD_SERIAL_GRAVITY=1: one after the other on the main stream.
+			int pc[3][4], npc = 0;
+			for (int q = 0; q < runs; q++) { pc[npc][0] = lo; pc[npc][1] = hi; pc[npc][2] = run_lo[q]; pc[npc][3] = run_hi[q]; npc++; }
 			if (P % 2 == 0 && P > 1) {  // antipodal slab: the pair's rectangle is split between its two ranks
 				const int h = (g + P / 2) % P;
 				int plo, phi;
 				body_slab(s, h, &plo, &phi);
-				if (g < h) rc = ass_launch_gravity_sym_pair(s, lo, half_point(lo, hi), plo, phi, s->acc, true, fpart, false);
-				else rc = ass_launch_gravity_sym_pair(s, lo, hi, half_point(plo, phi), phi, s->acc, true, fpart, false);
-				if (rc) return rc;
+				if (g < h) { pc[npc][0] = lo; pc[npc][1] = half_point(lo, hi); pc[npc][2] = plo; pc[npc][3] = phi; }
+				else { pc[npc][0] = lo; pc[npc][1] = hi; pc[npc][2] = half_point(plo, phi); pc[npc][3] = phi; }
+				npc++;
+			}
+			const char* serial = getenv("ASS_SHARD_SERIAL_GRAVITY");
+			if (serial && *serial && *serial != '0') {
+				for (int q = 0; q < npc; q++)
+					if ((rc = ass_launch_gravity_sym_pair(s, pc[q][0], pc[q][1], pc[q][2], pc[q][3], s->acc, true, fpart, false))) return rc;
+			} else {
+				for (int q = 0; q < npc; q++) {
+					if (pc[q][1] <= pc[q][0] || pc[q][3] <= pc[q][2]) continue;
+					CU_TRY(cudaStreamWaitEvent(sh.grav_stream[q], sh.drifted, 0));
+					CU_TRY(cudaStreamWaitEvent(sh.grav_stream[q], sh.pulled, 0));
+					if ((rc = ass_launch_gravity_sym_main(s, pc[q][0], pc[q][1], pc[q][2], pc[q][3], sh.grav_stream[q]))) return rc;
+					CU_TRY(cudaEventRecord(sh.grav_done[q], sh.grav_stream[q]));
+				}
+				ass_tic(s, ASS_K_GRAVITY);
+				for (int q = 0; q < npc; q++) {
+					if (pc[q][1] <= pc[q][0] || pc[q][3] <= pc[q][2]) continue;
+					CU_TRY(cudaStreamWaitEvent(s->stream, sh.grav_done[q], 0));
+					if ((rc = ass_launch_gravity_sym_finish(s, pc[q][0], pc[q][1], pc[q][2], pc[q][3], s->acc, true, fpart, false))) return rc;
+				}
+				ass_toc(s, ASS_K_GRAVITY);
 			}
 			// point masses: they pull on my body particles; whoever owns them sums everything onto them
 			if ((rc = one_sided_add(s, nb, n, lo, hi))) return rc;
@@ -592,6 +624,11 @@ void ass_shard_release(ass_sim* s) {
 		if (sh.peer_window[r] && sh.peer_is_ipc[r]) cudaIpcCloseMemHandle(sh.peer_window[r]);
 	if (sh.copy_stream) { cudaStreamSynchronize(sh.copy_stream); cudaStreamDestroy(sh.copy_stream); }
 	if (sh.pulled) cudaEventDestroy(sh.pulled);
+	if (sh.drifted) cudaEventDestroy(sh.drifted);
+	for (int q = 0; q < 3; q++) {
+		if (sh.grav_stream[q]) { cudaStreamSynchronize(sh.grav_stream[q]); cudaStreamDestroy(sh.grav_stream[q]); }
+		if (sh.grav_done[q]) cudaEventDestroy(sh.grav_done[q]);
+	}
 	// posm / vel and their alt twins alias the window: free it once and clear the aliases
 	cudaFree(sh.window);
 	s->posm = s->vel = s->posm_alt = s->vel_alt = nullptr;

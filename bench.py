@@ -316,6 +316,19 @@ def run_single(args, A, name, cfg, local, want_e2e=True, want_cpu=True, steps=No
     sim.timing(False)
     value = n * steps / (dev_ms * 1e-3)
 
+    # ---- gravity-free bodies (what every shipped module runs): a batch of steps is ONE launch (k_spring_steps) ----
+    batched = None
+    if not (cfg["gravity"] == 1 and cfg["af"] != 2):
+        kb = max(steps, 200)
+        sim.step(kb); sim.sync()
+        l0 = A.launch_count()
+        sim.l2_flush()
+        sim.mark_begin()
+        sim.step(kb)
+        b_ms = sim.mark_end()
+        batched = {"steps_per_call": kb, "ms_per_step": b_ms / kb, "value": n * kb / (b_ms * 1e-3), "unit": "node-steps/s", "gpu_launches": int(A.launch_count() - l0),
+                   "l2": "flushed before the batch; inside a batch the body stays in L2, as it does in a production run (the main record flushes before EVERY step and launches every step on its own)"}
+
     # ---- end to end through host buffers (the drop-in's always-coherent reb_step) ----
     e2e = None
     if want_e2e and not args.no_e2e:
@@ -394,7 +407,7 @@ def run_single(args, A, name, cfg, local, want_e2e=True, want_cpu=True, steps=No
         "metric": "node-steps/s", "value": value, "unit": "node-steps/s", "n_gpus": 1, "steps": steps, "warmup": warmup,
         "ms_per_step": dev_ms / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic", "config": config_of(name, cfg, n, ns, 1, "single"),
-        "clocks": clk, "e2e": e2e, "dropin_e2e": dropin, "gpu_launches": int(launches), "parity": parity,
+        "clocks": clk, "e2e": e2e, "batched": batched, "dropin_e2e": dropin, "gpu_launches": int(launches), "parity": parity,
         "roofline": dominant, "roofline_gravity": roof_g, "roofline_springs": roof_s, "cpu_baseline": cpu,
         "kernel_ms": {k: {"ms": v[0], "launches": v[1]} for k, v in kt.items()},
         "wall_ms_per_step_incl_flush": 1e3 * t_wall / steps, "setup": setup, "fp64_peak_tflops_measured": fp64_peak,

@@ -288,6 +288,12 @@ int ass_l2_flush(ass_sim* sim);                    /* overwrite a buffer larger 
 int ass_step_timed(ass_sim* sim, int nsteps, int with_heartbeat, double* device_ms);
 /* DFMA-only microbenchmark: the FP64 roofline denominator (MEASURED_PEAKS.json has none). iters ~ 1<<14. */
 int ass_probe_fp64_peak(int iters, double* tflops, double* ms);
+/* pair-once gravity between two particle ranges (identical: the triangle; disjoint: the rectangle), device-timed with the L2
+ * flushed before each of `reps` repetitions: the per-rank pieces of a sharded body, measurable on one GPU (tools/) */
+int ass_probe_gravity_pair(ass_sim* sim, int rlo, int rhi, int slo, int shi, int reps, double* ms_avg);
+/* several range pairs per repetition (ranges: n_pieces x {rlo, rhi, slo, shi}, at most 4), one after the other or with the
+ * pair kernels on streams of their own and the reductions afterwards: what a rank of a sharded body queues per step */
+int ass_probe_gravity_pieces(ass_sim* sim, int n_pieces, const int* ranges, int concurrent, int reps, double* ms_avg);
 /* device copy bandwidth (read+write bytes / time) for a buffer of `bytes` */
 int ass_probe_copy_bw(long long bytes, double* gbs);
 /* Self-check of the branch-free, correctly rounded square root inside the spring kernels (csrc/spring_math.cuh) against
