@@ -360,16 +360,15 @@ static int get_plan(ass_sim* s, int rlo, int rhi, int slo, int shi, SymPlan** ou
 	// resident CTA does not run it twice as fast, so fewer, fatter CTAs lose: C2 gravity 100 -> 116 us)
 	int cut = 1;
 	while (U == 1 && tiles * cut < 2 * slots && cut < SG_P / SG_TILE) cut *= 2;
-	// Round 2: pieces of 64 streamed particles where that saves a whole round of CTAs.  A body of ~1e4 particles has 55
-	// tiles: cut in 8 that is 440 CTAs = 1.49 rounds of the 296 slots, i.e. two rounds of 4 units of 32 streamed particles
-	// where 6 units would do; cut in 16 it is 2.97 rounds of 2 units (measured: 120.5 -> 111.6 us).  A CTA costs about one
-	// unit on top of its pairs (resident block, scratch rows), which is what the comparison charges; a 12 288-particle slab
-	// (2.1 rounds in 8, 4.2 in 16) stays at 8 -- measured slower in 16.  ASS_SYM_MAX_CUT caps the cut (measurements).
-	if (U == 1 && cut == SG_P / SG_TILE) {
-		auto cost = [&](int c) { return (double) ((tiles * c + slots - 1) / slots) * (32.0 / c + 1.0); };
-		if (cost(2 * cut) < 0.92 * cost(cut)) cut *= 2;
+	// (Round 2, measured and left off: pieces of 64 streamed particles where they save a whole round of CTAs -- a body of
+	// ~1e4 particles is 1.49 rounds of the 296 slots cut in 8 and 2.97 cut in 16.  On a GPU already under sustained FP64 load
+	// (power-limited clocks) that gains 7 %: 120.5 -> 111.6 us; on a cool one, as a short benchmark finds it, it loses 10 %:
+	// 97 -> 108 us, the per-CTA fixed cost -- resident block, scratch rows -- weighing more at full clocks; a 12 288-particle
+	// slab loses either way.  The kernel accepts pieces that end inside a tile; ASS_SYM_CUT forces a cut for measurements.)
+	if (const char* e = getenv("ASS_SYM_CUT")) {
+		const int c = atoi(e);
+		if (U == 1 && c >= 1 && c <= SG_P / 32 && (c & (c - 1)) == 0) cut = c;
 	}
-	if (const char* e = getenv("ASS_SYM_MAX_CUT")) cut = std::max(1, std::min(cut, atoi(e)));
 	const int piece = SG_P / cut;
 	std::vector<std::vector<SymCta>> per_block(nrb);
 	for (int rb = 0; rb < nrb; rb++) {
