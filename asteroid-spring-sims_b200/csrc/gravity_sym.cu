@@ -52,8 +52,8 @@ struct SymCta {
 	                 // [0, SG_P).  Bodies of ~1e4 particles have too few tiles to fill the machine: their tiles are cut.
 };
 
-__device__ __forceinline__ vec4d load_or_dummy(const vec4d* __restrict__ posm, int idx, int hi) {
-	if (idx < hi) return posm[idx];
+__device__ __forceinline__ vec4d load_or_dummy(const vec4d* __restrict__ posm, int idx, int lo, int hi) {
+	if (idx >= lo && idx < hi) return posm[idx];
 	// padding: massless and so far away that y^3 = r^-3 underflows to exactly 0 while r^2 (~3e300) stays finite, so a
 	// dummy contributes exactly 0 to real particles with or without the mass factor; dummies are pairwise distinct
 	vec4d p;
@@ -144,8 +144,8 @@ __device__ __forceinline__ void meet(const double2 xy, const double2 zm, int sid
 // range and the tiles are its lower triangle incl. the diagonal; rect != 0: the ranges are disjoint (two slabs of a
 // sharded body) and the tiles are the full rectangle, nsb streamed blocks wide.
 template <bool UNI>
-__global__ void __launch_bounds__(SG_T, SG_OCC) k_gravity_sym(const vec4d* __restrict__ posm, int rlo, int rhi, int slo, int shi, int rect, int nsb,
-		const SymCta* __restrict__ ctas, double soft2, double* __restrict__ res, size_t res_plane, double* __restrict__ str, size_t str_plane) {
+__global__ void __launch_bounds__(SG_T, SG_OCC) k_gravity_sym(const vec4d* __restrict__ posm, int rlo, int rhi, int slo, int shi, int rpad, int spad, int rect,
+		int nsb, const SymCta* __restrict__ ctas, double soft2, double* __restrict__ res, size_t res_plane, double* __restrict__ str, size_t str_plane) {
 	__shared__ double2 s_xy[SG_TILE], s_zm[SG_TILE];
 	__shared__ double s_acc[SG_W][3][SG_TILE];
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -155,28 +155,28 @@ __global__ void __launch_bounds__(SG_T, SG_OCC) k_gravity_sym(const vec4d* __res
 	int ridx[SG_R];
 #pragma unroll
 	for (int k = 0; k < SG_R; k++) {
-		ridx[k] = rlo + C.rb * SG_P + tid + k * SG_T;
-		const vec4d p = load_or_dummy(posm, ridx[k], rhi);
+		ridx[k] = rlo - rpad + C.rb * SG_P + tid + k * SG_T;  // blocks are counted from rlo - rpad: the padding leads block 0
+		const vec4d p = load_or_dummy(posm, ridx[k], rlo, rhi);
 		rx[k] = p.x; ry[k] = p.y; rz[k] = p.z; rm[k] = p.w;
 		rax[k] = 0.0; ray[k] = 0.0; raz[k] = 0.0;
 	}
 
 	for (int sb = C.s0; sb < C.s1; sb++) {
 		const bool diag = !rect && (sb == C.rb);
-		const int sbase = slo + sb * SG_P;
+		const int sbase = slo - spad + sb * SG_P;
 		const size_t tile_row = (rect ? (size_t) C.rb * (size_t) nsb + (size_t) sb                       // rectangle, row-major
 		                              : (size_t) C.rb * (size_t) (C.rb - 1) / 2 + (size_t) sb) * (size_t) SG_P;  // strict lower triangle
 		for (int t0 = C.t_lo; t0 < C.t_hi; t0 += SG_TILE) {
 			const int cnt = min(SG_TILE, C.t_hi - t0);  // a piece may end inside a tile (multiples of 32)
 			vec4d mine;
-			if (tid < SG_TILE) mine = load_or_dummy(posm, sbase + t0 + tid, shi);
+			if (tid < SG_TILE) mine = load_or_dummy(posm, sbase + t0 + tid, slo, shi);
 			__syncthreads();  // the previous tile's fold has finished reading s_acc / nobody still reads s_xy
 			if (tid < SG_TILE) {
 				s_xy[tid] = make_double2(mine.x, mine.y);
 				s_zm[tid] = make_double2(mine.z, mine.w);
 			}
 			__syncthreads();
-			if (sbase + t0 >= shi) continue;  // a tile of pure padding (uniform across the CTA)
+			if (sbase + t0 >= shi || sbase + t0 + cnt <= slo) continue;  // a tile of pure padding (uniform across the CTA)
 #pragma unroll 1
 			for (int c0 = 0; c0 < cnt; c0 += 32) {
 				double sax = 0.0, say = 0.0, saz = 0.0;
@@ -227,11 +227,11 @@ __global__ void __launch_bounds__(SG_T, SG_OCC) k_gravity_sym(const vec4d* __res
 // order.  be[2b], be[2b+1] = the CTAs whose resident block is b.  uniform != 0: the rows hold unweighted sums and every
 // particle has the mass of particle `lo`.  add != 0: out[i] += a_i instead of out[i] = a_i.
 __global__ void k_gravity_sym_reduce(const double* __restrict__ res, size_t res_plane, const double* __restrict__ str, size_t str_plane,
-		const int* __restrict__ be, int nb, int lo, int hi, double G, int uniform, const vec4d* __restrict__ posm, vec4d* __restrict__ out, int add) {
+		const int* __restrict__ be, int nb, int lo, int hi, int pad, double G, int uniform, const vec4d* __restrict__ posm, vec4d* __restrict__ out, int add) {
 	const int i = lo + blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= hi) return;
 	if (uniform) G *= posm[lo].w;
-	const int b = (i - lo) / SG_P, o = (i - lo) - b * SG_P;
+	const int b = (i - lo + pad) / SG_P, o = (i - lo + pad) - b * SG_P;
 	double rs[3] = { 0.0, 0.0, 0.0 }, ss[3] = { 0.0, 0.0, 0.0 };
 	for (int c = be[2 * b]; c < be[2 * b + 1]; c++) {
 		const size_t at = (size_t) c * SG_P + o;
@@ -248,11 +248,11 @@ __global__ void k_gravity_sym_reduce(const double* __restrict__ res, size_t res_
 }
 
 // Rectangle plans, resident side: a_i = +G * (rows of the CTAs whose resident block holds i), i in [rlo, rhi)
-__global__ void k_gravity_rect_reduce_res(const double* __restrict__ res, size_t res_plane, const int* __restrict__ be, int rlo, int rhi, double Gm,
+__global__ void k_gravity_rect_reduce_res(const double* __restrict__ res, size_t res_plane, const int* __restrict__ be, int rlo, int rhi, int rpad, double Gm,
 		vec4d* __restrict__ out, int add) {
 	const int i = rlo + blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= rhi) return;
-	const int b = (i - rlo) / SG_P, o = (i - rlo) - b * SG_P;
+	const int b = (i - rlo + rpad) / SG_P, o = (i - rlo + rpad) - b * SG_P;
 	double rs[3] = { 0.0, 0.0, 0.0 };
 	for (int c = be[2 * b]; c < be[2 * b + 1]; c++) {
 		const size_t at = (size_t) c * SG_P + o;
@@ -265,11 +265,11 @@ __global__ void k_gravity_rect_reduce_res(const double* __restrict__ res, size_t
 }
 
 // Rectangle plans, streamed side: a_j = -G * (rows of column block b over all resident blocks), j in [slo, shi)
-__global__ void k_gravity_rect_reduce_str(const double* __restrict__ str, size_t str_plane, int nrb, int nsb, int slo, int shi, double Gm,
+__global__ void k_gravity_rect_reduce_str(const double* __restrict__ str, size_t str_plane, int nrb, int nsb, int slo, int shi, int spad, double Gm,
 		vec4d* __restrict__ out, int add) {
 	const int j = slo + blockIdx.x * blockDim.x + threadIdx.x;
 	if (j >= shi) return;
-	const int b = (j - slo) / SG_P, o = (j - slo) - b * SG_P;
+	const int b = (j - slo + spad) / SG_P, o = (j - slo + spad) - b * SG_P;
 	double ss[3] = { 0.0, 0.0, 0.0 };
 	for (int rb = 0; rb < nrb; rb++) {
 		const size_t at = ((size_t) rb * (size_t) nsb + (size_t) b) * SG_P + o;
@@ -294,6 +294,7 @@ struct SymPlan {
 	int rlo = -1, rhi = -1, slo = -1, shi = -1;  // resident / streamed ranges (identical: triangle; disjoint: rectangle)
 	bool rect = false;
 	int nrb = 0, nsb = 0, n_cta = 0;
+	int rpad = 0, spad = 0;     // dummies in front of block 0 of the resident / streamed range (blocks are counted from lo - pad)
 	long long mass_epoch = -1;  // masses the `uniform` verdict was taken from (ass_sim::mass_epoch)
 	int uniform = 0;
 	double m_ref = 0.0;         // mass of particle rlo (the common mass when uniform)
@@ -351,6 +352,12 @@ static int get_plan(ass_sim* s, int rlo, int rhi, int slo, int shi, SymPlan** ou
 	plan->rect = !(rlo == slo && rhi == shi);
 	const int nrb = (rhi - rlo + SG_P - 1) / SG_P, nsb = (shi - slo + SG_P - 1) / SG_P;
 	plan->nrb = nrb; plan->nsb = nsb;
+	// The range's partial block is block 0, its padding in FRONT: block 0 is the streamed side of all its off-diagonal tiles
+	// (triangle: streamed block <= resident block), where tiles of pure padding are skipped 128 particles at a time, and
+	// the resident side of only one.  With the partial block last (round 1) it was resident in nb tiles, all its padding
+	// computed: a body of 9 327 particles (9.1 blocks) spent 10 of its 55 tiles on a block that is 11 % full.
+	plan->rpad = nrb * SG_P - (rhi - rlo);
+	plan->spad = nsb * SG_P - (shi - slo);
 	const long long tiles = plan->rect ? (long long) nrb * nsb : (long long) nrb * (nrb + 1) / 2;
 	// tiles per CTA: enough CTAs (>= ~16 per resident slot) for the block scheduler to balance, few enough rows
 	const long long slots = (long long) SG_OCC * ass_sm_count();
@@ -374,7 +381,11 @@ static int get_plan(ass_sim* s, int rlo, int rhi, int slo, int shi, SymPlan** ou
 	for (int rb = 0; rb < nrb; rb++) {
 		const int s_end = plan->rect ? nsb : rb + 1;  // rectangle: every streamed block; triangle: up to the diagonal
 		for (int s0 = 0; s0 < s_end; s0 += U)
-			for (int c = 0; c < cut; c++) per_block[rb].push_back({ rb, s0, std::min(s0 + U, s_end), c * piece, (c + 1) * piece });
+			for (int c = 0; c < cut; c++) {
+				// a piece of streamed block 0 that lies in its leading padding has nothing to do
+				if (U == 1 && s0 == 0 && (c + 1) * piece <= plan->spad) continue;
+				per_block[rb].push_back({ rb, s0, std::min(s0 + U, s_end), c * piece, (c + 1) * piece });
+			}
 	}
 	// CTAs of one resident block stay contiguous (the reduction walks be[2b] .. be[2b+1]); big blocks first
 	std::vector<SymCta> ctas;
@@ -430,10 +441,10 @@ int ass_launch_gravity_sym_main(ass_sim* s, int rlo, int rhi, int slo, int shi, 
 	if (rc) return rc;
 	const double soft2 = s->prm.softening * s->prm.softening;
 	if (p->uniform)
-		k_gravity_sym<true><<<p->n_cta, SG_T, 0, st>>>(s->posm, rlo, rhi, slo, shi, p->rect ? 1 : 0, p->nsb, p->d_ctas, soft2, p->d_res, p->res_plane,
+		k_gravity_sym<true><<<p->n_cta, SG_T, 0, st>>>(s->posm, rlo, rhi, slo, shi, p->rpad, p->spad, p->rect ? 1 : 0, p->nsb, p->d_ctas, soft2, p->d_res, p->res_plane,
 				p->d_str, p->str_plane);
 	else
-		k_gravity_sym<false><<<p->n_cta, SG_T, 0, st>>>(s->posm, rlo, rhi, slo, shi, p->rect ? 1 : 0, p->nsb, p->d_ctas, soft2, p->d_res, p->res_plane,
+		k_gravity_sym<false><<<p->n_cta, SG_T, 0, st>>>(s->posm, rlo, rhi, slo, shi, p->rpad, p->spad, p->rect ? 1 : 0, p->nsb, p->d_ctas, soft2, p->d_res, p->res_plane,
 				p->d_str, p->str_plane);
 	LAUNCH_CHECK();
 	return ASS_OK;
@@ -446,14 +457,14 @@ int ass_launch_gravity_sym_finish(ass_sim* s, int rlo, int rhi, int slo, int shi
 	if (rc) return rc;
 	if (!p->rect) {
 		k_gravity_sym_reduce<<<(rhi - rlo + 255) / 256, 256, 0, s->stream>>>(p->d_res, p->res_plane, p->d_str, p->str_plane, p->d_cta_begin, p->nrb, rlo, rhi,
-				s->prm.G, p->uniform, s->posm, res_out, res_add ? 1 : 0);
+				p->rpad, s->prm.G, p->uniform, s->posm, res_out, res_add ? 1 : 0);
 		LAUNCH_CHECK();
 	} else {
 		// uniform: the rows are unweighted sums and every particle of both ranges has the mass of particle rlo
 		const double Gm = p->uniform ? s->prm.G * p->m_ref : s->prm.G;
-		k_gravity_rect_reduce_res<<<(rhi - rlo + 255) / 256, 256, 0, s->stream>>>(p->d_res, p->res_plane, p->d_cta_begin, rlo, rhi, Gm, res_out, res_add ? 1 : 0);
+		k_gravity_rect_reduce_res<<<(rhi - rlo + 255) / 256, 256, 0, s->stream>>>(p->d_res, p->res_plane, p->d_cta_begin, rlo, rhi, p->rpad, Gm, res_out, res_add ? 1 : 0);
 		LAUNCH_CHECK();
-		k_gravity_rect_reduce_str<<<(shi - slo + 255) / 256, 256, 0, s->stream>>>(p->d_str, p->str_plane, p->nrb, p->nsb, slo, shi, Gm, str_out, str_add ? 1 : 0);
+		k_gravity_rect_reduce_str<<<(shi - slo + 255) / 256, 256, 0, s->stream>>>(p->d_str, p->str_plane, p->nrb, p->nsb, slo, shi, p->spad, Gm, str_out, str_add ? 1 : 0);
 		LAUNCH_CHECK();
 	}
 	return ASS_OK;
