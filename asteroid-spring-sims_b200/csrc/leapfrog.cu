@@ -190,14 +190,17 @@ static int step_loop(ass_sim* s, int nsteps, bool with_hb) {
 		// (springs.cu: k_spring_steps).  Same kernels' code, same bits as one launch per step (tests).
 		if (have_springs && !grav && !hb && !s->lap_flush && nsteps - step >= 2 && mirror_fresh && ass_spring_steps_applicable(s)) {
 			const int batch = nsteps - step;
-			if ((rc = ass_launch_spring_steps(s, af == 2, dt, batch))) return rc;
-			for (int i = 0; i < batch; i++) {  // the clock advances as the reference's does: twice dt/2 per step
-				s->prm.t += dt / 2.;
-				s->prm.t += dt / 2.;
+			if ((rc = ass_launch_spring_steps(s, af == 2, dt, batch)) < 0) return rc;
+			if (rc == 0) {
+				for (int i = 0; i < batch; i++) {  // the clock advances as the reference's does: twice dt/2 per step
+					s->prm.t += dt / 2.;
+					s->prm.t += dt / 2.;
+				}
+				s->prm.dt_last_done = dt;
+				s->predrifted = false;
+				return ASS_OK;
 			}
-			s->prm.dt_last_done = dt;
-			s->predrifted = false;
-			return ASS_OK;
+			// (refused by the device: one launch per step below)
 		}
 		s->predrifted = false;
 		s->prm.t += dt / 2.;

@@ -738,7 +738,14 @@ static int launch_steps_t(ass_sim* s, double dt, int nsteps) {
 	vec4d *posm_out = s->posm_alt, *vel_out = s->vel_alt;
 	unsigned* bar = s->d_step_bar;
 	void* args[] = { &P, &mirA, &mirB, &acc, &tiles, &tab, &grpT, &warp_off, &heL, &palf, &posm_out, &vel_out, &dt, &nsteps, &bar };
-	CU_TRY(cudaLaunchCooperativeKernel((const void*) kern, dim3((unsigned) s->tiles_grid), dim3(TL_THREADS), args, smem, s->stream));
+	// A device that cannot hold the whole grid at once right now (another context's kernels, MPS limits) refuses the launch
+	// instead of dead-locking at the barrier: the caller then steps with one launch per step (return value 1).
+	const cudaError_t e = cudaLaunchCooperativeKernel((const void*) kern, dim3((unsigned) s->tiles_grid), dim3(TL_THREADS), args, smem, s->stream);
+	if (e == cudaErrorCooperativeLaunchTooLarge || e == cudaErrorLaunchOutOfResources || e == cudaErrorNotSupported) {
+		cudaGetLastError();
+		return 1;
+	}
+	CU_TRY(e);
 	return ASS_OK;
 }
 
@@ -830,7 +837,8 @@ bool ass_spring_steps_applicable(const ass_sim* s) {
 
 // nsteps whole steps without gravity, heartbeat or any other work between the spring evaluations, starting from pre-drifted
 // positions with a fresh mirror: step i = springs + kick + drift, and for all but the last the next step's part1.
-// On return posm / vel / acc hold the end-of-batch state (not pre-drifted); the mirror is stale.
+// On return posm / vel / acc hold the end-of-batch state (not pre-drifted); the mirror is stale.  Returns 1 (and has done
+// nothing) if the device refuses the cooperative launch: the caller falls back to one launch per step.
 int ass_launch_spring_steps(ass_sim* s, bool zero_first, double dt, int nsteps) {
 	if (s->n == 0 || nsteps <= 0) return ASS_OK;
 	bool uni;
@@ -842,7 +850,10 @@ int ass_launch_spring_steps(ass_sim* s, bool zero_first, double dt, int nsteps) 
 	if (zero_first) rc = uni ? ASS_STEPS_U(true, true) : ASS_STEPS_U(true, false);
 	else rc = uni ? ASS_STEPS_U(false, true) : ASS_STEPS_U(false, false);
 #undef ASS_STEPS_U
-	if (rc) return rc;
+	if (rc) {
+		if (rc > 0) ass_toc(s, ASS_K_SPRINGS);  // refused: nothing ran (the timer's interval stays balanced)
+		return rc;
+	}
 	LAUNCH_CHECK();
 	ass_toc(s, ASS_K_SPRINGS);
 	std::swap(s->posm, s->posm_alt);

@@ -279,10 +279,13 @@ def parity_of_sim(A, dist, sim, p0, springs, cfg, n_perts, rank, world, bounds):
             res["xv_vs_1gpu_max_abs"] = float(dev.max())
             res["xv_worst"] = {"particle": int(worst[0]), "column": "x y z vx vy vz".split()[int(worst[1])], "value_1gpu": float(w2[worst]),
                                "body_max_abs": float(dev[:n - n_perts].max()) if n > n_perts else None}
-            res["xv_tol"] = POS_TOL
+            # x, v follow the accelerations: two runs whose accelerations may differ by ACC_TOL * max|a| (different order of
+            # summation: other blocks, other slabs) may differ by steps * dt * that much in v.  (C4: max|a| ~ 1e4.)
+            res["max_abs_acc"] = amax
+            res["xv_tol"] = POS_TOL + 2 * cfg["dt"] * ACC_TOL * amax
         checks = [res.get("acc_vs_oracle") is not None and res["acc_vs_oracle"] <= ACC_TOL]
         if sharded:
-            checks += [res["acc_own_slab_vs_1gpu"] <= ACC_TOL, res["xv_vs_1gpu_max_abs"] <= POS_TOL]
+            checks += [res["acc_own_slab_vs_1gpu"] <= ACC_TOL, res["xv_vs_1gpu_max_abs"] <= res["xv_tol"]]
         res["ok"] = bool(all(checks))
     return res
 
@@ -776,12 +779,16 @@ def run_dropin_e2e(p0, springs, cfg, steps_b200=50, label=""):
         out = {"body": {"N": int(n), "NS": int(ns), "workload": label}, "what": "reb_integrate of tests/dropin/problem.cpp: heartbeat print at t = 0 (write_resolved_with_E incl. grav_potential_energy) + the steps"}
         out["reference"] = run("synth_ref", 1, {})
         out["b200_same_call"] = run("synth_b200", 1, {"ASS_RESIDENT": "1"})       # the reference's call, like for like
-        out["b200_coherent"] = run("synth_b200", steps_b200, {"ASS_RESIDENT": "0"})
-        out["b200_resident"] = run("synth_b200", steps_b200, {"ASS_RESIDENT": "1"})
+        # steady state per step: the difference of two runs of different length (the t = 0 print and the one-time set-up
+        # inside the first spring_forces -- the spring layout -- cancel)
+        for key, env in (("b200_coherent", {"ASS_RESIDENT": "0"}), ("b200_resident", {"ASS_RESIDENT": "1"})):
+            short, long_ = run("synth_b200", steps_b200, env), run("synth_b200", 3 * steps_b200, env)
+            out[key] = long_
+            if "integrate_s" in short and "integrate_s" in long_:
+                out[key]["ms_per_step"] = 1e3 * (long_["integrate_s"] - short["integrate_s"]) / (2 * steps_b200)
+                out[key]["shorter_run"] = {"steps": short["steps"], "integrate_s": short["integrate_s"]}
         try:
             out["speedup_same_call"] = out["reference"]["integrate_s"] / out["b200_same_call"]["integrate_s"]
-            for k in ("b200_coherent", "b200_resident"):   # steady state: the t = 0 print amortised over the steps
-                out[k]["ms_per_step"] = 1e3 * (out[k]["integrate_s"] - out["b200_same_call"]["integrate_s"]) / max(out[k]["steps"] - 1, 1)
             # the t = 0 print must agree: Etot column (22) of the history file
             # (columns are 14 wide; the power column after Etot overflows its width and runs into it: cut by position)
             e_ref = float(out["reference"]["res_row"][14 * 22:14 * 23]); e_gpu = float(out["b200_same_call"]["res_row"][14 * 22:14 * 23])
