@@ -343,6 +343,8 @@ __global__ void __launch_bounds__(TL_THREADS, 1) k_spring_steps(const __grid_con
 	for (int step = 0; step < nsteps; step++) {
 		const bool last = step == nsteps - 1;
 		const bool even = (step & 1) == 0;
+		// (a CTA without tiles still keeps in step: its arrivals must not run ahead of the others')
+		if (heads.h[blockIdx.x].ntiles == 0 && step > 0) grid_wait(bar, (unsigned) step * gridDim.x);
 		tiles_pass<ZERO_FIRST, true, UNI, PAL1>(heads.h[blockIdx.x], tile_smem, &s_next, even ? mirA : mirB, acc, tiles, tab, grpT, warp_off, heL, palf, nkg1,
 				posm_out, vel_out, even ? outB : outA, dt, last ? 0 : 1, last, step > 0 ? bar : nullptr, (unsigned) step * gridDim.x);
 		if (!last) grid_arrive(bar);
