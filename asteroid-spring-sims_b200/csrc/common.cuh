@@ -35,7 +35,7 @@ static_assert(sizeof(HalfEdge) == 16, "HalfEdge must be 16 bytes");
 static_assert(sizeof(ass_spring) == 32, "ass_spring must match struct spring (32 B)");
 
 #define ASS_L_EPS 1e-6  // src_spring/springs.cpp:28
-#define ASS_LEN2_TINY 1e-280  // squared spring lengths at or below this count as coincident endpoints (spring_math.cuh)
+#define ASS_LEN2_FLOOR 1e-300  // added to every squared spring length: exact above 1e-284, keeps coincident endpoints finite (spring_math.cuh)
 #ifndef ASS_SPRING_LANES
 #define ASS_SPRING_LANES 2
 #endif

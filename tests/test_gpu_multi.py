@@ -162,9 +162,14 @@ sys.path.insert(0, %r)
 import torch, torch.distributed as dist
 import asteroid_spring_sims_b200 as A
 rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"])
-torch.cuda.set_device(rank)
-dist.init_process_group("nccl", device_id=torch.device("cuda", rank))
-A.init(rank)
+one_gpu = os.environ.get("ASS_TEST_ONE_GPU") == "1"    # both ranks on GPU 0: two processes, two contexts, time-sliced
+dev = 0 if one_gpu else rank
+torch.cuda.set_device(dev)
+if one_gpu:
+    dist.init_process_group("gloo")                    # (NCCL refuses two ranks on one device; only handles are swapped)
+else:
+    dist.init_process_group("nccl", device_id=torch.device("cuda", dev))
+A.init(dev)
 g = np.load(os.path.join(%r, "tests", "golden", "c1_d010.npz"))
 p = g["start"].copy(); sp = g["springs"]; n = len(p); d = float(g["d"][0])
 prm = dict(t=0.0, dt=2e-3, G=1.0, softening=d / 100.0, gravity=1, additional_forces=1)
@@ -202,6 +207,20 @@ def test_ipc_two_ranks(gpu, tmp_path):
                         "--master-port", "29541", str(script)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:]
     assert r.stdout.count("ok") >= 2, r.stdout[-3000:]   # both ranks print "rank <r> ok" (their lines may interleave)
+
+
+def test_ipc_two_ranks_on_one_gpu(gpu, tmp_path):
+    """The same two processes on ONE GPU (what a single-GPU test box can run): separate CUDA contexts, the windows mapped
+    through CUDA IPC, the ranks meeting through the device-side flags while the driver time-slices the two contexts -- a
+    missing flag, a stale window or a wrong epoch shows here exactly as it would across GPUs (only slower: a waiting
+    kernel spins through its time slice)."""
+    script = tmp_path / "worker.py"
+    script.write_text(IPC_WORKER % (ROOT, ROOT))
+    env = dict(os.environ, ASS_TEST_ONE_GPU="1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29543", str(script)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600, env=env)
+    assert r.returncode == 0, r.stdout[-3000:]
+    assert r.stdout.count("ok") >= 2, r.stdout[-3000:]
 
 
 def test_ensemble_more_members_than_sms(gpu):
