@@ -443,7 +443,9 @@ static int build_tiles_host(const SpringLayout& lay, int grid, int slots_limit, 
 	out.grid = grid;
 	auto pairs = [&](int w) { return (lay.warp_off[(size_t) w + 1] - lay.warp_off[w]) >> 6; };
 	std::vector<double> prefix((size_t) ns + 1, 0.0);
-	for (int w = 0; w < ns; w++) prefix[(size_t) w + 1] = prefix[w] + (double) pairs(w) + 0.75;
+	double slice_weight = 0.75;  // a slice's own work (header, own state, fold, epilogue) in pairs of steps
+	if (const char* e = getenv("ASS_TILE_SLICE_WEIGHT")) slice_weight = atof(e);
+	for (int w = 0; w < ns; w++) prefix[(size_t) w + 1] = prefix[w] + (double) pairs(w) + slice_weight;
 	std::vector<int> cut((size_t) grid + 1, 0);
 	{
 		int w = 0;
@@ -654,6 +656,7 @@ extern "C" int ass_selfcheck_spring_layout(const double* pos_xyzm, int n, const 
 			const TileDesc& T = th.tiles[t];
 			if (T.s0 != expect || T.s1 <= T.s0 || (T.n_slots & 7) || T.n_slots > th.slots_max || T.s1 - T.s0 > th.slices_max) viol++;
 			if (T.n_slots > slots_limit && T.s1 - T.s0 > 1) viol++;
+			if (tile_bytes(T.n_slots, T.s1 - T.s0) > TILE_BYTES_LIMIT || tile_bytes(T.n_slots, T.s1 - T.s0) > th.bytes_max) viol++;  // fits next to the record rings
 			expect = T.s1;
 			for (int i = 0; i < T.n_slots; i++) {
 				const int r = th.tab[(size_t) T.tab_off + i];

@@ -72,3 +72,24 @@ def test_layout_rejects_bad_springs(A):
     for pairs in ([(1, 1)], [(0, 4)], [(-1, 2)]):                      # springs.cpp:57-59 throws on i == j
         with pytest.raises(A.AssError):
             A.selfcheck_spring_layout(p, springs_of(A, pairs))
+
+
+def test_layout_invariants_on_random_graphs(A):
+    """Random sparse and dense graphs on random point sets, several grids and table sizes: every invariant the kernels rely on
+    (rows complete, transposed copy == CSR copy, padding points at the node itself, tiles partition the slices and fit in shared
+    memory next to the record rings, renumbered records lead back to the same ranks)."""
+    hypothesis = pytest.importorskip("hypothesis")
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=40, deadline=None)
+    @given(n=st.integers(2, 160), density=st.floats(0.01, 0.6), seed=st.integers(0, 10 ** 6), grid=st.sampled_from([1, 2, 5, 148]),
+           slots=st.sampled_from([64, 200, 1000, 1 << 20]))
+    def check(n, density, seed, grid, slots):
+        rng = np.random.default_rng(seed)
+        p = np.zeros((n, 11)); p[:, :3] = rng.uniform(-1, 1, (n, 3)); p[:, 9] = rng.uniform(0.5, 2.0, n)
+        pairs = [(i, j) for i in range(n) for j in range(i + 1, n) if rng.random() < density]
+        stt = A.selfcheck_spring_layout(p, springs_of(A, pairs), grid=grid, slots=slots)
+        assert stt["violations"] == 0
+        assert stt["records"] == 2 * len(pairs) + stt["padding"]
+
+    check()
