@@ -33,23 +33,21 @@
 
 namespace {
 
-#ifndef ASS_SYM_RESIDENTS
-#define ASS_SYM_RESIDENTS 4
-#endif
-#ifndef ASS_SYM_CTAS_PER_SM
-#define ASS_SYM_CTAS_PER_SM 2
-#endif
 constexpr int SG_T = 256;            // threads per CTA
 constexpr int SG_W = SG_T / 32;      // warps
-constexpr int SG_R = ASS_SYM_RESIDENTS;  // resident particles per thread (4 with 2 CTAs per SM; 3 with 3 was measured: profiles/r2_gravity_variants.md)
-constexpr int SG_OCC = ASS_SYM_CTAS_PER_SM;
-constexpr int SG_P = SG_T * SG_R;    // particles per block (1024)
+// Resident particles per thread R and CTAs per SM come in two compiled variants, chosen per plan (get_plan):
+//   R = 4, 2 CTAs / SM (128 registers): blocks of 1024 -- small problems (a ~1e4-particle body, the slabs of C3 / 8): fewer,
+//          fatter tiles quantise them better and every streamed particle's shared-memory load and shuffles serve 4 pairs;
+//   R = 3, 3 CTAs / SM (80 registers): blocks of 768, six warps per scheduler -- large problems: +1.9 % at C3
+//          (profiles/r2_gravity_variants.md), where the FP64 pipe idles 20 % of the time with four warps per scheduler.
+constexpr int SG_R_MAX = 4;
+constexpr int sg_occ(int R) { return R == 3 ? 3 : 2; }
 constexpr int SG_TILE = 128;         // streamed particles between block-wide reductions (4 chunks of 32)
 
 struct SymCta {
 	int rb, s0, s1;  // resident block, streamed blocks [s0, s1); a streamed block equal to rb is the diagonal tile
 	int t_lo, t_hi;  // streamed particles [t_lo, t_hi) of each of those blocks (multiples of 32); the whole block is
-	                 // [0, SG_P).  Bodies of ~1e4 particles have too few tiles to fill the machine: their tiles are cut.
+	                 // [0, P).  Bodies of ~1e4 particles have too few tiles to fill the machine: their tiles are cut.
 };
 
 __device__ __forceinline__ vec4d load_or_dummy(const vec4d* __restrict__ posm, int idx, int lo, int hi) {
@@ -74,7 +72,7 @@ __device__ __forceinline__ double rsqrt_seed(double a) {
 // One streamed particle meets the thread's SG_R residents.  Written stage by stage across the residents (not resident
 // by resident) so the SG_R dependent chains are interleaved in program order: FP64 results are needed several issue
 // slots after they are produced and the warp does not sit in fixed-latency waits.
-template <bool DIAG, bool UNI>
+template <bool DIAG, bool UNI, int SG_R>
 __device__ __forceinline__ void meet(const double2 xy, const double2 zm, int sidx, const double (&rx)[SG_R], const double (&ry)[SG_R],
 		const double (&rz)[SG_R], const double (&rm)[SG_R], const int (&ridx)[SG_R], double (&rax)[SG_R], double (&ray)[SG_R],
 		double (&raz)[SG_R], double& sax, double& say, double& saz, double soft2) {
@@ -143,11 +141,12 @@ __device__ __forceinline__ void meet(const double2 xy, const double2 zm, int sid
 // Resident particles come from [rlo, rhi), streamed particles from [slo, shi).  rect == 0: the two ranges are the same
 // range and the tiles are its lower triangle incl. the diagonal; rect != 0: the ranges are disjoint (two slabs of a
 // sharded body) and the tiles are the full rectangle, nsb streamed blocks wide.
-template <bool UNI>
-__global__ void __launch_bounds__(SG_T, SG_OCC) k_gravity_sym(const vec4d* __restrict__ posm, int rlo, int rhi, int slo, int shi, int rpad, int spad, int rect,
+template <bool UNI, int SG_R>
+__global__ void __launch_bounds__(SG_T, sg_occ(SG_R)) k_gravity_sym(const vec4d* __restrict__ posm, int rlo, int rhi, int slo, int shi, int rpad, int spad, int rect,
 		int nsb, const SymCta* __restrict__ ctas, double soft2, double* __restrict__ res, size_t res_plane, double* __restrict__ str, size_t str_plane) {
 	__shared__ double2 s_xy[SG_TILE], s_zm[SG_TILE];
 	__shared__ double s_acc[SG_W][3][SG_TILE];
+	constexpr int SG_P = SG_T * SG_R;  // particles per block
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const SymCta C = ctas[blockIdx.x];
 
@@ -184,13 +183,13 @@ __global__ void __launch_bounds__(SG_T, SG_OCC) k_gravity_sym(const vec4d* __res
 #pragma unroll 2
 					for (int s = 0; s < 32; s++) {
 						const int q = c0 + ((lane + s) & 31);
-						meet<true, UNI>(s_xy[q], s_zm[q], sbase + t0 + q, rx, ry, rz, rm, ridx, rax, ray, raz, sax, say, saz, soft2);
+						meet<true, UNI, SG_R>(s_xy[q], s_zm[q], sbase + t0 + q, rx, ry, rz, rm, ridx, rax, ray, raz, sax, say, saz, soft2);
 					}
 				} else {
 #pragma unroll 2
 					for (int s = 0; s < 32; s++) {
 						const int q = c0 + ((lane + s) & 31);
-						meet<false, UNI>(s_xy[q], s_zm[q], 0, rx, ry, rz, rm, ridx, rax, ray, raz, sax, say, saz, soft2);
+						meet<false, UNI, SG_R>(s_xy[q], s_zm[q], 0, rx, ry, rz, rm, ridx, rax, ray, raz, sax, say, saz, soft2);
 						// the streamed particle moves on to the lane below; take over the one from the lane above
 						sax = __shfl_sync(0xffffffffu, sax, (lane + 1) & 31);
 						say = __shfl_sync(0xffffffffu, say, (lane + 1) & 31);
@@ -227,7 +226,7 @@ __global__ void __launch_bounds__(SG_T, SG_OCC) k_gravity_sym(const vec4d* __res
 // order.  be[2b], be[2b+1] = the CTAs whose resident block is b.  uniform != 0: the rows hold unweighted sums and every
 // particle has the mass of particle `lo`.  add != 0: out[i] += a_i instead of out[i] = a_i.
 __global__ void k_gravity_sym_reduce(const double* __restrict__ res, size_t res_plane, const double* __restrict__ str, size_t str_plane,
-		const int* __restrict__ be, int nb, int lo, int hi, int pad, double G, int uniform, const vec4d* __restrict__ posm, vec4d* __restrict__ out, int add) {
+		const int* __restrict__ be, int nb, int lo, int hi, int pad, int SG_P, double G, int uniform, const vec4d* __restrict__ posm, vec4d* __restrict__ out, int add) {
 	const int i = lo + blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= hi) return;
 	if (uniform) G *= posm[lo].w;
@@ -248,7 +247,7 @@ __global__ void k_gravity_sym_reduce(const double* __restrict__ res, size_t res_
 }
 
 // Rectangle plans, resident side: a_i = +G * (rows of the CTAs whose resident block holds i), i in [rlo, rhi)
-__global__ void k_gravity_rect_reduce_res(const double* __restrict__ res, size_t res_plane, const int* __restrict__ be, int rlo, int rhi, int rpad, double Gm,
+__global__ void k_gravity_rect_reduce_res(const double* __restrict__ res, size_t res_plane, const int* __restrict__ be, int rlo, int rhi, int rpad, int SG_P, double Gm,
 		vec4d* __restrict__ out, int add) {
 	const int i = rlo + blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= rhi) return;
@@ -265,7 +264,7 @@ __global__ void k_gravity_rect_reduce_res(const double* __restrict__ res, size_t
 }
 
 // Rectangle plans, streamed side: a_j = -G * (rows of column block b over all resident blocks), j in [slo, shi)
-__global__ void k_gravity_rect_reduce_str(const double* __restrict__ str, size_t str_plane, int nrb, int nsb, int slo, int shi, int spad, double Gm,
+__global__ void k_gravity_rect_reduce_str(const double* __restrict__ str, size_t str_plane, int nrb, int nsb, int slo, int shi, int spad, int SG_P, double Gm,
 		vec4d* __restrict__ out, int add) {
 	const int j = slo + blockIdx.x * blockDim.x + threadIdx.x;
 	if (j >= shi) return;
@@ -294,6 +293,7 @@ struct SymPlan {
 	int rlo = -1, rhi = -1, slo = -1, shi = -1;  // resident / streamed ranges (identical: triangle; disjoint: rectangle)
 	bool rect = false;
 	int nrb = 0, nsb = 0, n_cta = 0;
+	int R = 4, P = 1024;        // residents per thread and particles per block of the kernel variant this plan runs
 	int rpad = 0, spad = 0;     // dummies in front of block 0 of the resident / streamed range (blocks are counted from lo - pad)
 	long long mass_epoch = -1;  // masses the `uniform` verdict was taken from (ass_sim::mass_epoch)
 	int uniform = 0;
@@ -316,8 +316,9 @@ void ass_sym_plans_free(ass_sim* s) {
 }
 
 // Is the pair-once kernel worth it for this many particles?  It needs enough (possibly cut) tiles to fill the machine:
-// a tile can be cut into SG_P / SG_TILE pieces.
+// a tile (blocks of 1024) can be cut into 8 pieces.
 bool ass_gravity_sym_applicable(int count) {
+	constexpr int SG_P = SG_T * SG_R_MAX;
 	const long long nb = (count + SG_P - 1) / SG_P;
 	return nb * (nb + 1) / 2 * (SG_P / SG_TILE) >= 2LL * ass_sm_count();  // (threshold as measured with pieces of 128)
 }
@@ -350,6 +351,15 @@ static int get_plan(ass_sim* s, int rlo, int rhi, int slo, int shi, SymPlan** ou
 	SymPlan* plan = new SymPlan();
 	plan->rlo = rlo; plan->rhi = rhi; plan->slo = slo; plan->shi = shi;
 	plan->rect = !(rlo == slo && rhi == shi);
+	// which kernel variant: three residents per thread (blocks of 768, three CTAs per SM) for large problems, four otherwise
+	{
+		const long long b4r = (rhi - rlo + 1023) / 1024, b4s = (shi - slo + 1023) / 1024;
+		const long long tiles4 = plan->rect ? b4r * b4s : b4r * (b4r + 1) / 2;
+		plan->R = tiles4 >= 2000 ? 3 : 4;
+		if (const char* e = getenv("ASS_SYM_R")) { const int r = atoi(e); if (r == 3 || r == 4) plan->R = r; }
+		plan->P = SG_T * plan->R;
+	}
+	const int SG_P = plan->P;
 	const int nrb = (rhi - rlo + SG_P - 1) / SG_P, nsb = (shi - slo + SG_P - 1) / SG_P;
 	plan->nrb = nrb; plan->nsb = nsb;
 	// The range's partial block is block 0, its padding in FRONT: block 0 is the streamed side of all its off-diagonal tiles
@@ -360,7 +370,7 @@ static int get_plan(ass_sim* s, int rlo, int rhi, int slo, int shi, SymPlan** ou
 	plan->spad = nsb * SG_P - (shi - slo);
 	const long long tiles = plan->rect ? (long long) nrb * nsb : (long long) nrb * (nrb + 1) / 2;
 	// tiles per CTA: enough CTAs (>= ~16 per resident slot) for the block scheduler to balance, few enough rows
-	const long long slots = (long long) SG_OCC * ass_sm_count();
+	const long long slots = (long long) sg_occ(plan->R) * ass_sm_count();
 	int U = (int) std::max(1LL, tiles / (slots * 16));
 	// few tiles (N ~ 1e4): cut every tile's streamed side into `cut` pieces so that ~2 CTAs per slot exist
 	// (measured and dropped: the coarsest cut with the shortest makespan in whole rounds of CTAs -- an SM with one
@@ -440,12 +450,12 @@ int ass_launch_gravity_sym_main(ass_sim* s, int rlo, int rhi, int slo, int shi, 
 	int rc = get_plan(s, rlo, rhi, slo, shi, &p);
 	if (rc) return rc;
 	const double soft2 = s->prm.softening * s->prm.softening;
-	if (p->uniform)
-		k_gravity_sym<true><<<p->n_cta, SG_T, 0, st>>>(s->posm, rlo, rhi, slo, shi, p->rpad, p->spad, p->rect ? 1 : 0, p->nsb, p->d_ctas, soft2, p->d_res, p->res_plane,
-				p->d_str, p->str_plane);
-	else
-		k_gravity_sym<false><<<p->n_cta, SG_T, 0, st>>>(s->posm, rlo, rhi, slo, shi, p->rpad, p->spad, p->rect ? 1 : 0, p->nsb, p->d_ctas, soft2, p->d_res, p->res_plane,
-				p->d_str, p->str_plane);
+#define ASS_SYM_LAUNCH(U, R)                                                                                                                     \
+	k_gravity_sym<U, R><<<p->n_cta, SG_T, 0, st>>>(s->posm, rlo, rhi, slo, shi, p->rpad, p->spad, p->rect ? 1 : 0, p->nsb, p->d_ctas, soft2, p->d_res, \
+			p->res_plane, p->d_str, p->str_plane)
+	if (p->R == 3) { if (p->uniform) ASS_SYM_LAUNCH(true, 3); else ASS_SYM_LAUNCH(false, 3); }
+	else { if (p->uniform) ASS_SYM_LAUNCH(true, 4); else ASS_SYM_LAUNCH(false, 4); }
+#undef ASS_SYM_LAUNCH
 	LAUNCH_CHECK();
 	return ASS_OK;
 }
@@ -457,14 +467,14 @@ int ass_launch_gravity_sym_finish(ass_sim* s, int rlo, int rhi, int slo, int shi
 	if (rc) return rc;
 	if (!p->rect) {
 		k_gravity_sym_reduce<<<(rhi - rlo + 255) / 256, 256, 0, s->stream>>>(p->d_res, p->res_plane, p->d_str, p->str_plane, p->d_cta_begin, p->nrb, rlo, rhi,
-				p->rpad, s->prm.G, p->uniform, s->posm, res_out, res_add ? 1 : 0);
+				p->rpad, p->P, s->prm.G, p->uniform, s->posm, res_out, res_add ? 1 : 0);
 		LAUNCH_CHECK();
 	} else {
 		// uniform: the rows are unweighted sums and every particle of both ranges has the mass of particle rlo
 		const double Gm = p->uniform ? s->prm.G * p->m_ref : s->prm.G;
-		k_gravity_rect_reduce_res<<<(rhi - rlo + 255) / 256, 256, 0, s->stream>>>(p->d_res, p->res_plane, p->d_cta_begin, rlo, rhi, p->rpad, Gm, res_out, res_add ? 1 : 0);
+		k_gravity_rect_reduce_res<<<(rhi - rlo + 255) / 256, 256, 0, s->stream>>>(p->d_res, p->res_plane, p->d_cta_begin, rlo, rhi, p->rpad, p->P, Gm, res_out, res_add ? 1 : 0);
 		LAUNCH_CHECK();
-		k_gravity_rect_reduce_str<<<(shi - slo + 255) / 256, 256, 0, s->stream>>>(p->d_str, p->str_plane, p->nrb, p->nsb, slo, shi, p->spad, Gm, str_out, str_add ? 1 : 0);
+		k_gravity_rect_reduce_str<<<(shi - slo + 255) / 256, 256, 0, s->stream>>>(p->d_str, p->str_plane, p->nrb, p->nsb, slo, shi, p->spad, p->P, Gm, str_out, str_add ? 1 : 0);
 		LAUNCH_CHECK();
 	}
 	return ASS_OK;

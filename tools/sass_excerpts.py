@@ -12,7 +12,8 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "asteroid-spring-sims_b200", "libass_b200.so")
 WANT = [
-    ("gravity_sym_uniform", r"k_gravity_symILb1E"),
+    ("gravity_sym_uniform_r3", r"k_gravity_symILb1ELi3E"),
+    ("gravity_sym_uniform_r4", r"k_gravity_symILb1ELi4E"),
     ("gravity_one_sided_ti4", r"k_gravityILi4ELb0E"),
     ("fp64_peak_probe", r"k_dfmaE"),
     ("spring_tiles_kick_uni_pal1", r"k_spring_tilesILb0ELb1ELb1ELb1E"),
