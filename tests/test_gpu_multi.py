@@ -156,6 +156,44 @@ def test_sharded_body_in_process(gpu, oracle, body010, nranks):
         s.close()
 
 
+def test_sharded_gravity_streams_and_serial_order_agree(gpu, body010, monkeypatch):
+    """The rectangle / antipodal pair kernels of a rank run on streams of their own next to the triangle (shard.cu);
+    ASS_SHARD_SERIAL_GRAVITY=1 queues them one after the other on the main stream.  Same scratch, same fixed-order reductions:
+    the gathered body must come out bit for bit the same (four ranks in this process, with a point mass)."""
+    g = body010
+    d = float(g["d"][0])
+    pert = np.zeros((1, 11)); pert[0, :3] = (7.0, 0.0, 0.0); pert[0, 4] = 0.4; pert[0, 9] = 1.0
+    p = np.vstack([g["start"].copy(), pert])
+    n = len(p)
+    prm = dict(t=0.0, dt=2e-3, G=1.0, softening=d / 100.0, gravity=1, additional_forces=1, n_perts=1)
+    nranks = 4
+    bounds = gpu.slab_bounds(n, nranks, align=256)
+    res = []
+    for serial in ("1", None):
+        if serial is None:
+            monkeypatch.delenv("ASS_SHARD_SERIAL_GRAVITY", raising=False)
+        else:
+            monkeypatch.setenv("ASS_SHARD_SERIAL_GRAVITY", serial)
+        sims = []
+        for r in range(nranks):
+            s = gpu.Sim(); s.upload(p); s.set_springs(g["springs"]); s.set_params(**prm); s.shard_setup(r, nranks, bounds)
+            sims.append(s)
+        for r in range(nranks):
+            for q in range(nranks):
+                if q != r:
+                    sims[r].shard_import_local(q, sims[q])
+        for s in sims: s.shard_step(3)
+        for s in sims: s.shard_gather()
+        for s in sims: s.sync()
+        outs = [s.download(p.copy()) for s in sims]
+        for s in sims: s.close()
+        res.append(outs)
+    for r in range(nranks):
+        lo, hi = bounds[r], bounds[r + 1]
+        assert same_bits(res[0][r][:, :6], res[1][r][:, :6])
+        assert same_bits(res[0][r][lo:hi, 6:9], res[1][r][lo:hi, 6:9])
+
+
 IPC_WORKER = r"""
 import os, sys, numpy as np
 sys.path.insert(0, %r)

@@ -768,3 +768,38 @@ def test_connect_and_mindist_survive_non_finite_positions(gpu, oracle, body015):
     assert md == oracle.mindist(q, n2=True)
     with new_sim(gpu, np.full((4, 11), np.nan)) as s:      # nothing finite at all
         assert len(s.connect_springs_dist(1.0, 0, 4, K, GAMMA)) == 0
+
+
+def test_step_timed_is_the_same_loop(gpu, body015):
+    """ass_step_timed (bench.py's timer: L2 overwritten before every step, a device-timed lap around every step's kernels)
+    runs the very loop ass_step runs: same bits afterwards, with and without gravity; it returns the summed laps."""
+    g = body015
+    start = g["start"].copy(); start[:, 6:9] = 0.0
+    for grav, af in ((1, 1), (0, 2)):
+        outs = []
+        for timed in (False, True):
+            with new_sim(gpu, start, g["springs"], gravity=grav, dt=1e-3, additional_forces=af, softening=1e-3) as s:
+                ms = s.step_timed(5) if timed else s.step(5)
+                if timed:
+                    assert 0.0 < ms < 1e3
+                outs.append((s.download(start.copy()), s.params.t))
+        assert same_bits(outs[0][0], outs[1][0]) and outs[0][1] == outs[1][1]
+
+
+def test_gravity_pieces_on_concurrent_streams_give_the_same_bits(gpu, body010):
+    """What a rank of a sharded body queues per step -- its own triangle and rectangles against other slabs -- as pair kernels on
+    streams of their own with the reductions afterwards (ass_probe_gravity_pieces, concurrent = 1) leaves exactly the
+    accelerations the same pieces leave one after the other: the kernels write disjoint scratch, the reductions keep their order."""
+    p = np.vstack([body010["start"]] * 9)            # 9 585 particles: enough blocks for the pair-once tiles
+    p[:, :3] += np.repeat(np.arange(9), len(body010["start"]))[:, None] * 3.0
+    n = len(p)
+    a, b, c = n // 4, n // 2, (3 * n) // 4
+    pieces = [(0, a, 0, a), (0, a, a, c), (0, a // 2, c, n)]
+    outs = []
+    for conc in (0, 1):
+        with new_sim(gpu, p, None, gravity=1, dt=1e-3, G=1.0, softening=1e-3) as s:
+            ms = s.probe_gravity_pieces(pieces, conc, reps=2)
+            assert ms > 0.0
+            outs.append(s.download(p.copy())[:a, 6:9].copy())
+    assert same_bits(outs[0], outs[1])
+    assert np.isfinite(outs[0]).all() and np.abs(outs[0]).max() > 0.0
