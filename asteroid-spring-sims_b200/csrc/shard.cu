@@ -628,7 +628,9 @@ void ass_shard_release(ass_sim* s) {
 	for (int q = 0; q < 3; q++) {
 		if (sh.grav_stream[q]) { cudaStreamSynchronize(sh.grav_stream[q]); cudaStreamDestroy(sh.grav_stream[q]); }
 		if (sh.grav_done[q]) cudaEventDestroy(sh.grav_done[q]);
+		sh.grav_stream[q] = nullptr; sh.grav_done[q] = nullptr;
 	}
+	sh.copy_stream = nullptr; sh.pulled = nullptr; sh.drifted = nullptr;
 	// posm / vel and their alt twins alias the window: free it once and clear the aliases
 	cudaFree(sh.window);
 	s->posm = s->vel = s->posm_alt = s->vel_alt = nullptr;
