@@ -9,7 +9,7 @@
 // The arithmetic is in spring_math.cuh.
 //
 // Algorithmic traffic: 32 B x NS + 80 B x N per evaluation.  Real DRAM traffic of the tiled kernel (ncu, C3):
-// 35 B x NS of half-edge stream (two 16-byte records per spring, + 11 % padding) + ~150 B x N of mirror, acc and outputs;
+// 34 B x NS of half-edge stream (two 16-byte records per spring, + 7 % padding) + ~150 B x N of mirror, acc and outputs;
 // the 48 B gathered per half-edge come out of shared memory, the tables are filled from L2 (~3 x 56 B x N).
 #include <stdlib.h>
 #include <string.h>
@@ -143,23 +143,27 @@ __global__ void __launch_bounds__(BLOCK) k_spring_forces(const GlobalNodes nodes
 //
 // A warp owns 32 / SPRING_LANES nodes of similar degree -- a SLICE -- and walks their rows in lock step: step t of lane
 // l is ONE record at warp_off + 32 t + l, so a step of the warp is 512 contiguous bytes and the trip count is the same
-// for every lane (no votes, no divergence, no per-row bookkeeping; spring_math.cuh: lane_spring_sum).
+// for every lane (no votes, no divergence, no per-row bookkeeping; spring_math.cuh: lane_spring_sum_ring).
 // Endpoint state comes out of SHARED memory.  Gathering it through L1 (an earlier version of this kernel) is bounded
-// by latency: even at a 90 % L1 hit rate nearly every warp-wide request contains a miss, and ~120 registers per thread
-// leave four warps per scheduler to hide it; the ensemble kernel, which gathers from shared memory, spends half the
-// time per half-edge.  So the body is treated like an ensemble of TILES.  CTAs are persistent, one per SM; CTA c owns
-// a contiguous run of slices (cut on the host so that every CTA carries the same number of step pairs), cut further
-// into tiles whose nodes AND all their neighbours (~3 x as many: 14 MB of L2 reads per evaluation at C3) fit in a
-// shared-memory table.  Per tile the CTA copies that state from the rank-ordered mirror into the table (and the
-// tile's slice headers next to it), then its sixteen warps pull slices from a counter -- no warp waits for a longer
-// share -- and run the arithmetic with table slots in place of ranks (heL: records renumbered on the host, slot =
-// rank mod 8 so the bank-group-aware row order still holds).  Records come straight from L2 / HBM, one pair of steps
-// ahead of the arithmetic, and a slice's records are requested into L2 while the slice before it is worked on.
-// Padding records (rows shorter than the slice's longest) point at the node itself and enter the sum with a zero
-// coefficient.  Same rows, same lanes, same order of summation as the CSR kernel: identical bits (tests).
-// (Streaming the records through per-warp bulk-copy rings, with the slices dealt round-robin so a warp's stream is
-// known in advance, was built and measured slower -- 32 us against 28 at C3: the polling and the fixed shares cost more
-// than the deeper prefetch saves.)
+// by latency: even at a 90 % L1 hit rate nearly every warp-wide request contains a miss; the ensemble kernel, which
+// gathers from shared memory, spends half the time per half-edge.  So the body is treated like an ensemble of TILES.
+// CTAs are persistent, one per SM; CTA c owns a contiguous run of slices (cut on the host so that every CTA carries the
+// same number of step pairs), cut further into tiles whose nodes AND all their neighbours (~3 x as many: 14 MB of L2
+// reads per evaluation at C3) fit in a shared-memory table.  Per tile the CTA copies that state from the rank-ordered
+// mirror into the table with cp.async, in two dependent round trips (table entries and slice headers, then the state:
+// tiles_pass), then its sixteen warps pull slices from a counter -- no warp waits for a longer share -- and run the
+// arithmetic with table slots in place of ranks (heL: records renumbered on the host, slot = rank mod 8 so the
+// bank-group-aware row order still holds).  A warp's records reach it through a ring of four 1 KB slots in shared memory
+// that the warp fills itself with cp.async, two pairs of steps ahead of the arithmetic and across slice boundaries
+// (spring_math.cuh: RecordStream): bytes in flight do not cost registers.  Padding records (rows shorter than the
+// slice's longest) point at the node itself: d = 0, a zero contribution.  Same rows, same lanes, same order of summation
+// as the CSR kernel: identical bits (tests).
+// Shared memory of a CTA: [record rings, 64 KB][table of the current tile][its slice headers]; tiles are cut against
+// what the rings leave (TILE_BYTES_LIMIT).
+// What bounds it (profiles/r2_spring_kernel_designs.md): instruction issue -- every spring is evaluated at both
+// endpoints, 36 FP64 instructions each, and an FP64 instruction holds the issue port for two cycles.
+// (Built and measured slower: per-warp bulk-copy rings with slices dealt round-robin; records two pairs ahead in
+// registers; requests into L2 32 slices ahead; 768 / 1024 threads with one chain per lane; 1 or 4 lanes per node.)
 // ---------------------------------------------------------------------------------------------------
 #ifndef ASS_TILE_THREADS
 #define ASS_TILE_THREADS 512
