@@ -399,6 +399,11 @@ def run_single(args, A, name, cfg, local, want_e2e=True, want_cpu=True, steps=No
         ach = alg * s_n / (s_ms * 1e-3) / 1e9
         roof_s = {"kernel": "k_spring_tiles<KICK> (springs + kick + drift)", "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
                   "traffic": traffic.get("springs"), "peak_source": hbm_src, "algorithmic_bytes_per_launch": alg, "ms_per_launch": s_ms / s_n}
+        # what actually bounds this formulation: every spring is evaluated at both endpoints, 36 FP64 instructions
+        # each, and an FP64 warp instruction holds its sub-partition's issue port for two cycles
+        t_issue_ms = 2 * ns * 36 / 32.0 * 2.0 / (4 * 148) / 1.965e9 * 1e3
+        roof_s["fp64_issue"] = {"fp64_instructions_per_spring": 72, "ms_at_full_fp64_issue_rate": t_issue_ms, "frac": t_issue_ms / (s_ms / s_n),
+                                "note": "2 x 36 FP64 warp-instructions per 32 springs, 2 issue cycles each, 592 sub-partitions at 1.965 GHz; padding records not counted"}
     dominant = roof_g if (roof_g and g_ms >= s_ms) else roof_s
 
     # ---- CPU baseline: the unmodified reference on this host, bounded sample ----
