@@ -127,7 +127,9 @@ int ass_leapfrog_part1(ass_sim* sim); /* reb_integrator_leapfrog_part1, src/inte
 int ass_leapfrog_part2(ass_sim* sim); /* reb_integrator_leapfrog_part2, src/integrator_leapfrog.c:52-67 */
 /* reb_step (src/rebound.c:69-144) x nsteps with the built-in additional_forces of params.additional_forces, fused
  * (gravity -> springs+kick+drift) and without returning to the host between steps.  with_heartbeat != 0 runs the
- * built-in heartbeat (params.heartbeat) after each step, as reb_integrate_raw does (src/rebound.c:640-641). */
+ * built-in heartbeat (params.heartbeat) after each step, as reb_integrate_raw does (src/rebound.c:640-641).
+ * Where nothing but the spring forces separates the steps (params.gravity == 0, or additional_forces == 2, and no
+ * heartbeat due) the whole batch runs as ONE cooperative launch with a grid barrier per step; same bits either way. */
 int ass_step(ass_sim* sim, int nsteps, int with_heartbeat);
 /* reb_integrate (src/rebound.c:621-704): heartbeat at t=0, then steps until tmax with reb_check_exit's
  * exact_finish_time handling (src/rebound.c:509-569).  Returns the REB_STATUS (>= 0) or a negative error. */
