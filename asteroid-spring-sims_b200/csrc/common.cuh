@@ -167,11 +167,12 @@ struct ass_sim {
 	HalfEdge* heL = nullptr;
 	int4* grpT = nullptr;
 	int* tile_tab = nullptr;
+	int* tile_sl_ord = nullptr;  // per tile: the order in which its slices are handed out (local indices; the longest first after the warps' fixed first ones)
 	int4* tile_desc = nullptr;  // (first slice, end slice, offset into tile_tab, slots)
 	std::vector<int> tile_heads;  // per CTA: (first tile, tile count, first tile's descriptor, last slice): kernel parameters
 	int tiles_grid = 0, tile_slots_max = 0, tile_slices_max = 0;
 	size_t tile_bytes_max = 0;  // shared memory of the largest tile (table + slice headers)
-	size_t heL_cap = 0, grpT_cap = 0, tile_tab_cap = 0, tile_desc_cap = 0;
+	size_t heL_cap = 0, grpT_cap = 0, tile_tab_cap = 0, tile_desc_cap = 0, tile_sl_ord_cap = 0;
 	double2* pal = nullptr;   // palette of distinct (k, gamma) pairs
 	double2* palf = nullptr;  // the same entries as the force kernels want them: (-k, -max(gamma, 0)); lives behind pal
 	int n_pal = 0;

@@ -57,7 +57,7 @@ __device__ __forceinline__ vec4d ldcg4(const vec4d* p) {
 // All per-node arrays (posm_g, vel_g, acc_g, ord) are in the member's rank order.
 template <bool UNI, bool PAL1>
 __global__ void __launch_bounds__(ET, 1) k_ensemble(const BodyDesc* __restrict__ desc, vec4d* __restrict__ posm_g, vec4d* __restrict__ vel_g,
-		vec4d* __restrict__ acc_g, const int* __restrict__ ord, const int2* __restrict__ grp, const int* __restrict__ warp_off,
+		vec4d* __restrict__ acc_g, const int* __restrict__ ord, const int2* __restrict__ grp, const int* __restrict__ sord, const int* __restrict__ warp_off,
 		const HalfEdge* __restrict__ heT, const double2* __restrict__ palf, int nsteps_total, int with_hb, int max_n, int n_bodies, int item_steps,
 		int* __restrict__ queue, int* __restrict__ done) {
 	extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -143,6 +143,7 @@ __global__ void __launch_bounds__(ET, 1) k_ensemble(const BodyDesc* __restrict__
 				if (lane == 0) sw = atomicAdd(&s_next, 1);
 				sw = __shfl_sync(0xffffffffu, sw, 0);
 				if (sw >= B.n_swarps) break;
+				sw = __ldg(sord + B.grp_off / GPW + sw);  // slices go out longest first: the tail the barrier waits for is the shortest ones
 				const int2 gi = __ldg(grp + B.grp_off + sw * GPW + lane / SPRING_LANES);  // (rank, degree); (-1, 0): padding group
 				const int off = __ldg(warp_off + B.swarp_off + sw);
 				const int P = (__ldg(warp_off + B.swarp_off + sw + 1) - off) >> 6;
@@ -272,6 +273,7 @@ struct ass_ensemble {
 	int* ord = nullptr;       // device index -> caller's node index inside its member
 	int2* grp = nullptr;      // lane groups of all members (common.cuh: ass_sim::grp), ranks local to the member
 	int* warp_off = nullptr;  // per member n_swarps + 1 offsets into heT
+	int* sord = nullptr;      // per member n_swarps slice numbers in hand-out order (by decreasing length)
 	HalfEdge* heT = nullptr;  // lane-transposed records of all members; nbr = rank inside the member
 	double2* palf = nullptr;  // distinct (-k, -max(gamma, 0)) pairs over all members
 	double* d_dense = nullptr;
@@ -286,7 +288,7 @@ struct ass_ensemble {
 static void ens_free(ass_ensemble* e) {
 	if (!e) return;
 	cudaFree(e->d_queue); cudaFree(e->d_desc); cudaFree(e->posm); cudaFree(e->vel); cudaFree(e->acc); cudaFree(e->perm); cudaFree(e->ord);
-	cudaFree(e->grp); cudaFree(e->warp_off); cudaFree(e->heT); cudaFree(e->palf); cudaFree(e->d_dense);
+	cudaFree(e->grp); cudaFree(e->sord); cudaFree(e->warp_off); cudaFree(e->heT); cudaFree(e->palf); cudaFree(e->d_dense);
 	if (e->e0) cudaEventDestroy(e->e0);
 	if (e->e1) cudaEventDestroy(e->e1);
 	if (e->stream) cudaStreamDestroy(e->stream);
@@ -323,6 +325,7 @@ extern "C" int ass_ensemble_create(ass_ensemble** out, int n_bodies, const int* 
 	std::vector<int> perm((size_t) std::max(total_nodes, 0)), ord((size_t) std::max(total_nodes, 0));
 	std::vector<int2> grp;
 	std::vector<int> warp_off;
+	std::vector<int> sord;
 	std::vector<HalfEdge> heT;
 	// palette of distinct (k, gamma) bit patterns over the whole ensemble (a sweep has a handful), stored as the force
 	// kernels want it (spring_math.cuh)
@@ -417,6 +420,13 @@ extern "C" int ass_ensemble_create(ass_ensemble** out, int n_bodies, const int* 
 				ord[(size_t) node_off[b] + lay.rank[(size_t) i]] = i;
 			}
 			grp.insert(grp.end(), lay.grp.begin(), lay.grp.end());
+			{
+				const int nsw = (int) lay.warp_off.size() - 1;
+				std::vector<int> o((size_t) nsw);
+				for (int w = 0; w < nsw; w++) o[(size_t) w] = w;
+				std::stable_sort(o.begin(), o.end(), [&](int a, int b) { return lay.warp_off[(size_t) a + 1] - lay.warp_off[a] > lay.warp_off[(size_t) b + 1] - lay.warp_off[b]; });
+				sord.insert(sord.end(), o.begin(), o.end());
+			}
 			for (int w : lay.warp_off) warp_off.push_back((int) (rec_base + w));
 			heT.insert(heT.end(), lay.heT.begin(), lay.heT.end());
 			e->total_he += 2LL * ns;
@@ -438,6 +448,7 @@ extern "C" int ass_ensemble_create(ass_ensemble** out, int n_bodies, const int* 
 	          cudaMalloc(&e->acc, sizeof(vec4d) * total_nodes) == cudaSuccess && cudaMalloc(&e->perm, sizeof(int) * total_nodes) == cudaSuccess &&
 	          cudaMalloc(&e->ord, sizeof(int) * total_nodes) == cudaSuccess && cudaMalloc(&e->grp, sizeof(int2) * std::max<size_t>(grp.size(), 1)) == cudaSuccess &&
 	          cudaMalloc(&e->warp_off, sizeof(int) * std::max<size_t>(warp_off.size(), 1)) == cudaSuccess &&
+	          cudaMalloc(&e->sord, sizeof(int) * std::max<size_t>(sord.size(), 1)) == cudaSuccess &&
 	          cudaMalloc(&e->heT, sizeof(HalfEdge) * std::max<size_t>(heT.size(), 1)) == cudaSuccess &&
 	          cudaMalloc(&e->palf, sizeof(double2) * std::max<size_t>(palf.size(), 1)) == cudaSuccess &&
 	          cudaMalloc(&e->d_dense, sizeof(double) * 10 * (size_t) total_nodes) == cudaSuccess && cudaMalloc(&d_rows, nb) == cudaSuccess;
@@ -452,6 +463,7 @@ extern "C" int ass_ensemble_create(ass_ensemble** out, int n_bodies, const int* 
 	cudaMemcpyAsync(e->ord, ord.data(), sizeof(int) * ord.size(), cudaMemcpyHostToDevice, e->stream);
 	if (!grp.empty()) cudaMemcpyAsync(e->grp, grp.data(), sizeof(int2) * grp.size(), cudaMemcpyHostToDevice, e->stream);
 	if (!warp_off.empty()) cudaMemcpyAsync(e->warp_off, warp_off.data(), sizeof(int) * warp_off.size(), cudaMemcpyHostToDevice, e->stream);
+	if (!sord.empty()) cudaMemcpyAsync(e->sord, sord.data(), sizeof(int) * sord.size(), cudaMemcpyHostToDevice, e->stream);
 	if (!heT.empty()) cudaMemcpyAsync(e->heT, heT.data(), sizeof(HalfEdge) * heT.size(), cudaMemcpyHostToDevice, e->stream);
 	if (!palf.empty()) cudaMemcpyAsync(e->palf, palf.data(), sizeof(double2) * palf.size(), cudaMemcpyHostToDevice, e->stream);
 	cudaMemcpyAsync(e->d_desc, e->desc.data(), sizeof(BodyDesc) * n_bodies, cudaMemcpyHostToDevice, e->stream);
@@ -502,7 +514,7 @@ extern "C" int ass_ensemble_step(ass_ensemble* e, int nsteps, int with_heartbeat
 	if (!e->d_queue) CU_TRY(cudaMalloc(&e->d_queue, sizeof(int) * ((size_t) e->n_bodies + 1)));
 	CU_TRY(cudaMemsetAsync(e->d_queue, 0, sizeof(int) * ((size_t) e->n_bodies + 1), e->stream));
 #define ASS_ENS(U, P1)                                                                                                                       \
-	k_ensemble<U, P1><<<grid, ET, e->smem, e->stream>>>(e->d_desc, e->posm, e->vel, e->acc, e->ord, e->grp, e->warp_off, e->heT, e->palf, nsteps, \
+	k_ensemble<U, P1><<<grid, ET, e->smem, e->stream>>>(e->d_desc, e->posm, e->vel, e->acc, e->ord, e->grp, e->sord, e->warp_off, e->heT, e->palf, nsteps, \
 			with_heartbeat, e->max_n, e->n_bodies, item_steps, e->d_queue, e->d_queue + 1)
 	if (e->uni_mass) { if (e->pal1) ASS_ENS(true, true); else ASS_ENS(true, false); }
 	else { if (e->pal1) ASS_ENS(false, true); else ASS_ENS(false, false); }

@@ -224,8 +224,8 @@ __device__ __forceinline__ void grid_wait(const unsigned* bar, unsigned target) 
 // One pass of a CTA over its tiles: the body of both kernels below.
 template <bool ZERO_FIRST, bool KICK, bool UNI, bool PAL1>
 __device__ __forceinline__ void tiles_pass(const CtaHead& H, unsigned char* tile_smem, int* s_next, const GlobalNodes mir, vec4d* __restrict__ acc,
-		const TileDesc* __restrict__ tiles, const int* __restrict__ tab, const int4* __restrict__ grpT, const int* __restrict__ warp_off,
-		const HalfEdge* __restrict__ heL, const double2* __restrict__ palf, const double2 nkg1, vec4d* __restrict__ posm_out,
+		const TileDesc* __restrict__ tiles, const int* __restrict__ tab, const int* __restrict__ sl_ord, const int4* __restrict__ grpT,
+		const int* __restrict__ warp_off, const HalfEdge* __restrict__ heL, const double2* __restrict__ palf, const double2 nkg1, vec4d* __restrict__ posm_out,
 		vec4d* __restrict__ vel_out, const SpringMirror out, double dt, int pre_drift_next, bool write_state, const unsigned* bar = nullptr,
 		unsigned bar_target = 0) {
 	// [record rings: TL_RING KB per warp][table: xy | zv | vxy | m, one entry per slot of THIS tile][headers: groups | record offsets]
@@ -241,6 +241,7 @@ __device__ __forceinline__ void tiles_pass(const CtaHead& H, unsigned char* tile
 		double* const s_m = (double*) (s_vxy + T.n_slots);
 		int4* const s_grp = (int4*) (s_m + T.n_slots);      // n_sl * GPW
 		int* const s_off = (int*) (s_grp + (size_t) n_sl * GPW);  // n_sl + 1
+		int* const s_ord = s_off + n_sl + 1;                      // n_sl: hand-out order of the slices (longest first)
 		const SharedNodes nodes{ s_xy, s_zv, s_vxy, s_m };
 		__syncthreads();  // everyone has left the previous tile (its table, headers and s_next)
 		// ---- before the table exists: this warp's first slice is slice `warp`; its header and first records are requested
@@ -265,6 +266,7 @@ __device__ __forceinline__ void tiles_pass(const CtaHead& H, unsigned char* tile
 		}
 		for (int i = tid; i < n_sl * GPW; i += TL_THREADS) cp_async_16(s_grp + i, grpT + (size_t) T.s0 * GPW + i);
 		for (int i = tid; i <= n_sl; i += TL_THREADS) cp_async_4(s_off + i, warp_off + T.s0 + i);
+		for (int i = tid; i < n_sl; i += TL_THREADS) cp_async_4(s_ord + i, sl_ord + T.s0 + i);
 		int P = (off1 - off) >> 6;  // first use of the headers: after every table request
 		rs.begin((const int4*) heL + off + lane, P);
 		rs.top_up();
@@ -286,7 +288,10 @@ __device__ __forceinline__ void tiles_pass(const CtaHead& H, unsigned char* tile
 			// the slice after this one: taken from the counter now, so its header and first records are on their way
 			// long before this slice's last pair
 			int nx = 0;
-			if (lane == 0) nx = atomicAdd(s_next, 1);
+			if (lane == 0) {
+				nx = atomicAdd(s_next, 1);
+				nx = nx < n_sl ? s_ord[nx] : n_sl;  // the counter hands out positions of the order, not slice numbers
+			}
 			nx = __shfl_sync(0xffffffffu, nx, 0);
 			const bool live = gi.x >= 0;
 			const int slot = live ? gi.x : 0;
@@ -317,14 +322,15 @@ __device__ __forceinline__ void tiles_pass(const CtaHead& H, unsigned char* tile
 
 template <bool ZERO_FIRST, bool KICK, bool UNI, bool PAL1>
 __global__ void __launch_bounds__(TL_THREADS, 1) k_spring_tiles(const __grid_constant__ TilesParams heads, const GlobalNodes mir, vec4d* __restrict__ acc,
-		const TileDesc* __restrict__ tiles, const int* __restrict__ tab, const int4* __restrict__ grpT, const int* __restrict__ warp_off,
-		const HalfEdge* __restrict__ heL, const double2* __restrict__ palf, vec4d* __restrict__ posm_out,
+		const TileDesc* __restrict__ tiles, const int* __restrict__ tab, const int* __restrict__ sl_ord, const int4* __restrict__ grpT,
+		const int* __restrict__ warp_off, const HalfEdge* __restrict__ heL, const double2* __restrict__ palf, vec4d* __restrict__ posm_out,
 		vec4d* __restrict__ vel_out, const SpringMirror out, double dt, int pre_drift_next) {
 	extern __shared__ __align__(128) unsigned char tile_smem[];
 	__shared__ int s_next;
 	double2 nkg1 = make_double2(0.0, 0.0);
 	if (PAL1) nkg1 = __ldg(palf);
-	tiles_pass<ZERO_FIRST, KICK, UNI, PAL1>(heads.h[blockIdx.x], tile_smem, &s_next, mir, acc, tiles, tab, grpT, warp_off, heL, palf, nkg1, posm_out, vel_out, out, dt, pre_drift_next, true);
+	tiles_pass<ZERO_FIRST, KICK, UNI, PAL1>(heads.h[blockIdx.x], tile_smem, &s_next, mir, acc, tiles, tab, sl_ord, grpT, warp_off, heL, palf, nkg1, posm_out, vel_out, out, dt,
+			pre_drift_next, true);
 }
 
 // The persistent multi-step form for bodies without a force term between the spring evaluations (REB_GRAVITY_NONE, or
@@ -336,8 +342,8 @@ __global__ void __launch_bounds__(TL_THREADS, 1) k_spring_tiles(const __grid_con
 // barrier spins).
 template <bool ZERO_FIRST, bool UNI, bool PAL1>
 __global__ void __launch_bounds__(TL_THREADS, 1) k_spring_steps(const __grid_constant__ TilesParams heads, const GlobalNodes mirA, const GlobalNodes mirB,
-		vec4d* __restrict__ acc, const TileDesc* __restrict__ tiles, const int* __restrict__ tab, const int4* __restrict__ grpT,
-		const int* __restrict__ warp_off, const HalfEdge* __restrict__ heL, const double2* __restrict__ palf,
+		vec4d* __restrict__ acc, const TileDesc* __restrict__ tiles, const int* __restrict__ tab, const int* __restrict__ sl_ord,
+		const int4* __restrict__ grpT, const int* __restrict__ warp_off, const HalfEdge* __restrict__ heL, const double2* __restrict__ palf,
 		vec4d* __restrict__ posm_out, vec4d* __restrict__ vel_out, double dt, int nsteps, unsigned* __restrict__ bar) {
 	extern __shared__ __align__(128) unsigned char tile_smem[];
 	__shared__ int s_next;
@@ -349,7 +355,7 @@ __global__ void __launch_bounds__(TL_THREADS, 1) k_spring_steps(const __grid_con
 		const bool even = (step & 1) == 0;
 		// (a CTA without tiles still keeps in step: its arrivals must not run ahead of the others')
 		if (heads.h[blockIdx.x].ntiles == 0 && step > 0) grid_wait(bar, (unsigned) step * gridDim.x);
-		tiles_pass<ZERO_FIRST, true, UNI, PAL1>(heads.h[blockIdx.x], tile_smem, &s_next, even ? mirA : mirB, acc, tiles, tab, grpT, warp_off, heL, palf, nkg1,
+		tiles_pass<ZERO_FIRST, true, UNI, PAL1>(heads.h[blockIdx.x], tile_smem, &s_next, even ? mirA : mirB, acc, tiles, tab, sl_ord, grpT, warp_off, heL, palf, nkg1,
 				posm_out, vel_out, even ? outB : outA, dt, last ? 0 : 1, last, step > 0 ? bar : nullptr, (unsigned) step * gridDim.x);
 		if (!last) grid_arrive(bar);
 	}
@@ -407,10 +413,10 @@ static void launch_csr(ass_sim* s, bool zero_first, bool uni, int lo, int hi, do
 
 // shared memory per table slot of the tiled kernel: three 16-byte pairs and the mass
 constexpr size_t TILE_SLOT_BYTES = 3 * sizeof(double2) + sizeof(double);
-// and in bytes, slice headers included (16 GPW + 4 bytes per slice): what is left of the SM's 227 KB next to the record rings
+// and in bytes, slice headers included (16 GPW + 8 bytes per slice: groups, record offset, hand-out order): what is left of the SM's 227 KB next to the record rings
 constexpr size_t TILE_SMEM_MAX = 227 * 1024 - 1024;  // dynamic shared memory the kernels opt in to
 constexpr size_t TILE_BYTES_LIMIT = TILE_SMEM_MAX - TL_RING_BYTES;
-static size_t tile_bytes(int slots, int slices) { return TILE_SLOT_BYTES * (size_t) slots + (size_t) slices * (GPW * sizeof(int4) + sizeof(int)) + 2 * sizeof(int); }
+static size_t tile_bytes(int slots, int slices) { return TILE_SLOT_BYTES * (size_t) slots + (size_t) slices * (GPW * sizeof(int4) + 2 * sizeof(int)) + 2 * sizeof(int); }
 static_assert(TILE_BYTES_LIMIT >= 64 * 1024, "no room for a table next to the record rings");
 
 template <class T>
@@ -434,6 +440,7 @@ struct TilesHost {
 	size_t bytes_max = 0;  // table + headers of the largest tile
 	std::vector<TileDesc> tiles;
 	std::vector<int> cta_tile, tab;
+	std::vector<int> sl_ord;  // per tile, at [s0, s1): local slice indices in hand-out order
 	std::vector<HalfEdge> heL;
 	std::vector<int4> grpT;
 };
@@ -468,6 +475,7 @@ static int build_tiles_host(const SpringLayout& lay, int grid, int slots_limit, 
 	std::vector<HalfEdge>& heL = out.heL;
 	std::vector<int4>& grpT = out.grpT;
 	tiles.clear(); tab.clear();
+	out.sl_ord.assign((size_t) ns, 0);
 	cta_tile.assign((size_t) grid + 1, 0);
 	heL = lay.heT;
 	grpT.assign(lay.grp.size(), make_int4(-1, -1, 0, 0));
@@ -524,6 +532,18 @@ static int build_tiles_host(const SpringLayout& lay, int grid, int slots_limit, 
 					heL[(size_t) at].nbr = live ? slot_of[(size_t) lay.heT[(size_t) at].nbr] : 0;
 				}
 			}
+			// hand-out order: warp w starts with slice w (its header is requested before the table exists); the others go out
+			// longest first, so that the last ones pulled -- the tail every warp waits for at the end of the tile -- are the
+			// shortest (boundary nodes).  The order of the slices does not touch any sum.
+			{
+				std::vector<int> rest;
+				for (int w = s0; w < sl; w++) {
+					if (w - s0 < TL_WARPS) out.sl_ord[(size_t) w] = w - s0;
+					else rest.push_back(w - s0);
+				}
+				std::stable_sort(rest.begin(), rest.end(), [&](int a, int b) { return pairs(s0 + a) > pairs(s0 + b); });
+				for (size_t i = 0; i < rest.size(); i++) out.sl_ord[(size_t) s0 + TL_WARPS + i] = rest[i];
+			}
 			out.slots_max = std::max(out.slots_max, n_slots);
 			out.slices_max = std::max(out.slices_max, sl - s0);
 			out.bytes_max = std::max(out.bytes_max, tile_bytes(n_slots, sl - s0));
@@ -551,6 +571,8 @@ int ass_build_spring_tiles(ass_sim* s, const SpringLayout& lay) {
 	if ((rc = tiles_reserve(s->grpT, s->grpT_cap, th.grpT.size(), "tile lane groups"))) return rc;
 	if ((rc = tiles_reserve(s->tile_tab, s->tile_tab_cap, th.tab.size(), "tile table entries"))) return rc;
 	if ((rc = tiles_reserve(s->tile_desc, s->tile_desc_cap, th.tiles.size(), "tile descriptors"))) return rc;
+	if ((rc = tiles_reserve(s->tile_sl_ord, s->tile_sl_ord_cap, th.sl_ord.size(), "slice hand-out order"))) return rc;
+	CU_TRY(cudaMemcpyAsync(s->tile_sl_ord, th.sl_ord.data(), sizeof(int) * th.sl_ord.size(), cudaMemcpyHostToDevice, s->stream));
 	CU_TRY(cudaMemcpyAsync(s->heL, th.heL.data(), sizeof(HalfEdge) * th.heL.size(), cudaMemcpyHostToDevice, s->stream));
 	CU_TRY(cudaMemcpyAsync(s->grpT, th.grpT.data(), sizeof(int4) * th.grpT.size(), cudaMemcpyHostToDevice, s->stream));
 	CU_TRY(cudaMemcpyAsync(s->tile_tab, th.tab.data(), sizeof(int) * th.tab.size(), cudaMemcpyHostToDevice, s->stream));
@@ -660,6 +682,14 @@ extern "C" int ass_selfcheck_spring_layout(const double* pos_xyzm, int n, const 
 			const TileDesc& T = th.tiles[t];
 			if (T.s0 != expect || T.s1 <= T.s0 || (T.n_slots & 7) || T.n_slots > th.slots_max || T.s1 - T.s0 > th.slices_max) viol++;
 			if (T.n_slots > slots_limit && T.s1 - T.s0 > 1) viol++;
+			{
+				std::vector<char> seen_sl((size_t) (T.s1 - T.s0), 0);
+				for (int w = T.s0; w < T.s1; w++) {
+					const int l = th.sl_ord[(size_t) w];
+					if (l < 0 || l >= T.s1 - T.s0 || seen_sl[(size_t) l]++) { viol++; break; }
+					if (w - T.s0 < TL_WARPS && l != w - T.s0) viol++;
+				}
+			}
 			if (tile_bytes(T.n_slots, T.s1 - T.s0) > TILE_BYTES_LIMIT || tile_bytes(T.n_slots, T.s1 - T.s0) > th.bytes_max) viol++;  // fits next to the record rings
 			expect = T.s1;
 			for (int i = 0; i < T.n_slots; i++) {
@@ -705,7 +735,7 @@ static int launch_tiles_t(ass_sim* s, double dt, int pre) {
 	}
 	TilesParams P;
 	memcpy(&P, s->tile_heads.data(), std::min(sizeof(P), s->tile_heads.size() * sizeof(int)));
-	kern<<<s->tiles_grid, TL_THREADS, smem, s->stream>>>(P, mirror_nodes(s), s->acc, (const TileDesc*) s->tile_desc, s->tile_tab, s->grpT, s->warp_off, s->heL,
+	kern<<<s->tiles_grid, TL_THREADS, smem, s->stream>>>(P, mirror_nodes(s), s->acc, (const TileDesc*) s->tile_desc, s->tile_tab, s->tile_sl_ord, s->grpT, s->warp_off, s->heL,
 			s->palf, KICK ? s->posm_alt : nullptr, KICK ? s->vel_alt : nullptr, s->mir_alt, dt, pre);
 	return ASS_OK;
 }
@@ -740,13 +770,14 @@ static int launch_steps_t(ass_sim* s, double dt, int nsteps) {
 	vec4d* acc = s->acc;
 	const TileDesc* tiles = (const TileDesc*) s->tile_desc;
 	const int* tab = s->tile_tab;
+	const int* sl_ord = s->tile_sl_ord;
 	const int4* grpT = s->grpT;
 	const int* warp_off = s->warp_off;
 	const HalfEdge* heL = s->heL;
 	const double2* palf = s->palf;
 	vec4d *posm_out = s->posm_alt, *vel_out = s->vel_alt;
 	unsigned* bar = s->d_step_bar;
-	void* args[] = { &P, &mirA, &mirB, &acc, &tiles, &tab, &grpT, &warp_off, &heL, &palf, &posm_out, &vel_out, &dt, &nsteps, &bar };
+	void* args[] = { &P, &mirA, &mirB, &acc, &tiles, &tab, &sl_ord, &grpT, &warp_off, &heL, &palf, &posm_out, &vel_out, &dt, &nsteps, &bar };
 	// A device that cannot hold the whole grid at once right now (another context's kernels, MPS limits) refuses the launch
 	// instead of dead-locking at the barrier: the caller then steps with one launch per step (return value 1).
 	const cudaError_t e = cudaLaunchCooperativeKernel((const void*) kern, dim3((unsigned) s->tiles_grid), dim3(TL_THREADS), args, smem, s->stream);

@@ -387,7 +387,7 @@ extern "C" int ass_destroy(ass_sim* s) {
 	ass_shard_release(s);  // a sharded simulation's posm / vel alias its exported window
 	ass_sym_plans_free(s);
 	cudaFree(s->slotT); cudaFree(s->warp_off);
-	cudaFree(s->heL); cudaFree(s->grpT); cudaFree(s->tile_tab); cudaFree(s->tile_desc);
+	cudaFree(s->heL); cudaFree(s->grpT); cudaFree(s->tile_tab); cudaFree(s->tile_desc); cudaFree(s->tile_sl_ord);
 	cudaFree(s->order); cudaFree(s->rank); cudaFree(s->mir_block); cudaFree(s->mir_m);
 	cudaFree(s->posm); cudaFree(s->vel); cudaFree(s->acc); cudaFree(s->posm_alt); cudaFree(s->vel_alt);
 	cudaFree(s->he); cudaFree(s->row_ptr); cudaFree(s->slot); cudaFree(s->pal);
