@@ -131,6 +131,14 @@ def selfcheck_sqrt(samples=1 << 28, exp_lo=-200, exp_hi=200):
     return bad.value, first.value
 
 
+def selfcheck_gravity_plan(n_res, n_str=0, rect=False, sm_count=148):
+    """Host-only check of the pair-once gravity plan (block cut, CTA list); needs no GPU.  'violations' must be 0."""
+    stats = (C.c_longlong * 8)()
+    _chk(lib().ass_selfcheck_gravity_plan(C.c_int(n_res), C.c_int(n_str), C.c_int(int(rect)), C.c_int(sm_count), stats))
+    keys = ("ctas", "residents", "cut", "tiles_per_cta", "resident_blocks", "streamed_blocks", "violations", "skipped")
+    return dict(zip(keys, [int(v) for v in stats]))
+
+
 def spring_lanes():
     """Lanes sharing one node's row in the spring kernels; a slice of the lane-transposed list holds 32 // lanes nodes."""
     return int(lib().ass_spring_lanes())

@@ -342,35 +342,35 @@ static int check_masses(ass_sim* s, SymPlan* plan) {
 	return ASS_OK;
 }
 
-static int get_plan(ass_sim* s, int rlo, int rhi, int slo, int shi, SymPlan** out) {
-	for (SymPlan* q : s->sym_plans)
-		if (q->rlo == rlo && q->rhi == rhi && q->slo == slo && q->shi == shi) {
-			*out = q;
-			return (q->mass_epoch != s->mass_epoch) ? check_masses(s, q) : ASS_OK;
-		}
-	SymPlan* plan = new SymPlan();
-	plan->rlo = rlo; plan->rhi = rhi; plan->slo = slo; plan->shi = shi;
-	plan->rect = !(rlo == slo && rhi == shi);
+// The host half of a plan: which kernel variant, how the two ranges are cut into blocks, and the list of CTAs.  Pure host
+// work (no device is touched: ass_selfcheck_gravity_plan drives it from the CPU test suite).
+struct SymCut {
+	int R = 4, P = 1024, nrb = 0, nsb = 0, rpad = 0, spad = 0, U = 1, cut = 1;
+	std::vector<SymCta> ctas;
+	std::vector<int> be;  // be[2b], be[2b+1]: the CTAs whose resident block is b
+};
+
+static void build_sym_cut(int n_res, int n_str, bool rect, int sm_count, SymCut& c) {
 	// which kernel variant: three residents per thread (blocks of 768, three CTAs per SM) for large problems, four otherwise
 	{
-		const long long b4r = (rhi - rlo + 1023) / 1024, b4s = (shi - slo + 1023) / 1024;
-		const long long tiles4 = plan->rect ? b4r * b4s : b4r * (b4r + 1) / 2;
-		plan->R = tiles4 >= 2000 ? 3 : 4;
-		if (const char* e = getenv("ASS_SYM_R")) { const int r = atoi(e); if (r == 3 || r == 4) plan->R = r; }
-		plan->P = SG_T * plan->R;
+		const long long b4r = (n_res + 1023) / 1024, b4s = (n_str + 1023) / 1024;
+		const long long tiles4 = rect ? b4r * b4s : b4r * (b4r + 1) / 2;
+		c.R = tiles4 >= 2000 ? 3 : 4;
+		if (const char* e = getenv("ASS_SYM_R")) { const int r = atoi(e); if (r == 3 || r == 4) c.R = r; }
+		c.P = SG_T * c.R;
 	}
-	const int SG_P = plan->P;
-	const int nrb = (rhi - rlo + SG_P - 1) / SG_P, nsb = (shi - slo + SG_P - 1) / SG_P;
-	plan->nrb = nrb; plan->nsb = nsb;
+	const int SG_P = c.P;
+	const int nrb = (n_res + SG_P - 1) / SG_P, nsb = (n_str + SG_P - 1) / SG_P;
+	c.nrb = nrb; c.nsb = nsb;
 	// The range's partial block is block 0, its padding in FRONT: block 0 is the streamed side of all its off-diagonal tiles
 	// (triangle: streamed block <= resident block), where tiles of pure padding are skipped 128 particles at a time, and
 	// the resident side of only one.  With the partial block last (round 1) it was resident in nb tiles, all its padding
 	// computed: a body of 9 327 particles (9.1 blocks) spent 10 of its 55 tiles on a block that is 11 % full.
-	plan->rpad = nrb * SG_P - (rhi - rlo);
-	plan->spad = nsb * SG_P - (shi - slo);
-	const long long tiles = plan->rect ? (long long) nrb * nsb : (long long) nrb * (nrb + 1) / 2;
+	c.rpad = nrb * SG_P - n_res;
+	c.spad = nsb * SG_P - n_str;
+	const long long tiles = rect ? (long long) nrb * nsb : (long long) nrb * (nrb + 1) / 2;
 	// tiles per CTA: enough CTAs (>= ~16 per resident slot) for the block scheduler to balance, few enough rows
-	const long long slots = (long long) sg_occ(plan->R) * ass_sm_count();
+	const long long slots = (long long) sg_occ(c.R) * sm_count;
 	int U = (int) std::max(1LL, tiles / (slots * 16));
 	// few tiles (N ~ 1e4): cut every tile's streamed side into `cut` pieces so that ~2 CTAs per slot exist
 	// (measured and dropped: the coarsest cut with the shortest makespan in whole rounds of CTAs -- an SM with one
@@ -383,28 +383,94 @@ static int get_plan(ass_sim* s, int rlo, int rhi, int slo, int shi, SymPlan** ou
 	// 97 -> 108 us, the per-CTA fixed cost -- resident block, scratch rows -- weighing more at full clocks; a 12 288-particle
 	// slab loses either way.  The kernel accepts pieces that end inside a tile; ASS_SYM_CUT forces a cut for measurements.)
 	if (const char* e = getenv("ASS_SYM_CUT")) {
-		const int c = atoi(e);
-		if (U == 1 && c >= 1 && c <= SG_P / 32 && (c & (c - 1)) == 0) cut = c;
+		const int f = atoi(e);
+		if (U == 1 && f >= 1 && f <= SG_P / 32 && (f & (f - 1)) == 0 && SG_P % f == 0 && (SG_P / f) % 32 == 0) cut = f;
 	}
+	c.U = U; c.cut = cut;
 	const int piece = SG_P / cut;
 	std::vector<std::vector<SymCta>> per_block(nrb);
 	for (int rb = 0; rb < nrb; rb++) {
-		const int s_end = plan->rect ? nsb : rb + 1;  // rectangle: every streamed block; triangle: up to the diagonal
+		const int s_end = rect ? nsb : rb + 1;  // rectangle: every streamed block; triangle: up to the diagonal
 		for (int s0 = 0; s0 < s_end; s0 += U)
-			for (int c = 0; c < cut; c++) {
+			for (int q = 0; q < cut; q++) {
 				// a piece of streamed block 0 that lies in its leading padding has nothing to do
-				if (U == 1 && s0 == 0 && (c + 1) * piece <= plan->spad) continue;
-				per_block[rb].push_back({ rb, s0, std::min(s0 + U, s_end), c * piece, (c + 1) * piece });
+				if (U == 1 && s0 == 0 && (q + 1) * piece <= c.spad) continue;
+				per_block[rb].push_back({ rb, s0, std::min(s0 + U, s_end), q * piece, (q + 1) * piece });
 			}
 	}
 	// CTAs of one resident block stay contiguous (the reduction walks be[2b] .. be[2b+1]); big blocks first
-	std::vector<SymCta> ctas;
-	std::vector<int> be((size_t) 2 * nrb);
+	c.ctas.clear();
+	c.be.assign((size_t) 2 * nrb, 0);
 	for (int b = nrb - 1; b >= 0; b--) {
-		be[2 * b] = (int) ctas.size();
-		ctas.insert(ctas.end(), per_block[b].begin(), per_block[b].end());
-		be[2 * b + 1] = (int) ctas.size();
+		c.be[2 * b] = (int) c.ctas.size();
+		c.ctas.insert(c.ctas.end(), per_block[b].begin(), per_block[b].end());
+		c.be[2 * b + 1] = (int) c.ctas.size();
 	}
+}
+
+// Host-only self-check of the plan for n_res resident and n_str streamed particles (rect == 0: one range against itself, n_str
+// ignored): every pair of a resident block and a REAL streamed particle must be covered by exactly one CTA (triangle: streamed
+// block <= resident block), CTAs of a resident block contiguous in the list, pieces multiples of 32 inside their block.
+// stats: [0] CTAs, [1] residents per thread, [2] cut, [3] tiles per CTA, [4] resident blocks, [5] streamed blocks,
+// [6] violations (must be 0), [7] pieces skipped because they lie in the leading padding.
+extern "C" int ass_selfcheck_gravity_plan(int n_res, int n_str, int rect, int sm_count, long long* stats) {
+	REQUIRE(stats && n_res > 0 && (!rect || n_str > 0) && sm_count > 0, ASS_EINVAL, "bad argument");
+	if (!rect) n_str = n_res;
+	SymCut c;
+	build_sym_cut(n_res, n_str, rect != 0, sm_count, c);
+	long long viol = 0;
+	const int P = c.P;
+	// coverage counts per (resident block, streamed block, chunk of 32)
+	std::vector<unsigned char> cover((size_t) c.nrb * c.nsb * (P / 32), 0);
+	for (size_t i = 0; i < c.ctas.size(); i++) {
+		const SymCta& q = c.ctas[i];
+		if (q.rb < 0 || q.rb >= c.nrb || q.s0 < 0 || q.s1 <= q.s0 || q.s1 > c.nsb || q.t_lo < 0 || q.t_hi > P || q.t_lo >= q.t_hi || (q.t_lo & 31) || (q.t_hi & 31)) { viol++; continue; }
+		if (!rect && q.s1 > q.rb + 1) viol++;
+		if ((int) i < c.be[2 * q.rb] || (int) i >= c.be[2 * q.rb + 1]) viol++;
+		for (int sb = q.s0; sb < q.s1; sb++)
+			for (int t = q.t_lo; t < q.t_hi; t += 32) cover[((size_t) q.rb * c.nsb + sb) * (P / 32) + t / 32]++;
+	}
+	long long expected_ctas = 0, skipped = 0;
+	for (int rb = 0; rb < c.nrb; rb++)
+		for (int sb = 0; sb < c.nsb; sb++) {
+			const bool in_domain = rect || sb <= rb;
+			for (int t = 0; t < P; t += 32) {
+				const int cnt = cover[((size_t) rb * c.nsb + sb) * (P / 32) + t / 32];
+				const bool real = (long long) sb * P + t + 32 > c.spad;  // the chunk holds at least one real streamed particle
+				if (!in_domain) { if (cnt) viol++; continue; }
+				if (real ? cnt != 1 : cnt > 1) viol++;
+			}
+		}
+	for (int b = 0; b < c.nrb; b++) {
+		if (c.be[2 * b] > c.be[2 * b + 1]) viol++;
+		expected_ctas += c.be[2 * b + 1] - c.be[2 * b];
+	}
+	if (expected_ctas != (long long) c.ctas.size()) viol++;
+	if (c.rpad < 0 || c.rpad >= P || c.spad < 0 || c.spad >= P) viol++;
+	{
+		const long long full = (long long) (rect ? (long long) c.nrb * c.nsb : (long long) c.nrb * (c.nrb + 1) / 2);
+		skipped = c.U == 1 ? full * c.cut - (long long) c.ctas.size() : 0;
+	}
+	stats[0] = (long long) c.ctas.size(); stats[1] = c.R; stats[2] = c.cut; stats[3] = c.U; stats[4] = c.nrb; stats[5] = c.nsb; stats[6] = viol; stats[7] = skipped;
+	return ASS_OK;
+}
+
+static int get_plan(ass_sim* s, int rlo, int rhi, int slo, int shi, SymPlan** out) {
+	for (SymPlan* q : s->sym_plans)
+		if (q->rlo == rlo && q->rhi == rhi && q->slo == slo && q->shi == shi) {
+			*out = q;
+			return (q->mass_epoch != s->mass_epoch) ? check_masses(s, q) : ASS_OK;
+		}
+	SymPlan* plan = new SymPlan();
+	plan->rlo = rlo; plan->rhi = rhi; plan->slo = slo; plan->shi = shi;
+	plan->rect = !(rlo == slo && rhi == shi);
+	SymCut cutp;
+	build_sym_cut(rhi - rlo, shi - slo, plan->rect, ass_sm_count(), cutp);
+	plan->R = cutp.R; plan->P = cutp.P; plan->nrb = cutp.nrb; plan->nsb = cutp.nsb; plan->rpad = cutp.rpad; plan->spad = cutp.spad;
+	const int SG_P = plan->P;
+	const int nrb = plan->nrb, nsb = plan->nsb;
+	const std::vector<SymCta>& ctas = cutp.ctas;
+	const std::vector<int>& be = cutp.be;
 	plan->n_cta = (int) ctas.size();
 	const size_t n_str_tiles = plan->rect ? (size_t) nrb * (size_t) nsb : (size_t) nrb * (size_t) (nrb - 1) / 2;
 	plan->res_plane = (size_t) plan->n_cta * SG_P;

@@ -308,6 +308,11 @@ int ass_selfcheck_sqrt(long long samples, int exp_lo, int exp_hi, long long* mis
  * [1] padding records, [2] tiles, [3] largest table, [4] gather passes per step summed over all quarter warps and
  * [5] their minimum (one each), [6] violated invariants (must be 0), [7] records in the lane-transposed copy. */
 int ass_selfcheck_spring_layout(const double* pos_xyzm, int n, const ass_spring* springs, int ns, int grid, int slots, long long* stats);
+/* Host-only self-check of the pair-once gravity plan for n_res resident and n_str streamed particles on a device with sm_count SMs
+ * (rect == 0: one range against itself): every (resident block, real streamed particle) pair covered by exactly one CTA.
+ * stats[0] CTAs, [1] residents per thread, [2] cut, [3] tiles per CTA, [4] / [5] resident / streamed blocks, [6] violations
+ * (must be 0), [7] pieces skipped because they lie in the leading padding. */
+int ass_selfcheck_gravity_plan(int n_res, int n_str, int rect, int sm_count, long long* stats);
 /* lanes that share one node's half-edge row in the spring kernels (a slice of the lane-transposed list = 32 / lanes nodes) */
 int ass_spring_lanes(void);
 /* total number of kernel launches issued by this library in this process */
