@@ -131,6 +131,15 @@ def selfcheck_sqrt(samples=1 << 28, exp_lo=-200, exp_hi=200):
     return bad.value, first.value
 
 
+def selfcheck_shard_division(bounds, n_body):
+    """Host-only check of the division of a sharded body's gravity by pairs of slabs; needs no GPU.  'violations' must be 0."""
+    b = (C.c_int * len(bounds))(*[int(x) for x in bounds])
+    stats = (C.c_longlong * 8)()
+    _chk(lib().ass_selfcheck_shard_division(C.c_int(len(bounds) - 1), b, C.c_int(n_body), stats))
+    keys = ("pieces", "segments", "violations", "most_pairs", "fewest_pairs")
+    return dict(zip(keys, [int(v) for v in stats]))
+
+
 def selfcheck_gravity_plan(n_res, n_str=0, rect=False, sm_count=148):
     """Host-only check of the pair-once gravity plan (block cut, CTA list); needs no GPU.  'violations' must be 0."""
     stats = (C.c_longlong * 8)()

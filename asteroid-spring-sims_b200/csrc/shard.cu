@@ -169,13 +169,16 @@ int n_sources(const ass_sim* s) { return (s->prm.n_active == -1) ? s->n : std::m
 bool gravity_on(const ass_sim* s) { return s->prm.gravity == 1 && s->prm.additional_forces != 2; }
 bool pairwise(const ass_sim* s) { return gravity_on(s) && n_sources(s) == s->n; }
 // body part of rank r's slab: trailing point masses [N - n_perts, N) are kept out of the pair-once kernels
-void body_slab(const ass_sim* s, int r, int* lo, int* hi) {
-	const int nb = s->n - std::max(0, std::min(s->prm.n_perts, s->n));
-	*lo = std::min(s->shard.bounds[r], nb);
-	*hi = std::min(s->shard.bounds[r + 1], nb);
-}
 // where an antipodal pair cuts the lower rank's slab
 int half_point(int lo, int hi) { return lo + (hi - lo) / 2; }
+// slab r of a body of nb particles cut at `bounds` (trailing point masses are not part of the body)
+void slab_of(const int* bounds, int nb, int r, int* lo, int* hi) {
+	*lo = std::min(bounds[r], nb);
+	*hi = std::min(bounds[r + 1], nb);
+}
+void body_slab(const ass_sim* s, int r, int* lo, int* hi) {
+	slab_of(s->shard.bounds.data(), s->n - std::max(0, std::min(s->prm.n_perts, s->n)), r, lo, hi);
+}
 
 // layout of the window, in vec4d units
 size_t win_posm(const ass_sim* s, int b) { return (size_t) b * 2 * (size_t) s->n; }
@@ -190,34 +193,58 @@ int* err_of(const ass_sim* s, vec4d* window) { return (int*) (flags_of(s, window
 // sequence wraps past the last slab.  One launch per run instead of one per slab: 3 x fewer launches and reductions at
 // P = 8, and a run of 3 slabs has enough tiles to fill the machine with tiles cut in 2 instead of 8 (a CTA that meets
 // only 128 streamed particles spends a tenth of its time loading and storing its 1024 residents).
-int rect_runs(const ass_sim* s, int (&run_lo)[2], int (&run_hi)[2]) {
-	const ShardInfo& sh = s->shard;
-	const int P = sh.nranks, g = sh.rank, D = (P - 1) / 2;
+int rect_runs_of(int P, int g, const int* bounds, int nb, int (&run_lo)[2], int (&run_hi)[2]) {
+	const int D = (P - 1) / 2;
 	if (D <= 0) return 0;
 	int lo, hi, n = 0;
 	const int first = g + 1, last = g + D;  // slab numbers before the wrap
 	if (last < P) {
-		body_slab(s, first, &run_lo[0], &hi); body_slab(s, last, &lo, &run_hi[0]);
+		slab_of(bounds, nb, first, &run_lo[0], &hi); slab_of(bounds, nb, last, &lo, &run_hi[0]);
 		n = 1;
 	} else {
-		if (first < P) { body_slab(s, first, &run_lo[n], &hi); body_slab(s, P - 1, &lo, &run_hi[n]); n++; }
-		body_slab(s, first < P ? 0 : first - P, &run_lo[n], &hi); body_slab(s, last - P, &lo, &run_hi[n]); n++;
+		if (first < P) { slab_of(bounds, nb, first, &run_lo[n], &hi); slab_of(bounds, nb, P - 1, &lo, &run_hi[n]); n++; }
+		slab_of(bounds, nb, first < P ? 0 : first - P, &run_lo[n], &hi); slab_of(bounds, nb, last - P, &lo, &run_hi[n]); n++;
 	}
 	return n;
 }
+int rect_runs(const ass_sim* s, int (&run_lo)[2], int (&run_hi)[2]) {
+	return rect_runs_of(s->shard.nranks, s->shard.rank, s->shard.bounds.data(), s->n - std::max(0, std::min(s->prm.n_perts, s->n)), run_lo, run_hi);
+}
+
+// Rank g's pair-once pieces {resident lo, hi, streamed lo, hi}: [0] the triangle of its own slab, then the rectangles against
+// the runs of the next D slabs, then (even P) its half of the antipodal rectangle.  Empty pieces are kept (callers skip them).
+int shard_pieces_of(int P, int g, const int* bounds, int nb, int (&pc)[4][4]) {
+	int lo, hi, npc = 0;
+	slab_of(bounds, nb, g, &lo, &hi);
+	pc[npc][0] = lo; pc[npc][1] = hi; pc[npc][2] = lo; pc[npc][3] = hi; npc++;
+	int run_lo[2], run_hi[2];
+	const int runs = rect_runs_of(P, g, bounds, nb, run_lo, run_hi);
+	for (int q = 0; q < runs; q++) { pc[npc][0] = lo; pc[npc][1] = hi; pc[npc][2] = run_lo[q]; pc[npc][3] = run_hi[q]; npc++; }
+	if (P % 2 == 0 && P > 1) {  // antipodal slab: the pair's rectangle is split between its two ranks
+		const int h = (g + P / 2) % P;
+		int plo, phi;
+		slab_of(bounds, nb, h, &plo, &phi);
+		if (g < h) { pc[npc][0] = lo; pc[npc][1] = half_point(lo, hi); pc[npc][2] = plo; pc[npc][3] = phi; }
+		else { pc[npc][0] = lo; pc[npc][1] = hi; pc[npc][2] = half_point(plo, phi); pc[npc][3] = phi; }
+		npc++;
+	}
+	return npc;
+}
 
 // (rank, first particle) of every partial the peers compute for rank g's slab, in the order they are added
-void partial_sources(const ass_sim* s, std::vector<std::pair<int, int>>& from) {
-	const ShardInfo& sh = s->shard;
-	const int R = sh.nranks, g = sh.rank, D = (R - 1) / 2;
+void partial_sources_of(int R, int g, const int* bounds, int nb, std::vector<std::pair<int, int>>& from) {
+	const int D = (R - 1) / 2;
 	int lo, hi;
-	body_slab(s, g, &lo, &hi);
+	slab_of(bounds, nb, g, &lo, &hi);
 	from.clear();
 	for (int d = 1; d <= D; d++) from.push_back({ ((g - d) % R + R) % R, lo });
 	if (R % 2 == 0 && R > 1) {
 		const int h = (g + R / 2) % R;
 		from.push_back({ h, g < h ? half_point(lo, hi) : lo });  // the higher rank covered only my upper half
 	}
+}
+void partial_sources(const ass_sim* s, std::vector<std::pair<int, int>>& from) {
+	partial_sources_of(s->shard.nranks, s->shard.rank, s->shard.bounds.data(), s->n - std::max(0, std::min(s->prm.n_perts, s->n)), from);
 }
 
 // dst (mine) <- src (in peer r's window): cnt vec4d
@@ -264,22 +291,14 @@ int shard_prepare(ass_sim* s) {
 	const int n = s->n;
 	size_t scratch_rows_bytes = 0;
 	if (pairwise(s)) {
-		const int P = sh.nranks, g = sh.rank, D = (P - 1) / 2;
+		const int P = sh.nranks, g = sh.rank;
 		const int nb = n - std::max(0, std::min(s->prm.n_perts, n));
 		int lo, hi;
 		body_slab(s, g, &lo, &hi);
-		if (hi > lo && (rc = ass_gravity_sym_prepare(s, lo, hi, lo, hi))) return rc;
-		int run_lo[2], run_hi[2];
-		const int runs = rect_runs(s, run_lo, run_hi);
-		for (int q = 0; q < runs; q++)
-			if (hi > lo && run_hi[q] > run_lo[q] && (rc = ass_gravity_sym_prepare(s, lo, hi, run_lo[q], run_hi[q]))) return rc;
-		if (P % 2 == 0 && P > 1) {
-			const int h = (g + P / 2) % P;
-			int plo, phi;
-			body_slab(s, h, &plo, &phi);
-			if (g < h) { if (half_point(lo, hi) > lo && phi > plo && (rc = ass_gravity_sym_prepare(s, lo, half_point(lo, hi), plo, phi))) return rc; }
-			else if (hi > lo && phi > half_point(plo, phi) && (rc = ass_gravity_sym_prepare(s, lo, hi, half_point(plo, phi), phi))) return rc;
-		}
+		int pc[4][4];
+		const int npc = shard_pieces_of(P, g, sh.bounds.data(), nb, pc);
+		for (int q = 0; q < npc; q++)
+			if (pc[q][1] > pc[q][0] && pc[q][3] > pc[q][2] && (rc = ass_gravity_sym_prepare(s, pc[q][0], pc[q][1], pc[q][2], pc[q][3]))) return rc;
 		const int rows = std::max(ass_gravity_rows(hi - lo, n - nb), ass_gravity_rows(sh.hi - std::max(sh.lo, nb), n));
 		scratch_rows_bytes = sizeof(vec4d) * (size_t) std::max(rows, 1) * (size_t) n;
 	} else if (gravity_on(s)) {
@@ -323,6 +342,93 @@ int check_device_error(ass_sim* s) {
 }
 
 }  // namespace
+
+// Host-only self-check of how gravity is divided by pairs of slabs (no device is touched): over all ranks, every unordered
+// pair of body particles must be evaluated by exactly one piece, and the partials a rank adds must be exactly the ones its
+// peers compute for its slab.  Checked on segments (the slabs cut at the antipodal half points).  stats: [0] pieces with
+// work, [1] segments, [2] violations (must be 0), [3] largest / [4] smallest number of pairs a rank evaluates.
+extern "C" int ass_selfcheck_shard_division(int nranks, const int* bounds, int n_body, long long* stats) {
+	REQUIRE(stats && bounds && nranks >= 1 && nranks <= ASS_SHARD_MAX_RANKS && n_body >= 0, ASS_EINVAL, "bad argument");
+	for (int r = 0; r < nranks; r++) REQUIRE(bounds[r] <= bounds[r + 1], ASS_EINVAL, "slab bounds must not decrease");
+	REQUIRE(bounds[0] == 0 && bounds[nranks] >= n_body, ASS_EINVAL, "slabs must cover the body");
+	const int P = nranks, nb = n_body;
+	std::vector<int> cutp;
+	for (int r = 0; r <= P; r++) cutp.push_back(std::min(bounds[r], nb));
+	for (int r = 0; r < P; r++) {
+		int lo, hi;
+		slab_of(bounds, nb, r, &lo, &hi);
+		cutp.push_back(half_point(lo, hi));
+	}
+	std::sort(cutp.begin(), cutp.end());
+	cutp.erase(std::unique(cutp.begin(), cutp.end()), cutp.end());
+	const int nseg = (int) cutp.size() - 1;
+	auto seg_of = [&](int x) { return (int) (std::lower_bound(cutp.begin(), cutp.end(), x) - cutp.begin()); };
+	long long viol = 0, pieces = 0, most = 0, least = -1;
+	std::vector<int> cover((size_t) std::max(nseg, 0) * std::max(nseg, 0), 0);
+	for (int g = 0; g < P; g++) {
+		int pc[4][4];
+		const int npc = shard_pieces_of(P, g, bounds, nb, pc);
+		long long pairs = 0;
+		for (int q = 0; q < npc; q++) {
+			const int rlo = pc[q][0], rhi = pc[q][1], slo = pc[q][2], shi = pc[q][3];
+			if (rhi <= rlo || shi <= slo) continue;
+			pieces++;
+			const bool tri = rlo == slo && rhi == shi;
+			if (!tri && !(rhi <= slo || shi <= rlo)) viol++;  // a rectangle's ranges must be disjoint
+			if (cutp[(size_t) seg_of(rlo)] != rlo || cutp[(size_t) seg_of(rhi)] != rhi || cutp[(size_t) seg_of(slo)] != slo || cutp[(size_t) seg_of(shi)] != shi) { viol++; continue; }
+			pairs += tri ? (long long) (rhi - rlo) * (rhi - rlo - 1) / 2 : (long long) (rhi - rlo) * (shi - slo);
+			for (int a = seg_of(rlo); a < seg_of(rhi); a++)
+				for (int b = seg_of(slo); b < seg_of(shi); b++) {
+					if (tri && b < a) continue;
+					cover[(size_t) std::min(a, b) * nseg + std::max(a, b)]++;
+				}
+			// whoever owns a slab the streamed range reaches into must expect this rank's partial, from the right particle on
+			if (!tri)
+				for (int h = 0; h < P; h++) {
+					int hlo, hhi;
+					slab_of(bounds, nb, h, &hlo, &hhi);
+					const int first = std::max(hlo, slo), last = std::min(hhi, shi);
+					if (last <= first) continue;
+					std::vector<std::pair<int, int>> from;
+					partial_sources_of(P, h, bounds, nb, from);
+					int hits = 0;
+					for (auto& f : from)
+						if (f.first == g) { hits++; if (f.second != first || last != hhi) viol++; }
+					if (hits != 1) viol++;
+				}
+		}
+		most = std::max(most, pairs);
+		least = least < 0 ? pairs : std::min(least, pairs);
+		// and nobody is expected who computes nothing for this slab
+		std::vector<std::pair<int, int>> from;
+		partial_sources_of(P, g, bounds, nb, from);
+		int glo, ghi;
+		slab_of(bounds, nb, g, &glo, &ghi);
+		for (auto& f : from) {
+			if (ghi <= f.second) continue;  // (nothing of the slab left from there on: the step skips it too)
+			// the source's piece that reaches into this slab must start where this rank starts adding -- unless the source has
+			// nothing to compute there (an empty slab or half slab of its own): its partials are the zeros the window was
+			// created with, and adding them changes nothing
+			int pc2[4][4];
+			const int n2 = shard_pieces_of(P, f.first, bounds, nb, pc2);
+			int with_work = 0, matching = 0;
+			for (int q = 1; q < n2; q++) {
+				if (pc2[q][1] <= pc2[q][0] || std::min(pc2[q][3], ghi) <= std::max(pc2[q][2], glo)) continue;
+				with_work++;
+				if (std::max(pc2[q][2], glo) == f.second && std::min(pc2[q][3], ghi) == ghi) matching++;
+			}
+			if (with_work != matching || with_work > 1) viol++;
+		}
+	}
+	for (int a = 0; a < nseg; a++)
+		for (int b = a; b < nseg; b++) {
+			const bool real = cutp[(size_t) a + 1] > cutp[(size_t) a] && cutp[(size_t) b + 1] > cutp[(size_t) b] && !(a == b && cutp[(size_t) a + 1] - cutp[(size_t) a] < 2);
+			const int c = cover[(size_t) a * nseg + b];
+			if (real ? c != 1 : c > 1) viol++;
+		}
+	stats[0] = pieces; stats[1] = nseg; stats[2] = viol; stats[3] = most; stats[4] = std::max(least, 0LL);
+	return ASS_OK;
+}
 
 extern "C" int ass_shard_setup(ass_sim* s, int rank, int nranks, const int* bounds) {
 	REQUIRE(s && bounds, ASS_EINVAL, "null argument");
@@ -477,24 +583,17 @@ extern "C" int ass_shard_step(ass_sim* s, int nsteps, int pre_drift_last) {
 			vec4d* fpart = sh.window + win_part(s);
 			int lo, hi;
 			body_slab(s, g, &lo, &hi);
-			int run_lo[2], run_hi[2];
-			const int runs = rect_runs(s, run_lo, run_hi);
 			// rectangles (both sides of every pair) and, for an even rank count, this rank's half of the antipodal rectangle.
 			// Their pair kernels run on streams of their own, next to the triangle still running on the main stream: each of
 			// these launches ends in a partly filled round of CTAs (a 12 288-particle slab is 2.1 / 2.9 / 1.9 rounds), and the
 			// block scheduler tops a draining kernel up with the next one's CTAs (measured on one GPU, tools/
 			// prof_gravity_pairs.py: 889 -> 815 us per rank and step at C3 / 8).  The fixed-order reductions follow on the
 			// main stream.  ASS_SHARD_SERIAL_GRAVITY=1: one after the other on the main stream.
-			int pc[3][4], npc = 0;
-			for (int q = 0; q < runs; q++) { pc[npc][0] = lo; pc[npc][1] = hi; pc[npc][2] = run_lo[q]; pc[npc][3] = run_hi[q]; npc++; }
-			if (P % 2 == 0 && P > 1) {  // antipodal slab: the pair's rectangle is split between its two ranks
-				const int h = (g + P / 2) % P;
-				int plo, phi;
-				body_slab(s, h, &plo, &phi);
-				if (g < h) { pc[npc][0] = lo; pc[npc][1] = half_point(lo, hi); pc[npc][2] = plo; pc[npc][3] = phi; }
-				else { pc[npc][0] = lo; pc[npc][1] = hi; pc[npc][2] = half_point(plo, phi); pc[npc][3] = phi; }
-				npc++;
-			}
+			int all[4][4], pc[3][4];
+			const int nall = shard_pieces_of(P, g, sh.bounds.data(), nb, all);  // [0] is the triangle, queued above
+			const int npc = nall - 1;
+			for (int q = 0; q < npc; q++)
+				for (int k = 0; k < 4; k++) pc[q][k] = all[q + 1][k];
 			const char* serial = getenv("ASS_SHARD_SERIAL_GRAVITY");
 			if (serial && *serial && *serial != '0') {
 				for (int q = 0; q < npc; q++)

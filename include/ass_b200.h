@@ -308,6 +308,10 @@ int ass_selfcheck_sqrt(long long samples, int exp_lo, int exp_hi, long long* mis
  * [1] padding records, [2] tiles, [3] largest table, [4] gather passes per step summed over all quarter warps and
  * [5] their minimum (one each), [6] violated invariants (must be 0), [7] records in the lane-transposed copy. */
 int ass_selfcheck_spring_layout(const double* pos_xyzm, int n, const ass_spring* springs, int ns, int grid, int slots, long long* stats);
+/* Host-only self-check of how a sharded body's gravity is divided by pairs of slabs: over all ranks every unordered pair of body
+ * particles is evaluated by exactly one piece, and the partial accelerations a rank adds are exactly those its peers compute.
+ * stats[0] pieces with work, [1] segments, [2] violations (must be 0), [3] / [4] most / fewest pairs on a rank. */
+int ass_selfcheck_shard_division(int nranks, const int* bounds, int n_body, long long* stats);
 /* Host-only self-check of the pair-once gravity plan for n_res resident and n_str streamed particles on a device with sm_count SMs
  * (rect == 0: one range against itself): every (resident block, real streamed particle) pair covered by exactly one CTA.
  * stats[0] CTAs, [1] residents per thread, [2] cut, [3] tiles per CTA, [4] / [5] resident / streamed blocks, [6] violations

@@ -69,3 +69,36 @@ def test_random_sizes(A):
         assert A.selfcheck_gravity_plan(n_res, n_str, rect=rect, sm_count=sms)["violations"] == 0
 
     check()
+
+
+# ---------------------------------------------------------------------------------------------------
+# a sharded body: gravity divided by pairs of slabs (csrc/shard.cu: shard_pieces_of, partial_sources_of)
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("nranks", [1, 2, 3, 4, 5, 6, 7, 8])
+@pytest.mark.parametrize("n,n_perts", [(96536, 0), (945597, 1), (1066, 1), (300, 0), (7, 0), (1, 0)])
+def test_every_pair_of_a_sharded_body_is_evaluated_once(A, nranks, n, n_perts):
+    """Over all ranks: own triangles + rectangles against the next (P-1)/2 slabs + the halves of the antipodal rectangles cover
+    every unordered pair of body particles exactly once, and the partial accelerations a rank adds are the ones its peers
+    compute for its slab (a peer with an empty slab contributes the zeros its window was created with)."""
+    for align in (1024, 256, 1):
+        bounds = A.slab_bounds(n, nranks, align=align)
+        st = A.selfcheck_shard_division(bounds, n - n_perts)
+        assert st["violations"] == 0, (bounds, st)
+        nb = n - n_perts
+        assert st["most_pairs"] >= nb * (nb - 1) // 2 // nranks
+    if n >= 90000 and nranks > 1:
+        st = A.selfcheck_shard_division(A.slab_bounds(n, nranks), n - n_perts)
+        assert st["fewest_pairs"] > 0.8 * st["most_pairs"]          # the same work on every rank (block-aligned slabs: the last one is shorter)
+
+
+def test_shard_division_random_bounds(A):
+    hypothesis = pytest.importorskip("hypothesis")
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=80, deadline=None)
+    @given(cuts=st.lists(st.integers(0, 5000), min_size=0, max_size=7), n=st.integers(0, 5000), perts=st.integers(0, 3))
+    def check(cuts, n, perts):
+        bounds = [0] + sorted(min(c, n) for c in cuts) + [n]
+        assert A.selfcheck_shard_division(bounds, max(n - perts, 0))["violations"] == 0
+
+    check()
