@@ -6,6 +6,7 @@
 #include <math.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <unordered_map>
 
@@ -879,6 +880,16 @@ void refine_ranks_for_bank_groups(int n, const ass_spring* sp, int ns, std::vect
 // pidx[q] = palette index of spring q; *bad_spring = first spring with an endpoint outside [0, n) or i == j, else -1.
 int ass_build_spring_layout(const vec4d* pos, int n, const ass_spring* sp, int ns, const int* pidx, SpringLayout& out, int* bad_spring) {
 	*bad_spring = -1;
+	// ASS_LAYOUT_TIMING=1: the phases' host times on stderr (tuning)
+	const char* tim_env = getenv("ASS_LAYOUT_TIMING");
+	const bool timing = tim_env && *tim_env && *tim_env != '0';
+	auto t_last = std::chrono::steady_clock::now();
+	auto lap = [&](const char* what) {
+		if (!timing) return;
+		const auto now = std::chrono::steady_clock::now();
+		fprintf(stderr, "[layout] %-28s %8.1f ms\n", what, 1e3 * std::chrono::duration<double>(now - t_last).count());
+		t_last = now;
+	};
 	for (int q = 0; q < ns; q++) {
 		const int i = sp[q].particle_1, j = sp[q].particle_2;
 		if (i < 0 || j < 0 || i >= n || j >= n || i == j) {
@@ -892,7 +903,9 @@ int ass_build_spring_layout(const vec4d* pos, int n, const ass_spring* sp, int n
 	rank.assign((size_t) n, 0);
 	morton_order(pos, (size_t) n, order);
 	for (int k = 0; k < n; k++) rank[(size_t) order[k]] = k;
+	lap("morton ranking");
 	refine_ranks_for_bank_groups(n, sp, ns, order, rank);
+	lap("rank refinement");
 	// rows by rank
 	row.assign((size_t) n + 1, 0);
 	for (int q = 0; q < ns; q++) {
@@ -916,6 +929,7 @@ int ass_build_spring_layout(const vec4d* pos, int n, const ass_spring* sp, int n
 		}
 	}
 	for (int k = 0; k < n; k++) std::sort(ent.begin() + row[k], ent.begin() + row[(size_t) k + 1]);
+	lap("rows");
 	// ---- the lane-transposed copy (common.cuh: ass_sim::heT) ----
 	// nodes -> lane groups: inside every block of ASS_SORT_BLOCK ranks, by decreasing degree (ties: by rank)
 	constexpr int L = SPRING_LANES, GPW = 32 / SPRING_LANES;
@@ -1011,6 +1025,7 @@ int ass_build_spring_layout(const vec4d* pos, int n, const ass_spring* sp, int n
 			}
 		}
 	}
+	lap("groups + row arrangement");
 	out.he.resize(nhe);
 	out.slot.resize(nhe);
 	for (size_t at = 0; at < nhe; at++) {
@@ -1055,6 +1070,7 @@ int ass_build_spring_layout(const vec4d* pos, int n, const ass_spring* sp, int n
 				}
 		}
 	}
+	lap("CSR + transposed copies");
 	return ASS_OK;
 }
 
