@@ -141,6 +141,31 @@ extern "C" int ass_leapfrog_part2(ass_sim* s) {
 	return rc;
 }
 
+// [reb_integrator_leapfrog_part1] ; [zero_accel] ; spring_forces ; reb_integrator_leapfrog_part2 as the fused kernels of the step
+// loop run them: for a caller that sees the four calls one by one but may defer them until the last (the drop-in in
+// resident mode: host/dropin.cpp).  Same bits as the four calls.  Without springs it is [part1] ; [zero_accel] ; part2.
+extern "C" int ass_substep_fused(ass_sim* s, int do_part1, int zero_first) {
+	ENTER(s);
+	REQUIRE(!s->predrifted, ASS_ESTATE, "internal: positions are mid-step");
+	REQUIRE(!s->shard.active, ASS_ESTATE, "not for a sharded simulation");
+	const double dt = s->prm.dt;
+	const bool have_springs = s->ns > 0 && s->row_ptr != nullptr;
+	int rc = ASS_OK;
+	if (do_part1) {
+		if ((rc = have_springs ? ass_launch_part1_mirrored(s, dt) : ass_launch_part1(s, dt))) return rc;
+		s->prm.t += dt / 2.;
+	}
+	if (have_springs) {
+		if ((rc = ass_launch_spring_kick_drift(s, zero_first != 0, dt, false, do_part1 != 0))) return rc;
+	} else {
+		if (zero_first && (rc = ass_launch_zero_accel(s))) return rc;
+		if ((rc = ass_launch_part2(s, dt))) return rc;
+	}
+	s->prm.t += dt / 2.;
+	s->prm.dt_last_done = dt;
+	return ASS_OK;
+}
+
 // ---------------------------------------------------------------------------------------------------
 // reb_step x nsteps without leaving the device
 // ---------------------------------------------------------------------------------------------------

@@ -57,6 +57,8 @@ struct Dropin {
 	unsigned pending = 0;      // fields written on the device inside a deferred sequence, not yet downloaded
 	int defer = 0;             // >0: inside one of our own multi-kernel sequences
 	bool in_run = false;       // inside reb_integrate
+	// resident mode: calls of one reb_step deferred until reb_integrator_leapfrog_part2 can run them as fused kernels
+	bool lazy_part1 = false, lazy_zero = false, lazy_springs = false;
 	// spring cache validity
 	bool topo_stale = true, prop_stale = true;
 	size_t sp_size = 0;
@@ -140,7 +142,36 @@ void pin_particles(reb_simulation* r, Dropin& d) {
 	}
 }
 
-void ensure_dev(reb_simulation* r, Dropin& d) {
+void push_params(reb_simulation* r, Dropin& d);
+void ensure_springs(Dropin& d);
+
+// Resident mode defers part1 / zero_accel / spring_forces of a reb_step (they return at once) so that
+// reb_integrator_leapfrog_part2 can run the lot as the fused kernels of the step loop: two launches instead of five, no
+// re-gather of the rank-ordered mirror.  Anything else that looks at the device state first SETTLES what is pending, in the
+// order it was asked for, through the ordinary calls -- the result is the same bits either way.
+// ASS_DROPIN_NO_FUSE=1: every call runs when it is made.
+bool lazy_ok(const Dropin& d) {
+	static int no_fuse = -1;
+	if (no_fuse < 0) {
+		const char* e = getenv("ASS_DROPIN_NO_FUSE");
+		no_fuse = (e && *e && strcmp(e, "0") != 0) ? 1 : 0;
+	}
+	return resident() && d.in_run && !no_fuse;
+}
+void settle(reb_simulation* r, Dropin& d) {
+	if (!(d.lazy_part1 || d.lazy_zero || d.lazy_springs)) return;
+	const bool p1 = d.lazy_part1, z = d.lazy_zero, sp = d.lazy_springs;
+	d.lazy_part1 = d.lazy_zero = d.lazy_springs = false;
+	if (p1) {
+		push_params(r, d);
+		OK(ass_leapfrog_part1(d.sim));
+	}
+	if (z) OK(ass_zero_accel(d.sim));
+	if (sp) OK(ass_spring_forces(d.sim));
+}
+
+void ensure_dev(reb_simulation* r, Dropin& d, bool settle_pending = true) {
+	if (settle_pending) settle(r, d);
 	if (d.dev_fresh && ass_num_particles(d.sim) == r->N) return;
 	if (d.in_run) pin_particles(r, d);
 	OK(ass_upload_particles(d.sim, r->particles, sizeof(reb_particle), r->N, ASS_F_ALL));
@@ -151,6 +182,7 @@ void ensure_dev(reb_simulation* r, Dropin& d) {
 }
 
 void flush_host(reb_simulation* r, Dropin& d) {
+	settle(r, d);
 	if (d.in_run && d.pending && r->N > 0) pin_particles(r, d);
 	if (d.pending && r->N > 0) OK(ass_download_particles(d.sim, r->particles, sizeof(reb_particle), r->N, d.pending));
 	d.pending = 0;
@@ -273,8 +305,12 @@ extern "C" void reb_integrator_leapfrog_part1(struct reb_simulation* r) {
 	r->gravity_ignore_terms = 0;
 	Dropin& d = get(r);
 	ensure_dev(r, d);
-	push_params(r, d);
-	OK(ass_leapfrog_part1(d.sim));
+	if (lazy_ok(d)) {
+		d.lazy_part1 = true;  // runs with what follows (settle / reb_integrator_leapfrog_part2)
+	} else {
+		push_params(r, d);
+		OK(ass_leapfrog_part1(d.sim));
+	}
 	r->t += r->dt / 2.;
 	wrote(r, d, ASS_F_POS);
 }
@@ -282,6 +318,18 @@ extern "C" void reb_integrator_leapfrog_part1(struct reb_simulation* r) {
 // src/integrator_leapfrog.c:52-67
 extern "C" void reb_integrator_leapfrog_part2(struct reb_simulation* r) {
 	Dropin& d = get(r);
+	if (lazy_ok(d) && d.lazy_springs) {
+		// [part1] [zero_accel] spring_forces part2, deferred until here: the fused kernels
+		ensure_dev(r, d, false);
+		const int p1 = d.lazy_part1 ? 1 : 0, z = d.lazy_zero ? 1 : 0;
+		d.lazy_part1 = d.lazy_zero = d.lazy_springs = false;
+		push_params(r, d);
+		OK(ass_substep_fused(d.sim, p1, z));
+		r->t += r->dt / 2.;
+		r->dt_last_done = r->dt;
+		wrote(r, d, ASS_F_POS | ASS_F_VEL | ASS_F_ACC);
+		return;
+	}
 	ensure_dev(r, d);
 	push_params(r, d);
 	OK(ass_leapfrog_part2(d.sim));
@@ -373,6 +421,14 @@ extern "C" int reb_output_check(struct reb_simulation* r, double interval) {
 // src_spring/springs.cpp:288-346
 void spring_forces(reb_simulation* const r) {
 	Dropin& d = get(r);
+	if (lazy_ok(d)) {
+		ensure_dev(r, d, false);
+		if (d.lazy_springs) settle(r, d);  // a second evaluation in one step: the first one runs now
+		ensure_springs(d);                  // the module's list as it is NOW
+		d.lazy_springs = true;
+		wrote(r, d, ASS_F_ACC);
+		return;
+	}
 	ensure_dev(r, d);
 	ensure_springs(d);
 	OK(ass_spring_forces(d.sim));
@@ -382,6 +438,13 @@ void spring_forces(reb_simulation* const r) {
 // src_spring/physics.cpp:557-564
 void zero_accel(reb_simulation* const r) {
 	Dropin& d = get(r);
+	if (lazy_ok(d)) {
+		ensure_dev(r, d, false);
+		if (d.lazy_springs) settle(r, d);  // zeroing AFTER a deferred evaluation: keep the order
+		d.lazy_zero = true;
+		wrote(r, d, ASS_F_ACC);
+		return;
+	}
 	ensure_dev(r, d);
 	OK(ass_zero_accel(d.sim));
 	wrote(r, d, ASS_F_ACC);

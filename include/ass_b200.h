@@ -125,6 +125,9 @@ int ass_gravity_basic(ass_sim* sim);  /* reb_calculate_acceleration, REB_GRAVITY
 int ass_set_gravity_kernel(ass_sim* sim, int which);
 int ass_leapfrog_part1(ass_sim* sim); /* reb_integrator_leapfrog_part1, src/integrator_leapfrog.c:39-51 */
 int ass_leapfrog_part2(ass_sim* sim); /* reb_integrator_leapfrog_part2, src/integrator_leapfrog.c:52-67 */
+/* [part1 ;] [zero_accel ;] spring_forces ; part2 of ONE step as the fused kernels run them (same bits as the separate calls):
+ * for a caller that is handed the calls one by one and may defer them until part2 (the drop-in in resident mode). */
+int ass_substep_fused(ass_sim* sim, int do_part1, int zero_first);
 /* reb_step (src/rebound.c:69-144) x nsteps with the built-in additional_forces of params.additional_forces, fused
  * (gravity -> springs+kick+drift) and without returning to the host between steps.  with_heartbeat != 0 runs the
  * built-in heartbeat (params.heartbeat) after each step, as reb_integrate_raw does (src/rebound.c:640-641).

@@ -175,6 +175,24 @@ def test_dropin_matches_reference(tmp_path, gravity, resident):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("gravity,point_mass", [(0, 0), (1, 0), (1, 1)])
+def test_resident_mode_defers_and_fuses_with_the_same_bits(tmp_path, gravity, point_mass):
+    """In resident mode part1 / zero_accel / spring_forces of a reb_step are deferred until reb_integrator_leapfrog_part2 runs them
+    as the fused kernels (dropin.cpp: lazy_ok / settle; quadrupole_accel in the phobos-shaped callback settles them early).
+    ASS_DROPIN_NO_FUSE=1 runs every call when it is made: the module's output files must be the same, byte for byte."""
+    build()
+    outs = []
+    for fuse in ("0", "1"):
+        d = str(tmp_path / ("fuse" + fuse))
+        run("synth_b200", d, gravity, {"ASS_RESIDENT": "1", "ASS_DROPIN_NO_FUSE": "0" if fuse == "1" else "1"}, point_mass=point_mass)
+        outs.append(parse(d))
+    (a_run, a_ext, a_head, a_state), (b_run, b_ext, b_head, b_state) = outs
+    assert a_run == b_run and a_head == b_head
+    assert np.array_equal(a_state, b_state)
+    assert np.array_equal(a_ext, b_ext)
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("shape", [1, 2, 3, 4])
 def test_dropin_other_shapes_rotations_and_stress(tmp_path, shape):
     """hcp / cubic lattices, the cube module's box, a cone; rotate_body + rotate_to_principal after the springs are
