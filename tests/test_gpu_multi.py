@@ -257,6 +257,8 @@ def test_ipc_two_ranks_on_one_gpu(gpu, tmp_path):
     env = dict(os.environ, ASS_TEST_ONE_GPU="1")
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
                         "--master-port", "29543", str(script)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600, env=env)
+    if r.returncode != 0 and ("busy or unavailable" in r.stdout or "exclusive" in r.stdout.lower()):
+        pytest.skip("this GPU does not admit a second process (exclusive compute mode)")
     assert r.returncode == 0, r.stdout[-3000:]
     assert r.stdout.count("ok") >= 2, r.stdout[-3000:]
 
